@@ -1,0 +1,169 @@
+/*
+ * sdeo.h — C ABI of the B200-native ControlNet-SD1.5 denoising kernels (libsdeo.so).
+ *
+ * Every entry point is `extern "C"`, takes plain device pointers / sizes / a cudaStream_t passed as void*,
+ * launches asynchronously on that stream, never allocates, never throws, and returns 0 on success or a
+ * negative SDEO_E* code. The reference has exactly one native interface on this path — the TensorRT plugin
+ * `GroupNormPlugin::enqueue(inputDesc, outputDesc, inputs, outputs, workspace, stream) noexcept -> int32`
+ * (plugin/groupNormPlugin/groupNormPlugin.cpp:179-228) — and every other op is an ATen call made from the
+ * Python modules (cited per function below). These functions are what a cgo/ctypes/pybind binding for the
+ * path binds instead.
+ *
+ * Activations are NHWC ("channels-last") bf16 unless noted; tokens are [rows, channels] bf16 row-major.
+ */
+#ifndef SDEO_H_
+#define SDEO_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDEO_OK 0
+#define SDEO_EINVAL (-22)   /* bad argument / unsupported shape */
+#define SDEO_ENOSYS (-38)   /* driver entry point missing (no CUDA driver / no sm_100 device) */
+#define SDEO_ECUDA (-5)     /* a CUDA runtime/driver call failed; see sdeo_last_error() */
+
+/* Human-readable description of the last failure on this thread. */
+const char* sdeo_last_error(void);
+/* Library ABI version (bumped on any signature change). */
+int sdeo_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution / linear on tcgen05 tensor cores (TMA-fed, TMEM accumulators).
+ * Replaces: nn.Conv2d 3x3 / 1x1 in ResBlock, Downsample, Upsample, zero convs, hint block
+ * (ldm/modules/diffusionmodules/openaimodel.py:200-240,150-152,106; cldm/cldm.py:147-163,281-282),
+ * nn.Linear in CrossAttention / GEGLU / FeedForward / time_embed (ldm/modules/attention.py:49-76,154-179;
+ * openaimodel.py:528-533), VAE convs (ldm/modules/diffusionmodules/model.py:100-127,571-617).
+ *
+ * y[pix, n] = epilogue( sum_{tap, c} x[pix*stride + tap - pad, c] * w[n, tap, c] )
+ * Linear layers are the 1x1 case with N=1, H=1, W=rows.
+ * ---------------------------------------------------------------------------------------------- */
+enum {
+  SDEO_EPI_NORMAL = 0, /* y = act(acc + bias + emb[batch]) * scale + residual                     */
+  SDEO_EPI_GEGLU = 1,  /* packed N tile = [x | gate]; y[:, j] = (x + bx) * gelu_erf(gate + bg)      */
+  SDEO_EPI_QKV = 2     /* scatter to head-major q,k [B,heads,tok,d] and transposed v [B,heads,d,ldv] */
+};
+enum { SDEO_ACT_NONE = 0, SDEO_ACT_SILU = 1 };
+
+typedef struct sdeo_conv_args {
+  /* input activation(s): x1 carries channels [0,c1), optional x2 channels [c1,c1+c2) (fused torch.cat, dim=1) */
+  const void* x1;   /* bf16, [n, h, w, ld1] with ld1 >= c1 (elements per pixel)                        */
+  const void* x2;   /* bf16 or NULL                                                                    */
+  int32_t n, h, w;  /* input spatial geometry                                                          */
+  int32_t c1, ld1;  /* channels used from x1 / its pixel stride in elements (multiple of 8)            */
+  int32_t c2, ld2;
+  /* filter */
+  const void* w_packed; /* bf16 [n_rows_packed, k_packed] from sdeo_pack_conv_weight (K-major)         */
+  int32_t cout;         /* logical output channels (rows of w before packing/padding)                  */
+  int32_t ksize;        /* 1 or 3                                                                      */
+  int32_t stride;       /* 1 or 2                                                                      */
+  int32_t pad;          /* 0 or 1                                                                      */
+  /* epilogue */
+  int32_t epi_mode;     /* SDEO_EPI_*                                                                  */
+  int32_t act;          /* SDEO_ACT_*                                                                  */
+  const float* bias;    /* fp32 [cout] (packed order for GEGLU) or NULL                                */
+  const float* emb;     /* fp32 [n, cout] per-sample additive term (ResBlock emb_layers) or NULL        */
+  const void* residual; /* bf16 [n, ho, wo, ldr] added after scaling, or NULL                          */
+  int32_t ldr;
+  float scale;          /* multiplies act(acc+bias+emb) (ControlNet control_scales); 1.0f otherwise    */
+  void* y;              /* bf16 (or fp32 if y_fp32) [n, ho, wo, ldy]                                   */
+  int32_t ldy;
+  int32_t y_fp32;
+  /* SDEO_EPI_QKV only: packed column n -> which = n / (heads*dhead) + qkv_first (0=q,1=k,2=v) */
+  void* q; void* k; void* vt;
+  int32_t heads, dhead, tokens, ldv, qkv_first;
+  /* split-K scratch (see sdeo_conv_workspace_bytes); may be NULL when the planner picks splits == 1 */
+  void* workspace;
+  size_t workspace_bytes;
+} sdeo_conv_args;
+
+/* Bytes of workspace the planner may use for these args (fp32 partial tiles + tile counters).
+ * The first sdeo_conv_counter_bytes() bytes hold the tile counters and must be zero before first use
+ * (the kernel leaves them zero again). */
+size_t sdeo_conv_workspace_bytes(const sdeo_conv_args* a);
+size_t sdeo_conv_counter_bytes(void);
+int sdeo_conv2d(const sdeo_conv_args* a, void* stream);
+
+/* Repack an fp32 filter [cout, cin, k, k] (PyTorch layout, device memory) into the K-major bf16 layout the
+ * kernel streams: [rows_packed, k*k*(chunks(c1)+chunks(c2))*64]. `geglu_bn` > 0 interleaves the two GEGLU
+ * halves per N tile of that width. Query sizes with sdeo_packed_rows / sdeo_packed_k. */
+int32_t sdeo_packed_rows(int32_t cout);
+int32_t sdeo_packed_k(int32_t c1, int32_t c2, int32_t ksize);
+int32_t sdeo_pick_bn(int32_t rows_packed, int32_t epi_mode, int32_t dhead);
+int sdeo_pack_conv_weight(const float* w, int32_t cout, int32_t c1, int32_t c2, int32_t ksize, int32_t geglu_bn,
+                          void* w_packed, void* stream);
+/* Same interleave for a GEGLU bias: [2*inner] -> packed order. */
+int sdeo_pack_geglu_bias(const float* b, int32_t n2, int32_t geglu_bn, float* b_packed, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GroupNorm(32)(+SiLU), NHWC. Replaces GroupNormPlugin::enqueue (groupNormPlugin.cpp:179-228,
+ * groupNormKernel.cu:49-266) and torch GroupNorm32 / Normalize (+ nn.SiLU)
+ * (ldm/modules/diffusionmodules/util.py:217-219; attention.py:88-89; model.py:46-47).
+ * Follows PyTorch numerics (eps applied, fp32 statistics), not the plugin's eps-less variance.
+ * x2 != NULL normalises torch.cat([x1, x2], dim=1) and writes the concatenated result.
+ * ---------------------------------------------------------------------------------------------- */
+size_t sdeo_groupnorm_workspace_bytes(int32_t n, int32_t hw, int32_t groups);
+int sdeo_groupnorm_nhwc(const void* x1, const void* x2, const float* gamma, const float* beta, void* y,
+                        int32_t n, int32_t hw, int32_t c1, int32_t c2, int32_t groups, float eps,
+                        int32_t with_silu, void* workspace, size_t workspace_bytes, void* stream);
+
+/* LayerNorm over the last dim of [rows, c] bf16 (nn.LayerNorm, attention.py:372-374), eps 1e-5. */
+int sdeo_layernorm(const void* x, const float* gamma, const float* beta, void* y, int32_t rows, int32_t c,
+                   float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Flash-style attention on tcgen05: o = softmax(q k^T * scale) v   (attention.py:227-249; model.py:186-199)
+ * q [B*heads, nq, d], k [B*heads, nkv, d], vt [B*heads, d, ldv] (ldv >= nkv, multiple of 8), o [B, nq, heads*d].
+ * d in {40, 80, 160, 512?}: multiples of 8, <= 256 on this build.
+ * ---------------------------------------------------------------------------------------------- */
+int sdeo_attention(const void* q, const void* k, const void* vt, void* o, int32_t batch, int32_t heads,
+                   int32_t nq, int32_t nkv, int32_t d, int32_t ldv, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Elementwise / layout passes
+ * ---------------------------------------------------------------------------------------------- */
+/* CFG combine + DDIM x_{t-1} update (cldm/ddim_hacked.py:192,208-230) in one pass over the latent:
+ *   e = eu + s (ec - eu);  x0 = (x - sqrt(1-a_t) e) * rsqrt(a_t);
+ *   x_prev = sqrt(a_prev) x0 + sqrt(1 - a_prev - sigma^2) e + sigma * noise
+ * coef_table is DEVICE memory, 8 floats per step row:
+ *   {s, sqrt_1m_at, rsqrt_at, sqrt_aprev, dir_coef, sigma, 0, 0}; row = step_idx ? *step_idx : 0
+ * (device-resident so that a captured CUDA graph replays for every step without host patching).
+ * eps_c / eps_u: fp32, NHWC with ld_eps floats per pixel when eps_nhwc != 0 (the UNet out-conv layout), else NCHW.
+ * eps_u may be NULL (no guidance: e = ec). x, noise, x_prev, pred_x0: fp32 NCHW [n, c, hw]; noise/pred_x0 may be NULL.
+ * x_next (optional): bf16 NHWC [dup*n, hw, ldn] copy of x_prev, channels >= c zero-filled, written dup times
+ * (the next step's cond+uncond network input). */
+int sdeo_cfg_ddim_step(const float* eps_c, const float* eps_u, int32_t eps_nhwc, int32_t ld_eps, const float* x,
+                       const float* noise, float* x_prev, float* pred_x0, void* x_next, int32_t dup, int32_t ldn,
+                       const float* coef_table, const int32_t* step_idx, int32_t n, int32_t c, int32_t hw,
+                       void* stream);
+/* *ctr += delta (single thread) — advances the device-side step index between graph replays. */
+int sdeo_counter_add(int32_t* ctr, int32_t delta, void* stream);
+/* fp32 NCHW -> bf16 NHWC with channel padding to ldy (zeros), and back (first c channels). */
+int sdeo_nchw_to_nhwc_bf16(const float* x, void* y, int32_t n, int32_t c, int32_t hw, int32_t ldy, void* stream);
+int sdeo_nhwc_bf16_to_nchw(const void* x, float* y, int32_t n, int32_t c, int32_t hw, int32_t ldx, void* stream);
+int sdeo_nhwc_f32_to_nchw(const float* x, float* y, int32_t n, int32_t c, int32_t hw, int32_t ldx, void* stream);
+/* nearest x2 upsample, NHWC bf16 (F.interpolate(scale_factor=2, mode="nearest"), openaimodel.py:115) */
+int sdeo_upsample_nearest2x(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c, void* stream);
+/* y = a + alpha*b (bf16, same shape) — ControlNet residual injection (cldm/cldm.py:35,41) */
+int sdeo_add_scaled(const void* a, const void* b, float alpha, void* y, int64_t count, void* stream);
+/* sinusoidal timestep embedding [cos | sin] (util.py:154-174) -> bf16 [n, ldy] (cols >= dim zero-filled).
+ * t is int64 device memory: t[i] for sample i, or, when step_idx != NULL, t[*step_idx] for every sample. */
+int sdeo_timestep_embedding(const int64_t* t, const int32_t* step_idx, void* y, int32_t n, int32_t dim, int32_t ldy,
+                            float max_period, void* stream);
+/* row-wise softmax(x * scale) over [rows, cols] bf16 (ld elements between rows), in place allowed (VAE AttnBlock) */
+int sdeo_softmax_rows(const void* x, void* y, int32_t rows, int32_t cols, int32_t ld, float scale, void* stream);
+/* y = silu(x) bf16 elementwise; y = bf16(x) from fp32; y = fp32(x) from bf16 */
+int sdeo_silu(const void* x, void* y, int64_t count, void* stream);
+int sdeo_f32_to_bf16(const float* x, void* y, int64_t count, void* stream);
+int sdeo_bf16_to_f32(const void* x, float* y, int64_t count, void* stream);
+/* VAE output: uint8 NHWC image = clip(x*127.5+127.5, 0, 255) from bf16 NHWC (canny2image_torch.py:68) */
+int sdeo_image_to_u8(const void* x, uint8_t* y, int32_t npix, int32_t c, int32_t ldx, void* stream);
+int sdeo_memset_async(void* p, int value, size_t bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDEO_H_ */

@@ -1,0 +1,318 @@
+// Elementwise / layout passes of the denoising loop: CFG + DDIM update, layout conversion at the NCHW fp32
+// boundary, nearest upsample, residual injection, timestep embedding, row softmax, image quantisation.
+#include "common.cuh"
+#include "host_util.h"
+#include "../../include/sdeo.h"
+
+namespace sdeo {
+
+// ---- CFG combine + DDIM update (+ next-step network input) --------------------------------------
+__global__ void cfg_ddim_kernel(const float* __restrict__ eps_c, const float* __restrict__ eps_u, int eps_nhwc,
+                                int ld_eps, const float* __restrict__ x, const float* __restrict__ noise,
+                                float* __restrict__ x_prev, float* __restrict__ pred_x0,
+                                __nv_bfloat16* __restrict__ x_next, int dup, int ldn,
+                                const float* __restrict__ coef_table, const int* __restrict__ step_idx, int n, int c,
+                                int hw) {
+  const int row = step_idx ? *step_idx : 0;
+  const float* cf = coef_table + (size_t)row * 8;
+  const float s = cf[0], sqrt_1m_at = cf[1], rsqrt_at = cf[2], sqrt_aprev = cf[3], dir_coef = cf[4], sigma = cf[5];
+  const long long total = (long long)n * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / hw);
+    const int p = (int)(i % hw);
+    for (int ch = 0; ch < c; ++ch) {
+      const long long nchw = ((long long)b * c + ch) * hw + p;
+      const long long ei = eps_nhwc ? (i * ld_eps + ch) : nchw;
+      const float ec = eps_c[ei];
+      float e = ec;
+      if (eps_u) {
+        const float eu = eps_u[ei];
+        e = eu + s * (ec - eu);
+      }
+      const float xv = x[nchw];
+      const float x0 = (xv - sqrt_1m_at * e) * rsqrt_at;
+      float xp = sqrt_aprev * x0 + dir_coef * e;
+      if (noise) xp += sigma * noise[nchw];
+      x_prev[nchw] = xp;
+      if (pred_x0) pred_x0[nchw] = x0;
+      if (x_next) {
+        for (int d = 0; d < dup; ++d) x_next[((long long)d * total + i) * ldn + ch] = __float2bfloat16(xp);
+      }
+    }
+    if (x_next) {
+      for (int d = 0; d < dup; ++d)
+        for (int ch = c; ch < ldn; ++ch) x_next[((long long)d * total + i) * ldn + ch] = __float2bfloat16(0.f);
+    }
+  }
+}
+
+__global__ void counter_add_kernel(int* ctr, int delta) { *ctr += delta; }
+
+// ---- layout conversion ---------------------------------------------------------------------------
+// NCHW fp32 -> NHWC bf16 (zero-padded to ldy channels). One thread per (pixel, channel-slot).
+__global__ void nchw_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int c,
+                                         int hw, int ldy) {
+  // tile transpose through shared memory: 32 channels x 32 pixels
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int ch = c0 + j, p = p0 + threadIdx.x;
+    tile[j][threadIdx.x] = (ch < c && p < hw) ? x[((long long)b * c + ch) * hw + p] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int p = p0 + j, ch = c0 + threadIdx.x;
+    if (p < hw && ch < ldy) y[((long long)b * hw + p) * ldy + ch] = __float2bfloat16(tile[threadIdx.x][j]);
+  }
+}
+
+template <typename TIn>
+__global__ void nhwc_to_nchw_f32_kernel(const TIn* __restrict__ x, float* __restrict__ y, int n, int c, int hw,
+                                        int ldx) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int p = p0 + j, ch = c0 + threadIdx.x;
+    float v = 0.f;
+    if (p < hw && ch < c) v = (float)x[((long long)b * hw + p) * ldx + ch];
+    tile[j][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int ch = c0 + j, p = p0 + threadIdx.x;
+    if (ch < c && p < hw) y[((long long)b * c + ch) * hw + p] = tile[threadIdx.x][j];
+  }
+}
+
+// ---- nearest x2 upsample, NHWC, 16-byte vectors ---------------------------------------------------
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int n, int h, int w, int cv) {
+  const long long total = (long long)n * (2 * h) * (2 * w) * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cv);
+    long long t = i / cv;
+    const int ox = (int)(t % (2 * w));
+    t /= (2 * w);
+    const int oy = (int)(t % (2 * h));
+    const int b = (int)(t / (2 * h));
+    y[i] = x[(((long long)b * h + (oy >> 1)) * w + (ox >> 1)) * cv + v];
+  }
+}
+
+// ---- y = a + alpha * b (bf16) ---------------------------------------------------------------------
+__global__ void add_scaled_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, float alpha,
+                                  uint4* __restrict__ y, long long nvec, const __nv_bfloat16* a_s,
+                                  const __nv_bfloat16* b_s, __nv_bfloat16* y_s, long long count) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const uint4 av = a[i], bv = b[i];
+    float2 a0 = unpack_bf16x2(av.x), a1 = unpack_bf16x2(av.y), a2 = unpack_bf16x2(av.z), a3 = unpack_bf16x2(av.w);
+    float2 b0 = unpack_bf16x2(bv.x), b1 = unpack_bf16x2(bv.y), b2 = unpack_bf16x2(bv.z), b3 = unpack_bf16x2(bv.w);
+    uint4 o;
+    o.x = pack_bf16x2(a0.x + alpha * b0.x, a0.y + alpha * b0.y);
+    o.y = pack_bf16x2(a1.x + alpha * b1.x, a1.y + alpha * b1.y);
+    o.z = pack_bf16x2(a2.x + alpha * b2.x, a2.y + alpha * b2.y);
+    o.w = pack_bf16x2(a3.x + alpha * b3.x, a3.y + alpha * b3.y);
+    y[i] = o;
+  }
+  // scalar tail
+  if (blockIdx.x == 0) {
+    for (long long i = nvec * 8 + threadIdx.x; i < count; i += blockDim.x)
+      y_s[i] = __float2bfloat16(__bfloat162float(a_s[i]) + alpha * __bfloat162float(b_s[i]));
+  }
+}
+
+// ---- timestep embedding: [cos(t f_i) | sin(t f_i)], f_i = exp(-ln(max_period) i / half) ------------
+__global__ void timestep_embedding_kernel(const long long* __restrict__ t, const int* __restrict__ step_idx,
+                                          __nv_bfloat16* __restrict__ y, int n, int dim, int ldy, float max_period) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * ldy) return;
+  const int b = i / ldy, col = i % ldy;
+  const float tv = (float)(step_idx ? t[*step_idx] : t[b]);
+  float v = 0.f;
+  if (col < 2 * half) {
+    const int k = col < half ? col : col - half;
+    const float freq = expf(-logf(max_period) * (float)k / (float)half);
+    const float arg = tv * freq;
+    v = col < half ? cosf(arg) : sinf(arg);
+  }
+  y[i] = __float2bfloat16(v);
+}
+
+__global__ void silu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long count) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x)
+    y[i] = __float2bfloat16(silu_f(__bfloat162float(x[i])));
+}
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long count) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x)
+    y[i] = __float2bfloat16(x[i]);
+}
+__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, long long count) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x)
+    y[i] = __bfloat162float(x[i]);
+}
+
+// ---- row softmax (VAE AttnBlock): one CTA per row, fp32 math -----------------------------------
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int cols, int ld,
+                    float scale_log2) {
+  __shared__ float red[8];
+  __shared__ float bcast;
+  const __nv_bfloat16* xr = x + (size_t)blockIdx.x * ld;
+  __nv_bfloat16* yr = y + (size_t)blockIdx.x * ld;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) m = fmaxf(m, __bfloat162float(xr[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = red[0];
+    for (int i = 1; i < 8; ++i) t = fmaxf(t, red[i]);
+    bcast = t;
+  }
+  __syncthreads();
+  m = bcast;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) s += exp2f((__bfloat162float(xr[i]) - m) * scale_log2);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __syncthreads();
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    bcast = 1.0f / t;
+  }
+  __syncthreads();
+  const float inv = bcast;
+  for (int i = threadIdx.x; i < cols; i += blockDim.x)
+    yr[i] = __float2bfloat16(exp2f((__bfloat162float(xr[i]) - m) * scale_log2) * inv);
+}
+
+__global__ void image_to_u8_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ y, long long npix, int c,
+                                   int ldx) {
+  const long long total = npix * c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / c;
+    const int ch = (int)(i % c);
+    float v = __bfloat162float(x[p * ldx + ch]) * 127.5f + 127.5f;
+    v = fminf(fmaxf(v, 0.f), 255.f);
+    y[i] = (uint8_t)v;  // truncation, like numpy astype(np.uint8) on a clipped float (canny2image_torch.py:68)
+  }
+}
+
+static int grid_for(long long work, int threads) {
+  long long b = (work + threads - 1) / threads;
+  if (b > 148 * 8) b = 148 * 8;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace sdeo
+
+using namespace sdeo;
+
+extern "C" int sdeo_cfg_ddim_step(const float* eps_c, const float* eps_u, int32_t eps_nhwc, int32_t ld_eps, const float* x,
+                                  const float* noise, float* x_prev, float* pred_x0, void* x_next, int32_t dup, int32_t ldn,
+                                  const float* coef_table, const int32_t* step_idx, int32_t n, int32_t c, int32_t hw,
+                                  void* stream) {
+  if (!eps_c || !x || !x_prev || !coef_table || n <= 0 || c <= 0 || hw <= 0) return set_error(SDEO_EINVAL, "cfg_ddim_step: bad args");
+  if (x_next && (dup <= 0 || ldn < c)) return set_error(SDEO_EINVAL, "cfg_ddim_step: bad x_next geometry");
+  if (eps_nhwc && ld_eps < c) return set_error(SDEO_EINVAL, "cfg_ddim_step: ld_eps < c");
+  const long long total = (long long)n * hw;
+  cfg_ddim_kernel<<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>(eps_c, eps_u, eps_nhwc, ld_eps, x, noise, x_prev,
+                                                                         pred_x0, (__nv_bfloat16*)x_next, dup, ldn,
+                                                                         coef_table, step_idx, n, c, hw);
+  return check_launch("cfg_ddim_step");
+}
+
+extern "C" int sdeo_counter_add(int32_t* ctr, int32_t delta, void* stream) {
+  if (!ctr) return set_error(SDEO_EINVAL, "counter_add: null");
+  counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(ctr, delta);
+  return check_launch("counter_add");
+}
+
+extern "C" int sdeo_nchw_to_nhwc_bf16(const float* x, void* y, int32_t n, int32_t c, int32_t hw, int32_t ldy, void* stream) {
+  if (!x || !y || n <= 0 || c <= 0 || hw <= 0 || ldy < c || n > 65535) return set_error(SDEO_EINVAL, "nchw_to_nhwc: bad args");
+  dim3 grid((hw + 31) / 32, (ldy + 31) / 32, n), block(32, 8);
+  nchw_to_nhwc_bf16_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, n, c, hw, ldy);
+  return check_launch("nchw_to_nhwc");
+}
+extern "C" int sdeo_nhwc_bf16_to_nchw(const void* x, float* y, int32_t n, int32_t c, int32_t hw, int32_t ldx, void* stream) {
+  if (!x || !y || n <= 0 || c <= 0 || hw <= 0 || ldx < c || n > 65535) return set_error(SDEO_EINVAL, "nhwc_to_nchw: bad args");
+  dim3 grid((hw + 31) / 32, (c + 31) / 32, n), block(32, 8);
+  nhwc_to_nchw_f32_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, y, n, c, hw, ldx);
+  return check_launch("nhwc_to_nchw");
+}
+extern "C" int sdeo_nhwc_f32_to_nchw(const float* x, float* y, int32_t n, int32_t c, int32_t hw, int32_t ldx, void* stream) {
+  if (!x || !y || n <= 0 || c <= 0 || hw <= 0 || ldx < c || n > 65535) return set_error(SDEO_EINVAL, "nhwc_f32_to_nchw: bad args");
+  dim3 grid((hw + 31) / 32, (c + 31) / 32, n), block(32, 8);
+  nhwc_to_nchw_f32_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(x, y, n, c, hw, ldx);
+  return check_launch("nhwc_f32_to_nchw");
+}
+
+extern "C" int sdeo_upsample_nearest2x(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c, void* stream) {
+  if (!x || !y || n <= 0 || h <= 0 || w <= 0 || c <= 0 || c % 8 != 0) return set_error(SDEO_EINVAL, "upsample2x: bad args");
+  const long long total = (long long)n * 4 * h * w * (c / 8);
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, n, h, w, c / 8);
+  return check_launch("upsample2x");
+}
+
+extern "C" int sdeo_add_scaled(const void* a, const void* b, float alpha, void* y, int64_t count, void* stream) {
+  if (!a || !b || !y || count <= 0) return set_error(SDEO_EINVAL, "add_scaled: bad args");
+  const bool aligned = (((uintptr_t)a | (uintptr_t)b | (uintptr_t)y) & 15) == 0;
+  const long long nvec = aligned ? count / 8 : 0;
+  add_scaled_kernel<<<grid_for(nvec > 0 ? nvec : 1, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)a, (const uint4*)b, alpha, (uint4*)y, nvec, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b,
+      (__nv_bfloat16*)y, count);
+  return check_launch("add_scaled");
+}
+
+extern "C" int sdeo_timestep_embedding(const int64_t* t, const int32_t* step_idx, void* y, int32_t n, int32_t dim,
+                                       int32_t ldy, float max_period, void* stream) {
+  if (!t || !y || n <= 0 || dim <= 0 || ldy < dim) return set_error(SDEO_EINVAL, "timestep_embedding: bad args");
+  const int total = n * ldy;
+  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>((const long long*)t, step_idx,
+                                                                                    (__nv_bfloat16*)y, n, dim, ldy, max_period);
+  return check_launch("timestep_embedding");
+}
+
+extern "C" int sdeo_silu(const void* x, void* y, int64_t count, void* stream) {
+  if (!x || !y || count <= 0) return set_error(SDEO_EINVAL, "silu: bad args");
+  silu_kernel<<<grid_for(count, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, count);
+  return check_launch("silu");
+}
+extern "C" int sdeo_f32_to_bf16(const float* x, void* y, int64_t count, void* stream) {
+  if (!x || !y || count <= 0) return set_error(SDEO_EINVAL, "f32_to_bf16: bad args");
+  f32_to_bf16_kernel<<<grid_for(count, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, count);
+  return check_launch("f32_to_bf16");
+}
+extern "C" int sdeo_bf16_to_f32(const void* x, float* y, int64_t count, void* stream) {
+  if (!x || !y || count <= 0) return set_error(SDEO_EINVAL, "bf16_to_f32: bad args");
+  bf16_to_f32_kernel<<<grid_for(count, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, y, count);
+  return check_launch("bf16_to_f32");
+}
+
+extern "C" int sdeo_softmax_rows(const void* x, void* y, int32_t rows, int32_t cols, int32_t ld, float scale, void* stream) {
+  if (!x || !y || rows <= 0 || cols <= 0 || ld < cols) return set_error(SDEO_EINVAL, "softmax_rows: bad args");
+  softmax_rows_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, cols, ld,
+                                                              scale * 1.4426950408889634f);
+  return check_launch("softmax_rows");
+}
+
+extern "C" int sdeo_image_to_u8(const void* x, uint8_t* y, int32_t npix, int32_t c, int32_t ldx, void* stream) {
+  if (!x || !y || npix <= 0 || c <= 0 || ldx < c) return set_error(SDEO_EINVAL, "image_to_u8: bad args");
+  image_to_u8_kernel<<<grid_for((long long)npix * c, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, y, npix, c, ldx);
+  return check_launch("image_to_u8");
+}

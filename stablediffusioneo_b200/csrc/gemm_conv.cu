@@ -1,0 +1,644 @@
+// Implicit-GEMM convolution / linear for sm_100a: TMA-fed, tcgen05.mma with TMEM accumulators.
+//
+// GEMM view:  D[pixel, cout] = sum_{tap, cin} X[pixel shifted by tap, cin] * W[cout, tap, cin]
+//   M = output pixels, tiled as a (bn x bh x bw) box of up to 128 pixels fetched by ONE 4-D TMA box per
+//       (tap, 64-channel chunk): the tap shift is a coordinate offset, the zero padding is TMA out-of-bounds
+//       fill, the stride-2 case is the tensor map's elementStrides, torch.cat([x1,x2],1) is two tensor maps.
+//   N = output channels, tile BN (multiple of 16, <= 256, chosen at run time).
+//   K = taps * channels in chunks of 64 bf16 (one 128-byte swizzle atom per row).
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
+// (TMEM -> registers -> bias / time-embedding / SiLU / scale / residual / GEGLU / QKV scatter -> global).
+// Split-K: partial tiles go to an fp32 workspace; the last CTA to arrive on a tile sums them in split order
+// (deterministic) and runs the epilogue.
+#include "common.cuh"
+#include "host_util.h"
+#include "../../include/sdeo.h"
+
+namespace sdeo {
+
+constexpr int kConvThreads = 192;
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kATileBytes = kBM * kBK * 2;  // 16 KB
+constexpr int kMaxTilesForCounters = 16384;
+
+struct ConvKParams {
+  // K loop
+  int kw, pad, stride;
+  int c1_chunks, chunks_per_tap;
+  int total_chunks, chunks_per_split, splits;
+  // M tiling
+  int bn_, bh, bw, rows_valid;
+  int tiles_h, tiles_w;
+  int N, Ho, Wo;
+  // N tiling
+  int BN, cout, stages, tmem_cols;
+  // epilogue
+  int epi_mode, act, y_fp32;
+  const float* bias;
+  const float* emb;
+  const __nv_bfloat16* residual;
+  int ldr;
+  float scale;
+  void* y;
+  int ldy;
+  // qkv
+  __nv_bfloat16* q;
+  __nv_bfloat16* k;
+  __nv_bfloat16* vt;
+  int heads, dhead, tokens, ldv, qkv_first;
+  // split-K
+  float* ws;
+  unsigned int* counters;
+};
+
+struct RowInfo {
+  bool valid;
+  int batch;     // sample index
+  long long pix; // linear output pixel index
+};
+
+// One 8-column group of the NORMAL epilogue for one row.
+__device__ __forceinline__ void epi_normal_store8(const ConvKParams& p, const RowInfo& ri, int n, const float* v) {
+  if (n >= p.cout) return;
+  float x[8];
+  const bool full = (n + 8 <= p.cout);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float t = v[j];
+    const int nn = n + j;
+    if (full || nn < p.cout) {
+      if (p.bias) t += __ldg(p.bias + nn);
+      if (p.emb) t += __ldg(p.emb + (long long)ri.batch * p.cout + nn);
+    }
+    if (p.act == SDEO_ACT_SILU) t = silu_f(t);
+    x[j] = t * p.scale;
+  }
+  if (p.residual) {
+    const __nv_bfloat16* rp = p.residual + ri.pix * p.ldr + n;
+    if (full && ((p.ldr & 7) == 0)) {
+      uint4 rv = *reinterpret_cast<const uint4*>(rp);
+      float2 a = unpack_bf16x2(rv.x), b = unpack_bf16x2(rv.y), c = unpack_bf16x2(rv.z), d = unpack_bf16x2(rv.w);
+      x[0] += a.x; x[1] += a.y; x[2] += b.x; x[3] += b.y; x[4] += c.x; x[5] += c.y; x[6] += d.x; x[7] += d.y;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (n + j < p.cout) x[j] += __bfloat162float(rp[j]);
+    }
+  }
+  if (p.y_fp32) {
+    float* yp = reinterpret_cast<float*>(p.y) + ri.pix * p.ldy + n;
+    if (full && ((p.ldy & 3) == 0)) {
+      *reinterpret_cast<float4*>(yp) = make_float4(x[0], x[1], x[2], x[3]);
+      *reinterpret_cast<float4*>(yp + 4) = make_float4(x[4], x[5], x[6], x[7]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (n + j < p.cout) yp[j] = x[j];
+    }
+  } else {
+    __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + ri.pix * p.ldy + n;
+    if (full && ((p.ldy & 7) == 0)) {
+      uint4 o;
+      o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]);
+      o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
+      *reinterpret_cast<uint4*>(yp) = o;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (n + j < p.cout) yp[j] = __float2bfloat16(x[j]);
+    }
+  }
+}
+
+// One 8-column group of the QKV epilogue: scatter into head-major q/k and transposed v.
+__device__ __forceinline__ void epi_qkv_store8(const ConvKParams& p, const RowInfo& ri, int n, const float* v) {
+  if (n >= p.cout) return;
+  const int C = p.heads * p.dhead;
+  const int which = n / C + p.qkv_first;
+  const int nc = n % C;
+  const int head = nc / p.dhead;
+  const int dd = nc % p.dhead;
+  const int b = (int)(ri.pix / p.tokens);
+  const int tok = (int)(ri.pix % p.tokens);
+  float x[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) x[j] = v[j] + (p.bias ? __ldg(p.bias + n + j) : 0.0f);
+  const long long bh = (long long)b * p.heads + head;
+  if (which < 2) {
+    __nv_bfloat16* dst = (which == 0 ? p.q : p.k) + (bh * p.tokens + tok) * p.dhead + dd;
+    uint4 o;
+    o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]);
+    o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
+    *reinterpret_cast<uint4*>(dst) = o;
+  } else {
+    __nv_bfloat16* dst = p.vt + (bh * p.dhead + dd) * p.ldv + tok;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[(long long)j * p.ldv] = __float2bfloat16(x[j]);
+  }
+}
+
+__device__ __forceinline__ void epi_geglu_store8(const ConvKParams& p, const RowInfo& ri, int n_out, int nb_x,
+                                                 int nb_g, const float* vx, const float* vg) {
+  // n_out: output column; nb_x / nb_g: packed bias indices of the x and gate columns
+  float x[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float a = vx[j] + (p.bias ? __ldg(p.bias + nb_x + j) : 0.0f);
+    float g = vg[j] + (p.bias ? __ldg(p.bias + nb_g + j) : 0.0f);
+    x[j] = a * gelu_erf_f(g);
+  }
+  __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + ri.pix * p.ldy + n_out;
+  uint4 o;
+  o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]);
+  o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
+  *reinterpret_cast<uint4*>(yp) = o;
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+                 const __grid_constant__ CUtensorMap tmB, const ConvKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+
+  const int stage_bytes = kATileBytes + p.BN * 128;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full_bar = empty_bar + p.stages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint32_t* flag_smem = tmem_ptr_smem + 1;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tile = blockIdx.x;
+  const int n_tile = blockIdx.y;
+  const int split = blockIdx.z;
+  const int iw = m_tile % p.tiles_w;
+  const int ih = (m_tile / p.tiles_w) % p.tiles_h;
+  const int in_ = m_tile / (p.tiles_w * p.tiles_h);
+  const int w0 = iw * p.bw, h0 = ih * p.bh, n0 = in_ * p.bn_;
+
+  const int k_begin = split * p.chunks_per_split;
+  int k_end = k_begin + p.chunks_per_split;
+  if (k_end > p.total_chunks) k_end = p.total_chunks;
+  const int nchunks = k_end - k_begin;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB);
+    if (p.chunks_per_tap > p.c1_chunks) tma_prefetch_desc(&tmA2);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const uint32_t tx_bytes = (uint32_t)(p.rows_valid + p.BN) * 128u;
+      for (int i = 0; i < nchunks; ++i) {
+        const int s = i % p.stages;
+        const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        mbar_expect_tx(&full_bar[s], tx_bytes);
+        const int kc = k_begin + i;
+        const int tap = kc / p.chunks_per_tap;
+        const int within = kc % p.chunks_per_tap;
+        const int ky = tap / p.kw, kx = tap % p.kw;
+        uint8_t* a_dst = smem + (size_t)s * stage_bytes;
+        uint8_t* b_dst = a_dst + kATileBytes;
+        const int wc = w0 * p.stride + kx - p.pad;
+        const int hc = h0 * p.stride + ky - p.pad;
+        if (within < p.c1_chunks)
+          tma_load_4d(a_dst, &tmA1, &full_bar[s], within * kBK, wc, hc, n0);
+        else
+          tma_load_4d(a_dst, &tmA2, &full_bar[s], (within - p.c1_chunks) * kBK, wc, hc, n0);
+        tma_load_2d(b_dst, &tmB, &full_bar[s], kc * kBK, n_tile * p.BN);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(kBM, (uint32_t)p.BN);
+      for (int i = 0; i < nchunks; ++i) {
+        const int s = i % p.stages;
+        const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t b_addr = a_addr + kATileBytes;
+        const uint64_t a_desc = umma_desc_k_sw128(a_addr);
+        const uint64_t b_desc = umma_desc_k_sw128(b_addr);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+          tc_mma_bf16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                      (i > 0 || k > 0) ? 1u : 0u);
+        }
+        tc_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
+      }
+      tc_commit(tmem_full_bar);    // accumulator complete
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;
+    const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const int et = threadIdx.x - 64;  // 0..127 epilogue thread id
+
+    RowInfo ri;
+    {
+      const int per_img = p.bh * p.bw;
+      const int nl = row / per_img;
+      const int rem = row % per_img;
+      const int hl = rem / p.bw, wl = rem % p.bw;
+      const int nn = n0 + nl, hh = h0 + hl, ww = w0 + wl;
+      ri.valid = (row < p.rows_valid) && (nn < p.N) && (hh < p.Ho) && (ww < p.Wo);
+      ri.batch = nn;
+      ri.pix = ((long long)nn * p.Ho + hh) * p.Wo + ww;
+    }
+
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+
+    bool do_epilogue = true;
+    const int tile_linear = blockIdx.y * gridDim.x + blockIdx.x;
+    float* ws_tile = nullptr;
+    if (p.splits > 1) {
+      // ---- write this split's partial tile: layout [BN/4][128 rows][4] fp32 ----
+      ws_tile = p.ws + ((size_t)tile_linear * p.splits) * (size_t)(kBM * p.BN);
+      float* mine = ws_tile + (size_t)split * (kBM * p.BN);
+      for (int c = 0; c < p.BN / 16; ++c) {
+        uint32_t r[16];
+        tmem_ld16(taddr_row + (uint32_t)(c * 16), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float4 v = make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]),
+                                 __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
+          *reinterpret_cast<float4*>(mine + ((size_t)(c * 4 + g) * kBM + row) * 4) = v;
+        }
+      }
+      __threadfence();
+      bar_sync(1, 128);
+      if (et == 0) {
+        const unsigned int prev = atomicAdd(&p.counters[tile_linear], 1u);
+        const bool last = (prev == (unsigned int)(p.splits - 1));
+        if (last) p.counters[tile_linear] = 0u;  // self-reset for the next launch
+        *flag_smem = last ? 1u : 0u;
+      }
+      bar_sync(1, 128);
+      do_epilogue = (*flag_smem != 0u);
+      if (do_epilogue) __threadfence();
+    }
+
+    if (do_epilogue) {
+      const int n_base = n_tile * p.BN;
+      if (p.epi_mode == SDEO_EPI_GEGLU) {
+        const int half = p.BN / 2;
+        for (int c = 0; c < half / 16; ++c) {
+          float vx[16], vg[16];
+          if (p.splits > 1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { vx[j] = 0.f; vg[j] = 0.f; }
+            for (int s = 0; s < p.splits; ++s) {
+              const float* part = ws_tile + (size_t)s * (kBM * p.BN);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float4 a = *reinterpret_cast<const float4*>(part + ((size_t)(c * 4 + g) * kBM + row) * 4);
+                float4 b = *reinterpret_cast<const float4*>(part + ((size_t)((half / 4) + c * 4 + g) * kBM + row) * 4);
+                vx[4 * g] += a.x; vx[4 * g + 1] += a.y; vx[4 * g + 2] += a.z; vx[4 * g + 3] += a.w;
+                vg[4 * g] += b.x; vg[4 * g + 1] += b.y; vg[4 * g + 2] += b.z; vg[4 * g + 3] += b.w;
+              }
+            }
+          } else {
+            uint32_t rx[16], rg[16];
+            tmem_ld16(taddr_row + (uint32_t)(c * 16), rx);
+            tmem_ld16(taddr_row + (uint32_t)(half + c * 16), rg);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { vx[j] = __uint_as_float(rx[j]); vg[j] = __uint_as_float(rg[j]); }
+          }
+          if (ri.valid) {
+            const int n_out = n_tile * half + c * 16;
+            epi_geglu_store8(p, ri, n_out, n_base + c * 16, n_base + half + c * 16, vx, vg);
+            epi_geglu_store8(p, ri, n_out + 8, n_base + c * 16 + 8, n_base + half + c * 16 + 8, vx + 8, vg + 8);
+          }
+        }
+      } else {
+        for (int c = 0; c < p.BN / 16; ++c) {
+          float v[16];
+          if (p.splits > 1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 0.f;
+            for (int s = 0; s < p.splits; ++s) {
+              const float* part = ws_tile + (size_t)s * (kBM * p.BN);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float4 a = *reinterpret_cast<const float4*>(part + ((size_t)(c * 4 + g) * kBM + row) * 4);
+                v[4 * g] += a.x; v[4 * g + 1] += a.y; v[4 * g + 2] += a.z; v[4 * g + 3] += a.w;
+              }
+            }
+          } else {
+            uint32_t r[16];
+            tmem_ld16(taddr_row + (uint32_t)(c * 16), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          }
+          if (ri.valid) {
+            const int n = n_base + c * 16;
+            if (p.epi_mode == SDEO_EPI_QKV) {
+              epi_qkv_store8(p, ri, n, v);
+              epi_qkv_store8(p, ri, n + 8, v + 8);
+            } else {
+              epi_normal_store8(p, ri, n, v);
+              epi_normal_store8(p, ri, n + 8, v + 8);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout,
+                                        int c1, int c2, int ksize, int rows_packed, int geglu_bn) {
+  const int c1c = (c1 + 63) / 64, c2c = (c2 + 63) / 64;
+  const int cpt = c1c + c2c;
+  const int taps = ksize * ksize;
+  const long long kp = (long long)taps * cpt * 64;
+  const long long total = (long long)rows_packed * kp;
+  const int cin = c1 + c2;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(idx / kp);
+    const long long kk = idx % kp;
+    const int tap = (int)(kk / (cpt * 64));
+    const int within = (int)((kk / 64) % cpt);
+    const int j = (int)(kk % 64);
+    int src_row = r;
+    if (geglu_bn > 0) {
+      const int half = geglu_bn / 2, inner = cout / 2;
+      const int t = r / geglu_bn, rr = r % geglu_bn;
+      src_row = (rr < half) ? (t * half + rr) : (inner + t * half + (rr - half));
+    }
+    int ci = -1;
+    if (within < c1c) {
+      const int c = within * 64 + j;
+      if (c < c1) ci = c;
+    } else {
+      const int c = (within - c1c) * 64 + j;
+      if (c < c2) ci = c1 + c;
+    }
+    float v = 0.f;
+    if (src_row < cout && ci >= 0) v = w[((long long)src_row * cin + ci) * taps + tap];
+    out[idx] = __float2bfloat16(v);
+  }
+}
+
+__global__ void pack_geglu_bias_kernel(const float* __restrict__ b, float* __restrict__ out, int n2, int geglu_bn) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n2) return;
+  const int half = geglu_bn / 2, inner = n2 / 2;
+  const int t = r / geglu_bn, rr = r % geglu_bn;
+  const int src = (rr < half) ? (t * half + rr) : (inner + t * half + (rr - half));
+  out[r] = b[src];
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: planner + launcher
+// ---------------------------------------------------------------------------------------------
+struct ConvPlan {
+  int Ho, Wo;
+  int bn_, bh, bw, tiles_n, tiles_h, tiles_w;
+  int rows_packed, BN, n_tiles;
+  int c1c, c2c, cpt, total_chunks, splits, cps;
+  int stages, tmem_cols;
+  size_t smem_bytes;
+};
+
+static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+static int pick_bn_impl(int rows_packed, int epi_mode) {
+  if (epi_mode == SDEO_EPI_GEGLU) {
+    // need BN % 32 == 0 and (rows/2) % (BN/2) == 0
+    static const int cand[] = {256, 192, 160, 128, 96, 64, 32};
+    for (int bn : cand)
+      if (rows_packed % bn == 0 && (rows_packed / 2) % (bn / 2) == 0) return bn;
+    return 0;
+  }
+  if (rows_packed <= 256) return rows_packed;
+  static const int cand[] = {256, 192, 160, 128, 96, 80, 64, 48, 32, 16};
+  for (int bn : cand)
+    if (rows_packed % bn == 0) return bn;
+  return 16;
+}
+
+static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl) {
+  if (!(a->ksize == 1 || a->ksize == 3)) return false;
+  if (!(a->stride == 1 || a->stride == 2)) return false;
+  if (a->pad != (a->ksize == 3 ? 1 : 0)) return false;
+  if (a->c1 <= 0 || (a->ld1 % 8) != 0 || (a->x2 && (a->ld2 % 8) != 0)) return false;
+  if (a->x2 && (a->c1 % 64) != 0) return false;
+  pl->Ho = (a->h + 2 * a->pad - a->ksize) / a->stride + 1;
+  pl->Wo = (a->w + 2 * a->pad - a->ksize) / a->stride + 1;
+  // ---- M tile box: minimise tile count, then prefer wide boxes ----
+  int best_tiles = INT32_MAX, bbn = 1, bbh = 1, bbw = 1;
+  const int maxw = pl->Wo < kBM ? pl->Wo : kBM;
+  for (int bw = maxw; bw >= 1; --bw) {
+    const int maxh = (kBM / bw) < pl->Ho ? (kBM / bw) : pl->Ho;
+    for (int bh = maxh; bh >= 1; --bh) {
+      int bn = 1;
+      if (bh == pl->Ho && bw == pl->Wo) {
+        bn = kBM / (bh * bw);
+        if (bn > a->n) bn = a->n;
+        if (bn < 1) bn = 1;
+      }
+      if (bw * a->stride > 256 || bh * a->stride > 256) continue;
+      const int tiles = ((a->n + bn - 1) / bn) * ((pl->Ho + bh - 1) / bh) * ((pl->Wo + bw - 1) / bw);
+      if (tiles < best_tiles) {
+        best_tiles = tiles; bbn = bn; bbh = bh; bbw = bw;
+      }
+    }
+  }
+  pl->bn_ = bbn; pl->bh = bbh; pl->bw = bbw;
+  pl->tiles_n = (a->n + bbn - 1) / bbn;
+  pl->tiles_h = (pl->Ho + bbh - 1) / bbh;
+  pl->tiles_w = (pl->Wo + bbw - 1) / bbw;
+  // ---- N tile ----
+  pl->rows_packed = round_up(a->cout, 16);
+  pl->BN = pick_bn_impl(pl->rows_packed, a->epi_mode);
+  if (pl->BN <= 0 || pl->BN > 256 || (pl->BN % 16) != 0) return false;
+  pl->n_tiles = pl->rows_packed / pl->BN;
+  // ---- K ----
+  pl->c1c = (a->c1 + 63) / 64;
+  pl->c2c = a->x2 ? (a->c2 + 63) / 64 : 0;
+  pl->cpt = pl->c1c + pl->c2c;
+  pl->total_chunks = a->ksize * a->ksize * pl->cpt;
+  const int base = best_tiles * pl->n_tiles;
+  int splits = 1;
+  if (base < 120 && a->workspace != nullptr) {
+    splits = (148 + base - 1) / base;
+    const int max_by_k = pl->total_chunks / 4;
+    if (splits > max_by_k) splits = max_by_k;
+    if (splits > 32) splits = 32;
+    if (splits < 1) splits = 1;
+  }
+  pl->cps = (pl->total_chunks + splits - 1) / splits;
+  pl->splits = (pl->total_chunks + pl->cps - 1) / pl->cps;
+  if (pl->splits > 1) {
+    const size_t need = sdeo_conv_counter_bytes() +
+                        (size_t)best_tiles * pl->n_tiles * pl->splits * kBM * pl->BN * sizeof(float);
+    if (need > a->workspace_bytes || best_tiles * pl->n_tiles > kMaxTilesForCounters) {
+      pl->splits = 1;
+      pl->cps = pl->total_chunks;
+    }
+  }
+  // ---- smem / tmem ----
+  const int stage_bytes = kATileBytes + pl->BN * 128;
+  int stages = (212 * 1024) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages > pl->cps) stages = pl->cps < 2 ? 2 : pl->cps;
+  pl->stages = stages;
+  pl->smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + (2 * stages + 1) * 8 + 16;
+  int tc = 32;
+  while (tc < pl->BN) tc *= 2;
+  pl->tmem_cols = tc;
+  return true;
+}
+
+}  // namespace sdeo
+
+using namespace sdeo;
+
+extern "C" size_t sdeo_conv_counter_bytes(void) { return (size_t)kMaxTilesForCounters * sizeof(unsigned int); }
+
+extern "C" size_t sdeo_conv_workspace_bytes(const sdeo_conv_args* a) {
+  // upper bound: the planner never uses more than ~148+ CTAs worth of partial tiles when splitting
+  (void)a;
+  return sdeo_conv_counter_bytes() + (size_t)320 * kBM * 256 * sizeof(float);
+}
+
+extern "C" int32_t sdeo_packed_rows(int32_t cout) { return round_up(cout, 16); }
+extern "C" int32_t sdeo_packed_k(int32_t c1, int32_t c2, int32_t ksize) {
+  return ksize * ksize * (((c1 + 63) / 64) + ((c2 + 63) / 64)) * 64;
+}
+extern "C" int32_t sdeo_pick_bn(int32_t rows_packed, int32_t epi_mode, int32_t dhead) {
+  (void)dhead;
+  return pick_bn_impl(rows_packed, epi_mode);
+}
+
+extern "C" int sdeo_pack_conv_weight(const float* w, int32_t cout, int32_t c1, int32_t c2, int32_t ksize,
+                                     int32_t geglu_bn, void* w_packed, void* stream) {
+  if (!w || !w_packed || cout <= 0 || c1 <= 0 || c2 < 0) return set_error(SDEO_EINVAL, "pack_conv_weight: bad args");
+  if (c2 > 0 && (c1 % 64) != 0) return set_error(SDEO_EINVAL, "pack_conv_weight: c1 must be a multiple of 64 when c2 > 0");
+  const int rows = round_up(cout, 16);
+  if (geglu_bn > 0 && (rows % geglu_bn != 0 || (cout / 2) % (geglu_bn / 2) != 0))
+    return set_error(SDEO_EINVAL, "pack_conv_weight: geglu tile does not divide rows");
+  const long long total = (long long)rows * sdeo_packed_k(c1, c2, ksize);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pack_conv_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)w_packed, cout, c1, c2, ksize,
+                                                                    rows, geglu_bn);
+  return check_launch("pack_conv_weight");
+}
+
+extern "C" int sdeo_pack_geglu_bias(const float* b, int32_t n2, int32_t geglu_bn, float* b_packed, void* stream) {
+  if (!b || !b_packed || n2 <= 0 || geglu_bn <= 0 || n2 % geglu_bn != 0) return set_error(SDEO_EINVAL, "pack_geglu_bias: bad args");
+  pack_geglu_bias_kernel<<<(n2 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(b, b_packed, n2, geglu_bn);
+  return check_launch("pack_geglu_bias");
+}
+
+extern "C" int sdeo_conv2d(const sdeo_conv_args* a, void* stream) {
+  if (!a || !a->x1 || !a->w_packed) return set_error(SDEO_EINVAL, "conv2d: null argument");
+  ConvPlan pl;
+  if (!make_plan(a, &pl)) return set_error(SDEO_EINVAL, "conv2d: unsupported geometry");
+  if (a->epi_mode == SDEO_EPI_QKV) {
+    if (!a->vt && !a->q && !a->k) return set_error(SDEO_EINVAL, "conv2d: qkv outputs missing");
+    if ((a->dhead % 8) != 0 || a->heads <= 0 || a->tokens <= 0) return set_error(SDEO_EINVAL, "conv2d: bad qkv geometry");
+    if ((a->cout % 8) != 0) return set_error(SDEO_EINVAL, "conv2d: qkv cout must be a multiple of 8");
+  } else if (!a->y) {
+    return set_error(SDEO_EINVAL, "conv2d: null output");
+  }
+  if (a->epi_mode == SDEO_EPI_GEGLU && ((a->cout % 32) != 0 || (a->ldy % 8) != 0))
+    return set_error(SDEO_EINVAL, "conv2d: bad geglu geometry");
+
+  CUtensorMap tmA1, tmA2, tmB;
+  const uint32_t st = (uint32_t)a->stride;
+  {
+    uint64_t dims[4] = {(uint64_t)a->c1, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n};
+    uint64_t strides[3] = {(uint64_t)a->ld1 * 2, (uint64_t)a->w * a->ld1 * 2, (uint64_t)a->h * a->w * a->ld1 * 2};
+    uint32_t box[4] = {64, (uint32_t)pl.bw * st, (uint32_t)pl.bh * st, (uint32_t)pl.bn_};
+    uint32_t es[4] = {1, st, st, 1};
+    int rc = encode_tmap_bf16(&tmA1, a->x1, 4, dims, strides, box, es);
+    if (rc) return rc;
+    tmA2 = tmA1;
+  }
+  if (a->x2) {
+    uint64_t dims[4] = {(uint64_t)a->c2, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n};
+    uint64_t strides[3] = {(uint64_t)a->ld2 * 2, (uint64_t)a->w * a->ld2 * 2, (uint64_t)a->h * a->w * a->ld2 * 2};
+    uint32_t box[4] = {64, (uint32_t)pl.bw * st, (uint32_t)pl.bh * st, (uint32_t)pl.bn_};
+    uint32_t es[4] = {1, st, st, 1};
+    int rc = encode_tmap_bf16(&tmA2, a->x2, 4, dims, strides, box, es);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t kp = (uint64_t)a->ksize * a->ksize * pl.cpt * 64;
+    uint64_t dims[2] = {kp, (uint64_t)pl.rows_packed};
+    uint64_t strides[1] = {kp * 2};
+    uint32_t box[2] = {64, (uint32_t)pl.BN};
+    uint32_t es[2] = {1, 1};
+    int rc = encode_tmap_bf16(&tmB, a->w_packed, 2, dims, strides, box, es);
+    if (rc) return rc;
+  }
+
+  ConvKParams p;
+  p.kw = a->ksize; p.pad = a->pad; p.stride = a->stride;
+  p.c1_chunks = pl.c1c; p.chunks_per_tap = pl.cpt;
+  p.total_chunks = pl.total_chunks; p.chunks_per_split = pl.cps; p.splits = pl.splits;
+  p.bn_ = pl.bn_; p.bh = pl.bh; p.bw = pl.bw; p.rows_valid = pl.bn_ * pl.bh * pl.bw;
+  p.tiles_h = pl.tiles_h; p.tiles_w = pl.tiles_w;
+  p.N = a->n; p.Ho = pl.Ho; p.Wo = pl.Wo;
+  p.BN = pl.BN; p.cout = a->cout; p.stages = pl.stages; p.tmem_cols = pl.tmem_cols;
+  p.epi_mode = a->epi_mode; p.act = a->act; p.y_fp32 = a->y_fp32;
+  p.bias = a->bias; p.emb = a->emb; p.residual = (const __nv_bfloat16*)a->residual; p.ldr = a->ldr;
+  p.scale = a->scale; p.y = a->y; p.ldy = a->ldy;
+  p.q = (__nv_bfloat16*)a->q; p.k = (__nv_bfloat16*)a->k; p.vt = (__nv_bfloat16*)a->vt;
+  p.heads = a->heads; p.dhead = a->dhead; p.tokens = a->tokens; p.ldv = a->ldv; p.qkv_first = a->qkv_first;
+  p.counters = (unsigned int*)a->workspace;
+  p.ws = a->workspace ? (float*)((uint8_t*)a->workspace + sdeo_conv_counter_bytes()) : nullptr;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return set_error(SDEO_ECUDA, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)(pl.tiles_n * pl.tiles_h * pl.tiles_w), (unsigned)pl.n_tiles, (unsigned)pl.splits);
+  conv_gemm_kernel<<<grid, kConvThreads, pl.smem_bytes, (cudaStream_t)stream>>>(tmA1, tmA2, tmB, p);
+  return check_launch("conv2d");
+}

@@ -1,0 +1,269 @@
+// GroupNorm(32)(+SiLU) over NHWC bf16 (optionally over the channel-concat of two tensors) and LayerNorm.
+// HBM-bound passes: 16-byte vector loads, fp32 statistics, deterministic two-level reduction (no atomics).
+#include "common.cuh"
+#include "host_util.h"
+#include "../../include/sdeo.h"
+
+namespace sdeo {
+
+constexpr int kGNThreads = 256;
+
+// Loads the 8-channel vector `v` (of the virtual concat [x1 | x2]) at pixel `pix`.
+__device__ __forceinline__ uint4 gn_load8(const __nv_bfloat16* x1, const __nv_bfloat16* x2, int c1, int c2,
+                                          long long pix, int v) {
+  const int c = v * 8;
+  if (c < c1) return *reinterpret_cast<const uint4*>(x1 + pix * c1 + c);
+  return *reinterpret_cast<const uint4*>(x2 + pix * c2 + (c - c1));
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
+// Pass 1: per (sample, pixel-chunk) partial sums per group -> ws[n][chunk][group][2]
+__global__ void __launch_bounds__(kGNThreads)
+gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, const __nv_bfloat16* __restrict__ x2, float* __restrict__ ws,
+                int hw, int c1, int c2, int groups, int chunks, int ppc) {
+  extern __shared__ float sm[];
+  const int C = c1 + c2;
+  const int cv = C / 8;
+  const int cpg = C / groups;
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int p_begin = chunk * ppc;
+  const int p_end = min(hw, p_begin + ppc);
+  float* chan_sum = sm;        // [C]
+  float* chan_sq = sm + C;     // [C]
+  float* part = sm + 2 * C;    // [R][cols][16]
+
+  const int cols = cv < kGNThreads ? cv : kGNThreads;  // channel vectors handled per pass
+  const int R = kGNThreads / cols;                     // pixel rows in flight
+  const int tr = threadIdx.x / cols, tv = threadIdx.x % cols;
+  const bool active = threadIdx.x < R * cols;
+
+  for (int vbase = 0; vbase < cv; vbase += cols) {
+    const int v = vbase + tv;
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+    if (active && v < cv) {
+      for (int pp = p_begin + tr; pp < p_end; pp += R) {
+        float f[8];
+        unpack8(gn_load8(x1, x2, c1, c2, (long long)n * hw + pp, v), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] += f[j] * f[j]; }
+      }
+    }
+    if (active) {
+      float* dst = part + ((size_t)tr * cols + tv) * 16;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { dst[j] = s[j]; dst[8 + j] = q[j]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < cols && v < cv) {
+      // thread tv (tr == 0) folds the R rows in fixed order
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+      for (int r = 0; r < R; ++r) {
+        const float* src = part + ((size_t)r * cols + tv) * 16;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] += src[j]; q[j] += src[8 + j]; }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { chan_sum[v * 8 + j] = s[j]; chan_sq[v * 8 + j] = q[j]; }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < groups) {
+    const int g = threadIdx.x;
+    float s = 0.f, q = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) { s += chan_sum[c]; q += chan_sq[c]; }
+    float* out = ws + (((size_t)n * chunks + chunk) * groups + g) * 2;
+    out[0] = s;
+    out[1] = q;
+  }
+}
+
+// Pass 2: finalize mean / rstd per group from the partials, normalise, affine, optional SiLU, store bf16.
+__global__ void __launch_bounds__(kGNThreads)
+gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, const __nv_bfloat16* __restrict__ x2,
+                const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ ws,
+                __nv_bfloat16* __restrict__ y, int hw, int c1, int c2, int groups, int chunks, int ppc, float eps,
+                int with_silu) {
+  __shared__ float s_mean[64], s_rstd[64];
+  const int C = c1 + c2;
+  const int cv = C / 8;
+  const int cpg = C / groups;
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  if (threadIdx.x < groups) {
+    const int g = threadIdx.x;
+    float s = 0.f, q = 0.f;
+    for (int k = 0; k < chunks; ++k) {
+      const float* in = ws + (((size_t)n * chunks + k) * groups + g) * 2;
+      s += in[0];
+      q += in[1];
+    }
+    const float inv = 1.0f / ((float)hw * (float)cpg);
+    const float mean = s * inv;
+    float var = q * inv - mean * mean;
+    var = var < 0.f ? 0.f : var;
+    s_mean[g] = mean;
+    s_rstd[g] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  const int p_begin = chunk * ppc;
+  const int p_end = min(hw, p_begin + ppc);
+  const int cols = cv < kGNThreads ? cv : kGNThreads;
+  const int R = kGNThreads / cols;
+  const int tr = threadIdx.x / cols, tv = threadIdx.x % cols;
+  if (threadIdx.x >= R * cols) return;
+  for (int vbase = 0; vbase < cv; vbase += cols) {
+    const int v = vbase + tv;
+    if (v >= cv) continue;
+    float a[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = v * 8 + j;
+      const int g = c / cpg;
+      const float ga = gamma[c] * s_rstd[g];
+      a[j] = ga;
+      b[j] = beta[c] - s_mean[g] * ga;
+    }
+    for (int pp = p_begin + tr; pp < p_end; pp += R) {
+      const long long pix = (long long)n * hw + pp;
+      float f[8];
+      unpack8(gn_load8(x1, x2, c1, c2, pix, v), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = f[j] * a[j] + b[j];
+        f[j] = with_silu ? silu_f(t) : t;
+      }
+      uint4 o;
+      o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+      o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+      *reinterpret_cast<uint4*>(y + pix * C + v * 8) = o;
+    }
+  }
+}
+
+static void gn_geometry(int n, int hw, int* chunks, int* ppc) {
+  int want = (148 * 4 + n - 1) / n;
+  if (want < 1) want = 1;
+  int p = (hw + want - 1) / want;
+  if (p < 8) p = hw < 8 ? hw : 8;
+  *ppc = p;
+  *chunks = (hw + p - 1) / p;
+}
+
+// One warp per row, the row lives in registers (C <= 2048): exact two-pass mean/variance.
+constexpr int kLNMaxVec = 8;
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 __nv_bfloat16* __restrict__ y, int rows, int C, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int cv = C / 8;
+  const __nv_bfloat16* xr = x + (size_t)warp * C;
+  float f[kLNMaxVec][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLNMaxVec; ++i) {
+    const int v = lane + i * 32;
+    if (v < cv) {
+      unpack8(*reinterpret_cast<const uint4*>(xr + v * 8), f[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += f[i][j];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLNMaxVec; ++i) {
+    const int v = lane + i * 32;
+    if (v < cv) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = f[i][j] - mean; q += d * d; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)C + eps);
+  __nv_bfloat16* yr = y + (size_t)warp * C;
+#pragma unroll
+  for (int i = 0; i < kLNMaxVec; ++i) {
+    const int v = lane + i * 32;
+    if (v < cv) {
+      const float4 g0 = *reinterpret_cast<const float4*>(gamma + v * 8);
+      const float4 g1 = *reinterpret_cast<const float4*>(gamma + v * 8 + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(beta + v * 8);
+      const float4 b1 = *reinterpret_cast<const float4*>(beta + v * 8 + 4);
+      float r[8];
+      r[0] = (f[i][0] - mean) * rstd * g0.x + b0.x; r[1] = (f[i][1] - mean) * rstd * g0.y + b0.y;
+      r[2] = (f[i][2] - mean) * rstd * g0.z + b0.z; r[3] = (f[i][3] - mean) * rstd * g0.w + b0.w;
+      r[4] = (f[i][4] - mean) * rstd * g1.x + b1.x; r[5] = (f[i][5] - mean) * rstd * g1.y + b1.y;
+      r[6] = (f[i][6] - mean) * rstd * g1.z + b1.z; r[7] = (f[i][7] - mean) * rstd * g1.w + b1.w;
+      uint4 o;
+      o.x = pack_bf16x2(r[0], r[1]); o.y = pack_bf16x2(r[2], r[3]);
+      o.z = pack_bf16x2(r[4], r[5]); o.w = pack_bf16x2(r[6], r[7]);
+      *reinterpret_cast<uint4*>(yr + v * 8) = o;
+    }
+  }
+}
+
+}  // namespace sdeo
+
+using namespace sdeo;
+
+extern "C" size_t sdeo_groupnorm_workspace_bytes(int32_t n, int32_t hw, int32_t groups) {
+  int chunks, ppc;
+  gn_geometry(n, hw, &chunks, &ppc);
+  return (size_t)n * chunks * groups * 2 * sizeof(float);
+}
+
+extern "C" int sdeo_groupnorm_nhwc(const void* x1, const void* x2, const float* gamma, const float* beta, void* y,
+                                   int32_t n, int32_t hw, int32_t c1, int32_t c2, int32_t groups, float eps,
+                                   int32_t with_silu, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!x1 || !gamma || !beta || !y || !workspace) return set_error(SDEO_EINVAL, "groupnorm: null argument");
+  if (!x2) c2 = 0;
+  const int C = c1 + c2;
+  if (n <= 0 || hw <= 0 || groups <= 0 || groups > 64 || C % groups != 0 || c1 % 8 != 0 || c2 % 8 != 0)
+    return set_error(SDEO_EINVAL, "groupnorm: unsupported geometry (need C % groups == 0, channels % 8 == 0, groups <= 64)");
+  if (n > 65535) return set_error(SDEO_EINVAL, "groupnorm: batch too large");
+  int chunks, ppc;
+  gn_geometry(n, hw, &chunks, &ppc);
+  if (workspace_bytes < (size_t)n * chunks * groups * 2 * sizeof(float))
+    return set_error(SDEO_EINVAL, "groupnorm: workspace too small");
+  const size_t smem = (size_t)(2 * C + kGNThreads * 16) * sizeof(float);
+  if (smem > 48 * 1024) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      if (e != cudaSuccess) return set_error(SDEO_ECUDA, cudaGetErrorString(e));
+      attr_set = true;
+    }
+    if (smem > 100 * 1024) return set_error(SDEO_EINVAL, "groupnorm: too many channels");
+  }
+  dim3 grid((unsigned)chunks, (unsigned)n);
+  gn_stats_kernel<<<grid, kGNThreads, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)x1, (const __nv_bfloat16*)x2,
+                                                                    (float*)workspace, hw, c1, c2, groups, chunks, ppc);
+  int rc = check_launch("groupnorm stats");
+  if (rc) return rc;
+  gn_apply_kernel<<<grid, kGNThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x1, (const __nv_bfloat16*)x2, gamma,
+                                                                 beta, (const float*)workspace, (__nv_bfloat16*)y, hw, c1,
+                                                                 c2, groups, chunks, ppc, eps, with_silu);
+  return check_launch("groupnorm apply");
+}
+
+extern "C" int sdeo_layernorm(const void* x, const float* gamma, const float* beta, void* y, int32_t rows, int32_t c,
+                              float eps, void* stream) {
+  if (!x || !gamma || !beta || !y) return set_error(SDEO_EINVAL, "layernorm: null argument");
+  if (rows <= 0 || c % 8 != 0 || c > kLNMaxVec * 32 * 8) return set_error(SDEO_EINVAL, "layernorm: need C % 8 == 0 and C <= 2048");
+  const int warps_per_block = 8;
+  const int blocks = (rows + warps_per_block - 1) / warps_per_block;
+  layernorm_kernel<<<blocks, warps_per_block * 32, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, gamma, beta,
+                                                                              (__nv_bfloat16*)y, rows, c, eps);
+  return check_launch("layernorm");
+}

@@ -1,0 +1,354 @@
+"""Torch-tensor front end of the C-ABI kernels. torch provides device memory and streams only; every op here
+is one call into libsdeo.so on the current CUDA stream. Activations are bf16, physically NHWC: shape [N, H, W, C]
+contiguous; token matrices are [rows, C] or [B, T, C] contiguous."""
+import ctypes
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from ._lib import ConvArgs, SDEO_ACT_NONE, SDEO_ACT_SILU, SDEO_EPI_GEGLU, SDEO_EPI_NORMAL, SDEO_EPI_QKV, check
+
+BF16 = torch.bfloat16
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _req(t, dtype, name):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise _lib.SdeoError(f"{name}: expected a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise _lib.SdeoError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.SdeoError(f"{name}: expected a contiguous tensor")
+
+
+class _Workspaces:
+    """Per-(device, slot) scratch: split-K partial tiles + tile counters for conv2d, GroupNorm partial sums.
+    Ops issued concurrently on different streams must use different slots (see `workspace_slot`)."""
+
+    def __init__(self):
+        self._conv = {}
+        self._gn = {}
+        self.slot = 0
+
+    def conv(self, device):
+        key = (device.index, self.slot)
+        ws = self._conv.get(key)
+        if ws is None:
+            lib = _lib.load()
+            nbytes = lib.sdeo_conv_workspace_bytes(None)
+            ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)  # counters must start at zero
+            self._conv[key] = ws
+        return ws
+
+    def gn(self, device, nbytes):
+        key = (device.index, self.slot)
+        ws = self._gn.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+            self._gn[key] = ws
+        return ws
+
+
+_workspaces = _Workspaces()
+
+
+class workspace_slot:
+    """Context manager selecting the scratch slot used by ops issued inside it (one slot per concurrent stream)."""
+
+    def __init__(self, slot):
+        self.slot = slot
+
+    def __enter__(self):
+        self.prev = _workspaces.slot
+        _workspaces.slot = self.slot
+
+    def __exit__(self, *exc):
+        _workspaces.slot = self.prev
+
+
+@dataclass
+class PackedWeight:
+    """bf16 K-major filter in the layout conv_gemm_kernel streams (see sdeo_pack_conv_weight)."""
+    data: torch.Tensor
+    cout: int
+    ksize: int
+    c1: int
+    c2: int
+    geglu_bn: int = 0
+
+
+def pack_conv_weight(weight, c1=None, c2=0, geglu=False):
+    """weight: fp32 [cout, cin, k, k] or [cout, cin] (Linear) on the GPU. c1/c2 split cin for fused concat inputs."""
+    lib = _lib.load()
+    if weight.dim() == 2:
+        weight = weight[:, :, None, None]
+    weight = weight.detach().to(torch.float32).contiguous()
+    _req(weight, torch.float32, "weight")
+    cout, cin, k, k2 = weight.shape
+    assert k == k2 and k in (1, 3)
+    if c1 is None:
+        c1 = cin
+    assert c1 + c2 == cin
+    rows = lib.sdeo_packed_rows(cout)
+    kp = lib.sdeo_packed_k(c1, c2, k)
+    geglu_bn = 0
+    if geglu:
+        geglu_bn = lib.sdeo_pick_bn(rows, SDEO_EPI_GEGLU, 0)
+        if geglu_bn <= 0:
+            raise _lib.SdeoError(f"no GEGLU tile for {cout} rows")
+    out = torch.empty((rows, kp), dtype=BF16, device=weight.device)
+    check(lib.sdeo_pack_conv_weight(_ptr(weight), cout, c1, c2, k, geglu_bn, _ptr(out), _stream()), "pack_conv_weight")
+    return PackedWeight(out, cout, k, c1, c2, geglu_bn)
+
+
+def pack_geglu_bias(bias, geglu_bn):
+    lib = _lib.load()
+    bias = bias.detach().to(torch.float32).contiguous()
+    out = torch.empty_like(bias)
+    check(lib.sdeo_pack_geglu_bias(_ptr(bias), bias.numel(), geglu_bn, _ptr(out), _stream()), "pack_geglu_bias")
+    return out
+
+
+def conv2d(x, pw, x2=None, bias=None, emb=None, residual=None, scale=1.0, act=SDEO_ACT_NONE, stride=1, out=None,
+           out_fp32=False, epi_mode=SDEO_EPI_NORMAL, qkv=None):
+    """x: [N,H,W,C1] bf16 (+ optional x2 [N,H,W,C2] = fused torch.cat along channels). Returns [N,Ho,Wo,cout]."""
+    lib = _lib.load()
+    _req(x, BF16, "x")
+    _req(x2, BF16, "x2")
+    _req(bias, torch.float32, "bias")
+    _req(emb, torch.float32, "emb")
+    _req(residual, BF16, "residual")
+    n, h, w, c1 = x.shape
+    assert c1 == pw.c1, f"conv2d: input has {c1} channels, filter packed for {pw.c1}"
+    c2 = 0
+    if x2 is not None:
+        assert x2.shape[:3] == x.shape[:3] and x2.shape[3] == pw.c2
+        c2 = pw.c2
+    else:
+        assert pw.c2 == 0
+    k = pw.ksize
+    pad = 1 if k == 3 else 0
+    ho = (h + 2 * pad - k) // stride + 1
+    wo = (w + 2 * pad - k) // stride + 1
+    a = ConvArgs()
+    a.x1, a.x2 = _ptr(x), _ptr(x2)
+    a.n, a.h, a.w = n, h, w
+    a.c1, a.ld1, a.c2, a.ld2 = c1, c1, c2, c2
+    a.w_packed = _ptr(pw.data)
+    a.cout, a.ksize, a.stride, a.pad = pw.cout, k, stride, pad
+    a.epi_mode, a.act = epi_mode, act
+    a.bias, a.emb = _ptr(bias), _ptr(emb)
+    a.scale = float(scale)
+    a.y_fp32 = 1 if out_fp32 else 0
+    if epi_mode == SDEO_EPI_QKV:
+        q, kk, vt, heads, dhead, tokens, ldv, first = qkv
+        a.q, a.k, a.vt = _ptr(q), _ptr(kk), _ptr(vt)
+        a.heads, a.dhead, a.tokens, a.ldv, a.qkv_first = heads, dhead, tokens, ldv, first
+        out = None
+    else:
+        cols = pw.cout // 2 if epi_mode == SDEO_EPI_GEGLU else pw.cout
+        if out is None:
+            out = torch.empty((n, ho, wo, cols), dtype=torch.float32 if out_fp32 else BF16, device=x.device)
+        else:
+            assert out.shape == (n, ho, wo, cols) and out.is_contiguous()
+            assert out.dtype == (torch.float32 if out_fp32 else BF16)
+        a.y, a.ldy = _ptr(out), cols
+        if residual is not None:
+            assert residual.shape == out.shape
+            a.residual, a.ldr = _ptr(residual), cols
+    ws = _workspaces.conv(x.device)
+    a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
+    check(lib.sdeo_conv2d(ctypes.byref(a), _stream()), "conv2d")
+    return out
+
+
+def linear(x, pw, bias=None, residual=None, act=SDEO_ACT_NONE, out_fp32=False, geglu=False):
+    """x: [..., K] bf16 -> [..., cout] (GEGLU: [..., cout/2]). Runs the 1x1 case of the implicit-GEMM kernel."""
+    lead = x.shape[:-1]
+    rows = 1
+    for s in lead:
+        rows *= s
+    x4 = x.reshape(1, 1, rows, x.shape[-1])
+    res4 = residual.reshape(1, 1, rows, residual.shape[-1]) if residual is not None else None
+    y = conv2d(x4, pw, bias=bias, residual=res4, act=act, out_fp32=out_fp32,
+               epi_mode=SDEO_EPI_GEGLU if geglu else SDEO_EPI_NORMAL)
+    return y.reshape(*lead, y.shape[-1])
+
+
+def qkv_project(x, pw, heads, dhead, first, q=None, k=None, vt=None, ldv=None, bias=None):
+    """x: [B, T, K] bf16. Packed rows hold consecutive blocks of heads*dhead columns for q/k/v starting at
+    `first` (0=q, 1=k, 2=v). Writes q,k as [B*heads, T, dhead] and v transposed as [B*heads, dhead, ldv]."""
+    b, t, kdim = x.shape
+    x4 = x.reshape(1, 1, b * t, kdim)
+    conv2d(x4, pw, bias=bias, epi_mode=SDEO_EPI_QKV, qkv=(q, k, vt, heads, dhead, t, ldv or 0, first))
+
+
+def groupnorm(x, gamma, beta, eps, silu, x2=None, groups=32, out=None):
+    """x: [N,H,W,C1] (+ x2 [N,H,W,C2]); returns the normalised concat [N,H,W,C1+C2]."""
+    lib = _lib.load()
+    _req(x, BF16, "x")
+    _req(x2, BF16, "x2")
+    _req(gamma, torch.float32, "gamma")
+    _req(beta, torch.float32, "beta")
+    n, h, w, c1 = x.shape
+    c2 = x2.shape[3] if x2 is not None else 0
+    if out is None:
+        out = torch.empty((n, h, w, c1 + c2), dtype=BF16, device=x.device)
+    nbytes = lib.sdeo_groupnorm_workspace_bytes(n, h * w, groups)
+    ws = _workspaces.gn(x.device, nbytes)
+    check(lib.sdeo_groupnorm_nhwc(_ptr(x), _ptr(x2), _ptr(gamma), _ptr(beta), _ptr(out), n, h * w, c1, c2, groups,
+                                  float(eps), 1 if silu else 0, _ptr(ws), ws.numel(), _stream()), "groupnorm")
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5):
+    lib = _lib.load()
+    _req(x, BF16, "x")
+    c = x.shape[-1]
+    rows = x.numel() // c
+    out = torch.empty_like(x)
+    check(lib.sdeo_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), rows, c, float(eps), _stream()), "layernorm")
+    return out
+
+
+def attention(q, k, vt, batch, heads, nq, nkv, d, ldv, scale, out=None):
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty((batch, nq, heads * d), dtype=BF16, device=q.device)
+    check(lib.sdeo_attention(_ptr(q), _ptr(k), _ptr(vt), _ptr(out), batch, heads, nq, nkv, d, ldv, float(scale),
+                             _stream()), "attention")
+    return out
+
+
+def softmax_rows(x, scale, out=None):
+    lib = _lib.load()
+    _req(x, BF16, "x")
+    rows, cols = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.sdeo_softmax_rows(_ptr(x), _ptr(out), rows, cols, cols, float(scale), _stream()), "softmax_rows")
+    return out
+
+
+def nchw_to_nhwc(x, ldy=None):
+    """fp32 [N,C,H,W] -> bf16 [N,H,W,ldy] (channels zero-padded to ldy, default round_up(C, 8))."""
+    lib = _lib.load()
+    x = x.contiguous()
+    _req(x, torch.float32, "x")
+    n, c, h, w = x.shape
+    if ldy is None:
+        ldy = (c + 7) // 8 * 8
+    out = torch.empty((n, h, w, ldy), dtype=BF16, device=x.device)
+    check(lib.sdeo_nchw_to_nhwc_bf16(_ptr(x), _ptr(out), n, c, h * w, ldy, _stream()), "nchw_to_nhwc")
+    return out
+
+
+def nhwc_to_nchw(x, c=None):
+    """bf16 or fp32 [N,H,W,ld] -> fp32 [N,c,H,W]."""
+    lib = _lib.load()
+    assert x.is_contiguous()
+    n, h, w, ld = x.shape
+    if c is None:
+        c = ld
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    if x.dtype == BF16:
+        check(lib.sdeo_nhwc_bf16_to_nchw(_ptr(x), _ptr(out), n, c, h * w, ld, _stream()), "nhwc_to_nchw")
+    else:
+        _req(x, torch.float32, "x")
+        check(lib.sdeo_nhwc_f32_to_nchw(_ptr(x), _ptr(out), n, c, h * w, ld, _stream()), "nhwc_f32_to_nchw")
+    return out
+
+
+def upsample_nearest2x(x):
+    lib = _lib.load()
+    _req(x, BF16, "x")
+    n, h, w, c = x.shape
+    out = torch.empty((n, 2 * h, 2 * w, c), dtype=BF16, device=x.device)
+    check(lib.sdeo_upsample_nearest2x(_ptr(x), _ptr(out), n, h, w, c, _stream()), "upsample2x")
+    return out
+
+
+def add_scaled(a, b, alpha=1.0, out=None):
+    lib = _lib.load()
+    _req(a, BF16, "a")
+    _req(b, BF16, "b")
+    assert a.shape == b.shape
+    if out is None:
+        out = torch.empty_like(a)
+    check(lib.sdeo_add_scaled(_ptr(a), _ptr(b), float(alpha), _ptr(out), a.numel(), _stream()), "add_scaled")
+    return out
+
+
+def timestep_embedding(t, n, dim, step_idx=None, max_period=10000.0):
+    """t: int64 device tensor ([n], or a per-step table when step_idx is given) -> bf16 [n, dim], [cos | sin]."""
+    lib = _lib.load()
+    _req(t, torch.int64, "t")
+    out = torch.empty((n, dim), dtype=BF16, device=t.device)
+    check(lib.sdeo_timestep_embedding(_ptr(t), _ptr(step_idx), _ptr(out), n, dim, dim, float(max_period), _stream()),
+          "timestep_embedding")
+    return out
+
+
+def silu(x):
+    lib = _lib.load()
+    _req(x, BF16, "x")
+    out = torch.empty_like(x)
+    check(lib.sdeo_silu(_ptr(x), _ptr(out), x.numel(), _stream()), "silu")
+    return out
+
+
+def to_bf16(x):
+    lib = _lib.load()
+    x = x.contiguous()
+    _req(x, torch.float32, "x")
+    out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    check(lib.sdeo_f32_to_bf16(_ptr(x), _ptr(out), x.numel(), _stream()), "f32_to_bf16")
+    return out
+
+
+def to_f32(x):
+    lib = _lib.load()
+    _req(x, BF16, "x")
+    out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    check(lib.sdeo_bf16_to_f32(_ptr(x), _ptr(out), x.numel(), _stream()), "bf16_to_f32")
+    return out
+
+
+def cfg_ddim_step(eps_c, eps_u, x, coef_table, step_idx=None, noise=None, x_prev=None, pred_x0=None, x_next=None,
+                  dup=0, eps_nhwc=False):
+    """x: fp32 [N,C,H,W]. eps_*: fp32 NCHW, or NHWC [N,H,W,ld] when eps_nhwc. Returns (x_prev, pred_x0)."""
+    lib = _lib.load()
+    _req(x, torch.float32, "x")
+    n, c, h, w = x.shape
+    ld_eps = eps_c.shape[-1] if eps_nhwc else 0
+    if x_prev is None:
+        x_prev = torch.empty_like(x)
+    ldn = x_next.shape[-1] if x_next is not None else 0
+    check(lib.sdeo_cfg_ddim_step(_ptr(eps_c), _ptr(eps_u), 1 if eps_nhwc else 0, ld_eps, _ptr(x), _ptr(noise),
+                                 _ptr(x_prev), _ptr(pred_x0), _ptr(x_next), dup, ldn, _ptr(coef_table),
+                                 _ptr(step_idx), n, c, h * w, _stream()), "cfg_ddim_step")
+    return x_prev, pred_x0
+
+
+def counter_add(ctr, delta=1):
+    lib = _lib.load()
+    check(lib.sdeo_counter_add(_ptr(ctr), int(delta), _stream()), "counter_add")
+
+
+def image_to_u8(x, c=3):
+    lib = _lib.load()
+    _req(x, BF16, "x")
+    n, h, w, ld = x.shape
+    out = torch.empty((n, h, w, c), dtype=torch.uint8, device=x.device)
+    check(lib.sdeo_image_to_u8(_ptr(x), _ptr(out), n * h * w, c, ld, _stream()), "image_to_u8")
+    return out

@@ -1,0 +1,319 @@
+"""GPU parity of each C-ABI kernel against plain torch fp32 math on the same bf16-rounded inputs.
+Tolerances: outputs are bf16 (8 mantissa bits) from fp32 accumulation -> relative L2 <= 4e-3 per op
+(north_star's end-to-end bar for bf16 is 1e-2)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+TOL = 4e-3
+
+
+def rel_l2(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+def bf16r(t):
+    return t.to(torch.bfloat16).float()
+
+
+def gen(shape, seed, dev, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dev)
+
+
+def nhwc(x_nchw):
+    return x_nchw.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def ref_conv(x_nchw, w, bias, stride, emb=None, act=False, scale=1.0, residual=None):
+    k = w.shape[-1]
+    y = F.conv2d(bf16r(x_nchw), bf16r(w), bias, stride=stride, padding=1 if k == 3 else 0)
+    if emb is not None:
+        y = y + emb[:, :, None, None]
+    if act:
+        y = F.silu(y)
+    y = y * scale
+    if residual is not None:
+        y = y + bf16r(residual)
+    return y
+
+
+CONV_CASES = [
+    # (n, cin, cout, h, w, k, stride)   -- shapes from SURVEY Appendix A (256x384, cond+uncond batch 2)
+    (2, 320, 320, 32, 48, 3, 1),
+    (2, 320, 320, 32, 48, 1, 1),
+    (2, 320, 320, 32, 48, 3, 2),     # Downsample
+    (2, 640, 1280, 8, 12, 3, 1),
+    (2, 1280, 1280, 8, 12, 3, 1),    # split-K, 96-row tiles
+    (2, 1280, 1280, 4, 6, 3, 1),     # tile box spans the batch
+    (1, 1280, 1280, 4, 6, 1, 1),
+    (2, 8, 320, 32, 48, 3, 1),       # conv_in (4 channels padded to 8)
+    (2, 320, 4, 32, 48, 3, 1),       # UNet out conv
+    (1, 16, 32, 64, 96, 3, 2),       # hint block stride 2, tiny channels
+    (1, 96, 96, 20, 28, 3, 1),       # ragged tiles
+    (3, 64, 48, 5, 7, 3, 1),         # odd everything
+    (1, 128, 3, 40, 56, 3, 1),       # VAE conv_out
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv2d_plain(cuda_device, case):
+    from stablediffusioneo_b200 import ops
+    n, cin, cout, h, w, k, stride = case
+    dev = cuda_device
+    x = gen((n, cin, h, w), 1, dev)
+    wt = gen((cout, cin, k, k), 2, dev, scale=1.0 / math.sqrt(cin * k * k))
+    b = gen((cout,), 3, dev)
+    pw = ops.pack_conv_weight(wt)
+    y = ops.conv2d(nhwc(x), pw, bias=b, stride=stride)
+    ref = ref_conv(x, wt, b, stride)
+    assert y.shape == (n, ref.shape[2], ref.shape[3], cout)
+    err = rel_l2(y.permute(0, 3, 1, 2), ref)
+    assert err < TOL, f"rel L2 {err}"
+
+
+def test_conv2d_full_epilogue(cuda_device):
+    """bias + per-sample time-embedding term + SiLU + scale + residual, fp32 and bf16 outputs."""
+    from stablediffusioneo_b200 import ops
+    dev = cuda_device
+    n, cin, cout, h, w = 2, 320, 640, 16, 24
+    x = gen((n, cin, h, w), 1, dev)
+    wt = gen((cout, cin, 3, 3), 2, dev, scale=1.0 / math.sqrt(cin * 9))
+    b = gen((cout,), 3, dev)
+    emb = gen((n, cout), 4, dev)
+    res = gen((n, cout, h, w), 5, dev)
+    pw = ops.pack_conv_weight(wt)
+    for act in (False, True):
+        ref = ref_conv(x, wt, b, 1, emb=emb, act=act, scale=0.7, residual=res)
+        y = ops.conv2d(nhwc(x), pw, bias=b, emb=emb.contiguous(), residual=nhwc(res), scale=0.7, act=1 if act else 0)
+        assert rel_l2(y.permute(0, 3, 1, 2), ref) < TOL
+        y32 = ops.conv2d(nhwc(x), pw, bias=b, emb=emb.contiguous(), residual=nhwc(res), scale=0.7, act=1 if act else 0,
+                         out_fp32=True)
+        assert y32.dtype == torch.float32
+        assert rel_l2(y32.permute(0, 3, 1, 2), ref) < 2e-3
+
+
+@pytest.mark.parametrize("c1,c2,cout,h,w,k", [(640, 320, 320, 32, 48, 3), (1280, 640, 1280, 8, 12, 1),
+                                               (1280, 1280, 1280, 4, 6, 3)])
+def test_conv2d_fused_concat(cuda_device, c1, c2, cout, h, w, k):
+    """torch.cat([h, skip], 1) -> conv (cldm/cldm.py:41 + ResBlock) as a dual-source K loop."""
+    from stablediffusioneo_b200 import ops
+    dev = cuda_device
+    xa, xb = gen((2, c1, h, w), 1, dev), gen((2, c2, h, w), 2, dev)
+    wt = gen((cout, c1 + c2, k, k), 3, dev, scale=1.0 / math.sqrt((c1 + c2) * k * k))
+    b = gen((cout,), 4, dev)
+    pw = ops.pack_conv_weight(wt, c1=c1, c2=c2)
+    y = ops.conv2d(nhwc(xa), pw, x2=nhwc(xb), bias=b)
+    ref = ref_conv(torch.cat([xa, xb], 1), wt, b, 1)
+    assert rel_l2(y.permute(0, 3, 1, 2), ref) < TOL
+
+
+@pytest.mark.parametrize("rows,kdim,ndim", [(3072, 320, 320), (768, 640, 640), (192, 1280, 1280), (48, 1280, 1280),
+                                            (2, 320, 1280), (2, 1280, 1280), (154, 768, 640), (77, 768, 2560)])
+def test_linear(cuda_device, rows, kdim, ndim):
+    from stablediffusioneo_b200 import ops
+    dev = cuda_device
+    x = gen((rows, kdim), 1, dev)
+    wt = gen((ndim, kdim), 2, dev, scale=1.0 / math.sqrt(kdim))
+    b = gen((ndim,), 3, dev)
+    res = gen((rows, ndim), 4, dev)
+    pw = ops.pack_conv_weight(wt)
+    y = ops.linear(x.to(torch.bfloat16), pw, bias=b, residual=res.to(torch.bfloat16))
+    ref = F.linear(bf16r(x), bf16r(wt), b) + bf16r(res)
+    assert rel_l2(y, ref) < TOL
+
+
+@pytest.mark.parametrize("rows,c", [(3072, 320), (768, 640), (192, 1280), (48, 1280)])
+def test_linear_geglu(cuda_device, rows, c):
+    """GEGLU (attention.py:49-56): proj -> chunk(2) -> x * gelu(gate), fused into the projection epilogue."""
+    from stablediffusioneo_b200 import ops
+    dev = cuda_device
+    inner = 4 * c
+    x = gen((rows, c), 1, dev)
+    wt = gen((2 * inner, c), 2, dev, scale=1.0 / math.sqrt(c))
+    b = gen((2 * inner,), 3, dev, scale=0.5)
+    pw = ops.pack_conv_weight(wt, geglu=True)
+    bp = ops.pack_geglu_bias(b, pw.geglu_bn)
+    y = ops.linear(x.to(torch.bfloat16), pw, bias=bp, geglu=True)
+    h = F.linear(bf16r(x), bf16r(wt), b)
+    a, g = h.chunk(2, dim=-1)
+    ref = a * F.gelu(g)
+    assert y.shape == (rows, inner)
+    assert rel_l2(y, ref) < TOL
+
+
+@pytest.mark.parametrize("b,t,c,heads", [(2, 1536, 320, 8), (2, 384, 640, 8), (2, 96, 1280, 8), (2, 24, 1280, 8)])
+def test_qkv_projection_layout(cuda_device, b, t, c, heads):
+    """Fused qkv_w = cat([Wq, Wk, Wv]).T (attention.py:170,193-194) with the head split (attention.py:227)."""
+    from stablediffusioneo_b200 import ops
+    dev = cuda_device
+    d = c // heads
+    x = gen((b, t, c), 1, dev)
+    wq, wk, wv = (gen((c, c), s, dev, scale=1.0 / math.sqrt(c)) for s in (2, 3, 4))
+    pw = ops.pack_conv_weight(torch.cat([wq, wk, wv], 0))
+    q = torch.empty((b * heads, t, d), dtype=torch.bfloat16, device=dev)
+    k = torch.empty_like(q)
+    vt = torch.empty((b * heads, d, t), dtype=torch.bfloat16, device=dev)
+    ops.qkv_project(x.to(torch.bfloat16), pw, heads, d, 0, q=q, k=k, vt=vt, ldv=t)
+    xr = bf16r(x)
+
+    def split(wm):
+        y = F.linear(xr, bf16r(wm))  # [b, t, c]
+        return y.view(b, t, heads, d).permute(0, 2, 1, 3).reshape(b * heads, t, d)
+
+    assert rel_l2(q, split(wq)) < TOL
+    assert rel_l2(k, split(wk)) < TOL
+    assert rel_l2(vt, split(wv).transpose(1, 2)) < TOL
+
+
+GN_CASES = [
+    # (n, c1, c2, h, w, eps, silu)
+    (2, 320, 0, 32, 48, 1e-5, True),
+    (2, 320, 0, 32, 48, 1e-6, False),
+    (2, 640, 320, 32, 48, 1e-5, True),     # C=960: concat seam inside group 21
+    (2, 1280, 640, 16, 24, 1e-5, True),    # C=1920: concat seam inside group 21
+    (2, 1280, 1280, 8, 12, 1e-5, True),    # C=2560 (> 256 channel vectors)
+    (2, 1280, 0, 4, 6, 1e-5, True),
+    (1, 128, 0, 64, 96, 1e-6, True),       # VAE: 4 channels per group
+    (3, 512, 0, 9, 7, 1e-6, False),
+]
+
+
+@pytest.mark.parametrize("case", GN_CASES)
+def test_groupnorm(cuda_device, case):
+    from stablediffusioneo_b200 import ops
+    n, c1, c2, h, w, eps, silu = case
+    dev = cuda_device
+    xa = gen((n, c1, h, w), 1, dev) * 1.7 + 0.3
+    xb = gen((n, c2, h, w), 2, dev) * 0.6 - 0.5 if c2 else None
+    gamma = gen((c1 + c2,), 3, dev) * 0.2 + 1.0
+    beta = gen((c1 + c2,), 4, dev) * 0.2
+    y = ops.groupnorm(nhwc(xa), gamma, beta, eps, silu, x2=nhwc(xb) if c2 else None)
+    xcat = bf16r(torch.cat([xa, xb], 1) if c2 else xa)
+    ref = F.group_norm(xcat, 32, gamma, beta, eps)
+    if silu:
+        ref = F.silu(ref)
+    assert rel_l2(y.permute(0, 3, 1, 2), ref) < TOL
+
+
+@pytest.mark.parametrize("rows,c", [(3072, 320), (768, 640), (192, 1280), (48, 1280), (5, 512)])
+def test_layernorm(cuda_device, rows, c):
+    from stablediffusioneo_b200 import ops
+    dev = cuda_device
+    x = gen((rows, c), 1, dev) * 2.0 + 0.5
+    gamma = gen((c,), 2, dev) * 0.2 + 1.0
+    beta = gen((c,), 3, dev) * 0.2
+    y = ops.layernorm(x.to(torch.bfloat16), gamma, beta, 1e-5)
+    ref = F.layer_norm(bf16r(x), (c,), gamma, beta, 1e-5)
+    assert rel_l2(y, ref) < TOL
+
+
+ATT_CASES = [
+    # (batch, heads, nq, nkv, d)
+    (2, 8, 1536, 1536, 40),
+    (2, 8, 384, 384, 80),
+    (2, 8, 96, 96, 160),
+    (2, 8, 24, 24, 160),
+    (2, 8, 1536, 77, 40),   # cross-attention, 77-token CLIP context
+    (2, 8, 384, 77, 80),
+    (2, 8, 96, 77, 160),
+    (2, 8, 24, 77, 160),
+    (1, 8, 576, 576, 80),   # 768x768: ragged query tile (576 = 4.5 x 128)
+    (1, 2, 200, 333, 40),   # ragged everything
+]
+
+
+@pytest.mark.parametrize("case", ATT_CASES)
+def test_attention(cuda_device, case):
+    """softmax(q k^T d^-1/2) v with fp32 scores (attention.py:227-249)."""
+    from stablediffusioneo_b200 import ops
+    b, heads, nq, nkv, d = case
+    dev = cuda_device
+    q = gen((b * heads, nq, d), 1, dev)
+    k = gen((b * heads, nkv, d), 2, dev)
+    v = gen((b * heads, nkv, d), 3, dev)
+    ldv = (nkv + 7) // 8 * 8
+    vt = torch.zeros((b * heads, d, ldv), dtype=torch.bfloat16, device=dev)
+    vt[:, :, :nkv] = v.transpose(1, 2).to(torch.bfloat16)
+    scale = d ** -0.5
+    o = ops.attention(q.to(torch.bfloat16), k.to(torch.bfloat16), vt, b, heads, nq, nkv, d, ldv, scale)
+    sim = torch.einsum("bid,bjd->bij", bf16r(q), bf16r(k)) * scale
+    ref = torch.einsum("bij,bjd->bid", sim.softmax(-1), bf16r(v))
+    ref = ref.view(b, heads, nq, d).permute(0, 2, 1, 3).reshape(b, nq, heads * d)
+    err = rel_l2(o, ref)
+    assert err < 8e-3, f"rel L2 {err}"  # P is rounded to bf16 before the PV product
+
+
+def test_elementwise(cuda_device):
+    from stablediffusioneo_b200 import ops
+    dev = cuda_device
+    # layout round trip with channel padding
+    x = gen((2, 4, 32, 48), 1, dev)
+    y = ops.nchw_to_nhwc(x, 8)
+    assert y.shape == (2, 32, 48, 8)
+    assert torch.equal(y[..., :4].float(), bf16r(x).permute(0, 2, 3, 1))
+    assert torch.count_nonzero(y[..., 4:]) == 0
+    back = ops.nhwc_to_nchw(y, 4)
+    assert torch.equal(back, bf16r(x))
+    x3 = gen((2, 320, 7, 5), 2, dev)
+    assert torch.equal(ops.nhwc_to_nchw(ops.nchw_to_nhwc(x3)), bf16r(x3))
+    # upsample
+    u = ops.upsample_nearest2x(nhwc(x3))
+    refu = F.interpolate(bf16r(x3), scale_factor=2, mode="nearest")
+    assert torch.equal(u.permute(0, 3, 1, 2).float(), refu)
+    # add_scaled
+    a, b = gen((3, 5, 7, 24), 3, dev), gen((3, 5, 7, 24), 4, dev)
+    s = ops.add_scaled(a.to(torch.bfloat16), b.to(torch.bfloat16), 0.5)
+    assert rel_l2(s, bf16r(a) + 0.5 * bf16r(b)) < TOL
+    # timestep embedding: [cos | sin] (util.py:165-169)
+    t = torch.tensor([951, 1], dtype=torch.int64, device=dev)
+    e = ops.timestep_embedding(t, 2, 320)
+    half = 160
+    freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32, device=dev) / half)
+    args = t[:, None].float() * freqs[None]
+    ref = torch.cat([torch.cos(args), torch.sin(args)], -1)
+    assert (e.float() - ref).abs().max().item() < 1e-2
+    # silu / casts
+    z = gen((1000,), 5, dev)
+    assert rel_l2(ops.silu(z.to(torch.bfloat16)), F.silu(bf16r(z))) < TOL
+    assert torch.equal(ops.to_f32(ops.to_bf16(z)), bf16r(z))
+    # row softmax
+    sm = gen((37, 1536), 6, dev) * 3
+    p = ops.softmax_rows(sm.to(torch.bfloat16), 0.125)
+    assert rel_l2(p, (bf16r(sm) * 0.125).softmax(-1)) < TOL
+
+
+def test_cfg_ddim_step(cuda_device):
+    """e = eu + s(ec - eu); x0 = (x - sqrt(1-a_t) e)/sqrt(a_t); x_prev = sqrt(a_prev) x0 + sqrt(1-a_prev-sig^2) e + sig*noise
+    (cldm/ddim_hacked.py:192,215,226-230)."""
+    from stablediffusioneo_b200 import ops
+    dev = cuda_device
+    n, c, h, w = 2, 4, 32, 48
+    ec, eu, x, noise = (gen((n, c, h, w), s, dev) for s in (1, 2, 3, 4))
+    a_t, a_prev, sigma, s = 0.35, 0.52, 0.1, 9.0
+    row = [s, math.sqrt(1 - a_t), 1 / math.sqrt(a_t), math.sqrt(a_prev), math.sqrt(1 - a_prev - sigma ** 2), sigma, 0, 0]
+    table = torch.tensor([[0.0] * 8, row], dtype=torch.float32, device=dev)
+    idx = torch.tensor([1], dtype=torch.int32, device=dev)
+    e = eu + s * (ec - eu)
+    x0 = (x - math.sqrt(1 - a_t) * e) / math.sqrt(a_t)
+    ref = math.sqrt(a_prev) * x0 + math.sqrt(1 - a_prev - sigma ** 2) * e + sigma * noise
+    pred = torch.empty_like(x)
+    xn = torch.empty((2 * n, h, w, 8), dtype=torch.bfloat16, device=dev)
+    xp, _ = ops.cfg_ddim_step(ec, eu, x, table, step_idx=idx, noise=noise, pred_x0=pred, x_next=xn, dup=2)
+    assert rel_l2(xp, ref) < 1e-5
+    assert rel_l2(pred, x0) < 1e-5
+    assert torch.equal(xn[:n, ..., :4].float(), bf16r(xp).permute(0, 2, 3, 1))
+    assert torch.equal(xn[n:], xn[:n])
+    assert torch.count_nonzero(xn[..., 4:]) == 0
+    # NHWC eps (the UNet out-conv layout), no noise
+    ec_l = ec.permute(0, 2, 3, 1).contiguous()
+    eu_l = eu.permute(0, 2, 3, 1).contiguous()
+    xp2, _ = ops.cfg_ddim_step(ec_l, eu_l, x, table, step_idx=idx, eps_nhwc=True)
+    assert rel_l2(xp2, ref - sigma * noise) < 1e-5
+    ops.counter_add(idx, 1)
+    assert idx.item() == 2
