@@ -141,8 +141,10 @@ int sdeo_cfg_ddim_step(const float* eps_c, const float* eps_u, int32_t eps_nhwc,
                        void* stream);
 /* *ctr += delta (single thread) — advances the device-side step index between graph replays. */
 int sdeo_counter_add(int32_t* ctr, int32_t delta, void* stream);
-/* fp32 NCHW -> bf16 NHWC with channel padding to ldy (zeros), and back (first c channels). */
-int sdeo_nchw_to_nhwc_bf16(const float* x, void* y, int32_t n, int32_t c, int32_t hw, int32_t ldy, void* stream);
+/* fp32 NCHW -> bf16 NHWC (y = scale * x) with channel padding to ldy (zeros), and back (first c channels).
+ * `scale` folds decode_first_stage's 1/scale_factor (canny2image_torch.py:64-67) into the layout pass. */
+int sdeo_nchw_to_nhwc_bf16(const float* x, void* y, int32_t n, int32_t c, int32_t hw, int32_t ldy, float scale,
+                           void* stream);
 int sdeo_nhwc_bf16_to_nchw(const void* x, float* y, int32_t n, int32_t c, int32_t hw, int32_t ldx, void* stream);
 int sdeo_nhwc_f32_to_nchw(const float* x, float* y, int32_t n, int32_t c, int32_t hw, int32_t ldx, void* stream);
 /* nearest x2 upsample, NHWC bf16 (F.interpolate(scale_factor=2, mode="nearest"), openaimodel.py:115) */
@@ -153,8 +155,9 @@ int sdeo_add_scaled(const void* a, const void* b, float alpha, void* y, int64_t 
  * t is int64 device memory: t[i] for sample i, or, when step_idx != NULL, t[*step_idx] for every sample. */
 int sdeo_timestep_embedding(const int64_t* t, const int32_t* step_idx, void* y, int32_t n, int32_t dim, int32_t ldy,
                             float max_period, void* stream);
-/* row-wise softmax(x * scale) over [rows, cols] bf16 (ld elements between rows), in place allowed (VAE AttnBlock) */
-int sdeo_softmax_rows(const void* x, void* y, int32_t rows, int32_t cols, int32_t ld, float scale, void* stream);
+/* row-wise softmax(x * scale): fp32 scores [rows, cols] (ldx) -> bf16 probabilities (ldy)  (VAE AttnBlock, model.py:192-193) */
+int sdeo_softmax_rows(const float* x, void* y, int32_t rows, int32_t cols, int32_t ldx, int32_t ldy, float scale,
+                      void* stream);
 /* y = silu(x) bf16 elementwise; y = bf16(x) from fp32; y = fp32(x) from bf16 */
 int sdeo_silu(const void* x, void* y, int64_t count, void* stream);
 int sdeo_f32_to_bf16(const float* x, void* y, int64_t count, void* stream);

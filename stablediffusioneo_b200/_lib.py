@@ -50,13 +50,13 @@ SIGNATURES = {
                                    c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                    c_void_p]),
     "sdeo_counter_add": (c_int, [c_void_p, c_int32, c_void_p]),
-    "sdeo_nchw_to_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "sdeo_nchw_to_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_float, c_void_p]),
     "sdeo_nhwc_bf16_to_nchw": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "sdeo_nhwc_f32_to_nchw": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "sdeo_upsample_nearest2x": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "sdeo_add_scaled": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_int64, c_void_p]),
     "sdeo_timestep_embedding": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_void_p]),
-    "sdeo_softmax_rows": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_void_p]),
+    "sdeo_softmax_rows": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_float, c_void_p]),
     "sdeo_silu": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "sdeo_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "sdeo_bf16_to_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),

@@ -1,0 +1,293 @@
+"""ControlledUnetModel / ControlNet / ControlLDM with the reference's names, constructor arguments, forward
+signatures and state-dict keys (cldm/cldm.py), running on libsdeo.so.
+
+The hot entry point is ControlLDM.apply_model(x_noisy, t, cond) (cldm/cldm.py:328-341). Internally it reorders the
+two independent halves — UNet encoder first, then ControlNet — so that every ControlNet zero-conv adds its scaled
+output straight onto the UNet skip it controls (`hs.pop() + control.pop()`, cldm/cldm.py:41, and `h += control.pop()`,
+:35) in the conv epilogue: no 13 scale kernels (:338), no 13 add kernels."""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..ldm.modules.attention import SpatialTransformer
+from ..ldm.modules.diffusionmodules.openaimodel import (Downsample, ResBlock, TimestepEmbedSequential, UNetModel,
+                                                        _check_supported)
+from ..ldm.modules.diffusionmodules.util import (BF16, CatPair, SiLU, conv_nd, is_internal, linear, make_beta_schedule,
+                                                 nchw_view, nhwc, timestep_embedding, to_external, to_internal,
+                                                 zero_module)
+from ..ldm.modules.diffusionmodules.model import Decoder
+
+
+def _ctx_internal(context):
+    return context.contiguous() if context.dtype == BF16 else ops.to_bf16(context.float())
+
+
+class ControlledUnetModel(UNetModel):
+    def run_encoder(self, x, emb, context):
+        hs = []
+        h = x
+        for module in self.input_blocks:
+            h = module.run(h, emb, context)
+            hs.append(h)
+        h = self.middle_block.run(h, emb, context)
+        return hs, h
+
+    def run_decoder(self, h, hs, emb, context):
+        hs = list(hs)
+        for module in self.output_blocks:
+            h = module.run(CatPair(h, hs.pop()), emb, context)
+        return self.run_out(h)
+
+    def run(self, x, emb, context, control=None, only_mid_control=False):
+        """cldm/cldm.py:23-45 on internal tensors; `control` (13 internal tensors, already scaled) is consumed."""
+        hs, h = self.run_encoder(x, emb, context)
+        if control is not None:
+            h = ops_add(h, control.pop())
+            if not only_mid_control:
+                hs = [ops_add(s, c) for s, c in zip(hs, control)]
+                del control[:]
+        return self.run_decoder(h, hs, emb, context)
+
+    def forward(self, x, timesteps=None, context=None, control=None, only_mid_control=False, **kwargs):
+        ctx = _ctx_internal(context)
+        emb = self.embed_time(timesteps)
+        ctl = None
+        if control is not None:
+            ctl = [to_internal(c) for c in control]
+            del control[:]  # the reference pops the caller's list empty (cldm/cldm.py:35-41)
+        return to_external(self.run(to_internal(x), emb, ctx, ctl, only_mid_control), self.out_channels)
+
+
+def ops_add(a, b):
+    return nchw_view(ops.add_scaled(nhwc(a), nhwc(b), 1.0))
+
+
+class ControlNet(nn.Module):
+    def __init__(self, image_size, in_channels, model_channels, hint_channels, num_res_blocks, attention_resolutions,
+                 dropout=0, channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, use_checkpoint=False, use_fp16=False,
+                 num_heads=-1, num_head_channels=-1, num_heads_upsample=-1, use_scale_shift_norm=False,
+                 resblock_updown=False, use_new_attention_order=False, use_spatial_transformer=False,
+                 transformer_depth=1, context_dim=None, n_embed=None, legacy=True, disable_self_attentions=None,
+                 num_attention_blocks=None, disable_middle_self_attn=False, use_linear_in_transformer=False):
+        super().__init__()
+        _check_supported(dims, None, use_scale_shift_norm, resblock_updown, use_spatial_transformer, context_dim,
+                         n_embed, num_heads, num_head_channels, disable_self_attentions, num_attention_blocks,
+                         use_linear_in_transformer, conv_resample)
+        if type(context_dim).__name__ == "ListConfig":
+            context_dim = list(context_dim)
+        self.dims = dims
+        self.image_size = image_size
+        self.in_channels = in_channels
+        self.model_channels = model_channels
+        self.num_res_blocks = len(channel_mult) * [num_res_blocks] if isinstance(num_res_blocks, int) else list(num_res_blocks)
+        self.attention_resolutions = attention_resolutions
+        self.dropout = dropout
+        self.channel_mult = channel_mult
+        self.conv_resample = conv_resample
+        self.use_checkpoint = use_checkpoint
+        self.dtype = torch.float32
+        self.num_heads = num_heads
+        self.num_head_channels = num_head_channels
+        self.num_heads_upsample = num_heads if num_heads_upsample == -1 else num_heads_upsample
+        self.predict_codebook_ids = False
+
+        time_embed_dim = model_channels * 4
+        self.time_embed = nn.Sequential(linear(model_channels, time_embed_dim), SiLU(),
+                                        linear(time_embed_dim, time_embed_dim))
+        self.input_blocks = nn.ModuleList([TimestepEmbedSequential(conv_nd(dims, in_channels, model_channels, 3, padding=1))])
+        self.zero_convs = nn.ModuleList([self.make_zero_conv(model_channels)])
+
+        # hint encoder (cldm/cldm.py:147-163): 3->16->16->32(s2)->32->96(s2)->96->256(s2)->model_channels, SiLU between
+        widths, strides = [16, 16, 32, 32, 96, 96, 256], [1, 1, 2, 1, 2, 1, 2]
+        layers, cin = [], hint_channels
+        for wd, s in zip(widths, strides):
+            layers += [conv_nd(dims, cin, wd, 3, padding=1, stride=s), SiLU()]
+            cin = wd
+        layers.append(zero_module(conv_nd(dims, cin, model_channels, 3, padding=1)))
+        self.input_hint_block = TimestepEmbedSequential(*layers)
+
+        def res(cin_, cout_):
+            return ResBlock(cin_, time_embed_dim, dropout, out_channels=cout_, dims=dims, use_checkpoint=use_checkpoint)
+
+        def st(c):
+            return SpatialTransformer(c, num_heads, c // num_heads, depth=transformer_depth, context_dim=context_dim,
+                                      disable_self_attn=False, use_linear=False, use_checkpoint=use_checkpoint)
+
+        self._feature_size = model_channels
+        ch, ds = model_channels, 1
+        for level, mult in enumerate(channel_mult):
+            for _ in range(self.num_res_blocks[level]):
+                blk = [res(ch, mult * model_channels)]
+                ch = mult * model_channels
+                if ds in attention_resolutions:
+                    blk.append(st(ch))
+                self.input_blocks.append(TimestepEmbedSequential(*blk))
+                self.zero_convs.append(self.make_zero_conv(ch))
+            if level != len(channel_mult) - 1:
+                self.input_blocks.append(TimestepEmbedSequential(Downsample(ch, conv_resample, dims=dims, out_channels=ch)))
+                self.zero_convs.append(self.make_zero_conv(ch))
+                ds *= 2
+        self.middle_block = TimestepEmbedSequential(res(ch, ch), st(ch), res(ch, ch))
+        self.middle_block_out = self.make_zero_conv(ch)
+
+    def make_zero_conv(self, channels):
+        return TimestepEmbedSequential(zero_module(conv_nd(self.dims, channels, channels, 1, padding=0)))
+
+    # ---- pieces --------------------------------------------------------------------------------------------
+    def embed_time(self, timesteps):
+        t_emb = timestep_embedding(timesteps, self.model_channels, repeat_only=False)
+        return self.time_embed[2].run(self.time_embed[0].run(t_emb, act=ops.SDEO_ACT_SILU))
+
+    def run_hint(self, hint):
+        """input_hint_block on an internal hint tensor; each SiLU is fused into the preceding conv's epilogue.
+        Depends only on the hint: callers hoist it out of the denoising loop (the reference recomputes it 40x/image)."""
+        h = hint
+        layers = list(self.input_hint_block)
+        i = 0
+        while i < len(layers):
+            conv = layers[i]
+            fused = i + 1 < len(layers) and isinstance(layers[i + 1], SiLU)
+            h = conv.run(h, act=ops.SDEO_ACT_SILU if fused else ops.SDEO_ACT_NONE)
+            i += 2 if fused else 1
+        return h
+
+    def run(self, x, guided_hint, emb, context, scales=None, add_to=None, only_mid=False):
+        """cldm/cldm.py:284-305. Returns 13 tensors: scale_i * zero_conv_i(h_i) [+ add_to[i] when given]
+        (only_mid: entries 0..11 are add_to[i] untouched)."""
+        scales = [1.0] * (len(self.zero_convs) + 1) if scales is None else list(scales)
+        outs = []
+        h = x
+        for i, (module, zero_conv) in enumerate(zip(self.input_blocks, self.zero_convs)):
+            if i == 0:
+                # h = conv_in(x) + guided_hint (cldm/cldm.py:294-297): residual add in the conv epilogue
+                h = module[0].run(h, residual=guided_hint)
+            else:
+                h = module.run(h, emb, context)
+            if only_mid and add_to is not None:
+                outs.append(add_to[i])
+            else:
+                outs.append(zero_conv[0].run(h, scale=scales[i], residual=add_to[i] if add_to is not None else None))
+        h = self.middle_block.run(h, emb, context)
+        outs.append(self.middle_block_out[0].run(h, scale=scales[-1], residual=add_to[-1] if add_to is not None else None))
+        return outs
+
+    def forward(self, x, hint, timesteps, context, **kwargs):
+        ctx = _ctx_internal(context)
+        emb = self.embed_time(timesteps)
+        guided = self.run_hint(to_internal(hint))
+        outs = self.run(to_internal(x), guided, emb, ctx)
+        return [to_external(o) for o in outs]
+
+
+class DiffusionWrapper(nn.Module):
+    """`model.diffusion_model` holder — keeps the checkpoint prefix `model.diffusion_model.*` (ddpm.py, absent)."""
+
+    def __init__(self, diffusion_model):
+        super().__init__()
+        self.diffusion_model = diffusion_model
+
+
+class FirstStage(nn.Module):
+    """AutoencoderKL's decode half: `first_stage_model.post_quant_conv.*`, `first_stage_model.decoder.*`."""
+
+    def __init__(self, ddconfig, embed_dim=4):
+        super().__init__()
+        self.decoder = Decoder(**ddconfig)
+        self.post_quant_conv = conv_nd(2, embed_dim, ddconfig["z_channels"], 1)
+
+    def decode(self, z):
+        return self.decoder(self.post_quant_conv(z))
+
+
+SD15_UNET_KW = dict(image_size=32, in_channels=4, model_channels=320, num_res_blocks=2, attention_resolutions=[4, 2, 1],
+                    channel_mult=[1, 2, 4, 4], num_heads=8, use_spatial_transformer=True, transformer_depth=1,
+                    context_dim=768, use_checkpoint=False, legacy=False)
+SD15_VAE_KW = dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128, ch_mult=[1, 2, 4, 4],
+                   num_res_blocks=2, attn_resolutions=[], dropout=0.0)
+
+
+class ControlLDM(nn.Module):
+    """The object canny2image_torch.py samples from. The reference derives it from ldm.models.diffusion.ddpm
+    .LatentDiffusion, which is absent from the reference tree; the attributes DDIMSampler and the
+    pipeline need are provided here: schedule buffers (linear, 1000 steps, 0.00085..0.012), `parameterization`,
+    `scale_factor`, `apply_model`, `decode_first_stage`, `control_scales`, `only_mid_control`."""
+
+    def __init__(self, unet_config=None, control_stage_config=None, first_stage_config=None, control_key="hint",
+                 only_mid_control=False, timesteps=1000, linear_start=0.00085, linear_end=0.012, scale_factor=0.18215,
+                 parameterization="eps"):
+        super().__init__()
+        unet_kw = dict(SD15_UNET_KW if unet_config is None else unet_config)
+        cn_kw = dict(control_stage_config) if control_stage_config is not None else dict(unet_kw, hint_channels=3)
+        self.model = DiffusionWrapper(ControlledUnetModel(out_channels=unet_kw.pop("out_channels", 4), **unet_kw))
+        cn_kw.pop("out_channels", None)
+        self.control_model = ControlNet(**cn_kw)
+        self.first_stage_model = FirstStage(dict(SD15_VAE_KW if first_stage_config is None else first_stage_config))
+        self.control_key = control_key
+        self.only_mid_control = only_mid_control
+        self.control_scales = [1.0] * 13
+        self.parameterization = parameterization
+        self.scale_factor = scale_factor
+        self.channels = unet_kw["in_channels"]
+        self.num_timesteps = int(timesteps)
+        betas = make_beta_schedule("linear", timesteps, linear_start=linear_start, linear_end=linear_end)
+        alphas_cumprod = np.cumprod(1.0 - betas, axis=0)
+        f32 = lambda a: torch.tensor(a, dtype=torch.float32)
+        self.register_buffer("betas", f32(betas), persistent=False)
+        self.register_buffer("alphas_cumprod", f32(alphas_cumprod), persistent=False)
+        self.register_buffer("alphas_cumprod_prev", f32(np.append(1.0, alphas_cumprod[:-1])), persistent=False)
+        self.register_buffer("sqrt_one_minus_alphas_cumprod", f32(np.sqrt(1.0 - alphas_cumprod)), persistent=False)
+        self._hint_cache = None
+
+    @property
+    def device(self):
+        return self.betas.device
+
+    # ---- hoisted, loop-invariant pieces ------------------------------------------------------------------
+    def guided_hint(self, hint):
+        """input_hint_block(hint), cached while the caller keeps passing the same (unmodified) hint tensor object."""
+        c = self._hint_cache
+        if c is None or c[0]() is not hint or c[1] != hint._version:
+            import weakref
+            self._hint_cache = (weakref.ref(hint), hint._version, self.control_model.run_hint(to_internal(hint)))
+        return self._hint_cache[2]
+
+    def eps_internal(self, x, timesteps, ctx, guided_hint):
+        """One ControlNet+UNet pass on internal tensors. x [N,8(4 used),h,w] bf16; returns eps fp32 NHWC-physical
+        [N, 4, h, w]-shaped view. guided_hint None = UNet only (cond['c_concat'] is None, cldm/cldm.py:334-335)."""
+        unet = self.model.diffusion_model
+        emb_u = unet.embed_time(timesteps)
+        hs, h = unet.run_encoder(x, emb_u, ctx)
+        if guided_hint is not None:
+            emb_c = self.control_model.embed_time(timesteps)
+            outs = self.control_model.run(x, guided_hint, emb_c, ctx, scales=self.control_scales, add_to=hs + [h],
+                                          only_mid=self.only_mid_control)
+            hs, h = outs[:-1], outs[-1]
+        return unet.run_decoder(h, hs, emb_u, ctx)
+
+    def apply_model(self, x_noisy, t, cond, *args, **kwargs):
+        """cldm/cldm.py:328-341: eps = UNet(x, t, ctx, control = scales * ControlNet(x, hint, t, ctx))."""
+        assert isinstance(cond, dict)
+        cond_txt = cond["c_crossattn"]
+        cond_txt = cond_txt[0] if len(cond_txt) == 1 else torch.cat(cond_txt, 1)
+        ctx = _ctx_internal(cond_txt)
+        guided = None
+        if cond["c_concat"] is not None:
+            hint = cond["c_concat"][0] if len(cond["c_concat"]) == 1 else torch.cat(cond["c_concat"], 1)
+            guided = self.guided_hint(hint)
+        eps = self.eps_internal(to_internal(x_noisy), t, ctx, guided)
+        return to_external(eps, self.model.diffusion_model.out_channels)
+
+    @torch.no_grad()
+    def decode_first_stage(self, z):
+        """z / scale_factor -> post_quant_conv -> Decoder (canny2image_torch.py:63-67). fp32 NCHW in [-1, 1]."""
+        fs = self.first_stage_model
+        zi = to_internal(z, scale=1.0 / self.scale_factor)
+        return to_external(fs.decoder.run(fs.post_quant_conv.run(zi)), fs.decoder.out_ch)
+
+    def decode_first_stage_u8(self, z):
+        """decode + 'b c h w -> b h w c' * 127.5 + 127.5, clip, uint8 (canny2image_torch.py:68) on the device."""
+        fs = self.first_stage_model
+        zi = to_internal(z, scale=1.0 / self.scale_factor)
+        img = fs.decoder.run(fs.post_quant_conv.run(zi))
+        return ops.image_to_u8(nhwc(img), fs.decoder.out_ch)

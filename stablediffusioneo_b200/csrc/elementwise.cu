@@ -52,14 +52,14 @@ __global__ void counter_add_kernel(int* ctr, int delta) { *ctr += delta; }
 // ---- layout conversion ---------------------------------------------------------------------------
 // NCHW fp32 -> NHWC bf16 (zero-padded to ldy channels). One thread per (pixel, channel-slot).
 __global__ void nchw_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int c,
-                                         int hw, int ldy) {
+                                         int hw, int ldy, float scale) {
   // tile transpose through shared memory: 32 channels x 32 pixels
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int ch = c0 + j, p = p0 + threadIdx.x;
-    tile[j][threadIdx.x] = (ch < c && p < hw) ? x[((long long)b * c + ch) * hw + p] : 0.f;
+    tile[j][threadIdx.x] = (ch < c && p < hw) ? x[((long long)b * c + ch) * hw + p] * scale : 0.f;
   }
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -161,15 +161,15 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ x, float* _
 
 // ---- row softmax (VAE AttnBlock): one CTA per row, fp32 math -----------------------------------
 __global__ void __launch_bounds__(256)
-softmax_rows_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int cols, int ld,
+softmax_rows_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int cols, int ld, int ldy,
                     float scale_log2) {
   __shared__ float red[8];
   __shared__ float bcast;
-  const __nv_bfloat16* xr = x + (size_t)blockIdx.x * ld;
-  __nv_bfloat16* yr = y + (size_t)blockIdx.x * ld;
+  const float* xr = x + (size_t)blockIdx.x * ld;
+  __nv_bfloat16* yr = y + (size_t)blockIdx.x * ldy;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float m = -INFINITY;
-  for (int i = threadIdx.x; i < cols; i += blockDim.x) m = fmaxf(m, __bfloat162float(xr[i]));
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) m = fmaxf(m, xr[i]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if (lane == 0) red[warp] = m;
@@ -182,7 +182,7 @@ softmax_rows_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restri
   __syncthreads();
   m = bcast;
   float s = 0.f;
-  for (int i = threadIdx.x; i < cols; i += blockDim.x) s += exp2f((__bfloat162float(xr[i]) - m) * scale_log2);
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) s += exp2f((xr[i] - m) * scale_log2);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   __syncthreads();
@@ -196,7 +196,7 @@ softmax_rows_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restri
   __syncthreads();
   const float inv = bcast;
   for (int i = threadIdx.x; i < cols; i += blockDim.x)
-    yr[i] = __float2bfloat16(exp2f((__bfloat162float(xr[i]) - m) * scale_log2) * inv);
+    yr[i] = __float2bfloat16(exp2f((xr[i] - m) * scale_log2) * inv);
 }
 
 __global__ void image_to_u8_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ y, long long npix, int c,
@@ -243,10 +243,11 @@ extern "C" int sdeo_counter_add(int32_t* ctr, int32_t delta, void* stream) {
   return check_launch("counter_add");
 }
 
-extern "C" int sdeo_nchw_to_nhwc_bf16(const float* x, void* y, int32_t n, int32_t c, int32_t hw, int32_t ldy, void* stream) {
+extern "C" int sdeo_nchw_to_nhwc_bf16(const float* x, void* y, int32_t n, int32_t c, int32_t hw, int32_t ldy, float scale,
+                                      void* stream) {
   if (!x || !y || n <= 0 || c <= 0 || hw <= 0 || ldy < c || n > 65535) return set_error(SDEO_EINVAL, "nchw_to_nhwc: bad args");
   dim3 grid((hw + 31) / 32, (ldy + 31) / 32, n), block(32, 8);
-  nchw_to_nhwc_bf16_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, n, c, hw, ldy);
+  nchw_to_nhwc_bf16_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, n, c, hw, ldy, scale);
   return check_launch("nchw_to_nhwc");
 }
 extern "C" int sdeo_nhwc_bf16_to_nchw(const void* x, float* y, int32_t n, int32_t c, int32_t hw, int32_t ldx, void* stream) {
@@ -304,9 +305,10 @@ extern "C" int sdeo_bf16_to_f32(const void* x, float* y, int64_t count, void* st
   return check_launch("bf16_to_f32");
 }
 
-extern "C" int sdeo_softmax_rows(const void* x, void* y, int32_t rows, int32_t cols, int32_t ld, float scale, void* stream) {
-  if (!x || !y || rows <= 0 || cols <= 0 || ld < cols) return set_error(SDEO_EINVAL, "softmax_rows: bad args");
-  softmax_rows_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, cols, ld,
+extern "C" int sdeo_softmax_rows(const float* x, void* y, int32_t rows, int32_t cols, int32_t ldx, int32_t ldy, float scale,
+                                 void* stream) {
+  if (!x || !y || rows <= 0 || cols <= 0 || ldx < cols || ldy < cols) return set_error(SDEO_EINVAL, "softmax_rows: bad args");
+  softmax_rows_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, cols, ldx, ldy,
                                                               scale * 1.4426950408889634f);
   return check_launch("softmax_rows");
 }

@@ -1,0 +1,298 @@
+"""Leaf layers and schedule helpers with the reference's names (ldm/modules/diffusionmodules/util.py), executing
+on the sm_100a kernels in libsdeo.so. Parameters keep PyTorch's names/shapes/dtypes so state dicts interchange
+with the reference modules; the packed bf16 filters the kernels stream are derived caches.
+
+Activation convention ("internal" tensors): bf16, logical shape [N, C, H, W], channels_last memory (physically
+NHWC). Any public module also accepts "external" fp32 NCHW tensors and then returns fp32 NCHW (see `boundary`)."""
+import functools
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ... import ops
+from ..._lib import SDEO_ACT_NONE, SDEO_ACT_SILU
+
+BF16 = torch.bfloat16
+
+
+# ------------------------------------------------------------------------------------------------------------
+# tensor format helpers
+# ------------------------------------------------------------------------------------------------------------
+class CatPair:
+    """A deferred torch.cat([a, b], dim=1) of two internal tensors (cldm/cldm.py:39,41): consumers fuse the concat
+    (dual-source GroupNorm, dual-source K loop in the conv)."""
+
+    def __init__(self, a, b):
+        assert a.shape[0] == b.shape[0] and a.shape[2:] == b.shape[2:]
+        self.a, self.b = a, b
+
+    @property
+    def shape(self):
+        return (self.a.shape[0], self.a.shape[1] + self.b.shape[1]) + tuple(self.a.shape[2:])
+
+
+def is_internal(x):
+    if isinstance(x, CatPair):
+        return True
+    return x.dtype == BF16 and x.dim() == 4 and x.permute(0, 2, 3, 1).is_contiguous()
+
+
+def nhwc(x):
+    """internal [N,C,H,W] channels_last -> zero-copy [N,H,W,C] contiguous view."""
+    return x.permute(0, 2, 3, 1)
+
+
+def nchw_view(y):
+    """[N,H,W,C] contiguous -> internal [N,C,H,W] channels_last view."""
+    return y.permute(0, 3, 1, 2)
+
+
+def to_internal(x, pad_to=8, scale=1.0):
+    """fp32 NCHW of any layout -> internal tensor = scale * x, channels zero-padded to a multiple of `pad_to`
+    (TMA needs a 16-byte pixel stride; convs ignore the padded tail)."""
+    if is_internal(x):
+        assert scale == 1.0
+        return x
+    if x.dtype != torch.float32:
+        x = x.float()
+    c = x.shape[1]
+    ld = (c + pad_to - 1) // pad_to * pad_to
+    y = ops.nchw_to_nhwc(x.contiguous(), ld, scale)
+    return nchw_view(y)
+
+
+def to_external(x, c=None):
+    """internal (bf16) or fp32 NHWC-physical tensor -> fp32 NCHW contiguous (first c channels)."""
+    return ops.nhwc_to_nchw(nhwc(x), c)
+
+
+def boundary(fn):
+    """forward(self, x, ...) wrapper: external fp32 NCHW in -> fp32 NCHW out; internal in -> internal out."""
+
+    @functools.wraps(fn)
+    def wrapped(self, x, *args, **kwargs):
+        if is_internal(x):
+            return fn(self, x, *args, **kwargs)
+        y = fn(self, to_internal(x), *args, **kwargs)
+        if isinstance(y, (list, tuple)):
+            return type(y)(to_external(t) for t in y)
+        return to_external(y)
+
+    return wrapped
+
+
+def tokens_boundary(fn):
+    """Same for token tensors [B, T, C]: fp32 in -> fp32 out, bf16 in -> bf16 out."""
+
+    @functools.wraps(fn)
+    def wrapped(self, x, *args, **kwargs):
+        if x.dtype == BF16:
+            return fn(self, x.contiguous(), *args, **kwargs)
+        y = fn(self, ops.to_bf16(x.float()), *args, **kwargs)
+        return ops.to_f32(y)
+
+    return wrapped
+
+
+def _param_key(*params):
+    return tuple((p.data_ptr(), p._version, p.device) for p in params if p is not None)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# layers
+# ------------------------------------------------------------------------------------------------------------
+class Conv2d(nn.Conv2d):
+    """nn.Conv2d (3x3 pad 1 / 1x1 pad 0, stride 1 or 2) on the tcgen05 implicit-GEMM kernel."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        k = self.kernel_size[0]
+        if self.kernel_size != (k, k) or k not in (1, 3) or self.stride[0] not in (1, 2) or self.stride[0] != self.stride[1] \
+                or self.padding != ((k // 2), (k // 2)) or self.groups != 1 or self.dilation != (1, 1):
+            raise NotImplementedError(f"Conv2d configuration not on the ControlNet-SD1.5 path: {self}")
+        self._cache = {}
+
+    def packed(self, split=None):
+        """PackedWeight for input channels split (c1, c2) (fused concat) or a single source. A ragged cin (4, 3)
+        reads an input whose pixel stride is padded to 8 channels; TMA zero-fills beyond cin."""
+        key = (_param_key(self.weight), split)
+        hit = self._cache.get("w")
+        if hit is None or hit[0] != key:
+            w = self.weight.detach()
+            if split is None:
+                pw = ops.pack_conv_weight(w)
+            else:
+                pw = ops.pack_conv_weight(w, c1=split[0], c2=split[1])
+            self._cache["w"] = (key, pw)
+            hit = self._cache["w"]
+        return hit[1]
+
+    def bias_f32(self):
+        return self.bias.detach() if self.bias is not None else None
+
+    def run(self, x, emb=None, residual=None, scale=1.0, act=SDEO_ACT_NONE, out_fp32=False):
+        """x: internal tensor or CatPair. Returns an internal tensor (fp32 NHWC-physical when out_fp32). A bf16
+        output whose channel count is not a multiple of 8 is zero-padded to one (so a following conv can TMA it)."""
+        res = nhwc(residual) if residual is not None else None
+        out = None
+        cout = self.out_channels
+        if not out_fp32 and cout % 8 != 0:
+            assert residual is None
+            n, _, h, w = x.shape
+            k, s = self.kernel_size[0], self.stride[0]
+            ho, wo = (h + 2 * (k // 2) - k) // s + 1, (w + 2 * (k // 2) - k) // s + 1
+            out = torch.empty((n, ho, wo, (cout + 7) // 8 * 8), dtype=BF16, device=self.weight.device)
+            ops.memset(out, 0)
+        if isinstance(x, CatPair):
+            pw = self.packed((x.a.shape[1], x.b.shape[1]))
+            y = ops.conv2d(nhwc(x.a), pw, x2=nhwc(x.b), bias=self.bias_f32(), emb=emb, residual=res, scale=scale,
+                           act=act, stride=self.stride[0], out_fp32=out_fp32, out=out)
+        else:
+            pw = self.packed()
+            y = ops.conv2d(nhwc(x), pw, bias=self.bias_f32(), emb=emb, residual=res, scale=scale, act=act,
+                           stride=self.stride[0], out_fp32=out_fp32, out=out)
+        return nchw_view(y)
+
+    def forward(self, x):
+        if is_internal(x):
+            return self.run(x)
+        return to_external(self.run(to_internal(x)), self.out_channels)
+
+
+class Linear(nn.Linear):
+    """nn.Linear on the same GEMM kernel (1x1 case). Token tensors [..., K] bf16."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self._cache = {}
+
+    def packed(self):
+        key = _param_key(self.weight)
+        hit = self._cache.get("w")
+        if hit is None or hit[0] != key:
+            self._cache["w"] = (key, ops.pack_conv_weight(self.weight.detach()))
+            hit = self._cache["w"]
+        return hit[1]
+
+    def run(self, x, residual=None, act=SDEO_ACT_NONE, out_fp32=False):
+        b = self.bias.detach() if self.bias is not None else None
+        return ops.linear(x, self.packed(), bias=b, residual=residual, act=act, out_fp32=out_fp32)
+
+    def forward(self, x):
+        if x.dtype == BF16:
+            return self.run(x.contiguous())
+        return ops.to_f32(self.run(ops.to_bf16(x.float())))
+
+
+class GroupNorm32(nn.GroupNorm):
+    """GroupNorm with fp32 statistics (util.py:217-219); `run(..., silu=True)` fuses the following nn.SiLU
+    (the groupNormPlugin bSwish contract, groupNormPlugin.cpp:291-304). Accepts a CatPair (concat seam may fall
+    inside a group)."""
+
+    def run(self, x, silu=False):
+        if isinstance(x, CatPair):
+            y = ops.groupnorm(nhwc(x.a), self.weight.detach(), self.bias.detach(), self.eps, silu, x2=nhwc(x.b),
+                              groups=self.num_groups)
+        else:
+            y = ops.groupnorm(nhwc(x), self.weight.detach(), self.bias.detach(), self.eps, silu, groups=self.num_groups)
+        return nchw_view(y)
+
+    @boundary
+    def forward(self, x):
+        return self.run(x, silu=False)
+
+
+class LayerNorm(nn.LayerNorm):
+    def run(self, x):
+        return ops.layernorm(x, self.weight.detach(), self.bias.detach(), self.eps)
+
+    def forward(self, x):
+        if x.dtype == BF16:
+            return self.run(x.contiguous())
+        return ops.to_f32(self.run(ops.to_bf16(x.float())))
+
+
+class SiLU(nn.Module):
+    """x * sigmoid(x). Inside ResBlock / hint block it is fused into the neighbouring kernel; standalone it is one pass."""
+
+    def forward(self, x):
+        if x.dtype == BF16:
+            return ops.silu(x.contiguous())
+        return ops.to_f32(ops.silu(ops.to_bf16(x.float())))
+
+
+def conv_nd(dims, *args, **kwargs):
+    if dims != 2:
+        raise NotImplementedError("only dims=2 is on the ControlNet-SD1.5 path")
+    return Conv2d(*args, **kwargs)
+
+
+def linear(*args, **kwargs):
+    return Linear(*args, **kwargs)
+
+
+def normalization(channels):
+    return GroupNorm32(32, channels)
+
+
+def zero_module(module):
+    for p in module.parameters():
+        p.detach().zero_()
+    return module
+
+
+def timestep_embedding(timesteps, dim, max_period=10000, repeat_only=False):
+    """[cos | sin] sinusoidal embedding (util.py:154-174) -> bf16 [N, dim] on the device."""
+    if repeat_only:
+        raise NotImplementedError("repeat_only timestep embedding is not on the ControlNet-SD1.5 path")
+    t = timesteps.to(torch.int64).contiguous()
+    return ops.timestep_embedding(t, t.shape[0], dim, max_period=float(max_period))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# schedules (host side, numpy; util.py:21-74)
+# ------------------------------------------------------------------------------------------------------------
+def make_beta_schedule(schedule, n_timestep, linear_start=1e-4, linear_end=2e-2, cosine_s=8e-3):
+    if schedule != "linear":
+        raise NotImplementedError(f"schedule '{schedule}' is not on the ControlNet-SD1.5 path")
+    betas = torch.linspace(linear_start ** 0.5, linear_end ** 0.5, n_timestep, dtype=torch.float64) ** 2
+    return betas.numpy()
+
+
+def make_ddim_timesteps(ddim_discr_method, num_ddim_timesteps, num_ddpm_timesteps, verbose=True):
+    if ddim_discr_method == "uniform":
+        c = num_ddpm_timesteps // num_ddim_timesteps
+        ddim_timesteps = np.asarray(list(range(0, num_ddpm_timesteps, c)))
+    elif ddim_discr_method == "quad":
+        ddim_timesteps = ((np.linspace(0, np.sqrt(num_ddpm_timesteps * .8), num_ddim_timesteps)) ** 2).astype(int)
+    else:
+        raise NotImplementedError(f'There is no ddim discretization method called "{ddim_discr_method}"')
+    steps_out = ddim_timesteps + 1
+    if verbose:
+        print(f"Selected timesteps for ddim sampler: {steps_out}")
+    return steps_out
+
+
+def make_ddim_sampling_parameters(alphacums, ddim_timesteps, eta, verbose=True):
+    alphas = alphacums[ddim_timesteps]
+    alphas_prev = np.asarray([alphacums[0]] + alphacums[ddim_timesteps[:-1]].tolist())
+    sigmas = eta * np.sqrt((1 - alphas_prev) / (1 - alphas) * (1 - alphas / alphas_prev))
+    if verbose:
+        print(f"Selected alphas for ddim sampler: a_t: {alphas}; a_(t-1): {alphas_prev}")
+        print(f"For the chosen value of eta, which is {eta}, this results in the following sigma_t schedule for ddim "
+              f"sampler {sigmas}")
+    return sigmas, alphas, alphas_prev
+
+
+def noise_like(shape, device, repeat=False):
+    if repeat:
+        return torch.randn((1, *shape[1:]), device=device).repeat(shape[0], *((1,) * (len(shape) - 1)))
+    return torch.randn(shape, device=device)
+
+
+def extract_into_tensor(a, t, x_shape):
+    b, *_ = t.shape
+    out = a.gather(-1, t)
+    return out.reshape(b, *((1,) * (len(x_shape) - 1)))

@@ -128,12 +128,14 @@ def conv2d(x, pw, x2=None, bias=None, emb=None, residual=None, scale=1.0, act=SD
     _req(bias, torch.float32, "bias")
     _req(emb, torch.float32, "emb")
     _req(residual, BF16, "residual")
-    n, h, w, c1 = x.shape
-    assert c1 == pw.c1, f"conv2d: input has {c1} channels, filter packed for {pw.c1}"
-    c2 = 0
+    n, h, w, ld1 = x.shape
+    c1 = pw.c1
+    # the pixel stride may exceed the channels the filter consumes (zero-padded / ignored tail channels)
+    assert ld1 >= c1 and (ld1 == c1 or ld1 - c1 < 8), f"conv2d: input has {ld1} channels, filter packed for {c1}"
+    c2, ld2 = 0, 0
     if x2 is not None:
-        assert x2.shape[:3] == x.shape[:3] and x2.shape[3] == pw.c2
-        c2 = pw.c2
+        assert x2.shape[:3] == x.shape[:3] and x2.shape[3] == pw.c2 and ld1 == c1
+        c2 = ld2 = pw.c2
     else:
         assert pw.c2 == 0
     k = pw.ksize
@@ -143,7 +145,7 @@ def conv2d(x, pw, x2=None, bias=None, emb=None, residual=None, scale=1.0, act=SD
     a = ConvArgs()
     a.x1, a.x2 = _ptr(x), _ptr(x2)
     a.n, a.h, a.w = n, h, w
-    a.c1, a.ld1, a.c2, a.ld2 = c1, c1, c2, c2
+    a.c1, a.ld1, a.c2, a.ld2 = c1, ld1, c2, ld2
     a.w_packed = _ptr(pw.data)
     a.cout, a.ksize, a.stride, a.pad = pw.cout, k, stride, pad
     a.epi_mode, a.act = epi_mode, act
@@ -160,12 +162,12 @@ def conv2d(x, pw, x2=None, bias=None, emb=None, residual=None, scale=1.0, act=SD
         if out is None:
             out = torch.empty((n, ho, wo, cols), dtype=torch.float32 if out_fp32 else BF16, device=x.device)
         else:
-            assert out.shape == (n, ho, wo, cols) and out.is_contiguous()
+            assert out.shape[:3] == (n, ho, wo) and out.shape[3] >= cols and out.is_contiguous()
             assert out.dtype == (torch.float32 if out_fp32 else BF16)
-        a.y, a.ldy = _ptr(out), cols
+        a.y, a.ldy = _ptr(out), out.shape[3]
         if residual is not None:
-            assert residual.shape == out.shape
-            a.residual, a.ldr = _ptr(residual), cols
+            assert residual.shape[:3] == (n, ho, wo) and residual.shape[3] >= cols and residual.is_contiguous()
+            a.residual, a.ldr = _ptr(residual), residual.shape[3]
     ws = _workspaces.conv(x.device)
     a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
     check(lib.sdeo_conv2d(ctypes.byref(a), _stream()), "conv2d")
@@ -231,17 +233,18 @@ def attention(q, k, vt, batch, heads, nq, nkv, d, ldv, scale, out=None):
 
 
 def softmax_rows(x, scale, out=None):
+    """fp32 scores [rows, cols] -> bf16 softmax(x * scale) rows."""
     lib = _lib.load()
-    _req(x, BF16, "x")
+    _req(x, torch.float32, "x")
     rows, cols = x.shape
     if out is None:
-        out = torch.empty_like(x)
-    check(lib.sdeo_softmax_rows(_ptr(x), _ptr(out), rows, cols, cols, float(scale), _stream()), "softmax_rows")
+        out = torch.empty((rows, cols), dtype=BF16, device=x.device)
+    check(lib.sdeo_softmax_rows(_ptr(x), _ptr(out), rows, cols, cols, cols, float(scale), _stream()), "softmax_rows")
     return out
 
 
-def nchw_to_nhwc(x, ldy=None):
-    """fp32 [N,C,H,W] -> bf16 [N,H,W,ldy] (channels zero-padded to ldy, default round_up(C, 8))."""
+def nchw_to_nhwc(x, ldy=None, scale=1.0):
+    """fp32 [N,C,H,W] -> bf16 [N,H,W,ldy] = scale * x (channels zero-padded to ldy, default round_up(C, 8))."""
     lib = _lib.load()
     x = x.contiguous()
     _req(x, torch.float32, "x")
@@ -249,7 +252,7 @@ def nchw_to_nhwc(x, ldy=None):
     if ldy is None:
         ldy = (c + 7) // 8 * 8
     out = torch.empty((n, h, w, ldy), dtype=BF16, device=x.device)
-    check(lib.sdeo_nchw_to_nhwc_bf16(_ptr(x), _ptr(out), n, c, h * w, ldy, _stream()), "nchw_to_nhwc")
+    check(lib.sdeo_nchw_to_nhwc_bf16(_ptr(x), _ptr(out), n, c, h * w, ldy, float(scale), _stream()), "nchw_to_nhwc")
     return out
 
 
@@ -338,6 +341,13 @@ def cfg_ddim_step(eps_c, eps_u, x, coef_table, step_idx=None, noise=None, x_prev
                                  _ptr(x_prev), _ptr(pred_x0), _ptr(x_next), dup, ldn, _ptr(coef_table),
                                  _ptr(step_idx), n, c, h * w, _stream()), "cfg_ddim_step")
     return x_prev, pred_x0
+
+
+def memset(t, value=0):
+    lib = _lib.load()
+    assert t.is_contiguous()
+    check(lib.sdeo_memset_async(_ptr(t), int(value), t.numel() * t.element_size(), _stream()), "memset")
+    return t
 
 
 def counter_add(ctr, delta=1):
