@@ -1,0 +1,338 @@
+"""DDIMSampler with the reference's interface (cldm/ddim_hacked.py): make_schedule, sample, ddim_sampling,
+p_sample_ddim -> (samples, intermediates).
+
+Two execution paths, same arithmetic:
+  * generic: p_sample_ddim calls model.apply_model for cond and uncond (any duck-typed model) and runs the CFG
+    combine + DDIM update as ONE fused kernel (the reference: ~12 elementwise launches + 4 host-syncing torch.full);
+  * engine (model is our ControlLDM, eta == 0, standard options): cond and uncond run as one batch of 2B through
+    ControlNet+UNet (one weight pass), hint features and cross-attention K/V are hoisted out of the loop, the whole
+    step — timestep embedding to x_{t-1} — is one CUDA graph replayed per step, with the step's timestep and DDIM
+    coefficients read from device tables through a device-side step counter (no host patching between replays).
+"""
+import math
+
+import numpy as np
+import torch
+from tqdm import tqdm
+
+from .. import ops
+from ..ldm.modules.diffusionmodules.util import (BF16, make_ddim_sampling_parameters, make_ddim_timesteps, noise_like,
+                                                 extract_into_tensor, nhwc, to_internal)
+
+
+class DDIMSampler(object):
+    def __init__(self, model, schedule="linear", **kwargs):
+        super().__init__()
+        self.model = model
+        self.ddpm_num_timesteps = model.num_timesteps
+        self.schedule = schedule
+        self.use_engine = True     # set False to force the generic two-call path
+        self.use_cuda_graph = True
+        self._engine = None
+
+    def register_buffer(self, name, attr):
+        # the reference hard-codes cuda (ddim_hacked.py:17-21); follow the model's device instead
+        if type(attr) == torch.Tensor and attr.device != self.model.device:
+            attr = attr.to(self.model.device)
+        setattr(self, name, attr)
+
+    def make_schedule(self, ddim_num_steps, ddim_discretize="uniform", ddim_eta=0., verbose=True):
+        self.ddim_timesteps = make_ddim_timesteps(ddim_discr_method=ddim_discretize, num_ddim_timesteps=ddim_num_steps,
+                                                  num_ddpm_timesteps=self.ddpm_num_timesteps, verbose=verbose)
+        alphas_cumprod = self.model.alphas_cumprod
+        assert alphas_cumprod.shape[0] == self.ddpm_num_timesteps, 'alphas have to be defined for each timestep'
+        to_torch = lambda x: x.clone().detach().to(torch.float32).to(self.model.device)
+        self.register_buffer('betas', to_torch(self.model.betas))
+        self.register_buffer('alphas_cumprod', to_torch(alphas_cumprod))
+        self.register_buffer('alphas_cumprod_prev', to_torch(self.model.alphas_cumprod_prev))
+        ac = alphas_cumprod.detach().cpu()
+        self.register_buffer('sqrt_alphas_cumprod', to_torch(np.sqrt(ac)))
+        self.register_buffer('sqrt_one_minus_alphas_cumprod', to_torch(np.sqrt(1. - ac)))
+        self.register_buffer('log_one_minus_alphas_cumprod', to_torch(np.log(1. - ac)))
+        self.register_buffer('sqrt_recip_alphas_cumprod', to_torch(np.sqrt(1. / ac)))
+        self.register_buffer('sqrt_recipm1_alphas_cumprod', to_torch(np.sqrt(1. / ac - 1)))
+        ddim_sigmas, ddim_alphas, ddim_alphas_prev = make_ddim_sampling_parameters(
+            alphacums=ac, ddim_timesteps=self.ddim_timesteps, eta=ddim_eta, verbose=verbose)
+        self.register_buffer('ddim_sigmas', ddim_sigmas)
+        self.register_buffer('ddim_alphas', ddim_alphas)
+        self.register_buffer('ddim_alphas_prev', ddim_alphas_prev)
+        self.register_buffer('ddim_sqrt_one_minus_alphas', np.sqrt(1. - ddim_alphas))
+        acp = self.model.alphas_cumprod_prev.detach().cpu()
+        sigmas_for_original_sampling_steps = ddim_eta * torch.sqrt((1 - acp) / (1 - ac) * (1 - ac / acp))
+        self.register_buffer('ddim_sigmas_for_original_num_steps', sigmas_for_original_sampling_steps)
+
+    # --------------------------------------------------------------------------------------------------------
+    def _coef_row(self, index, scale):
+        """The six scalars of one step (ddim_hacked.py:208-230) as the fused kernel's coefficient row."""
+        a_t = float(self.ddim_alphas[index])
+        a_prev = float(self.ddim_alphas_prev[index])
+        sigma_t = float(self.ddim_sigmas[index])
+        sqrt_1m_at = float(self.ddim_sqrt_one_minus_alphas[index])
+        return [float(scale), sqrt_1m_at, 1.0 / math.sqrt(a_t), math.sqrt(a_prev),
+                math.sqrt(max(1.0 - a_prev - sigma_t ** 2, 0.0)), sigma_t, 0.0, 0.0]
+
+    @torch.no_grad()
+    def sample(self, S, batch_size, shape, conditioning=None, callback=None, normals_sequence=None, img_callback=None,
+               quantize_x0=False, eta=0., mask=None, x0=None, temperature=1., noise_dropout=0., score_corrector=None,
+               corrector_kwargs=None, verbose=True, x_T=None, log_every_t=100, unconditional_guidance_scale=1.,
+               unconditional_conditioning=None, dynamic_threshold=None, ucg_schedule=None, **kwargs):
+        if conditioning is not None and isinstance(conditioning, dict):
+            ctmp = conditioning[list(conditioning.keys())[0]]
+            while isinstance(ctmp, list):
+                ctmp = ctmp[0]
+            if ctmp.shape[0] != batch_size:
+                print(f"Warning: Got {ctmp.shape[0]} conditionings but batch-size is {batch_size}")
+        self.make_schedule(ddim_num_steps=S, ddim_eta=eta, verbose=verbose)
+        C, H, W = shape
+        size = (batch_size, C, H, W)
+        if verbose:
+            print(f'Data shape for DDIM sampling is {size}, eta {eta}')
+        return self.ddim_sampling(conditioning, size, callback=callback, img_callback=img_callback,
+                                  quantize_denoised=quantize_x0, mask=mask, x0=x0, ddim_use_original_steps=False,
+                                  noise_dropout=noise_dropout, temperature=temperature, score_corrector=score_corrector,
+                                  corrector_kwargs=corrector_kwargs, x_T=x_T, log_every_t=log_every_t,
+                                  unconditional_guidance_scale=unconditional_guidance_scale,
+                                  unconditional_conditioning=unconditional_conditioning,
+                                  dynamic_threshold=dynamic_threshold, ucg_schedule=ucg_schedule, verbose=verbose)
+
+    def _engine_ok(self, cond, uncond, scale, mask, callback, img_callback, quantize_denoised, score_corrector,
+                   dynamic_threshold, ucg_schedule, ddim_use_original_steps, timesteps, noise_dropout, temperature):
+        from .cldm import ControlLDM
+        if not (self.use_engine and isinstance(self.model, ControlLDM)):
+            return False
+        if any(v is not None for v in (mask, callback, img_callback, score_corrector, dynamic_threshold, ucg_schedule,
+                                       timesteps)) or quantize_denoised or ddim_use_original_steps:
+            return False
+        if float(np.max(np.abs(np.asarray(self.ddim_sigmas)))) != 0.0:
+            return False  # eta > 0 draws fresh noise every step: generic path
+        if not isinstance(cond, dict) or self.model.parameterization != "eps":
+            return False
+        if uncond is not None and scale != 1.0:
+            if not isinstance(uncond, dict):
+                return False
+            if (cond["c_concat"] is None) != (uncond["c_concat"] is None):
+                return False  # guess mode: the uncond pass skips the ControlNet -> two different graphs
+        return True
+
+    @torch.no_grad()
+    def ddim_sampling(self, cond, shape, x_T=None, ddim_use_original_steps=False, callback=None, timesteps=None,
+                      quantize_denoised=False, mask=None, x0=None, img_callback=None, log_every_t=100, temperature=1.,
+                      noise_dropout=0., score_corrector=None, corrector_kwargs=None, unconditional_guidance_scale=1.,
+                      unconditional_conditioning=None, dynamic_threshold=None, ucg_schedule=None, verbose=True):
+        device = self.model.betas.device
+        b = shape[0]
+        img = torch.randn(shape, device=device) if x_T is None else x_T.to(device=device, dtype=torch.float32)
+        if self._engine_ok(cond, unconditional_conditioning, unconditional_guidance_scale, mask, callback, img_callback,
+                           quantize_denoised, score_corrector, dynamic_threshold, ucg_schedule,
+                           ddim_use_original_steps, timesteps, noise_dropout, temperature):
+            return self._engine_sampling(cond, unconditional_conditioning, unconditional_guidance_scale, img,
+                                         log_every_t)
+
+        if timesteps is None:
+            timesteps = self.ddpm_num_timesteps if ddim_use_original_steps else self.ddim_timesteps
+        elif timesteps is not None and not ddim_use_original_steps:
+            subset_end = int(min(timesteps / self.ddim_timesteps.shape[0], 1) * self.ddim_timesteps.shape[0]) - 1
+            timesteps = self.ddim_timesteps[:subset_end]
+        if ddim_use_original_steps:
+            raise NotImplementedError("ddim_use_original_steps is not on the ControlNet-SD1.5 path")
+        intermediates = {'x_inter': [img], 'pred_x0': [img]}
+        time_range = np.flip(timesteps)
+        total_steps = timesteps.shape[0]
+        iterator = tqdm(time_range, desc='DDIM Sampler', total=total_steps, disable=not verbose)
+        for i, step in enumerate(iterator):
+            index = total_steps - i - 1
+            ts = torch.full((b,), int(step), device=device, dtype=torch.long)
+            if mask is not None:
+                raise NotImplementedError("mask/x0 blending is not on the ControlNet-SD1.5 path")
+            if ucg_schedule is not None:
+                assert len(ucg_schedule) == len(time_range)
+                unconditional_guidance_scale = ucg_schedule[i]
+            img, pred_x0 = self.p_sample_ddim(img, cond, ts, index=index, use_original_steps=False,
+                                              quantize_denoised=quantize_denoised, temperature=temperature,
+                                              noise_dropout=noise_dropout, score_corrector=score_corrector,
+                                              corrector_kwargs=corrector_kwargs,
+                                              unconditional_guidance_scale=unconditional_guidance_scale,
+                                              unconditional_conditioning=unconditional_conditioning,
+                                              dynamic_threshold=dynamic_threshold)
+            if callback:
+                callback(i)
+            if img_callback:
+                img_callback(pred_x0, i)
+            if index % log_every_t == 0 or index == total_steps - 1:
+                intermediates['x_inter'].append(img)
+                intermediates['pred_x0'].append(pred_x0)
+        return img, intermediates
+
+    @torch.no_grad()
+    def p_sample_ddim(self, x, c, t, index, repeat_noise=False, use_original_steps=False, quantize_denoised=False,
+                      temperature=1., noise_dropout=0., score_corrector=None, corrector_kwargs=None,
+                      unconditional_guidance_scale=1., unconditional_conditioning=None, dynamic_threshold=None):
+        """ddim_hacked.py:181-231. eps from model.apply_model (cond, then uncond); CFG + x0 + x_{t-1} in one kernel."""
+        if use_original_steps or quantize_denoised or score_corrector is not None or dynamic_threshold is not None \
+                or noise_dropout > 0. or self.model.parameterization != "eps":
+            raise NotImplementedError("option not on the ControlNet-SD1.5 path")
+        guided = not (unconditional_conditioning is None or unconditional_guidance_scale == 1.)
+        e_c = self.model.apply_model(x, t, c).contiguous()
+        e_u = self.model.apply_model(x, t, unconditional_conditioning).contiguous() if guided else None
+        row = self._coef_row(index, unconditional_guidance_scale if guided else 1.0)
+        coef = torch.tensor([row], dtype=torch.float32, device=x.device)
+        noise = None
+        if row[5] != 0.0:
+            noise = (noise_like(x.shape, x.device, repeat_noise) * temperature).contiguous()
+        pred_x0 = torch.empty_like(x)
+        x_prev, _ = ops.cfg_ddim_step(e_c, e_u, x.contiguous(), coef, noise=noise, pred_x0=pred_x0)
+        return x_prev, pred_x0
+
+    # --------------------------------------------------------------------------------------------------------
+    def _engine_sampling(self, cond, uncond, scale, x_T, log_every_t):
+        guided = not (uncond is None or scale == 1.)
+        S = int(self.ddim_timesteps.shape[0])
+        eng = self._engine
+        key = _EngineKey(self.model, x_T, cond, uncond if guided else None, S, self.use_cuda_graph)
+        if eng is None or eng.key != key:
+            eng = self._engine = _Engine(self.model, key, self.use_cuda_graph)
+        time_range = np.flip(self.ddim_timesteps)
+        rows = [self._coef_row(S - i - 1, scale if guided else 1.0) for i in range(S)]
+        img, pred_x0, first = eng.run(x_T, cond, uncond if guided else None, [int(t) for t in time_range], rows)
+        # the reference logs x_inter / pred_x0 when index % log_every_t == 0 or index == S-1 (ddim_hacked.py:174-176):
+        # with S <= log_every_t that is the first step (index S-1) and the last (index 0)
+        inter = {'x_inter': [x_T, first[0], img], 'pred_x0': [x_T, first[1], pred_x0]}
+        if S == 1:
+            inter = {'x_inter': [x_T, img], 'pred_x0': [x_T, pred_x0]}
+        return img, inter
+
+
+class _EngineKey:
+    def __init__(self, model, x_T, cond, uncond, S, graph):
+        hint = cond["c_concat"]
+        self.t = (id(model), tuple(x_T.shape), tuple(cond["c_crossattn"][0].shape),
+                  None if hint is None else tuple(hint[0].shape), uncond is not None, S, graph,
+                  tuple(model.control_scales), model.only_mid_control)
+
+    def __eq__(self, other):
+        return isinstance(other, _EngineKey) and self.t == other.t
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+
+class _Engine:
+    """Static buffers + one captured CUDA graph for a (model, shapes, S) combination."""
+
+    def __init__(self, model, key, use_graph):
+        self.model, self.key, self.use_graph = model, key, use_graph
+        self.graph = None
+        self.ready = False
+
+    def _alloc(self, x_T, cond, uncond, S):
+        dev = x_T.device
+        b, c, h, w = x_T.shape
+        self.dup = 2 if uncond is not None else 1
+        nb = self.dup * b
+        self.x_lat = torch.empty((b, c, h, w), dtype=torch.float32, device=dev)
+        self.pred_x0 = torch.empty_like(self.x_lat)
+        self.first_x = torch.empty_like(self.x_lat)
+        self.first_p = torch.empty_like(self.x_lat)
+        self.x_in = torch.empty((nb, h, w, 8), dtype=BF16, device=dev)
+        self.ts_table = torch.zeros((S,), dtype=torch.int64, device=dev)
+        self.coef = torch.zeros((S, 8), dtype=torch.float32, device=dev)
+        self.step = torch.zeros((1,), dtype=torch.int32, device=dev)
+        ctx_shape = cond["c_crossattn"][0].shape
+        self.ctx = torch.empty((nb, ctx_shape[1], ctx_shape[2]), dtype=BF16, device=dev)
+        self.has_hint = cond["c_concat"] is not None
+        if self.has_hint:
+            hs = cond["c_concat"][0].shape
+            self.hint = torch.empty((nb, hs[1], hs[2], hs[3]), dtype=torch.float32, device=dev)
+
+    def _load_inputs(self, x_T, cond, uncond, ts, rows):
+        b = x_T.shape[0]
+        self.x_lat.copy_(x_T)
+        ops.memset(self.step, 0)
+        self.ts_table.copy_(torch.tensor(ts, dtype=torch.int64), non_blocking=True)
+        self.coef.copy_(torch.tensor(rows, dtype=torch.float32), non_blocking=True)
+        conds = [cond] + ([uncond] if uncond is not None else [])
+        for i, cd in enumerate(conds):
+            ctx = cd["c_crossattn"][0] if len(cd["c_crossattn"]) == 1 else torch.cat(cd["c_crossattn"], 1)
+            ctx = ctx.to(self.ctx.device)
+            self.ctx[i * b:(i + 1) * b].copy_(ctx if ctx.dtype == BF16 else ops.to_bf16(ctx.float().contiguous()))
+            if self.has_hint:
+                hint = cd["c_concat"][0] if len(cd["c_concat"]) == 1 else torch.cat(cd["c_concat"], 1)
+                self.hint[i * b:(i + 1) * b].copy_(hint)
+        # network input for step 0: bf16 NHWC copy of x_T, channels padded to 8, duplicated for cond/uncond
+        x0 = ops.nchw_to_nhwc(self.x_lat, 8)
+        for i in range(self.dup):
+            self.x_in[i * b:(i + 1) * b].copy_(x0)
+
+    def _prologue(self):
+        """Loop-invariant work: hint encoder and cross-attention K/V of every transformer block. Results live in
+        buffers allocated once, because the captured graph holds their addresses."""
+        m = self.model
+        if self.has_hint:
+            g = m.control_model.run_hint(to_internal(self.hint))
+            if getattr(self, "guided", None) is None:
+                self.guided = g
+            else:
+                self.guided.copy_(g)
+        else:
+            self.guided = None
+        from ..ldm.modules.attention import CrossAttention
+        mods = list(m.model.diffusion_model.modules()) + (list(m.control_model.modules()) if self.has_hint else [])
+        for mod in mods:
+            if isinstance(mod, CrossAttention) and not mod.is_self:
+                st = mod.kv_static
+                if st is not None and st[0] is self.ctx:
+                    mod.project_kv(self.ctx, k=st[1], vt=st[2])
+                else:
+                    k, vt, nkv, ldv = mod.project_kv(self.ctx)
+                    mod.kv_static = (self.ctx, k, vt, nkv, ldv)
+
+    def _step(self):
+        m = self.model
+        unet = m.model.diffusion_model
+        nb = self.x_in.shape[0]
+        b = self.x_lat.shape[0]
+        x = self.x_in.permute(0, 3, 1, 2)
+        t_emb = ops.timestep_embedding(self.ts_table, nb, unet.model_channels, step_idx=self.step)
+        emb_u = unet.time_embed[2].run(unet.time_embed[0].run(t_emb, act=ops.SDEO_ACT_SILU))
+        hs, h = unet.run_encoder(x, emb_u, self.ctx)
+        if self.has_hint:
+            cn = m.control_model
+            emb_c = cn.time_embed[2].run(cn.time_embed[0].run(t_emb, act=ops.SDEO_ACT_SILU))
+            outs = cn.run(x, self.guided, emb_c, self.ctx, scales=m.control_scales, add_to=hs + [h],
+                          only_mid=m.only_mid_control)
+            hs, h = outs[:-1], outs[-1]
+        eps = nhwc(unet.run_decoder(h, hs, emb_u, self.ctx))          # fp32 [nb, h, w, 4]
+        eps_c = eps[:b]
+        eps_u = eps[b:] if self.dup == 2 else None
+        ops.cfg_ddim_step(eps_c, eps_u, self.x_lat, self.coef, step_idx=self.step, x_prev=self.x_lat,
+                          pred_x0=self.pred_x0, x_next=self.x_in, dup=self.dup, eps_nhwc=True)
+        ops.counter_add(self.step, 1)
+
+    def run(self, x_T, cond, uncond, ts, rows):
+        S = len(ts)
+        if not self.ready:
+            self._alloc(x_T, cond, uncond, S)
+        self._load_inputs(x_T, cond, uncond, ts, rows)
+        self._prologue()
+        if self.use_graph and self.graph is None:
+            # warm-up once eagerly (packs weights, sizes workspaces), then capture the step
+            self._step()
+            torch.cuda.synchronize()
+            self._load_inputs(x_T, cond, uncond, ts, rows)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step()
+            self.graph = g
+            self._load_inputs(x_T, cond, uncond, ts, rows)
+        self.ready = True
+        first = None
+        for i in range(S):
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._step()
+            if i == 0:
+                self.first_x.copy_(self.x_lat)
+                self.first_p.copy_(self.pred_x0)
+                first = (self.first_x, self.first_p)
+        return self.x_lat.clone(), self.pred_x0.clone(), first

@@ -110,13 +110,14 @@ class CrossAttention(nn.Module):
             hit = self._cache[which]
         return hit[1]
 
-    def project_kv(self, context):
+    def project_kv(self, context, k=None, vt=None):
         """k [B*heads, nkv, d], vt [B*heads, d, ldv] for a context [B, nkv, ctx_dim] (one GEMM on kv_w)."""
         b, nkv, _ = context.shape
         h, d = self.heads, self.dim_head
         ldv = (nkv + 7) // 8 * 8
-        k = torch.empty((b * h, nkv, d), dtype=BF16, device=context.device)
-        vt = torch.empty((b * h, d, ldv), dtype=BF16, device=context.device)
+        if k is None:
+            k = torch.empty((b * h, nkv, d), dtype=BF16, device=context.device)
+            vt = torch.empty((b * h, d, ldv), dtype=BF16, device=context.device)
         ops.qkv_project(context, self._packed("kv"), h, d, 1, k=k, vt=vt, ldv=ldv)
         return k, vt, nkv, ldv
 

@@ -4,7 +4,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from ... import ops
+from .... import ops
 from .util import BF16, Conv2d, GroupNorm32, is_internal, nchw_view, nhwc, to_external, to_internal
 
 

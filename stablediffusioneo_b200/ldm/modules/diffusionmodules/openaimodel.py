@@ -12,7 +12,7 @@ from abc import abstractmethod
 import torch
 import torch.nn as nn
 
-from ... import ops
+from .... import ops
 from ..attention import SpatialTransformer
 from .util import (BF16, CatPair, Conv2d, SiLU, conv_nd, is_internal, linear, nchw_view, nhwc, normalization,
                    timestep_embedding, to_external, to_internal, zero_module)

@@ -11,8 +11,8 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from ... import ops
-from ..._lib import SDEO_ACT_NONE, SDEO_ACT_SILU
+from .... import ops
+from ...._lib import SDEO_ACT_NONE, SDEO_ACT_SILU
 
 BF16 = torch.bfloat16
 
@@ -257,7 +257,7 @@ def timestep_embedding(timesteps, dim, max_period=10000, repeat_only=False):
 def make_beta_schedule(schedule, n_timestep, linear_start=1e-4, linear_end=2e-2, cosine_s=8e-3):
     if schedule != "linear":
         raise NotImplementedError(f"schedule '{schedule}' is not on the ControlNet-SD1.5 path")
-    betas = torch.linspace(linear_start ** 0.5, linear_end ** 0.5, n_timestep, dtype=torch.float64) ** 2
+    betas = torch.linspace(linear_start ** 0.5, linear_end ** 0.5, n_timestep, dtype=torch.float64, device="cpu") ** 2
     return betas.numpy()
 
 

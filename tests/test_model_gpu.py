@@ -1,0 +1,168 @@
+"""End-to-end GPU parity of the CUDA path against golden vectors produced by the REAL reference modules
+(tests/golden/make_golden.py) and against the CPU oracle, on identical weights / seeds / inputs.
+
+Gates (north_star): per-step eps relative L2 <= 1e-2 in bf16, teacher-forced (the reference's x_t
+fed at each step) and free-running final latents; decoded image vs the reference's image."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import O, build_control_ldm, canny_hint, inputs_on, load_golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+EPS_TOL = 1e-2
+
+
+@pytest.fixture(scope="module")
+def tiny(cuda_device):
+    return build_control_ldm(O.TINY, O.TINY_VAE, cuda_device), load_golden("tiny")
+
+
+@pytest.fixture(scope="module")
+def sd15(cuda_device):
+    return build_control_ldm(O.SD15, O.SD15_VAE, cuda_device), load_golden("sd15_256x384")
+
+
+def _ts(dev, t=951):
+    return torch.full((1,), t, dtype=torch.long, device=dev)
+
+
+def test_tiny_state_dict_matches_reference_names(tiny):
+    """Our modules expose exactly the reference's parameter names/shapes (strict load in build_control_ldm) and the
+    fused qkv_w / kv_w attributes with the reference's layout (attention.py:170,173)."""
+    model, _ = tiny
+    att = model.model.diffusion_model.input_blocks[1][1].transformer_blocks[0]
+    c = att.attn1.to_q.weight.shape[0]
+    assert att.attn1.qkv_w.shape == (c, 3 * c)
+    assert torch.equal(att.attn1.qkv_w[:, :c], att.attn1.to_q.weight.t())
+    assert att.attn2.kv_w.shape == (O.TINY.context_dim, 2 * c)
+
+
+def test_tiny_apply_model(tiny, cuda_device):
+    model, g = tiny
+    x_T, cond, uncond = inputs_on(O.TINY, 8, 16, cuda_device)
+    eps_c = model.apply_model(x_T, _ts(cuda_device), cond)
+    eps_u = model.apply_model(x_T, _ts(cuda_device), uncond)
+    assert rel_l2(eps_c, g["eps_c_t951"]) < EPS_TOL
+    assert rel_l2(eps_u, g["eps_u_t951"]) < EPS_TOL
+    nocontrol = dict(cond, c_concat=None)
+    assert rel_l2(model.apply_model(x_T, _ts(cuda_device), nocontrol), g["eps_nocontrol_t951"]) < EPS_TOL
+
+
+def test_tiny_module_surface(tiny, cuda_device):
+    """The public forward()s (fp32 NCHW in/out) of ControlNet and ControlledUnetModel, used the reference's way:
+    13 control tensors -> scaled -> consumed by the UNet (cldm/cldm.py:337-339)."""
+    model, g = tiny
+    x_T, cond, _ = inputs_on(O.TINY, 8, 16, cuda_device)
+    ctx = cond["c_crossattn"][0]
+    control = model.control_model(x=x_T, hint=cond["c_concat"][0], timesteps=_ts(cuda_device), context=ctx)
+    assert len(control) == 13
+    stats = torch.tensor([[c.float().mean().item(), c.float().norm().item()] for c in control])
+    assert torch.allclose(stats[:, 1], g["control_stats"][:, 1], rtol=2e-2)
+    assert rel_l2(control[-1], g["control_last"]) < EPS_TOL
+    assert rel_l2(control[0], g["control_first"]) < EPS_TOL
+    control = [c * s for c, s in zip(control, model.control_scales)]
+    eps = model.model.diffusion_model(x=x_T, timesteps=_ts(cuda_device), context=ctx, control=control,
+                                      only_mid_control=False)
+    assert control == []  # consumed, like the reference's .pop()
+    assert rel_l2(eps, g["eps_c_t951"]) < EPS_TOL
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_tiny_sampler(tiny, cuda_device, graph):
+    from stablediffusioneo_b200.cldm.ddim_hacked import DDIMSampler
+    model, g = tiny
+    x_T, cond, uncond = inputs_on(O.TINY, 8, 16, cuda_device)
+    sampler = DDIMSampler(model)
+    sampler.use_cuda_graph = graph
+    for _ in range(2):  # second call reuses the captured graph with reloaded inputs
+        samples, inter = sampler.sample(g["S"], 1, (4, 8, 16), cond, verbose=False, eta=0.0, x_T=x_T,
+                                        unconditional_guidance_scale=9.0, unconditional_conditioning=uncond)
+        assert rel_l2(samples, g["samples"]) < 3e-2
+    assert np.array_equal(np.asarray(sampler.ddim_timesteps), g["ddim_timesteps"].numpy())
+    assert np.allclose(np.asarray(sampler.ddim_alphas, dtype=np.float64), g["ddim_alphas"].numpy(), rtol=1e-6)
+    assert np.allclose(np.asarray(sampler.ddim_alphas_prev, dtype=np.float64), g["ddim_alphas_prev"].numpy(), rtol=1e-6)
+    assert len(inter["x_inter"]) == 3
+
+
+def test_tiny_sampler_generic_path(tiny, cuda_device):
+    """p_sample_ddim through two apply_model calls (any duck-typed model) + the fused CFG/DDIM kernel."""
+    from stablediffusioneo_b200.cldm.ddim_hacked import DDIMSampler
+    model, g = tiny
+    x_T, cond, uncond = inputs_on(O.TINY, 8, 16, cuda_device)
+    sampler = DDIMSampler(model)
+    sampler.use_engine = False
+    samples, _ = sampler.sample(g["S"], 1, (4, 8, 16), cond, verbose=False, eta=0.0, x_T=x_T,
+                                unconditional_guidance_scale=9.0, unconditional_conditioning=uncond)
+    assert rel_l2(samples, g["samples"]) < 3e-2
+
+
+def test_tiny_decode(tiny, cuda_device):
+    model, g = tiny
+    img = model.decode_first_stage(g["decode_in"].to(cuda_device))
+    assert rel_l2(img, g["decoded"]) < 2e-2
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# full SD1.5 size, BASELINE configs[1]: 256x384, batch 1, DDIM 20, CFG 9.0
+# ---------------------------------------------------------------------------------------------------------------
+def test_sd15_eps_single_step(sd15, cuda_device):
+    model, g = sd15
+    x_T, cond, uncond = inputs_on(O.SD15, 32, 48, cuda_device, hint=canny_hint())
+    e_c = model.apply_model(x_T, _ts(cuda_device), cond)
+    e_u = model.apply_model(x_T, _ts(cuda_device), uncond)
+    errs = (rel_l2(e_c, g["eps_c_t951"]), rel_l2(e_u, g["eps_u_t951"]))
+    print("eps rel L2 (cond, uncond):", errs)
+    assert max(errs) < EPS_TOL
+
+
+def test_sd15_eps_teacher_forced(sd15, cuda_device):
+    """Feed the reference's own x_t at several steps of its 20-step trajectory; compare eps per step."""
+    model, g = sd15
+    _, cond, uncond = inputs_on(O.SD15, 32, 48, cuda_device, hint=canny_hint())
+    # reconstruct the reference trajectory's x_t from its eps calls: cond/uncond alternate (ddim_hacked.py:190-191)
+    sch = O.ddim_schedule(20)
+    x = O.make_inputs(O.SD15, 1, 32, 48)[0]
+    eps_calls, ts = g["eps_calls"], g["call_timesteps"]
+    worst = 0.0
+    for i in range(20):
+        index = 19 - i
+        e_c_ref, e_u_ref = eps_calls[2 * i], eps_calls[2 * i + 1]
+        if i in (0, 5, 10, 15, 19):
+            t = _ts(cuda_device, int(ts[2 * i]))
+            e_c = model.apply_model(x.to(cuda_device), t, cond)
+            worst = max(worst, rel_l2(e_c, e_c_ref))
+        e_t = e_u_ref + 9.0 * (e_c_ref - e_u_ref)
+        x, _ = O.ddim_update(x, e_t, float(sch["alphas"][index]), float(sch["alphas_prev"][index]), 0.0,
+                             float(sch["sqrt_one_minus_alphas"][index]))
+    assert rel_l2(x, g["samples"]) < 1e-5  # the oracle's DDIM update reproduces the reference trajectory
+    print("teacher-forced worst eps rel L2:", worst)
+    assert worst < EPS_TOL
+
+
+def test_sd15_sample_and_decode(sd15, cuda_device):
+    """DDIMSampler.sample (engine path: batched cond+uncond, CUDA graph) -> final latents -> VAE decode -> uint8."""
+    from stablediffusioneo_b200.cldm.ddim_hacked import DDIMSampler
+    model, g = sd15
+    x_T, cond, uncond = inputs_on(O.SD15, 32, 48, cuda_device, hint=canny_hint())
+    sampler = DDIMSampler(model)
+    samples, _ = sampler.sample(20, 1, (4, 32, 48), cond, verbose=False, eta=0.0, x_T=x_T,
+                                unconditional_guidance_scale=9.0, unconditional_conditioning=uncond)
+    err = rel_l2(samples, g["samples"])
+    print("free-running 20-step latent rel L2:", err)
+    assert err < 5e-2
+    # decode the REFERENCE's latents (isolates the VAE) and our own (whole pipeline)
+    img_ref_lat = model.decode_first_stage(g["samples"].to(cuda_device))
+    e_dec = rel_l2(img_ref_lat, g["decoded"])
+    print("VAE decode rel L2:", e_dec)
+    assert e_dec < 2e-2
+    u8 = model.decode_first_stage_u8(samples).cpu().numpy()
+    ref_u8 = O.to_uint8_image(g["decoded"])
+    assert u8.shape == ref_u8.shape == (1, 256, 384, 3)
+    diff = np.abs(u8.astype(np.int32) - ref_u8.astype(np.int32))
+    mse = float((diff.astype(np.float64) ** 2).mean())
+    psnr = 10 * np.log10(255.0 ** 2 / max(mse, 1e-12))
+    print(f"final image vs reference: mean abs diff {diff.mean():.3f} / 255, PSNR {psnr:.1f} dB")
+    # PD (Inception features, compute_score.py:11-17) needs pytorch_fid weights that are not in the image; PSNR stands in.
+    assert psnr > 25.0
