@@ -66,12 +66,15 @@ typedef struct sdeo_conv_args {
   int32_t act;          /* SDEO_ACT_*                                                                  */
   const float* bias;    /* fp32 [cout] (packed order for GEGLU) or NULL                                */
   const float* emb;     /* fp32 [n, cout] per-sample additive term (ResBlock emb_layers) or NULL        */
-  const void* residual; /* bf16 [n, ho, wo, ldr] added after scaling, or NULL                          */
+  const void* residual; /* [n, ho, wo, ldr] added after scaling, or NULL; bf16, or fp32 if residual_f32 */
   int32_t ldr;
+  int32_t residual_f32;
   float scale;          /* multiplies act(acc+bias+emb) (ControlNet control_scales); 1.0f otherwise    */
   void* y;              /* bf16 (or fp32 if y_fp32) [n, ho, wo, ldy]                                   */
   int32_t ldy;
   int32_t y_fp32;
+  void* y2;             /* optional bf16 twin of an fp32 y (residual-stream tensors kept in fp32 are also   */
+  int32_t ldy2;         /* written in bf16 for consumers that read them through TMA); NULL otherwise        */
   /* SDEO_EPI_QKV only: packed column n -> which = n / (heads*dhead) + qkv_first (0=q,1=k,2=v) */
   void* q; void* k; void* vt;
   int32_t heads, dhead, tokens, ldv, qkv_first;
@@ -106,13 +109,14 @@ int sdeo_pack_geglu_bias(const float* b, int32_t n2, int32_t geglu_bn, float* b_
  * x2 != NULL normalises torch.cat([x1, x2], dim=1) and writes the concatenated result.
  * ---------------------------------------------------------------------------------------------- */
 size_t sdeo_groupnorm_workspace_bytes(int32_t n, int32_t hw, int32_t groups);
-int sdeo_groupnorm_nhwc(const void* x1, const void* x2, const float* gamma, const float* beta, void* y,
+/* x1/x2: bf16, or fp32 when x_f32 != 0 (fp32 residual-stream tensors); y is always bf16. */
+int sdeo_groupnorm_nhwc(const void* x1, const void* x2, int32_t x_f32, const float* gamma, const float* beta, void* y,
                         int32_t n, int32_t hw, int32_t c1, int32_t c2, int32_t groups, float eps,
                         int32_t with_silu, void* workspace, size_t workspace_bytes, void* stream);
 
 /* LayerNorm over the last dim of [rows, c] bf16 (nn.LayerNorm, attention.py:372-374), eps 1e-5. */
-int sdeo_layernorm(const void* x, const float* gamma, const float* beta, void* y, int32_t rows, int32_t c,
-                   float eps, void* stream);
+int sdeo_layernorm(const void* x, int32_t x_f32, const float* gamma, const float* beta, void* y, int32_t rows,
+                   int32_t c, float eps, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Flash-style attention on tcgen05: o = softmax(q k^T * scale) v   (attention.py:227-249; model.py:186-199)

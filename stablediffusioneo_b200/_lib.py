@@ -19,9 +19,9 @@ class ConvArgs(Structure):
         ("w_packed", c_void_p),
         ("cout", c_int32), ("ksize", c_int32), ("stride", c_int32), ("pad", c_int32),
         ("epi_mode", c_int32), ("act", c_int32),
-        ("bias", c_void_p), ("emb", c_void_p), ("residual", c_void_p), ("ldr", c_int32),
+        ("bias", c_void_p), ("emb", c_void_p), ("residual", c_void_p), ("ldr", c_int32), ("residual_f32", c_int32),
         ("scale", c_float),
-        ("y", c_void_p), ("ldy", c_int32), ("y_fp32", c_int32),
+        ("y", c_void_p), ("ldy", c_int32), ("y_fp32", c_int32), ("y2", c_void_p), ("ldy2", c_int32),
         ("q", c_void_p), ("k", c_void_p), ("vt", c_void_p),
         ("heads", c_int32), ("dhead", c_int32), ("tokens", c_int32), ("ldv", c_int32), ("qkv_first", c_int32),
         ("workspace", c_void_p), ("workspace_bytes", c_size_t),
@@ -41,9 +41,9 @@ SIGNATURES = {
     "sdeo_pack_conv_weight": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "sdeo_pack_geglu_bias": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "sdeo_groupnorm_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
-    "sdeo_groupnorm_nhwc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+    "sdeo_groupnorm_nhwc": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                     c_int32, c_int32, c_float, c_int32, c_void_p, c_size_t, c_void_p]),
-    "sdeo_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p]),
+    "sdeo_layernorm": (c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p]),
     "sdeo_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                c_int32, c_float, c_void_p]),
     "sdeo_cfg_ddim_step": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,

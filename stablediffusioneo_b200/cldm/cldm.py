@@ -13,8 +13,9 @@ from .. import ops
 from ..ldm.modules.attention import SpatialTransformer
 from ..ldm.modules.diffusionmodules.openaimodel import (Downsample, ResBlock, TimestepEmbedSequential, UNetModel,
                                                         _check_supported)
+from ..ldm.modules.diffusionmodules import util
 from ..ldm.modules.diffusionmodules.util import (BF16, CatPair, SiLU, conv_nd, is_internal, linear, make_beta_schedule,
-                                                 nchw_view, nhwc, timestep_embedding, to_external, to_internal,
+                                                 nchw_view, nhwc, operand, timestep_embedding, to_external, to_internal,
                                                  zero_module)
 from ..ldm.modules.diffusionmodules.model import Decoder
 
@@ -60,7 +61,8 @@ class ControlledUnetModel(UNetModel):
 
 
 def ops_add(a, b):
-    return nchw_view(ops.add_scaled(nhwc(a), nhwc(b), 1.0))
+    """a + b on internal tensors of either kind (the generic, unfused injection path): bf16 result."""
+    return nchw_view(ops.add_scaled(nhwc(operand(a)), nhwc(operand(b)), 1.0))
 
 
 class ControlNet(nn.Module):
@@ -161,15 +163,17 @@ class ControlNet(nn.Module):
         for i, (module, zero_conv) in enumerate(zip(self.input_blocks, self.zero_convs)):
             if i == 0:
                 # h = conv_in(x) + guided_hint (cldm/cldm.py:294-297): residual add in the conv epilogue
-                h = module[0].run(h, residual=guided_hint)
+                h = module[0].run(h, residual=guided_hint, stream=util.STREAM_FP32)
             else:
                 h = module.run(h, emb, context)
             if only_mid and add_to is not None:
                 outs.append(add_to[i])
             else:
-                outs.append(zero_conv[0].run(h, scale=scales[i], residual=add_to[i] if add_to is not None else None))
+                outs.append(zero_conv[0].run(h, scale=scales[i], residual=add_to[i] if add_to is not None else None,
+                                             stream=util.STREAM_FP32))
         h = self.middle_block.run(h, emb, context)
-        outs.append(self.middle_block_out[0].run(h, scale=scales[-1], residual=add_to[-1] if add_to is not None else None))
+        outs.append(self.middle_block_out[0].run(h, scale=scales[-1], residual=add_to[-1] if add_to is not None else None,
+                                                 stream=util.STREAM_FP32))
         return outs
 
     def forward(self, x, hint, timesteps, context, **kwargs):

@@ -60,14 +60,18 @@ class DDIMSampler(object):
         acp = self.model.alphas_cumprod_prev.detach().cpu()
         sigmas_for_original_sampling_steps = ddim_eta * torch.sqrt((1 - acp) / (1 - ac) * (1 - ac / acp))
         self.register_buffer('ddim_sigmas_for_original_num_steps', sigmas_for_original_sampling_steps)
+        # host copies of the per-step scalars (the reference reads them from device tensors with a sync per step)
+        self._h = dict(alphas=np.asarray(ddim_alphas, dtype=np.float64), alphas_prev=np.asarray(ddim_alphas_prev, dtype=np.float64),
+                       sigmas=np.asarray(ddim_sigmas, dtype=np.float64),
+                       sqrt_one_minus_alphas=np.asarray(np.sqrt(1. - ddim_alphas), dtype=np.float64))
 
     # --------------------------------------------------------------------------------------------------------
     def _coef_row(self, index, scale):
         """The six scalars of one step (ddim_hacked.py:208-230) as the fused kernel's coefficient row."""
-        a_t = float(self.ddim_alphas[index])
-        a_prev = float(self.ddim_alphas_prev[index])
-        sigma_t = float(self.ddim_sigmas[index])
-        sqrt_1m_at = float(self.ddim_sqrt_one_minus_alphas[index])
+        a_t = float(self._h["alphas"][index])
+        a_prev = float(self._h["alphas_prev"][index])
+        sigma_t = float(self._h["sigmas"][index])
+        sqrt_1m_at = float(self._h["sqrt_one_minus_alphas"][index])
         return [float(scale), sqrt_1m_at, 1.0 / math.sqrt(a_t), math.sqrt(a_prev),
                 math.sqrt(max(1.0 - a_prev - sigma_t ** 2, 0.0)), sigma_t, 0.0, 0.0]
 
@@ -103,7 +107,7 @@ class DDIMSampler(object):
         if any(v is not None for v in (mask, callback, img_callback, score_corrector, dynamic_threshold, ucg_schedule,
                                        timesteps)) or quantize_denoised or ddim_use_original_steps:
             return False
-        if float(np.max(np.abs(np.asarray(self.ddim_sigmas)))) != 0.0:
+        if float(np.max(np.abs(self._h["sigmas"]))) != 0.0:
             return False  # eta > 0 draws fresh noise every step: generic path
         if not isinstance(cond, dict) or self.model.parameterization != "eps":
             return False

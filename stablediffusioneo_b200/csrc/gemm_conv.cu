@@ -38,10 +38,12 @@ struct ConvKParams {
   const float* bias;
   const float* emb;
   const __nv_bfloat16* residual;
-  int ldr;
+  int ldr, residual_f32;
   float scale;
   void* y;
   int ldy;
+  __nv_bfloat16* y2;
+  int ldy2;
   // qkv
   __nv_bfloat16* q;
   __nv_bfloat16* k;
@@ -74,7 +76,17 @@ __device__ __forceinline__ void epi_normal_store8(const ConvKParams& p, const Ro
     if (p.act == SDEO_ACT_SILU) t = silu_f(t);
     x[j] = t * p.scale;
   }
-  if (p.residual) {
+  if (p.residual && p.residual_f32) {
+    const float* rp = reinterpret_cast<const float*>(p.residual) + ri.pix * p.ldr + n;
+    if (full && ((p.ldr & 3) == 0)) {
+      const float4 a = *reinterpret_cast<const float4*>(rp), b = *reinterpret_cast<const float4*>(rp + 4);
+      x[0] += a.x; x[1] += a.y; x[2] += a.z; x[3] += a.w; x[4] += b.x; x[5] += b.y; x[6] += b.z; x[7] += b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (n + j < p.cout) x[j] += rp[j];
+    }
+  } else if (p.residual) {
     const __nv_bfloat16* rp = p.residual + ri.pix * p.ldr + n;
     if (full && ((p.ldr & 7) == 0)) {
       uint4 rv = *reinterpret_cast<const uint4*>(rp);
@@ -95,6 +107,19 @@ __device__ __forceinline__ void epi_normal_store8(const ConvKParams& p, const Ro
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         if (n + j < p.cout) yp[j] = x[j];
+    }
+    if (p.y2) {  // bf16 twin of an fp32 residual-stream tensor, for consumers that read it through TMA
+      __nv_bfloat16* y2p = p.y2 + ri.pix * p.ldy2 + n;
+      if (full && ((p.ldy2 & 7) == 0)) {
+        uint4 o;
+        o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]);
+        o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
+        *reinterpret_cast<uint4*>(y2p) = o;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (n + j < p.cout) y2p[j] = __float2bfloat16(x[j]);
+      }
     }
   } else {
     __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + ri.pix * p.ldy + n;
@@ -627,6 +652,9 @@ extern "C" int sdeo_conv2d(const sdeo_conv_args* a, void* stream) {
   p.epi_mode = a->epi_mode; p.act = a->act; p.y_fp32 = a->y_fp32;
   p.bias = a->bias; p.emb = a->emb; p.residual = (const __nv_bfloat16*)a->residual; p.ldr = a->ldr;
   p.scale = a->scale; p.y = a->y; p.ldy = a->ldy;
+  p.residual_f32 = a->residual_f32;
+  p.y2 = (a->y_fp32 && a->epi_mode == SDEO_EPI_NORMAL) ? (__nv_bfloat16*)a->y2 : nullptr;
+  p.ldy2 = a->ldy2;
   p.q = (__nv_bfloat16*)a->q; p.k = (__nv_bfloat16*)a->k; p.vt = (__nv_bfloat16*)a->vt;
   p.heads = a->heads; p.dhead = a->dhead; p.tokens = a->tokens; p.ldv = a->ldv; p.qkv_first = a->qkv_first;
   p.counters = (unsigned int*)a->workspace;

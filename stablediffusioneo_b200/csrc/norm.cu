@@ -8,22 +8,30 @@ namespace sdeo {
 
 constexpr int kGNThreads = 256;
 
-// Loads the 8-channel vector `v` (of the virtual concat [x1 | x2]) at pixel `pix`.
-__device__ __forceinline__ uint4 gn_load8(const __nv_bfloat16* x1, const __nv_bfloat16* x2, int c1, int c2,
-                                          long long pix, int v) {
-  const int c = v * 8;
-  if (c < c1) return *reinterpret_cast<const uint4*>(x1 + pix * c1 + c);
-  return *reinterpret_cast<const uint4*>(x2 + pix * c2 + (c - c1));
-}
-
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
   float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
 
+// 8 consecutive channels as fp32 from a bf16 or an fp32 (residual-stream) tensor.
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float* f) { unpack8(*reinterpret_cast<const uint4*>(p), f); }
+__device__ __forceinline__ void load8(const float* p, float* f) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// Loads the 8-channel vector `v` (of the virtual concat [x1 | x2]) at pixel `pix`.
+template <typename T>
+__device__ __forceinline__ void gn_load8(const T* x1, const T* x2, int c1, int c2, long long pix, int v, float* f) {
+  const int c = v * 8;
+  if (c < c1) load8(x1 + pix * c1 + c, f);
+  else load8(x2 + pix * c2 + (c - c1), f);
+}
+
 // Pass 1: per (sample, pixel-chunk) partial sums per group -> ws[n][chunk][group][2]
+template <typename T>
 __global__ void __launch_bounds__(kGNThreads)
-gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, const __nv_bfloat16* __restrict__ x2, float* __restrict__ ws,
+gn_stats_kernel(const T* __restrict__ x1, const T* __restrict__ x2, float* __restrict__ ws,
                 int hw, int c1, int c2, int groups, int chunks, int ppc) {
   extern __shared__ float sm[];
   const int C = c1 + c2;
@@ -49,7 +57,7 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, const __nv_bfloat16* __res
     if (active && v < cv) {
       for (int pp = p_begin + tr; pp < p_end; pp += R) {
         float f[8];
-        unpack8(gn_load8(x1, x2, c1, c2, (long long)n * hw + pp, v), f);
+        gn_load8(x1, x2, c1, c2, (long long)n * hw + pp, v, f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] += f[j] * f[j]; }
       }
@@ -85,8 +93,9 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, const __nv_bfloat16* __res
 }
 
 // Pass 2: finalize mean / rstd per group from the partials, normalise, affine, optional SiLU, store bf16.
+template <typename T>
 __global__ void __launch_bounds__(kGNThreads)
-gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, const __nv_bfloat16* __restrict__ x2,
+gn_apply_kernel(const T* __restrict__ x1, const T* __restrict__ x2,
                 const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ ws,
                 __nv_bfloat16* __restrict__ y, int hw, int c1, int c2, int groups, int chunks, int ppc, float eps,
                 int with_silu) {
@@ -132,7 +141,7 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, const __nv_bfloat16* __res
     for (int pp = p_begin + tr; pp < p_end; pp += R) {
       const long long pix = (long long)n * hw + pp;
       float f[8];
-      unpack8(gn_load8(x1, x2, c1, c2, pix, v), f);
+      gn_load8(x1, x2, c1, c2, pix, v, f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float t = f[j] * a[j] + b[j];
@@ -157,21 +166,22 @@ static void gn_geometry(int n, int hw, int* chunks, int* ppc) {
 
 // One warp per row, the row lives in registers (C <= 2048): exact two-pass mean/variance.
 constexpr int kLNMaxVec = 8;
+template <typename T>
 __global__ void __launch_bounds__(256)
-layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+layernorm_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  __nv_bfloat16* __restrict__ y, int rows, int C, float eps) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const int cv = C / 8;
-  const __nv_bfloat16* xr = x + (size_t)warp * C;
+  const T* xr = x + (size_t)warp * C;
   float f[kLNMaxVec][8];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < kLNMaxVec; ++i) {
     const int v = lane + i * 32;
     if (v < cv) {
-      unpack8(*reinterpret_cast<const uint4*>(xr + v * 8), f[i]);
+      load8(xr + v * 8, f[i]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += f[i][j];
     }
@@ -223,8 +233,8 @@ extern "C" size_t sdeo_groupnorm_workspace_bytes(int32_t n, int32_t hw, int32_t 
   return (size_t)n * chunks * groups * 2 * sizeof(float);
 }
 
-extern "C" int sdeo_groupnorm_nhwc(const void* x1, const void* x2, const float* gamma, const float* beta, void* y,
-                                   int32_t n, int32_t hw, int32_t c1, int32_t c2, int32_t groups, float eps,
+extern "C" int sdeo_groupnorm_nhwc(const void* x1, const void* x2, int32_t x_f32, const float* gamma, const float* beta,
+                                   void* y, int32_t n, int32_t hw, int32_t c1, int32_t c2, int32_t groups, float eps,
                                    int32_t with_silu, void* workspace, size_t workspace_bytes, void* stream) {
   if (!x1 || !gamma || !beta || !y || !workspace) return set_error(SDEO_EINVAL, "groupnorm: null argument");
   if (!x2) c2 = 0;
@@ -240,30 +250,46 @@ extern "C" int sdeo_groupnorm_nhwc(const void* x1, const void* x2, const float* 
   if (smem > 48 * 1024) {
     static bool attr_set = false;
     if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaError_t e = cudaFuncSetAttribute(gn_stats_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gn_stats_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
       if (e != cudaSuccess) return set_error(SDEO_ECUDA, cudaGetErrorString(e));
       attr_set = true;
     }
     if (smem > 100 * 1024) return set_error(SDEO_EINVAL, "groupnorm: too many channels");
   }
   dim3 grid((unsigned)chunks, (unsigned)n);
-  gn_stats_kernel<<<grid, kGNThreads, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)x1, (const __nv_bfloat16*)x2,
-                                                                    (float*)workspace, hw, c1, c2, groups, chunks, ppc);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x_f32)
+    gn_stats_kernel<float><<<grid, kGNThreads, smem, st>>>((const float*)x1, (const float*)x2, (float*)workspace, hw, c1, c2,
+                                                           groups, chunks, ppc);
+  else
+    gn_stats_kernel<__nv_bfloat16><<<grid, kGNThreads, smem, st>>>((const __nv_bfloat16*)x1, (const __nv_bfloat16*)x2,
+                                                                   (float*)workspace, hw, c1, c2, groups, chunks, ppc);
   int rc = check_launch("groupnorm stats");
   if (rc) return rc;
-  gn_apply_kernel<<<grid, kGNThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x1, (const __nv_bfloat16*)x2, gamma,
-                                                                 beta, (const float*)workspace, (__nv_bfloat16*)y, hw, c1,
-                                                                 c2, groups, chunks, ppc, eps, with_silu);
+  if (x_f32)
+    gn_apply_kernel<float><<<grid, kGNThreads, 0, st>>>((const float*)x1, (const float*)x2, gamma, beta,
+                                                        (const float*)workspace, (__nv_bfloat16*)y, hw, c1, c2, groups,
+                                                        chunks, ppc, eps, with_silu);
+  else
+    gn_apply_kernel<__nv_bfloat16><<<grid, kGNThreads, 0, st>>>((const __nv_bfloat16*)x1, (const __nv_bfloat16*)x2, gamma,
+                                                                beta, (const float*)workspace, (__nv_bfloat16*)y, hw, c1,
+                                                                c2, groups, chunks, ppc, eps, with_silu);
   return check_launch("groupnorm apply");
 }
 
-extern "C" int sdeo_layernorm(const void* x, const float* gamma, const float* beta, void* y, int32_t rows, int32_t c,
-                              float eps, void* stream) {
+extern "C" int sdeo_layernorm(const void* x, int32_t x_f32, const float* gamma, const float* beta, void* y, int32_t rows,
+                              int32_t c, float eps, void* stream) {
   if (!x || !gamma || !beta || !y) return set_error(SDEO_EINVAL, "layernorm: null argument");
   if (rows <= 0 || c % 8 != 0 || c > kLNMaxVec * 32 * 8) return set_error(SDEO_EINVAL, "layernorm: need C % 8 == 0 and C <= 2048");
   const int warps_per_block = 8;
   const int blocks = (rows + warps_per_block - 1) / warps_per_block;
-  layernorm_kernel<<<blocks, warps_per_block * 32, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, gamma, beta,
-                                                                              (__nv_bfloat16*)y, rows, c, eps);
+  if (x_f32)
+    layernorm_kernel<float><<<blocks, warps_per_block * 32, 0, (cudaStream_t)stream>>>((const float*)x, gamma, beta,
+                                                                                       (__nv_bfloat16*)y, rows, c, eps);
+  else
+    layernorm_kernel<__nv_bfloat16><<<blocks, warps_per_block * 32, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, gamma, beta, (__nv_bfloat16*)y, rows, c, eps);
   return check_launch("layernorm");
 }

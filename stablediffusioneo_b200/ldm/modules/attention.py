@@ -10,8 +10,9 @@ import torch
 import torch.nn as nn
 
 from ... import ops
+from .diffusionmodules import util
 from .diffusionmodules.util import (BF16, Conv2d, GroupNorm32, LayerNorm, Linear, _param_key, boundary, nhwc,
-                                    nchw_view, tokens_boundary, zero_module)
+                                    nchw_view, operand, tokens_boundary, zero_module)
 
 
 def exists(val):
@@ -62,8 +63,8 @@ class FeedForward(nn.Module):
             raise NotImplementedError("only the GEGLU feed-forward is on the ControlNet-SD1.5 path")
         self.net = nn.Sequential(GEGLU(dim, inner_dim), nn.Dropout(dropout), Linear(inner_dim, dim_out))
 
-    def run(self, x, residual=None):
-        return self.net[2].run(self.net[0].run(x), residual=residual)
+    def run(self, x, residual=None, stream=False):
+        return self.net[2].run(self.net[0].run(x), residual=residual, stream=stream, twin=stream)
 
     @tokens_boundary
     def forward(self, x):
@@ -121,16 +122,18 @@ class CrossAttention(nn.Module):
         ops.qkv_project(context, self._packed("kv"), h, d, 1, k=k, vt=vt, ldv=ldv)
         return k, vt, nkv, ldv
 
-    def run(self, x, context=None, residual=None):
-        """x: [B, T, C] bf16; context [B, nkv, ctx_dim] bf16 or None (self-attention). Returns to_out(attn) (+ residual)."""
+    def run(self, x, context=None, residual=None, stream=False):
+        """x: [B, T, C] bf16; context [B, nkv, ctx_dim] bf16 or None (self-attention). Returns to_out(attn) (+ residual);
+        `stream`: the result is an fp32 residual-stream tensor."""
         b, t, _ = x.shape
         h, d = self.heads, self.dim_head
         q = torch.empty((b * h, t, d), dtype=BF16, device=x.device)
         if context is None:
+            ldv = (t + 7) // 8 * 8
             k = torch.empty_like(q)
-            vt = torch.empty((b * h, d, t), dtype=BF16, device=x.device)
-            ops.qkv_project(x, self._packed("qkv"), h, d, 0, q=q, k=k, vt=vt, ldv=t)
-            nkv, ldv = t, t
+            vt = torch.empty((b * h, d, ldv), dtype=BF16, device=x.device)
+            ops.qkv_project(x, self._packed("qkv"), h, d, 0, q=q, k=k, vt=vt, ldv=ldv)
+            nkv = t
         else:
             ops.qkv_project(x, self._packed("q"), h, d, 0, q=q)
             if self.kv_static is not None and self.kv_static[0] is context:
@@ -138,7 +141,7 @@ class CrossAttention(nn.Module):
             else:
                 k, vt, nkv, ldv = self.project_kv(context)
         o = ops.attention(q, k, vt, b, h, t, nkv, d, ldv, self.scale)
-        return self.to_out[0].run(o, residual=residual)
+        return self.to_out[0].run(o, residual=residual, stream=stream)
 
     def forward(self, x, context=None, mask=None):
         if exists(mask):
@@ -167,16 +170,18 @@ class BasicTransformerBlock(nn.Module):
 
     def run(self, x, context=None):
         """attention.py:381-385; each residual add rides in the epilogue of the branch's last GEMM."""
-        x = self.attn1.run(self.norm1.run(x), context if self.disable_self_attn else None, residual=x)
-        x = self.attn2.run(self.norm2.run(x), context, residual=x)
-        x = self.ff.run(self.norm3.run(x), residual=x)
+        st = util.STREAM_FP32
+        x = self.attn1.run(self.norm1.run(x), context if self.disable_self_attn else None, residual=x, stream=st)
+        x = self.attn2.run(self.norm2.run(x), context, residual=x, stream=st)
+        x = self.ff.run(self.norm3.run(x), residual=x, stream=st)
         return x
 
     def forward(self, x, context=None):
         if x.dtype == BF16:
             return self.run(x.contiguous(), context)
         ctx = ops.to_bf16(context.float()) if context is not None else None
-        return ops.to_f32(self.run(ops.to_bf16(x.float()), ctx))
+        y = self.run(ops.to_bf16(x.float()), ctx)
+        return y if y.dtype == torch.float32 else ops.to_f32(y)
 
 
 class SpatialTransformer(nn.Module):
@@ -206,12 +211,14 @@ class SpatialTransformer(nn.Module):
             context = [context]
         b, c, h, w = x.shape
         x_in = x
-        t = self.proj_in.run(self.norm.run(x, silu=False))
+        st = util.STREAM_FP32
+        t = self.proj_in.run(self.norm.run(x, silu=False), out_fp32=st)   # the token stream's first value
         tok = nhwc(t).reshape(b, h * w, t.shape[1])
         for i, block in enumerate(self.transformer_blocks):
             tok = block.run(tok, context[i])
+        tok = operand(tok)                                                 # bf16 twin written by the last ff GEMM
         t = nchw_view(tok.reshape(b, h, w, tok.shape[-1]))
-        return self.proj_out.run(t, residual=x_in)
+        return self.proj_out.run(t, residual=x_in, stream=st)
 
     def forward(self, x, context=None):
         from .diffusionmodules.util import is_internal, to_external, to_internal

@@ -14,7 +14,8 @@ import torch.nn as nn
 
 from .... import ops
 from ..attention import SpatialTransformer
-from .util import (BF16, CatPair, Conv2d, SiLU, conv_nd, is_internal, linear, nchw_view, nhwc, normalization,
+from . import util
+from .util import (BF16, CatPair, Conv2d, SiLU, conv_nd, is_internal, linear, nchw_view, nhwc, normalization, operand,
                    timestep_embedding, to_external, to_internal, zero_module)
 
 
@@ -55,6 +56,8 @@ class TimestepEmbedSequential(nn.Sequential, TimestepBlock):
                 x = layer.run(x, context)
             elif isinstance(layer, SiLU):
                 raise RuntimeError("SiLU inside TimestepEmbedSequential is fused by the owning module")
+            elif isinstance(layer, Conv2d):
+                x = layer.run(x, stream=util.STREAM_FP32)
             else:
                 x = layer.run(x)
         return x
@@ -88,8 +91,8 @@ class Upsample(nn.Module):
 
     def run(self, x):
         assert x.shape[1] == self.channels
-        y = nchw_view(ops.upsample_nearest2x(nhwc(x)))
-        return self.conv.run(y) if self.use_conv else y
+        y = nchw_view(ops.upsample_nearest2x(nhwc(operand(x))))
+        return self.conv.run(y, stream=util.STREAM_FP32) if self.use_conv else y
 
     def forward(self, x):
         if is_internal(x):
@@ -112,7 +115,7 @@ class Downsample(nn.Module):
 
     def run(self, x):
         assert x.shape[1] == self.channels
-        return self.op.run(x)
+        return self.op.run(x, stream=util.STREAM_FP32)
 
     def forward(self, x):
         if is_internal(x):
@@ -158,7 +161,7 @@ class ResBlock(TimestepBlock):
             skip = x
         else:
             skip = self.skip_connection.run(x)
-        return self.out_layers[3].run(h, residual=skip)
+        return self.out_layers[3].run(h, residual=skip, stream=util.STREAM_FP32)
 
     def forward(self, x, emb):
         if is_internal(x):

@@ -120,14 +120,16 @@ def pack_geglu_bias(bias, geglu_bn):
 
 
 def conv2d(x, pw, x2=None, bias=None, emb=None, residual=None, scale=1.0, act=SDEO_ACT_NONE, stride=1, out=None,
-           out_fp32=False, epi_mode=SDEO_EPI_NORMAL, qkv=None):
-    """x: [N,H,W,C1] bf16 (+ optional x2 [N,H,W,C2] = fused torch.cat along channels). Returns [N,Ho,Wo,cout]."""
+           out_fp32=False, epi_mode=SDEO_EPI_NORMAL, qkv=None, twin=False):
+    """x: [N,H,W,C1] bf16 (+ optional x2 [N,H,W,C2] = fused torch.cat along channels). Returns [N,Ho,Wo,cout].
+    residual may be bf16 or fp32. out_fp32 + twin=True additionally writes a bf16 copy and returns (y_f32, y_bf16)."""
     lib = _lib.load()
     _req(x, BF16, "x")
     _req(x2, BF16, "x2")
     _req(bias, torch.float32, "bias")
     _req(emb, torch.float32, "emb")
-    _req(residual, BF16, "residual")
+    if residual is not None and residual.dtype != torch.float32:
+        _req(residual, BF16, "residual")
     n, h, w, ld1 = x.shape
     c1 = pw.c1
     # the pixel stride may exceed the channels the filter consumes (zero-padded / ignored tail channels)
@@ -168,13 +170,19 @@ def conv2d(x, pw, x2=None, bias=None, emb=None, residual=None, scale=1.0, act=SD
         if residual is not None:
             assert residual.shape[:3] == (n, ho, wo) and residual.shape[3] >= cols and residual.is_contiguous()
             a.residual, a.ldr = _ptr(residual), residual.shape[3]
+            a.residual_f32 = 1 if residual.dtype == torch.float32 else 0
+    out2 = None
+    if twin:
+        assert out_fp32 and epi_mode == SDEO_EPI_NORMAL
+        out2 = torch.empty(out.shape, dtype=BF16, device=x.device)
+        a.y2, a.ldy2 = _ptr(out2), out2.shape[3]
     ws = _workspaces.conv(x.device)
     a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
     check(lib.sdeo_conv2d(ctypes.byref(a), _stream()), "conv2d")
-    return out
+    return (out, out2) if twin else out
 
 
-def linear(x, pw, bias=None, residual=None, act=SDEO_ACT_NONE, out_fp32=False, geglu=False):
+def linear(x, pw, bias=None, residual=None, act=SDEO_ACT_NONE, out_fp32=False, geglu=False, twin=False):
     """x: [..., K] bf16 -> [..., cout] (GEGLU: [..., cout/2]). Runs the 1x1 case of the implicit-GEMM kernel."""
     lead = x.shape[:-1]
     rows = 1
@@ -183,7 +191,9 @@ def linear(x, pw, bias=None, residual=None, act=SDEO_ACT_NONE, out_fp32=False, g
     x4 = x.reshape(1, 1, rows, x.shape[-1])
     res4 = residual.reshape(1, 1, rows, residual.shape[-1]) if residual is not None else None
     y = conv2d(x4, pw, bias=bias, residual=res4, act=act, out_fp32=out_fp32,
-               epi_mode=SDEO_EPI_GEGLU if geglu else SDEO_EPI_NORMAL)
+               epi_mode=SDEO_EPI_GEGLU if geglu else SDEO_EPI_NORMAL, twin=twin)
+    if twin:
+        return y[0].reshape(*lead, y[0].shape[-1]), y[1].reshape(*lead, y[1].shape[-1])
     return y.reshape(*lead, y.shape[-1])
 
 
@@ -198,8 +208,9 @@ def qkv_project(x, pw, heads, dhead, first, q=None, k=None, vt=None, ldv=None, b
 def groupnorm(x, gamma, beta, eps, silu, x2=None, groups=32, out=None):
     """x: [N,H,W,C1] (+ x2 [N,H,W,C2]); returns the normalised concat [N,H,W,C1+C2]."""
     lib = _lib.load()
-    _req(x, BF16, "x")
-    _req(x2, BF16, "x2")
+    f32 = x.dtype == torch.float32
+    _req(x, torch.float32 if f32 else BF16, "x")
+    _req(x2, torch.float32 if f32 else BF16, "x2")
     _req(gamma, torch.float32, "gamma")
     _req(beta, torch.float32, "beta")
     n, h, w, c1 = x.shape
@@ -208,18 +219,21 @@ def groupnorm(x, gamma, beta, eps, silu, x2=None, groups=32, out=None):
         out = torch.empty((n, h, w, c1 + c2), dtype=BF16, device=x.device)
     nbytes = lib.sdeo_groupnorm_workspace_bytes(n, h * w, groups)
     ws = _workspaces.gn(x.device, nbytes)
-    check(lib.sdeo_groupnorm_nhwc(_ptr(x), _ptr(x2), _ptr(gamma), _ptr(beta), _ptr(out), n, h * w, c1, c2, groups,
+    check(lib.sdeo_groupnorm_nhwc(_ptr(x), _ptr(x2), 1 if f32 else 0, _ptr(gamma), _ptr(beta), _ptr(out), n, h * w, c1, c2, groups,
                                   float(eps), 1 if silu else 0, _ptr(ws), ws.numel(), _stream()), "groupnorm")
     return out
 
 
 def layernorm(x, gamma, beta, eps=1e-5):
+    """x: bf16 or fp32 (residual stream) [..., C] -> bf16."""
     lib = _lib.load()
-    _req(x, BF16, "x")
+    f32 = x.dtype == torch.float32
+    _req(x, torch.float32 if f32 else BF16, "x")
     c = x.shape[-1]
     rows = x.numel() // c
-    out = torch.empty_like(x)
-    check(lib.sdeo_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), rows, c, float(eps), _stream()), "layernorm")
+    out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    check(lib.sdeo_layernorm(_ptr(x), 1 if f32 else 0, _ptr(gamma), _ptr(beta), _ptr(out), rows, c, float(eps), _stream()),
+          "layernorm")
     return out
 
 

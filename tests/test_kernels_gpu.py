@@ -96,6 +96,14 @@ def test_conv2d_full_epilogue(cuda_device):
                          out_fp32=True)
         assert y32.dtype == torch.float32
         assert rel_l2(y32.permute(0, 3, 1, 2), ref) < 2e-3
+        # fp32 residual stream: fp32 residual in, fp32 out + bf16 twin
+        res32 = res.permute(0, 2, 3, 1).contiguous()
+        ref32 = ref_conv(x, wt, b, 1, emb=emb, act=act, scale=0.7) + res
+        ys, yt = ops.conv2d(nhwc(x), pw, bias=b, emb=emb.contiguous(), residual=res32, scale=0.7, act=1 if act else 0,
+                            out_fp32=True, twin=True)
+        assert ys.dtype == torch.float32 and yt.dtype == torch.bfloat16
+        assert rel_l2(ys.permute(0, 3, 1, 2), ref32) < 2e-3
+        assert torch.equal(yt, ys.to(torch.bfloat16))
 
 
 @pytest.mark.parametrize("c1,c2,cout,h,w,k", [(640, 320, 320, 32, 48, 3), (1280, 640, 1280, 8, 12, 1),
@@ -199,6 +207,11 @@ def test_groupnorm(cuda_device, case):
     if silu:
         ref = F.silu(ref)
     assert rel_l2(y.permute(0, 3, 1, 2), ref) < TOL
+    # fp32 (residual-stream) inputs
+    f32 = lambda t: t.permute(0, 2, 3, 1).contiguous()
+    y32 = ops.groupnorm(f32(xa), gamma, beta, eps, silu, x2=f32(xb) if c2 else None)
+    ref32 = F.group_norm(torch.cat([xa, xb], 1) if c2 else xa, 32, gamma, beta, eps)
+    assert rel_l2(y32.permute(0, 3, 1, 2), F.silu(ref32) if silu else ref32) < TOL
 
 
 @pytest.mark.parametrize("rows,c", [(3072, 320), (768, 640), (192, 1280), (48, 1280), (5, 512)])
@@ -211,6 +224,8 @@ def test_layernorm(cuda_device, rows, c):
     y = ops.layernorm(x.to(torch.bfloat16), gamma, beta, 1e-5)
     ref = F.layer_norm(bf16r(x), (c,), gamma, beta, 1e-5)
     assert rel_l2(y, ref) < TOL
+    y32 = ops.layernorm(x.contiguous(), gamma, beta, 1e-5)  # fp32 residual-stream input
+    assert y32.dtype == torch.bfloat16 and rel_l2(y32, F.layer_norm(x, (c,), gamma, beta, 1e-5)) < TOL
 
 
 ATT_CASES = [
