@@ -149,7 +149,27 @@ def _spec_block(p, block: Block, emb_ch, ctx_dim):
     return s
 
 
+def _is_zero_init(name: str) -> bool:
+    """Tensors the reference zero-initialises (openaimodel.py:228,731; attention.py:422; cldm/cldm.py:162,282)."""
+    return (name.endswith("out_layers.3.weight") or name.endswith("proj_out.weight") or name.startswith("zero_convs.")
+            or name.startswith("middle_block_out.") or name == "out.2.weight" or name == "input_hint_block.14.weight")
+
+
+def _mark_regular(spec):
+    """'w' -> 'wk' (PyTorch-default-init variance 1/(3 fan_in)) for every weight the reference does NOT zero-initialise;
+    the zero-initialised ones keep 'w' = N(0, 1/fan_in). This is SURVEY.md §8d's synthetic-weight scheme."""
+    return [(n, sh, "wk" if (k == "w" and not _is_zero_init(n)) else k) for n, sh, k in spec]
+
+
 def unet_param_spec(cfg: UNetConfig):
+    return _mark_regular(_unet_param_spec(cfg))
+
+
+def controlnet_param_spec(cfg: UNetConfig):
+    return _mark_regular(_controlnet_param_spec(cfg))
+
+
+def _unet_param_spec(cfg: UNetConfig):
     inp, mid, out, _ = unet_layout(cfg)
     mc, te = cfg.model_channels, cfg.model_channels * 4
     s = [("time_embed.0.weight", (te, mc), "w"), ("time_embed.0.bias", (te,), "b"),
@@ -168,7 +188,7 @@ HINT_CHANNELS = [16, 16, 32, 32, 96, 96, 256]   # cldm/cldm.py:147-163
 HINT_STRIDES = [1, 1, 2, 1, 2, 1, 2, 1]
 
 
-def controlnet_param_spec(cfg: UNetConfig):
+def _controlnet_param_spec(cfg: UNetConfig):
     inp, mid, _, chans = unet_layout(cfg)
     mc, te = cfg.model_channels, cfg.model_channels * 4
     s = [("time_embed.0.weight", (te, mc), "w"), ("time_embed.0.bias", (te,), "b"),
@@ -238,7 +258,9 @@ def vae_param_spec(cfg: VAEConfig):
 def make_weights(spec, seed: int, prefix: str = "") -> SD:
     """Deterministic synthetic weights, one Philox stream per tensor name (no dependence on construction order).
     Every tensor is non-zero — the reference's zero-initialised layers (openaimodel.py:228,731; attention.py:422;
-    cldm.py:162,282) would make eps identically 0 and the parity check vacuous (SURVEY.md §7 'zero-init trap')."""
+    cldm.py:162,282) would make eps identically 0 and the parity check vacuous (SURVEY.md §7 'zero-init trap').
+    Kinds: 'w' N(0, 1/fan_in); 'wk' N(0, 1/(3 fan_in)) = the variance of PyTorch's default kaiming-uniform init;
+    'b'/'norm_b' N(0, 0.1^2); 'norm_w' 1 + N(0, 0.1^2)."""
     import zlib
     sd = {}
     for name, shape, kind in spec:
@@ -248,6 +270,9 @@ def make_weights(spec, seed: int, prefix: str = "") -> SD:
         if kind == "w":
             fan_in = int(np.prod(shape[1:]))
             x *= 1.0 / math.sqrt(fan_in)
+        elif kind == "wk":
+            fan_in = int(np.prod(shape[1:]))
+            x *= 1.0 / math.sqrt(3.0 * fan_in)
         elif kind == "b" or kind == "norm_b":
             x *= 0.1
         elif kind == "norm_w":

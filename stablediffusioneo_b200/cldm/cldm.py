@@ -150,7 +150,9 @@ class ControlNet(nn.Module):
         while i < len(layers):
             conv = layers[i]
             fused = i + 1 < len(layers) and isinstance(layers[i + 1], SiLU)
-            h = conv.run(h, act=ops.SDEO_ACT_SILU if fused else ops.SDEO_ACT_NONE)
+            last = i + (2 if fused else 1) >= len(layers)
+            h = conv.run(h, act=ops.SDEO_ACT_SILU if fused else ops.SDEO_ACT_NONE,
+                         out_fp32=last and util.STREAM_FP32)   # the result is a residual term of conv_in's epilogue
             i += 2 if fused else 1
         return h
 

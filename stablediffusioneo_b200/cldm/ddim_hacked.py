@@ -234,6 +234,7 @@ class _Engine:
         self.dup = 2 if uncond is not None else 1
         nb = self.dup * b
         self.x_lat = torch.empty((b, c, h, w), dtype=torch.float32, device=dev)
+        self.x_keep = torch.empty_like(self.x_lat)
         self.pred_x0 = torch.empty_like(self.x_lat)
         self.first_x = torch.empty_like(self.x_lat)
         self.first_p = torch.empty_like(self.x_lat)
@@ -250,8 +251,7 @@ class _Engine:
 
     def _load_inputs(self, x_T, cond, uncond, ts, rows):
         b = x_T.shape[0]
-        self.x_lat.copy_(x_T)
-        ops.memset(self.step, 0)
+        self.x_keep.copy_(x_T, non_blocking=True)
         self.ts_table.copy_(torch.tensor(ts, dtype=torch.int64), non_blocking=True)
         self.coef.copy_(torch.tensor(rows, dtype=torch.float32), non_blocking=True)
         conds = [cond] + ([uncond] if uncond is not None else [])
@@ -261,8 +261,15 @@ class _Engine:
             self.ctx[i * b:(i + 1) * b].copy_(ctx if ctx.dtype == BF16 else ops.to_bf16(ctx.float().contiguous()))
             if self.has_hint:
                 hint = cd["c_concat"][0] if len(cd["c_concat"]) == 1 else torch.cat(cd["c_concat"], 1)
-                self.hint[i * b:(i + 1) * b].copy_(hint)
-        # network input for step 0: bf16 NHWC copy of x_T, channels padded to 8, duplicated for cond/uncond
+                self.hint[i * b:(i + 1) * b].copy_(hint, non_blocking=True)
+        self.reset_latent()
+
+    def reset_latent(self):
+        """Rewind to step 0 with the resident x_T: latent, step counter, and the bf16 NHWC network input
+        (channels padded to 8, duplicated for cond/uncond). Device-side only."""
+        b = self.x_lat.shape[0]
+        self.x_lat.copy_(self.x_keep)
+        ops.memset(self.step, 0)
         x0 = ops.nchw_to_nhwc(self.x_lat, 8)
         for i in range(self.dup):
             self.x_in[i * b:(i + 1) * b].copy_(x0)
@@ -312,29 +319,40 @@ class _Engine:
                           pred_x0=self.pred_x0, x_next=self.x_in, dup=self.dup, eps_nhwc=True)
         ops.counter_add(self.step, 1)
 
-    def run(self, x_T, cond, uncond, ts, rows):
+    def prepare(self, x_T, cond, uncond, ts, rows):
+        """Upload inputs, run the loop-invariant prologue and (first time) capture the per-step CUDA graph."""
         S = len(ts)
         if not self.ready:
             self._alloc(x_T, cond, uncond, S)
+        self.S = S
         self._load_inputs(x_T, cond, uncond, ts, rows)
         self._prologue()
         if self.use_graph and self.graph is None:
             # warm-up once eagerly (packs weights, sizes workspaces), then capture the step
             self._step()
             torch.cuda.synchronize()
-            self._load_inputs(x_T, cond, uncond, ts, rows)
+            self.reset_latent()
+            n0 = ops.LAUNCHES
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._step()
+            self.launches_per_step = ops.LAUNCHES - n0
             self.graph = g
-            self._load_inputs(x_T, cond, uncond, ts, rows)
+            self.reset_latent()
         self.ready = True
+
+    def step(self):
+        """One denoising step: graph replay (or the eager launch sequence)."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step()
+
+    def run(self, x_T, cond, uncond, ts, rows):
+        self.prepare(x_T, cond, uncond, ts, rows)
         first = None
-        for i in range(S):
-            if self.graph is not None:
-                self.graph.replay()
-            else:
-                self._step()
+        for i in range(self.S):
+            self.step()
             if i == 0:
                 self.first_x.copy_(self.x_lat)
                 self.first_p.copy_(self.pred_x0)

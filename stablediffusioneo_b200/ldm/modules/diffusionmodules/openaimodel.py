@@ -154,13 +154,14 @@ class ResBlock(TimestepBlock):
         """x: internal tensor or CatPair (decoder blocks); emb: bf16 [N, emb_channels]."""
         h = self.in_layers[0].run(x, silu=True)
         emb_out = self.emb_layers[1].run(silu_of(emb), out_fp32=True)       # fp32 [N, Cout]
-        h = self.in_layers[2].run(h, emb=emb_out)
+        # GEMM results that feed a normalisation or a residual add stay fp32 (no extra bf16 rounding in the branch)
+        h = self.in_layers[2].run(h, emb=emb_out, out_fp32=util.STREAM_FP32)
         h = self.out_layers[0].run(h, silu=True)
         if isinstance(self.skip_connection, nn.Identity):
             assert not isinstance(x, CatPair)
             skip = x
         else:
-            skip = self.skip_connection.run(x)
+            skip = self.skip_connection.run(x, out_fp32=util.STREAM_FP32)
         return self.out_layers[3].run(h, residual=skip, stream=util.STREAM_FP32)
 
     def forward(self, x, emb):

@@ -7,9 +7,21 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib
-from ._lib import ConvArgs, SDEO_ACT_NONE, SDEO_ACT_SILU, SDEO_EPI_GEGLU, SDEO_EPI_NORMAL, SDEO_EPI_QKV, check
+from ._lib import ConvArgs, SDEO_ACT_NONE, SDEO_ACT_SILU, SDEO_EPI_GEGLU, SDEO_EPI_NORMAL, SDEO_EPI_QKV
+from ._lib import check as _check
 
 BF16 = torch.bfloat16
+
+# Number of libsdeo kernels launched through this module (bench.py reports it as `gpu_launches`).
+LAUNCHES = 0
+_KERNELS_PER_CALL = {"groupnorm": 2}
+
+
+def check(rc, what=""):
+    global LAUNCHES
+    _check(rc, what)
+    LAUNCHES += _KERNELS_PER_CALL.get(what, 1)
+
 
 
 def _stream():

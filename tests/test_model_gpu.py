@@ -80,9 +80,10 @@ def test_tiny_sampler(tiny, cuda_device, graph):
         samples, inter = sampler.sample(g["S"], 1, (4, 8, 16), cond, verbose=False, eta=0.0, x_T=x_T,
                                         unconditional_guidance_scale=9.0, unconditional_conditioning=uncond)
         assert rel_l2(samples, g["samples"]) < 3e-2
+    host = lambda t: np.asarray(t.cpu() if torch.is_tensor(t) else t, dtype=np.float64)
     assert np.array_equal(np.asarray(sampler.ddim_timesteps), g["ddim_timesteps"].numpy())
-    assert np.allclose(np.asarray(sampler.ddim_alphas, dtype=np.float64), g["ddim_alphas"].numpy(), rtol=1e-6)
-    assert np.allclose(np.asarray(sampler.ddim_alphas_prev, dtype=np.float64), g["ddim_alphas_prev"].numpy(), rtol=1e-6)
+    assert np.allclose(host(sampler.ddim_alphas), g["ddim_alphas"].numpy(), rtol=1e-6)
+    assert np.allclose(host(sampler.ddim_alphas_prev), g["ddim_alphas_prev"].numpy(), rtol=1e-6)
     assert len(inter["x_inter"]) == 3
 
 
