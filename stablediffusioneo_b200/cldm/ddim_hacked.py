@@ -241,7 +241,7 @@ class _Engine:
         self.x_in = torch.empty((nb, h, w, 8), dtype=BF16, device=dev)
         self.ts_table = torch.zeros((S,), dtype=torch.int64, device=dev)
         self.coef = torch.zeros((S, 8), dtype=torch.float32, device=dev)
-        self.step = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self.step_ctr = torch.zeros((1,), dtype=torch.int32, device=dev)
         ctx_shape = cond["c_crossattn"][0].shape
         self.ctx = torch.empty((nb, ctx_shape[1], ctx_shape[2]), dtype=BF16, device=dev)
         self.has_hint = cond["c_concat"] is not None
@@ -269,7 +269,7 @@ class _Engine:
         (channels padded to 8, duplicated for cond/uncond). Device-side only."""
         b = self.x_lat.shape[0]
         self.x_lat.copy_(self.x_keep)
-        ops.memset(self.step, 0)
+        ops.memset(self.step_ctr, 0)
         x0 = ops.nchw_to_nhwc(self.x_lat, 8)
         for i in range(self.dup):
             self.x_in[i * b:(i + 1) * b].copy_(x0)
@@ -303,7 +303,7 @@ class _Engine:
         nb = self.x_in.shape[0]
         b = self.x_lat.shape[0]
         x = self.x_in.permute(0, 3, 1, 2)
-        t_emb = ops.timestep_embedding(self.ts_table, nb, unet.model_channels, step_idx=self.step)
+        t_emb = ops.timestep_embedding(self.ts_table, nb, unet.model_channels, step_idx=self.step_ctr)
         emb_u = unet.time_embed[2].run(unet.time_embed[0].run(t_emb, act=ops.SDEO_ACT_SILU))
         hs, h = unet.run_encoder(x, emb_u, self.ctx)
         if self.has_hint:
@@ -315,9 +315,9 @@ class _Engine:
         eps = nhwc(unet.run_decoder(h, hs, emb_u, self.ctx))          # fp32 [nb, h, w, 4]
         eps_c = eps[:b]
         eps_u = eps[b:] if self.dup == 2 else None
-        ops.cfg_ddim_step(eps_c, eps_u, self.x_lat, self.coef, step_idx=self.step, x_prev=self.x_lat,
+        ops.cfg_ddim_step(eps_c, eps_u, self.x_lat, self.coef, step_idx=self.step_ctr, x_prev=self.x_lat,
                           pred_x0=self.pred_x0, x_next=self.x_in, dup=self.dup, eps_nhwc=True)
-        ops.counter_add(self.step, 1)
+        ops.counter_add(self.step_ctr, 1)
 
     def prepare(self, x_T, cond, uncond, ts, rows):
         """Upload inputs, run the loop-invariant prologue and (first time) capture the per-step CUDA graph."""
