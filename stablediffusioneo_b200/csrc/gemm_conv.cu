@@ -6,21 +6,30 @@
 //       fill, the stride-2 case is the tensor map's elementStrides, torch.cat([x1,x2],1) is two tensor maps.
 //   N = output channels, tile BN (multiple of 16, <= 256, chosen at run time).
 //   K = taps * channels in chunks of 64 bf16 (one 128-byte swizzle atom per row).
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
-// (TMEM -> registers -> bias / time-embedding / SiLU / scale / residual / GEGLU / QKV scatter -> global).
-// Split-K: partial tiles go to an fp32 workspace; the last CTA to arrive on a tile sums them in split order
-// (deterministic) and runs the epilogue.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+//
+// Epilogue, two phases:
+//   1. TMEM -> registers -> fp32 tile in shared memory (the drained pipeline stages are reused), thread = row.
+//   2. the tile is walked in (row, 8-column) items with consecutive threads on consecutive columns, so that bias /
+//      time-embedding / residual loads and the output stores are coalesced 16-32 byte vectors with many in flight:
+//      bias + emb -> SiLU -> scale -> + residual -> bf16 / fp32 (+ bf16 twin) | GEGLU | QKV scatter.
+// Split-K (small-M, weight-streaming layers): the S K-slices of one output tile run as ONE THREAD-BLOCK CLUSTER
+// (1,1,S). After the mainloop every CTA holds its partial tile in its own shared memory; after a cluster barrier CTA r
+// reduces rows [r*128/S, (r+1)*128/S) over all S partials through distributed shared memory (ld.shared::cluster), in
+// rank order (deterministic), and runs the epilogue for those rows. No global workspace, no atomics.
 #include "common.cuh"
 #include "host_util.h"
 #include "../../include/sdeo.h"
+#include <stdlib.h>
 
 namespace sdeo {
 
 constexpr int kConvThreads = 192;
+constexpr int kEpiThreads = 128;
 constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kATileBytes = kBM * kBK * 2;  // 16 KB
-constexpr int kMaxTilesForCounters = 16384;
+constexpr int kMaxCluster = 8;              // portable cluster size limit
 
 struct ConvKParams {
   // K loop
@@ -37,7 +46,7 @@ struct ConvKParams {
   int epi_mode, act, y_fp32;
   const float* bias;
   const float* emb;
-  const __nv_bfloat16* residual;
+  const void* residual;
   int ldr, residual_f32;
   float scale;
   void* y;
@@ -49,95 +58,136 @@ struct ConvKParams {
   __nv_bfloat16* k;
   __nv_bfloat16* vt;
   int heads, dhead, tokens, ldv, qkv_first;
-  // split-K
-  float* ws;
-  unsigned int* counters;
 };
 
 struct RowInfo {
   bool valid;
-  int batch;     // sample index
-  long long pix; // linear output pixel index
+  int batch;      // sample index
+  long long pix;  // linear output pixel index
 };
 
-// One 8-column group of the NORMAL epilogue for one row.
-__device__ __forceinline__ void epi_normal_store8(const ConvKParams& p, const RowInfo& ri, int n, const float* v) {
+// ---- cluster / distributed shared memory ----
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t dsmem_addr(uint32_t local_smem_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+__device__ __forceinline__ void load8_f32(const float* p, float* f) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void load8_bf16(const __nv_bfloat16* p, float* f) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8_bf16(const float* x) {
+  uint4 o;
+  o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]);
+  o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
+  return o;
+}
+
+// NORMAL epilogue of one (row, 8 columns) item: v holds the fp32 accumulators of columns n .. n+7.
+__device__ __forceinline__ void epi_normal_item(const ConvKParams& p, const RowInfo& ri, int n, float* v) {
   if (n >= p.cout) return;
-  float x[8];
   const bool full = (n + 8 <= p.cout);
+  if (full) {
+    if (p.bias) {
+      float b[8];
+      load8_f32(p.bias + n, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += b[j];
+    }
+    if (p.emb) {
+      float e[8];
+      load8_f32(p.emb + (long long)ri.batch * p.cout + n, e);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += e[j];
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (n + j < p.cout) {
+        if (p.bias) v[j] += __ldg(p.bias + n + j);
+        if (p.emb) v[j] += __ldg(p.emb + (long long)ri.batch * p.cout + n + j);
+      }
+    }
+  }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     float t = v[j];
-    const int nn = n + j;
-    if (full || nn < p.cout) {
-      if (p.bias) t += __ldg(p.bias + nn);
-      if (p.emb) t += __ldg(p.emb + (long long)ri.batch * p.cout + nn);
-    }
     if (p.act == SDEO_ACT_SILU) t = silu_f(t);
-    x[j] = t * p.scale;
+    v[j] = t * p.scale;
   }
-  if (p.residual && p.residual_f32) {
-    const float* rp = reinterpret_cast<const float*>(p.residual) + ri.pix * p.ldr + n;
-    if (full && ((p.ldr & 3) == 0)) {
-      const float4 a = *reinterpret_cast<const float4*>(rp), b = *reinterpret_cast<const float4*>(rp + 4);
-      x[0] += a.x; x[1] += a.y; x[2] += a.z; x[3] += a.w; x[4] += b.x; x[5] += b.y; x[6] += b.z; x[7] += b.w;
-    } else {
+  if (p.residual) {
+    if (p.residual_f32) {
+      const float* rp = reinterpret_cast<const float*>(p.residual) + ri.pix * p.ldr + n;
+      if (full && ((p.ldr & 3) == 0)) {
+        const float4 a = *reinterpret_cast<const float4*>(rp), b = *reinterpret_cast<const float4*>(rp + 4);
+        v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+      } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (n + j < p.cout) x[j] += rp[j];
-    }
-  } else if (p.residual) {
-    const __nv_bfloat16* rp = p.residual + ri.pix * p.ldr + n;
-    if (full && ((p.ldr & 7) == 0)) {
-      uint4 rv = *reinterpret_cast<const uint4*>(rp);
-      float2 a = unpack_bf16x2(rv.x), b = unpack_bf16x2(rv.y), c = unpack_bf16x2(rv.z), d = unpack_bf16x2(rv.w);
-      x[0] += a.x; x[1] += a.y; x[2] += b.x; x[3] += b.y; x[4] += c.x; x[5] += c.y; x[6] += d.x; x[7] += d.y;
+        for (int j = 0; j < 8; ++j)
+          if (n + j < p.cout) v[j] += rp[j];
+      }
     } else {
+      const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + ri.pix * p.ldr + n;
+      if (full && ((p.ldr & 7) == 0)) {
+        float r[8];
+        load8_bf16(rp, r);
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (n + j < p.cout) x[j] += __bfloat162float(rp[j]);
+        for (int j = 0; j < 8; ++j) v[j] += r[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (n + j < p.cout) v[j] += __bfloat162float(rp[j]);
+      }
     }
   }
   if (p.y_fp32) {
     float* yp = reinterpret_cast<float*>(p.y) + ri.pix * p.ldy + n;
     if (full && ((p.ldy & 3) == 0)) {
-      *reinterpret_cast<float4*>(yp) = make_float4(x[0], x[1], x[2], x[3]);
-      *reinterpret_cast<float4*>(yp + 4) = make_float4(x[4], x[5], x[6], x[7]);
+      *reinterpret_cast<float4*>(yp) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(yp + 4) = make_float4(v[4], v[5], v[6], v[7]);
     } else {
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        if (n + j < p.cout) yp[j] = x[j];
+        if (n + j < p.cout) yp[j] = v[j];
     }
     if (p.y2) {  // bf16 twin of an fp32 residual-stream tensor, for consumers that read it through TMA
       __nv_bfloat16* y2p = p.y2 + ri.pix * p.ldy2 + n;
       if (full && ((p.ldy2 & 7) == 0)) {
-        uint4 o;
-        o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]);
-        o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
-        *reinterpret_cast<uint4*>(y2p) = o;
+        *reinterpret_cast<uint4*>(y2p) = pack8_bf16(v);
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          if (n + j < p.cout) y2p[j] = __float2bfloat16(x[j]);
+          if (n + j < p.cout) y2p[j] = __float2bfloat16(v[j]);
       }
     }
   } else {
     __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + ri.pix * p.ldy + n;
     if (full && ((p.ldy & 7) == 0)) {
-      uint4 o;
-      o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]);
-      o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
-      *reinterpret_cast<uint4*>(yp) = o;
+      *reinterpret_cast<uint4*>(yp) = pack8_bf16(v);
     } else {
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        if (n + j < p.cout) yp[j] = __float2bfloat16(x[j]);
+        if (n + j < p.cout) yp[j] = __float2bfloat16(v[j]);
     }
   }
 }
 
-// One 8-column group of the QKV epilogue: scatter into head-major q/k and transposed v.
-__device__ __forceinline__ void epi_qkv_store8(const ConvKParams& p, const RowInfo& ri, int n, const float* v) {
+// QKV epilogue of one item: scatter into head-major q/k and transposed v.
+__device__ __forceinline__ void epi_qkv_item(const ConvKParams& p, const RowInfo& ri, int n, float* v) {
   if (n >= p.cout) return;
   const int C = p.heads * p.dhead;
   const int which = n / C + p.qkv_first;
@@ -146,38 +196,38 @@ __device__ __forceinline__ void epi_qkv_store8(const ConvKParams& p, const RowIn
   const int dd = nc % p.dhead;
   const int b = (int)(ri.pix / p.tokens);
   const int tok = (int)(ri.pix % p.tokens);
-  float x[8];
+  if (p.bias) {
+    float bb[8];
+    load8_f32(p.bias + n, bb);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) x[j] = v[j] + (p.bias ? __ldg(p.bias + n + j) : 0.0f);
+    for (int j = 0; j < 8; ++j) v[j] += bb[j];
+  }
   const long long bh = (long long)b * p.heads + head;
   if (which < 2) {
     __nv_bfloat16* dst = (which == 0 ? p.q : p.k) + (bh * p.tokens + tok) * p.dhead + dd;
-    uint4 o;
-    o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]);
-    o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
-    *reinterpret_cast<uint4*>(dst) = o;
+    *reinterpret_cast<uint4*>(dst) = pack8_bf16(v);
   } else {
     __nv_bfloat16* dst = p.vt + (bh * p.dhead + dd) * p.ldv + tok;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dst[(long long)j * p.ldv] = __float2bfloat16(x[j]);
+    for (int j = 0; j < 8; ++j) dst[(long long)j * p.ldv] = __float2bfloat16(v[j]);
   }
 }
 
-__device__ __forceinline__ void epi_geglu_store8(const ConvKParams& p, const RowInfo& ri, int n_out, int nb_x,
-                                                 int nb_g, const float* vx, const float* vg) {
-  // n_out: output column; nb_x / nb_g: packed bias indices of the x and gate columns
-  float x[8];
+// GEGLU epilogue of one item: y[:, n_out..+7] = (x + bx) * gelu(gate + bg); nb_x / nb_g index the packed bias.
+__device__ __forceinline__ void epi_geglu_item(const ConvKParams& p, const RowInfo& ri, int n_out, int nb_x, int nb_g,
+                                               const float* vx, const float* vg) {
+  float bx[8], bg[8], x[8];
+  if (p.bias) {
+    load8_f32(p.bias + nb_x, bx);
+    load8_f32(p.bias + nb_g, bg);
+  } else {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float a = vx[j] + (p.bias ? __ldg(p.bias + nb_x + j) : 0.0f);
-    float g = vg[j] + (p.bias ? __ldg(p.bias + nb_g + j) : 0.0f);
-    x[j] = a * gelu_erf_f(g);
+    for (int j = 0; j < 8; ++j) { bx[j] = 0.f; bg[j] = 0.f; }
   }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) x[j] = (vx[j] + bx[j]) * gelu_erf_f(vg[j] + bg[j]);
   __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + ri.pix * p.ldy + n_out;
-  uint4 o;
-  o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]);
-  o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
-  *reinterpret_cast<uint4*>(yp) = o;
+  *reinterpret_cast<uint4*>(yp) = pack8_bf16(x);
 }
 
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -187,19 +237,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
-  const int stage_bytes = kATileBytes + p.BN * 128;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
-  uint64_t* empty_bar = full_bar + p.stages;
-  uint64_t* tmem_full_bar = empty_bar + p.stages;
+  // layout: [barriers: 1 KB][pipeline stages, reused as the fp32 epilogue tile]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty_bar = full_bar + 16;
+  uint64_t* tmem_full_bar = empty_bar + 16;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  uint32_t* flag_smem = tmem_ptr_smem + 1;
+  uint8_t* tiles = smem + 1024;
+  const int stage_bytes = kATileBytes + p.BN * 128;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   const int m_tile = blockIdx.x;
   const int n_tile = blockIdx.y;
-  const int split = blockIdx.z;
+  const int split = blockIdx.z;  // == rank in the (1,1,S) cluster
   const int iw = m_tile % p.tiles_w;
   const int ih = (m_tile / p.tiles_w) % p.tiles_h;
   const int in_ = m_tile / (p.tiles_w * p.tiles_h);
@@ -230,6 +281,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  const int LD = p.BN + 4;  // fp32 tile row pitch in floats: 16-byte aligned rows, conflict-free 16 B row writes
+  float* tile = reinterpret_cast<float*>(tiles);
+
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -243,7 +297,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         const int tap = kc / p.chunks_per_tap;
         const int within = kc % p.chunks_per_tap;
         const int ky = tap / p.kw, kx = tap % p.kw;
-        uint8_t* a_dst = smem + (size_t)s * stage_bytes;
+        uint8_t* a_dst = tiles + (size_t)s * stage_bytes;
         uint8_t* b_dst = a_dst + kATileBytes;
         const int wc = w0 * p.stride + kx - p.pad;
         const int hc = h0 * p.stride + ky - p.pad;
@@ -263,7 +317,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t a_addr = smem_u32(tiles + (size_t)s * stage_bytes);
         const uint32_t b_addr = a_addr + kATileBytes;
         const uint64_t a_desc = umma_desc_k_sw128(a_addr);
         const uint64_t b_desc = umma_desc_k_sw128(b_addr);
@@ -275,132 +329,111 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         }
         tc_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
       }
-      tc_commit(tmem_full_bar);    // accumulator complete
+      tc_commit(tmem_full_bar);    // accumulator complete (all MMAs done => every stage has been consumed)
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue phase 1: TMEM -> fp32 tile in shared memory (thread = row) =====================
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
     const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const int et = threadIdx.x - 64;  // 0..127 epilogue thread id
-
-    RowInfo ri;
-    {
-      const int per_img = p.bh * p.bw;
-      const int nl = row / per_img;
-      const int rem = row % per_img;
-      const int hl = rem / p.bw, wl = rem % p.bw;
-      const int nn = n0 + nl, hh = h0 + hl, ww = w0 + wl;
-      ri.valid = (row < p.rows_valid) && (nn < p.N) && (hh < p.Ho) && (ww < p.Wo);
-      ri.batch = nn;
-      ri.pix = ((long long)nn * p.Ho + hh) * p.Wo + ww;
-    }
-
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-
-    bool do_epilogue = true;
-    const int tile_linear = blockIdx.y * gridDim.x + blockIdx.x;
-    float* ws_tile = nullptr;
-    if (p.splits > 1) {
-      // ---- write this split's partial tile: layout [BN/4][128 rows][4] fp32 ----
-      ws_tile = p.ws + ((size_t)tile_linear * p.splits) * (size_t)(kBM * p.BN);
-      float* mine = ws_tile + (size_t)split * (kBM * p.BN);
-      for (int c = 0; c < p.BN / 16; ++c) {
-        uint32_t r[16];
-        tmem_ld16(taddr_row + (uint32_t)(c * 16), r);
-        tmem_ld_wait();
+    float* trow = tile + (size_t)row * LD;
+    int c = 0;
+    for (; c + 32 <= p.BN; c += 32) {
+      uint32_t r[32];
+      tmem_ld32(taddr_row + (uint32_t)c, r);
+      tmem_ld_wait();
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float4 v = make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]),
-                                 __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
-          *reinterpret_cast<float4*>(mine + ((size_t)(c * 4 + g) * kBM + row) * 4) = v;
-        }
-      }
-      __threadfence();
-      bar_sync(1, 128);
-      if (et == 0) {
-        const unsigned int prev = atomicAdd(&p.counters[tile_linear], 1u);
-        const bool last = (prev == (unsigned int)(p.splits - 1));
-        if (last) p.counters[tile_linear] = 0u;  // self-reset for the next launch
-        *flag_smem = last ? 1u : 0u;
-      }
-      bar_sync(1, 128);
-      do_epilogue = (*flag_smem != 0u);
-      if (do_epilogue) __threadfence();
+      for (int g = 0; g < 8; ++g)
+        *reinterpret_cast<float4*>(trow + c + 4 * g) =
+            make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
+                        __uint_as_float(r[4 * g + 3]));
     }
+    if (c < p.BN) {
+      uint32_t r[16];
+      tmem_ld16(taddr_row + (uint32_t)c, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<float4*>(trow + c + 4 * g) =
+            make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
+                        __uint_as_float(r[4 * g + 3]));
+    }
+    tc_fence_before();
+  }
 
-    if (do_epilogue) {
-      const int n_base = n_tile * p.BN;
-      if (p.epi_mode == SDEO_EPI_GEGLU) {
-        const int half = p.BN / 2;
-        for (int c = 0; c < half / 16; ++c) {
-          float vx[16], vg[16];
-          if (p.splits > 1) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { vx[j] = 0.f; vg[j] = 0.f; }
-            for (int s = 0; s < p.splits; ++s) {
-              const float* part = ws_tile + (size_t)s * (kBM * p.BN);
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                float4 a = *reinterpret_cast<const float4*>(part + ((size_t)(c * 4 + g) * kBM + row) * 4);
-                float4 b = *reinterpret_cast<const float4*>(part + ((size_t)((half / 4) + c * 4 + g) * kBM + row) * 4);
-                vx[4 * g] += a.x; vx[4 * g + 1] += a.y; vx[4 * g + 2] += a.z; vx[4 * g + 3] += a.w;
-                vg[4 * g] += b.x; vg[4 * g + 1] += b.y; vg[4 * g + 2] += b.z; vg[4 * g + 3] += b.w;
-              }
-            }
-          } else {
-            uint32_t rx[16], rg[16];
-            tmem_ld16(taddr_row + (uint32_t)(c * 16), rx);
-            tmem_ld16(taddr_row + (uint32_t)(half + c * 16), rg);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { vx[j] = __uint_as_float(rx[j]); vg[j] = __uint_as_float(rg[j]); }
-          }
-          if (ri.valid) {
-            const int n_out = n_tile * half + c * 16;
-            epi_geglu_store8(p, ri, n_out, n_base + c * 16, n_base + half + c * 16, vx, vg);
-            epi_geglu_store8(p, ri, n_out + 8, n_base + c * 16 + 8, n_base + half + c * 16 + 8, vx + 8, vg + 8);
-          }
+  // ---- partial tiles complete: CTA-wide (S == 1) or cluster-wide (S > 1) barrier ----
+  __syncwarp();
+  if (p.splits > 1) cluster_sync_all();
+  else __syncthreads();
+
+  if (warp >= 2) {
+    // ===================== epilogue phase 2: coalesced items (row, 8 columns) =====================
+    const int et = threadIdx.x - 64;
+    const int S = p.splits;
+    const int rows_per = (p.rows_valid + S - 1) / S;
+    const int r_begin = split * rows_per;
+    const int r_end = min(p.rows_valid, r_begin + rows_per);
+    const int per_img = p.bh * p.bw;
+    const bool geglu = (p.epi_mode == SDEO_EPI_GEGLU);
+    const int cols_items = geglu ? p.BN / 16 : p.BN / 8;  // items per row
+    const int n_items = (r_end > r_begin ? (r_end - r_begin) : 0) * cols_items;
+    const uint32_t tile_saddr = smem_u32(tile);
+    const int n_base = n_tile * p.BN;
+    for (int it = et; it < n_items; it += kEpiThreads) {
+      const int row = r_begin + it / cols_items;
+      const int cv = it % cols_items;
+      RowInfo ri;
+      {
+        const int nl = row / per_img;
+        const int rem = row % per_img;
+        const int hl = rem / p.bw, wl = rem % p.bw;
+        const int nn = n0 + nl, hh = h0 + hl, ww = w0 + wl;
+        ri.valid = (nn < p.N) && (hh < p.Ho) && (ww < p.Wo);
+        ri.batch = nn;
+        ri.pix = ((long long)nn * p.Ho + hh) * p.Wo + ww;
+      }
+      const int col = cv * 8;
+      float v[8], g[8];
+      if (S == 1) {
+        const float* src = tile + (size_t)row * LD + col;
+        const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        if (geglu) {
+          const float4 c2 = *reinterpret_cast<const float4*>(src + p.BN / 2), d2 = *reinterpret_cast<const float4*>(src + p.BN / 2 + 4);
+          g[0] = c2.x; g[1] = c2.y; g[2] = c2.z; g[3] = c2.w; g[4] = d2.x; g[5] = d2.y; g[6] = d2.z; g[7] = d2.w;
         }
       } else {
-        for (int c = 0; c < p.BN / 16; ++c) {
-          float v[16];
-          if (p.splits > 1) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = 0.f;
-            for (int s = 0; s < p.splits; ++s) {
-              const float* part = ws_tile + (size_t)s * (kBM * p.BN);
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                float4 a = *reinterpret_cast<const float4*>(part + ((size_t)(c * 4 + g) * kBM + row) * 4);
-                v[4 * g] += a.x; v[4 * g + 1] += a.y; v[4 * g + 2] += a.z; v[4 * g + 3] += a.w;
-              }
-            }
-          } else {
-            uint32_t r[16];
-            tmem_ld16(taddr_row + (uint32_t)(c * 16), r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-          }
-          if (ri.valid) {
-            const int n = n_base + c * 16;
-            if (p.epi_mode == SDEO_EPI_QKV) {
-              epi_qkv_store8(p, ri, n, v);
-              epi_qkv_store8(p, ri, n + 8, v + 8);
-            } else {
-              epi_normal_store8(p, ri, n, v);
-              epi_normal_store8(p, ri, n + 8, v + 8);
-            }
+        for (int j = 0; j < 8; ++j) { v[j] = 0.f; g[j] = 0.f; }
+        const uint32_t off = (uint32_t)(((size_t)row * LD + col) * sizeof(float));
+        for (int s = 0; s < S; ++s) {  // rank order: deterministic
+          const uint32_t base = dsmem_addr(tile_saddr, (uint32_t)s) + off;
+          const float4 a = ld_dsmem_f4(base), b = ld_dsmem_f4(base + 16);
+          v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+          if (geglu) {
+            const float4 c2 = ld_dsmem_f4(base + (uint32_t)(p.BN / 2) * 4u), d2 = ld_dsmem_f4(base + (uint32_t)(p.BN / 2) * 4u + 16);
+            g[0] += c2.x; g[1] += c2.y; g[2] += c2.z; g[3] += c2.w; g[4] += d2.x; g[5] += d2.y; g[6] += d2.z; g[7] += d2.w;
           }
         }
+      }
+      if (!ri.valid) continue;
+      if (geglu) {
+        epi_geglu_item(p, ri, n_tile * (p.BN / 2) + col, n_base + col, n_base + p.BN / 2 + col, v, g);
+      } else if (p.epi_mode == SDEO_EPI_QKV) {
+        epi_qkv_item(p, ri, n_base + col, v);
+      } else {
+        epi_normal_item(p, ri, n_base + col, v);
       }
     }
   }
 
+  // ---- teardown: nobody may exit while a peer still reads its tile through DSMEM ----
   tc_fence_before();
-  __syncthreads();
+  __syncwarp();
+  if (p.splits > 1) cluster_sync_all();
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
@@ -514,58 +547,71 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl) {
   pl->tiles_n = (a->n + bbn - 1) / bbn;
   pl->tiles_h = (pl->Ho + bbh - 1) / bbh;
   pl->tiles_w = (pl->Wo + bbw - 1) / bbw;
-  // ---- N tile ----
-  pl->rows_packed = round_up(a->cout, 16);
-  pl->BN = pick_bn_impl(pl->rows_packed, a->epi_mode);
-  if (pl->BN <= 0 || pl->BN > 256 || (pl->BN % 16) != 0) return false;
-  pl->n_tiles = pl->rows_packed / pl->BN;
   // ---- K ----
   pl->c1c = (a->c1 + 63) / 64;
   pl->c2c = a->x2 ? (a->c2 + 63) / 64 : 0;
   pl->cpt = pl->c1c + pl->c2c;
   pl->total_chunks = a->ksize * a->ksize * pl->cpt;
-  const int base = best_tiles * pl->n_tiles;
-  int splits = 1;
-  if (base < 120 && a->workspace != nullptr) {
-    splits = (148 + base - 1) / base;
-    const int max_by_k = pl->total_chunks / 4;
-    if (splits > max_by_k) splits = max_by_k;
-    if (splits > 32) splits = 32;
-    if (splits < 1) splits = 1;
-  }
-  pl->cps = (pl->total_chunks + splits - 1) / splits;
-  pl->splits = (pl->total_chunks + pl->cps - 1) / pl->cps;
-  if (pl->splits > 1) {
-    const size_t need = sdeo_conv_counter_bytes() +
-                        (size_t)best_tiles * pl->n_tiles * pl->splits * kBM * pl->BN * sizeof(float);
-    if (need > a->workspace_bytes || best_tiles * pl->n_tiles > kMaxTilesForCounters) {
-      pl->splits = 1;
-      pl->cps = pl->total_chunks;
+  // ---- N tile ----
+  pl->rows_packed = round_up(a->cout, 16);
+  pl->BN = pick_bn_impl(pl->rows_packed, a->epi_mode);
+  if (a->epi_mode != SDEO_EPI_GEGLU && pl->rows_packed > 128) {
+    // weight-streaming layers with very few M tiles: narrower N tiles put more SMs on the weight stream
+    // (cluster split-K is capped at kMaxCluster K-slices per tile)
+    static const int cand[] = {256, 192, 160, 128, 96, 80, 64};
+    for (int bn : cand) {
+      if (bn > pl->BN || pl->rows_packed % bn != 0) continue;
+      pl->BN = bn;
+      if (best_tiles * (pl->rows_packed / bn) * kMaxCluster >= 120 || pl->total_chunks < 32) break;
     }
   }
+  if (const char* e = getenv("SDEO_FORCE_BN")) {  // tuning aid; GEGLU tiles are fixed by the weight packing
+    const int f = atoi(e);
+    if (a->epi_mode != SDEO_EPI_GEGLU && f >= 16 && f <= 256 && f % 16 == 0 && pl->rows_packed % f == 0) pl->BN = f;
+  }
+  if (pl->BN <= 0 || pl->BN > 256 || (pl->BN % 16) != 0) return false;
+  pl->n_tiles = pl->rows_packed / pl->BN;
+  // ---- split-K over a thread-block cluster ----
+  const int base = best_tiles * pl->n_tiles;
+  int splits = 1;
+  if (base < 120) {
+    splits = (148 + base - 1) / base;
+    const int max_by_k = pl->total_chunks / 4;  // at least 4 K chunks per slice
+    if (splits > max_by_k) splits = max_by_k;
+    if (splits > kMaxCluster) splits = kMaxCluster;
+    if (splits < 1) splits = 1;
+  }
+  if (const char* e = getenv("SDEO_FORCE_SPLITS")) {  // tuning aid (tools/bench_conv.py)
+    const int f = atoi(e);
+    if (f >= 1 && f <= kMaxCluster) splits = f > pl->total_chunks ? pl->total_chunks : f;
+  }
+  pl->cps = (pl->total_chunks + splits - 1) / splits;
+  pl->splits = (pl->total_chunks + pl->cps - 1) / pl->cps;  // every slice gets >= 1 chunk
   // ---- smem / tmem ----
   const int stage_bytes = kATileBytes + pl->BN * 128;
-  int stages = (212 * 1024) / stage_bytes;
+  const int tile_bytes = kBM * (pl->BN + 4) * 4;  // fp32 epilogue tile, aliases the pipeline stages
+  int stages = (208 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages > pl->cps) stages = pl->cps < 2 ? 2 : pl->cps;
   pl->stages = stages;
-  pl->smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + (2 * stages + 1) * 8 + 16;
+  size_t body = (size_t)stages * stage_bytes;
+  if (body < (size_t)tile_bytes) body = tile_bytes;
+  pl->smem_bytes = 1024 /*align slack*/ + 1024 /*barriers*/ + body;
   int tc = 32;
   while (tc < pl->BN) tc *= 2;
   pl->tmem_cols = tc;
-  return true;
+  return pl->smem_bytes <= 227 * 1024;
 }
 
 }  // namespace sdeo
 
 using namespace sdeo;
 
-extern "C" size_t sdeo_conv_counter_bytes(void) { return (size_t)kMaxTilesForCounters * sizeof(unsigned int); }
+extern "C" size_t sdeo_conv_counter_bytes(void) { return 0; }
 
 extern "C" size_t sdeo_conv_workspace_bytes(const sdeo_conv_args* a) {
-  // upper bound: the planner never uses more than ~148+ CTAs worth of partial tiles when splitting
-  (void)a;
-  return sdeo_conv_counter_bytes() + (size_t)320 * kBM * 256 * sizeof(float);
+  (void)a;  // split-K partials live in distributed shared memory; no global scratch is needed any more
+  return 0;
 }
 
 extern "C" int32_t sdeo_packed_rows(int32_t cout) { return round_up(cout, 16); }
@@ -650,15 +696,13 @@ extern "C" int sdeo_conv2d(const sdeo_conv_args* a, void* stream) {
   p.N = a->n; p.Ho = pl.Ho; p.Wo = pl.Wo;
   p.BN = pl.BN; p.cout = a->cout; p.stages = pl.stages; p.tmem_cols = pl.tmem_cols;
   p.epi_mode = a->epi_mode; p.act = a->act; p.y_fp32 = a->y_fp32;
-  p.bias = a->bias; p.emb = a->emb; p.residual = (const __nv_bfloat16*)a->residual; p.ldr = a->ldr;
+  p.bias = a->bias; p.emb = a->emb; p.residual = a->residual; p.ldr = a->ldr;
   p.scale = a->scale; p.y = a->y; p.ldy = a->ldy;
   p.residual_f32 = a->residual_f32;
   p.y2 = (a->y_fp32 && a->epi_mode == SDEO_EPI_NORMAL) ? (__nv_bfloat16*)a->y2 : nullptr;
   p.ldy2 = a->ldy2;
   p.q = (__nv_bfloat16*)a->q; p.k = (__nv_bfloat16*)a->k; p.vt = (__nv_bfloat16*)a->vt;
   p.heads = a->heads; p.dhead = a->dhead; p.tokens = a->tokens; p.ldv = a->ldv; p.qkv_first = a->qkv_first;
-  p.counters = (unsigned int*)a->workspace;
-  p.ws = a->workspace ? (float*)((uint8_t*)a->workspace + sdeo_conv_counter_bytes()) : nullptr;
 
   static bool attr_set = false;
   if (!attr_set) {
@@ -666,7 +710,19 @@ extern "C" int sdeo_conv2d(const sdeo_conv_args* a, void* stream) {
     if (e != cudaSuccess) return set_error(SDEO_ECUDA, cudaGetErrorString(e));
     attr_set = true;
   }
-  dim3 grid((unsigned)(pl.tiles_n * pl.tiles_h * pl.tiles_w), (unsigned)pl.n_tiles, (unsigned)pl.splits);
-  conv_gemm_kernel<<<grid, kConvThreads, pl.smem_bytes, (cudaStream_t)stream>>>(tmA1, tmA2, tmB, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(pl.tiles_n * pl.tiles_h * pl.tiles_w), (unsigned)pl.n_tiles, (unsigned)pl.splits);
+  cfg.blockDim = dim3(kConvThreads);
+  cfg.dynamicSmemBytes = pl.smem_bytes;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = (unsigned)pl.splits;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel, tmA1, tmA2, tmB, p);
+  if (e != cudaSuccess) return set_error(SDEO_ECUDA, cudaGetErrorString(e));
   return check_launch("conv2d");
 }

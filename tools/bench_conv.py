@@ -1,0 +1,91 @@
+"""Micro-benchmark of conv_gemm_kernel on the layer shapes of the 256x384 workload (cond+uncond batch 2).
+python tools/bench_conv.py [--iters N] [--only SUBSTR]. Prints us / TFLOP/s / weight GB/s per shape (CUDA events, warm)."""
+import argparse
+import math
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from stablediffusioneo_b200 import ops  # noqa: E402
+
+BF = torch.bfloat16
+ap = argparse.ArgumentParser()
+ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--only", default="")
+args = ap.parse_args()
+dev = torch.device("cuda:0")
+
+# (name, n, h, w, c1, c2, cout, k, stride, mode)  mode: plain | stream | geglu | qkv
+CASES = [
+    ("conv3 320->320 @32x48 stream", 2, 32, 48, 320, 0, 320, 3, 1, "stream"),
+    ("conv3 320->320 @32x48 emb", 2, 32, 48, 320, 0, 320, 3, 1, "plain32"),
+    ("conv1 320->320 @32x48 stream", 2, 32, 48, 320, 0, 320, 1, 1, "stream"),
+    ("lin   320->960 qkv M=3072", 1, 1, 3072, 320, 0, 960, 1, 1, "qkv"),
+    ("lin   320->2560 geglu M=3072", 1, 1, 3072, 320, 0, 2560, 1, 1, "geglu"),
+    ("lin   1280->320 M=3072 stream", 1, 1, 3072, 1280, 0, 320, 1, 1, "stream"),
+    ("conv3 960->320 @32x48 dual", 2, 32, 48, 640, 320, 320, 3, 1, "plain32"),
+    ("conv3 320->320 s2 @32x48", 2, 32, 48, 320, 0, 320, 3, 2, "stream"),
+    ("conv3 640->640 @16x24 stream", 2, 16, 24, 640, 0, 640, 3, 1, "stream"),
+    ("lin   640->5120 geglu M=768", 1, 1, 768, 640, 0, 5120, 1, 1, "geglu"),
+    ("conv3 1280->1280 @8x12 stream", 2, 8, 12, 1280, 0, 1280, 3, 1, "stream"),
+    ("conv3 2560->1280 @8x12 dual", 2, 8, 12, 1280, 1280, 1280, 3, 1, "plain32"),
+    ("lin   1280->10240 geglu M=192", 1, 1, 192, 1280, 0, 10240, 1, 1, "geglu"),
+    ("lin   5120->1280 M=192 stream", 1, 1, 192, 5120, 0, 1280, 1, 1, "stream"),
+    ("conv3 1280->1280 @4x6 stream", 2, 4, 6, 1280, 0, 1280, 3, 1, "stream"),
+    ("conv1 1280->1280 @4x6 stream", 2, 4, 6, 1280, 0, 1280, 1, 1, "stream"),
+    ("lin   1280->1280 M=2 emb", 1, 1, 2, 1280, 0, 1280, 1, 1, "plain32"),
+    ("conv3 8->320 @32x48 conv_in", 2, 32, 48, 8, 0, 320, 3, 1, "stream"),
+    ("conv3 320->4 @32x48 out", 2, 32, 48, 320, 0, 4, 3, 1, "plain32"),
+]
+
+tot = 0.0
+for name, n, h, w, c1, c2, cout, k, stride, mode in CASES:
+    if args.only and args.only not in name:
+        continue
+    cin = c1 + c2
+    wt = torch.randn((cout, cin, k, k), device=dev) / math.sqrt(cin * k * k)
+    x1 = torch.randn((n, h, w, c1), device=dev).to(BF)
+    x2 = torch.randn((n, h, w, c2), device=dev).to(BF) if c2 else None
+    pad = k // 2
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    bias = torch.randn((cout,), device=dev)
+    kw = dict(bias=bias, stride=stride)
+    if mode == "geglu":
+        pw = ops.pack_conv_weight(wt, geglu=True)
+        kw.update(bias=ops.pack_geglu_bias(bias, pw.geglu_bn), epi_mode=ops.SDEO_EPI_GEGLU)
+    else:
+        pw = ops.pack_conv_weight(wt, c1=c1, c2=c2)
+    if mode == "stream":
+        kw.update(residual=torch.randn((n, ho, wo, cout), device=dev), out_fp32=True, twin=True)
+    elif mode == "plain32":
+        kw.update(emb=torch.randn((n, cout), device=dev), out_fp32=True)
+    elif mode == "qkv":
+        heads, d, t = 8, cout // 24, w
+        q = torch.empty((2 * heads, t // 2, d), dtype=BF, device=dev)
+        kk = torch.empty_like(q)
+        vt = torch.empty((2 * heads, d, t // 2), dtype=BF, device=dev)
+        kw.update(epi_mode=ops.SDEO_EPI_QKV, qkv=(q, kk, vt, heads, d, t // 2, t // 2, 0), bias=None)
+    run = lambda: ops.conv2d(x1, pw, x2=x2, **kw)
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    # capture the launches in a CUDA graph so that host launch overhead (ctypes + tensor-map encodes) is excluded
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(args.iters):
+            run()
+    g.replay()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    g.replay()
+    e.record()
+    torch.cuda.synchronize()
+    us = s.elapsed_time(e) * 1000 / args.iters
+    flops = 2.0 * n * ho * wo * cout * cin * k * k
+    wbytes = pw.data.numel() * 2
+    tot += us
+    print(f"{name:34s} {us:8.1f} us  {flops / us / 1e6:7.1f} TFLOP/s  weights {wbytes / us / 1e3:7.1f} GB/s")
+print(f"sum {tot:.1f} us")
