@@ -575,7 +575,7 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl) {
   const int base = best_tiles * pl->n_tiles;
   int splits = 1;
   if (base < 120) {
-    splits = (148 + base - 1) / base;
+    splits = 148 / base;  // one CTA per SM: never spill into a second wave
     const int max_by_k = pl->total_chunks / 4;  // at least 4 K chunks per slice
     if (splits > max_by_k) splits = max_by_k;
     if (splits > kMaxCluster) splits = kMaxCluster;
