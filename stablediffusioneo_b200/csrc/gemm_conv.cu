@@ -24,7 +24,7 @@
 
 namespace sdeo {
 
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 384;  // warp 0 TMA, warp 1 MMA, warps 2..5 TMEM drain; all 12 warps run epilogue phase 2
 constexpr int kEpiThreads = 128;
 constexpr int kBM = 128;
 constexpr int kBK = 64;
@@ -58,7 +58,13 @@ struct ConvKParams {
   __nv_bfloat16* k;
   __nv_bfloat16* vt;
   int heads, dhead, tokens, ldv, qkv_first;
+  long long* dbg;  // optional per-CTA phase timestamps (SDEO_CONV_DEBUG), 16 slots per CTA
 };
+
+#define SDEO_DBG(slot)                                                                               \
+  do {                                                                                               \
+    if (p.dbg) p.dbg[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (slot)] = clock64(); \
+  } while (0)
 
 struct RowInfo {
   bool valid;
@@ -97,8 +103,53 @@ __device__ __forceinline__ uint4 pack8_bf16(const float* x) {
   return o;
 }
 
+// Compile-time epilogue variants (the hot instantiations carry no runtime flag tests or scalar tails).
+enum { OUT_BF16 = 0, OUT_F32 = 1, OUT_F32_TWIN = 2 };
+enum { RES_NONE = 0, RES_BF16 = 1, RES_F32 = 2 };
+
+// NORMAL epilogue, fast path: cout % 8 == 0 and all row pitches vector-aligned (checked on the host).
+template <int OUT, int RES>
+__device__ __forceinline__ void epi_normal_fast(const ConvKParams& p, long long pix, int batch, int n, float* v,
+                                                const uint4& raw0, const uint4& raw1) {
+  if (p.bias) {
+    float b[8];
+    load8_f32(p.bias + n, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += b[j];
+  }
+  if (p.emb) {
+    float e[8];
+    load8_f32(p.emb + (long long)batch * p.cout + n, e);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += e[j];
+  }
+  if (p.act == SDEO_ACT_SILU) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] *= p.scale;
+  if (RES == RES_F32) {
+    v[0] += __uint_as_float(raw0.x); v[1] += __uint_as_float(raw0.y); v[2] += __uint_as_float(raw0.z);
+    v[3] += __uint_as_float(raw0.w); v[4] += __uint_as_float(raw1.x); v[5] += __uint_as_float(raw1.y);
+    v[6] += __uint_as_float(raw1.z); v[7] += __uint_as_float(raw1.w);
+  } else if (RES == RES_BF16) {
+    float2 a = unpack_bf16x2(raw0.x), b = unpack_bf16x2(raw0.y), c = unpack_bf16x2(raw0.z), d = unpack_bf16x2(raw0.w);
+    v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y; v[4] += c.x; v[5] += c.y; v[6] += d.x; v[7] += d.y;
+  }
+  if (OUT == OUT_BF16) {
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + pix * p.ldy + n) = pack8_bf16(v);
+  } else {
+    float* yp = reinterpret_cast<float*>(p.y) + pix * p.ldy + n;
+    *reinterpret_cast<float4*>(yp) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(yp + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    if (OUT == OUT_F32_TWIN) *reinterpret_cast<uint4*>(p.y2 + pix * p.ldy2 + n) = pack8_bf16(v);
+  }
+}
+
 // NORMAL epilogue of one (row, 8 columns) item: v holds the fp32 accumulators of columns n .. n+7.
-__device__ __forceinline__ void epi_normal_item(const ConvKParams& p, const RowInfo& ri, int n, float* v) {
+__device__ __noinline__ void epi_normal_item(const ConvKParams& p, const RowInfo& ri, int n, float* v, bool res_pref,
+                                                const uint4& raw0, const uint4& raw1) {
   if (n >= p.cout) return;
   const bool full = (n + 8 <= p.cout);
   if (full) {
@@ -129,7 +180,16 @@ __device__ __forceinline__ void epi_normal_item(const ConvKParams& p, const RowI
     if (p.act == SDEO_ACT_SILU) t = silu_f(t);
     v[j] = t * p.scale;
   }
-  if (p.residual) {
+  if (res_pref) {  // residual vector was prefetched by the caller (8 columns, aligned)
+    if (p.residual_f32) {
+      v[0] += __uint_as_float(raw0.x); v[1] += __uint_as_float(raw0.y); v[2] += __uint_as_float(raw0.z);
+      v[3] += __uint_as_float(raw0.w); v[4] += __uint_as_float(raw1.x); v[5] += __uint_as_float(raw1.y);
+      v[6] += __uint_as_float(raw1.z); v[7] += __uint_as_float(raw1.w);
+    } else {
+      float2 a = unpack_bf16x2(raw0.x), b = unpack_bf16x2(raw0.y), c = unpack_bf16x2(raw0.z), d = unpack_bf16x2(raw0.w);
+      v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y; v[4] += c.x; v[5] += c.y; v[6] += d.x; v[7] += d.y;
+    }
+  } else if (p.residual) {
     if (p.residual_f32) {
       const float* rp = reinterpret_cast<const float*>(p.residual) + ri.pix * p.ldr + n;
       if (full && ((p.ldr & 3) == 0)) {
@@ -230,6 +290,8 @@ __device__ __forceinline__ void epi_geglu_item(const ConvKParams& p, const RowIn
   *reinterpret_cast<uint4*>(yp) = pack8_bf16(x);
 }
 
+// MODE: SDEO_EPI_*; OUT / RES: see enums above; FAST: vector-aligned NORMAL epilogue (else the generic item path).
+template <int MODE, int OUT, int RES, bool FAST>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmB, const ConvKParams p) {
@@ -242,6 +304,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   uint64_t* empty_bar = full_bar + 16;
   uint64_t* tmem_full_bar = empty_bar + 16;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  int* row_pix = reinterpret_cast<int*>(smem + 512);  // [128] output pixel index per tile row
   uint8_t* tiles = smem + 1024;
   const int stage_bytes = kATileBytes + p.BN * 128;
 
@@ -261,6 +324,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   if (k_end > p.total_chunks) k_end = p.total_chunks;
   const int nchunks = k_end - k_begin;
 
+  if (threadIdx.x == 0) SDEO_DBG(0);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmB);
@@ -280,6 +344,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (threadIdx.x == 0) SDEO_DBG(1);
 
   const int LD = p.BN + 4;  // fp32 tile row pitch in floats: 16-byte aligned rows, conflict-free 16 B row writes
   float* tile = reinterpret_cast<float*>(tiles);
@@ -317,6 +382,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
+        if (i == 0) SDEO_DBG(2);
         const uint32_t a_addr = smem_u32(tiles + (size_t)s * stage_bytes);
         const uint32_t b_addr = a_addr + kATileBytes;
         const uint64_t a_desc = umma_desc_k_sw128(a_addr);
@@ -330,14 +396,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         tc_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
       }
       tc_commit(tmem_full_bar);    // accumulator complete (all MMAs done => every stage has been consumed)
+      SDEO_DBG(3);
     }
-  } else {
+  } else if (warp < 6) {
     // ===================== epilogue phase 1: TMEM -> fp32 tile in shared memory (thread = row) =====================
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
     const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    {  // output pixel of this tile row (-1: padding row / outside the image), shared with phase 2
+      const int per_img = p.bh * p.bw;
+      const int nl = row / per_img;
+      const int rem = row % per_img;
+      const int hl = rem / p.bw, wl = rem % p.bw;
+      const int nn = n0 + nl, hh = h0 + hl, ww = w0 + wl;
+      const bool ok = (row < p.rows_valid) && (nn < p.N) && (hh < p.Ho) && (ww < p.Wo);
+      row_pix[row] = ok ? (nn * p.Ho + hh) * p.Wo + ww : -1;
+    }
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) SDEO_DBG(4);
     float* trow = tile + (size_t)row * LD;
     int c = 0;
     for (; c + 32 <= p.BN; c += 32) {
@@ -361,6 +438,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
                         __uint_as_float(r[4 * g + 3]));
     }
     tc_fence_before();
+    if (threadIdx.x == 64) SDEO_DBG(5);
   }
 
   // ---- partial tiles complete: CTA-wide (S == 1) or cluster-wide (S > 1) barrier ----
@@ -368,72 +446,137 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   if (p.splits > 1) cluster_sync_all();
   else __syncthreads();
 
-  if (warp >= 2) {
-    // ===================== epilogue phase 2: coalesced items (row, 8 columns) =====================
-    const int et = threadIdx.x - 64;
+  if (threadIdx.x == 64) SDEO_DBG(6);
+  {
+    // ===================== epilogue phase 2: coalesced (row, 8-column) items, all 12 warps =====================
+    // Items are processed U at a time per thread: every load of a batch (tile values from local / distributed
+    // shared memory, residual vectors from global memory) is issued before the first value is used. The item
+    // index advances without divisions (row / column stepping by the constant thread count).
+    constexpr int U = 2;
+    constexpr bool geglu = (MODE == SDEO_EPI_GEGLU);
     const int S = p.splits;
     const int rows_per = (p.rows_valid + S - 1) / S;
     const int r_begin = split * rows_per;
     const int r_end = min(p.rows_valid, r_begin + rows_per);
-    const int per_img = p.bh * p.bw;
-    const bool geglu = (p.epi_mode == SDEO_EPI_GEGLU);
     const int cols_items = geglu ? p.BN / 16 : p.BN / 8;  // items per row
-    const int n_items = (r_end > r_begin ? (r_end - r_begin) : 0) * cols_items;
     const uint32_t tile_saddr = smem_u32(tile);
     const int n_base = n_tile * p.BN;
-    for (int it = et; it < n_items; it += kEpiThreads) {
-      const int row = r_begin + it / cols_items;
-      const int cv = it % cols_items;
-      RowInfo ri;
-      {
-        const int nl = row / per_img;
-        const int rem = row % per_img;
-        const int hl = rem / p.bw, wl = rem % p.bw;
-        const int nn = n0 + nl, hh = h0 + hl, ww = w0 + wl;
-        ri.valid = (nn < p.N) && (hh < p.Ho) && (ww < p.Wo);
-        ri.batch = nn;
-        ri.pix = ((long long)nn * p.Ho + hh) * p.Wo + ww;
+    const int hw_out = p.Ho * p.Wo;
+    const int half = p.BN / 2;
+    const int step_rows = kConvThreads / cols_items, step_cols = kConvThreads % cols_items;
+    int row = r_begin + (int)threadIdx.x / cols_items;
+    int ci = (int)threadIdx.x % cols_items;
+    while (row < r_end) {
+      float v[U][8], g[U][8];
+      uint4 raw0[U], raw1[U];
+      int pixs[U], cols[U];
+      uint32_t offs[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        pixs[u] = -1;
+        cols[u] = ci * 8;
+        offs[u] = (uint32_t)(((size_t)(row < r_end ? row : r_begin) * LD + cols[u]) * sizeof(float));
+        if (row < r_end) {
+          pixs[u] = row_pix[row];
+          if (MODE == SDEO_EPI_NORMAL && FAST && RES != RES_NONE && pixs[u] >= 0) {
+            if (RES == RES_F32) {
+              const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.residual) +
+                                                               (long long)pixs[u] * p.ldr + n_base + cols[u]);
+              raw0[u] = rp[0];
+              raw1[u] = rp[1];
+            } else {
+              raw0[u] = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) +
+                                                        (long long)pixs[u] * p.ldr + n_base + cols[u]);
+            }
+          }
+        }
+        // advance to this thread's next item
+        ci += step_cols;
+        row += step_rows;
+        if (ci >= cols_items) { ci -= cols_items; ++row; }
       }
-      const int col = cv * 8;
-      float v[8], g[8];
       if (S == 1) {
-        const float* src = tile + (size_t)row * LD + col;
-        const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        if (geglu) {
-          const float4 c2 = *reinterpret_cast<const float4*>(src + p.BN / 2), d2 = *reinterpret_cast<const float4*>(src + p.BN / 2 + 4);
-          g[0] = c2.x; g[1] = c2.y; g[2] = c2.z; g[3] = c2.w; g[4] = d2.x; g[5] = d2.y; g[6] = d2.z; g[7] = d2.w;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float* src = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(tile) + offs[u]);
+          const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+          v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w; v[u][4] = b.x; v[u][5] = b.y; v[u][6] = b.z; v[u][7] = b.w;
+          if (geglu) {
+            const float4 c2 = *reinterpret_cast<const float4*>(src + half), d2 = *reinterpret_cast<const float4*>(src + half + 4);
+            g[u][0] = c2.x; g[u][1] = c2.y; g[u][2] = c2.z; g[u][3] = c2.w; g[u][4] = d2.x; g[u][5] = d2.y; g[u][6] = d2.z; g[u][7] = d2.w;
+          }
         }
       } else {
+        // distributed-shared-memory reduction: all S partial vectors of an item are requested before the first
+        // add (remote shared memory latency is ~1k cycles under load), summed in rank order (deterministic)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { v[j] = 0.f; g[j] = 0.f; }
-        const uint32_t off = (uint32_t)(((size_t)row * LD + col) * sizeof(float));
-        for (int s = 0; s < S; ++s) {  // rank order: deterministic
-          const uint32_t base = dsmem_addr(tile_saddr, (uint32_t)s) + off;
-          const float4 a = ld_dsmem_f4(base), b = ld_dsmem_f4(base + 16);
-          v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+        for (int u = 0; u < U; ++u) {
+          float4 a[kMaxCluster], b[kMaxCluster];
+#pragma unroll
+          for (int s = 0; s < kMaxCluster; ++s) {
+            if (s < S) {
+              const uint32_t peer = dsmem_addr(tile_saddr, (uint32_t)s) + offs[u];
+              a[s] = ld_dsmem_f4(peer);
+              b[s] = ld_dsmem_f4(peer + 16);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[u][j] = 0.f;
+#pragma unroll
+          for (int s = 0; s < kMaxCluster; ++s) {
+            if (s < S) {
+              v[u][0] += a[s].x; v[u][1] += a[s].y; v[u][2] += a[s].z; v[u][3] += a[s].w;
+              v[u][4] += b[s].x; v[u][5] += b[s].y; v[u][6] += b[s].z; v[u][7] += b[s].w;
+            }
+          }
           if (geglu) {
-            const float4 c2 = ld_dsmem_f4(base + (uint32_t)(p.BN / 2) * 4u), d2 = ld_dsmem_f4(base + (uint32_t)(p.BN / 2) * 4u + 16);
-            g[0] += c2.x; g[1] += c2.y; g[2] += c2.z; g[3] += c2.w; g[4] += d2.x; g[5] += d2.y; g[6] += d2.z; g[7] += d2.w;
+#pragma unroll
+            for (int s = 0; s < kMaxCluster; ++s) {
+              if (s < S) {
+                const uint32_t peer = dsmem_addr(tile_saddr, (uint32_t)s) + offs[u] + (uint32_t)half * 4u;
+                a[s] = ld_dsmem_f4(peer);
+                b[s] = ld_dsmem_f4(peer + 16);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[u][j] = 0.f;
+#pragma unroll
+            for (int s = 0; s < kMaxCluster; ++s) {
+              if (s < S) {
+                g[u][0] += a[s].x; g[u][1] += a[s].y; g[u][2] += a[s].z; g[u][3] += a[s].w;
+                g[u][4] += b[s].x; g[u][5] += b[s].y; g[u][6] += b[s].z; g[u][7] += b[s].w;
+              }
+            }
           }
         }
       }
-      if (!ri.valid) continue;
-      if (geglu) {
-        epi_geglu_item(p, ri, n_tile * (p.BN / 2) + col, n_base + col, n_base + p.BN / 2 + col, v, g);
-      } else if (p.epi_mode == SDEO_EPI_QKV) {
-        epi_qkv_item(p, ri, n_base + col, v);
-      } else {
-        epi_normal_item(p, ri, n_base + col, v);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (pixs[u] < 0) continue;
+        const int col = cols[u];
+        if (MODE == SDEO_EPI_GEGLU) {
+          RowInfo ri; ri.valid = true; ri.pix = pixs[u]; ri.batch = 0;
+          epi_geglu_item(p, ri, n_tile * half + col, n_base + col, n_base + half + col, v[u], g[u]);
+        } else if (MODE == SDEO_EPI_QKV) {
+          RowInfo ri; ri.valid = true; ri.pix = pixs[u]; ri.batch = 0;
+          epi_qkv_item(p, ri, n_base + col, v[u]);
+        } else if (FAST) {
+          epi_normal_fast<OUT, RES>(p, (long long)pixs[u], p.emb ? pixs[u] / hw_out : 0, n_base + col, v[u], raw0[u], raw1[u]);
+        } else {
+          RowInfo ri; ri.valid = true; ri.pix = pixs[u]; ri.batch = p.emb ? pixs[u] / hw_out : 0;
+          epi_normal_item(p, ri, n_base + col, v[u], false, raw0[u], raw1[u]);
+        }
       }
     }
   }
 
+  if (threadIdx.x == 64) SDEO_DBG(7);
   // ---- teardown: nobody may exit while a peer still reads its tile through DSMEM ----
   tc_fence_before();
   __syncwarp();
   if (p.splits > 1) cluster_sync_all();
   else __syncthreads();
+  if (threadIdx.x == 64) SDEO_DBG(8);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
@@ -703,12 +846,46 @@ extern "C" int sdeo_conv2d(const sdeo_conv_args* a, void* stream) {
   p.ldy2 = a->ldy2;
   p.q = (__nv_bfloat16*)a->q; p.k = (__nv_bfloat16*)a->k; p.vt = (__nv_bfloat16*)a->vt;
   p.heads = a->heads; p.dhead = a->dhead; p.tokens = a->tokens; p.ldv = a->ldv; p.qkv_first = a->qkv_first;
+  p.dbg = nullptr;
+  if (const char* e = getenv("SDEO_CONV_DEBUG")) p.dbg = (long long*)strtoull(e, nullptr, 16);
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return set_error(SDEO_ECUDA, cudaGetErrorString(e));
-    attr_set = true;
+  // ---- pick the kernel instantiation ----
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvKParams);
+  KernelFn fn = nullptr;
+  if (a->epi_mode == SDEO_EPI_GEGLU) {
+    fn = conv_gemm_kernel<SDEO_EPI_GEGLU, OUT_BF16, RES_NONE, true>;
+  } else if (a->epi_mode == SDEO_EPI_QKV) {
+    fn = conv_gemm_kernel<SDEO_EPI_QKV, OUT_BF16, RES_NONE, true>;
+  } else {
+    const int out_kind = !a->y_fp32 ? OUT_BF16 : (p.y2 ? OUT_F32_TWIN : OUT_F32);
+    const int res_kind = !a->residual ? RES_NONE : (a->residual_f32 ? RES_F32 : RES_BF16);
+    bool fast = (a->cout % 8 == 0);
+    fast = fast && (out_kind == OUT_BF16 ? (a->ldy % 8 == 0) : (a->ldy % 4 == 0));
+    if (out_kind == OUT_F32_TWIN) fast = fast && (a->ldy2 % 8 == 0);
+    if (res_kind == RES_BF16) fast = fast && (a->ldr % 8 == 0);
+    if (res_kind == RES_F32) fast = fast && (a->ldr % 4 == 0);
+    if (!fast) {
+      fn = conv_gemm_kernel<SDEO_EPI_NORMAL, OUT_BF16, RES_NONE, false>;
+    } else {
+#define SDEO_PICK(O, R) if (out_kind == O && res_kind == R) fn = conv_gemm_kernel<SDEO_EPI_NORMAL, O, R, true>;
+      SDEO_PICK(OUT_BF16, RES_NONE) SDEO_PICK(OUT_BF16, RES_BF16) SDEO_PICK(OUT_BF16, RES_F32)
+      SDEO_PICK(OUT_F32, RES_NONE) SDEO_PICK(OUT_F32, RES_BF16) SDEO_PICK(OUT_F32, RES_F32)
+      SDEO_PICK(OUT_F32_TWIN, RES_NONE) SDEO_PICK(OUT_F32_TWIN, RES_BF16) SDEO_PICK(OUT_F32_TWIN, RES_F32)
+#undef SDEO_PICK
+    }
+  }
+  if (!fn) return set_error(SDEO_EINVAL, "conv2d: no kernel instantiation");
+  {
+    // opt in to > 48 KB of dynamic shared memory, once per instantiation
+    static KernelFn configured[16];
+    static int n_configured = 0;
+    bool seen = false;
+    for (int i = 0; i < n_configured; ++i) seen = seen || (configured[i] == fn);
+    if (!seen) {
+      cudaError_t e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return set_error(SDEO_ECUDA, cudaGetErrorString(e));
+      if (n_configured < 16) configured[n_configured++] = fn;
+    }
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(pl.tiles_n * pl.tiles_h * pl.tiles_w), (unsigned)pl.n_tiles, (unsigned)pl.splits);
@@ -722,7 +899,7 @@ extern "C" int sdeo_conv2d(const sdeo_conv_args* a, void* stream) {
   attr[0].val.clusterDim.z = (unsigned)pl.splits;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel, tmA1, tmA2, tmB, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, fn, tmA1, tmA2, tmB, p);
   if (e != cudaSuccess) return set_error(SDEO_ECUDA, cudaGetErrorString(e));
   return check_launch("conv2d");
 }

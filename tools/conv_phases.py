@@ -1,0 +1,53 @@
+"""Per-CTA phase timing of conv_gemm_kernel via the SDEO_CONV_DEBUG clock64 slots. python tools/conv_phases.py [SUBSTR]"""
+import math
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from stablediffusioneo_b200 import ops  # noqa: E402
+
+BF = torch.bfloat16
+dev = torch.device("cuda:0")
+CASES = {
+    "out": (2, 32, 48, 320, 4, 3, "plain32"),
+    "conv1": (2, 32, 48, 320, 320, 1, "stream"),
+    "conv3": (2, 32, 48, 320, 320, 3, "stream"),
+    "mid": (2, 8, 12, 1280, 1280, 3, "stream"),
+    "c1_plain": (2, 32, 48, 320, 320, 1, "plain"),
+    "c1_res16": (2, 32, 48, 320, 320, 1, "res16"),
+    "c1_f32": (2, 32, 48, 320, 320, 1, "plain32"),
+    "c1_f32res": (2, 32, 48, 320, 320, 1, "f32res"),
+}
+names = sys.argv[1:] or list(CASES)
+for name in names:
+    n, h, w, cin, cout, k, mode = CASES[name]
+    wt = torch.randn((cout, cin, k, k), device=dev) / math.sqrt(cin * k * k)
+    x = torch.randn((n, h, w, cin), device=dev).to(BF)
+    pw = ops.pack_conv_weight(wt)
+    kw = dict(bias=torch.randn((cout,), device=dev))
+    if mode == "stream":
+        kw.update(residual=torch.randn((n, h, w, cout), device=dev), out_fp32=True, twin=True)
+    elif mode == "f32res":
+        kw.update(residual=torch.randn((n, h, w, cout), device=dev), out_fp32=True)
+    elif mode == "res16":
+        kw.update(residual=torch.randn((n, h, w, cout), device=dev).to(BF))
+    elif mode == "plain32":
+        kw.update(out_fp32=True)
+    dbg = torch.zeros((4096, 16), dtype=torch.int64, device=dev)
+    for _ in range(3):
+        ops.conv2d(x, pw, **kw)
+    torch.cuda.synchronize()
+    os.environ["SDEO_CONV_DEBUG"] = hex(dbg.data_ptr())
+    ops.conv2d(x, pw, **kw)
+    torch.cuda.synchronize()
+    del os.environ["SDEO_CONV_DEBUG"]
+    d = dbg.cpu()
+    used = d[d[:, 0] != 0]
+    rel = (used - used[:, :1]).float()
+    lab = ["start", "prologue", "first data", "mma issued", "acc ready", "phase1", "barrier", "phase2", "end"]
+    print(f"== {name}: {used.shape[0]} CTAs; cycles since CTA start (median / max)")
+    for i in range(1, 9):
+        col = rel[:, i]
+        print(f"   {lab[i]:11s} {col.median().item():9.0f} {col.max().item():9.0f}")
