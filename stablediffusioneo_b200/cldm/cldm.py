@@ -156,27 +156,38 @@ class ControlNet(nn.Module):
             i += 2 if fused else 1
         return h
 
-    def run(self, x, guided_hint, emb, context, scales=None, add_to=None, only_mid=False):
-        """cldm/cldm.py:284-305. Returns 13 tensors: scale_i * zero_conv_i(h_i) [+ add_to[i] when given]
-        (only_mid: entries 0..11 are add_to[i] untouched)."""
-        scales = [1.0] * (len(self.zero_convs) + 1) if scales is None else list(scales)
-        outs = []
+    def run_body(self, x, guided_hint, emb, context):
+        """The encoder copy without its zero convs: returns the 13 feature maps h_i the zero convs read
+        (12 input blocks + middle block). Independent of the UNet, so it can run on its own stream."""
+        feats = []
         h = x
-        for i, (module, zero_conv) in enumerate(zip(self.input_blocks, self.zero_convs)):
+        for i, module in enumerate(self.input_blocks):
             if i == 0:
                 # h = conv_in(x) + guided_hint (cldm/cldm.py:294-297): residual add in the conv epilogue
                 h = module[0].run(h, residual=guided_hint, stream=util.STREAM_FP32)
             else:
                 h = module.run(h, emb, context)
-            if only_mid and add_to is not None:
+            feats.append(h)
+        feats.append(self.middle_block.run(h, emb, context))
+        return feats
+
+    def run_zero_convs(self, feats, scales=None, add_to=None, only_mid=False):
+        """13 outputs: scale_i * zero_conv_i(h_i) [+ add_to[i]] (only_mid: entries 0..11 are add_to[i] untouched)."""
+        scales = [1.0] * (len(self.zero_convs) + 1) if scales is None else list(scales)
+        convs = [z[0] for z in self.zero_convs] + [self.middle_block_out[0]]
+        outs = []
+        for i, (conv, h) in enumerate(zip(convs, feats)):
+            last = i == len(convs) - 1
+            if only_mid and add_to is not None and not last:
                 outs.append(add_to[i])
             else:
-                outs.append(zero_conv[0].run(h, scale=scales[i], residual=add_to[i] if add_to is not None else None,
-                                             stream=util.STREAM_FP32))
-        h = self.middle_block.run(h, emb, context)
-        outs.append(self.middle_block_out[0].run(h, scale=scales[-1], residual=add_to[-1] if add_to is not None else None,
-                                                 stream=util.STREAM_FP32))
+                outs.append(conv.run(h, scale=scales[i], residual=add_to[i] if add_to is not None else None,
+                                     stream=util.STREAM_FP32))
         return outs
+
+    def run(self, x, guided_hint, emb, context, scales=None, add_to=None, only_mid=False):
+        """cldm/cldm.py:284-305 on internal tensors."""
+        return self.run_zero_convs(self.run_body(x, guided_hint, emb, context), scales, add_to, only_mid)
 
     def forward(self, x, hint, timesteps, context, **kwargs):
         ctx = _ctx_internal(context)

@@ -233,6 +233,7 @@ class _Engine:
         b, c, h, w = x_T.shape
         self.dup = 2 if uncond is not None else 1
         nb = self.dup * b
+        self.side_stream = torch.cuda.Stream(device=dev)
         self.x_lat = torch.empty((b, c, h, w), dtype=torch.float32, device=dev)
         self.x_keep = torch.empty_like(self.x_lat)
         self.pred_x0 = torch.empty_like(self.x_lat)
@@ -305,13 +306,22 @@ class _Engine:
         x = self.x_in.permute(0, 3, 1, 2)
         t_emb = ops.timestep_embedding(self.ts_table, nb, unet.model_channels, step_idx=self.step_ctr)
         emb_u = unet.time_embed[2].run(unet.time_embed[0].run(t_emb, act=ops.SDEO_ACT_SILU))
-        hs, h = unet.run_encoder(x, emb_u, self.ctx)
         if self.has_hint:
+            # the UNet encoder and the ControlNet body are independent: run them on two streams (captured as two
+            # branches of the step graph), then apply the 13 zero convs onto the UNet skips
             cn = m.control_model
-            emb_c = cn.time_embed[2].run(cn.time_embed[0].run(t_emb, act=ops.SDEO_ACT_SILU))
-            outs = cn.run(x, self.guided, emb_c, self.ctx, scales=m.control_scales, add_to=hs + [h],
-                          only_mid=m.only_mid_control)
+            main = torch.cuda.current_stream()
+            side = self.side_stream
+            side.wait_stream(main)
+            with torch.cuda.stream(side), ops.workspace_slot(1):
+                emb_c = cn.time_embed[2].run(cn.time_embed[0].run(t_emb, act=ops.SDEO_ACT_SILU))
+                feats = cn.run_body(x, self.guided, emb_c, self.ctx)
+            hs, h = unet.run_encoder(x, emb_u, self.ctx)
+            main.wait_stream(side)
+            outs = cn.run_zero_convs(feats, scales=m.control_scales, add_to=hs + [h], only_mid=m.only_mid_control)
             hs, h = outs[:-1], outs[-1]
+        else:
+            hs, h = unet.run_encoder(x, emb_u, self.ctx)
         eps = nhwc(unet.run_decoder(h, hs, emb_u, self.ctx))          # fp32 [nb, h, w, 4]
         eps_c = eps[:b]
         eps_u = eps[b:] if self.dup == 2 else None

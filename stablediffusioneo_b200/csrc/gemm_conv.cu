@@ -452,7 +452,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     // Items are processed U at a time per thread: every load of a batch (tile values from local / distributed
     // shared memory, residual vectors from global memory) is issued before the first value is used. The item
     // index advances without divisions (row / column stepping by the constant thread count).
-    constexpr int U = 2;
+    constexpr int U = 2;  // measured: U = 4 is slower (register pressure, longer dependent chains in split mode)
     constexpr bool geglu = (MODE == SDEO_EPI_GEGLU);
     const int S = p.splits;
     const int rows_per = (p.rows_valid + S - 1) / S;
@@ -717,7 +717,7 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl) {
   // ---- split-K over a thread-block cluster ----
   const int base = best_tiles * pl->n_tiles;
   int splits = 1;
-  if (base < 120) {
+  if (base <= 40) {  // measured: with >= 48 tiles the cluster reduction costs more than the extra SMs give back
     splits = 148 / base;  // one CTA per SM: never spill into a second wave
     const int max_by_k = pl->total_chunks / 4;  // at least 4 K chunks per slice
     if (splits > max_by_k) splits = max_by_k;
