@@ -266,10 +266,49 @@ __device__ __forceinline__ void epi_qkv_item(const ConvKParams& p, const RowInfo
   if (which < 2) {
     __nv_bfloat16* dst = (which == 0 ? p.q : p.k) + (bh * p.tokens + tok) * p.dhead + dd;
     *reinterpret_cast<uint4*>(dst) = pack8_bf16(v);
-  } else {
-    __nv_bfloat16* dst = p.vt + (bh * p.dhead + dd) * p.ldv + tok;
+  }
+  // which == 2 (v): written transposed by qkv_store_vt() with a token-major item mapping
+}
+
+// V^T part of the QKV epilogue: item = (8 consecutive token rows, one v column) -> ONE 16-byte store into
+// vt[b*heads + head][dd][tok .. tok+7]. Lanes run along the columns so the shared-memory reads are conflict-free.
+__device__ __forceinline__ void qkv_store_vt(const ConvKParams& p, const float* tile, int LD, const int* row_pix,
+                                             int n_base, int tid, int nthreads) {
+  const int C = p.heads * p.dhead;
+  int vb = (2 - p.qkv_first) * C, ve = (3 - p.qkv_first) * C;  // global column range holding v
+  if (vb < n_base) vb = n_base;
+  if (ve > n_base + p.BN) ve = n_base + p.BN;
+  if (ve > p.cout) ve = p.cout;
+  const int ncols = ve - vb;
+  if (ncols <= 0 || !p.vt) return;
+  const int groups = (p.rows_valid + 7) / 8;
+  for (int it = tid; it < groups * ncols; it += nthreads) {
+    const int c = it % ncols, g = it / ncols;
+    const int n = vb + c;
+    const int nc = n - (2 - p.qkv_first) * C;
+    const int head = nc / p.dhead, dd = nc % p.dhead;
+    const float bias = p.bias ? __ldg(p.bias + n) : 0.f;
+    float x[8];
+    int pix[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dst[(long long)j * p.ldv] = __float2bfloat16(v[j]);
+    for (int i = 0; i < 8; ++i) {
+      const int r = g * 8 + i;
+      pix[i] = r < p.rows_valid ? row_pix[r] : -1;
+      x[i] = tile[(size_t)r * LD + (n - n_base)] + bias;
+    }
+    const int tok0 = pix[0] >= 0 ? pix[0] % p.tokens : 0;
+    const bool vec = pix[0] >= 0 && pix[7] == pix[0] + 7 && tok0 + 7 < p.tokens && (tok0 & 7) == 0;
+    if (vec) {
+      const long long bh = (long long)(pix[0] / p.tokens) * p.heads + head;
+      *reinterpret_cast<uint4*>(p.vt + (bh * p.dhead + dd) * p.ldv + tok0) = pack8_bf16(x);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (pix[i] < 0) continue;
+        const long long bh = (long long)(pix[i] / p.tokens) * p.heads + head;
+        p.vt[(bh * p.dhead + dd) * p.ldv + pix[i] % p.tokens] = __float2bfloat16(x[i]);
+      }
+    }
   }
 }
 
@@ -568,6 +607,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         }
       }
     }
+    if (MODE == SDEO_EPI_QKV) qkv_store_vt(p, tile, LD, row_pix, n_base, (int)threadIdx.x, kConvThreads);  // S == 1
   }
 
   if (threadIdx.x == 64) SDEO_DBG(7);
@@ -717,7 +757,7 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl) {
   // ---- split-K over a thread-block cluster ----
   const int base = best_tiles * pl->n_tiles;
   int splits = 1;
-  if (base <= 40) {  // measured: with >= 48 tiles the cluster reduction costs more than the extra SMs give back
+  if (base <= 40 && a->epi_mode != SDEO_EPI_QKV) {  // (the V^T scatter reads the local tile only) measured: with >= 48 tiles the cluster reduction costs more than the extra SMs give back
     splits = 148 / base;  // one CTA per SM: never spill into a second wave
     const int max_by_k = pl->total_chunks / 4;  // at least 4 K chunks per slice
     if (splits > max_by_k) splits = max_by_k;
@@ -726,7 +766,7 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl) {
   }
   if (const char* e = getenv("SDEO_FORCE_SPLITS")) {  // tuning aid (tools/bench_conv.py)
     const int f = atoi(e);
-    if (f >= 1 && f <= kMaxCluster) splits = f > pl->total_chunks ? pl->total_chunks : f;
+    if (f >= 1 && f <= kMaxCluster && a->epi_mode != SDEO_EPI_QKV) splits = f > pl->total_chunks ? pl->total_chunks : f;
   }
   pl->cps = (pl->total_chunks + splits - 1) / splits;
   pl->splits = (pl->total_chunks + pl->cps - 1) / pl->cps;  // every slice gets >= 1 chunk
