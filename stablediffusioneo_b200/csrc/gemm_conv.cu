@@ -59,6 +59,7 @@ struct ConvKParams {
   __nv_bfloat16* vt;
   int heads, dhead, tokens, ldv, qkv_first;
   long long* dbg;  // optional per-CTA phase timestamps (SDEO_CONV_DEBUG), 16 slots per CTA
+  float* ws;       // split-K partial tiles in global memory (L2-resident); nullptr: reduce through DSMEM instead
 };
 
 #define SDEO_DBG(slot)                                                                               \
@@ -482,6 +483,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
 
   // ---- partial tiles complete: CTA-wide (S == 1) or cluster-wide (S > 1) barrier ----
   __syncwarp();
+  const size_t ws_tile_floats = (size_t)kBM * LD;
+  const float* ws_tile0 = nullptr;  // partial of K-slice 0 of this output tile
+  if (p.splits > 1 && p.ws) {
+    // publish this CTA's partial tile to the L2-resident workspace with coalesced 16-byte stores: the reduction then
+    // reads all S partials with many independent global loads in flight (remote shared memory was measured slower)
+    __syncthreads();
+    const size_t tile_linear = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+    float* ws_tile = p.ws + tile_linear * p.splits * ws_tile_floats;
+    ws_tile0 = ws_tile;
+    float4* dst = reinterpret_cast<float4*>(ws_tile + (size_t)split * ws_tile_floats);
+    const float4* src = reinterpret_cast<const float4*>(tile);
+    const int nvec = p.rows_valid * LD / 4;
+    for (int i = threadIdx.x; i < nvec; i += kConvThreads) dst[i] = src[i];
+    __threadfence();
+  }
   if (p.splits > 1) cluster_sync_all();
   else __syncthreads();
 
@@ -554,9 +570,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
 #pragma unroll
           for (int s = 0; s < kMaxCluster; ++s) {
             if (s < S) {
-              const uint32_t peer = dsmem_addr(tile_saddr, (uint32_t)s) + offs[u];
-              a[s] = ld_dsmem_f4(peer);
-              b[s] = ld_dsmem_f4(peer + 16);
+              if (ws_tile0) {
+                const float4* gp = reinterpret_cast<const float4*>(
+                    reinterpret_cast<const uint8_t*>(ws_tile0 + (size_t)s * ws_tile_floats) + offs[u]);
+                a[s] = __ldcg(gp);
+                b[s] = __ldcg(gp + 1);
+              } else {
+                const uint32_t peer = dsmem_addr(tile_saddr, (uint32_t)s) + offs[u];
+                a[s] = ld_dsmem_f4(peer);
+                b[s] = ld_dsmem_f4(peer + 16);
+              }
             }
           }
 #pragma unroll
@@ -572,9 +595,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
 #pragma unroll
             for (int s = 0; s < kMaxCluster; ++s) {
               if (s < S) {
-                const uint32_t peer = dsmem_addr(tile_saddr, (uint32_t)s) + offs[u] + (uint32_t)half * 4u;
-                a[s] = ld_dsmem_f4(peer);
-                b[s] = ld_dsmem_f4(peer + 16);
+                if (ws_tile0) {
+                  const float4* gp = reinterpret_cast<const float4*>(
+                      reinterpret_cast<const uint8_t*>(ws_tile0 + (size_t)s * ws_tile_floats) + offs[u] + (size_t)half * 4u);
+                  a[s] = __ldcg(gp);
+                  b[s] = __ldcg(gp + 1);
+                } else {
+                  const uint32_t peer = dsmem_addr(tile_saddr, (uint32_t)s) + offs[u] + (uint32_t)half * 4u;
+                  a[s] = ld_dsmem_f4(peer);
+                  b[s] = ld_dsmem_f4(peer + 16);
+                }
               }
             }
 #pragma unroll
@@ -786,6 +816,8 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl) {
   return pl->smem_bytes <= 227 * 1024;
 }
 
+static inline int cfg_tiles(const ConvPlan& pl) { return pl.tiles_n * pl.tiles_h * pl.tiles_w * pl.n_tiles; }
+
 }  // namespace sdeo
 
 using namespace sdeo;
@@ -793,8 +825,8 @@ using namespace sdeo;
 extern "C" size_t sdeo_conv_counter_bytes(void) { return 0; }
 
 extern "C" size_t sdeo_conv_workspace_bytes(const sdeo_conv_args* a) {
-  (void)a;  // split-K partials live in distributed shared memory; no global scratch is needed any more
-  return 0;
+  (void)a;  // split-K partial tiles: at most one 128 x (256+4) fp32 tile per resident CTA (one CTA per SM, 148 SMs)
+  return (size_t)160 * kBM * (256 + 4) * sizeof(float);
 }
 
 extern "C" int32_t sdeo_packed_rows(int32_t cout) { return round_up(cout, 16); }
@@ -888,6 +920,11 @@ extern "C" int sdeo_conv2d(const sdeo_conv_args* a, void* stream) {
   p.heads = a->heads; p.dhead = a->dhead; p.tokens = a->tokens; p.ldv = a->ldv; p.qkv_first = a->qkv_first;
   p.dbg = nullptr;
   if (const char* e = getenv("SDEO_CONV_DEBUG")) p.dbg = (long long*)strtoull(e, nullptr, 16);
+  p.ws = nullptr;
+  if (pl.splits > 1 && a->workspace && !getenv("SDEO_SPLITK_DSMEM")) {
+    const size_t need = (size_t)cfg_tiles(pl) * pl.splits * kBM * (pl.BN + 4) * sizeof(float);
+    if (need <= a->workspace_bytes) p.ws = (float*)a->workspace;
+  }
 
   // ---- pick the kernel instantiation ----
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvKParams);

@@ -156,10 +156,12 @@ gn_apply_kernel(const T* __restrict__ x1, const T* __restrict__ x2,
 }
 
 static void gn_geometry(int n, int hw, int* chunks, int* ppc) {
-  int want = (148 * 4 + n - 1) / n;
+  // about 1.5 CTAs per SM over the batch, and at least 16 pixels per CTA (these tensors are small: per-CTA fixed
+  // costs and the apply kernel's per-CTA fold over the chunk partials dominate otherwise)
+  int want = (148 * 3 / 2 + n - 1) / n;
   if (want < 1) want = 1;
   int p = (hw + want - 1) / want;
-  if (p < 8) p = hw < 8 ? hw : 8;
+  if (p < 16) p = hw < 16 ? hw : 16;
   *ppc = p;
   *chunks = (hw + p - 1) / p;
 }
