@@ -787,7 +787,7 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl) {
   // ---- split-K over a thread-block cluster ----
   const int base = best_tiles * pl->n_tiles;
   int splits = 1;
-  if (base <= 40 && a->epi_mode != SDEO_EPI_QKV) {  // (the V^T scatter reads the local tile only) measured: with >= 48 tiles the cluster reduction costs more than the extra SMs give back
+  if ((base <= 40 || (pl->total_chunks >= 80 && base <= 74)) && a->epi_mode != SDEO_EPI_QKV) {  // (the V^T scatter reads the local tile only) measured: with >= 48 tiles the cluster reduction costs more than the extra SMs give back
     splits = 148 / base;  // one CTA per SM: never spill into a second wave
     const int max_by_k = pl->total_chunks / 4;  // at least 4 K chunks per slice
     if (splits > max_by_k) splits = max_by_k;

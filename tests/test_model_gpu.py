@@ -168,3 +168,56 @@ def test_sd15_sample_and_decode(sd15, cuda_device):
     print(f"final image vs reference: mean abs diff {diff.mean():.3f} / 255, PSNR {psnr:.1f} dB")
     # PD (Inception features, compute_score.py:11-17) needs pytorch_fid weights that are not in the image; PSNR stands in.
     assert psnr > 25.0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# other BASELINE configs as parity cases (oracle computed on the fly on the host CPU; sizes it finishes in seconds)
+# ---------------------------------------------------------------------------------------------------------------
+def test_sd15_512x512_eps_vs_oracle(sd15, cuda_device):
+    """BASELINE configs[2] shape (512x512 -> latent 64x64, 4096 tokens at the top level): one eps prediction."""
+    from helpers import oracle_weights
+    model, _ = sd15
+    sd_unet, sd_cn, _ = oracle_weights(O.SD15, O.SD15_VAE)
+    x_T, cond, _ = O.make_inputs(O.SD15, 1, 64, 64)
+    ts = torch.full((1,), 501, dtype=torch.long)
+    with torch.no_grad():
+        ref = O.apply_model(sd_unet, sd_cn, O.SD15, x_T, ts, cond)
+    dev = cuda_device
+    cond_d = {"c_concat": [cond["c_concat"][0].to(dev)], "c_crossattn": [cond["c_crossattn"][0].to(dev)]}
+    eps = model.apply_model(x_T.to(dev), ts.to(dev), cond_d)
+    err = rel_l2(eps, ref)
+    print("512x512 eps rel L2 vs oracle:", err)
+    assert err < EPS_TOL
+
+
+def test_sd15_batch2_matches_batch1(sd15, cuda_device):
+    """Samples are independent (no cross-sample op): a batch of 2 different inputs equals two batch-1 calls."""
+    model, _ = sd15
+    dev = cuda_device
+    xa, ca, _ = inputs_on(O.SD15, 32, 48, dev, hint=canny_hint())
+    g = torch.Generator().manual_seed(5)
+    xb = torch.randn((1, 4, 32, 48), generator=g).to(dev)
+    ctxb = torch.randn((1, 77, 768), generator=g).to(dev)
+    hb = (torch.rand((1, 1, 256, 384), generator=g) > 0.8).float().expand(-1, 3, -1, -1).contiguous().to(dev)
+    cb = {"c_concat": [hb], "c_crossattn": [ctxb]}
+    t = torch.tensor([951, 301], dtype=torch.long, device=dev)
+    both = {"c_concat": [torch.cat([ca["c_concat"][0], hb])], "c_crossattn": [torch.cat([ca["c_crossattn"][0], ctxb])]}
+    e2 = model.apply_model(torch.cat([xa, xb]), t, both)
+    ea = model.apply_model(xa, t[:1], ca)
+    eb = model.apply_model(xb, t[1:], cb)
+    assert rel_l2(e2[:1], ea) < 2e-3 and rel_l2(e2[1:], eb) < 2e-3
+
+
+def test_vae_decode_512_vs_oracle(sd15, cuda_device):
+    """BASELINE configs[4] shape at batch 1: VAE decode of a 64x64 latent (512x512 image) vs the CPU oracle."""
+    from helpers import oracle_weights
+    model, _ = sd15
+    _, _, sd_vae = oracle_weights(O.SD15, O.SD15_VAE)
+    z = torch.randn((1, 4, 64, 64), generator=torch.Generator().manual_seed(3)) * 0.18215 * 4.0
+    with torch.no_grad():
+        ref = O.vae_decode(sd_vae, O.SD15_VAE, z)
+    img = model.decode_first_stage(z.to(cuda_device))
+    assert img.shape == (1, 3, 512, 512)
+    err = rel_l2(img, ref)
+    print("VAE 512x512 decode rel L2 vs oracle:", err)
+    assert err < 2e-2
