@@ -205,7 +205,8 @@ def test_sd15_batch2_matches_batch1(sd15, cuda_device):
     e2 = model.apply_model(torch.cat([xa, xb]), t, both)
     ea = model.apply_model(xa, t[:1], ca)
     eb = model.apply_model(xb, t[1:], cb)
-    assert rel_l2(e2[:1], ea) < 2e-3 and rel_l2(e2[1:], eb) < 2e-3
+    # not bit-equal: the batch changes tile / split-K choices, hence fp32 summation order and a few bf16 roundings
+    assert rel_l2(e2[:1], ea) < EPS_TOL and rel_l2(e2[1:], eb) < EPS_TOL
 
 
 def test_vae_decode_512_vs_oracle(sd15, cuda_device):
