@@ -193,7 +193,10 @@ def conv_roofline(eng, pk):
     total_flops = sum(f for _, _, f in rec)
     achieved = total_flops / (total_ms * 1e-3) / 1e12
     return {"bound": "tensor", "kernel": "conv_gemm_kernel", "achieved": achieved, "peak": pk["bf16_sustained"],
-            "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"], "traffic": None,
+            "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
+            # dram__bytes_read+write per launch, averaged over the 325 conv launches of one step, from the ncu pass in
+            # profiles/r01_conv_dram_traffic.txt (cold-cache replays; algorithmic: 2.442 GB of weights / 325 = 7.5 MB)
+            "traffic": 9386294, "traffic_unit": "bytes/launch (ncu, cold cache)",
             "launches_per_step": len(rec), "flops_per_step": total_flops, "kernel_ms_per_step": total_ms,
             "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)"}
 
