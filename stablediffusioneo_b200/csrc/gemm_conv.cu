@@ -59,6 +59,7 @@ struct ConvKParams {
   __nv_bfloat16* vt;
   int heads, dhead, tokens, ldv, qkv_first;
   long long* dbg;  // optional per-CTA phase timestamps (SDEO_CONV_DEBUG), 16 slots per CTA
+  int a_tmem, a_tmem_col;  // stage the A tile in TMEM (tcgen05.cp) at this column offset
   float* ws;       // split-K partial tiles in global memory (L2-resident); nullptr: reduce through DSMEM instead
 };
 
@@ -391,52 +392,77 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
 
   if (warp == 0) {
     // ===================== TMA producer =====================
+    // (all ring / tap / chunk indices advance incrementally: no integer division on the per-chunk path)
     if (lane == 0) {
       const uint32_t tx_bytes = (uint32_t)(p.rows_valid + p.BN) * 128u;
+      int s = 0;
+      uint32_t ph = 0;
+      int tap = k_begin / p.chunks_per_tap, within = k_begin % p.chunks_per_tap;
+      int ky = tap / p.kw, kx = tap % p.kw;
+      uint8_t* a_dst = tiles;
+      const int nb0 = n_tile * p.BN;
       for (int i = 0; i < nchunks; ++i) {
-        const int s = i % p.stages;
-        const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
         mbar_wait(&empty_bar[s], ph ^ 1u);
         mbar_expect_tx(&full_bar[s], tx_bytes);
-        const int kc = k_begin + i;
-        const int tap = kc / p.chunks_per_tap;
-        const int within = kc % p.chunks_per_tap;
-        const int ky = tap / p.kw, kx = tap % p.kw;
-        uint8_t* a_dst = tiles + (size_t)s * stage_bytes;
-        uint8_t* b_dst = a_dst + kATileBytes;
         const int wc = w0 * p.stride + kx - p.pad;
         const int hc = h0 * p.stride + ky - p.pad;
         if (within < p.c1_chunks)
           tma_load_4d(a_dst, &tmA1, &full_bar[s], within * kBK, wc, hc, n0);
         else
           tma_load_4d(a_dst, &tmA2, &full_bar[s], (within - p.c1_chunks) * kBK, wc, hc, n0);
-        tma_load_2d(b_dst, &tmB, &full_bar[s], kc * kBK, n_tile * p.BN);
+        tma_load_2d(a_dst + kATileBytes, &tmB, &full_bar[s], (k_begin + i) * kBK, nb0);
+        if (++within == p.chunks_per_tap) {
+          within = 0;
+          if (++kx == p.kw) { kx = 0; ++ky; }
+        }
+        a_dst += stage_bytes;
+        if (++s == p.stages) { s = 0; ph ^= 1u; a_dst = tiles; }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // One thread feeds the tensor pipe: everything between two chunks' MMAs is on the critical path (the pipe idles
+    // while this thread probes the barrier), so the loop carries precomputed descriptors and no divisions.
+    // The whole warp runs the loop (warp-uniform control flow and descriptor arithmetic stay in uniform registers);
+    // one elected lane issues the tcgen05 instructions.
+    {
       const uint32_t idesc = umma_idesc_bf16(kBM, (uint32_t)p.BN);
+      const uint64_t a_desc0 = umma_desc_k_sw128(smem_u32(tiles));
+      const uint64_t b_desc0 = umma_desc_k_sw128(smem_u32(tiles) + kATileBytes);
+      const uint64_t desc_step = (uint64_t)(stage_bytes >> 4);  // start-address field advances by one stage
+      int s = 0;
+      uint32_t ph = 0;
+      uint64_t a_desc = a_desc0, b_desc = b_desc0;
       for (int i = 0; i < nchunks; ++i) {
-        const int s = i % p.stages;
-        const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        if (i == 0) SDEO_DBG(2);
-        const uint32_t a_addr = smem_u32(tiles + (size_t)s * stage_bytes);
-        const uint32_t b_addr = a_addr + kATileBytes;
-        const uint64_t a_desc = umma_desc_k_sw128(a_addr);
-        const uint64_t b_desc = umma_desc_k_sw128(b_addr);
+        if (elect_one()) {
+          if (p.a_tmem) {
+            // optional: stage the A tile in TMEM (tcgen05.cp, in issue order with the MMAs), A operand from TMEM
+            const uint32_t a_tm = tmem_base + (uint32_t)p.a_tmem_col + (uint32_t)((i & 1) * 32);
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
-          // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-          tc_mma_bf16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                      (i > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kBK / 16; ++k) tc_cp_128x256b(a_tm + (uint32_t)(8 * k), a_desc + (uint64_t)(2 * k));
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+              tc_mma_bf16_ts(tmem_base, a_tm + (uint32_t)(8 * k), b_desc + (uint64_t)(2 * k), idesc, (i > 0 || k > 0) ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k) {
+              // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+              tc_mma_bf16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                          (i > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+          tc_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
         }
-        tc_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
+        __syncwarp();
+        a_desc += desc_step;
+        b_desc += desc_step;
+        if (++s == p.stages) { s = 0; ph ^= 1u; a_desc = a_desc0; b_desc = b_desc0; }
       }
-      tc_commit(tmem_full_bar);    // accumulator complete (all MMAs done => every stage has been consumed)
-      SDEO_DBG(3);
+      if (elect_one()) tc_commit(tmem_full_bar);  // accumulator complete (all MMAs done => every stage consumed)
+      __syncwarp();
+      if (lane == 0) SDEO_DBG(3);
     }
   } else if (warp < 6) {
     // ===================== epilogue phase 1: TMEM -> fp32 tile in shared memory (thread = row) =====================
@@ -811,7 +837,7 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl) {
   if (body < (size_t)tile_bytes) body = tile_bytes;
   pl->smem_bytes = 1024 /*align slack*/ + 1024 /*barriers*/ + body;
   int tc = 32;
-  while (tc < pl->BN) tc *= 2;
+  while (tc < pl->BN + 64) tc *= 2;  // accumulator + 2 x 32 columns of A staging
   pl->tmem_cols = tc;
   return pl->smem_bytes <= 227 * 1024;
 }
@@ -920,6 +946,8 @@ extern "C" int sdeo_conv2d(const sdeo_conv_args* a, void* stream) {
   p.heads = a->heads; p.dhead = a->dhead; p.tokens = a->tokens; p.ldv = a->ldv; p.qkv_first = a->qkv_first;
   p.dbg = nullptr;
   if (const char* e = getenv("SDEO_CONV_DEBUG")) p.dbg = (long long*)strtoull(e, nullptr, 16);
+  p.a_tmem = getenv("SDEO_A_TMEM") ? 1 : 0;  // measured: no gain over A from shared memory; kept as an option
+  p.a_tmem_col = pl.tmem_cols - 64;
   p.ws = nullptr;
   if (pl.splits > 1 && a->workspace && !getenv("SDEO_SPLITK_DSMEM")) {
     const size_t need = (size_t)cfg_tiles(pl) * pl.splits * kBM * (pl.BN + 4) * sizeof(float);

@@ -51,3 +51,7 @@ for name in names:
     for i in range(1, 9):
         col = rel[:, i]
         print(f"   {lab[i]:11s} {col.median().item():9.0f} {col.max().item():9.0f}")
+    if used[:, 9].max() > 0:
+        for a, b, c, nm in ((9, 10, 11, "chunk 8"), (12, 13, 14, "chunk 16")):
+            print(f"   {nm}: at {rel[:, a].median().item():.0f}; wait-for-data {(used[:, b] - used[:, a]).float().median().item():.0f}"
+                  f" cycles; issue 4 MMAs + commit {(used[:, c] - used[:, b]).float().median().item():.0f} cycles")
