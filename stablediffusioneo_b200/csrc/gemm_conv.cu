@@ -59,6 +59,7 @@ struct ConvKParams {
   __nv_bfloat16* vt;
   int heads, dhead, tokens, ldv, qkv_first;
   long long* dbg;  // optional per-CTA phase timestamps (SDEO_CONV_DEBUG), 16 slots per CTA
+  int res_smem_off;        // > 0: idle warps prefetch the residual tile into shared memory at this byte offset
   int a_tmem, a_tmem_col;  // stage the A tile in TMEM (tcgen05.cp) at this column offset
   float* ws;       // split-K partial tiles in global memory (L2-resident); nullptr: reduce through DSMEM instead
 };
@@ -143,8 +144,16 @@ __device__ __forceinline__ void epi_normal_fast(const ConvKParams& p, long long 
     *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + pix * p.ldy + n) = pack8_bf16(v);
   } else {
     float* yp = reinterpret_cast<float*>(p.y) + pix * p.ldy + n;
-    *reinterpret_cast<float4*>(yp) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(yp + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    if ((p.ldy & 7) == 0) {
+      // one 256-bit store per lane: whole 32-byte sectors (two 16-byte stores per lane leave every sector half-written
+      // per instruction and halved the measured store rate)
+      asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(yp), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                   "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                   : "memory");
+    } else {
+      *reinterpret_cast<float4*>(yp) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(yp + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
     if (OUT == OUT_F32_TWIN) *reinterpret_cast<uint4*>(p.y2 + pix * p.ldy2 + n) = pack8_bf16(v);
   }
 }
@@ -507,6 +516,36 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     if (threadIdx.x == 64) SDEO_DBG(5);
   }
 
+  if (MODE == SDEO_EPI_NORMAL && FAST && RES != RES_NONE && warp >= 6 && p.res_smem_off) {
+    // ===================== residual prefetch (warps 6..11, concurrent with the mainloop) =====================
+    // cp.async 16-byte copies of the residual rows this CTA's epilogue will add, into a dense [row][BN] buffer.
+    constexpr int kElem = (RES == RES_F32) ? 4 : 2;
+    const int S = p.splits;
+    const int rows_per = (p.rows_valid + S - 1) / S;
+    const int r_begin = split * rows_per;
+    const int r_end = min(p.rows_valid, r_begin + rows_per);
+    const int vpr = p.BN * kElem / 16;  // 16-byte vectors per row
+    const int per_img = p.bh * p.bw;
+    const int n_base = n_tile * p.BN;
+    const uint32_t res_s = smem_u32(smem + p.res_smem_off);
+    const uint8_t* res_g = reinterpret_cast<const uint8_t*>(p.residual);
+    const int total = (r_end > r_begin ? r_end - r_begin : 0) * vpr;
+    for (int it = (int)threadIdx.x - 192; it < total; it += kConvThreads - 192) {
+      const int row = r_begin + it / vpr, v = it % vpr;
+      const int nl = row / per_img, rem = row % per_img;
+      const int hl = rem / p.bw, wl = rem % p.bw;
+      const int nn = n0 + nl, hh = h0 + hl, ww = w0 + wl;
+      const int col = v * (16 / kElem);
+      if (nn < p.N && hh < p.Ho && ww < p.Wo && n_base + col < p.cout) {
+        const long long pix = ((long long)nn * p.Ho + hh) * p.Wo + ww;
+        const uint8_t* src = res_g + ((size_t)pix * p.ldr + n_base + col) * kElem;
+        const uint32_t dst = res_s + (uint32_t)((row * p.BN + col) * kElem);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+  }
+
   // ---- partial tiles complete: CTA-wide (S == 1) or cluster-wide (S > 1) barrier ----
   __syncwarp();
   const size_t ws_tile_floats = (size_t)kBM * LD;
@@ -559,7 +598,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         offs[u] = (uint32_t)(((size_t)(row < r_end ? row : r_begin) * LD + cols[u]) * sizeof(float));
         if (row < r_end) {
           pixs[u] = row_pix[row];
-          if (MODE == SDEO_EPI_NORMAL && FAST && RES != RES_NONE && pixs[u] >= 0) {
+          if (MODE == SDEO_EPI_NORMAL && FAST && RES != RES_NONE && pixs[u] >= 0 && p.res_smem_off) {
+            constexpr int kElem = (RES == RES_F32) ? 4 : 2;
+            const uint4* rp = reinterpret_cast<const uint4*>(smem + p.res_smem_off + (size_t)(row * p.BN + cols[u]) * kElem);
+            raw0[u] = rp[0];
+            if (RES == RES_F32) raw1[u] = rp[1];
+          } else if (MODE == SDEO_EPI_NORMAL && FAST && RES != RES_NONE && pixs[u] >= 0) {
             if (RES == RES_F32) {
               const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.residual) +
                                                                (long long)pixs[u] * p.ldr + n_base + cols[u]);
@@ -735,6 +779,7 @@ struct ConvPlan {
   int rows_packed, BN, n_tiles;
   int c1c, c2c, cpt, total_chunks, splits, cps;
   int stages, tmem_cols;
+  int res_smem_off;
   size_t smem_bytes;
 };
 
@@ -794,7 +839,7 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl) {
   // ---- N tile ----
   pl->rows_packed = round_up(a->cout, 16);
   pl->BN = pick_bn_impl(pl->rows_packed, a->epi_mode);
-  if (a->epi_mode != SDEO_EPI_GEGLU && pl->rows_packed > 128) {
+  if (a->epi_mode != SDEO_EPI_GEGLU && pl->rows_packed > 128 && best_tiles <= 2) {
     // weight-streaming layers with very few M tiles: narrower N tiles put more SMs on the weight stream
     // (cluster split-K is capped at kMaxCluster K-slices per tile)
     static const int cand[] = {256, 192, 160, 128, 96, 80, 64};
@@ -832,10 +877,21 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl) {
   int stages = (208 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages > pl->cps) stages = pl->cps < 2 ? 2 : pl->cps;
+  // residual tile prefetched into shared memory by the otherwise idle warps, if >= 4 pipeline stages still fit
+  pl->res_smem_off = 0;
+  int res_bytes = 0;
+  if (a->residual && a->epi_mode == SDEO_EPI_NORMAL && !getenv("SDEO_NO_RES_PREFETCH")) {
+    res_bytes = kBM * pl->BN * (a->residual_f32 ? 4 : 2);
+    int st2 = (208 * 1024 - res_bytes) / stage_bytes;
+    if (st2 > stages) st2 = stages;
+    const int need = pl->cps < 4 ? (pl->cps < 2 ? 2 : pl->cps) : 4;
+    if (st2 >= need && (size_t)st2 * stage_bytes >= (size_t)tile_bytes) stages = st2; else res_bytes = 0;
+  }
   pl->stages = stages;
   size_t body = (size_t)stages * stage_bytes;
   if (body < (size_t)tile_bytes) body = tile_bytes;
-  pl->smem_bytes = 1024 /*align slack*/ + 1024 /*barriers*/ + body;
+  if (res_bytes) pl->res_smem_off = 1024 + (int)body;
+  pl->smem_bytes = 1024 /*align slack*/ + 1024 /*barriers*/ + body + res_bytes;
   int tc = 32;
   while (tc < pl->BN + 64) tc *= 2;  // accumulator + 2 x 32 columns of A staging
   pl->tmem_cols = tc;
@@ -946,6 +1002,7 @@ extern "C" int sdeo_conv2d(const sdeo_conv_args* a, void* stream) {
   p.heads = a->heads; p.dhead = a->dhead; p.tokens = a->tokens; p.ldv = a->ldv; p.qkv_first = a->qkv_first;
   p.dbg = nullptr;
   if (const char* e = getenv("SDEO_CONV_DEBUG")) p.dbg = (long long*)strtoull(e, nullptr, 16);
+  p.res_smem_off = pl.res_smem_off;
   p.a_tmem = getenv("SDEO_A_TMEM") ? 1 : 0;  // measured: no gain over A from shared memory; kept as an option
   p.a_tmem_col = pl.tmem_cols - 64;
   p.ws = nullptr;
