@@ -89,6 +89,10 @@ typedef struct sdeo_conv_args {
 size_t sdeo_conv_workspace_bytes(const sdeo_conv_args* a);
 size_t sdeo_conv_counter_bytes(void);
 int sdeo_conv2d(const sdeo_conv_args* a, void* stream);
+/* Enable (1) / disable (0) per-shape autotuning of the N tile and the number of K slices: the first eager call of a
+ * layer shape times the candidates on the caller's stream and caches the winner (calls made while the stream is
+ * being captured into a CUDA graph only read the cache). */
+int sdeo_conv_autotune(int enable);
 
 /* Repack an fp32 filter [cout, cin, k, k] (PyTorch layout, device memory) into the K-major bf16 layout the
  * kernel streams: [rows_packed, k*k*(chunks(c1)+chunks(c2))*64]. `geglu_bn` > 0 interleaves the two GEGLU

@@ -35,6 +35,7 @@ SIGNATURES = {
     "sdeo_conv_workspace_bytes": (c_size_t, [POINTER(ConvArgs)]),
     "sdeo_conv_counter_bytes": (c_size_t, []),
     "sdeo_conv2d": (c_int, [POINTER(ConvArgs), c_void_p]),
+    "sdeo_conv_autotune": (c_int, [c_int]),
     "sdeo_packed_rows": (c_int32, [c_int32]),
     "sdeo_packed_k": (c_int32, [c_int32, c_int32, c_int32]),
     "sdeo_pick_bn": (c_int32, [c_int32, c_int32, c_int32]),

@@ -255,6 +255,7 @@ class ControlLDM(nn.Module):
         self.register_buffer("alphas_cumprod_prev", f32(np.append(1.0, alphas_cumprod[:-1])), persistent=False)
         self.register_buffer("sqrt_one_minus_alphas_cumprod", f32(np.sqrt(1.0 - alphas_cumprod)), persistent=False)
         self._hint_cache = None
+        ops.set_autotune(True)  # first eager call of each layer shape picks its tile / split-K configuration
 
     @property
     def device(self):

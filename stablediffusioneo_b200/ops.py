@@ -369,6 +369,11 @@ def cfg_ddim_step(eps_c, eps_u, x, coef_table, step_idx=None, noise=None, x_prev
     return x_prev, pred_x0
 
 
+def set_autotune(enable=True):
+    """Per-shape autotuning of the conv/linear kernel's N tile and K slices (see sdeo_conv_autotune)."""
+    _check(_lib.load().sdeo_conv_autotune(1 if enable else 0), "conv_autotune")
+
+
 def memset(t, value=0):
     lib = _lib.load()
     assert t.is_contiguous()
