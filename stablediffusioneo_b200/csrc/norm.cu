@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "host_util.h"
 #include "../../include/sdeo.h"
+#include <stdlib.h>
 
 namespace sdeo {
 
@@ -155,6 +156,175 @@ gn_apply_kernel(const T* __restrict__ x1, const T* __restrict__ x2,
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Single-launch GroupNorm for the denoiser's small tensors: ONE THREAD-BLOCK CLUSTER of kGNCluster CTAs per sample.
+// Each CTA reduces its share of the pixels to per-group (sum, sumsq) in its shared memory, the cluster exchanges the
+// 2*groups partials through distributed shared memory (rank order: deterministic), then every CTA normalises its own
+// pixels (second read comes from L2). Replaces the stats + apply pair (2 launches, a global workspace round trip).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kGNCluster = 8;
+constexpr int kGNCThreads = 512;
+
+template <typename T>
+__global__ void __launch_bounds__(kGNCThreads)
+gn_cluster_kernel(const T* __restrict__ x1, const T* __restrict__ x2, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int hw, int c1, int c2, int groups,
+                  float eps, int with_silu) {
+  extern __shared__ float sm[];
+  __shared__ float grp[128];            // [2][groups] this CTA's partial sums, read by the peers
+  __shared__ float s_mean[64], s_rstd[64];
+  const int C = c1 + c2;
+  const int cv = C / 8;
+  const int cpg = C / groups;
+  const int n = blockIdx.y, rank = blockIdx.x;  // cluster = the kGNCluster CTAs along x
+  const int ppc = (hw + kGNCluster - 1) / kGNCluster;
+  const int p_begin = rank * ppc;
+  const int p_end = min(hw, p_begin + ppc);
+  float* chan_sum = sm;        // [C]
+  float* chan_sq = sm + C;     // [C]
+  float* part = sm + 2 * C;    // [R][cols][16]
+  const int cols = cv < kGNCThreads ? cv : kGNCThreads;
+  const int R = kGNCThreads / cols;
+  const int tr = threadIdx.x / cols, tv = threadIdx.x % cols;
+  const bool active = threadIdx.x < R * cols;
+
+  for (int vbase = 0; vbase < cv; vbase += cols) {
+    const int v = vbase + tv;
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+    if (active && v < cv) {
+      int pp = p_begin + tr;
+      for (; pp + 3 * R < p_end; pp += 4 * R) {  // 4 independent loads in flight per thread
+        float f0[8], f1[8], f2[8], f3[8];
+        gn_load8(x1, x2, c1, c2, (long long)n * hw + pp, v, f0);
+        gn_load8(x1, x2, c1, c2, (long long)n * hw + pp + R, v, f1);
+        gn_load8(x1, x2, c1, c2, (long long)n * hw + pp + 2 * R, v, f2);
+        gn_load8(x1, x2, c1, c2, (long long)n * hw + pp + 3 * R, v, f3);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s[j] += (f0[j] + f1[j]) + (f2[j] + f3[j]);
+          q[j] += (f0[j] * f0[j] + f1[j] * f1[j]) + (f2[j] * f2[j] + f3[j] * f3[j]);
+        }
+      }
+      for (; pp < p_end; pp += R) {
+        float f[8];
+        gn_load8(x1, x2, c1, c2, (long long)n * hw + pp, v, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] += f[j] * f[j]; }
+      }
+    }
+    if (active) {
+      float* dst = part + ((size_t)tr * cols + tv) * 16;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { dst[j] = s[j]; dst[8 + j] = q[j]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < cols && v < cv) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+      for (int r = 0; r < R; ++r) {
+        const float* src = part + ((size_t)r * cols + tv) * 16;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] += src[j]; q[j] += src[8 + j]; }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { chan_sum[v * 8 + j] = s[j]; chan_sq[v * 8 + j] = q[j]; }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < groups) {
+    const int g = threadIdx.x;
+    float s = 0.f, q = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) { s += chan_sum[c]; q += chan_sq[c]; }
+    grp[g] = s;
+    grp[groups + g] = q;
+  }
+  // ---- exchange the partials across the cluster ----
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (threadIdx.x < groups) {
+    const int g = threadIdx.x;
+    float s = 0.f, q = 0.f;
+    const uint32_t local = smem_u32(grp);
+    for (int r = 0; r < kGNCluster; ++r) {
+      uint32_t peer;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer) : "r"(local), "r"(r));
+      float a, b;
+      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(a) : "r"(peer + (uint32_t)g * 4u));
+      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(b) : "r"(peer + (uint32_t)(groups + g) * 4u));
+      s += a;
+      q += b;
+    }
+    const float inv = 1.0f / ((float)hw * (float)cpg);
+    const float mean = s * inv;
+    float var = q * inv - mean * mean;
+    var = var < 0.f ? 0.f : var;
+    s_mean[g] = mean;
+    s_rstd[g] = rsqrtf(var + eps);
+  }
+  // nobody may exit (or overwrite grp) while a peer still reads it; also publishes s_mean / s_rstd CTA-wide
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+
+  // ---- normalise this CTA's pixels ----
+  if (!active) return;
+  for (int vbase = 0; vbase < cv; vbase += cols) {
+    const int v = vbase + tv;
+    if (v >= cv) continue;
+    float a[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = v * 8 + j;
+      const int g = c / cpg;
+      const float ga = gamma[c] * s_rstd[g];
+      a[j] = ga;
+      b[j] = beta[c] - s_mean[g] * ga;
+    }
+    for (int pp = p_begin + tr; pp < p_end; pp += R) {
+      const long long pix = (long long)n * hw + pp;
+      float f[8];
+      gn_load8(x1, x2, c1, c2, pix, v, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = f[j] * a[j] + b[j];
+        f[j] = with_silu ? silu_f(t) : t;
+      }
+      uint4 o;
+      o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+      o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+      *reinterpret_cast<uint4*>(y + pix * C + v * 8) = o;
+    }
+  }
+}
+
+template <typename T>
+static int launch_gn_cluster(const void* x1, const void* x2, const float* gamma, const float* beta, void* y, int n, int hw,
+                             int c1, int c2, int groups, float eps, int with_silu, cudaStream_t st) {
+  const int C = c1 + c2;
+  const size_t smem = (size_t)(2 * C + kGNCThreads * 16) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gn_cluster_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) return set_error(SDEO_ECUDA, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kGNCluster, (unsigned)n);
+  cfg.blockDim = dim3(kGNCThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kGNCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gn_cluster_kernel<T>, (const T*)x1, (const T*)x2, gamma, beta, (__nv_bfloat16*)y, hw,
+                                     c1, c2, groups, eps, with_silu);
+  if (e != cudaSuccess) return set_error(SDEO_ECUDA, cudaGetErrorString(e));
+  return check_launch("groupnorm (cluster)");
+}
+
 static void gn_geometry(int n, int hw, int* chunks, int* ppc) {
   // about 1.5 CTAs per SM over the batch, and at least 16 pixels per CTA (these tensors are small: per-CTA fixed
   // costs and the apply kernel's per-CTA fold over the chunk partials dominate otherwise)
@@ -244,6 +414,13 @@ extern "C" int sdeo_groupnorm_nhwc(const void* x1, const void* x2, int32_t x_f32
   if (n <= 0 || hw <= 0 || groups <= 0 || groups > 64 || C % groups != 0 || c1 % 8 != 0 || c2 % 8 != 0)
     return set_error(SDEO_EINVAL, "groupnorm: unsupported geometry (need C % groups == 0, channels % 8 == 0, groups <= 64)");
   if (n > 65535) return set_error(SDEO_EINVAL, "groupnorm: batch too large");
+  // small tensors (the denoiser's): one cluster per sample, single launch; big ones (VAE): two-pass grid
+  if ((long long)hw * C <= (1LL << 21) && hw >= kGNCluster && (size_t)(2 * C + kGNCThreads * 16) * 4 <= 100 * 1024 &&
+      !getenv("SDEO_GN_TWO_PASS")) {
+    if (x_f32)
+      return launch_gn_cluster<float>(x1, x2, gamma, beta, y, n, hw, c1, c2, groups, eps, with_silu, (cudaStream_t)stream);
+    return launch_gn_cluster<__nv_bfloat16>(x1, x2, gamma, beta, y, n, hw, c1, c2, groups, eps, with_silu, (cudaStream_t)stream);
+  }
   int chunks, ppc;
   gn_geometry(n, hw, &chunks, &ppc);
   if (workspace_bytes < (size_t)n * chunks * groups * 2 * sizeof(float))

