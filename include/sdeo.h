@@ -30,6 +30,11 @@ extern "C" {
 const char* sdeo_last_error(void);
 /* Library ABI version (bumped on any signature change). */
 int sdeo_version(void);
+/* Programmatic dependent launch (default on; also SDEO_NO_PDL=1): every kernel of the library is launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization and orders itself behind its stream predecessor with
+ * griddepcontrol.wait, so launch latency, the kernel prologue and the weight prefetch of call N+1 overlap the tail of
+ * call N (also inside captured CUDA graphs). Stream semantics seen by the caller are unchanged. */
+int sdeo_set_pdl(int enable);
 
 /* ------------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution / linear on tcgen05 tensor cores (TMA-fed, TMEM accumulators).
@@ -66,6 +71,9 @@ typedef struct sdeo_conv_args {
   int32_t act;          /* SDEO_ACT_*                                                                  */
   const float* bias;    /* fp32 [cout] (packed order for GEGLU) or NULL                                */
   const float* emb;     /* fp32 [n, cout] per-sample additive term (ResBlock emb_layers) or NULL        */
+  const int32_t* emb_step; /* optional device pointer: table mode, emb is [S, cout] and EVERY sample adds row
+                              *emb_step (the per-image table of emb_layers outputs for all S DDIM timesteps,
+                              indexed by the device-side step counter). NULL: row = sample index             */
   const void* residual; /* [n, ho, wo, ldr] added after scaling, or NULL; bf16, or fp32 if residual_f32 */
   int32_t ldr;
   int32_t residual_f32;

@@ -19,7 +19,7 @@ class ConvArgs(Structure):
         ("w_packed", c_void_p),
         ("cout", c_int32), ("ksize", c_int32), ("stride", c_int32), ("pad", c_int32),
         ("epi_mode", c_int32), ("act", c_int32),
-        ("bias", c_void_p), ("emb", c_void_p), ("residual", c_void_p), ("ldr", c_int32), ("residual_f32", c_int32),
+        ("bias", c_void_p), ("emb", c_void_p), ("emb_step", c_void_p), ("residual", c_void_p), ("ldr", c_int32), ("residual_f32", c_int32),
         ("scale", c_float),
         ("y", c_void_p), ("ldy", c_int32), ("y_fp32", c_int32), ("y2", c_void_p), ("ldy2", c_int32),
         ("q", c_void_p), ("k", c_void_p), ("vt", c_void_p),
@@ -32,6 +32,7 @@ class ConvArgs(Structure):
 SIGNATURES = {
     "sdeo_last_error": (c_char_p, []),
     "sdeo_version": (c_int, []),
+    "sdeo_set_pdl": (c_int, [c_int]),
     "sdeo_conv_workspace_bytes": (c_size_t, [POINTER(ConvArgs)]),
     "sdeo_conv_counter_bytes": (c_size_t, []),
     "sdeo_conv2d": (c_int, [POINTER(ConvArgs), c_void_p]),

@@ -253,6 +253,7 @@ class _Engine:
     def _load_inputs(self, x_T, cond, uncond, ts, rows):
         b = x_T.shape[0]
         self.x_keep.copy_(x_T, non_blocking=True)
+        self._ts_host = [int(v) for v in ts]
         self.ts_table.copy_(torch.tensor(ts, dtype=torch.int64), non_blocking=True)
         self.coef.copy_(torch.tensor(rows, dtype=torch.float32), non_blocking=True)
         conds = [cond] + ([uncond] if uncond is not None else [])
@@ -287,6 +288,16 @@ class _Engine:
                 self.guided.copy_(g)
         else:
             self.guided = None
+        # time-embedding tables: emb_layers outputs of every ResBlock for all S timesteps (depend only on t)
+        from ..ldm.modules.diffusionmodules.openaimodel import StepEmb
+        unet = m.model.diffusion_model
+        ts_key = tuple(self._ts_host)
+        if getattr(self, "_emb_key", None) != ts_key:
+            t_emb_all = ops.timestep_embedding(self.ts_table, self.S, unet.model_channels)
+            self.emb_u = StepEmb.build(unet, t_emb_all, self.step_ctr, into=getattr(self, "emb_u", None))
+            if self.has_hint:
+                self.emb_c = StepEmb.build(m.control_model, t_emb_all, self.step_ctr, into=getattr(self, "emb_c", None))
+            self._emb_key = ts_key
         from ..ldm.modules.attention import CrossAttention
         mods = list(m.model.diffusion_model.modules()) + (list(m.control_model.modules()) if self.has_hint else [])
         for mod in mods:
@@ -304,8 +315,7 @@ class _Engine:
         nb = self.x_in.shape[0]
         b = self.x_lat.shape[0]
         x = self.x_in.permute(0, 3, 1, 2)
-        t_emb = ops.timestep_embedding(self.ts_table, nb, unet.model_channels, step_idx=self.step_ctr)
-        emb_u = unet.time_embed[2].run(unet.time_embed[0].run(t_emb, act=ops.SDEO_ACT_SILU))
+        emb_u = self.emb_u  # per-image [S, Cout] tables, row selected on the device by step_ctr (see _prologue)
         if self.has_hint:
             # the UNet encoder and the ControlNet body are independent: run them on two streams (captured as two
             # branches of the step graph), then apply the 13 zero convs onto the UNet skips
@@ -314,8 +324,7 @@ class _Engine:
             side = self.side_stream
             side.wait_stream(main)
             with torch.cuda.stream(side), ops.workspace_slot(1):
-                emb_c = cn.time_embed[2].run(cn.time_embed[0].run(t_emb, act=ops.SDEO_ACT_SILU))
-                feats = cn.run_body(x, self.guided, emb_c, self.ctx)
+                feats = cn.run_body(x, self.guided, self.emb_c, self.ctx)
             hs, h = unet.run_encoder(x, emb_u, self.ctx)
             main.wait_stream(side)
             outs = cn.run_zero_convs(feats, scales=m.control_scales, add_to=hs + [h], only_mid=m.only_mid_control)

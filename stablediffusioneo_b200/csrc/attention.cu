@@ -79,6 +79,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t tmem_base = *tmem_ptr_smem;
   const uint32_t tmem_S = tmem_base;          // 128 columns
   const uint32_t tmem_O = tmem_base + 128;    // dv16 columns
+  griddep_launch_dependents();  // PDL (after this CTA's own TMEM allocation, see gemm_conv.cu)
+  griddep_wait();  // q/k/v are written by the preceding projection kernels; o may still be read by an earlier one
 
   if (warp == 0) {
     if (lane == 0) {
@@ -304,6 +306,6 @@ extern "C" int sdeo_attention(const void* q, const void* k, const void* vt, void
     attr_set = true;
   }
   dim3 grid((unsigned)((nq + kTileQ - 1) / kTileQ), (unsigned)BH);
-  attention_kernel<<<grid, kAttThreads, smem, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
-  return check_launch("attention");
+  return launch_k("attention", attention_kernel, grid, dim3(kAttThreads), smem, (cudaStream_t)stream, dim3(1, 1, 1), tmQ, tmK,
+                  tmV, p);
 }

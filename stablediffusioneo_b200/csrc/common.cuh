@@ -28,6 +28,17 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL): every kernel of the library is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization (host_util.h launch_k), so kernel N+1 of a stream is scheduled
+// while kernel N still runs. griddep_launch_dependents() at the top lets the successor start its prologue (barrier
+// init, TMEM allocation, descriptor prefetch, weight prefetch); griddep_wait() blocks until every predecessor grid has
+// completed and flushed its memory -- nothing produced by (or still read by) an earlier kernel may be touched before it.
+// Both are no-ops for a kernel launched without the attribute.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
 // exact-erf GELU (F.gelu default in the reference, attention.py:56)

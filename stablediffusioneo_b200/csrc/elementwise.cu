@@ -13,6 +13,8 @@ __global__ void cfg_ddim_kernel(const float* __restrict__ eps_c, const float* __
                                 __nv_bfloat16* __restrict__ x_next, int dup, int ldn,
                                 const float* __restrict__ coef_table, const int* __restrict__ step_idx, int n, int c,
                                 int hw) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int row = step_idx ? *step_idx : 0;
   const float* cf = coef_table + (size_t)row * 8;
   const float s = cf[0], sqrt_1m_at = cf[1], rsqrt_at = cf[2], sqrt_aprev = cf[3], dir_coef = cf[4], sigma = cf[5];
@@ -47,12 +49,18 @@ __global__ void cfg_ddim_kernel(const float* __restrict__ eps_c, const float* __
   }
 }
 
-__global__ void counter_add_kernel(int* ctr, int delta) { *ctr += delta; }
+__global__ void counter_add_kernel(int* ctr, int delta) {
+  griddep_launch_dependents();
+  griddep_wait();
+  *ctr += delta;
+}
 
 // ---- layout conversion ---------------------------------------------------------------------------
 // NCHW fp32 -> NHWC bf16 (zero-padded to ldy channels). One thread per (pixel, channel-slot).
 __global__ void nchw_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int c,
                                          int hw, int ldy, float scale) {
+  griddep_launch_dependents();
+  griddep_wait();
   // tile transpose through shared memory: 32 channels x 32 pixels
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
@@ -71,6 +79,8 @@ __global__ void nchw_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloa
 template <typename TIn>
 __global__ void nhwc_to_nchw_f32_kernel(const TIn* __restrict__ x, float* __restrict__ y, int n, int c, int hw,
                                         int ldx) {
+  griddep_launch_dependents();
+  griddep_wait();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -89,6 +99,8 @@ __global__ void nhwc_to_nchw_f32_kernel(const TIn* __restrict__ x, float* __rest
 
 // ---- nearest x2 upsample, NHWC, 16-byte vectors ---------------------------------------------------
 __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int n, int h, int w, int cv) {
+  griddep_launch_dependents();
+  griddep_wait();
   const long long total = (long long)n * (2 * h) * (2 * w) * cv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -106,6 +118,8 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict
 __global__ void add_scaled_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, float alpha,
                                   uint4* __restrict__ y, long long nvec, const __nv_bfloat16* a_s,
                                   const __nv_bfloat16* b_s, __nv_bfloat16* y_s, long long count) {
+  griddep_launch_dependents();
+  griddep_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
     const uint4 av = a[i], bv = b[i];
@@ -128,6 +142,8 @@ __global__ void add_scaled_kernel(const uint4* __restrict__ a, const uint4* __re
 // ---- timestep embedding: [cos(t f_i) | sin(t f_i)], f_i = exp(-ln(max_period) i / half) ------------
 __global__ void timestep_embedding_kernel(const long long* __restrict__ t, const int* __restrict__ step_idx,
                                           __nv_bfloat16* __restrict__ y, int n, int dim, int ldy, float max_period) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * ldy) return;
@@ -144,16 +160,22 @@ __global__ void timestep_embedding_kernel(const long long* __restrict__ t, const
 }
 
 __global__ void silu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long count) {
+  griddep_launch_dependents();
+  griddep_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
        i += (long long)gridDim.x * blockDim.x)
     y[i] = __float2bfloat16(silu_f(__bfloat162float(x[i])));
 }
 __global__ void f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long count) {
+  griddep_launch_dependents();
+  griddep_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
        i += (long long)gridDim.x * blockDim.x)
     y[i] = __float2bfloat16(x[i]);
 }
 __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, long long count) {
+  griddep_launch_dependents();
+  griddep_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
        i += (long long)gridDim.x * blockDim.x)
     y[i] = __bfloat162float(x[i]);
@@ -163,6 +185,8 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ x, float* _
 __global__ void __launch_bounds__(256)
 softmax_rows_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int cols, int ld, int ldy,
                     float scale_log2) {
+  griddep_launch_dependents();
+  griddep_wait();
   __shared__ float red[8];
   __shared__ float bcast;
   const float* xr = x + (size_t)blockIdx.x * ld;
@@ -201,6 +225,8 @@ softmax_rows_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, 
 
 __global__ void image_to_u8_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ y, long long npix, int c,
                                    int ldx) {
+  griddep_launch_dependents();
+  griddep_wait();
   const long long total = npix * c;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -231,90 +257,71 @@ extern "C" int sdeo_cfg_ddim_step(const float* eps_c, const float* eps_u, int32_
   if (x_next && (dup <= 0 || ldn < c)) return set_error(SDEO_EINVAL, "cfg_ddim_step: bad x_next geometry");
   if (eps_nhwc && ld_eps < c) return set_error(SDEO_EINVAL, "cfg_ddim_step: ld_eps < c");
   const long long total = (long long)n * hw;
-  cfg_ddim_kernel<<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>(eps_c, eps_u, eps_nhwc, ld_eps, x, noise, x_prev,
-                                                                         pred_x0, (__nv_bfloat16*)x_next, dup, ldn,
-                                                                         coef_table, step_idx, n, c, hw);
-  return check_launch("cfg_ddim_step");
+  return launch_k("cfg_ddim_step", cfg_ddim_kernel, dim3(grid_for(total, 128)), dim3(128), 0, (cudaStream_t)stream, dim3(1, 1, 1), eps_c, eps_u, eps_nhwc, ld_eps, x, noise, x_prev, pred_x0, (__nv_bfloat16*)x_next, dup, ldn, coef_table, step_idx, n, c, hw);
 }
 
 extern "C" int sdeo_counter_add(int32_t* ctr, int32_t delta, void* stream) {
   if (!ctr) return set_error(SDEO_EINVAL, "counter_add: null");
-  counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(ctr, delta);
-  return check_launch("counter_add");
+  return launch_k("counter_add", counter_add_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, dim3(1, 1, 1), ctr, delta);
 }
 
 extern "C" int sdeo_nchw_to_nhwc_bf16(const float* x, void* y, int32_t n, int32_t c, int32_t hw, int32_t ldy, float scale,
                                       void* stream) {
   if (!x || !y || n <= 0 || c <= 0 || hw <= 0 || ldy < c || n > 65535) return set_error(SDEO_EINVAL, "nchw_to_nhwc: bad args");
   dim3 grid((hw + 31) / 32, (ldy + 31) / 32, n), block(32, 8);
-  nchw_to_nhwc_bf16_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, n, c, hw, ldy, scale);
-  return check_launch("nchw_to_nhwc");
+  return launch_k("nchw_to_nhwc", nchw_to_nhwc_bf16_kernel, dim3(grid), dim3(block), 0, (cudaStream_t)stream, dim3(1, 1, 1), x, (__nv_bfloat16*)y, n, c, hw, ldy, scale);
 }
 extern "C" int sdeo_nhwc_bf16_to_nchw(const void* x, float* y, int32_t n, int32_t c, int32_t hw, int32_t ldx, void* stream) {
   if (!x || !y || n <= 0 || c <= 0 || hw <= 0 || ldx < c || n > 65535) return set_error(SDEO_EINVAL, "nhwc_to_nchw: bad args");
   dim3 grid((hw + 31) / 32, (c + 31) / 32, n), block(32, 8);
-  nhwc_to_nchw_f32_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, y, n, c, hw, ldx);
-  return check_launch("nhwc_to_nchw");
+  return launch_k("nhwc_to_nchw", nhwc_to_nchw_f32_kernel<__nv_bfloat16>, dim3(grid), dim3(block), 0, (cudaStream_t)stream, dim3(1, 1, 1), (const __nv_bfloat16*)x, y, n, c, hw, ldx);
 }
 extern "C" int sdeo_nhwc_f32_to_nchw(const float* x, float* y, int32_t n, int32_t c, int32_t hw, int32_t ldx, void* stream) {
   if (!x || !y || n <= 0 || c <= 0 || hw <= 0 || ldx < c || n > 65535) return set_error(SDEO_EINVAL, "nhwc_f32_to_nchw: bad args");
   dim3 grid((hw + 31) / 32, (c + 31) / 32, n), block(32, 8);
-  nhwc_to_nchw_f32_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(x, y, n, c, hw, ldx);
-  return check_launch("nhwc_f32_to_nchw");
+  return launch_k("nhwc_f32_to_nchw", nhwc_to_nchw_f32_kernel<float>, dim3(grid), dim3(block), 0, (cudaStream_t)stream, dim3(1, 1, 1), x, y, n, c, hw, ldx);
 }
 
 extern "C" int sdeo_upsample_nearest2x(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c, void* stream) {
   if (!x || !y || n <= 0 || h <= 0 || w <= 0 || c <= 0 || c % 8 != 0) return set_error(SDEO_EINVAL, "upsample2x: bad args");
   const long long total = (long long)n * 4 * h * w * (c / 8);
-  upsample2x_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, n, h, w, c / 8);
-  return check_launch("upsample2x");
+  return launch_k("upsample2x", upsample2x_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, dim3(1, 1, 1), (const uint4*)x, (uint4*)y, n, h, w, c / 8);
 }
 
 extern "C" int sdeo_add_scaled(const void* a, const void* b, float alpha, void* y, int64_t count, void* stream) {
   if (!a || !b || !y || count <= 0) return set_error(SDEO_EINVAL, "add_scaled: bad args");
   const bool aligned = (((uintptr_t)a | (uintptr_t)b | (uintptr_t)y) & 15) == 0;
   const long long nvec = aligned ? count / 8 : 0;
-  add_scaled_kernel<<<grid_for(nvec > 0 ? nvec : 1, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const uint4*)a, (const uint4*)b, alpha, (uint4*)y, nvec, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b,
-      (__nv_bfloat16*)y, count);
-  return check_launch("add_scaled");
+  return launch_k("add_scaled", add_scaled_kernel, dim3(grid_for(nvec > 0 ? nvec : 1, 256)), dim3(256), 0, (cudaStream_t)stream, dim3(1, 1, 1), (const uint4*)a, (const uint4*)b, alpha, (uint4*)y, nvec, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (__nv_bfloat16*)y, count);
 }
 
 extern "C" int sdeo_timestep_embedding(const int64_t* t, const int32_t* step_idx, void* y, int32_t n, int32_t dim,
                                        int32_t ldy, float max_period, void* stream) {
   if (!t || !y || n <= 0 || dim <= 0 || ldy < dim) return set_error(SDEO_EINVAL, "timestep_embedding: bad args");
   const int total = n * ldy;
-  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>((const long long*)t, step_idx,
-                                                                                    (__nv_bfloat16*)y, n, dim, ldy, max_period);
-  return check_launch("timestep_embedding");
+  return launch_k("timestep_embedding", timestep_embedding_kernel, dim3((total + 127) / 128), dim3(128), 0, (cudaStream_t)stream, dim3(1, 1, 1), (const long long*)t, step_idx, (__nv_bfloat16*)y, n, dim, ldy, max_period);
 }
 
 extern "C" int sdeo_silu(const void* x, void* y, int64_t count, void* stream) {
   if (!x || !y || count <= 0) return set_error(SDEO_EINVAL, "silu: bad args");
-  silu_kernel<<<grid_for(count, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, count);
-  return check_launch("silu");
+  return launch_k("silu", silu_kernel, dim3(grid_for(count, 256)), dim3(256), 0, (cudaStream_t)stream, dim3(1, 1, 1), (const __nv_bfloat16*)x, (__nv_bfloat16*)y, count);
 }
 extern "C" int sdeo_f32_to_bf16(const float* x, void* y, int64_t count, void* stream) {
   if (!x || !y || count <= 0) return set_error(SDEO_EINVAL, "f32_to_bf16: bad args");
-  f32_to_bf16_kernel<<<grid_for(count, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, count);
-  return check_launch("f32_to_bf16");
+  return launch_k("f32_to_bf16", f32_to_bf16_kernel, dim3(grid_for(count, 256)), dim3(256), 0, (cudaStream_t)stream, dim3(1, 1, 1), x, (__nv_bfloat16*)y, count);
 }
 extern "C" int sdeo_bf16_to_f32(const void* x, float* y, int64_t count, void* stream) {
   if (!x || !y || count <= 0) return set_error(SDEO_EINVAL, "bf16_to_f32: bad args");
-  bf16_to_f32_kernel<<<grid_for(count, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, y, count);
-  return check_launch("bf16_to_f32");
+  return launch_k("bf16_to_f32", bf16_to_f32_kernel, dim3(grid_for(count, 256)), dim3(256), 0, (cudaStream_t)stream, dim3(1, 1, 1), (const __nv_bfloat16*)x, y, count);
 }
 
 extern "C" int sdeo_softmax_rows(const float* x, void* y, int32_t rows, int32_t cols, int32_t ldx, int32_t ldy, float scale,
                                  void* stream) {
   if (!x || !y || rows <= 0 || cols <= 0 || ldx < cols || ldy < cols) return set_error(SDEO_EINVAL, "softmax_rows: bad args");
-  softmax_rows_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, cols, ldx, ldy,
-                                                              scale * 1.4426950408889634f);
-  return check_launch("softmax_rows");
+  return launch_k("softmax_rows", softmax_rows_kernel, dim3(rows), dim3(256), 0, (cudaStream_t)stream, dim3(1, 1, 1), x, (__nv_bfloat16*)y, cols, ldx, ldy, scale * 1.4426950408889634f);
 }
 
 extern "C" int sdeo_image_to_u8(const void* x, uint8_t* y, int32_t npix, int32_t c, int32_t ldx, void* stream) {
   if (!x || !y || npix <= 0 || c <= 0 || ldx < c) return set_error(SDEO_EINVAL, "image_to_u8: bad args");
-  image_to_u8_kernel<<<grid_for((long long)npix * c, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, y, npix, c, ldx);
-  return check_launch("image_to_u8");
+  return launch_k("image_to_u8", image_to_u8_kernel, dim3(grid_for((long long)npix * c, 256)), dim3(256), 0, (cudaStream_t)stream, dim3(1, 1, 1), (const __nv_bfloat16*)x, y, npix, c, ldx);
 }

@@ -46,6 +46,7 @@ struct ConvKParams {
   int epi_mode, act, y_fp32;
   const float* bias;
   const float* emb;
+  const int* emb_step;  // table mode: every sample adds row *emb_step of emb (device-side DDIM step counter)
   const void* residual;
   int ldr, residual_f32;
   float scale;
@@ -83,6 +84,12 @@ __device__ __forceinline__ uint32_t dsmem_addr(uint32_t local_smem_addr, uint32_
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
   return r;
+}
+__device__ __forceinline__ void st_dsmem_f4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void st_smem_f4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr) {
   float4 v;
@@ -395,31 +402,59 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   if (threadIdx.x == 0) SDEO_DBG(1);
+  // PDL: the next kernel of the stream may start its prologue / weight prefetch from here on. (Not earlier: a
+  // successor CTA co-resident on this SM must not win the TMEM allocation while this CTA still needs its own -- it
+  // would hold the columns until this grid completes, i.e. forever.)
+  griddep_launch_dependents();
+  // PDL: activations, residual, emb and the output buffers belong to earlier kernels of the stream until the grid
+  // dependency resolves. Only the TMA thread goes on without waiting: it first streams WEIGHT tiles (constants).
+  if (threadIdx.x != 0) griddep_wait();
 
   const int LD = p.BN + 4;  // fp32 tile row pitch in floats: 16-byte aligned rows, conflict-free 16 B row writes
   float* tile = reinterpret_cast<float*>(tiles);
+  if (threadIdx.x >= 128 && threadIdx.x < 256) {
+    // output pixel of every tile row (-1: padding row / outside the image), read by epilogue phase 2
+    const int row = (int)threadIdx.x - 128;
+    const int per_img = p.bh * p.bw;
+    const int nl = row / per_img;
+    const int rem = row % per_img;
+    const int hl = rem / p.bw, wl = rem % p.bw;
+    const int nn = n0 + nl, hh = h0 + hl, ww = w0 + wl;
+    const bool ok = (row < p.rows_valid) && (nn < p.N) && (hh < p.Ho) && (ww < p.Wo);
+    row_pix[row] = ok ? (nn * p.Ho + hh) * p.Wo + ww : -1;
+  }
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     // (all ring / tap / chunk indices advance incrementally: no integer division on the per-chunk path)
     if (lane == 0) {
       const uint32_t tx_bytes = (uint32_t)(p.rows_valid + p.BN) * 128u;
+      const int nb0 = n_tile * p.BN;
+      // the first ring pass needs no empty-slot wait; its weight tiles are requested before the grid dependency
+      // resolves, so the weight stream of this layer overlaps the tail of the previous kernel
+      const int npre = nchunks < p.stages ? nchunks : p.stages;
+      for (int i = 0; i < npre; ++i) {
+        mbar_expect_tx(&full_bar[i], tx_bytes);
+        tma_load_2d(tiles + (size_t)i * stage_bytes + kATileBytes, &tmB, &full_bar[i], (k_begin + i) * kBK, nb0);
+      }
+      griddep_wait();
       int s = 0;
       uint32_t ph = 0;
       int tap = k_begin / p.chunks_per_tap, within = k_begin % p.chunks_per_tap;
       int ky = tap / p.kw, kx = tap % p.kw;
       uint8_t* a_dst = tiles;
-      const int nb0 = n_tile * p.BN;
       for (int i = 0; i < nchunks; ++i) {
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        mbar_expect_tx(&full_bar[s], tx_bytes);
+        if (i >= npre) {
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_expect_tx(&full_bar[s], tx_bytes);
+        }
         const int wc = w0 * p.stride + kx - p.pad;
         const int hc = h0 * p.stride + ky - p.pad;
         if (within < p.c1_chunks)
           tma_load_4d(a_dst, &tmA1, &full_bar[s], within * kBK, wc, hc, n0);
         else
           tma_load_4d(a_dst, &tmA2, &full_bar[s], (within - p.c1_chunks) * kBK, wc, hc, n0);
-        tma_load_2d(a_dst + kATileBytes, &tmB, &full_bar[s], (k_begin + i) * kBK, nb0);
+        if (i >= npre) tma_load_2d(a_dst + kATileBytes, &tmB, &full_bar[s], (k_begin + i) * kBK, nb0);
         if (++within == p.chunks_per_tap) {
           within = 0;
           if (++kx == p.kw) { kx = 0; ++ky; }
@@ -473,47 +508,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       __syncwarp();
       if (lane == 0) SDEO_DBG(3);
     }
-  } else if (warp < 6) {
-    // ===================== epilogue phase 1: TMEM -> fp32 tile in shared memory (thread = row) =====================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = quarter * 32 + lane;
-    const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    {  // output pixel of this tile row (-1: padding row / outside the image), shared with phase 2
-      const int per_img = p.bh * p.bw;
-      const int nl = row / per_img;
-      const int rem = row % per_img;
-      const int hl = rem / p.bw, wl = rem % p.bw;
-      const int nn = n0 + nl, hh = h0 + hl, ww = w0 + wl;
-      const bool ok = (row < p.rows_valid) && (nn < p.N) && (hh < p.Ho) && (ww < p.Wo);
-      row_pix[row] = ok ? (nn * p.Ho + hh) * p.Wo + ww : -1;
-    }
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    if (threadIdx.x == 64) SDEO_DBG(4);
-    float* trow = tile + (size_t)row * LD;
-    int c = 0;
-    for (; c + 32 <= p.BN; c += 32) {
-      uint32_t r[32];
-      tmem_ld32(taddr_row + (uint32_t)c, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int g = 0; g < 8; ++g)
-        *reinterpret_cast<float4*>(trow + c + 4 * g) =
-            make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
-                        __uint_as_float(r[4 * g + 3]));
-    }
-    if (c < p.BN) {
-      uint32_t r[16];
-      tmem_ld16(taddr_row + (uint32_t)c, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int g = 0; g < 4; ++g)
-        *reinterpret_cast<float4*>(trow + c + 4 * g) =
-            make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
-                        __uint_as_float(r[4 * g + 3]));
-    }
-    tc_fence_before();
-    if (threadIdx.x == 64) SDEO_DBG(5);
   }
 
   if (MODE == SDEO_EPI_NORMAL && FAST && RES != RES_NONE && warp >= 6 && p.res_smem_off) {
@@ -546,24 +540,62 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
   }
 
-  // ---- partial tiles complete: CTA-wide (S == 1) or cluster-wide (S > 1) barrier ----
+  // ===================== epilogue phase 1: TMEM -> fp32 rows in shared memory, all 12 warps =====================
+  // A warp may read the TMEM lane quarter (warp % 4); the three warps of a quarter split the columns in 32-wide
+  // chunks. S == 1: rows land in this CTA's own tile (the drained pipeline stages). S > 1 (split-K cluster): every
+  // row is PUSHED through distributed shared memory (st.shared::cluster, fire-and-forget) into the shared memory of
+  // the CTA that owns it: owner r reduces rows [r*rows_per, (r+1)*rows_per) and receives one slice per K-slice rank,
+  // laid out [S][rows_per][LD]. Cluster barrier #1 makes sure every peer's MMAs have finished reading the pipeline
+  // stages the slices overwrite; barrier #2 publishes the pushes. No global workspace, no remote loads, no atomics.
   __syncwarp();
-  const size_t ws_tile_floats = (size_t)kBM * LD;
-  const float* ws_tile0 = nullptr;  // partial of K-slice 0 of this output tile
-  if (p.splits > 1 && p.ws) {
-    // publish this CTA's partial tile to the L2-resident workspace with coalesced 16-byte stores: the reduction then
-    // reads all S partials with many independent global loads in flight (remote shared memory was measured slower)
-    __syncthreads();
-    const size_t tile_linear = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
-    float* ws_tile = p.ws + tile_linear * p.splits * ws_tile_floats;
-    ws_tile0 = ws_tile;
-    float4* dst = reinterpret_cast<float4*>(ws_tile + (size_t)split * ws_tile_floats);
-    const float4* src = reinterpret_cast<const float4*>(tile);
-    const int nvec = p.rows_valid * LD / 4;
-    for (int i = threadIdx.x; i < nvec; i += kConvThreads) dst[i] = src[i];
-    __threadfence();
+  const int S = p.splits;
+  const int rows_per = (p.rows_valid + S - 1) / S;
+  mbar_wait(tmem_full_bar, 0);
+  tc_fence_after();
+  if (threadIdx.x == 64) SDEO_DBG(4);
+  if (S > 1) cluster_sync_all();
+  {
+    const int quarter = warp & 3, third = warp >> 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    uint32_t dst_row;  // shared::cluster address of this row's first column
+    if (S > 1) {
+      const int owner = row < p.rows_valid ? row / rows_per : split;
+      const int lrow = row < p.rows_valid ? row - owner * rows_per : 0;
+      dst_row = dsmem_addr(smem_u32(tile), (uint32_t)owner) + (uint32_t)(((split * rows_per + lrow) * LD) * 4);
+    } else {
+      dst_row = smem_u32(tile) + (uint32_t)(row * LD * 4);  // own shared memory (shared::cta window)
+    }
+    const bool live = (S == 1) || (row < p.rows_valid);
+    for (int c = third * 32; c < p.BN; c += 96) {
+      if (c + 32 <= p.BN) {
+        uint32_t r[32];
+        tmem_ld32(taddr_row + (uint32_t)c, r);
+        tmem_ld_wait();
+        if (live) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            if (S > 1) st_dsmem_f4(dst_row + (uint32_t)((c + 4 * g) * 4), r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
+            else st_smem_f4(dst_row + (uint32_t)((c + 4 * g) * 4), r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
+          }
+        }
+      } else {
+        uint32_t r[16];
+        tmem_ld16(taddr_row + (uint32_t)c, r);
+        tmem_ld_wait();
+        if (live) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (S > 1) st_dsmem_f4(dst_row + (uint32_t)((c + 4 * g) * 4), r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
+            else st_smem_f4(dst_row + (uint32_t)((c + 4 * g) * 4), r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
+          }
+        }
+      }
+    }
+    tc_fence_before();
   }
-  if (p.splits > 1) cluster_sync_all();
+  if (threadIdx.x == 64) SDEO_DBG(5);
+  if (S > 1) cluster_sync_all();
   else __syncthreads();
 
   if (threadIdx.x == 64) SDEO_DBG(6);
@@ -574,15 +606,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     // index advances without divisions (row / column stepping by the constant thread count).
     constexpr int U = 2;  // measured: U = 4 is slower (register pressure, longer dependent chains in split mode)
     constexpr bool geglu = (MODE == SDEO_EPI_GEGLU);
-    const int S = p.splits;
-    const int rows_per = (p.rows_valid + S - 1) / S;
     const int r_begin = split * rows_per;
     const int r_end = min(p.rows_valid, r_begin + rows_per);
     const int cols_items = geglu ? p.BN / 16 : p.BN / 8;  // items per row
-    const uint32_t tile_saddr = smem_u32(tile);
     const int n_base = n_tile * p.BN;
+    const uint32_t slice_bytes = (uint32_t)(rows_per * LD) * 4u;  // S > 1: one received slice per K-slice rank
     const int hw_out = p.Ho * p.Wo;
     const int half = p.BN / 2;
+    const int emb_row_fixed = (p.emb && p.emb_step) ? __ldg(p.emb_step) : -1;
     const int step_rows = kConvThreads / cols_items, step_cols = kConvThreads % cols_items;
     int row = r_begin + (int)threadIdx.x / cols_items;
     int ci = (int)threadIdx.x % cols_items;
@@ -595,7 +626,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       for (int u = 0; u < U; ++u) {
         pixs[u] = -1;
         cols[u] = ci * 8;
-        offs[u] = (uint32_t)(((size_t)(row < r_end ? row : r_begin) * LD + cols[u]) * sizeof(float));
+        // S == 1: the tile is indexed by the tile row; S > 1: slices hold this CTA's rows only (row - r_begin)
+        offs[u] = (uint32_t)(((size_t)(row < r_end ? row - (S > 1 ? r_begin : 0) : 0) * LD + cols[u]) * sizeof(float));
         if (row < r_end) {
           pixs[u] = row_pix[row];
           if (MODE == SDEO_EPI_NORMAL && FAST && RES != RES_NONE && pixs[u] >= 0 && p.res_smem_off) {
@@ -632,59 +664,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           }
         }
       } else {
-        // distributed-shared-memory reduction: all S partial vectors of an item are requested before the first
-        // add (remote shared memory latency is ~1k cycles under load), summed in rank order (deterministic)
+        // the S partial vectors of an item sit in this CTA's own shared memory (pushed by the peers): summed in rank
+        // order, so the result does not depend on timing
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          float4 a[kMaxCluster], b[kMaxCluster];
 #pragma unroll
-          for (int s = 0; s < kMaxCluster; ++s) {
-            if (s < S) {
-              if (ws_tile0) {
-                const float4* gp = reinterpret_cast<const float4*>(
-                    reinterpret_cast<const uint8_t*>(ws_tile0 + (size_t)s * ws_tile_floats) + offs[u]);
-                a[s] = __ldcg(gp);
-                b[s] = __ldcg(gp + 1);
-              } else {
-                const uint32_t peer = dsmem_addr(tile_saddr, (uint32_t)s) + offs[u];
-                a[s] = ld_dsmem_f4(peer);
-                b[s] = ld_dsmem_f4(peer + 16);
-              }
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[u][j] = 0.f;
-#pragma unroll
-          for (int s = 0; s < kMaxCluster; ++s) {
-            if (s < S) {
-              v[u][0] += a[s].x; v[u][1] += a[s].y; v[u][2] += a[s].z; v[u][3] += a[s].w;
-              v[u][4] += b[s].x; v[u][5] += b[s].y; v[u][6] += b[s].z; v[u][7] += b[s].w;
-            }
-          }
-          if (geglu) {
-#pragma unroll
-            for (int s = 0; s < kMaxCluster; ++s) {
-              if (s < S) {
-                if (ws_tile0) {
-                  const float4* gp = reinterpret_cast<const float4*>(
-                      reinterpret_cast<const uint8_t*>(ws_tile0 + (size_t)s * ws_tile_floats) + offs[u] + (size_t)half * 4u);
-                  a[s] = __ldcg(gp);
-                  b[s] = __ldcg(gp + 1);
-                } else {
-                  const uint32_t peer = dsmem_addr(tile_saddr, (uint32_t)s) + offs[u] + (uint32_t)half * 4u;
-                  a[s] = ld_dsmem_f4(peer);
-                  b[s] = ld_dsmem_f4(peer + 16);
-                }
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) g[u][j] = 0.f;
-#pragma unroll
-            for (int s = 0; s < kMaxCluster; ++s) {
-              if (s < S) {
-                g[u][0] += a[s].x; g[u][1] += a[s].y; g[u][2] += a[s].z; g[u][3] += a[s].w;
-                g[u][4] += b[s].x; g[u][5] += b[s].y; g[u][6] += b[s].z; g[u][7] += b[s].w;
-              }
+          for (int j = 0; j < 8; ++j) { v[u][j] = 0.f; g[u][j] = 0.f; }
+          const uint8_t* src0 = reinterpret_cast<const uint8_t*>(tile) + offs[u];
+          for (int s = 0; s < S; ++s) {
+            const float* src = reinterpret_cast<const float*>(src0 + (size_t)s * slice_bytes);
+            const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+            v[u][0] += a.x; v[u][1] += a.y; v[u][2] += a.z; v[u][3] += a.w;
+            v[u][4] += b.x; v[u][5] += b.y; v[u][6] += b.z; v[u][7] += b.w;
+            if (geglu) {
+              const float4 c2 = *reinterpret_cast<const float4*>(src + half), d2 = *reinterpret_cast<const float4*>(src + half + 4);
+              g[u][0] += c2.x; g[u][1] += c2.y; g[u][2] += c2.z; g[u][3] += c2.w;
+              g[u][4] += d2.x; g[u][5] += d2.y; g[u][6] += d2.z; g[u][7] += d2.w;
             }
           }
         }
@@ -700,9 +695,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           RowInfo ri; ri.valid = true; ri.pix = pixs[u]; ri.batch = 0;
           epi_qkv_item(p, ri, n_base + col, v[u]);
         } else if (FAST) {
-          epi_normal_fast<OUT, RES>(p, (long long)pixs[u], p.emb ? pixs[u] / hw_out : 0, n_base + col, v[u], raw0[u], raw1[u]);
+          epi_normal_fast<OUT, RES>(p, (long long)pixs[u], p.emb ? (emb_row_fixed >= 0 ? emb_row_fixed : pixs[u] / hw_out) : 0, n_base + col, v[u], raw0[u], raw1[u]);
         } else {
-          RowInfo ri; ri.valid = true; ri.pix = pixs[u]; ri.batch = p.emb ? pixs[u] / hw_out : 0;
+          RowInfo ri; ri.valid = true; ri.pix = pixs[u]; ri.batch = p.emb ? (emb_row_fixed >= 0 ? emb_row_fixed : pixs[u] / hw_out) : 0;
           epi_normal_item(p, ri, n_base + col, v[u], false, raw0[u], raw1[u]);
         }
       }
@@ -711,11 +706,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   }
 
   if (threadIdx.x == 64) SDEO_DBG(7);
-  // ---- teardown: nobody may exit while a peer still reads its tile through DSMEM ----
+  // ---- teardown (no peer touches this CTA's shared memory after cluster barrier #2) ----
   tc_fence_before();
-  __syncwarp();
-  if (p.splits > 1) cluster_sync_all();
-  else __syncthreads();
+  __syncthreads();
   if (threadIdx.x == 64) SDEO_DBG(8);
   if (warp == 1) {
     tc_fence_after();
@@ -876,7 +869,8 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl, int force_bn = 0, i
   pl->splits = (pl->total_chunks + pl->cps - 1) / pl->cps;  // every slice gets >= 1 chunk
   // ---- smem / tmem ----
   const int stage_bytes = kATileBytes + pl->BN * 128;
-  const int tile_bytes = kBM * (pl->BN + 4) * 4;  // fp32 epilogue tile, aliases the pipeline stages
+  // fp32 epilogue tile, aliases the pipeline stages; split-K: S slices of ceil(rows/S) rows (up to S - 1 extra rows)
+  const int tile_bytes = (kBM + (pl->splits > 1 ? kMaxCluster : 0)) * (pl->BN + 4) * 4;
   int stages = (208 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages > pl->cps) stages = pl->cps < 2 ? 2 : pl->cps;
@@ -1076,7 +1070,7 @@ static int launch_conv(const sdeo_conv_args* a, const ConvPlan& pl, void* stream
   p.N = a->n; p.Ho = pl.Ho; p.Wo = pl.Wo;
   p.BN = pl.BN; p.cout = a->cout; p.stages = pl.stages; p.tmem_cols = pl.tmem_cols;
   p.epi_mode = a->epi_mode; p.act = a->act; p.y_fp32 = a->y_fp32;
-  p.bias = a->bias; p.emb = a->emb; p.residual = a->residual; p.ldr = a->ldr;
+  p.bias = a->bias; p.emb = a->emb; p.emb_step = a->emb ? a->emb_step : nullptr; p.residual = a->residual; p.ldr = a->ldr;
   p.scale = a->scale; p.y = a->y; p.ldy = a->ldy;
   p.residual_f32 = a->residual_f32;
   p.y2 = (a->y_fp32 && a->epi_mode == SDEO_EPI_NORMAL) ? (__nv_bfloat16*)a->y2 : nullptr;
@@ -1088,11 +1082,7 @@ static int launch_conv(const sdeo_conv_args* a, const ConvPlan& pl, void* stream
   p.res_smem_off = pl.res_smem_off;
   p.a_tmem = getenv("SDEO_A_TMEM") ? 1 : 0;  // measured: no gain over A from shared memory; kept as an option
   p.a_tmem_col = pl.tmem_cols - 64;
-  p.ws = nullptr;
-  if (pl.splits > 1 && a->workspace && !getenv("SDEO_SPLITK_DSMEM")) {
-    const size_t need = (size_t)cfg_tiles(pl) * pl.splits * kBM * (pl.BN + 4) * sizeof(float);
-    if (need <= a->workspace_bytes) p.ws = (float*)a->workspace;
-  }
+  p.ws = nullptr;  // (split-K partials travel through distributed shared memory; the workspace argument is unused)
 
   // ---- pick the kernel instantiation ----
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvKParams);
@@ -1132,19 +1122,6 @@ static int launch_conv(const sdeo_conv_args* a, const ConvPlan& pl, void* stream
       if (n_configured < 16) configured[n_configured++] = fn;
     }
   }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(pl.tiles_n * pl.tiles_h * pl.tiles_w), (unsigned)pl.n_tiles, (unsigned)pl.splits);
-  cfg.blockDim = dim3(kConvThreads);
-  cfg.dynamicSmemBytes = pl.smem_bytes;
-  cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = (unsigned)pl.splits;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, fn, tmA1, tmA2, tmB, p);
-  if (e != cudaSuccess) return set_error(SDEO_ECUDA, cudaGetErrorString(e));
-  return check_launch("conv2d");
+  return launch_k("conv2d", fn, dim3((unsigned)(pl.tiles_n * pl.tiles_h * pl.tiles_w), (unsigned)pl.n_tiles, (unsigned)pl.splits),
+                  dim3(kConvThreads), pl.smem_bytes, (cudaStream_t)stream, dim3(1, 1, (unsigned)pl.splits), tmA1, tmA2, tmB, p);
 }

@@ -3,6 +3,7 @@
 #include <cudaTypedefs.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace sdeo {
 
@@ -19,6 +20,16 @@ int check_launch(const char* what) {
   snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
   return SDEO_ECUDA;
 }
+
+static int g_pdl = -1;
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("SDEO_NO_PDL");
+    g_pdl = (e && e[0] && e[0] != '0') ? 0 : 1;
+  }
+  return g_pdl != 0;
+}
+void set_pdl(int on) { g_pdl = on ? 1 : 0; }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -70,6 +81,10 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
 
 extern "C" const char* sdeo_last_error(void) { return sdeo::g_err; }
 extern "C" int sdeo_version(void) { return 1; }
+extern "C" int sdeo_set_pdl(int enable) {
+  sdeo::set_pdl(enable);
+  return SDEO_OK;
+}
 extern "C" int sdeo_memset_async(void* p, int value, size_t bytes, void* stream) {
   cudaError_t e = cudaMemsetAsync(p, value, bytes, (cudaStream_t)stream);
   if (e != cudaSuccess) return sdeo::set_error(SDEO_ECUDA, cudaGetErrorString(e));

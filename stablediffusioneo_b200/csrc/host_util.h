@@ -17,4 +17,42 @@ int check_launch(const char* what);
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                      const uint32_t* box, const uint32_t* elem_strides);
 
+// Programmatic dependent launch switch (default on; SDEO_NO_PDL=1 or sdeo_set_pdl(0) turns it off).
+bool pdl_enabled();
+
+// Launches `fn` with an optional thread-block cluster and, when enabled, the programmatic-stream-serialization
+// attribute. EVERY kernel launched through here must execute griddep_wait() before its first access to memory that an
+// earlier kernel wrote or still reads (common.cuh).
+template <typename... KArgs, typename... Args>
+int launch_k(const char* what, void (*fn)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, dim3 cluster,
+             Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cluster.x * cluster.y * cluster.z > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster.x;
+    attr[na].val.clusterDim.y = cluster.y;
+    attr[na].val.clusterDim.z = cluster.z;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = (unsigned)na;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, fn, static_cast<KArgs>(args)...);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return set_error(-5 /* SDEO_ECUDA */, cudaGetErrorString(e));
+  }
+  return check_launch(what);
+}
+
 }  // namespace sdeo

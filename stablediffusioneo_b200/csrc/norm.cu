@@ -34,6 +34,8 @@ template <typename T>
 __global__ void __launch_bounds__(kGNThreads)
 gn_stats_kernel(const T* __restrict__ x1, const T* __restrict__ x2, float* __restrict__ ws,
                 int hw, int c1, int c2, int groups, int chunks, int ppc) {
+  griddep_launch_dependents();
+  griddep_wait();
   extern __shared__ float sm[];
   const int C = c1 + c2;
   const int cv = C / 8;
@@ -100,6 +102,8 @@ gn_apply_kernel(const T* __restrict__ x1, const T* __restrict__ x2,
                 const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ ws,
                 __nv_bfloat16* __restrict__ y, int hw, int c1, int c2, int groups, int chunks, int ppc, float eps,
                 int with_silu) {
+  griddep_launch_dependents();
+  griddep_wait();
   __shared__ float s_mean[64], s_rstd[64];
   const int C = c1 + c2;
   const int cv = C / 8;
@@ -170,6 +174,8 @@ __global__ void __launch_bounds__(kGNCThreads)
 gn_cluster_kernel(const T* __restrict__ x1, const T* __restrict__ x2, const float* __restrict__ gamma,
                   const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int hw, int c1, int c2, int groups,
                   float eps, int with_silu) {
+  griddep_launch_dependents();
+  griddep_wait();
   extern __shared__ float sm[];
   __shared__ float grp[128];            // [2][groups] this CTA's partial sums, read by the peers
   __shared__ float s_mean[64], s_rstd[64];
@@ -307,22 +313,9 @@ static int launch_gn_cluster(const void* x1, const void* x2, const float* gamma,
     if (e != cudaSuccess) return set_error(SDEO_ECUDA, cudaGetErrorString(e));
     attr_set = true;
   }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(kGNCluster, (unsigned)n);
-  cfg.blockDim = dim3(kGNCThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kGNCluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gn_cluster_kernel<T>, (const T*)x1, (const T*)x2, gamma, beta, (__nv_bfloat16*)y, hw,
-                                     c1, c2, groups, eps, with_silu);
-  if (e != cudaSuccess) return set_error(SDEO_ECUDA, cudaGetErrorString(e));
-  return check_launch("groupnorm (cluster)");
+  return launch_k("groupnorm (cluster)", gn_cluster_kernel<T>, dim3(kGNCluster, (unsigned)n), dim3(kGNCThreads), smem, st,
+                  dim3(kGNCluster, 1, 1), (const T*)x1, (const T*)x2, gamma, beta, (__nv_bfloat16*)y, hw, c1, c2, groups, eps,
+                  with_silu);
 }
 
 static void gn_geometry(int n, int hw, int* chunks, int* ppc) {
@@ -342,6 +335,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  __nv_bfloat16* __restrict__ y, int rows, int C, float eps) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -439,23 +434,22 @@ extern "C" int sdeo_groupnorm_nhwc(const void* x1, const void* x2, int32_t x_f32
   }
   dim3 grid((unsigned)chunks, (unsigned)n);
   cudaStream_t st = (cudaStream_t)stream;
+  const dim3 one(1, 1, 1);
+  int rc;
   if (x_f32)
-    gn_stats_kernel<float><<<grid, kGNThreads, smem, st>>>((const float*)x1, (const float*)x2, (float*)workspace, hw, c1, c2,
-                                                           groups, chunks, ppc);
+    rc = launch_k("groupnorm stats", gn_stats_kernel<float>, grid, dim3(kGNThreads), smem, st, one, (const float*)x1,
+                  (const float*)x2, (float*)workspace, hw, c1, c2, groups, chunks, ppc);
   else
-    gn_stats_kernel<__nv_bfloat16><<<grid, kGNThreads, smem, st>>>((const __nv_bfloat16*)x1, (const __nv_bfloat16*)x2,
-                                                                   (float*)workspace, hw, c1, c2, groups, chunks, ppc);
-  int rc = check_launch("groupnorm stats");
+    rc = launch_k("groupnorm stats", gn_stats_kernel<__nv_bfloat16>, grid, dim3(kGNThreads), smem, st, one,
+                  (const __nv_bfloat16*)x1, (const __nv_bfloat16*)x2, (float*)workspace, hw, c1, c2, groups, chunks, ppc);
   if (rc) return rc;
   if (x_f32)
-    gn_apply_kernel<float><<<grid, kGNThreads, 0, st>>>((const float*)x1, (const float*)x2, gamma, beta,
-                                                        (const float*)workspace, (__nv_bfloat16*)y, hw, c1, c2, groups,
-                                                        chunks, ppc, eps, with_silu);
-  else
-    gn_apply_kernel<__nv_bfloat16><<<grid, kGNThreads, 0, st>>>((const __nv_bfloat16*)x1, (const __nv_bfloat16*)x2, gamma,
-                                                                beta, (const float*)workspace, (__nv_bfloat16*)y, hw, c1,
-                                                                c2, groups, chunks, ppc, eps, with_silu);
-  return check_launch("groupnorm apply");
+    return launch_k("groupnorm apply", gn_apply_kernel<float>, grid, dim3(kGNThreads), 0, st, one, (const float*)x1,
+                    (const float*)x2, gamma, beta, (const float*)workspace, (__nv_bfloat16*)y, hw, c1, c2, groups, chunks,
+                    ppc, eps, with_silu);
+  return launch_k("groupnorm apply", gn_apply_kernel<__nv_bfloat16>, grid, dim3(kGNThreads), 0, st, one,
+                  (const __nv_bfloat16*)x1, (const __nv_bfloat16*)x2, gamma, beta, (const float*)workspace,
+                  (__nv_bfloat16*)y, hw, c1, c2, groups, chunks, ppc, eps, with_silu);
 }
 
 extern "C" int sdeo_layernorm(const void* x, int32_t x_f32, const float* gamma, const float* beta, void* y, int32_t rows,
@@ -464,11 +458,10 @@ extern "C" int sdeo_layernorm(const void* x, int32_t x_f32, const float* gamma, 
   if (rows <= 0 || c % 8 != 0 || c > kLNMaxVec * 32 * 8) return set_error(SDEO_EINVAL, "layernorm: need C % 8 == 0 and C <= 2048");
   const int warps_per_block = 8;
   const int blocks = (rows + warps_per_block - 1) / warps_per_block;
+  const dim3 one(1, 1, 1);
   if (x_f32)
-    layernorm_kernel<float><<<blocks, warps_per_block * 32, 0, (cudaStream_t)stream>>>((const float*)x, gamma, beta,
-                                                                                       (__nv_bfloat16*)y, rows, c, eps);
-  else
-    layernorm_kernel<__nv_bfloat16><<<blocks, warps_per_block * 32, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)x, gamma, beta, (__nv_bfloat16*)y, rows, c, eps);
-  return check_launch("layernorm");
+    return launch_k("layernorm", layernorm_kernel<float>, dim3(blocks), dim3(warps_per_block * 32), 0, (cudaStream_t)stream,
+                    one, (const float*)x, gamma, beta, (__nv_bfloat16*)y, rows, c, eps);
+  return launch_k("layernorm", layernorm_kernel<__nv_bfloat16>, dim3(blocks), dim3(warps_per_block * 32), 0,
+                  (cudaStream_t)stream, one, (const __nv_bfloat16*)x, gamma, beta, (__nv_bfloat16*)y, rows, c, eps);
 }

@@ -163,7 +163,7 @@ class Conv2d(nn.Conv2d):
     def bias_f32(self):
         return self.bias.detach() if self.bias is not None else None
 
-    def run(self, x, emb=None, residual=None, scale=1.0, act=SDEO_ACT_NONE, out_fp32=False, stream=False):
+    def run(self, x, emb=None, residual=None, scale=1.0, act=SDEO_ACT_NONE, out_fp32=False, stream=False, emb_step=None):
         """x: internal tensor (bf16 or fp32 stream) or CatPair. Returns an internal bf16 tensor; fp32 NHWC-physical when
         out_fp32; an fp32 stream tensor with a bf16 twin when `stream`. A bf16 output whose channel count is not a
         multiple of 8 is zero-padded to one (so a following conv can TMA it)."""
@@ -178,7 +178,7 @@ class Conv2d(nn.Conv2d):
             out = torch.empty((n, ho, wo, (cout + 7) // 8 * 8), dtype=BF16, device=self.weight.device)
             ops.memset(out, 0)
         kw = dict(bias=self.bias_f32(), emb=emb, residual=res, scale=scale, act=act, stride=self.stride[0],
-                  out_fp32=out_fp32 or stream, out=out, twin=stream)
+                  out_fp32=out_fp32 or stream, out=out, twin=stream, emb_step=emb_step)
         if isinstance(x, CatPair):
             a, b = operand(x.a), operand(x.b)
             y = ops.conv2d(nhwc(a), self.packed((a.shape[1], b.shape[1])), x2=nhwc(b), **kw)

@@ -132,9 +132,11 @@ def pack_geglu_bias(bias, geglu_bn):
 
 
 def conv2d(x, pw, x2=None, bias=None, emb=None, residual=None, scale=1.0, act=SDEO_ACT_NONE, stride=1, out=None,
-           out_fp32=False, epi_mode=SDEO_EPI_NORMAL, qkv=None, twin=False):
+           out_fp32=False, epi_mode=SDEO_EPI_NORMAL, qkv=None, twin=False, emb_step=None):
     """x: [N,H,W,C1] bf16 (+ optional x2 [N,H,W,C2] = fused torch.cat along channels). Returns [N,Ho,Wo,cout].
-    residual may be bf16 or fp32. out_fp32 + twin=True additionally writes a bf16 copy and returns (y_f32, y_bf16)."""
+    residual may be bf16 or fp32. out_fp32 + twin=True additionally writes a bf16 copy and returns (y_f32, y_bf16).
+    emb: fp32 [N, cout] (row = sample), or with emb_step (int32 device scalar) a table [S, cout] whose row *emb_step is
+    added to every sample."""
     lib = _lib.load()
     _req(x, BF16, "x")
     _req(x2, BF16, "x2")
@@ -164,6 +166,9 @@ def conv2d(x, pw, x2=None, bias=None, emb=None, residual=None, scale=1.0, act=SD
     a.cout, a.ksize, a.stride, a.pad = pw.cout, k, stride, pad
     a.epi_mode, a.act = epi_mode, act
     a.bias, a.emb = _ptr(bias), _ptr(emb)
+    if emb_step is not None:
+        _req(emb_step, torch.int32, "emb_step")
+        a.emb_step = _ptr(emb_step)
     a.scale = float(scale)
     a.y_fp32 = 1 if out_fp32 else 0
     if epi_mode == SDEO_EPI_QKV:

@@ -14,8 +14,11 @@ BF = torch.bfloat16
 ap = argparse.ArgumentParser()
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--only", default="")
+ap.add_argument("--autotune", action="store_true")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
+if args.autotune:
+    ops.set_autotune(True)
 
 # (name, n, h, w, c1, c2, cout, k, stride, mode)  mode: plain | stream | geglu | qkv
 CASES = [
