@@ -33,6 +33,7 @@ SIGNATURES = {
     "sdeo_last_error": (c_char_p, []),
     "sdeo_version": (c_int, []),
     "sdeo_set_pdl": (c_int, [c_int]),
+    "sdeo_set_trace": (c_int, [c_void_p]),
     "sdeo_conv_workspace_bytes": (c_size_t, [POINTER(ConvArgs)]),
     "sdeo_conv_counter_bytes": (c_size_t, []),
     "sdeo_conv2d": (c_int, [POINTER(ConvArgs), c_void_p]),

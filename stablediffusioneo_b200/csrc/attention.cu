@@ -4,16 +4,22 @@
 // Layouts (produced by the QKV epilogue of gemm_conv.cu): q,k [B*heads, n, d] bf16; vt [B*heads, d, ldv] bf16
 // (V transposed, so every MMA operand is K-major); o [B, nq, heads*d] bf16.
 // One CTA per (128-query tile, batch*head). Warp 0: TMA producer. Warp 1: TMEM allocator + MMA issuer.
-// Warps 2..5: softmax / O-rescale / epilogue.
+// Warps 2..9: softmax / O-rescale / epilogue, two threads per query row (64 of the 128 S columns each).
 #include "common.cuh"
 #include "host_util.h"
 #include "../../include/sdeo.h"
 
 namespace sdeo {
 
-constexpr int kAttThreads = 192;
+constexpr int kAttThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 softmax (two threads per query row)
 constexpr int kTileQ = 128;
 constexpr int kTileKV = 128;
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 struct AttParams {
   int nq, nkv, d, heads;
@@ -49,11 +55,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* p_full = bars + 6;
   uint64_t* o_done = bars + 7;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+  float* s_xchg = reinterpret_cast<float*>(bars + 16);  // [2][128] partner exchange (row max / row sum)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q_tile = blockIdx.x;
   const int bh = blockIdx.y;
   const int n_kv_tiles = (p.nkv + kTileKV - 1) / kTileKV;
+  const int trc = trace_start(2);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -80,7 +88,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t tmem_S = tmem_base;          // 128 columns
   const uint32_t tmem_O = tmem_base + 128;    // dv16 columns
   griddep_launch_dependents();  // PDL (after this CTA's own TMEM allocation, see gemm_conv.cu)
-  griddep_wait();  // q/k/v are written by the preceding projection kernels; o may still be read by an earlier one
+  griddep_wait();  trace_mark(trc, 2);  // q/k/v are written by the preceding projection kernels; o may still be read by an earlier one
 
   if (warp == 0) {
     if (lane == 0) {
@@ -103,7 +111,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const uint32_t q_addr = smem_u32(sQ);
       const uint32_t p_addr = smem_u32(sP);
       const uint32_t idesc_pv = umma_idesc_bf16(128, (uint32_t)p.dv16);
-      for (int j = 0; j < n_kv_tiles; ++j) {
+      // S(j) = Q K_j^T : M=128 (queries), N=kv16, K=dk16
+      auto issue_s = [&](int j) {
         const int s = j % p.kv_stages;
         const uint32_t ph = (uint32_t)(j / p.kv_stages) & 1u;
         const int kv_cols = min(kTileKV, p.nkv - j * kTileKV);
@@ -111,8 +120,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_wait(&kv_full[s], ph);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sKV + (size_t)s * kv_stage_bytes);
-        const uint32_t v_addr = k_addr + (uint32_t)k_bytes;
-        // ---- S = Q K^T : M=128 (queries), N=kv16, K=dk16 ----
         const uint32_t idesc_s = umma_idesc_bf16(128, (uint32_t)kv16);
         for (int kk = 0; kk < p.dk16 / 16; ++kk) {
           const int c = kk >> 2, ki = kk & 3;
@@ -121,9 +128,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tc_mma_bf16(tmem_S, a_desc, b_desc, idesc_s, kk > 0 ? 1u : 0u);
         }
         tc_commit(s_full);
-        // ---- O += P V : M=128, N=dv16, K=kv16 ----
+      };
+      issue_s(0);
+      for (int j = 0; j < n_kv_tiles; ++j) {
+        const int s = j % p.kv_stages;
+        const int kv_cols = min(kTileKV, p.nkv - j * kTileKV);
+        const int kv16 = (kv_cols + 15) & ~15;
+        const uint32_t v_addr = smem_u32(sKV + (size_t)s * kv_stage_bytes) + (uint32_t)k_bytes;
+        // the softmax warps have read S(j) into registers and written P(j) once p_full(j) completes: S(j+1) may
+        // overwrite the S columns now and runs on the tensor pipe ahead of PV(j), so that the next tile's row
+        // maxima overlap this tile's PV (needs the second K/V stage; with one stage K_{j+1} waits for PV(j))
         mbar_wait(p_full, (uint32_t)j & 1u);
         tc_fence_after();
+        if (j + 1 < n_kv_tiles && p.kv_stages > 1) issue_s(j + 1);
+        // ---- O += P V : M=128, N=dv16, K=kv16 ----
         for (int kk = 0; kk < kv16 / 16; ++kk) {
           const int c = kk >> 2, ki = kk & 3;
           const uint64_t a_desc = umma_desc_k_sw128(p_addr + (uint32_t)(c * kTileQ * 128)) + (uint64_t)(2 * ki);
@@ -132,71 +150,73 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         tc_commit(&kv_empty[s]);
         tc_commit(o_done);
+        if (j + 1 < n_kv_tiles && p.kv_stages == 1) issue_s(j + 1);
       }
     }
   } else {
-    // ===================== softmax / correction / epilogue: thread = query row =====================
+    // ===================== softmax / correction / epilogue: TWO threads per query row =====================
+    // warps 2..5 take columns [0, 64) of the 128-wide S tile, warps 6..9 columns [64, 128); the partners of a row
+    // exchange their partial row maximum (per tile) and row sum (once, at the end) through shared memory.
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const int st = threadIdx.x - 64;  // 0..127
-    float m_run = -INFINITY;  // running max of s * scale_log2
-    float l_run = 0.f;
-    uint8_t* p_row = sP + row * 128;
+    const int st = threadIdx.x - 64;  // 0..255
+    float m_run = -INFINITY;  // running max of s * scale_log2 (identical in both partners)
+    float l_run = 0.f;        // running sum over this thread's columns
+    uint8_t* p_row = sP + half * (kTileQ * 128) + row * 128;  // this thread's 64 columns = one 128-byte chunk row
+    const int n_oc = p.dv16 / 16;                 // 16-column chunks of O
+    const int oc_begin = half == 0 ? 0 : (n_oc + 1) / 2, oc_end = half == 0 ? (n_oc + 1) / 2 : n_oc;
 
     for (int j = 0; j < n_kv_tiles; ++j) {
       const int kv_cols = min(kTileKV, p.nkv - j * kTileKV);
-      const int n32 = (kv_cols + 31) / 32;
+      const int ncols = min(64, max(0, kv_cols - half * 64));  // valid columns among this thread's 64
       mbar_wait(s_full, (uint32_t)j & 1u);
       tc_fence_after();
-      // pass 1: row max
-      float m_tile = -INFINITY;
-      for (int c = 0; c < n32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_S + lane_off + (uint32_t)(c * 32), r);
-        tmem_ld_wait();
+      uint32_t r0[32], r1[32];
+      if (ncols > 0) tmem_ld32(tmem_S + lane_off + (uint32_t)(half * 64), r0);
+      if (ncols > 32) tmem_ld32(tmem_S + lane_off + (uint32_t)(half * 64 + 32), r1);
+      tmem_ld_wait();
+      float m_loc = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < kv_cols) m_tile = fmaxf(m_tile, __uint_as_float(r[i]));
+      for (int i = 0; i < 32; ++i) {
+        if (i < ncols) m_loc = fmaxf(m_loc, __uint_as_float(r0[i]));
+        if (32 + i < ncols) m_loc = fmaxf(m_loc, __uint_as_float(r1[i]));
       }
+      s_xchg[half * kTileQ + row] = m_loc;
+      bar_sync(2, 256);
+      const float m_tile = fmaxf(m_loc, s_xchg[(half ^ 1) * kTileQ + row]);
       const float m_new = fmaxf(m_run, m_tile * p.scale_log2);
-      const float alpha = exp2f(m_run - m_new);  // 0 on the first tile (m_run = -inf)
-      // previous PV must have finished reading P (and updating O) before we overwrite either
+      const float alpha = fast_exp2(m_run - m_new);  // 0 on the first tile (m_run = -inf)
+      // previous PV must have finished reading P (and updating O) before either is overwritten
       if (j > 0) {
         mbar_wait(o_done, (uint32_t)(j - 1) & 1u);
         tc_fence_after();
       }
-      // pass 2: p = exp2(s*scale - m_new), write bf16 P (swizzled K-major), accumulate row sum
       float l_tile = 0.f;
-      for (int c = 0; c < n32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_S + lane_off + (uint32_t)(c * 32), r);
-        tmem_ld_wait();
-        float pv[32];
+      if (half * 64 < ((kv_cols + 15) & ~15)) {  // the PV contraction reads this chunk
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float e = exp2f(__uint_as_float(r[i]) * p.scale_log2 - m_new);
-          pv[i] = (c * 32 + i < kv_cols) ? e : 0.f;
-          l_tile += pv[i];
-        }
-        // 32 columns = 4 16-byte units in chunk (c / 2), units (c & 1) * 4 .. +3
-        uint8_t* chunk_base = p_row + (c >> 1) * (kTileQ * 128);
+        for (int u = 0; u < 8; ++u) {
+          float pv[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int unit = (c & 1) * 4 + u;
+          for (int i = 0; i < 8; ++i) {
+            const int cidx = u * 8 + i;
+            const float sv = __uint_as_float(cidx < 32 ? r0[cidx & 31] : r1[cidx & 31]);
+            const float e = fast_exp2(sv * p.scale_log2 - m_new);
+            pv[i] = (cidx < ncols) ? e : 0.f;
+            l_tile += pv[i];
+          }
           uint4 v;
-          v.x = pack_bf16x2(pv[u * 8 + 0], pv[u * 8 + 1]);
-          v.y = pack_bf16x2(pv[u * 8 + 2], pv[u * 8 + 3]);
-          v.z = pack_bf16x2(pv[u * 8 + 4], pv[u * 8 + 5]);
-          v.w = pack_bf16x2(pv[u * 8 + 6], pv[u * 8 + 7]);
-          *reinterpret_cast<uint4*>(chunk_base + ((unit ^ (row & 7)) << 4)) = v;
+          v.x = pack_bf16x2(pv[0], pv[1]); v.y = pack_bf16x2(pv[2], pv[3]);
+          v.z = pack_bf16x2(pv[4], pv[5]); v.w = pack_bf16x2(pv[6], pv[7]);
+          *reinterpret_cast<uint4*>(p_row + ((u ^ (row & 7)) << 4)) = v;
         }
       }
       l_run = l_run * alpha + l_tile;
       m_run = m_new;
-      // rescale O (skip when no row of this warp moved its max; never needed on the first tile)
+      // rescale this thread's share of the O columns (skipped when no row of the warp moved its max)
       if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
-        for (int c = 0; c < p.dv16 / 16; ++c) {
+        for (int c = oc_begin; c < oc_end; ++c) {
           uint32_t r[16];
           tmem_ld16(tmem_O + lane_off + (uint32_t)(c * 16), r);
           tmem_ld_wait();
@@ -208,17 +228,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      bar_sync(1, 128);
+      bar_sync(1, 256);
       if (st == 0) mbar_arrive(p_full);
     }
     // ---- epilogue: O / l -> bf16 [B, nq, heads*d] ----
+    s_xchg[half * kTileQ + row] = l_run;
+    bar_sync(2, 256);
+    const float inv_l = 1.0f / (l_run + s_xchg[(half ^ 1) * kTileQ + row]);
     mbar_wait(o_done, (uint32_t)(n_kv_tiles - 1) & 1u);
     tc_fence_after();
-    const float inv_l = 1.0f / l_run;
     const int qi = q_tile * kTileQ + row;
     const int b = bh / p.heads, head = bh % p.heads;
     __nv_bfloat16* orow = p.o + ((size_t)b * p.nq + qi) * ((size_t)p.heads * p.d) + (size_t)head * p.d;
-    for (int c = 0; c < p.dv16 / 16; ++c) {
+    for (int c = oc_begin; c < oc_end; ++c) {
       uint32_t r[16];
       tmem_ld16(tmem_O + lane_off + (uint32_t)(c * 16), r);
       tmem_ld_wait();
@@ -241,6 +263,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  trace_mark(trc, 3);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
@@ -250,6 +273,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 }  // namespace sdeo
 
 using namespace sdeo;
+SDEO_DEFINE_TRACE_SETTER(sdeo_trace_set_attention)
 
 extern "C" int sdeo_attention(const void* q, const void* k, const void* vt, void* o, int32_t batch, int32_t heads,
                               int32_t nq, int32_t nkv, int32_t d, int32_t ldv, float scale, void* stream) {
@@ -267,7 +291,7 @@ extern "C" int sdeo_attention(const void* q, const void* k, const void* vt, void
   p.o = (__nv_bfloat16*)o;
   const int q_bytes = p.nkc * kTileQ * 128;
   const int kv_stage = p.nkc * kTileKV * 128 + 2 * p.dv16 * 128;
-  const int fixed = q_bytes + 2 * kTileQ * 128 + 1024 + 128;
+  const int fixed = q_bytes + 2 * kTileQ * 128 + 1024 + 128 + 2 * kTileQ * 4;
   p.kv_stages = (fixed + 2 * kv_stage <= 220 * 1024 && nkv > kTileKV) ? 2 : 1;
   const size_t smem = (size_t)fixed + (size_t)p.kv_stages * kv_stage;
   int tc = 32;

@@ -39,6 +39,35 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// ---------------------------------------------------------------------------------------------
+// optional kernel timeline (sdeo_set_trace): block (0,0,0) thread 0 of every kernel records
+// [tag, t_start, t_dependency_resolved, t_end] (globaltimer ns) into a caller-provided buffer:
+// buf[0] = record count (atomic), buf[1] = capacity, records from buf[4]. One pointer per translation unit.
+// ---------------------------------------------------------------------------------------------
+static __device__ unsigned long long* g_sdeo_trace = nullptr;
+__device__ __forceinline__ unsigned long long sdeo_gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ int trace_start(unsigned long long tag) {
+  if ((blockIdx.x | blockIdx.y | blockIdx.z | threadIdx.x | threadIdx.y) != 0) return -1;
+  unsigned long long* b = g_sdeo_trace;
+  if (!b) return -1;
+  const unsigned long long i = atomicAdd(b, 1ULL);
+  if (i >= b[1]) return -1;
+  b[4 + 4 * i] = tag | ((unsigned long long)(gridDim.x * gridDim.y * gridDim.z) << 8);
+  b[4 + 4 * i + 1] = sdeo_gtime();
+  return (int)i;
+}
+__device__ __forceinline__ void trace_mark(int i, int slot) {
+  if (i >= 0) g_sdeo_trace[4 + 4 * (unsigned long long)i + slot] = sdeo_gtime();
+}
+#define SDEO_DEFINE_TRACE_SETTER(name)                                                       \
+  extern "C" int name(void* buf) {                                                           \
+    return cudaMemcpyToSymbol(sdeo::g_sdeo_trace, &buf, sizeof(void*)) == cudaSuccess ? 0 : -5; \
+  }
+
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
 // exact-erf GELU (F.gelu default in the reference, attention.py:56)

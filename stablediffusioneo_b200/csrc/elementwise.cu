@@ -13,8 +13,11 @@ __global__ void cfg_ddim_kernel(const float* __restrict__ eps_c, const float* __
                                 __nv_bfloat16* __restrict__ x_next, int dup, int ldn,
                                 const float* __restrict__ coef_table, const int* __restrict__ step_idx, int n, int c,
                                 int hw) {
+  const int trc = trace_start(5);
   griddep_launch_dependents();
   griddep_wait();
+  trace_mark(trc, 2);
+  trace_mark(trc, 3);
   const int row = step_idx ? *step_idx : 0;
   const float* cf = coef_table + (size_t)row * 8;
   const float s = cf[0], sqrt_1m_at = cf[1], rsqrt_at = cf[2], sqrt_aprev = cf[3], dir_coef = cf[4], sigma = cf[5];
@@ -50,8 +53,11 @@ __global__ void cfg_ddim_kernel(const float* __restrict__ eps_c, const float* __
 }
 
 __global__ void counter_add_kernel(int* ctr, int delta) {
+  const int trc = trace_start(5);
   griddep_launch_dependents();
   griddep_wait();
+  trace_mark(trc, 2);
+  trace_mark(trc, 3);
   *ctr += delta;
 }
 
@@ -59,8 +65,11 @@ __global__ void counter_add_kernel(int* ctr, int delta) {
 // NCHW fp32 -> NHWC bf16 (zero-padded to ldy channels). One thread per (pixel, channel-slot).
 __global__ void nchw_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int c,
                                          int hw, int ldy, float scale) {
+  const int trc = trace_start(5);
   griddep_launch_dependents();
   griddep_wait();
+  trace_mark(trc, 2);
+  trace_mark(trc, 3);
   // tile transpose through shared memory: 32 channels x 32 pixels
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
@@ -79,8 +88,11 @@ __global__ void nchw_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloa
 template <typename TIn>
 __global__ void nhwc_to_nchw_f32_kernel(const TIn* __restrict__ x, float* __restrict__ y, int n, int c, int hw,
                                         int ldx) {
+  const int trc = trace_start(5);
   griddep_launch_dependents();
   griddep_wait();
+  trace_mark(trc, 2);
+  trace_mark(trc, 3);
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -99,8 +111,11 @@ __global__ void nhwc_to_nchw_f32_kernel(const TIn* __restrict__ x, float* __rest
 
 // ---- nearest x2 upsample, NHWC, 16-byte vectors ---------------------------------------------------
 __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int n, int h, int w, int cv) {
+  const int trc = trace_start(5);
   griddep_launch_dependents();
   griddep_wait();
+  trace_mark(trc, 2);
+  trace_mark(trc, 3);
   const long long total = (long long)n * (2 * h) * (2 * w) * cv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -118,8 +133,11 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict
 __global__ void add_scaled_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, float alpha,
                                   uint4* __restrict__ y, long long nvec, const __nv_bfloat16* a_s,
                                   const __nv_bfloat16* b_s, __nv_bfloat16* y_s, long long count) {
+  const int trc = trace_start(5);
   griddep_launch_dependents();
   griddep_wait();
+  trace_mark(trc, 2);
+  trace_mark(trc, 3);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
     const uint4 av = a[i], bv = b[i];
@@ -142,8 +160,11 @@ __global__ void add_scaled_kernel(const uint4* __restrict__ a, const uint4* __re
 // ---- timestep embedding: [cos(t f_i) | sin(t f_i)], f_i = exp(-ln(max_period) i / half) ------------
 __global__ void timestep_embedding_kernel(const long long* __restrict__ t, const int* __restrict__ step_idx,
                                           __nv_bfloat16* __restrict__ y, int n, int dim, int ldy, float max_period) {
+  const int trc = trace_start(5);
   griddep_launch_dependents();
   griddep_wait();
+  trace_mark(trc, 2);
+  trace_mark(trc, 3);
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * ldy) return;
@@ -160,22 +181,31 @@ __global__ void timestep_embedding_kernel(const long long* __restrict__ t, const
 }
 
 __global__ void silu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long count) {
+  const int trc = trace_start(5);
   griddep_launch_dependents();
   griddep_wait();
+  trace_mark(trc, 2);
+  trace_mark(trc, 3);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
        i += (long long)gridDim.x * blockDim.x)
     y[i] = __float2bfloat16(silu_f(__bfloat162float(x[i])));
 }
 __global__ void f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long count) {
+  const int trc = trace_start(5);
   griddep_launch_dependents();
   griddep_wait();
+  trace_mark(trc, 2);
+  trace_mark(trc, 3);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
        i += (long long)gridDim.x * blockDim.x)
     y[i] = __float2bfloat16(x[i]);
 }
 __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, long long count) {
+  const int trc = trace_start(5);
   griddep_launch_dependents();
   griddep_wait();
+  trace_mark(trc, 2);
+  trace_mark(trc, 3);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
        i += (long long)gridDim.x * blockDim.x)
     y[i] = __bfloat162float(x[i]);
@@ -185,8 +215,11 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ x, float* _
 __global__ void __launch_bounds__(256)
 softmax_rows_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int cols, int ld, int ldy,
                     float scale_log2) {
+  const int trc = trace_start(5);
   griddep_launch_dependents();
   griddep_wait();
+  trace_mark(trc, 2);
+  trace_mark(trc, 3);
   __shared__ float red[8];
   __shared__ float bcast;
   const float* xr = x + (size_t)blockIdx.x * ld;
@@ -225,8 +258,11 @@ softmax_rows_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, 
 
 __global__ void image_to_u8_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ y, long long npix, int c,
                                    int ldx) {
+  const int trc = trace_start(5);
   griddep_launch_dependents();
   griddep_wait();
+  trace_mark(trc, 2);
+  trace_mark(trc, 3);
   const long long total = npix * c;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -248,6 +284,7 @@ static int grid_for(long long work, int threads) {
 }  // namespace sdeo
 
 using namespace sdeo;
+SDEO_DEFINE_TRACE_SETTER(sdeo_trace_set_elementwise)
 
 extern "C" int sdeo_cfg_ddim_step(const float* eps_c, const float* eps_u, int32_t eps_nhwc, int32_t ld_eps, const float* x,
                                   const float* noise, float* x_prev, float* pred_x0, void* x_next, int32_t dup, int32_t ldn,

@@ -382,6 +382,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   const int nchunks = k_end - k_begin;
 
   if (threadIdx.x == 0) SDEO_DBG(0);
+  const int trc = trace_start(1ULL | ((unsigned long long)MODE << 40) | ((unsigned long long)p.splits << 44) |
+                              ((unsigned long long)p.BN << 48));
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmB);
@@ -438,6 +440,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         tma_load_2d(tiles + (size_t)i * stage_bytes + kATileBytes, &tmB, &full_bar[i], (k_begin + i) * kBK, nb0);
       }
       griddep_wait();
+      trace_mark(trc, 2);
       int s = 0;
       uint32_t ph = 0;
       int tap = k_begin / p.chunks_per_tap, within = k_begin % p.chunks_per_tap;
@@ -709,6 +712,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   // ---- teardown (no peer touches this CTA's shared memory after cluster barrier #2) ----
   tc_fence_before();
   __syncthreads();
+  trace_mark(trc, 3);
   if (threadIdx.x == 64) SDEO_DBG(8);
   if (warp == 1) {
     tc_fence_after();
@@ -900,6 +904,7 @@ static inline int cfg_tiles(const ConvPlan& pl) { return pl.tiles_n * pl.tiles_h
 }  // namespace sdeo
 
 using namespace sdeo;
+SDEO_DEFINE_TRACE_SETTER(sdeo_trace_set_conv)
 
 extern "C" size_t sdeo_conv_counter_bytes(void) { return 0; }
 

@@ -81,6 +81,14 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
 
 extern "C" const char* sdeo_last_error(void) { return sdeo::g_err; }
 extern "C" int sdeo_version(void) { return 1; }
+extern "C" int sdeo_trace_set_conv(void*);
+extern "C" int sdeo_trace_set_attention(void*);
+extern "C" int sdeo_trace_set_norm(void*);
+extern "C" int sdeo_trace_set_elementwise(void*);
+extern "C" int sdeo_set_trace(void* buf) {
+  int rc = sdeo_trace_set_conv(buf) | sdeo_trace_set_attention(buf) | sdeo_trace_set_norm(buf) | sdeo_trace_set_elementwise(buf);
+  return rc ? sdeo::set_error(SDEO_ECUDA, "set_trace: cudaMemcpyToSymbol failed") : SDEO_OK;
+}
 extern "C" int sdeo_set_pdl(int enable) {
   sdeo::set_pdl(enable);
   return SDEO_OK;

@@ -66,7 +66,7 @@ class _Workspaces:
         key = (device.index, self.slot)
         ws = self._gn.get(key)
         if ws is None or ws.numel() < nbytes:
-            ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+            ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)  # barrier words start at zero
             self._gn[key] = ws
         return ws
 

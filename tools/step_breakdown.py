@@ -55,7 +55,7 @@ def wrap(name, keyfn):
 
 
 def conv_key(x, pw, x2=None, bias=None, emb=None, residual=None, scale=1.0, act=0, stride=1, out=None, out_fp32=False,
-             epi_mode=0, qkv=None, twin=False):
+             epi_mode=0, qkv=None, twin=False, emb_step=None):
     n, hh, ww, _ = x.shape
     k = pw.ksize
     ho, wo = (hh + 2 * (k // 2) - k) // stride + 1, (ww + 2 * (k // 2) - k) // stride + 1
