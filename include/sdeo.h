@@ -124,9 +124,7 @@ int sdeo_pack_geglu_bias(const float* b, int32_t n2, int32_t geglu_bn, float* b_
  * Follows PyTorch numerics (eps applied, fp32 statistics), not the plugin's eps-less variance.
  * x2 != NULL normalises torch.cat([x1, x2], dim=1) and writes the concatenated result.
  * ---------------------------------------------------------------------------------------------- */
-/* The workspace must be ZERO-INITIALISED once by the caller before its first use (its first 256 bytes hold the arrival
- * counters of the single-launch variant's inter-CTA barrier; the kernel leaves them ready for the next call) and must
- * not be shared by calls that may run concurrently (one workspace per stream). */
+/* One workspace per stream: calls that may run concurrently must not share it. */
 size_t sdeo_groupnorm_workspace_bytes(int32_t n, int32_t hw, int32_t groups);
 /* x1/x2: bf16, or fp32 when x_f32 != 0 (fp32 residual-stream tensors); y is always bf16. */
 int sdeo_groupnorm_nhwc(const void* x1, const void* x2, int32_t x_f32, const float* gamma, const float* beta, void* y,

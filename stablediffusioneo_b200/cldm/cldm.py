@@ -34,9 +34,13 @@ class ControlledUnetModel(UNetModel):
         h = self.middle_block.run(h, emb, context)
         return hs, h
 
-    def run_decoder(self, h, hs, emb, context):
+    def run_decoder(self, h, hs, emb, context, before_block=None):
+        """before_block(k): optional hook called before output block k reads its skip tensor hs[len(hs) - 1 - k]
+        (the step engine waits there for the zero conv that produced it on the side stream)."""
         hs = list(hs)
-        for module in self.output_blocks:
+        for k, module in enumerate(self.output_blocks):
+            if before_block is not None:
+                before_block(k)
             h = module.run(CatPair(h, hs.pop()), emb, context)
         return self.run_out(h)
 
@@ -171,18 +175,22 @@ class ControlNet(nn.Module):
         feats.append(self.middle_block.run(h, emb, context))
         return feats
 
-    def run_zero_convs(self, feats, scales=None, add_to=None, only_mid=False):
-        """13 outputs: scale_i * zero_conv_i(h_i) [+ add_to[i]] (only_mid: entries 0..11 are add_to[i] untouched)."""
+    def run_zero_convs(self, feats, scales=None, add_to=None, only_mid=False, order=None, after=None):
+        """13 outputs: scale_i * zero_conv_i(h_i) [+ add_to[i]] (only_mid: entries 0..11 are add_to[i] untouched).
+        order: launch order of the 13 convs (default 0..12); after(i): hook called once output i has been enqueued."""
         scales = [1.0] * (len(self.zero_convs) + 1) if scales is None else list(scales)
         convs = [z[0] for z in self.zero_convs] + [self.middle_block_out[0]]
-        outs = []
-        for i, (conv, h) in enumerate(zip(convs, feats)):
+        outs = [None] * len(convs)
+        for i in (range(len(convs)) if order is None else order):
+            conv, h = convs[i], feats[i]
             last = i == len(convs) - 1
             if only_mid and add_to is not None and not last:
-                outs.append(add_to[i])
+                outs[i] = add_to[i]
             else:
-                outs.append(conv.run(h, scale=scales[i], residual=add_to[i] if add_to is not None else None,
-                                     stream=util.STREAM_FP32))
+                outs[i] = conv.run(h, scale=scales[i], residual=add_to[i] if add_to is not None else None,
+                                   stream=util.STREAM_FP32)
+            if after is not None:
+                after(i)
         return outs
 
     def run(self, x, guided_hint, emb, context, scales=None, add_to=None, only_mid=False):

@@ -326,12 +326,26 @@ class _Engine:
             with torch.cuda.stream(side), ops.workspace_slot(1):
                 feats = cn.run_body(x, self.guided, self.emb_c, self.ctx)
             hs, h = unet.run_encoder(x, emb_u, self.ctx)
-            main.wait_stream(side)
-            outs = cn.run_zero_convs(feats, scales=m.control_scales, add_to=hs + [h], only_mid=m.only_mid_control)
+            # the 13 zero convs (+ control scale + add onto the UNet skips) stay on the side stream, launched in the
+            # order the decoder consumes them; the decoder waits per tensor, so only the first ones are on its path
+            side.wait_stream(main)
+            n_out = len(hs) + 1
+            if getattr(self, "_zc_events", None) is None:
+                self._zc_events = [torch.cuda.Event() for _ in range(n_out)]
+            evs = self._zc_events
+            with torch.cuda.stream(side), ops.workspace_slot(1):
+                outs = cn.run_zero_convs(feats, scales=m.control_scales, add_to=hs + [h], only_mid=m.only_mid_control,
+                                         order=range(n_out - 1, -1, -1), after=lambda i: evs[i].record(side))
+            main.wait_event(evs[n_out - 1])
+            # the encoder outputs are read (as residuals) by the side stream: keep them alive until the step has been
+            # enqueued, or main's allocator would hand their memory to the decoder while the zero convs still read it
+            enc_keep = (hs, h)  # noqa: F841
             hs, h = outs[:-1], outs[-1]
+            eps = nhwc(unet.run_decoder(h, hs, self.emb_u, self.ctx,
+                                        before_block=lambda k: main.wait_event(evs[n_out - 2 - k])))
         else:
             hs, h = unet.run_encoder(x, emb_u, self.ctx)
-        eps = nhwc(unet.run_decoder(h, hs, emb_u, self.ctx))          # fp32 [nb, h, w, 4]
+            eps = nhwc(unet.run_decoder(h, hs, emb_u, self.ctx))          # fp32 [nb, h, w, 4]
         eps_c = eps[:b]
         eps_u = eps[b:] if self.dup == 2 else None
         ops.cfg_ddim_step(eps_c, eps_u, self.x_lat, self.coef, step_idx=self.step_ctr, x_prev=self.x_lat,

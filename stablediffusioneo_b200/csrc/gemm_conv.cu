@@ -88,6 +88,20 @@ __device__ __forceinline__ uint32_t dsmem_addr(uint32_t local_smem_addr, uint32_
 __device__ __forceinline__ void st_dsmem_f4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ void cluster_arrive() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// bulk copy of `bytes` (multiple of 16) from this CTA's shared memory into a peer's, completing on the PEER's mbarrier
+__device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes,
+                                                uint32_t mbar_cluster_addr) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   dst_cluster_addr),
+               "r"(src_cta_addr), "r"(bytes), "r"(mbar_cluster_addr)
+               : "memory");
+}
 __device__ __forceinline__ void st_smem_f4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -361,6 +375,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   uint64_t* empty_bar = full_bar + 16;
   uint64_t* tmem_full_bar = empty_bar + 16;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* recv_bar = full_bar + 48;  // split-K: completes when all S partial slices of this CTA's rows have arrived
   int* row_pix = reinterpret_cast<int*>(smem + 512);  // [128] output pixel index per tile row
   uint8_t* tiles = smem + 1024;
   const int stage_bytes = kATileBytes + p.BN * 128;
@@ -393,7 +408,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
+    mbar_init(recv_bar, 1);
     fence_mbar_init();
+    if (p.splits > 1) {
+      // bytes this CTA will receive: one slice of its own rows from each of the S K-slice ranks (armed here, long
+      // before any peer can push: pushes start after a cluster barrier this CTA has not arrived at yet)
+      const int rp = (p.rows_valid + p.splits - 1) / p.splits;
+      int mine = min(p.rows_valid, (split + 1) * rp) - split * rp;
+      if (mine < 0) mine = 0;
+      mbar_expect_tx(recv_bar, (uint32_t)(p.splits * mine * (p.BN + 4) * 4));
+    }
   }
   if (warp == 1) {
     tmem_alloc(tmem_ptr_smem, (uint32_t)p.tmem_cols);
@@ -543,33 +567,30 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
   }
 
-  // ===================== epilogue phase 1: TMEM -> fp32 rows in shared memory, all 12 warps =====================
+  // ===================== epilogue phase 1: TMEM -> fp32 tile in shared memory, all 12 warps =====================
   // A warp may read the TMEM lane quarter (warp % 4); the three warps of a quarter split the columns in 32-wide
-  // chunks. S == 1: rows land in this CTA's own tile (the drained pipeline stages). S > 1 (split-K cluster): every
-  // row is PUSHED through distributed shared memory (st.shared::cluster, fire-and-forget) into the shared memory of
-  // the CTA that owns it: owner r reduces rows [r*rows_per, (r+1)*rows_per) and receives one slice per K-slice rank,
-  // laid out [S][rows_per][LD]. Cluster barrier #1 makes sure every peer's MMAs have finished reading the pipeline
-  // stages the slices overwrite; barrier #2 publishes the pushes. No global workspace, no remote loads, no atomics.
+  // chunks; rows land in this CTA's own tile (the drained pipeline stages).
+  // Split-K (S > 1, one cluster per output tile): CTA r reduces rows [r*rows_per, (r+1)*rows_per). After its tile is
+  // complete every CTA sends, for each owner r, the contiguous rows_per x LD block of its tile with ONE asynchronous
+  // bulk copy through distributed shared memory (cp.async.bulk.shared::cluster) into slot [own rank] of the owner's
+  // receive area [S][rows_per][LD]; the copy completes on the owner's mbarrier, which doubles as the "all partials are
+  // here" signal. The first cluster barrier (arrive right after the accumulator is complete, wait after phase 1) only
+  // guards the receive areas, which alias the peers' pipeline stages; the second (arrive after the slices are in, wait
+  // at teardown) keeps every CTA's shared memory alive until its outgoing copies have been read.
   __syncwarp();
   const int S = p.splits;
   const int rows_per = (p.rows_valid + S - 1) / S;
+  float* recv = tile + (size_t)p.rows_valid * LD;  // S > 1 only: right behind the valid rows of the tile
   mbar_wait(tmem_full_bar, 0);
   tc_fence_after();
   if (threadIdx.x == 64) SDEO_DBG(4);
-  if (S > 1) cluster_sync_all();
+  if (S > 1) cluster_arrive();
   {
     const int quarter = warp & 3, third = warp >> 2;
     const int row = quarter * 32 + lane;
     const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    uint32_t dst_row;  // shared::cluster address of this row's first column
-    if (S > 1) {
-      const int owner = row < p.rows_valid ? row / rows_per : split;
-      const int lrow = row < p.rows_valid ? row - owner * rows_per : 0;
-      dst_row = dsmem_addr(smem_u32(tile), (uint32_t)owner) + (uint32_t)(((split * rows_per + lrow) * LD) * 4);
-    } else {
-      dst_row = smem_u32(tile) + (uint32_t)(row * LD * 4);  // own shared memory (shared::cta window)
-    }
-    const bool live = (S == 1) || (row < p.rows_valid);
+    const uint32_t dst_row = smem_u32(tile) + (uint32_t)(row * LD * 4);
+    const bool live = (S == 1) || (row < p.rows_valid);  // split-K: the receive area starts right behind the valid rows
     for (int c = third * 32; c < p.BN; c += 96) {
       if (c + 32 <= p.BN) {
         uint32_t r[32];
@@ -577,10 +598,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         tmem_ld_wait();
         if (live) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            if (S > 1) st_dsmem_f4(dst_row + (uint32_t)((c + 4 * g) * 4), r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
-            else st_smem_f4(dst_row + (uint32_t)((c + 4 * g) * 4), r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
-          }
+          for (int g = 0; g < 8; ++g) st_smem_f4(dst_row + (uint32_t)((c + 4 * g) * 4), r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
         }
       } else {
         uint32_t r[16];
@@ -588,18 +606,31 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         tmem_ld_wait();
         if (live) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (S > 1) st_dsmem_f4(dst_row + (uint32_t)((c + 4 * g) * 4), r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
-            else st_smem_f4(dst_row + (uint32_t)((c + 4 * g) * 4), r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
-          }
+          for (int g = 0; g < 4; ++g) st_smem_f4(dst_row + (uint32_t)((c + 4 * g) * 4), r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
         }
       }
     }
     tc_fence_before();
   }
   if (threadIdx.x == 64) SDEO_DBG(5);
-  if (S > 1) cluster_sync_all();
-  else __syncthreads();
+  if (S > 1) {
+    fence_proxy_async_smem();  // the tile was written by ordinary stores; the bulk copies read it through the async proxy
+    __syncthreads();
+    cluster_wait();            // every peer's MMAs are done: the receive areas are free
+    if (threadIdx.x < (unsigned)S) {
+      const int r = (int)threadIdx.x;
+      int rows_r = min(p.rows_valid, (r + 1) * rows_per) - r * rows_per;
+      if (rows_r > 0) {
+        const uint32_t src = smem_u32(tile) + (uint32_t)(r * rows_per * LD * 4);
+        const uint32_t dst = dsmem_addr(smem_u32(recv) + (uint32_t)(split * rows_per * LD * 4), (uint32_t)r);
+        dsmem_bulk_copy(dst, src, (uint32_t)(rows_r * LD * 4), dsmem_addr(smem_u32(recv_bar), (uint32_t)r));
+      }
+    }
+    mbar_wait(recv_bar, 0);
+    cluster_arrive();          // (waited for at teardown)
+  } else {
+    __syncthreads();
+  }
 
   if (threadIdx.x == 64) SDEO_DBG(6);
   {
@@ -673,7 +704,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         for (int u = 0; u < U; ++u) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) { v[u][j] = 0.f; g[u][j] = 0.f; }
-          const uint8_t* src0 = reinterpret_cast<const uint8_t*>(tile) + offs[u];
+          const uint8_t* src0 = reinterpret_cast<const uint8_t*>(recv) + offs[u];
           for (int s = 0; s < S; ++s) {
             const float* src = reinterpret_cast<const float*>(src0 + (size_t)s * slice_bytes);
             const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
@@ -709,8 +740,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   }
 
   if (threadIdx.x == 64) SDEO_DBG(7);
-  // ---- teardown (no peer touches this CTA's shared memory after cluster barrier #2) ----
+  // ---- teardown (split-K: peers may still be reading this CTA's tile until the second cluster barrier completes) ----
   tc_fence_before();
+  if (p.splits > 1) cluster_wait();
   __syncthreads();
   trace_mark(trc, 3);
   if (threadIdx.x == 64) SDEO_DBG(8);
@@ -872,31 +904,48 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl, int force_bn = 0, i
   pl->cps = (pl->total_chunks + splits - 1) / splits;
   pl->splits = (pl->total_chunks + pl->cps - 1) / pl->cps;  // every slice gets >= 1 chunk
   // ---- smem / tmem ----
+  const int kSmemMax = 227 * 1024, kFixed = 2048;  // 1 KB alignment slack + 1 KB barriers / row table
   const int stage_bytes = kATileBytes + pl->BN * 128;
-  // fp32 epilogue tile, aliases the pipeline stages; split-K: S slices of ceil(rows/S) rows (up to S - 1 extra rows)
-  const int tile_bytes = (kBM + (pl->splits > 1 ? kMaxCluster : 0)) * (pl->BN + 4) * 4;
-  int stages = (208 * 1024) / stage_bytes;
-  if (stages > 8) stages = 8;
-  if (stages > pl->cps) stages = pl->cps < 2 ? 2 : pl->cps;
-  // residual tile prefetched into shared memory by the otherwise idle warps, if >= 4 pipeline stages still fit
+  const int rows_valid = pl->bn_ * pl->bh * pl->bw;
+  // fp32 epilogue tile, aliases the pipeline stages. Split-K: the tile (valid rows only) plus the receive area
+  // [S][ceil(rows/S)][LD] the peers' bulk copies land in.
+  auto tile_bytes_for = [&](int sp) {
+    const int rp = (rows_valid + sp - 1) / sp;
+    return (sp > 1 ? rows_valid + sp * rp : kBM) * (pl->BN + 4) * 4;
+  };
+  if (pl->splits > 1 && kFixed + tile_bytes_for(pl->splits) > kSmemMax) {
+    if (force_splits > 0 || getenv("SDEO_FORCE_SPLITS")) return false;  // (the autotuner skips this candidate)
+    pl->splits = 1;
+    pl->cps = pl->total_chunks;
+  }
+  const int tile_bytes = tile_bytes_for(pl->splits);
+  auto stages_for = [&](int extra) {  // pipeline depth that fits next to `extra` bytes of residual buffer
+    if (kFixed + tile_bytes + extra > kSmemMax) return 0;
+    int st = (kSmemMax - kFixed - extra) / stage_bytes;
+    if (st > 8) st = 8;
+    if (st > pl->cps) st = pl->cps < 2 ? 2 : pl->cps;
+    return st;
+  };
+  int stages = stages_for(0);
+  if (stages < 2) return false;
+  // residual tile prefetched into shared memory by the otherwise idle warps, if enough pipeline stages still fit
   pl->res_smem_off = 0;
   int res_bytes = 0;
   if (a->residual && a->epi_mode == SDEO_EPI_NORMAL && !getenv("SDEO_NO_RES_PREFETCH")) {
     res_bytes = kBM * pl->BN * (a->residual_f32 ? 4 : 2);
-    int st2 = (208 * 1024 - res_bytes) / stage_bytes;
-    if (st2 > stages) st2 = stages;
-    const int need = pl->cps < 4 ? (pl->cps < 2 ? 2 : pl->cps) : 4;
-    if (st2 >= need && (size_t)st2 * stage_bytes >= (size_t)tile_bytes) stages = st2; else res_bytes = 0;
+    const int st2 = stages_for(res_bytes);
+    const int need = pl->cps < 3 ? (pl->cps < 2 ? 2 : pl->cps) : 3;
+    if (st2 >= need) stages = st2; else res_bytes = 0;
   }
   pl->stages = stages;
   size_t body = (size_t)stages * stage_bytes;
   if (body < (size_t)tile_bytes) body = tile_bytes;
   if (res_bytes) pl->res_smem_off = 1024 + (int)body;
-  pl->smem_bytes = 1024 /*align slack*/ + 1024 /*barriers*/ + body + res_bytes;
+  pl->smem_bytes = kFixed + body + res_bytes;
   int tc = 32;
   while (tc < pl->BN + 64) tc *= 2;  // accumulator + 2 x 32 columns of A staging
   pl->tmem_cols = tc;
-  return pl->smem_bytes <= 227 * 1024;
+  return pl->smem_bytes <= (size_t)kSmemMax;
 }
 
 static inline int cfg_tiles(const ConvPlan& pl) { return pl.tiles_n * pl.tiles_h * pl.tiles_w * pl.n_tiles; }

@@ -21,6 +21,23 @@ __device__ __forceinline__ void load8(const float* p, float* f) {
   f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
 
+__device__ __forceinline__ void load8_ro(const float* p, float* f) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// Stores 8 values back in the input's own dtype (exact round trip of load8).
+__device__ __forceinline__ void store8(float* p, const float* f) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float* f) {
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = o;
+}
+
 // Loads the 8-channel vector `v` (of the virtual concat [x1 | x2]) at pixel `pix`.
 template <typename T>
 __device__ __forceinline__ void gn_load8(const T* x1, const T* x2, int c1, int c2, long long pix, int v, float* f) {
@@ -108,7 +125,7 @@ gn_stats_kernel(const T* __restrict__ x1, const T* __restrict__ x2, float* __res
     float* out = ws + (((size_t)n * chunks + chunk) * groups + g) * 2;
     out[0] = s;
     out[1] = q;
-  }
+  }  trace_mark(trc, 3);
 }
 
 // Pass 2: finalize mean / rstd per group from the partials, normalise, affine, optional SiLU, store bf16.
@@ -171,13 +188,13 @@ gn_apply_kernel(const T* __restrict__ x1, const T* __restrict__ x2,
     const int v = vbase + tv;
     if (v >= cv) continue;
     float a[8], b[8];
+    load8_ro(gamma + v * 8, a);
+    load8_ro(beta + v * 8, b);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = v * 8 + j;
-      const int g = c / cpg;
-      const float ga = gamma[c] * s_rstd[g];
-      a[j] = ga;
-      b[j] = beta[c] - s_mean[g] * ga;
+      const int g = (v * 8 + j) / cpg;
+      a[j] *= s_rstd[g];
+      b[j] -= s_mean[g] * a[j];
     }
     int pp = p_begin + tr;
     for (; pp + 3 * R < p_end; pp += 4 * R) {  // 4 independent loads in flight per thread
@@ -221,32 +238,36 @@ gn_apply_kernel(const T* __restrict__ x1, const T* __restrict__ x2,
 // 2*groups partials through distributed shared memory (rank order: deterministic), then every CTA normalises its own
 // pixels (second read comes from L2). Replaces the stats + apply pair (2 launches, a global workspace round trip).
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kGNCluster = 8;
+constexpr int kGNCluster = 8;       // portable cluster size
+constexpr int kGNClusterBig = 16;   // non-portable size, used when a sample has enough rows
 constexpr int kGNCThreads = 512;
+constexpr int kGNCMaxSmem = 160 * 1024;
 
 template <typename T>
 __global__ void __launch_bounds__(kGNCThreads)
 gn_cluster_kernel(const T* __restrict__ x1, const T* __restrict__ x2, const float* __restrict__ gamma,
                   const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int hw, int c1, int c2, int groups,
-                  float eps, int with_silu) {
+                  float eps, int with_silu, int cache_rows) {
   const int trc = trace_start(3);
   griddep_launch_dependents();
   griddep_wait();
   trace_mark(trc, 2);
   trace_mark(trc, 3);
   extern __shared__ float sm[];
-  __shared__ float grp[128];            // [2][groups] this CTA's partial sums, read by the peers
+  __shared__ float2 all[kGNClusterBig * 64];  // [cluster rank][group] (sum, sumsq) partials of the whole cluster
   __shared__ float s_mean[64], s_rstd[64];
   const int C = c1 + c2;
   const int cv = C / 8;
   const int cpg = C / groups;
-  const int n = blockIdx.y, rank = blockIdx.x;  // cluster = the kGNCluster CTAs along x
-  const int ppc = (hw + kGNCluster - 1) / kGNCluster;
+  const int n = blockIdx.y, rank = blockIdx.x;  // cluster = the gridDim.x CTAs along x
+  const int csize = gridDim.x;
+  const int ppc = (hw + csize - 1) / csize;
   const int p_begin = rank * ppc;
   const int p_end = min(hw, p_begin + ppc);
   float* chan_sum = sm;        // [C]
   float* chan_sq = sm + C;     // [C]
   float* part = sm + 2 * C;    // [R][cols][16]
+  T* cache = reinterpret_cast<T*>(part + kGNCThreads * 16);  // [cache_rows][C]: this CTA's rows (pass 2 reads them here)
   const int cols = cv < kGNCThreads ? cv : kGNCThreads;
   const int R = kGNCThreads / cols;
   const int tr = threadIdx.x / cols, tv = threadIdx.x % cols;
@@ -265,6 +286,12 @@ gn_cluster_kernel(const T* __restrict__ x1, const T* __restrict__ x2, const floa
         gn_load8(x1, x2, c1, c2, (long long)n * hw + pp + R, v, f1);
         gn_load8(x1, x2, c1, c2, (long long)n * hw + pp + 2 * R, v, f2);
         gn_load8(x1, x2, c1, c2, (long long)n * hw + pp + 3 * R, v, f3);
+        if (cache_rows) {
+          store8(cache + (size_t)(pp - p_begin) * C + v * 8, f0);
+          store8(cache + (size_t)(pp + R - p_begin) * C + v * 8, f1);
+          store8(cache + (size_t)(pp + 2 * R - p_begin) * C + v * 8, f2);
+          store8(cache + (size_t)(pp + 3 * R - p_begin) * C + v * 8, f3);
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           s[j] += (f0[j] + f1[j]) + (f2[j] + f3[j]);
@@ -274,6 +301,7 @@ gn_cluster_kernel(const T* __restrict__ x1, const T* __restrict__ x2, const floa
       for (; pp < p_end; pp += R) {
         float f[8];
         gn_load8(x1, x2, c1, c2, (long long)n * hw + pp, v, f);
+        if (cache_rows) store8(cache + (size_t)(pp - p_begin) * C + v * 8, f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] += f[j] * f[j]; }
       }
@@ -297,27 +325,28 @@ gn_cluster_kernel(const T* __restrict__ x1, const T* __restrict__ x2, const floa
     }
     __syncthreads();
   }
+  // ---- exchange the partials across the cluster: every CTA PUSHES its (sum, sumsq) per group into the all[] array of
+  // every peer (remote stores are fire-and-forget; remote loads would cost one round trip each), one cluster barrier
+  // publishes them, then each CTA folds its local copy in rank order (deterministic) ----
   if (threadIdx.x < groups) {
     const int g = threadIdx.x;
     float s = 0.f, q = 0.f;
     for (int c = g * cpg; c < (g + 1) * cpg; ++c) { s += chan_sum[c]; q += chan_sq[c]; }
-    grp[g] = s;
-    grp[groups + g] = q;
+    const uint32_t slot = smem_u32(all) + (uint32_t)((rank * groups + g) * 8);
+    for (int r = 0; r < csize; ++r) {
+      uint32_t peer;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer) : "r"(slot), "r"(r));
+      asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(peer), "f"(s), "f"(q) : "memory");
+    }
   }
-  // ---- exchange the partials across the cluster ----
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   if (threadIdx.x < groups) {
     const int g = threadIdx.x;
     float s = 0.f, q = 0.f;
-    const uint32_t local = smem_u32(grp);
-    for (int r = 0; r < kGNCluster; ++r) {
-      uint32_t peer;
-      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer) : "r"(local), "r"(r));
-      float a, b;
-      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(a) : "r"(peer + (uint32_t)g * 4u));
-      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(b) : "r"(peer + (uint32_t)(groups + g) * 4u));
-      s += a;
-      q += b;
+    for (int r = 0; r < csize; ++r) {
+      const float2 v2 = all[r * groups + g];
+      s += v2.x;
+      q += v2.y;
     }
     const float inv = 1.0f / ((float)hw * (float)cpg);
     const float mean = s * inv;
@@ -326,8 +355,7 @@ gn_cluster_kernel(const T* __restrict__ x1, const T* __restrict__ x2, const floa
     s_mean[g] = mean;
     s_rstd[g] = rsqrtf(var + eps);
   }
-  // nobody may exit (or overwrite grp) while a peer still reads it; also publishes s_mean / s_rstd CTA-wide
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  __syncthreads();  // (no peer touches this CTA's shared memory after the cluster barrier above)
 
   // ---- normalise this CTA's pixels ----
   if (!active) return;
@@ -335,18 +363,19 @@ gn_cluster_kernel(const T* __restrict__ x1, const T* __restrict__ x2, const floa
     const int v = vbase + tv;
     if (v >= cv) continue;
     float a[8], b[8];
+    load8_ro(gamma + v * 8, a);
+    load8_ro(beta + v * 8, b);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = v * 8 + j;
-      const int g = c / cpg;
-      const float ga = gamma[c] * s_rstd[g];
-      a[j] = ga;
-      b[j] = beta[c] - s_mean[g] * ga;
+      const int g = (v * 8 + j) / cpg;
+      a[j] *= s_rstd[g];
+      b[j] -= s_mean[g] * a[j];
     }
     for (int pp = p_begin + tr; pp < p_end; pp += R) {
       const long long pix = (long long)n * hw + pp;
       float f[8];
-      gn_load8(x1, x2, c1, c2, pix, v, f);
+      if (cache_rows) load8(cache + (size_t)(pp - p_begin) * C + v * 8, f);
+      else gn_load8(x1, x2, c1, c2, pix, v, f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float t = f[j] * a[j] + b[j];
@@ -365,215 +394,23 @@ template <typename T>
 static int launch_gn_cluster(const void* x1, const void* x2, const float* gamma, const float* beta, void* y, int n, int hw,
                              int c1, int c2, int groups, float eps, int with_silu, cudaStream_t st) {
   const int C = c1 + c2;
-  const size_t smem = (size_t)(2 * C + kGNCThreads * 16) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gn_cluster_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  static int attr_state = 0;  // 0: not configured, 1: portable sizes only, 2: 16-CTA clusters allowed
+  if (!attr_state) {
+    cudaError_t e = cudaFuncSetAttribute(gn_cluster_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGNCMaxSmem);
     if (e != cudaSuccess) return set_error(SDEO_ECUDA, cudaGetErrorString(e));
-    attr_set = true;
+    e = cudaFuncSetAttribute(gn_cluster_kernel<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    attr_state = (e == cudaSuccess && !getenv("SDEO_GN_CLUSTER8")) ? 2 : 1;
+    (void)cudaGetLastError();
   }
-  return launch_k("groupnorm (cluster)", gn_cluster_kernel<T>, dim3(kGNCluster, (unsigned)n), dim3(kGNCThreads), smem, st,
-                  dim3(kGNCluster, 1, 1), (const T*)x1, (const T*)x2, gamma, beta, (__nv_bfloat16*)y, hw, c1, c2, groups, eps,
-                  with_silu);
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Single-launch, single-read GroupNorm for the denoiser's tensors: P CTAs per sample, every CTA keeps its pixel rows
-// in shared memory. Pass 1 reduces them to per-group (sum, sumsq) partials in global memory; a software barrier among
-// the P CTAs of the sample (arrival counter + generation word in the workspace; all CTAs of the grid are co-resident:
-// grid <= 148, <= 96 KB of shared memory) publishes them; every CTA then folds the P partials in rank order
-// (deterministic) and normalises its rows straight from shared memory. HBM/L2 traffic: 1 read + 1 write of the tensor.
-// ---------------------------------------------------------------------------------------------------------
-constexpr int kGNGThreads = 256;
-constexpr int kGNGMaxSmem = 96 * 1024;
-constexpr int kGNGSyncBytes = 256;  // head of the workspace: {count, generation} per sample, zero-initialised once
-
-__device__ __forceinline__ void copy8_raw(__nv_bfloat16* dst, const __nv_bfloat16* src) {
-  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
-}
-__device__ __forceinline__ void copy8_raw(float* dst, const float* src) {
-  const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
-  *reinterpret_cast<float4*>(dst) = a;
-  *reinterpret_cast<float4*>(dst + 4) = b;
-}
-
-template <typename T>
-__global__ void __launch_bounds__(kGNGThreads)
-gn_grid_kernel(const T* __restrict__ x1, const T* __restrict__ x2, const float* __restrict__ gamma,
-               const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ part,
-               unsigned int* __restrict__ sync, int hw, int c1, int c2, int groups, float eps, int with_silu, int ppc) {
-  extern __shared__ uint8_t gsm[];
-  __shared__ float s_mean[64], s_rstd[64];
-  const int trc = trace_start(3);
-  griddep_launch_dependents();
-  griddep_wait();
-  trace_mark(trc, 2);
-  trace_mark(trc, 3);
-  const int C = c1 + c2;
-  const int cv = C / 8;
-  const int cpg = C / groups;
-  const int n = blockIdx.y, rank = blockIdx.x, P = gridDim.x;
-  const int p_begin = rank * ppc;
-  const int p_end = min(hw, p_begin + ppc);
-  T* data = reinterpret_cast<T*>(gsm);                                   // [ppc][C] raw rows
-  float* chan_sum = reinterpret_cast<float*>(gsm + (size_t)ppc * C * sizeof(T));  // [C]
-  float* chan_sq = chan_sum + C;                                         // [C]
-  float* red = chan_sq + C;                                              // [R][cols][16]
-  const int cols = cv < kGNGThreads ? cv : kGNGThreads;
-  const int R = kGNGThreads / cols;
-  const int tr = threadIdx.x / cols, tv = threadIdx.x % cols;
-  const bool active = threadIdx.x < R * cols;
-
-  // ---- pass 1: global -> shared memory, per-channel sums ----
-  for (int vbase = 0; vbase < cv; vbase += cols) {
-    const int v = vbase + tv;
-    float s[8], q[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
-    if (active && v < cv) {
-      const int c = v * 8;
-      const T* src = c < c1 ? x1 + c : x2 + (c - c1);
-      const int ld = c < c1 ? c1 : c2;
-      for (int pp = p_begin + tr; pp < p_end; pp += R) {
-        T* d = data + (size_t)(pp - p_begin) * C + c;
-        copy8_raw(d, src + ((long long)n * hw + pp) * ld);
-        float f[8];
-        load8(d, f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] += f[j] * f[j]; }
-      }
-    }
-    if (active) {
-      float* dst = red + ((size_t)tr * cols + tv) * 16;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { dst[j] = s[j]; dst[8 + j] = q[j]; }
-    }
-    __syncthreads();
-    if (threadIdx.x < cols && v < cv) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
-      for (int r = 0; r < R; ++r) {
-        const float* src = red + ((size_t)r * cols + tv) * 16;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { s[j] += src[j]; q[j] += src[8 + j]; }
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { chan_sum[v * 8 + j] = s[j]; chan_sq[v * 8 + j] = q[j]; }
-    }
-    __syncthreads();
-  }
-  float gs = 0.f, gq = 0.f;
-  if (threadIdx.x < groups) {
-    const int g = threadIdx.x;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) { gs += chan_sum[c]; gq += chan_sq[c]; }
-    if (P > 1) {
-      float* out = part + (((size_t)n * P + rank) * groups + g) * 2;
-      __stcg(out, gs);
-      __stcg(out + 1, gq);
-    }
-  }
-  // ---- barrier among the P CTAs of this sample ----
-  if (P > 1) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned int* count = sync + 2 * n;
-      volatile unsigned int* gen = sync + 2 * n + 1;
-      const unsigned int g0 = *gen;  // read before arriving: the generation cannot advance until this CTA has arrived
-      __threadfence();
-      if (atomicAdd(count, 1u) == (unsigned int)(P - 1)) {
-        *count = 0u;  // ready for the next launch (stream-ordered after this one)
-        __threadfence();
-        atomicAdd((unsigned int*)gen, 1u);
-      } else {
-        const long long t0 = clock64();
-        while (*gen == g0) {
-          if (clock64() - t0 > 4000000000LL) {
-            printf("sdeo: groupnorm grid barrier timed out (block %d,%d)\n", (int)blockIdx.x, (int)blockIdx.y);
-            __trap();
-          }
-        }
-      }
-      __threadfence();
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x < groups) {
-    const int g = threadIdx.x;
-    if (P > 1) {
-      gs = 0.f; gq = 0.f;
-      for (int r = 0; r < P; ++r) {
-        const float* in = part + (((size_t)n * P + r) * groups + g) * 2;
-        gs += __ldcg(in);
-        gq += __ldcg(in + 1);
-      }
-    }
-    const float inv = 1.0f / ((float)hw * (float)cpg);
-    const float mean = gs * inv;
-    float var = gq * inv - mean * mean;
-    var = var < 0.f ? 0.f : var;
-    s_mean[g] = mean;
-    s_rstd[g] = rsqrtf(var + eps);
-  }
-  __syncthreads();
-  // ---- pass 2: normalise from shared memory ----
-  if (!active) return;
-  for (int vbase = 0; vbase < cv; vbase += cols) {
-    const int v = vbase + tv;
-    if (v >= cv) continue;
-    float a[8], b[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = v * 8 + j;
-      const int g = c / cpg;
-      const float ga = gamma[c] * s_rstd[g];
-      a[j] = ga;
-      b[j] = beta[c] - s_mean[g] * ga;
-    }
-    for (int pp = p_begin + tr; pp < p_end; pp += R) {
-      float f[8];
-      load8(data + (size_t)(pp - p_begin) * C + v * 8, f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float t = f[j] * a[j] + b[j];
-        f[j] = with_silu ? silu_f(t) : t;
-      }
-      uint4 o;
-      o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-      o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-      *reinterpret_cast<uint4*>(y + ((long long)n * hw + pp) * C + v * 8) = o;
-    }
-  }
-  trace_mark(trc, 3);
-}
-
-// Geometry of the grid variant: P CTAs per sample x ppc pixel rows each; false if the tensor does not fit.
-static bool gn_grid_geometry(int n, int hw, int C, int elem, int* P, int* ppc, size_t* smem) {
-  if (n > 16) return false;
-  int per = 148 / n;
-  if (per < 1) per = 1;
-  int rows = (hw + per - 1) / per;
-  if (rows < 4) rows = hw < 4 ? hw : 4;
-  *ppc = rows;
-  *P = (hw + rows - 1) / rows;
-  *smem = (size_t)rows * C * elem + (size_t)(2 * C + kGNGThreads * 16) * sizeof(float);
-  return *smem <= (size_t)kGNGMaxSmem;
-}
-
-template <typename T>
-static int launch_gn_grid(const void* x1, const void* x2, const float* gamma, const float* beta, void* y, void* workspace,
-                          int n, int hw, int c1, int c2, int groups, float eps, int with_silu, int P, int ppc, size_t smem,
-                          cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gn_grid_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGNGMaxSmem);
-    if (e != cudaSuccess) return set_error(SDEO_ECUDA, cudaGetErrorString(e));
-    attr_set = true;
-  }
-  unsigned int* sync = reinterpret_cast<unsigned int*>(workspace);
-  float* part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + kGNGSyncBytes);
-  return launch_k("groupnorm (grid)", gn_grid_kernel<T>, dim3((unsigned)P, (unsigned)n), dim3(kGNGThreads), smem, st,
-                  dim3(1, 1, 1), (const T*)x1, (const T*)x2, gamma, beta, (__nv_bfloat16*)y, part, sync, hw, c1, c2, groups,
-                  eps, with_silu, ppc);
+  const int csize = (attr_state == 2 && hw >= 4 * kGNClusterBig) ? kGNClusterBig : kGNCluster;
+  const int ppc = (hw + csize - 1) / csize;
+  const size_t base = (size_t)(2 * C + kGNCThreads * 16) * sizeof(float);
+  const size_t cache = (size_t)ppc * C * sizeof(T);
+  const int cache_rows = (base + cache <= (size_t)kGNCMaxSmem) ? ppc : 0;  // rows kept in shared memory: single read
+  const size_t smem = base + (cache_rows ? cache : 0);
+  return launch_k("groupnorm (cluster)", gn_cluster_kernel<T>, dim3((unsigned)csize, (unsigned)n), dim3(kGNCThreads), smem, st,
+                  dim3((unsigned)csize, 1, 1), (const T*)x1, (const T*)x2, gamma, beta, (__nv_bfloat16*)y, hw, c1, c2, groups,
+                  eps, with_silu, cache_rows);
 }
 
 static void gn_geometry(int n, int hw, int* chunks, int* ppc) {
@@ -660,9 +497,7 @@ SDEO_DEFINE_TRACE_SETTER(sdeo_trace_set_norm)
 extern "C" size_t sdeo_groupnorm_workspace_bytes(int32_t n, int32_t hw, int32_t groups) {
   int chunks, ppc;
   gn_geometry(n, hw, &chunks, &ppc);
-  size_t two_pass = (size_t)n * chunks * groups * 2 * sizeof(float);
-  size_t grid = (size_t)n * 148 * groups * 2 * sizeof(float);
-  return kGNGSyncBytes + (two_pass > grid ? two_pass : grid);
+  return (size_t)n * chunks * groups * 2 * sizeof(float);
 }
 
 extern "C" int sdeo_groupnorm_nhwc(const void* x1, const void* x2, int32_t x_f32, const float* gamma, const float* beta,
@@ -674,24 +509,6 @@ extern "C" int sdeo_groupnorm_nhwc(const void* x1, const void* x2, int32_t x_f32
   if (n <= 0 || hw <= 0 || groups <= 0 || groups > 64 || C % groups != 0 || c1 % 8 != 0 || c2 % 8 != 0)
     return set_error(SDEO_EINVAL, "groupnorm: unsupported geometry (need C % groups == 0, channels % 8 == 0, groups <= 64)");
   if (n > 65535) return set_error(SDEO_EINVAL, "groupnorm: batch too large");
-  // SDEO_GN_GRID=1: single-read variant (P CTAs per sample + software barrier). Measured on the two-stream step graph
-  // it is SLOWER than the cluster variant below (4.90 vs 4.56 ms/step): its ~128 CTAs must all become resident before
-  // any can pass the barrier, which serialises it against the other branch's 200 KB-smem GEMM CTAs. Off by default.
-  {
-    int P, ppc;
-    size_t smem;
-    const int elem = x_f32 ? 4 : 2;
-    if (getenv("SDEO_GN_GRID") && workspace_bytes >= kGNGSyncBytes + (size_t)n * 148 * groups * 2 * sizeof(float) &&
-        gn_grid_geometry(n, hw, C, elem, &P, &ppc, &smem)) {
-      if (x_f32)
-        return launch_gn_grid<float>(x1, x2, gamma, beta, y, workspace, n, hw, c1, c2, groups, eps, with_silu, P, ppc, smem,
-                                     (cudaStream_t)stream);
-      return launch_gn_grid<__nv_bfloat16>(x1, x2, gamma, beta, y, workspace, n, hw, c1, c2, groups, eps, with_silu, P, ppc,
-                                           smem, (cudaStream_t)stream);
-    }
-  }
-  workspace = reinterpret_cast<uint8_t*>(workspace) + kGNGSyncBytes;  // the head holds the grid variant's barrier words
-  workspace_bytes = workspace_bytes > (size_t)kGNGSyncBytes ? workspace_bytes - kGNGSyncBytes : 0;
   // small tensors: one cluster per sample, single launch; big ones (VAE): two-pass grid
   static long long cluster_max = -1;  // elements per sample up to which the single-launch cluster variant is used
   if (cluster_max < 0) {
