@@ -90,9 +90,14 @@ typedef struct sdeo_conv_args {
   /* SDEO_EPI_QKV only: packed column n -> which = n / (heads*dhead) + qkv_first (0=q,1=k,2=v) */
   void* q; void* k; void* vt;
   int32_t heads, dhead, tokens, ldv, qkv_first;
-  /* split-K scratch (see sdeo_conv_workspace_bytes); may be NULL when the planner picks splits == 1 */
+  /* split-K scratch (unused since split-K partials travel through distributed shared memory; may be NULL) */
   void* workspace;
   size_t workspace_bytes;
+  /* optional: per-channel partial statistics of the FINAL fp32 output for the GroupNorm that consumes it (replaces
+   * that GroupNorm's own pass over the tensor, groupNormKernel.cu:49-120 / F.group_norm's statistics). fp32
+   * [slots][cout][2] = (sum, sum of squares) over the rows of one (M tile, K slice) slot; a sample's slots are
+   * contiguous. Size and layout come from sdeo_conv_gn_stats_slots(); consumed by sdeo_groupnorm_apply_stats(). */
+  float* gn_stats;
 } sdeo_conv_args;
 
 /* Bytes of workspace the planner may use for these args (fp32 partial tiles + tile counters).
@@ -101,6 +106,11 @@ typedef struct sdeo_conv_args {
 size_t sdeo_conv_workspace_bytes(const sdeo_conv_args* a);
 size_t sdeo_conv_counter_bytes(void);
 int sdeo_conv2d(const sdeo_conv_args* a, void* stream);
+/* GroupNorm partial statistics geometry for these args: *max_slots_total = upper bound of slots (allocate
+ * max_slots_total * cout * 2 floats; independent of tuning); *parts_per_sample = slots per sample under the plan
+ * sdeo_conv2d currently uses for this shape (call it AFTER sdeo_conv2d; 0 = this call produces no statistics: bf16
+ * output, unaligned pitches, or an M tile that spans two samples). */
+int sdeo_conv_gn_stats_slots(const sdeo_conv_args* a, int32_t* max_slots_total, int32_t* parts_per_sample);
 /* Enable (1) / disable (0) per-shape autotuning of the N tile and the number of K slices: the first eager call of a
  * layer shape times the candidates on the caller's stream and caches the winner (calls made while the stream is
  * being captured into a CUDA graph only read the cache). */
@@ -130,6 +140,13 @@ size_t sdeo_groupnorm_workspace_bytes(int32_t n, int32_t hw, int32_t groups);
 int sdeo_groupnorm_nhwc(const void* x1, const void* x2, int32_t x_f32, const float* gamma, const float* beta, void* y,
                         int32_t n, int32_t hw, int32_t c1, int32_t c2, int32_t groups, float eps,
                         int32_t with_silu, void* workspace, size_t workspace_bytes, void* stream);
+/* Same normalisation with the statistics taken from the partials the producing convolutions left
+ * (sdeo_conv_args::gn_stats): stats1 = fp32 [n][parts1][c1][2] for x1, stats2 likewise for x2 (NULL without x2). The
+ * tensor is read once. Results match sdeo_groupnorm_nhwc up to fp32 summation order. */
+int sdeo_groupnorm_apply_stats(const void* x1, const void* x2, int32_t x_f32, const float* stats1, int32_t parts1,
+                               const float* stats2, int32_t parts2, const float* gamma, const float* beta, void* y,
+                               int32_t n, int32_t hw, int32_t c1, int32_t c2, int32_t groups, float eps, int32_t with_silu,
+                               void* stream);
 
 /* LayerNorm over the last dim of [rows, c] bf16 (nn.LayerNorm, attention.py:372-374), eps 1e-5. */
 int sdeo_layernorm(const void* x, int32_t x_f32, const float* gamma, const float* beta, void* y, int32_t rows,

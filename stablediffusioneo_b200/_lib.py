@@ -25,6 +25,7 @@ class ConvArgs(Structure):
         ("q", c_void_p), ("k", c_void_p), ("vt", c_void_p),
         ("heads", c_int32), ("dhead", c_int32), ("tokens", c_int32), ("ldv", c_int32), ("qkv_first", c_int32),
         ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+        ("gn_stats", c_void_p),
     ]
 
 
@@ -38,6 +39,9 @@ SIGNATURES = {
     "sdeo_conv_counter_bytes": (c_size_t, []),
     "sdeo_conv2d": (c_int, [POINTER(ConvArgs), c_void_p]),
     "sdeo_conv_autotune": (c_int, [c_int]),
+    "sdeo_conv_gn_stats_slots": (c_int, [POINTER(ConvArgs), POINTER(c_int32), POINTER(c_int32)]),
+    "sdeo_groupnorm_apply_stats": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p,
+                                           c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, c_int32, c_void_p]),
     "sdeo_packed_rows": (c_int32, [c_int32]),
     "sdeo_packed_k": (c_int32, [c_int32, c_int32, c_int32]),
     "sdeo_pick_bn": (c_int32, [c_int32, c_int32, c_int32]),

@@ -168,7 +168,7 @@ class ControlNet(nn.Module):
         for i, module in enumerate(self.input_blocks):
             if i == 0:
                 # h = conv_in(x) + guided_hint (cldm/cldm.py:294-297): residual add in the conv epilogue
-                h = module[0].run(h, residual=guided_hint, stream=util.STREAM_FP32)
+                h = module[0].run(h, residual=guided_hint, stream=util.STREAM_FP32, gn_stats=True)
             else:
                 h = module.run(h, emb, context)
             feats.append(h)
@@ -188,7 +188,7 @@ class ControlNet(nn.Module):
                 outs[i] = add_to[i]
             else:
                 outs[i] = conv.run(h, scale=scales[i], residual=add_to[i] if add_to is not None else None,
-                                   stream=util.STREAM_FP32)
+                                   stream=util.STREAM_FP32, gn_stats=add_to is not None)
             if after is not None:
                 after(i)
         return outs

@@ -62,7 +62,8 @@ struct ConvKParams {
   long long* dbg;  // optional per-CTA phase timestamps (SDEO_CONV_DEBUG), 16 slots per CTA
   int res_smem_off;        // > 0: idle warps prefetch the residual tile into shared memory at this byte offset
   int a_tmem, a_tmem_col;  // stage the A tile in TMEM (tcgen05.cp) at this column offset
-  float* ws;       // split-K partial tiles in global memory (L2-resident); nullptr: reduce through DSMEM instead
+  float* ws;       // (unused: split-K partials travel through distributed shared memory)
+  float2* gn_stats;  // STATS: per-(M tile, K-slice rank) per-channel (sum, sum of squares) of the final outputs
 };
 
 #define SDEO_DBG(slot)                                                                               \
@@ -362,7 +363,10 @@ __device__ __forceinline__ void epi_geglu_item(const ConvKParams& p, const RowIn
 }
 
 // MODE: SDEO_EPI_*; OUT / RES: see enums above; FAST: vector-aligned NORMAL epilogue (else the generic item path).
-template <int MODE, int OUT, int RES, bool FAST>
+// STATS (NORMAL + FAST + fp32 output only): the epilogue also reduces the FINAL output values of this CTA's rows to
+// per-channel (sum, sum of squares) and writes them to p.gn_stats[(M tile * S + K-slice rank)][cout] -- the GroupNorm
+// that consumes this tensor folds those partials instead of re-reading the tensor for its statistics.
+template <int MODE, int OUT, int RES, bool FAST, bool STATS>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmB, const ConvKParams p) {
@@ -648,9 +652,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     const int hw_out = p.Ho * p.Wo;
     const int half = p.BN / 2;
     const int emb_row_fixed = (p.emb && p.emb_step) ? __ldg(p.emb_step) : -1;
-    const int step_rows = kConvThreads / cols_items, step_cols = kConvThreads % cols_items;
+    // STATS: every thread keeps ONE column item (ci) and strides over rows, so that it can accumulate column sums in
+    // registers; the (at most cols_items - 1) threads beyond the last full row group stay idle.
+    const int step_rows = kConvThreads / cols_items, step_cols = STATS ? 0 : kConvThreads % cols_items;
     int row = r_begin + (int)threadIdx.x / cols_items;
     int ci = (int)threadIdx.x % cols_items;
+    if (STATS && (int)threadIdx.x >= step_rows * cols_items) row = r_end;
+    float st_s[STATS ? 8 : 1], st_q[STATS ? 8 : 1];
+    if (STATS) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { st_s[j] = 0.f; st_q[j] = 0.f; }
+    }
     while (row < r_end) {
       float v[U][8], g[U][8];
       uint4 raw0[U], raw1[U];
@@ -730,6 +742,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           epi_qkv_item(p, ri, n_base + col, v[u]);
         } else if (FAST) {
           epi_normal_fast<OUT, RES>(p, (long long)pixs[u], p.emb ? (emb_row_fixed >= 0 ? emb_row_fixed : pixs[u] / hw_out) : 0, n_base + col, v[u], raw0[u], raw1[u]);
+          if (STATS) {  // v[u] now holds the values that were stored
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { st_s[j] += v[u][j]; st_q[j] += v[u][j] * v[u][j]; }
+          }
         } else {
           RowInfo ri; ri.valid = true; ri.pix = pixs[u]; ri.batch = p.emb ? (emb_row_fixed >= 0 ? emb_row_fixed : pixs[u] / hw_out) : 0;
           epi_normal_item(p, ri, n_base + col, v[u], false, raw0[u], raw1[u]);
@@ -737,12 +753,48 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       }
     }
     if (MODE == SDEO_EPI_QKV) qkv_store_vt(p, tile, LD, row_pix, n_base, (int)threadIdx.x, kConvThreads);  // S == 1
+    if (STATS) {
+      // column sums of this CTA's rows: registers -> shared memory (one 16-float record per thread) -> one thread per
+      // channel adds the row groups in fixed order (deterministic) -> global partial [M tile * S + rank][channel]
+      if (S > 1) cluster_wait();  // the scratch below reuses the tile, which peers read until this barrier completes
+      __syncthreads();
+      float* scratch = reinterpret_cast<float*>(tiles);
+      if ((int)threadIdx.x < step_rows * cols_items) {
+        float* dst = scratch + (size_t)threadIdx.x * 16;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { dst[j] = st_s[j]; dst[8 + j] = st_q[j]; }
+      }
+      __syncthreads();
+      // 2*BN values (sum and sum of squares per channel); kparts thread groups split the row groups of a value, a
+      // second pass adds the kparts partial sums: both in fixed order
+      const int nval = 2 * p.BN;
+      const int kparts = kConvThreads / nval > 0 ? kConvThreads / nval : 1;
+      float* part2 = scratch + (size_t)kConvThreads * 16;  // [kparts][nval]
+      const int t = (int)threadIdx.x;
+      if (t < nval * kparts) {
+        const int val = t % nval, part = t / nval;
+        const int c = val % p.BN, sq = val / p.BN;
+        const float* src = scratch + (size_t)(c >> 3) * 16 + sq * 8 + (c & 7);
+        float acc = 0.f;
+        for (int rg = part; rg < step_rows; rg += kparts) acc += src[(size_t)rg * cols_items * 16];
+        part2[part * nval + val] = acc;
+      }
+      __syncthreads();
+      if (t < nval) {
+        const int c = t % p.BN, sq = t / p.BN;
+        if (n_base + c < p.cout) {
+          float acc = 0.f;
+          for (int k = 0; k < kparts; ++k) acc += part2[k * nval + t];
+          reinterpret_cast<float*>(p.gn_stats)[(((size_t)m_tile * S + split) * p.cout + n_base + c) * 2 + sq] = acc;
+        }
+      }
+    }
   }
 
   if (threadIdx.x == 64) SDEO_DBG(7);
   // ---- teardown (split-K: peers may still be reading this CTA's tile until the second cluster barrier completes) ----
   tc_fence_before();
-  if (p.splits > 1) cluster_wait();
+  if (p.splits > 1 && !STATS) cluster_wait();
   __syncthreads();
   trace_mark(trc, 3);
   if (threadIdx.x == 64) SDEO_DBG(8);
@@ -994,6 +1046,17 @@ extern "C" int sdeo_pack_geglu_bias(const float* b, int32_t n2, int32_t geglu_bn
 
 static int launch_conv(const sdeo_conv_args* a, const ConvPlan& pl, void* stream);
 
+// GroupNorm partial statistics (sdeo_conv_args::gn_stats): produced by the vector-aligned NORMAL epilogue with an fp32
+// output when no M tile spans two samples. Returns the number of partial slots per sample (M tiles per sample x K
+// slices) under plan `pl`, 0 if this call does not produce them.
+static int stats_parts(const sdeo_conv_args* a, const ConvPlan& pl) {
+  if (!a->gn_stats || a->epi_mode != SDEO_EPI_NORMAL || !a->y_fp32 || pl.bn_ != 1) return 0;
+  bool fast = (a->cout % 8 == 0) && (a->ldy % 4 == 0);
+  if (a->y2) fast = fast && (a->ldy2 % 8 == 0);
+  if (a->residual) fast = fast && (a->residual_f32 ? (a->ldr % 4 == 0) : (a->ldr % 8 == 0));
+  return fast ? pl.tiles_h * pl.tiles_w * pl.splits : 0;
+}
+
 // ---- per-shape autotuning of (N tile, K slices) -------------------------------------------------------------
 // The best tile / split-K choice depends on the layer shape in ways the heuristic does not capture (measured: 2 K
 // slices speed up the 3x3 convs at M=3072 by 20-30% and slow the GEGLU linears down 2x). With autotuning enabled
@@ -1010,7 +1073,7 @@ int g_autotune = 0;
 
 TuneKey tune_key(const sdeo_conv_args* a) {
   TuneKey k = {a->n, a->h, a->w, a->c1, a->x2 ? a->c2 : 0, a->cout, a->ksize, a->stride, a->epi_mode, a->y_fp32,
-               a->residual ? (a->residual_f32 ? 2 : 1) : 0, a->y2 ? 1 : 0, a->emb ? 1 : 0, a->act, a->dhead, 0};
+               a->residual ? (a->residual_f32 ? 2 : 1) : 0, a->y2 ? 1 : 0, a->emb ? 1 : 0, a->act, a->dhead, a->gn_stats ? 1 : 0};
   return k;
 }
 
@@ -1057,22 +1120,41 @@ extern "C" int sdeo_conv_autotune(int enable) {
   return SDEO_OK;
 }
 
-extern "C" int sdeo_conv2d(const sdeo_conv_args* a, void* stream) {
-  if (!a || !a->x1 || !a->w_packed) return set_error(SDEO_EINVAL, "conv2d: null argument");
+// Resolves the plan sdeo_conv2d uses for these args: the autotuned (N tile, K slices) if the shape has been tuned
+// (tuning it first when `stream` is given and autotuning is on), the heuristic otherwise.
+static bool resolve_plan(const sdeo_conv_args* a, void* stream, bool may_tune, ConvPlan* pl) {
   int force_bn = 0, force_s = 0;
   if (g_autotune && !getenv("SDEO_FORCE_BN") && !getenv("SDEO_FORCE_SPLITS")) {
     std::lock_guard<std::mutex> lock(g_tune_mu);
     const TuneKey key = tune_key(a);
     auto it = g_tuned.find(key);
-    if (it == g_tuned.end()) {
+    if (it == g_tuned.end() && may_tune) {
       std::pair<int, int> best;
       if (tune_shape(a, stream, &best)) it = g_tuned.emplace(key, best).first;
     }
     if (it != g_tuned.end()) { force_bn = it->second.first; force_s = it->second.second; }
   }
+  return make_plan(a, pl, force_bn, force_s);
+}
+
+extern "C" int sdeo_conv2d(const sdeo_conv_args* a, void* stream) {
+  if (!a || !a->x1 || !a->w_packed) return set_error(SDEO_EINVAL, "conv2d: null argument");
   ConvPlan pl;
-  if (!make_plan(a, &pl, force_bn, force_s)) return set_error(SDEO_EINVAL, "conv2d: unsupported geometry");
+  if (!resolve_plan(a, stream, true, &pl)) return set_error(SDEO_EINVAL, "conv2d: unsupported geometry");
   return launch_conv(a, pl, stream);
+}
+
+extern "C" int sdeo_conv_gn_stats_slots(const sdeo_conv_args* a, int32_t* max_slots_total, int32_t* parts_per_sample) {
+  if (!a) return set_error(SDEO_EINVAL, "conv_gn_stats_slots: null argument");
+  ConvPlan pl;
+  if (!resolve_plan(a, nullptr, false, &pl)) return set_error(SDEO_EINVAL, "conv_gn_stats_slots: unsupported geometry");
+  if (max_slots_total) *max_slots_total = pl.tiles_n * pl.tiles_h * pl.tiles_w * kMaxCluster;
+  if (parts_per_sample) {
+    sdeo_conv_args b = *a;
+    if (!b.gn_stats) b.gn_stats = (float*)(uintptr_t)16;  // "would be produced if a buffer were given"
+    *parts_per_sample = stats_parts(&b, pl);
+  }
+  return SDEO_OK;
 }
 
 static int launch_conv(const sdeo_conv_args* a, const ConvPlan& pl, void* stream) {
@@ -1137,14 +1219,15 @@ static int launch_conv(const sdeo_conv_args* a, const ConvPlan& pl, void* stream
   p.a_tmem = getenv("SDEO_A_TMEM") ? 1 : 0;  // measured: no gain over A from shared memory; kept as an option
   p.a_tmem_col = pl.tmem_cols - 64;
   p.ws = nullptr;  // (split-K partials travel through distributed shared memory; the workspace argument is unused)
+  p.gn_stats = nullptr;
 
   // ---- pick the kernel instantiation ----
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvKParams);
   KernelFn fn = nullptr;
   if (a->epi_mode == SDEO_EPI_GEGLU) {
-    fn = conv_gemm_kernel<SDEO_EPI_GEGLU, OUT_BF16, RES_NONE, true>;
+    fn = conv_gemm_kernel<SDEO_EPI_GEGLU, OUT_BF16, RES_NONE, true, false>;
   } else if (a->epi_mode == SDEO_EPI_QKV) {
-    fn = conv_gemm_kernel<SDEO_EPI_QKV, OUT_BF16, RES_NONE, true>;
+    fn = conv_gemm_kernel<SDEO_EPI_QKV, OUT_BF16, RES_NONE, true, false>;
   } else {
     const int out_kind = !a->y_fp32 ? OUT_BF16 : (p.y2 ? OUT_F32_TWIN : OUT_F32);
     const int res_kind = !a->residual ? RES_NONE : (a->residual_f32 ? RES_F32 : RES_BF16);
@@ -1154,9 +1237,15 @@ static int launch_conv(const sdeo_conv_args* a, const ConvPlan& pl, void* stream
     if (res_kind == RES_BF16) fast = fast && (a->ldr % 8 == 0);
     if (res_kind == RES_F32) fast = fast && (a->ldr % 4 == 0);
     if (!fast) {
-      fn = conv_gemm_kernel<SDEO_EPI_NORMAL, OUT_BF16, RES_NONE, false>;
+      fn = conv_gemm_kernel<SDEO_EPI_NORMAL, OUT_BF16, RES_NONE, false, false>;
+    } else if (stats_parts(a, pl) > 0) {
+      p.gn_stats = (float2*)a->gn_stats;
+#define SDEO_PICK(O, R) if (out_kind == O && res_kind == R) fn = conv_gemm_kernel<SDEO_EPI_NORMAL, O, R, true, true>;
+      SDEO_PICK(OUT_F32, RES_NONE) SDEO_PICK(OUT_F32, RES_BF16) SDEO_PICK(OUT_F32, RES_F32)
+      SDEO_PICK(OUT_F32_TWIN, RES_NONE) SDEO_PICK(OUT_F32_TWIN, RES_BF16) SDEO_PICK(OUT_F32_TWIN, RES_F32)
+#undef SDEO_PICK
     } else {
-#define SDEO_PICK(O, R) if (out_kind == O && res_kind == R) fn = conv_gemm_kernel<SDEO_EPI_NORMAL, O, R, true>;
+#define SDEO_PICK(O, R) if (out_kind == O && res_kind == R) fn = conv_gemm_kernel<SDEO_EPI_NORMAL, O, R, true, false>;
       SDEO_PICK(OUT_BF16, RES_NONE) SDEO_PICK(OUT_BF16, RES_BF16) SDEO_PICK(OUT_BF16, RES_F32)
       SDEO_PICK(OUT_F32, RES_NONE) SDEO_PICK(OUT_F32, RES_BF16) SDEO_PICK(OUT_F32, RES_F32)
       SDEO_PICK(OUT_F32_TWIN, RES_NONE) SDEO_PICK(OUT_F32_TWIN, RES_BF16) SDEO_PICK(OUT_F32_TWIN, RES_F32)
@@ -1166,14 +1255,14 @@ static int launch_conv(const sdeo_conv_args* a, const ConvPlan& pl, void* stream
   if (!fn) return set_error(SDEO_EINVAL, "conv2d: no kernel instantiation");
   {
     // opt in to > 48 KB of dynamic shared memory, once per instantiation
-    static KernelFn configured[16];
+    static KernelFn configured[32];
     static int n_configured = 0;
     bool seen = false;
     for (int i = 0; i < n_configured; ++i) seen = seen || (configured[i] == fn);
     if (!seen) {
       cudaError_t e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess) return set_error(SDEO_ECUDA, cudaGetErrorString(e));
-      if (n_configured < 16) configured[n_configured++] = fn;
+      if (n_configured < 32) configured[n_configured++] = fn;
     }
   }
   return launch_k("conv2d", fn, dim3((unsigned)(pl.tiles_n * pl.tiles_h * pl.tiles_w), (unsigned)pl.n_tiles, (unsigned)pl.splits),

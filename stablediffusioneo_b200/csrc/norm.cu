@@ -424,6 +424,121 @@ static void gn_geometry(int n, int hw, int* chunks, int* ppc) {
   *chunks = (hw + p - 1) / p;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// GroupNorm from precomputed partial statistics: the convolutions that PRODUCED x1 / x2 left per-channel (sum, sum of
+// squares) partials of their final outputs (sdeo_conv_args::gn_stats, [sample][part][channel]); every CTA folds the
+// partials of its sample in fixed order (deterministic), forms the group statistics (any grouping, including groups
+// that straddle the concat seam) and normalises its pixel rows. The tensor is read once; no statistics pass.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kGNThreads)
+gn_apply_stats_kernel(const T* __restrict__ x1, const T* __restrict__ x2, const float2* __restrict__ st1, int parts1,
+                      const float2* __restrict__ st2, int parts2, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int hw, int c1, int c2, int groups,
+                      int gslab, int ppc, float eps, int with_silu) {
+  // grid: (pixel-row chunk, channel slab of `gslab` groups, sample). A CTA folds only its slab's partials.
+  const int trc = trace_start(3);
+  griddep_launch_dependents();
+  griddep_wait();
+  trace_mark(trc, 2);
+  extern __shared__ float sm[];
+  __shared__ float s_mean[64], s_rstd[64];
+  const int C = c1 + c2;
+  const int cpg = C / groups;
+  const int n = blockIdx.z, chunk = blockIdx.x, slab = blockIdx.y;
+  const int g_lo = slab * gslab;
+  const int ng = min(gslab, groups - g_lo);
+  const int c_lo = g_lo * cpg, cs = ng * cpg;  // this CTA's channels [c_lo, c_lo + cs), cs % 8 == 0
+  float* chan_sum = sm;       // [cs]
+  float* chan_sq = sm + cs;   // [cs]
+  for (int cl = threadIdx.x; cl < cs; cl += kGNThreads) {
+    const int c = c_lo + cl;
+    const bool first = c < c1;
+    const float2* src = first ? st1 + (size_t)n * parts1 * c1 + c : st2 + (size_t)n * parts2 * c2 + (c - c1);
+    const int parts = first ? parts1 : parts2, ld = first ? c1 : c2;
+    float s = 0.f, q = 0.f;
+    int k = 0;
+    for (; k + 4 <= parts; k += 4) {  // 4 independent loads in flight, added in slot order
+      const float2 a0 = __ldcg(src + (size_t)k * ld), a1 = __ldcg(src + (size_t)(k + 1) * ld);
+      const float2 a2 = __ldcg(src + (size_t)(k + 2) * ld), a3 = __ldcg(src + (size_t)(k + 3) * ld);
+      s += a0.x; q += a0.y; s += a1.x; q += a1.y; s += a2.x; q += a2.y; s += a3.x; q += a3.y;
+    }
+    for (; k < parts; ++k) {
+      const float2 a0 = __ldcg(src + (size_t)k * ld);
+      s += a0.x; q += a0.y;
+    }
+    chan_sum[cl] = s;
+    chan_sq[cl] = q;
+  }
+  __syncthreads();
+  if (threadIdx.x < ng) {
+    const int g = threadIdx.x;
+    float s = 0.f, q = 0.f;
+    for (int cl = g * cpg; cl < (g + 1) * cpg; ++cl) { s += chan_sum[cl]; q += chan_sq[cl]; }
+    const float inv = 1.0f / ((float)hw * (float)cpg);
+    const float mean = s * inv;
+    float var = q * inv - mean * mean;
+    var = var < 0.f ? 0.f : var;
+    s_mean[g] = mean;
+    s_rstd[g] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  const int p_begin = chunk * ppc;
+  const int p_end = min(hw, p_begin + ppc);
+  const int cvs = cs / 8, v_lo = c_lo / 8;
+  const int cols = cvs < kGNThreads ? cvs : kGNThreads;
+  const int R = kGNThreads / cols;
+  const int tr = threadIdx.x / cols, tv = threadIdx.x % cols;
+  if (threadIdx.x < R * cols) {
+    for (int vbase = 0; vbase < cvs; vbase += cols) {
+      if (vbase + tv >= cvs) continue;
+      const int v = v_lo + vbase + tv;  // 8-channel vector of the virtual concat
+      float a[8], b[8];
+      load8_ro(gamma + v * 8, a);
+      load8_ro(beta + v * 8, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int g = (v * 8 + j) / cpg - g_lo;
+        a[j] *= s_rstd[g];
+        b[j] -= s_mean[g] * a[j];
+      }
+      int pp = p_begin + tr;
+      for (; pp + 3 * R < p_end; pp += 4 * R) {  // 4 independent loads in flight per thread
+        float f[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) gn_load8(x1, x2, c1, c2, (long long)n * hw + pp + u * R, v, f[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float t = f[u][j] * a[j] + b[j];
+            f[u][j] = with_silu ? silu_f(t) : t;
+          }
+          uint4 o;
+          o.x = pack_bf16x2(f[u][0], f[u][1]); o.y = pack_bf16x2(f[u][2], f[u][3]);
+          o.z = pack_bf16x2(f[u][4], f[u][5]); o.w = pack_bf16x2(f[u][6], f[u][7]);
+          *reinterpret_cast<uint4*>(y + ((long long)n * hw + pp + u * R) * C + v * 8) = o;
+        }
+      }
+      for (; pp < p_end; pp += R) {
+        const long long pix = (long long)n * hw + pp;
+        float f[8];
+        gn_load8(x1, x2, c1, c2, pix, v, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float t = f[j] * a[j] + b[j];
+          f[j] = with_silu ? silu_f(t) : t;
+        }
+        uint4 o;
+        o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+        o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+        *reinterpret_cast<uint4*>(y + pix * C + v * 8) = o;
+      }
+    }
+  }
+  trace_mark(trc, 3);
+}
+
 // One warp per row, the row lives in registers (C <= 2048): exact two-pass mean/variance.
 constexpr int kLNMaxVec = 8;
 template <typename T>
@@ -555,6 +670,40 @@ extern "C" int sdeo_groupnorm_nhwc(const void* x1, const void* x2, int32_t x_f32
   return launch_k("groupnorm apply", gn_apply_kernel<__nv_bfloat16>, grid, dim3(kGNThreads), 0, st, one,
                   (const __nv_bfloat16*)x1, (const __nv_bfloat16*)x2, gamma, beta, (const float*)workspace,
                   (__nv_bfloat16*)y, hw, c1, c2, groups, chunks, ppc, eps, with_silu);
+}
+
+extern "C" int sdeo_groupnorm_apply_stats(const void* x1, const void* x2, int32_t x_f32, const float* stats1, int32_t parts1,
+                                          const float* stats2, int32_t parts2, const float* gamma, const float* beta, void* y,
+                                          int32_t n, int32_t hw, int32_t c1, int32_t c2, int32_t groups, float eps,
+                                          int32_t with_silu, void* stream) {
+  if (!x1 || !stats1 || !gamma || !beta || !y || parts1 <= 0) return set_error(SDEO_EINVAL, "groupnorm_apply_stats: null argument");
+  if (!x2) c2 = 0;
+  if (x2 && (!stats2 || parts2 <= 0)) return set_error(SDEO_EINVAL, "groupnorm_apply_stats: x2 given without its statistics");
+  const int C = c1 + c2;
+  if (n <= 0 || n > 65535 || hw <= 0 || groups <= 0 || groups > 64 || C % groups != 0 || c1 % 8 != 0 || c2 % 8 != 0)
+    return set_error(SDEO_EINVAL, "groupnorm_apply_stats: unsupported geometry");
+  // grid: (row chunks, channel slabs, samples). A slab = a quarter of the groups when that keeps 8-channel vectors whole:
+  // every CTA then folds a quarter of the partial statistics. About two CTAs per SM, at least 4 pixel rows each.
+  const int cpg = C / groups;
+  int gslab = groups;
+  if (groups % 4 == 0 && ((groups / 4) * cpg) % 8 == 0) gslab = groups / 4;
+  const int slabs = (groups + gslab - 1) / gslab;
+  if ((gslab * cpg) % 8 != 0 && slabs > 1) return set_error(SDEO_EINVAL, "groupnorm_apply_stats: slab not vector aligned");
+  int want = (296 + n * slabs - 1) / (n * slabs);
+  if (want < 1) want = 1;
+  int ppc = (hw + want - 1) / want;
+  if (ppc < 4) ppc = hw < 4 ? hw : 4;
+  const int chunks = (hw + ppc - 1) / ppc;
+  const size_t smem = (size_t)2 * gslab * cpg * sizeof(float);
+  const dim3 grid((unsigned)chunks, (unsigned)slabs, (unsigned)n), one(1, 1, 1);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x_f32)
+    return launch_k("groupnorm apply (stats)", gn_apply_stats_kernel<float>, grid, dim3(kGNThreads), smem, st, one,
+                    (const float*)x1, (const float*)x2, (const float2*)stats1, parts1, (const float2*)stats2, parts2, gamma, beta,
+                    (__nv_bfloat16*)y, hw, c1, c2, groups, gslab, ppc, eps, with_silu);
+  return launch_k("groupnorm apply (stats)", gn_apply_stats_kernel<__nv_bfloat16>, grid, dim3(kGNThreads), smem, st, one,
+                  (const __nv_bfloat16*)x1, (const __nv_bfloat16*)x2, (const float2*)stats1, parts1, (const float2*)stats2,
+                  parts2, gamma, beta, (__nv_bfloat16*)y, hw, c1, c2, groups, gslab, ppc, eps, with_silu);
 }
 
 extern "C" int sdeo_layernorm(const void* x, int32_t x_f32, const float* gamma, const float* beta, void* y, int32_t rows,

@@ -218,7 +218,7 @@ class SpatialTransformer(nn.Module):
             tok = block.run(tok, context[i])
         tok = operand(tok)                                                 # bf16 twin written by the last ff GEMM
         t = nchw_view(tok.reshape(b, h, w, tok.shape[-1]))
-        return self.proj_out.run(t, residual=x_in, stream=st)
+        return self.proj_out.run(t, residual=x_in, stream=st, gn_stats=True)  # feeds the next ResBlock's GroupNorm
 
     def forward(self, x, context=None):
         from .diffusionmodules.util import is_internal, to_external, to_internal

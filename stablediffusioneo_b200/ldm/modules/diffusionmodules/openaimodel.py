@@ -82,7 +82,7 @@ class TimestepEmbedSequential(nn.Sequential, TimestepBlock):
             elif isinstance(layer, SiLU):
                 raise RuntimeError("SiLU inside TimestepEmbedSequential is fused by the owning module")
             elif isinstance(layer, Conv2d):
-                x = layer.run(x, stream=util.STREAM_FP32)
+                x = layer.run(x, stream=util.STREAM_FP32, gn_stats=True)
             else:
                 x = layer.run(x)
         return x
@@ -117,7 +117,7 @@ class Upsample(nn.Module):
     def run(self, x):
         assert x.shape[1] == self.channels
         y = nchw_view(ops.upsample_nearest2x(nhwc(operand(x))))
-        return self.conv.run(y, stream=util.STREAM_FP32) if self.use_conv else y
+        return self.conv.run(y, stream=util.STREAM_FP32, gn_stats=True) if self.use_conv else y
 
     def forward(self, x):
         if is_internal(x):
@@ -140,7 +140,7 @@ class Downsample(nn.Module):
 
     def run(self, x):
         assert x.shape[1] == self.channels
-        return self.op.run(x, stream=util.STREAM_FP32)
+        return self.op.run(x, stream=util.STREAM_FP32, gn_stats=True)
 
     def forward(self, x):
         if is_internal(x):
@@ -184,14 +184,14 @@ class ResBlock(TimestepBlock):
         else:
             emb_out = self.emb_layers[1].run(silu_of(emb), out_fp32=True)   # fp32 [N, Cout]
         # GEMM results that feed a normalisation or a residual add stay fp32 (no extra bf16 rounding in the branch)
-        h = self.in_layers[2].run(h, emb=emb_out, emb_step=emb_step, out_fp32=util.STREAM_FP32)
+        h = self.in_layers[2].run(h, emb=emb_out, emb_step=emb_step, out_fp32=util.STREAM_FP32, gn_stats=True)
         h = self.out_layers[0].run(h, silu=True)
         if isinstance(self.skip_connection, nn.Identity):
             assert not isinstance(x, CatPair)
             skip = x
         else:
             skip = self.skip_connection.run(x, out_fp32=util.STREAM_FP32)
-        return self.out_layers[3].run(h, residual=skip, stream=util.STREAM_FP32)
+        return self.out_layers[3].run(h, residual=skip, stream=util.STREAM_FP32, gn_stats=True)
 
     def forward(self, x, emb):
         if is_internal(x):

@@ -5,6 +5,7 @@ with the reference modules; the packed bf16 filters the kernels stream are deriv
 Activation convention ("internal" tensors): bf16, logical shape [N, C, H, W], channels_last memory (physically
 NHWC). Any public module also accepts "external" fp32 NCHW tensors and then returns fp32 NCHW (see `boundary`)."""
 import functools
+import os
 import math
 
 import numpy as np
@@ -38,12 +39,16 @@ class CatPair:
 # eps rel L2 1.3e-2 with a bf16 stream vs the 1e-2 gate). A stream tensor is an fp32 NHWC-physical tensor tagged
 # `_sdeo_stream`, optionally carrying `_twin`: the bf16 copy the producing epilogue wrote for TMA consumers.
 STREAM_FP32 = True
+# Convolutions whose fp32 output feeds a GroupNorm also emit per-channel partial statistics from their epilogue
+# (sdeo_conv_args::gn_stats); the GroupNorm then reads the tensor once. SDEO_NO_GN_STATS=1 restores the standalone pass.
+FUSE_GN_STATS = not os.environ.get("SDEO_NO_GN_STATS")
 
 
 def make_stream(y_f32, y_bf16=None):
     """[N,H,W,C] fp32 (+ optional bf16 twin) from a conv epilogue -> tagged internal stream tensor."""
     t = nchw_view(y_f32) if y_f32.dim() == 4 else y_f32
     t._sdeo_stream = True
+    t._gn_stats = getattr(y_f32, "_gn_stats", None)
     t._twin = None if y_bf16 is None else (nchw_view(y_bf16) if y_bf16.dim() == 4 else y_bf16)
     return t
 
@@ -163,7 +168,8 @@ class Conv2d(nn.Conv2d):
     def bias_f32(self):
         return self.bias.detach() if self.bias is not None else None
 
-    def run(self, x, emb=None, residual=None, scale=1.0, act=SDEO_ACT_NONE, out_fp32=False, stream=False, emb_step=None):
+    def run(self, x, emb=None, residual=None, scale=1.0, act=SDEO_ACT_NONE, out_fp32=False, stream=False, emb_step=None,
+            gn_stats=False):
         """x: internal tensor (bf16 or fp32 stream) or CatPair. Returns an internal bf16 tensor; fp32 NHWC-physical when
         out_fp32; an fp32 stream tensor with a bf16 twin when `stream`. A bf16 output whose channel count is not a
         multiple of 8 is zero-padded to one (so a following conv can TMA it)."""
@@ -178,7 +184,8 @@ class Conv2d(nn.Conv2d):
             out = torch.empty((n, ho, wo, (cout + 7) // 8 * 8), dtype=BF16, device=self.weight.device)
             ops.memset(out, 0)
         kw = dict(bias=self.bias_f32(), emb=emb, residual=res, scale=scale, act=act, stride=self.stride[0],
-                  out_fp32=out_fp32 or stream, out=out, twin=stream, emb_step=emb_step)
+                  out_fp32=out_fp32 or stream, out=out, twin=stream, emb_step=emb_step,
+                  gn_stats=gn_stats and (out_fp32 or stream) and FUSE_GN_STATS)
         if isinstance(x, CatPair):
             a, b = operand(x.a), operand(x.b)
             y = ops.conv2d(nhwc(a), self.packed((a.shape[1], b.shape[1])), x2=nhwc(b), **kw)
@@ -186,7 +193,9 @@ class Conv2d(nn.Conv2d):
             y = ops.conv2d(nhwc(operand(x)), self.packed(), **kw)
         if stream:
             return make_stream(y[0], y[1])
-        return nchw_view(y)
+        t = nchw_view(y)
+        t._gn_stats = getattr(y, "_gn_stats", None)
+        return t
 
     def forward(self, x):
         if is_internal(x):
@@ -232,12 +241,15 @@ class GroupNorm32(nn.GroupNorm):
     def run(self, x, silu=False):
         if isinstance(x, CatPair):
             a, b = x.a, x.b
+            sa, sb = getattr(a, "_gn_stats", None), getattr(b, "_gn_stats", None)
             if a.dtype != b.dtype:  # mixed stream / bf16 halves: read both as bf16
                 a, b = operand(a), operand(b)
+                sa = sb = None
             y = ops.groupnorm(nhwc(a), self.weight.detach(), self.bias.detach(), self.eps, silu, x2=nhwc(b),
-                              groups=self.num_groups)
+                              groups=self.num_groups, stats=sa if sb is not None else None, stats2=sb)
         else:
-            y = ops.groupnorm(nhwc(x), self.weight.detach(), self.bias.detach(), self.eps, silu, groups=self.num_groups)
+            y = ops.groupnorm(nhwc(x), self.weight.detach(), self.bias.detach(), self.eps, silu, groups=self.num_groups,
+                              stats=getattr(x, "_gn_stats", None))
         return nchw_view(y)
 
     @boundary

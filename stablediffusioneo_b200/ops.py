@@ -132,11 +132,13 @@ def pack_geglu_bias(bias, geglu_bn):
 
 
 def conv2d(x, pw, x2=None, bias=None, emb=None, residual=None, scale=1.0, act=SDEO_ACT_NONE, stride=1, out=None,
-           out_fp32=False, epi_mode=SDEO_EPI_NORMAL, qkv=None, twin=False, emb_step=None):
+           out_fp32=False, epi_mode=SDEO_EPI_NORMAL, qkv=None, twin=False, emb_step=None, gn_stats=False):
     """x: [N,H,W,C1] bf16 (+ optional x2 [N,H,W,C2] = fused torch.cat along channels). Returns [N,Ho,Wo,cout].
     residual may be bf16 or fp32. out_fp32 + twin=True additionally writes a bf16 copy and returns (y_f32, y_bf16).
     emb: fp32 [N, cout] (row = sample), or with emb_step (int32 device scalar) a table [S, cout] whose row *emb_step is
-    added to every sample."""
+    added to every sample. gn_stats (fp32 outputs): the epilogue also leaves per-channel partial statistics for the
+    GroupNorm that consumes the result; they are attached to the returned fp32 tensor as `_gn_stats = (buffer, parts
+    per sample)` when the kernel produced them (see groupnorm(stats=...))."""
     lib = _lib.load()
     _req(x, BF16, "x")
     _req(x2, BF16, "x2")
@@ -195,7 +197,18 @@ def conv2d(x, pw, x2=None, bias=None, emb=None, residual=None, scale=1.0, act=SD
         a.y2, a.ldy2 = _ptr(out2), out2.shape[3]
     ws = _workspaces.conv(x.device)
     a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
+    stats_buf = None
+    if gn_stats and out_fp32 and epi_mode == SDEO_EPI_NORMAL:
+        mx = ctypes.c_int32(0)
+        _check(lib.sdeo_conv_gn_stats_slots(ctypes.byref(a), ctypes.byref(mx), None), "conv_gn_stats_slots")
+        stats_buf = torch.empty((mx.value, pw.cout, 2), dtype=torch.float32, device=x.device)
+        a.gn_stats = _ptr(stats_buf)
     check(lib.sdeo_conv2d(ctypes.byref(a), _stream()), "conv2d")
+    if stats_buf is not None:
+        parts = ctypes.c_int32(0)
+        _check(lib.sdeo_conv_gn_stats_slots(ctypes.byref(a), None, ctypes.byref(parts)), "conv_gn_stats_slots")
+        if parts.value > 0:
+            out._gn_stats = (stats_buf, parts.value)
     return (out, out2) if twin else out
 
 
@@ -222,8 +235,9 @@ def qkv_project(x, pw, heads, dhead, first, q=None, k=None, vt=None, ldv=None, b
     conv2d(x4, pw, bias=bias, epi_mode=SDEO_EPI_QKV, qkv=(q, k, vt, heads, dhead, t, ldv or 0, first))
 
 
-def groupnorm(x, gamma, beta, eps, silu, x2=None, groups=32, out=None):
-    """x: [N,H,W,C1] (+ x2 [N,H,W,C2]); returns the normalised concat [N,H,W,C1+C2]."""
+def groupnorm(x, gamma, beta, eps, silu, x2=None, groups=32, out=None, stats=None, stats2=None):
+    """x: [N,H,W,C1] (+ x2 [N,H,W,C2]); returns the normalised concat [N,H,W,C1+C2]. stats / stats2: the `_gn_stats`
+    (buffer, parts per sample) the producing convolutions attached to x / x2 -- the tensor is then read only once."""
     lib = _lib.load()
     f32 = x.dtype == torch.float32
     _req(x, torch.float32 if f32 else BF16, "x")
@@ -234,6 +248,12 @@ def groupnorm(x, gamma, beta, eps, silu, x2=None, groups=32, out=None):
     c2 = x2.shape[3] if x2 is not None else 0
     if out is None:
         out = torch.empty((n, h, w, c1 + c2), dtype=BF16, device=x.device)
+    if stats is not None and (x2 is None or stats2 is not None):
+        s2 = stats2 if x2 is not None else (None, 0)
+        check(lib.sdeo_groupnorm_apply_stats(_ptr(x), _ptr(x2), 1 if f32 else 0, _ptr(stats[0]), stats[1], _ptr(s2[0]), s2[1],
+                                             _ptr(gamma), _ptr(beta), _ptr(out), n, h * w, c1, c2, groups, float(eps),
+                                             1 if silu else 0, _stream()), "groupnorm_apply_stats")
+        return out
     nbytes = lib.sdeo_groupnorm_workspace_bytes(n, h * w, groups)
     ws = _workspaces.gn(x.device, nbytes)
     check(lib.sdeo_groupnorm_nhwc(_ptr(x), _ptr(x2), 1 if f32 else 0, _ptr(gamma), _ptr(beta), _ptr(out), n, h * w, c1, c2, groups,

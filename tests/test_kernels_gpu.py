@@ -234,6 +234,51 @@ def test_groupnorm_repeated_and_deterministic(cuda_device):
                 assert torch.equal(y, outs[len(outs) - 3 + [320, 1280, 640].index(c)] if False else outs[[320, 1280, 640].index(c)])
 
 
+@pytest.mark.parametrize("autotune", [False, True])
+@pytest.mark.parametrize("case", [
+    # (n, cin, cout, h, w, k, cat)  cat: GroupNorm over the concat of two conv outputs (decoder blocks)
+    (2, 320, 320, 32, 48, 3, False),     # 12 M tiles per sample
+    (2, 640, 640, 16, 24, 1, False),
+    (2, 1280, 1280, 8, 12, 3, True),     # split-K cluster, 96-row tiles; concat 2560 channels (80 per group)
+    (2, 640, 320, 32, 48, 3, True),      # concat 640 channels
+    (1, 96, 96, 20, 28, 3, False),       # ragged tiles, 3 channels per group
+    (2, 1280, 1280, 4, 6, 3, False),     # tile box spans the batch: no fused statistics, standalone pass
+])
+def test_groupnorm_from_conv_statistics(cuda_device, case, autotune):
+    """conv epilogue -> per-channel partial statistics -> GroupNorm that reads the tensor once, against
+    F.group_norm of the very tensor the conv wrote (and against the standalone GroupNorm kernel)."""
+    from stablediffusioneo_b200 import ops
+    n, cin, cout, h, w, k, cat = case
+    dev = cuda_device
+    ops.set_autotune(autotune)
+    try:
+        outs = []
+        for seed in ((1, 2) if cat else (1,)):
+            x = gen((n, cin, h, w), seed, dev)
+            wt = gen((cout, cin, k, k), 10 + seed, dev) / math.sqrt(cin * k * k)
+            bias = gen((cout,), 20 + seed, dev) * 0.1
+            res = gen((n, h, w, cout), 30 + seed, dev)
+            y, _ = ops.conv2d(nhwc(x), ops.pack_conv_weight(wt), bias=bias, residual=res, out_fp32=True, twin=True,
+                              gn_stats=True)
+            outs.append(y)
+    finally:
+        ops.set_autotune(False)
+    spans_batch = h * w * n <= 128 and n > 1
+    for y in outs:
+        assert (getattr(y, "_gn_stats", None) is None) == spans_batch
+    ctot = cout * len(outs)
+    gamma = gen((ctot,), 3, dev) * 0.2 + 1.0
+    beta = gen((ctot,), 4, dev) * 0.2
+    st = [getattr(y, "_gn_stats", None) for y in outs]
+    x2 = outs[1] if cat else None
+    y_fused = ops.groupnorm(outs[0], gamma, beta, 1e-5, True, x2=x2, stats=st[0], stats2=st[1] if cat else None)
+    y_plain = ops.groupnorm(outs[0], gamma, beta, 1e-5, True, x2=x2)
+    full = torch.cat(outs, 3).permute(0, 3, 1, 2)
+    ref = F.silu(F.group_norm(full, 32, gamma, beta, 1e-5))
+    assert rel_l2(y_fused.permute(0, 3, 1, 2), ref) < TOL
+    assert rel_l2(y_fused, y_plain) < 2e-3   # same math, different fp32 summation order (+ bf16 rounding flips)
+
+
 @pytest.mark.parametrize("rows,c", [(3072, 320), (768, 640), (192, 1280), (48, 1280), (5, 512)])
 def test_layernorm(cuda_device, rows, c):
     from stablediffusioneo_b200 import ops
