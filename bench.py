@@ -11,7 +11,11 @@ value  : device-resident throughput, steps/s over all ranks (inputs already in H
 e2e    : same metric through the public API — DDIMSampler.sample(...) fed pinned HOST tensors (x_T, hint, contexts
          copied host->device every image, final latents copied device->host), ceil(K/20) images
 roofline: the dominant kernel (conv_gemm_kernel, tensor-core bound) — executed conv/linear FLOPs of one step divided
-         by the summed CUDA-event durations of those launches (eager pass on a back-logged stream)
+         by the time those launches take INSIDE the timed step graph: the library's kernel trace (globaltimer stamps
+         written by block 0 of every kernel during one graph replay: dependency resolved -> block end, plus the idle
+         tail that follows each conv kernel before any other kernel is past its dependency). The older figure —
+         CUDA events around every eager launch on a back-logged stream — is kept as `achieved_eager_events`: it
+         serialises the step and adds ~10 us of event/launch latency to every 5-10 us kernel.
 cpu_baseline / --impl reference: the CPU fp32 port of the reference path (oracle/) timed on the host cores.
 """
 import argparse
@@ -33,6 +37,7 @@ LATENT_HW = (32, 48)
 CFG_SCALE = 9.0
 WORKLOAD = "ControlNet-canny SD1.5 256x384 batch 1, DDIM 20 steps, CFG 9.0 (BASELINE configs[1])"
 FLOPS_PER_STEP = 740.0e9          # one DDIM step = 2 x (ControlNet 95.6 + UNet 274.4) GF at 32x48
+CONV_DRAM_BYTES_PER_LAUNCH = 9386294   # ncu dram__bytes_read.sum + write.sum over one step's conv launches / launches
 WEIGHT_BYTES_PER_STEP = 2.442e9   # bf16 UNet 1.719 GB + ControlNet 0.723 GB, streamed once per step (cond+uncond batched)
 
 
@@ -191,13 +196,33 @@ def conv_roofline(eng, pk):
     eng.reset_latent()
     total_ms = sum(s.elapsed_time(e) for s, e, _ in rec)
     total_flops = sum(f for _, _, f in rec)
-    achieved = total_flops / (total_ms * 1e-3) / 1e12
+    eager = total_flops / (total_ms * 1e-3) / 1e12
+    # in-graph: one replay of the captured step with the kernel trace on
+    from stablediffusioneo_b200 import trace
+    for _ in range(3):
+        eng.step()
+    recs = trace.capture(eng.step, eng.x_lat.device)
+    eng.reset_latent()
+    summ = trace.summarize(recs)
+    conv = summ["kinds"]["conv"]
+    conv_us = conv["busy_us"] + conv["tail_us"]
+    busy_all = sum(k["busy_us"] for k in summ["kinds"].values())
+    achieved = total_flops / (conv_us * 1e-6) / 1e12
     return {"bound": "tensor", "kernel": "conv_gemm_kernel", "achieved": achieved, "peak": pk["bf16_sustained"],
             "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
-            # dram__bytes_read+write per launch, averaged over the 325 conv launches of one step, from the ncu pass in
-            # profiles/r01_conv_dram_traffic.txt (cold-cache replays; algorithmic: 2.442 GB of weights / 325 = 7.5 MB)
-            "traffic": 9386294, "traffic_unit": "bytes/launch (ncu, cold cache)",
-            "launches_per_step": len(rec), "flops_per_step": total_flops, "kernel_ms_per_step": total_ms,
+            # dram__bytes_read+write per launch, averaged over the conv launches of one step (ncu --graph-profiling node,
+            # profiles/r01_conv_dram_traffic.txt; cold-cache replays; algorithmic: 2.442 GB of weights / launches)
+            "traffic": CONV_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes/launch (ncu, cold cache)",
+            "launches_per_step": conv["launches"], "flops_per_step": total_flops,
+            "kernel_ms_per_step": conv_us * 1e-3, "kernel_busy_ms_per_step": conv["busy_us"] * 1e-3,
+            "avg_launch_us": conv_us / conv["launches"],
+            "kernel_share_of_step_kernel_time": conv["busy_us"] / busy_all,
+            "method": "sdeo_set_trace during one replay of the timed step graph: sum over conv launches of (grid "
+                      "dependency resolved -> block-0 end) + the idle tail after each until another kernel runs",
+            "achieved_eager_events": eager, "eager_events_ms_per_step": total_ms,
+            "step_trace": {k: {"launches": v["launches"], "busy_us": round(v["busy_us"], 1), "tail_us": round(v["tail_us"], 1)}
+                           for k, v in summ["kinds"].items()},
+            "step_trace_span_us": summ["span_us"], "step_trace_busy_union_us": summ["busy_union_us"],
             "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)"}
 
 

@@ -35,66 +35,40 @@ sampler.sample(4, 1, (4, h, w), cond, verbose=False, eta=0.0, x_T=x_T, unconditi
 torch.cuda.synchronize()
 eng = sampler._engine
 assert eng.graph is not None
-cap = 4096
-buf = torch.zeros(4 + 4 * cap, dtype=torch.int64, device=dev)
-buf[1] = cap
-lib = _lib.load()
+from stablediffusioneo_b200 import trace  # noqa: E402
+
 eng.reset_latent()
 for _ in range(3):
     eng.step()
 torch.cuda.synchronize()
-assert lib.sdeo_set_trace(ctypes.c_void_p(buf.data_ptr())) == 0
 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-s.record()
-eng.step()
-e.record()
-torch.cuda.synchronize()
-lib.sdeo_set_trace(None)
-b = buf.cpu()
-n = int(b[0])
-rec = b[4:4 + 4 * n].reshape(n, 4)
-tag = rec[:, 0] & 0xFF
-grid = (rec[:, 0] >> 8) & 0xFFFFFFFF
-mode = (rec[:, 0] >> 40) & 0xF
-splits = (rec[:, 0] >> 44) & 0xF
-bn = (rec[:, 0] >> 48) & 0xFFF
-t0 = int(rec[:, 1].min())
-ts, td, te = (rec[:, 1] - t0).double() / 1e3, (rec[:, 2] - t0).double() / 1e3, (rec[:, 3] - t0).double() / 1e3
-names = {1: "conv", 2: "attention", 3: "groupnorm", 4: "layernorm", 5: "elementwise"}
-print(f"{n} kernels traced; event time {s.elapsed_time(e) * 1e3:.1f} us; trace span {float(te.max()):.1f} us")
-# busy union of [dep, end]
-iv = sorted((float(a), float(c)) for a, c in zip(td, te))
-busy, cur_s, cur_e = 0.0, None, None
-for a, c in iv:
-    if cur_e is None or a > cur_e:
-        if cur_e is not None:
-            busy += cur_e - cur_s
-        cur_s, cur_e = a, c
-    else:
-        cur_e = max(cur_e, c)
-busy += cur_e - cur_s
-print(f"union of [dependency resolved, block-0 end] intervals: {busy:.1f} us busy, {float(te.max()) - busy:.1f} us with no kernel past its dependency")
-agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
-for i in range(n):
-    a = agg[names.get(int(tag[i]), "?")]
-    a[0] += 1
-    a[1] += float(te[i] - td[i])
-    a[2] += float(td[i] - ts[i])
-for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-    print(f"  {k:12s} {a[0]:4d} kernels  sum(dep->end) {a[1]:8.1f} us  avg {a[1] / a[0]:6.2f}  sum(start->dep, hidden by PDL) {a[2]:8.1f} us")
-order = sorted(range(n), key=lambda i: -float(te[i] - td[i]))
+
+
+def one_step():
+    s.record()
+    eng.step()
+    e.record()
+
+
+rec = trace.capture(one_step, dev)
+summ = trace.summarize(rec)
+n = len(rec)
+print(f"{n} kernels traced; event time {s.elapsed_time(e) * 1e3:.1f} us; trace span {summ['span_us']:.1f} us")
+print(f"union of [dependency resolved, block-0 end] intervals: {summ['busy_union_us']:.1f} us busy, "
+      f"{summ['span_us'] - summ['busy_union_us']:.1f} us with no kernel past its dependency")
+for k, a in sorted(summ["kinds"].items(), key=lambda kv: -kv[1]["busy_us"]):
+    print(f"  {k:12s} {a['launches']:4d} kernels  sum(dep->end) {a['busy_us']:8.1f} us  avg {a['busy_us'] / a['launches']:6.2f}  "
+          f"idle tail after them {a['tail_us']:7.1f} us  sum(start->dep, hidden by PDL) {a['hidden_prologue_us']:8.1f} us")
 print("longest kernels (dep->end us):")
-for i in order[:25]:
-    print(f"  {names.get(int(tag[i]), '?'):10s} grid {int(grid[i]):5d} mode {int(mode[i])} splits {int(splits[i])} BN {int(bn[i]):3d}  "
-          f"{float(te[i] - td[i]):7.2f} us  (start {float(ts[i]):8.1f})")
+for r in sorted(rec, key=lambda r: -(r.end - r.dep))[:25]:
+    print(f"  {r.kind:10s} grid {r.grid:5d} mode {r.mode} splits {r.splits} BN {r.bn:3d}  {r.end - r.dep:7.2f} us  (start {r.start:8.1f})")
 hist = collections.Counter()
-for i in range(n):
-    if int(tag[i]) == 1:
-        hist[min(int(float(te[i] - td[i]) // 2) * 2, 40)] += 1
+for r in rec:
+    if r.kind == "conv":
+        hist[min(int((r.end - r.dep) // 2) * 2, 40)] += 1
 print("conv dep->end histogram (us bucket: count):", dict(sorted(hist.items())))
 if args.csv:
     with open(args.csv, "w") as f:
-        f.write("idx,kind,grid,mode,splits,bn,start_us,dep_us,end_us\n")
-        for i in sorted(range(n), key=lambda i: float(ts[i])):
-            f.write(f"{i},{names.get(int(tag[i]), '?')},{int(grid[i])},{int(mode[i])},{int(splits[i])},{int(bn[i])},"
-                    f"{float(ts[i]):.2f},{float(td[i]):.2f},{float(te[i]):.2f}\n")
+        f.write("kind,grid,mode,splits,bn,start_us,dep_us,end_us\n")
+        for r in sorted(rec, key=lambda r: r.start):
+            f.write(f"{r.kind},{r.grid},{r.mode},{r.splits},{r.bn},{r.start:.2f},{r.dep:.2f},{r.end:.2f}\n")
