@@ -785,7 +785,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         if (n_base + c < p.cout) {
           float acc = 0.f;
           for (int k = 0; k < kparts; ++k) acc += part2[k * nval + t];
-          reinterpret_cast<float*>(p.gn_stats)[(((size_t)m_tile * S + split) * p.cout + n_base + c) * 2 + sq] = acc;
+          // slot = sample * (parts per sample) + part. One sample per tile: part = (spatial tile, K-slice rank). A tile
+          // that holds several whole samples (tiny feature maps) is only handled as a split-K cluster whose per-rank
+          // row ranges do not straddle samples (checked on the host): part = position of the range inside the sample.
+          int sample = n0, part = (ih * p.tiles_w + iw) * S + split, pps = p.tiles_h * p.tiles_w * S;
+          if (p.bn_ > 1) {
+            const int per_img = p.bh * p.bw;
+            sample = n0 + r_begin / per_img;
+            part = (r_begin % per_img) / rows_per;
+            pps = per_img / rows_per;
+          }
+          if (r_begin < p.rows_valid && sample < p.N)
+            reinterpret_cast<float*>(p.gn_stats)[(((size_t)sample * pps + part) * p.cout + n_base + c) * 2 + sq] = acc;
         }
       }
     }
@@ -1050,11 +1061,17 @@ static int launch_conv(const sdeo_conv_args* a, const ConvPlan& pl, void* stream
 // output when no M tile spans two samples. Returns the number of partial slots per sample (M tiles per sample x K
 // slices) under plan `pl`, 0 if this call does not produce them.
 static int stats_parts(const sdeo_conv_args* a, const ConvPlan& pl) {
-  if (!a->gn_stats || a->epi_mode != SDEO_EPI_NORMAL || !a->y_fp32 || pl.bn_ != 1) return 0;
+  if (!a->gn_stats || a->epi_mode != SDEO_EPI_NORMAL || !a->y_fp32) return 0;
   bool fast = (a->cout % 8 == 0) && (a->ldy % 4 == 0);
   if (a->y2) fast = fast && (a->ldy2 % 8 == 0);
   if (a->residual) fast = fast && (a->residual_f32 ? (a->ldr % 4 == 0) : (a->ldr % 8 == 0));
-  return fast ? pl.tiles_h * pl.tiles_w * pl.splits : 0;
+  if (!fast) return 0;
+  if (pl.bn_ == 1) return pl.tiles_h * pl.tiles_w * pl.splits;
+  // several whole samples per tile: only as a split-K cluster whose per-rank row ranges stay inside one sample
+  const int per_img = pl.bh * pl.bw, rows_valid = pl.bn_ * per_img;
+  const int rows_per = (rows_valid + pl.splits - 1) / pl.splits;
+  if (pl.splits > 1 && per_img % rows_per == 0) return per_img / rows_per;
+  return 0;
 }
 
 // ---- per-shape autotuning of (N tile, K slices) -------------------------------------------------------------
