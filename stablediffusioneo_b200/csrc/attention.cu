@@ -32,7 +32,7 @@ struct AttParams {
   __nv_bfloat16* o;
 };
 
-__global__ void __launch_bounds__(kAttThreads)
+__global__ void __launch_bounds__(kAttThreads, 2)  // two CTAs per SM (d = 40: 106 KB of shared memory each): 192 tiles fit one wave
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const AttParams p) {
   extern __shared__ uint8_t smem_raw[];
