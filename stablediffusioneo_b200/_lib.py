@@ -4,7 +4,8 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint8, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_C", "libsdeo.so")
+# SDEO_LIB: load another build of the same ABI (A/B comparisons of kernel changes on one GPU box)
+LIB_PATH = os.environ.get("SDEO_LIB") or os.path.join(HERE, "_C", "libsdeo.so")
 
 SDEO_EPI_NORMAL, SDEO_EPI_GEGLU, SDEO_EPI_QKV = 0, 1, 2
 SDEO_ACT_NONE, SDEO_ACT_SILU = 0, 1
