@@ -1,5 +1,8 @@
-"""Runs two eager (non-graph) denoising steps of the 256x384 workload so that ncu can list / capture the kernels of
-one step: python tools/profile_step.py [--latent H W] [--steps N]. The last step's launches are the steady state."""
+"""Runs the 256x384 workload (cond+uncond batch 2) so that ncu can list / capture the kernels of one denoising step:
+python tools/profile_step.py [--latent H W] [--steps N] [--graph]. After the warm-up sample (which also autotunes the conv
+shapes) ONE more step runs inside the NVTX range "sdeo_step":
+  ncu --nvtx --nvtx-include "sdeo_step/" --graph-profiling node --metrics gpu__time_duration.sum ... python tools/profile_step.py --graph
+profiles exactly the kernel nodes of one replay of the captured step graph."""
 import argparse
 import os
 import sys
@@ -32,4 +35,12 @@ n0 = ops.LAUNCHES
 samples, _ = sampler.sample(args.steps, 1, (4, h, w), cond, verbose=False, eta=0.0, x_T=x_T,
                             unconditional_guidance_scale=9.0, unconditional_conditioning=uncond)
 torch.cuda.synchronize()
+eng = sampler._engine
+eng.reset_latent()
+eng.step()
+torch.cuda.synchronize()
+torch.cuda.nvtx.range_push("sdeo_step")
+eng.step()
+torch.cuda.synchronize()
+torch.cuda.nvtx.range_pop()
 print("launches", ops.LAUNCHES - n0, "finite", bool(torch.isfinite(samples).all()))
