@@ -190,6 +190,25 @@ def test_sd15_512x512_eps_vs_oracle(sd15, cuda_device):
     assert err < EPS_TOL
 
 
+def test_sd15_768x768_eps_vs_oracle(sd15, cuda_device):
+    """BASELINE configs[3] shape at batch 1 (768x768 -> latent 96x96, 9216 tokens of head_dim 40 at the top level,
+    2304 x 80, 576 x 160): one eps prediction. Exercises 72-tile convolutions, the long-sequence attention and the
+    GroupNorm partial-statistics fold with many parts."""
+    from helpers import oracle_weights
+    model, _ = sd15
+    sd_unet, sd_cn, _ = oracle_weights(O.SD15, O.SD15_VAE)
+    x_T, cond, _ = O.make_inputs(O.SD15, 1, 96, 96)
+    ts = torch.full((1,), 251, dtype=torch.long)
+    with torch.no_grad():
+        ref = O.apply_model(sd_unet, sd_cn, O.SD15, x_T, ts, cond)
+    dev = cuda_device
+    cond_d = {"c_concat": [cond["c_concat"][0].to(dev)], "c_crossattn": [cond["c_crossattn"][0].to(dev)]}
+    eps = model.apply_model(x_T.to(dev), ts.to(dev), cond_d)
+    err = rel_l2(eps, ref)
+    print("768x768 eps rel L2 vs oracle:", err)
+    assert err < EPS_TOL
+
+
 def test_sd15_batch2_matches_batch1(sd15, cuda_device):
     """Samples are independent (no cross-sample op): a batch of 2 different inputs equals two batch-1 calls."""
     model, _ = sd15
