@@ -115,6 +115,10 @@ int sdeo_conv_gn_stats_slots(const sdeo_conv_args* a, int32_t* max_slots_total, 
  * layer shape times the candidates on the caller's stream and caches the winner (calls made while the stream is
  * being captured into a CUDA graph only read the cache). */
 int sdeo_conv_autotune(int enable);
+/* CTA budget of subsequent sdeo_conv2d launches (0 = whole GPU, the default). A caller that runs two independent
+ * branches on two streams sets ~half the SM count while it enqueues them, so that both branches' kernels fit on the
+ * GPU side by side (one CTA per SM at ~200 KB of shared memory); tile / split-K choices are tuned per budget. */
+int sdeo_conv_set_cta_budget(int max_ctas);
 
 /* Repack an fp32 filter [cout, cin, k, k] (PyTorch layout, device memory) into the K-major bf16 layout the
  * kernel streams: [rows_packed, k*k*(chunks(c1)+chunks(c2))*64]. `geglu_bn` > 0 interleaves the two GEGLU

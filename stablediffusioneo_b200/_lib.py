@@ -40,6 +40,7 @@ SIGNATURES = {
     "sdeo_conv_counter_bytes": (c_size_t, []),
     "sdeo_conv2d": (c_int, [POINTER(ConvArgs), c_void_p]),
     "sdeo_conv_autotune": (c_int, [c_int]),
+    "sdeo_conv_set_cta_budget": (c_int, [c_int]),
     "sdeo_conv_gn_stats_slots": (c_int, [POINTER(ConvArgs), POINTER(c_int32), POINTER(c_int32)]),
     "sdeo_groupnorm_apply_stats": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p,
                                            c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, c_int32, c_void_p]),

@@ -10,6 +10,7 @@ Two execution paths, same arithmetic:
     coefficients read from device tables through a device-side step counter (no host patching between replays).
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -323,9 +324,12 @@ class _Engine:
             main = torch.cuda.current_stream()
             side = self.side_stream
             side.wait_stream(main)
-            with torch.cuda.stream(side), ops.workspace_slot(1):
-                feats = cn.run_body(x, self.guided, self.emb_c, self.ctx)
-            hs, h = unet.run_encoder(x, emb_u, self.ctx)
+            # while both branches are in flight every GEMM launch is limited to about half the SMs, so that the two
+            # streams' kernels really run side by side (SDEO_BRANCH_CTAS, default 74; 0 = no limit)
+            with ops.cta_budget(int(os.environ.get("SDEO_BRANCH_CTAS", "74"))):
+                with torch.cuda.stream(side), ops.workspace_slot(1):
+                    feats = cn.run_body(x, self.guided, self.emb_c, self.ctx)
+                hs, h = unet.run_encoder(x, emb_u, self.ctx)
             # the 13 zero convs (+ control scale + add onto the UNet skips) stay on the side stream, launched in the
             # order the decoder consumes them; the decoder waits per tensor, so only the first ones are on its path
             side.wait_stream(main)

@@ -795,7 +795,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
             part = (r_begin % per_img) / rows_per;
             pps = per_img / rows_per;
           }
-          if (r_begin < p.rows_valid && sample < p.N)
+          // (one sample per tile: a rank without rows still owns a slot and writes zeros into it)
+          if (p.bn_ == 1 || (r_begin < p.rows_valid && sample < p.N))
             reinterpret_cast<float*>(p.gn_stats)[(((size_t)sample * pps + part) * p.cout + n_base + c) * 2 + sq] = acc;
         }
       }
@@ -892,6 +893,12 @@ static int pick_bn_impl(int rows_packed, int epi_mode) {
   return 16;
 }
 
+// CTA budget of one launch (sdeo_conv_set_cta_budget): 0 = the whole GPU. The step engine halves it while two
+// independent branches (UNet encoder || ControlNet body) run on two streams: at one 200 KB CTA per SM two 100-CTA
+// kernels cannot co-run, two <= 74-CTA kernels can, and these layers are latency-bound, not throughput-bound.
+static int g_cta_budget = 0;
+static inline int cta_limit() { return g_cta_budget > 0 && g_cta_budget < 148 ? g_cta_budget : 148; }
+
 static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl, int force_bn = 0, int force_splits = 0) {
   if (!(a->ksize == 1 || a->ksize == 3)) return false;
   if (!(a->stride == 1 || a->stride == 2)) return false;
@@ -952,7 +959,7 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl, int force_bn = 0, i
   const int base = best_tiles * pl->n_tiles;
   int splits = 1;
   if ((base <= 40 || (pl->total_chunks >= 80 && base <= 74)) && a->epi_mode != SDEO_EPI_QKV) {  // (the V^T scatter reads the local tile only) measured: with >= 48 tiles the cluster reduction costs more than the extra SMs give back
-    splits = 148 / base;  // one CTA per SM: never spill into a second wave
+    splits = cta_limit() / base;  // one CTA per SM: never spill into a second wave
     const int max_by_k = pl->total_chunks / 4;  // at least 4 K chunks per slice
     if (splits > max_by_k) splits = max_by_k;
     if (splits > kMaxCluster) splits = kMaxCluster;
@@ -1090,8 +1097,22 @@ int g_autotune = 0;
 
 TuneKey tune_key(const sdeo_conv_args* a) {
   TuneKey k = {a->n, a->h, a->w, a->c1, a->x2 ? a->c2 : 0, a->cout, a->ksize, a->stride, a->epi_mode, a->y_fp32,
-               a->residual ? (a->residual_f32 ? 2 : 1) : 0, a->y2 ? 1 : 0, a->emb ? 1 : 0, a->act, a->dhead, a->gn_stats ? 1 : 0};
+               a->residual ? (a->residual_f32 ? 2 : 1) : 0, a->y2 ? 1 : 0, a->emb ? 1 : 0, a->act, a->dhead,
+               (a->gn_stats ? 1 : 0) | (cta_limit() << 1)};
   return k;
+}
+
+// true if some (BN, 1) candidate of this shape fits the CTA budget (else the budget cannot be honoured at all)
+bool any_within_budget(const sdeo_conv_args* a, const ConvPlan& base) {
+  static const int bns[] = {256, 192, 160, 128, 96, 80, 64};
+  if (base.tiles_n * base.tiles_h * base.tiles_w * base.n_tiles <= cta_limit()) return true;
+  if (a->epi_mode == SDEO_EPI_GEGLU) return false;
+  for (int bn : bns) {
+    ConvPlan pl;
+    if (base.rows_packed % bn != 0 || !make_plan(a, &pl, bn, 1) || pl.BN != bn) continue;
+    if (pl.tiles_n * pl.tiles_h * pl.tiles_w * pl.n_tiles <= cta_limit()) return true;
+  }
+  return false;
 }
 
 bool tune_shape(const sdeo_conv_args* a, void* stream, std::pair<int, int>* best) {
@@ -1114,7 +1135,8 @@ bool tune_shape(const sdeo_conv_args* a, void* stream, std::pair<int, int>* best
       ConvPlan pl;
       if (!make_plan(a, &pl, bn, sp) || pl.BN != bn || pl.splits != sp) continue;
       const int ctas = pl.tiles_n * pl.tiles_h * pl.tiles_w * pl.n_tiles * pl.splits;
-      if (sp > 1 && ctas > 148) continue;  // K slices must not spill into a second wave
+      if (sp > 1 && ctas > cta_limit()) continue;  // K slices must not spill into a second wave
+      if (g_cta_budget > 0 && ctas > cta_limit() && any_within_budget(a, base)) continue;  // honour the CTA budget
       if (launch_conv(a, pl, stream) != 0) { (void)cudaGetLastError(); continue; }
       cudaEventRecord(e0, st);
       bool ok = true;
@@ -1131,6 +1153,11 @@ bool tune_shape(const sdeo_conv_args* a, void* stream, std::pair<int, int>* best
   return true;
 }
 }  // namespace
+
+extern "C" int sdeo_conv_set_cta_budget(int max_ctas) {
+  g_cta_budget = max_ctas;
+  return SDEO_OK;
+}
 
 extern "C" int sdeo_conv_autotune(int enable) {
   g_autotune = enable;

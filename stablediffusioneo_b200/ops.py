@@ -399,6 +399,19 @@ def set_autotune(enable=True):
     _check(_lib.load().sdeo_conv_autotune(1 if enable else 0), "conv_autotune")
 
 
+class cta_budget:
+    """Context manager: convolutions / linears enqueued inside use at most `n` CTAs each (see sdeo_conv_set_cta_budget)."""
+
+    def __init__(self, n):
+        self.n = int(n)
+
+    def __enter__(self):
+        _check(_lib.load().sdeo_conv_set_cta_budget(self.n), "conv_set_cta_budget")
+
+    def __exit__(self, *exc):
+        _check(_lib.load().sdeo_conv_set_cta_budget(0), "conv_set_cta_budget")
+
+
 def memset(t, value=0):
     lib = _lib.load()
     assert t.is_contiguous()

@@ -244,6 +244,7 @@ def test_groupnorm_repeated_and_deterministic(cuda_device):
     (1, 96, 96, 20, 28, 3, False),       # ragged tiles, 3 channels per group
     (2, 1280, 1280, 4, 6, 3, False),     # tile box spans the batch: statistics per K-slice rank (or standalone pass)
     (2, 2560, 1280, 4, 6, 3, True),
+    (1, 1280, 1280, 1, 2, 3, False),     # 2 output rows, up to 8 K slices: ranks without rows own zero slots
 ])
 def test_groupnorm_from_conv_statistics(cuda_device, case, autotune):
     """conv epilogue -> per-channel partial statistics -> GroupNorm that reads the tensor once, against
