@@ -98,6 +98,19 @@ typedef struct sdeo_conv_args {
    * [slots][cout][2] = (sum, sum of squares) over the rows of one (M tile, K slice) slot; a sample's slots are
    * contiguous. Size and layout come from sdeo_conv_gn_stats_slots(); consumed by sdeo_groupnorm_apply_stats(). */
   float* gn_stats;
+  /* optional, producer of a LayerNorm input (nn.LayerNorm, attention.py:372-374): per output row the (sum, sum of
+   * squares) over each N tile's columns, fp32 [parts][row_stats_ld][2] (row_stats_ld >= n*ho*wo rows). Geometry from
+   * sdeo_conv_row_stats_parts(). Mutually exclusive with gn_stats. */
+  float* row_stats;
+  int32_t row_stats_ld;
+  /* optional, LayerNorm FOLDED into this GEMM (any epilogue mode): x1 is the raw (un-normalised) bf16 input, the packed
+   * weight carries gamma (W' = W * gamma along K), `bias` carries beta @ W^T. With mean / rstd of every input row taken
+   * from the producer's row statistics (ln_parts partials of ln_ld rows; ln_c = normalised width; ln_eps), the epilogue
+   * computes rstd[row] * (acc - mean[row] * ln_csum[n]) + bias[n]; ln_csum[n] = sum_k of the PACKED bf16 weight row n. */
+  const float* ln_stats;
+  int32_t ln_parts, ln_ld, ln_c;
+  float ln_eps;
+  const float* ln_csum;
 } sdeo_conv_args;
 
 /* Bytes of workspace the planner may use for these args (fp32 partial tiles + tile counters).
@@ -111,6 +124,9 @@ int sdeo_conv2d(const sdeo_conv_args* a, void* stream);
  * sdeo_conv2d currently uses for this shape (call it AFTER sdeo_conv2d; 0 = this call produces no statistics: bf16
  * output, unaligned pitches, or an M tile that spans two samples). */
 int sdeo_conv_gn_stats_slots(const sdeo_conv_args* a, int32_t* max_slots_total, int32_t* parts_per_sample);
+/* Row statistics geometry: *max_parts = upper bound of N tiles (allocate max_parts * row_stats_ld * 2 floats);
+ * *parts = N tiles under the plan sdeo_conv2d currently uses (call it AFTER sdeo_conv2d; 0 = not produced). */
+int sdeo_conv_row_stats_parts(const sdeo_conv_args* a, int32_t* max_parts, int32_t* parts);
 /* Enable (1) / disable (0) per-shape autotuning of the N tile and the number of K slices: the first eager call of a
  * layer shape times the candidates on the caller's stream and caches the winner (calls made while the stream is
  * being captured into a CUDA graph only read the cache). */

@@ -27,6 +27,9 @@ class ConvArgs(Structure):
         ("heads", c_int32), ("dhead", c_int32), ("tokens", c_int32), ("ldv", c_int32), ("qkv_first", c_int32),
         ("workspace", c_void_p), ("workspace_bytes", c_size_t),
         ("gn_stats", c_void_p),
+        ("row_stats", c_void_p), ("row_stats_ld", c_int32),
+        ("ln_stats", c_void_p), ("ln_parts", c_int32), ("ln_ld", c_int32), ("ln_c", c_int32), ("ln_eps", ctypes.c_float),
+        ("ln_csum", c_void_p),
     ]
 
 
@@ -42,6 +45,7 @@ SIGNATURES = {
     "sdeo_conv_autotune": (c_int, [c_int]),
     "sdeo_conv_set_cta_budget": (c_int, [c_int]),
     "sdeo_conv_gn_stats_slots": (c_int, [POINTER(ConvArgs), POINTER(c_int32), POINTER(c_int32)]),
+    "sdeo_conv_row_stats_parts": (c_int, [POINTER(ConvArgs), POINTER(c_int32), POINTER(c_int32)]),
     "sdeo_groupnorm_apply_stats": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p,
                                            c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, c_int32, c_void_p]),
     "sdeo_packed_rows": (c_int32, [c_int32]),

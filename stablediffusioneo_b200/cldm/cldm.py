@@ -5,6 +5,8 @@ The hot entry point is ControlLDM.apply_model(x_noisy, t, cond) (cldm/cldm.py:32
 two independent halves — UNet encoder first, then ControlNet — so that every ControlNet zero-conv adds its scaled
 output straight onto the UNet skip it controls (`hs.pop() + control.pop()`, cldm/cldm.py:41, and `h += control.pop()`,
 :35) in the conv epilogue: no 13 scale kernels (:338), no 13 add kernels."""
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -263,7 +265,8 @@ class ControlLDM(nn.Module):
         self.register_buffer("alphas_cumprod_prev", f32(np.append(1.0, alphas_cumprod[:-1])), persistent=False)
         self.register_buffer("sqrt_one_minus_alphas_cumprod", f32(np.sqrt(1.0 - alphas_cumprod)), persistent=False)
         self._hint_cache = None
-        ops.set_autotune(True)  # first eager call of each layer shape picks its tile / split-K configuration
+        # first eager call of each layer shape picks its tile / split-K configuration (SDEO_NO_AUTOTUNE=1: heuristics only)
+        ops.set_autotune(not os.environ.get("SDEO_NO_AUTOTUNE"))
 
     @property
     def device(self):

@@ -63,7 +63,17 @@ struct ConvKParams {
   int res_smem_off;        // > 0: idle warps prefetch the residual tile into shared memory at this byte offset
   int a_tmem, a_tmem_col;  // stage the A tile in TMEM (tcgen05.cp) at this column offset
   float* ws;       // (unused: split-K partials travel through distributed shared memory)
-  float2* gn_stats;  // STATS: per-(M tile, K-slice rank) per-channel (sum, sum of squares) of the final outputs
+  // STATS == 2 (producer of a LayerNorm input): per output row (sum, sum of squares) over this N tile's columns
+  float2* row_stats;      // [n_tile][row_stats_ld]
+  int row_stats_ld;
+  // LayerNorm folded into this GEMM (its A operand is the RAW bf16 x, its weight carries gamma): the epilogue turns
+  // acc into rstd[row] * (acc - mean[row] * csum[n]) (+ bias', which carries beta @ W). mean / rstd come from the
+  // producer's row statistics: ln_parts partials per row.
+  const float2* ln_stats;  // [ln_parts][ln_ld]
+  int ln_parts, ln_ld;
+  float ln_invc, ln_eps;
+  const float* ln_csum;    // [rows_packed] column sums of the packed (bf16) weight, packed row order
+  float2* gn_stats;  // STATS == 1: per-(M tile, K-slice rank) per-channel (sum, sum of squares) of the final outputs
 };
 
 #define SDEO_DBG(slot)                                                                               \
@@ -306,7 +316,7 @@ __device__ __forceinline__ void epi_qkv_item(const ConvKParams& p, const RowInfo
 // V^T part of the QKV epilogue: item = (8 consecutive token rows, one v column) -> ONE 16-byte store into
 // vt[b*heads + head][dd][tok .. tok+7]. Lanes run along the columns so the shared-memory reads are conflict-free.
 __device__ __forceinline__ void qkv_store_vt(const ConvKParams& p, const float* tile, int LD, const int* row_pix,
-                                             int n_base, int tid, int nthreads) {
+                                             const float2* ln_vec, int n_base, int tid, int nthreads) {
   const int C = p.heads * p.dhead;
   int vb = (2 - p.qkv_first) * C, ve = (3 - p.qkv_first) * C;  // global column range holding v
   if (vb < n_base) vb = n_base;
@@ -321,13 +331,19 @@ __device__ __forceinline__ void qkv_store_vt(const ConvKParams& p, const float* 
     const int nc = n - (2 - p.qkv_first) * C;
     const int head = nc / p.dhead, dd = nc % p.dhead;
     const float bias = p.bias ? __ldg(p.bias + n) : 0.f;
+    const float csum = ln_vec ? __ldg(p.ln_csum + n) : 0.f;
     float x[8];
     int pix[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int r = g * 8 + i;
       pix[i] = r < p.rows_valid ? row_pix[r] : -1;
-      x[i] = tile[(size_t)r * LD + (n - n_base)] + bias;
+      float a = tile[(size_t)r * LD + (n - n_base)];
+      if (ln_vec) {  // folded LayerNorm (see ConvKParams::ln_stats)
+        const float2 mr = ln_vec[r];
+        a = mr.y * (a - mr.x * csum);
+      }
+      x[i] = a + bias;
     }
     const int tok0 = pix[0] >= 0 ? pix[0] % p.tokens : 0;
     const bool vec = pix[0] >= 0 && pix[7] == pix[0] + 7 && tok0 + 7 < p.tokens && (tok0 & 7) == 0;
@@ -366,7 +382,9 @@ __device__ __forceinline__ void epi_geglu_item(const ConvKParams& p, const RowIn
 // STATS (NORMAL + FAST + fp32 output only): the epilogue also reduces the FINAL output values of this CTA's rows to
 // per-channel (sum, sum of squares) and writes them to p.gn_stats[(M tile * S + K-slice rank)][cout] -- the GroupNorm
 // that consumes this tensor folds those partials instead of re-reading the tensor for its statistics.
-template <int MODE, int OUT, int RES, bool FAST, bool STATS>
+// (STATS == 2: per-row statistics for a LayerNorm consumer instead, see ConvKParams::row_stats.)
+// LNF: a LayerNorm is folded into this GEMM (ConvKParams::ln_stats); kept out of the other instantiations' code.
+template <int MODE, int OUT, int RES, bool FAST, int STATS, bool LNF>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmB, const ConvKParams p) {
@@ -381,7 +399,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
   uint64_t* recv_bar = full_bar + 48;  // split-K: completes when all S partial slices of this CTA's rows have arrived
   int* row_pix = reinterpret_cast<int*>(smem + 512);  // [128] output pixel index per tile row
-  uint8_t* tiles = smem + 1024;
+  float2* ln_vec = reinterpret_cast<float2*>(smem + 1024);  // [128] (mean, rstd) of the folded LayerNorm per tile row
+  uint8_t* tiles = smem + 2048;
   const int stage_bytes = kATileBytes + p.BN * 128;
 
   const int warp = threadIdx.x >> 5;
@@ -541,6 +560,34 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     }
   }
 
+  if (LNF && warp >= 6) {
+    // ===================== folded LayerNorm: (mean, rstd) of every tile row (warps 6..11, during the mainloop) =========
+    const int per_img = p.bh * p.bw;
+    for (int row = (int)threadIdx.x - 192; row < kBM; row += kConvThreads - 192) {
+      const int nl = row / per_img, rem = row % per_img;
+      const int hl = rem / p.bw, wl = rem % p.bw;
+      const int nn = n0 + nl, hh = h0 + hl, ww = w0 + wl;
+      float2 mr = make_float2(0.f, 0.f);
+      if (row < p.rows_valid && nn < p.N && hh < p.Ho && ww < p.Wo) {
+        const long long pix = ((long long)nn * p.Ho + hh) * p.Wo + ww;
+        float sm_ = 0.f, sq_ = 0.f;
+        for (int k0 = 0; k0 < p.ln_parts; k0 += 8) {  // up to 8 independent loads in flight, added in part order
+          float2 a[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            a[k] = (k0 + k < p.ln_parts) ? __ldcg(p.ln_stats + (size_t)(k0 + k) * p.ln_ld + pix) : make_float2(0.f, 0.f);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { sm_ += a[k].x; sq_ += a[k].y; }
+        }
+        const float mean = sm_ * p.ln_invc;
+        float var = sq_ * p.ln_invc - mean * mean;
+        var = var < 0.f ? 0.f : var;
+        mr = make_float2(mean, rsqrtf(var + p.ln_eps));
+      }
+      ln_vec[row] = mr;
+    }
+  }
+
   if (MODE == SDEO_EPI_NORMAL && FAST && RES != RES_NONE && warp >= 6 && p.res_smem_off) {
     // ===================== residual prefetch (warps 6..11, concurrent with the mainloop) =====================
     // cp.async 16-byte copies of the residual rows this CTA's epilogue will add, into a dense [row][BN] buffer.
@@ -658,19 +705,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     int row = r_begin + (int)threadIdx.x / cols_items;
     int ci = (int)threadIdx.x % cols_items;
     if (STATS && (int)threadIdx.x >= step_rows * cols_items) row = r_end;
-    float st_s[STATS ? 8 : 1], st_q[STATS ? 8 : 1];
-    if (STATS) {
+    float st_s[STATS == 1 ? 8 : 1], st_q[STATS == 1 ? 8 : 1];
+    if (STATS == 1) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) { st_s[j] = 0.f; st_q[j] = 0.f; }
     }
-    while (row < r_end) {
+    // STATS == 2 reduces every row over the cols_items lanes that hold it with warp shuffles: all 384 threads then run
+    // the same number of iterations (items beyond the last row are dummies)
+    int iters_left = (max(r_end - r_begin, 0) + step_rows * U - 1) / (step_rows * U);
+    while (STATS == 2 ? (iters_left-- > 0) : (row < r_end)) {
       float v[U][8], g[U][8];
       uint4 raw0[U], raw1[U];
-      int pixs[U], cols[U];
+      int pixs[U], cols[U], rws[U];
       uint32_t offs[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         pixs[u] = -1;
+        rws[u] = row < r_end ? row : r_begin;
         cols[u] = ci * 8;
         // S == 1: the tile is indexed by the tile row; S > 1: slices hold this CTA's rows only (row - r_begin)
         offs[u] = (uint32_t)(((size_t)(row < r_end ? row - (S > 1 ? r_begin : 0) : 0) * LD + cols[u]) * sizeof(float));
@@ -730,8 +781,39 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           }
         }
       }
+      if (LNF) {  // folded LayerNorm: acc -> rstd * (acc - mean * csum)
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (pixs[u] < 0) continue;
+          const float2 mr = ln_vec[rws[u]];
+          float cs[8];
+          load8_f32(p.ln_csum + n_base + cols[u], cs);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[u][j] = mr.y * (v[u][j] - mr.x * cs[j]);
+          if (geglu) {
+            load8_f32(p.ln_csum + n_base + half + cols[u], cs);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[u][j] = mr.y * (g[u][j] - mr.x * cs[j]);
+          }
+        }
+      }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
+        if (STATS == 2) {
+          // every lane takes part in the shuffles; lanes without a valid item contribute zeros
+          float rs = 0.f, rq = 0.f;
+          if (pixs[u] >= 0) {
+            epi_normal_fast<OUT, RES>(p, (long long)pixs[u], p.emb ? (emb_row_fixed >= 0 ? emb_row_fixed : pixs[u] / hw_out) : 0, n_base + cols[u], v[u], raw0[u], raw1[u]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { rs += v[u][j]; rq += v[u][j] * v[u][j]; }
+          }
+          for (int off = cols_items >> 1; off > 0; off >>= 1) {
+            rs += __shfl_xor_sync(0xffffffffu, rs, off);
+            rq += __shfl_xor_sync(0xffffffffu, rq, off);
+          }
+          if (pixs[u] >= 0 && ci == 0) p.row_stats[(size_t)n_tile * p.row_stats_ld + pixs[u]] = make_float2(rs, rq);
+          continue;
+        }
         if (pixs[u] < 0) continue;
         const int col = cols[u];
         if (MODE == SDEO_EPI_GEGLU) {
@@ -742,7 +824,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           epi_qkv_item(p, ri, n_base + col, v[u]);
         } else if (FAST) {
           epi_normal_fast<OUT, RES>(p, (long long)pixs[u], p.emb ? (emb_row_fixed >= 0 ? emb_row_fixed : pixs[u] / hw_out) : 0, n_base + col, v[u], raw0[u], raw1[u]);
-          if (STATS) {  // v[u] now holds the values that were stored
+          if (STATS == 1) {  // v[u] now holds the values that were stored
 #pragma unroll
             for (int j = 0; j < 8; ++j) { st_s[j] += v[u][j]; st_q[j] += v[u][j] * v[u][j]; }
           }
@@ -752,8 +834,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         }
       }
     }
-    if (MODE == SDEO_EPI_QKV) qkv_store_vt(p, tile, LD, row_pix, n_base, (int)threadIdx.x, kConvThreads);  // S == 1
-    if (STATS) {
+    if (MODE == SDEO_EPI_QKV) qkv_store_vt(p, tile, LD, row_pix, LNF ? ln_vec : nullptr, n_base, (int)threadIdx.x, kConvThreads);  // S == 1
+    if (STATS == 1) {
       // column sums of this CTA's rows: registers -> shared memory (one 16-float record per thread) -> one thread per
       // channel adds the row groups in fixed order (deterministic) -> global partial [M tile * S + rank][channel]
       if (S > 1) cluster_wait();  // the scratch below reuses the tile, which peers read until this barrier completes
@@ -771,8 +853,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       const int kparts = kConvThreads / nval > 0 ? kConvThreads / nval : 1;
       float* part2 = scratch + (size_t)kConvThreads * 16;  // [kparts][nval]
       const int t = (int)threadIdx.x;
-      if (t < nval * kparts) {
-        const int val = t % nval, part = t / nval;
+      for (int idx = t; idx < nval * kparts; idx += kConvThreads) {  // (BN = 256: 512 values for 384 threads)
+        const int val = idx % nval, part = idx / nval;
         const int c = val % p.BN, sq = val / p.BN;
         const float* src = scratch + (size_t)(c >> 3) * 16 + sq * 8 + (c & 7);
         float acc = 0.f;
@@ -780,11 +862,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         part2[part * nval + val] = acc;
       }
       __syncthreads();
-      if (t < nval) {
-        const int c = t % p.BN, sq = t / p.BN;
+      for (int val = t; val < nval; val += kConvThreads) {
+        const int c = val % p.BN, sq = val / p.BN;
         if (n_base + c < p.cout) {
           float acc = 0.f;
-          for (int k = 0; k < kparts; ++k) acc += part2[k * nval + t];
+          for (int k = 0; k < kparts; ++k) acc += part2[k * nval + val];
           // slot = sample * (parts per sample) + part. One sample per tile: part = (spatial tile, K-slice rank). A tile
           // that holds several whole samples (tiny feature maps) is only handled as a split-K cluster whose per-rank
           // row ranges do not straddle samples (checked on the host): part = position of the range inside the sample.
@@ -806,7 +888,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   if (threadIdx.x == 64) SDEO_DBG(7);
   // ---- teardown (split-K: peers may still be reading this CTA's tile until the second cluster barrier completes) ----
   tc_fence_before();
-  if (p.splits > 1 && !STATS) cluster_wait();
+  if (p.splits > 1 && STATS != 1) cluster_wait();
   __syncthreads();
   trace_mark(trc, 3);
   if (threadIdx.x == 64) SDEO_DBG(8);
@@ -953,6 +1035,14 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl, int force_bn = 0, i
     const int f = atoi(e);
     if (a->epi_mode != SDEO_EPI_GEGLU && f >= 16 && f <= 256 && f % 16 == 0 && pl->rows_packed % f == 0) pl->BN = f;
   }
+  if (a->row_stats && a->epi_mode == SDEO_EPI_NORMAL && pl->BN != 64 && pl->BN != 128 && pl->BN != 256) {
+    if (force_bn > 0) return false;  // (the autotuner skips this candidate)
+    int pick = 0;
+    for (int bn : {256, 128, 64})
+      if (!pick && pl->rows_packed % bn == 0) pick = bn;
+    if (!pick) return false;
+    pl->BN = pick;
+  }
   if (pl->BN <= 0 || pl->BN > 256 || (pl->BN % 16) != 0) return false;
   pl->n_tiles = pl->rows_packed / pl->BN;
   // ---- split-K over a thread-block cluster ----
@@ -974,7 +1064,7 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl, int force_bn = 0, i
   pl->cps = (pl->total_chunks + splits - 1) / splits;
   pl->splits = (pl->total_chunks + pl->cps - 1) / pl->cps;  // every slice gets >= 1 chunk
   // ---- smem / tmem ----
-  const int kSmemMax = 227 * 1024, kFixed = 2048;  // 1 KB alignment slack + 1 KB barriers / row table
+  const int kSmemMax = 227 * 1024, kFixed = 3072;  // 1 KB alignment slack + 2 KB barriers / row tables
   const int stage_bytes = kATileBytes + pl->BN * 128;
   const int rows_valid = pl->bn_ * pl->bh * pl->bw;
   // fp32 epilogue tile, aliases the pipeline stages. Split-K: the tile (valid rows only) plus the receive area
@@ -1010,7 +1100,7 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl, int force_bn = 0, i
   pl->stages = stages;
   size_t body = (size_t)stages * stage_bytes;
   if (body < (size_t)tile_bytes) body = tile_bytes;
-  if (res_bytes) pl->res_smem_off = 1024 + (int)body;
+  if (res_bytes) pl->res_smem_off = 2048 + (int)body;
   pl->smem_bytes = kFixed + body + res_bytes;
   int tc = 32;
   while (tc < pl->BN + 64) tc *= 2;  // accumulator + 2 x 32 columns of A staging
@@ -1067,8 +1157,18 @@ static int launch_conv(const sdeo_conv_args* a, const ConvPlan& pl, void* stream
 // GroupNorm partial statistics (sdeo_conv_args::gn_stats): produced by the vector-aligned NORMAL epilogue with an fp32
 // output when no M tile spans two samples. Returns the number of partial slots per sample (M tiles per sample x K
 // slices) under plan `pl`, 0 if this call does not produce them.
+// Row statistics (sdeo_conv_args::row_stats) need the vector-aligned NORMAL epilogue with an fp32 output and an N tile of
+// 64 / 128 / 256 columns (the lanes that hold one row must form an aligned power-of-two group of a warp).
+static bool row_stats_ok(const sdeo_conv_args* a, const ConvPlan& pl) {
+  if (!a->row_stats || a->epi_mode != SDEO_EPI_NORMAL || !a->y_fp32) return false;
+  bool fast = (a->cout % 8 == 0) && (a->ldy % 4 == 0);
+  if (a->y2) fast = fast && (a->ldy2 % 8 == 0);
+  if (a->residual) fast = fast && (a->residual_f32 ? (a->ldr % 4 == 0) : (a->ldr % 8 == 0));
+  return fast && (pl.BN == 64 || pl.BN == 128 || pl.BN == 256);
+}
+
 static int stats_parts(const sdeo_conv_args* a, const ConvPlan& pl) {
-  if (!a->gn_stats || a->epi_mode != SDEO_EPI_NORMAL || !a->y_fp32) return 0;
+  if (!a->gn_stats || a->row_stats || a->epi_mode != SDEO_EPI_NORMAL || !a->y_fp32) return 0;
   bool fast = (a->cout % 8 == 0) && (a->ldy % 4 == 0);
   if (a->y2) fast = fast && (a->ldy2 % 8 == 0);
   if (a->residual) fast = fast && (a->residual_f32 ? (a->ldr % 4 == 0) : (a->ldr % 8 == 0));
@@ -1098,7 +1198,7 @@ int g_autotune = 0;
 TuneKey tune_key(const sdeo_conv_args* a) {
   TuneKey k = {a->n, a->h, a->w, a->c1, a->x2 ? a->c2 : 0, a->cout, a->ksize, a->stride, a->epi_mode, a->y_fp32,
                a->residual ? (a->residual_f32 ? 2 : 1) : 0, a->y2 ? 1 : 0, a->emb ? 1 : 0, a->act, a->dhead,
-               (a->gn_stats ? 1 : 0) | (cta_limit() << 1)};
+               (a->gn_stats ? 1 : 0) | (a->row_stats ? 2 : 0) | (a->ln_stats ? 4 : 0) | (cta_limit() << 3)};
   return k;
 }
 
@@ -1188,6 +1288,17 @@ extern "C" int sdeo_conv2d(const sdeo_conv_args* a, void* stream) {
   return launch_conv(a, pl, stream);
 }
 
+extern "C" int sdeo_conv_row_stats_parts(const sdeo_conv_args* a, int32_t* max_parts, int32_t* parts) {
+  if (!a) return set_error(SDEO_EINVAL, "conv_row_stats_parts: null argument");
+  ConvPlan pl;
+  sdeo_conv_args b = *a;
+  if (!b.row_stats) b.row_stats = (float*)(uintptr_t)16;  // "would be produced if a buffer were given"
+  if (!resolve_plan(&b, nullptr, false, &pl)) return set_error(SDEO_EINVAL, "conv_row_stats_parts: unsupported geometry");
+  if (max_parts) *max_parts = (pl.rows_packed + 63) / 64;
+  if (parts) *parts = row_stats_ok(&b, pl) ? pl.n_tiles : 0;
+  return SDEO_OK;
+}
+
 extern "C" int sdeo_conv_gn_stats_slots(const sdeo_conv_args* a, int32_t* max_slots_total, int32_t* parts_per_sample) {
   if (!a) return set_error(SDEO_EINVAL, "conv_gn_stats_slots: null argument");
   ConvPlan pl;
@@ -1264,14 +1375,21 @@ static int launch_conv(const sdeo_conv_args* a, const ConvPlan& pl, void* stream
   p.a_tmem_col = pl.tmem_cols - 64;
   p.ws = nullptr;  // (split-K partials travel through distributed shared memory; the workspace argument is unused)
   p.gn_stats = nullptr;
+  p.row_stats = nullptr; p.row_stats_ld = 0;
+  p.ln_stats = (const float2*)a->ln_stats; p.ln_parts = a->ln_parts; p.ln_ld = a->ln_ld;
+  p.ln_invc = a->ln_c > 0 ? 1.0f / (float)a->ln_c : 0.f; p.ln_eps = a->ln_eps; p.ln_csum = a->ln_csum;
+  if (p.ln_stats && (!p.ln_csum || p.ln_parts <= 0 || a->ln_c <= 0))
+    return set_error(SDEO_EINVAL, "conv2d: folded LayerNorm needs ln_csum, ln_parts and ln_c");
 
   // ---- pick the kernel instantiation ----
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvKParams);
   KernelFn fn = nullptr;
   if (a->epi_mode == SDEO_EPI_GEGLU) {
-    fn = conv_gemm_kernel<SDEO_EPI_GEGLU, OUT_BF16, RES_NONE, true, false>;
+    fn = p.ln_stats ? conv_gemm_kernel<SDEO_EPI_GEGLU, OUT_BF16, RES_NONE, true, 0, true>
+                    : conv_gemm_kernel<SDEO_EPI_GEGLU, OUT_BF16, RES_NONE, true, 0, false>;
   } else if (a->epi_mode == SDEO_EPI_QKV) {
-    fn = conv_gemm_kernel<SDEO_EPI_QKV, OUT_BF16, RES_NONE, true, false>;
+    fn = p.ln_stats ? conv_gemm_kernel<SDEO_EPI_QKV, OUT_BF16, RES_NONE, true, 0, true>
+                    : conv_gemm_kernel<SDEO_EPI_QKV, OUT_BF16, RES_NONE, true, 0, false>;
   } else {
     const int out_kind = !a->y_fp32 ? OUT_BF16 : (p.y2 ? OUT_F32_TWIN : OUT_F32);
     const int res_kind = !a->residual ? RES_NONE : (a->residual_f32 ? RES_F32 : RES_BF16);
@@ -1281,15 +1399,29 @@ static int launch_conv(const sdeo_conv_args* a, const ConvPlan& pl, void* stream
     if (res_kind == RES_BF16) fast = fast && (a->ldr % 8 == 0);
     if (res_kind == RES_F32) fast = fast && (a->ldr % 4 == 0);
     if (!fast) {
-      fn = conv_gemm_kernel<SDEO_EPI_NORMAL, OUT_BF16, RES_NONE, false, false>;
+      if (p.ln_stats) return set_error(SDEO_EINVAL, "conv2d: folded LayerNorm needs the vector-aligned epilogue");
+      fn = conv_gemm_kernel<SDEO_EPI_NORMAL, OUT_BF16, RES_NONE, false, 0, false>;
+    } else if (p.ln_stats) {
+      // (plain-epilogue consumers of a folded LayerNorm: bf16 or fp32 output, no residual; used by the tests)
+      if (res_kind != RES_NONE || out_kind == OUT_F32_TWIN)
+        return set_error(SDEO_EINVAL, "conv2d: folded LayerNorm supports the QKV, GEGLU and residual-free plain epilogues");
+      fn = out_kind == OUT_F32 ? conv_gemm_kernel<SDEO_EPI_NORMAL, OUT_F32, RES_NONE, true, 0, true>
+                               : conv_gemm_kernel<SDEO_EPI_NORMAL, OUT_BF16, RES_NONE, true, 0, true>;
+    } else if (row_stats_ok(a, pl)) {
+      p.row_stats = (float2*)a->row_stats;
+      p.row_stats_ld = a->row_stats_ld;
+#define SDEO_PICK(O, R) if (out_kind == O && res_kind == R) fn = conv_gemm_kernel<SDEO_EPI_NORMAL, O, R, true, 2, false>;
+      SDEO_PICK(OUT_F32, RES_NONE) SDEO_PICK(OUT_F32, RES_BF16) SDEO_PICK(OUT_F32, RES_F32)
+      SDEO_PICK(OUT_F32_TWIN, RES_NONE) SDEO_PICK(OUT_F32_TWIN, RES_BF16) SDEO_PICK(OUT_F32_TWIN, RES_F32)
+#undef SDEO_PICK
     } else if (stats_parts(a, pl) > 0) {
       p.gn_stats = (float2*)a->gn_stats;
-#define SDEO_PICK(O, R) if (out_kind == O && res_kind == R) fn = conv_gemm_kernel<SDEO_EPI_NORMAL, O, R, true, true>;
+#define SDEO_PICK(O, R) if (out_kind == O && res_kind == R) fn = conv_gemm_kernel<SDEO_EPI_NORMAL, O, R, true, 1, false>;
       SDEO_PICK(OUT_F32, RES_NONE) SDEO_PICK(OUT_F32, RES_BF16) SDEO_PICK(OUT_F32, RES_F32)
       SDEO_PICK(OUT_F32_TWIN, RES_NONE) SDEO_PICK(OUT_F32_TWIN, RES_BF16) SDEO_PICK(OUT_F32_TWIN, RES_F32)
 #undef SDEO_PICK
     } else {
-#define SDEO_PICK(O, R) if (out_kind == O && res_kind == R) fn = conv_gemm_kernel<SDEO_EPI_NORMAL, O, R, true, false>;
+#define SDEO_PICK(O, R) if (out_kind == O && res_kind == R) fn = conv_gemm_kernel<SDEO_EPI_NORMAL, O, R, true, 0, false>;
       SDEO_PICK(OUT_BF16, RES_NONE) SDEO_PICK(OUT_BF16, RES_BF16) SDEO_PICK(OUT_BF16, RES_F32)
       SDEO_PICK(OUT_F32, RES_NONE) SDEO_PICK(OUT_F32, RES_BF16) SDEO_PICK(OUT_F32, RES_F32)
       SDEO_PICK(OUT_F32_TWIN, RES_NONE) SDEO_PICK(OUT_F32_TWIN, RES_BF16) SDEO_PICK(OUT_F32_TWIN, RES_F32)
@@ -1299,14 +1431,14 @@ static int launch_conv(const sdeo_conv_args* a, const ConvPlan& pl, void* stream
   if (!fn) return set_error(SDEO_EINVAL, "conv2d: no kernel instantiation");
   {
     // opt in to > 48 KB of dynamic shared memory, once per instantiation
-    static KernelFn configured[32];
+    static KernelFn configured[48];
     static int n_configured = 0;
     bool seen = false;
     for (int i = 0; i < n_configured; ++i) seen = seen || (configured[i] == fn);
     if (!seen) {
       cudaError_t e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess) return set_error(SDEO_ECUDA, cudaGetErrorString(e));
-      if (n_configured < 32) configured[n_configured++] = fn;
+      if (n_configured < 48) configured[n_configured++] = fn;
     }
   }
   return launch_k("conv2d", fn, dim3((unsigned)(pl.tiles_n * pl.tiles_h * pl.tiles_w), (unsigned)pl.n_tiles, (unsigned)pl.splits),

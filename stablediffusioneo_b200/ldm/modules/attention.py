@@ -45,7 +45,18 @@ class GEGLU(nn.Module):
             hit = self._cache["w"]
         return hit[1], hit[2]
 
+    def _packed_ln(self, ln):
+        key = _param_key(self.proj.weight, self.proj.bias, ln.weight, ln.bias)
+        hit = self._cache.get("ln")
+        if hit is None or hit[0] != key:
+            self._cache["ln"] = (key,) + util.fold_ln_weight(self.proj.weight, self.proj.bias, ln, geglu=True)
+            hit = self._cache["ln"]
+        return hit[1:]
+
     def run(self, x):
+        if isinstance(x, util.DeferredLN):  # LayerNorm folded into this projection
+            pw, pb, csum = self._packed_ln(x.ln)
+            return ops.linear(x.raw(), pw, bias=pb, geglu=True, ln=x.fold(csum))
         pw, pb = self._packed()
         return ops.linear(x, pw, bias=pb, geglu=True)
 
@@ -111,6 +122,16 @@ class CrossAttention(nn.Module):
             hit = self._cache[which]
         return hit[1]
 
+    def _packed_ln(self, which, ln):
+        params = (self.to_q.weight, self.to_k.weight, self.to_v.weight) if which == "qkv" else (self.to_q.weight,)
+        key = _param_key(*params, ln.weight, ln.bias)
+        hit = self._cache.get(which + "_ln")
+        if hit is None or hit[0] != key:
+            w = torch.cat([p.detach() for p in params], 0)
+            self._cache[which + "_ln"] = (key,) + util.fold_ln_weight(w, None, ln)
+            hit = self._cache[which + "_ln"]
+        return hit[1:]
+
     def project_kv(self, context, k=None, vt=None):
         """k [B*heads, nkv, d], vt [B*heads, d, ldv] for a context [B, nkv, ctx_dim] (one GEMM on kv_w)."""
         b, nkv, _ = context.shape
@@ -122,9 +143,13 @@ class CrossAttention(nn.Module):
         ops.qkv_project(context, self._packed("kv"), h, d, 1, k=k, vt=vt, ldv=ldv)
         return k, vt, nkv, ldv
 
-    def run(self, x, context=None, residual=None, stream=False):
-        """x: [B, T, C] bf16; context [B, nkv, ctx_dim] bf16 or None (self-attention). Returns to_out(attn) (+ residual);
-        `stream`: the result is an fp32 residual-stream tensor."""
+    def run(self, x, context=None, residual=None, stream=False, feeds_ln=False):
+        """x: [B, T, C] bf16 (or a DeferredLN: the LayerNorm is folded into the q / qkv projection); context
+        [B, nkv, ctx_dim] bf16 or None (self-attention). Returns to_out(attn) (+ residual); `stream`: the result is an
+        fp32 residual-stream tensor; feeds_ln: it feeds a LayerNorm (bf16 twin + row statistics from the epilogue)."""
+        ln = x if isinstance(x, util.DeferredLN) else None
+        if ln is not None:
+            x = ln.raw()
         b, t, _ = x.shape
         h, d = self.heads, self.dim_head
         q = torch.empty((b * h, t, d), dtype=BF16, device=x.device)
@@ -132,16 +157,25 @@ class CrossAttention(nn.Module):
             ldv = (t + 7) // 8 * 8
             k = torch.empty_like(q)
             vt = torch.empty((b * h, d, ldv), dtype=BF16, device=x.device)
-            ops.qkv_project(x, self._packed("qkv"), h, d, 0, q=q, k=k, vt=vt, ldv=ldv)
+            if ln is not None:
+                pw, bp, csum = self._packed_ln("qkv", ln.ln)
+                ops.qkv_project(x, pw, h, d, 0, q=q, k=k, vt=vt, ldv=ldv, bias=bp, ln=ln.fold(csum))
+            else:
+                ops.qkv_project(x, self._packed("qkv"), h, d, 0, q=q, k=k, vt=vt, ldv=ldv)
             nkv = t
         else:
-            ops.qkv_project(x, self._packed("q"), h, d, 0, q=q)
+            if ln is not None:
+                pw, bp, csum = self._packed_ln("q", ln.ln)
+                ops.qkv_project(x, pw, h, d, 0, q=q, bias=bp, ln=ln.fold(csum))
+            else:
+                ops.qkv_project(x, self._packed("q"), h, d, 0, q=q)
             if self.kv_static is not None and self.kv_static[0] is context:
                 _, k, vt, nkv, ldv = self.kv_static
             else:
                 k, vt, nkv, ldv = self.project_kv(context)
         o = ops.attention(q, k, vt, b, h, t, nkv, d, ldv, self.scale)
-        return self.to_out[0].run(o, residual=residual, stream=stream)
+        return self.to_out[0].run(o, residual=residual, stream=stream, twin=stream and feeds_ln,
+                                  row_stats=stream and feeds_ln)
 
     def forward(self, x, context=None, mask=None):
         if exists(mask):
@@ -171,8 +205,9 @@ class BasicTransformerBlock(nn.Module):
     def run(self, x, context=None):
         """attention.py:381-385; each residual add rides in the epilogue of the branch's last GEMM."""
         st = util.STREAM_FP32
-        x = self.attn1.run(self.norm1.run(x), context if self.disable_self_attn else None, residual=x, stream=st)
-        x = self.attn2.run(self.norm2.run(x), context, residual=x, stream=st)
+        x = self.attn1.run(self.norm1.run(x), context if self.disable_self_attn else None, residual=x, stream=st,
+                           feeds_ln=True)
+        x = self.attn2.run(self.norm2.run(x), context, residual=x, stream=st, feeds_ln=True)
         x = self.ff.run(self.norm3.run(x), residual=x, stream=st)
         return x
 
@@ -212,8 +247,13 @@ class SpatialTransformer(nn.Module):
         b, c, h, w = x.shape
         x_in = x
         st = util.STREAM_FP32
-        t = self.proj_in.run(self.norm.run(x, silu=False), out_fp32=st)   # the token stream's first value
+        t = self.proj_in.run(self.norm.run(x, silu=False), out_fp32=st, stream=st, row_stats=st)  # the token stream
         tok = nhwc(t).reshape(b, h * w, t.shape[1])
+        if getattr(t, "_sdeo_stream", False):  # [B,H,W,C] stream -> [B,T,C] stream (same memory), attributes carried over
+            tok._sdeo_stream = True
+            tok._twin = nhwc(t._twin).reshape(b, h * w, t.shape[1]) if t._twin is not None else None
+            tok._gn_stats = None
+            tok._row_stats = t._row_stats
         for i, block in enumerate(self.transformer_blocks):
             tok = block.run(tok, context[i])
         tok = operand(tok)                                                 # bf16 twin written by the last ff GEMM

@@ -42,6 +42,59 @@ STREAM_FP32 = True
 # Convolutions whose fp32 output feeds a GroupNorm also emit per-channel partial statistics from their epilogue
 # (sdeo_conv_args::gn_stats); the GroupNorm then reads the tensor once. SDEO_NO_GN_STATS=1 restores the standalone pass.
 FUSE_GN_STATS = not os.environ.get("SDEO_NO_GN_STATS")
+# LayerNorms of the transformer blocks are folded into the GEMM that consumes them (no LayerNorm kernel, no normalised
+# tensor in memory): the producer of the LayerNorm input leaves per-row (sum, sum of squares) partials, the consumer runs
+# on the raw bf16 input with gamma folded into its weight and corrects acc -> rstd * (acc - mean * colsum) + bias' in its
+# epilogue. SDEO_NO_LN_FOLD=1 restores the standalone LayerNorm pass.
+FOLD_LN = not os.environ.get("SDEO_NO_LN_FOLD")
+
+
+class DeferredLN:
+    """LayerNorm(x) that has not been computed: the raw bf16 x (the fp32 stream's twin), the row statistics its
+    producer left, and the LayerNorm module. Consumers (CrossAttention / GEGLU projections) fold it into their GEMM;
+    `.value()` materialises it with the standalone kernel for anything else."""
+
+    def __init__(self, x, ln):
+        self.x, self.ln = x, ln
+
+    @property
+    def shape(self):
+        return self.x.shape
+
+    @property
+    def device(self):
+        return self.x.device
+
+    @property
+    def dtype(self):
+        return BF16
+
+    def raw(self):
+        return operand(self.x)
+
+    def value(self):
+        return ops.layernorm(self.x, self.ln.weight.detach(), self.ln.bias.detach(), self.ln.eps)
+
+    def fold(self, csum):
+        buf, parts, rows = self.x._row_stats
+        return ops.LnFold(buf, parts, rows, self.x.shape[-1], self.ln.eps, csum)
+
+
+def fold_ln_weight(weight, bias, ln, geglu=False):
+    """(packed weight of W * gamma, bias' = bias + W @ beta in the kernel's row order, column sums of the PACKED bf16
+    weight) for a Linear [out, in] whose input is LayerNorm `ln`."""
+    w = weight.detach().float()
+    g, b = ln.weight.detach().float(), ln.bias.detach().float()
+    pw = ops.pack_conv_weight(w * g[None, :], geglu=geglu)
+    bp = w @ b
+    if bias is not None:
+        bp = bp + bias.detach().float()
+    bp = ops.pack_geglu_bias(bp.contiguous(), pw.geglu_bn) if geglu else bp.contiguous()
+    rows = pw.data.shape[0]
+    csum = pw.data.float().sum(dim=1).contiguous()
+    if bp.numel() < rows:  # rows are padded to a multiple of 16
+        bp = torch.cat([bp, torch.zeros(rows - bp.numel(), dtype=bp.dtype, device=bp.device)])
+    return pw, bp, csum
 
 
 def make_stream(y_f32, y_bf16=None):
@@ -49,6 +102,7 @@ def make_stream(y_f32, y_bf16=None):
     t = nchw_view(y_f32) if y_f32.dim() == 4 else y_f32
     t._sdeo_stream = True
     t._gn_stats = getattr(y_f32, "_gn_stats", None)
+    t._row_stats = getattr(y_f32, "_row_stats", None)
     t._twin = None if y_bf16 is None else (nchw_view(y_bf16) if y_bf16.dim() == 4 else y_bf16)
     return t
 
@@ -169,7 +223,7 @@ class Conv2d(nn.Conv2d):
         return self.bias.detach() if self.bias is not None else None
 
     def run(self, x, emb=None, residual=None, scale=1.0, act=SDEO_ACT_NONE, out_fp32=False, stream=False, emb_step=None,
-            gn_stats=False):
+            gn_stats=False, row_stats=False):
         """x: internal tensor (bf16 or fp32 stream) or CatPair. Returns an internal bf16 tensor; fp32 NHWC-physical when
         out_fp32; an fp32 stream tensor with a bf16 twin when `stream`. A bf16 output whose channel count is not a
         multiple of 8 is zero-padded to one (so a following conv can TMA it)."""
@@ -185,7 +239,8 @@ class Conv2d(nn.Conv2d):
             ops.memset(out, 0)
         kw = dict(bias=self.bias_f32(), emb=emb, residual=res, scale=scale, act=act, stride=self.stride[0],
                   out_fp32=out_fp32 or stream, out=out, twin=stream, emb_step=emb_step,
-                  gn_stats=gn_stats and (out_fp32 or stream) and FUSE_GN_STATS)
+                  gn_stats=gn_stats and (out_fp32 or stream) and FUSE_GN_STATS,
+                  row_stats=row_stats and (out_fp32 or stream) and FOLD_LN)
         if isinstance(x, CatPair):
             a, b = operand(x.a), operand(x.b)
             y = ops.conv2d(nhwc(a), self.packed((a.shape[1], b.shape[1])), x2=nhwc(b), **kw)
@@ -218,11 +273,12 @@ class Linear(nn.Linear):
             hit = self._cache["w"]
         return hit[1]
 
-    def run(self, x, residual=None, act=SDEO_ACT_NONE, out_fp32=False, stream=False, twin=False):
-        """x: bf16 tokens. stream: fp32 output tagged as residual stream (bf16 twin attached when `twin`)."""
+    def run(self, x, residual=None, act=SDEO_ACT_NONE, out_fp32=False, stream=False, twin=False, row_stats=False):
+        """x: bf16 tokens. stream: fp32 output tagged as residual stream (bf16 twin attached when `twin`); row_stats: the
+        output feeds a LayerNorm that its consumer folds (per-row statistics from this epilogue)."""
         b = self.bias.detach() if self.bias is not None else None
         y = ops.linear(operand(x), self.packed(), bias=b, residual=residual, act=act, out_fp32=out_fp32 or stream,
-                       twin=stream and twin)
+                       twin=stream and twin, row_stats=row_stats and (out_fp32 or stream) and FOLD_LN)
         if stream:
             return make_stream(*y) if twin else make_stream(y)
         return y
@@ -259,6 +315,10 @@ class GroupNorm32(nn.GroupNorm):
 
 class LayerNorm(nn.LayerNorm):
     def run(self, x):
+        """bf16 LayerNorm(x) -- or, when x carries its producer's row statistics and a bf16 twin, a DeferredLN that the
+        consuming projection folds into its GEMM."""
+        if FOLD_LN and getattr(x, "_row_stats", None) is not None and getattr(x, "_twin", None) is not None:
+            return DeferredLN(x, self)
         return ops.layernorm(x, self.weight.detach(), self.bias.detach(), self.eps)
 
     def forward(self, x):

@@ -132,13 +132,16 @@ def pack_geglu_bias(bias, geglu_bn):
 
 
 def conv2d(x, pw, x2=None, bias=None, emb=None, residual=None, scale=1.0, act=SDEO_ACT_NONE, stride=1, out=None,
-           out_fp32=False, epi_mode=SDEO_EPI_NORMAL, qkv=None, twin=False, emb_step=None, gn_stats=False):
+           out_fp32=False, epi_mode=SDEO_EPI_NORMAL, qkv=None, twin=False, emb_step=None, gn_stats=False, row_stats=False,
+           ln=None):
     """x: [N,H,W,C1] bf16 (+ optional x2 [N,H,W,C2] = fused torch.cat along channels). Returns [N,Ho,Wo,cout].
     residual may be bf16 or fp32. out_fp32 + twin=True additionally writes a bf16 copy and returns (y_f32, y_bf16).
     emb: fp32 [N, cout] (row = sample), or with emb_step (int32 device scalar) a table [S, cout] whose row *emb_step is
     added to every sample. gn_stats (fp32 outputs): the epilogue also leaves per-channel partial statistics for the
     GroupNorm that consumes the result; they are attached to the returned fp32 tensor as `_gn_stats = (buffer, parts
-    per sample)` when the kernel produced them (see groupnorm(stats=...))."""
+    per sample)` when the kernel produced them (see groupnorm(stats=...)). row_stats (fp32 outputs feeding a LayerNorm):
+    per-row partial statistics, attached as `_row_stats = (buffer, parts, rows)`. ln: LnFold -- this GEMM applies a
+    LayerNorm to its input rows in the epilogue (x is the raw bf16 input; pw / bias carry gamma / beta)."""
     lib = _lib.load()
     _req(x, BF16, "x")
     _req(x2, BF16, "x2")
@@ -197,6 +200,17 @@ def conv2d(x, pw, x2=None, bias=None, emb=None, residual=None, scale=1.0, act=SD
         a.y2, a.ldy2 = _ptr(out2), out2.shape[3]
     ws = _workspaces.conv(x.device)
     a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
+    if ln is not None:
+        a.ln_stats, a.ln_parts, a.ln_ld = _ptr(ln.stats), ln.parts, ln.rows
+        a.ln_c, a.ln_eps, a.ln_csum = ln.c, float(ln.eps), _ptr(ln.csum)
+        assert ln.rows == n * ho * wo and ln.c == c1 and c2 == 0
+    rows_buf = None
+    if row_stats and out_fp32 and epi_mode == SDEO_EPI_NORMAL:
+        mx = ctypes.c_int32(0)
+        _check(lib.sdeo_conv_row_stats_parts(ctypes.byref(a), ctypes.byref(mx), None), "conv_row_stats_parts")
+        rows_buf = torch.empty((mx.value, n * ho * wo, 2), dtype=torch.float32, device=x.device)
+        a.row_stats, a.row_stats_ld = _ptr(rows_buf), n * ho * wo
+        gn_stats = False
     stats_buf = None
     if gn_stats and out_fp32 and epi_mode == SDEO_EPI_NORMAL:
         mx = ctypes.c_int32(0)
@@ -209,10 +223,28 @@ def conv2d(x, pw, x2=None, bias=None, emb=None, residual=None, scale=1.0, act=SD
         _check(lib.sdeo_conv_gn_stats_slots(ctypes.byref(a), None, ctypes.byref(parts)), "conv_gn_stats_slots")
         if parts.value > 0:
             out._gn_stats = (stats_buf, parts.value)
+    if rows_buf is not None:
+        parts = ctypes.c_int32(0)
+        _check(lib.sdeo_conv_row_stats_parts(ctypes.byref(a), None, ctypes.byref(parts)), "conv_row_stats_parts")
+        if parts.value > 0:
+            out._row_stats = (rows_buf, parts.value, n * ho * wo)
     return (out, out2) if twin else out
 
 
-def linear(x, pw, bias=None, residual=None, act=SDEO_ACT_NONE, out_fp32=False, geglu=False, twin=False):
+@dataclass
+class LnFold:
+    """A LayerNorm folded into the GEMM that consumes it: row statistics of the raw input (from its producer's
+    epilogue), the normalised width, eps, and the column sums of the gamma-scaled packed weight."""
+    stats: torch.Tensor
+    parts: int
+    rows: int
+    c: int
+    eps: float
+    csum: torch.Tensor
+
+
+def linear(x, pw, bias=None, residual=None, act=SDEO_ACT_NONE, out_fp32=False, geglu=False, twin=False, row_stats=False,
+           ln=None):
     """x: [..., K] bf16 -> [..., cout] (GEGLU: [..., cout/2]). Runs the 1x1 case of the implicit-GEMM kernel."""
     lead = x.shape[:-1]
     rows = 1
@@ -221,18 +253,22 @@ def linear(x, pw, bias=None, residual=None, act=SDEO_ACT_NONE, out_fp32=False, g
     x4 = x.reshape(1, 1, rows, x.shape[-1])
     res4 = residual.reshape(1, 1, rows, residual.shape[-1]) if residual is not None else None
     y = conv2d(x4, pw, bias=bias, residual=res4, act=act, out_fp32=out_fp32,
-               epi_mode=SDEO_EPI_GEGLU if geglu else SDEO_EPI_NORMAL, twin=twin)
+               epi_mode=SDEO_EPI_GEGLU if geglu else SDEO_EPI_NORMAL, twin=twin, row_stats=row_stats, ln=ln)
+    y0 = y[0] if twin else y
+    r0 = y0.reshape(*lead, y0.shape[-1])
+    if getattr(y0, "_row_stats", None) is not None:
+        r0._row_stats = y0._row_stats
     if twin:
-        return y[0].reshape(*lead, y[0].shape[-1]), y[1].reshape(*lead, y[1].shape[-1])
-    return y.reshape(*lead, y.shape[-1])
+        return r0, y[1].reshape(*lead, y[1].shape[-1])
+    return r0
 
 
-def qkv_project(x, pw, heads, dhead, first, q=None, k=None, vt=None, ldv=None, bias=None):
+def qkv_project(x, pw, heads, dhead, first, q=None, k=None, vt=None, ldv=None, bias=None, ln=None):
     """x: [B, T, K] bf16. Packed rows hold consecutive blocks of heads*dhead columns for q/k/v starting at
     `first` (0=q, 1=k, 2=v). Writes q,k as [B*heads, T, dhead] and v transposed as [B*heads, dhead, ldv]."""
     b, t, kdim = x.shape
     x4 = x.reshape(1, 1, b * t, kdim)
-    conv2d(x4, pw, bias=bias, epi_mode=SDEO_EPI_QKV, qkv=(q, k, vt, heads, dhead, t, ldv or 0, first))
+    conv2d(x4, pw, bias=bias, epi_mode=SDEO_EPI_QKV, qkv=(q, k, vt, heads, dhead, t, ldv or 0, first), ln=ln)
 
 
 def groupnorm(x, gamma, beta, eps, silu, x2=None, groups=32, out=None, stats=None, stats2=None):

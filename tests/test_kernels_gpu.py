@@ -281,6 +281,79 @@ def test_groupnorm_from_conv_statistics(cuda_device, case, autotune):
     assert rel_l2(y_fused, y_plain) < 2e-3   # same math, different fp32 summation order (+ bf16 rounding flips)
 
 
+def test_groupnorm_statistics_every_tile_config(cuda_device):
+    """The fused statistics under every (N tile, K slices) configuration the planner / autotuner can pick, forced
+    through SDEO_FORCE_BN / SDEO_FORCE_SPLITS (N tile 256 carries 512 statistics values for 384 threads)."""
+    import os
+    from stablediffusioneo_b200 import ops
+    dev = cuda_device
+    n, cin, cout, h, w, k = 2, 1280, 1280, 8, 12, 3
+    x = gen((n, cin, h, w), 1, dev)
+    wt = gen((cout, cin, k, k), 11, dev) / math.sqrt(cin * k * k)
+    res = gen((n, h, w, cout), 31, dev)
+    pw = ops.pack_conv_weight(wt)
+    gamma = gen((cout,), 3, dev) * 0.2 + 1.0
+    beta = gen((cout,), 4, dev) * 0.2
+    checked = 0
+    try:
+        for bn in (64, 80, 128, 160, 256):
+            for sp in (1, 2, 4, 8):
+                os.environ["SDEO_FORCE_BN"], os.environ["SDEO_FORCE_SPLITS"] = str(bn), str(sp)
+                try:
+                    y, _ = ops.conv2d(nhwc(x), pw, residual=res, out_fp32=True, twin=True, gn_stats=True)
+                except Exception:
+                    continue  # configuration does not fit shared memory
+                st = getattr(y, "_gn_stats", None)
+                assert st is not None
+                out = ops.groupnorm(y, gamma, beta, 1e-5, True, stats=st)
+                ref = F.silu(F.group_norm(y.permute(0, 3, 1, 2), 32, gamma, beta, 1e-5))
+                assert rel_l2(out.permute(0, 3, 1, 2), ref) < TOL, (bn, sp)
+                checked += 1
+    finally:
+        os.environ.pop("SDEO_FORCE_BN", None)
+        os.environ.pop("SDEO_FORCE_SPLITS", None)
+    assert checked >= 12
+
+
+@pytest.mark.parametrize("rows,c,geglu", [(3072, 320, False), (768, 640, True), (192, 1280, False), (48, 1280, True),
+                                          (24, 1280, False)])
+def test_layernorm_folded_into_gemm(cuda_device, rows, c, geglu):
+    """Producer GEMM (fp32 stream + bf16 twin + per-row statistics) -> consumer GEMM on the RAW twin with the LayerNorm
+    folded (gamma in the weight, beta in the bias, mean / rstd correction in the epilogue), against
+    F.layer_norm(fp32 stream) @ W in fp32 and against the standalone LayerNorm kernel + plain GEMM."""
+    from stablediffusioneo_b200 import ops
+    from stablediffusioneo_b200.ldm.modules.diffusionmodules import util
+    dev = cuda_device
+    xin = gen((rows, c), 1, dev).to(torch.bfloat16)
+    wp = gen((c, c), 2, dev) / math.sqrt(c)
+    res = gen((rows, c), 3, dev) * 1.5 + 0.4          # rows with a clearly non-zero mean
+    y, y16 = ops.linear(xin, ops.pack_conv_weight(wp), residual=res, out_fp32=True, twin=True, row_stats=True)
+    assert getattr(y, "_row_stats", None) is not None
+    ln = torch.nn.LayerNorm(c).to(dev)
+    with torch.no_grad():
+        ln.weight.copy_(gen((c,), 4, dev) * 0.2 + 1.0)
+        ln.bias.copy_(gen((c,), 5, dev) * 0.2)
+    nout = 2 * c if geglu else 3 * c
+    w = gen((nout, c), 6, dev) / math.sqrt(c)
+    bias = gen((nout,), 7, dev) * 0.1
+    pw, bp, csum = util.fold_ln_weight(w, bias, ln, geglu=geglu)
+    buf, parts, nrows = y._row_stats
+    fold = ops.LnFold(buf, parts, nrows, c, ln.eps, csum)
+    out = ops.linear(y16, pw, bias=bp, geglu=geglu, ln=fold, out_fp32=not geglu)
+    z = F.layer_norm(y, (c,), ln.weight, ln.bias, ln.eps) @ bf16r(w).t() + bias
+    ref = z[:, :c] * F.gelu(z[:, c:]) if geglu else z
+    # the raw rows (mean 0.2 sigma here) are rounded to bf16 BEFORE the mean is removed: slightly above the per-op TOL
+    assert rel_l2(out, ref) < 1.5 * TOL
+    # the unfused path on the same data
+    lnx = ops.layernorm(y, ln.weight.detach(), ln.bias.detach(), ln.eps)
+    if geglu:
+        pw0 = ops.pack_conv_weight(w, geglu=True)
+        plain = ops.linear(lnx, pw0, bias=ops.pack_geglu_bias(bias, pw0.geglu_bn), geglu=True)
+    else:
+        plain = ops.linear(lnx, ops.pack_conv_weight(w), bias=bias, out_fp32=True)
+    assert rel_l2(out, plain) < 6e-3
+
+
 @pytest.mark.parametrize("rows,c", [(3072, 320), (768, 640), (192, 1280), (48, 1280), (5, 512)])
 def test_layernorm(cuda_device, rows, c):
     from stablediffusioneo_b200 import ops
