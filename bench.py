@@ -37,7 +37,7 @@ LATENT_HW = (32, 48)
 CFG_SCALE = 9.0
 WORKLOAD = "ControlNet-canny SD1.5 256x384 batch 1, DDIM 20 steps, CFG 9.0 (BASELINE configs[1])"
 FLOPS_PER_STEP = 740.0e9          # one DDIM step = 2 x (ControlNet 95.6 + UNet 274.4) GF at 32x48
-CONV_DRAM_BYTES_PER_LAUNCH = 10264969  # ncu dram__bytes_read.sum + write.sum over one step's conv launches / launches
+CONV_DRAM_BYTES_PER_LAUNCH = 10284140  # ncu dram__bytes_read.sum + write.sum over one step's conv launches / launches
 WEIGHT_BYTES_PER_STEP = 2.442e9   # bf16 UNet 1.719 GB + ControlNet 0.723 GB, streamed once per step (cond+uncond batched)
 
 
@@ -211,7 +211,7 @@ def conv_roofline(eng, pk):
     return {"bound": "tensor", "kernel": "conv_gemm_kernel", "achieved": achieved, "peak": pk["bf16_sustained"],
             "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
             # dram__bytes_read+write per launch, averaged over the conv launches of one step (ncu --graph-profiling node,
-            # profiles/r01b_launches_step_summary.txt; cold-cache replays; algorithmic: 2.442 GB of weights / launches)
+            # profiles/r01c_launches_step_summary.txt; cold-cache replays; algorithmic: 2.442 GB of weights / launches)
             "traffic": CONV_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes/launch (ncu, cold cache)",
             "launches_per_step": conv["launches"], "flops_per_step": total_flops,
             "kernel_ms_per_step": conv_us * 1e-3, "kernel_busy_ms_per_step": conv["busy_us"] * 1e-3,
