@@ -560,6 +560,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     }
   }
 
+  if (warp >= 6) {
+    // the epilogue's per-column vectors (bias, time-embedding row, folded-LayerNorm column sums) are its only global
+    // loads that are not prefetched otherwise: the idle warps pull their cache lines into L1 during the mainloop
+    const int t = (int)threadIdx.x - 192;
+    const int nb = n_tile * p.BN;
+    const int lines = (p.BN * 4 + 127) / 128;
+    if (t < lines && nb + t * 32 < p.cout) {
+      if (p.bias) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + nb + t * 32));
+      if (LNF) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.ln_csum + nb + t * 32));
+      if (p.emb) {
+        const int erow = p.emb_step ? __ldg(p.emb_step) : n0;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p.emb + (long long)erow * p.cout + nb + t * 32));
+      }
+    }
+  }
+
   if (LNF && warp >= 6) {
     // ===================== folded LayerNorm: (mean, rstd) of every tile row (warps 6..11, during the mainloop) =========
     const int per_img = p.bh * p.bw;
