@@ -216,6 +216,9 @@ def conv_roofline(eng, pk):
             "launches_per_step": conv["launches"], "flops_per_step": total_flops,
             "kernel_ms_per_step": conv_us * 1e-3, "kernel_busy_ms_per_step": conv["busy_us"] * 1e-3,
             "avg_launch_us": conv_us / conv["launches"],
+            # the same FLOPs over the wall-clock time during which at least one conv kernel runs (+ tails): the two
+            # streams' launches overlap in time, `achieved` charges every launch its full duration
+            "achieved_while_running": total_flops / ((conv["union_us"] + conv["tail_us"]) * 1e-6) / 1e12,
             "kernel_share_of_step_kernel_time": conv["busy_us"] / busy_all,
             "method": "sdeo_set_trace during one replay of the timed step graph: sum over conv launches of (grid "
                       "dependency resolved -> block-0 end) + the idle tail after each until another kernel runs",

@@ -58,4 +58,16 @@ def summarize(records):
             union += r.end - (max(cur_end, r.dep) if cur_end is not None else r.dep)
             cur_end, last = r.end, r
     span = max(r.end for r in records) if records else 0.0
+    # per kind: wall-clock time during which at least one kernel of that kind is past its dependency (launches of the
+    # two streams that run side by side are not counted twice)
+    for kind, a in per.items():
+        cur_e, u = None, 0.0
+        for r in sorted((r for r in records if r.kind == kind), key=lambda r: r.dep):
+            if cur_e is None or r.dep > cur_e:
+                u += r.end - r.dep
+                cur_e = r.end
+            elif r.end > cur_e:
+                u += r.end - cur_e
+                cur_e = r.end
+        a["union_us"] = u
     return {"kinds": per, "busy_union_us": union, "span_us": span}
