@@ -55,7 +55,7 @@ enum {
   SDEO_EPI_GEGLU = 1,  /* packed N tile = [x | gate]; y[:, j] = (x + bx) * gelu_erf(gate + bg)      */
   SDEO_EPI_QKV = 2     /* scatter to head-major q,k [B,heads,tok,d] and transposed v [B,heads,d,ldv] */
 };
-enum { SDEO_ACT_NONE = 0, SDEO_ACT_SILU = 1 };
+enum { SDEO_ACT_NONE = 0, SDEO_ACT_SILU = 1, SDEO_ACT_QUICK_GELU = 2 /* x * sigmoid(1.702 x): CLIP text MLP */ };
 
 typedef struct sdeo_conv_args {
   /* input activation(s): x1 carries channels [0,c1), optional x2 channels [c1,c1+c2) (fused torch.cat, dim=1) */
@@ -179,6 +179,13 @@ int sdeo_layernorm(const void* x, int32_t x_f32, const float* gamma, const float
  * ---------------------------------------------------------------------------------------------- */
 int sdeo_attention(const void* q, const void* k, const void* vt, void* o, int32_t batch, int32_t heads,
                    int32_t nq, int32_t nkv, int32_t d, int32_t ldv, float scale, void* stream);
+/* Same with a causal mask (query i attends keys 0..i; nq == nkv == n): the CLIP text encoder's self-attention
+ * (transformers CLIPTextModel, used by FrozenCLIPEmbedder, ldm/modules/encoders/modules.py:123-141). */
+int sdeo_attention_causal(const void* q, const void* k, const void* vt, void* o, int32_t batch, int32_t heads, int32_t n,
+                          int32_t d, int32_t ldv, float scale, void* stream);
+/* y[r] = tok[ids[r]] + pos[r % t] (fp32 [rows, c]) + optional bf16 copy y2: CLIP token + position embeddings. */
+int sdeo_embedding_add(const int64_t* ids, const float* tok, const float* pos, float* y, void* y2, int32_t rows, int32_t t,
+                       int32_t c, int32_t vocab, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Elementwise / layout passes

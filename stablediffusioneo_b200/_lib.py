@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SDEO_LIB") or os.path.join(HERE, "_C", "libsdeo.so")
 
 SDEO_EPI_NORMAL, SDEO_EPI_GEGLU, SDEO_EPI_QKV = 0, 1, 2
-SDEO_ACT_NONE, SDEO_ACT_SILU = 0, 1
+SDEO_ACT_NONE, SDEO_ACT_SILU, SDEO_ACT_QUICK_GELU = 0, 1, 2
 
 
 class ConvArgs(Structure):
@@ -69,6 +69,10 @@ SIGNATURES = {
     "sdeo_upsample_nearest2x": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "sdeo_add_scaled": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_int64, c_void_p]),
     "sdeo_timestep_embedding": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_void_p]),
+    "sdeo_attention_causal": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                      c_float, c_void_p]),
+    "sdeo_embedding_add": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                   c_void_p]),
     "sdeo_softmax_rows": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_float, c_void_p]),
     "sdeo_silu": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "sdeo_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),

@@ -242,7 +242,7 @@ class ControlLDM(nn.Module):
 
     def __init__(self, unet_config=None, control_stage_config=None, first_stage_config=None, control_key="hint",
                  only_mid_control=False, timesteps=1000, linear_start=0.00085, linear_end=0.012, scale_factor=0.18215,
-                 parameterization="eps"):
+                 parameterization="eps", cond_stage_config=None):
         super().__init__()
         unet_kw = dict(SD15_UNET_KW if unet_config is None else unet_config)
         cn_kw = dict(control_stage_config) if control_stage_config is not None else dict(unet_kw, hint_channels=3)
@@ -250,6 +250,12 @@ class ControlLDM(nn.Module):
         cn_kw.pop("out_channels", None)
         self.control_model = ControlNet(**cn_kw)
         self.first_stage_model = FirstStage(dict(SD15_VAE_KW if first_stage_config is None else first_stage_config))
+        # optional text encoder (`cond_stage_model.*` checkpoint keys): cond_stage_config = {} builds the CLIP ViT-L/14
+        # text tower of cldm_v15.yaml; None (default) leaves prompt encoding to the caller
+        self.cond_stage_model = None
+        if cond_stage_config is not None:
+            from ..ldm.modules.encoders.modules import FrozenCLIPEmbedder
+            self.cond_stage_model = FrozenCLIPEmbedder(**dict(cond_stage_config))
         self.control_key = control_key
         self.only_mid_control = only_mid_control
         self.control_scales = [1.0] * 13
@@ -306,6 +312,14 @@ class ControlLDM(nn.Module):
             guided = self.guided_hint(hint)
         eps = self.eps_internal(to_internal(x_noisy), t, ctx, guided)
         return to_external(eps, self.model.diffusion_model.out_channels)
+
+    @torch.no_grad()
+    def get_learned_conditioning(self, c):
+        """Prompt(s) (token ids [B, 77], or strings when the tokenizer files are on disk) -> context [B, 77, 768]
+        (ddpm.py's get_learned_conditioning -> cond_stage_model.encode, canny2image_torch.py:47,52)."""
+        if self.cond_stage_model is None:
+            raise RuntimeError("ControlLDM was built without a text encoder: pass cond_stage_config={}")
+        return self.cond_stage_model.encode(c)
 
     @torch.no_grad()
     def decode_first_stage(self, z):

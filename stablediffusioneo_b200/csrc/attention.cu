@@ -23,6 +23,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
 
 struct AttParams {
   int nq, nkv, d, heads;
+  int causal;     // 1: query i attends keys 0..i only (CLIP text encoder)
   int nkc;        // ceil(d / 64): 64-wide K chunks of the QK^T contraction
   int dk16;       // round_up(d, 16): contraction length actually multiplied
   int dv16;       // round_up(d, 16): N of the PV MMA
@@ -170,7 +171,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
     for (int j = 0; j < n_kv_tiles; ++j) {
       const int kv_cols = min(kTileKV, p.nkv - j * kTileKV);
-      const int ncols = min(64, max(0, kv_cols - half * 64));  // valid columns among this thread's 64
+      int kv_lim = kv_cols;  // valid key columns of this tile for this query row
+      if (p.causal) kv_lim = min(kv_cols, max(0, q_tile * kTileQ + row + 1 - j * kTileKV));
+      const int ncols = min(64, max(0, kv_lim - half * 64));  // valid columns among this thread's 64
       mbar_wait(s_full, (uint32_t)j & 1u);
       tc_fence_after();
       uint32_t r0[32], r1[32];
@@ -275,8 +278,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 using namespace sdeo;
 SDEO_DEFINE_TRACE_SETTER(sdeo_trace_set_attention)
 
+static int attention_impl(const void* q, const void* k, const void* vt, void* o, int32_t batch, int32_t heads, int32_t nq,
+                          int32_t nkv, int32_t d, int32_t ldv, float scale, int causal, void* stream);
+
 extern "C" int sdeo_attention(const void* q, const void* k, const void* vt, void* o, int32_t batch, int32_t heads,
                               int32_t nq, int32_t nkv, int32_t d, int32_t ldv, float scale, void* stream) {
+  return attention_impl(q, k, vt, o, batch, heads, nq, nkv, d, ldv, scale, 0, stream);
+}
+
+extern "C" int sdeo_attention_causal(const void* q, const void* k, const void* vt, void* o, int32_t batch, int32_t heads,
+                                     int32_t n, int32_t d, int32_t ldv, float scale, void* stream) {
+  return attention_impl(q, k, vt, o, batch, heads, n, n, d, ldv, scale, 1, stream);
+}
+
+static int attention_impl(const void* q, const void* k, const void* vt, void* o, int32_t batch, int32_t heads, int32_t nq,
+                          int32_t nkv, int32_t d, int32_t ldv, float scale, int causal, void* stream) {
   if (!q || !k || !vt || !o) return set_error(SDEO_EINVAL, "attention: null argument");
   if (batch <= 0 || heads <= 0 || nq <= 0 || nkv <= 0 || d <= 0 || d % 8 != 0 || d > 192 || ldv < nkv || ldv % 8 != 0)
     return set_error(SDEO_EINVAL, "attention: unsupported geometry (need d % 8 == 0, d <= 192, ldv % 8 == 0)");
@@ -284,6 +300,7 @@ extern "C" int sdeo_attention(const void* q, const void* k, const void* vt, void
   if (BH > 65535) return set_error(SDEO_EINVAL, "attention: batch*heads too large");
   AttParams p;
   p.nq = nq; p.nkv = nkv; p.d = d; p.heads = heads;
+  p.causal = causal;
   p.nkc = (d + 63) / 64;
   p.dk16 = (d + 15) & ~15;
   p.dv16 = p.dk16;

@@ -70,6 +70,9 @@ __device__ __forceinline__ void trace_mark(int i, int slot) {
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
+// CLIP's quick_gelu: x * sigmoid(1.702 x) (transformers activations.py QuickGELUActivation)
+__device__ __forceinline__ float quick_gelu_f(float x) { return x / (1.0f + __expf(-1.702f * x)); }
+
 // exact-erf GELU (F.gelu default in the reference, attention.py:56)
 __device__ __forceinline__ float gelu_erf_f(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));

@@ -274,6 +274,26 @@ __global__ void image_to_u8_kernel(const __nv_bfloat16* __restrict__ x, uint8_t*
   }
 }
 
+// ---- token + position embedding lookup (CLIP text encoder input): y = tok[ids[r]] + pos[r % T], fp32 + bf16 twin ----
+__global__ void embedding_add_kernel(const long long* __restrict__ ids, const float* __restrict__ tok,
+                                     const float* __restrict__ pos, float* __restrict__ y, __nv_bfloat16* __restrict__ y2,
+                                     int rows, int T, int C, int vocab) {
+  const int trc = trace_start(5);
+  griddep_launch_dependents();
+  griddep_wait();
+  trace_mark(trc, 2);
+  trace_mark(trc, 3);
+  const long long total = (long long)rows * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / C), c = (int)(i % C);
+    long long id = ids[r];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    const float v = tok[id * C + c] + pos[(long long)(r % T) * C + c];
+    y[i] = v;
+    if (y2) y2[i] = __float2bfloat16(v);
+  }
+}
+
 static int grid_for(long long work, int threads) {
   long long b = (work + threads - 1) / threads;
   if (b > 148 * 8) b = 148 * 8;
@@ -337,6 +357,13 @@ extern "C" int sdeo_timestep_embedding(const int64_t* t, const int32_t* step_idx
   if (!t || !y || n <= 0 || dim <= 0 || ldy < dim) return set_error(SDEO_EINVAL, "timestep_embedding: bad args");
   const int total = n * ldy;
   return launch_k("timestep_embedding", timestep_embedding_kernel, dim3((total + 127) / 128), dim3(128), 0, (cudaStream_t)stream, dim3(1, 1, 1), (const long long*)t, step_idx, (__nv_bfloat16*)y, n, dim, ldy, max_period);
+}
+
+extern "C" int sdeo_embedding_add(const int64_t* ids, const float* tok, const float* pos, float* y, void* y2, int32_t rows,
+                                  int32_t t, int32_t c, int32_t vocab, void* stream) {
+  if (!ids || !tok || !pos || !y || rows <= 0 || t <= 0 || c <= 0 || vocab <= 0) return set_error(SDEO_EINVAL, "embedding_add: bad args");
+  return launch_k("embedding_add", embedding_add_kernel, dim3(grid_for((long long)rows * c, 256)), dim3(256), 0,
+                  (cudaStream_t)stream, dim3(1, 1, 1), (const long long*)ids, tok, pos, y, (__nv_bfloat16*)y2, rows, t, c, vocab);
 }
 
 extern "C" int sdeo_silu(const void* x, void* y, int64_t count, void* stream) {

@@ -161,6 +161,9 @@ __device__ __forceinline__ void epi_normal_fast(const ConvKParams& p, long long 
   if (p.act == SDEO_ACT_SILU) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
+  } else if (p.act == SDEO_ACT_QUICK_GELU) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = quick_gelu_f(v[j]);
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] *= p.scale;
@@ -221,6 +224,7 @@ __device__ __noinline__ void epi_normal_item(const ConvKParams& p, const RowInfo
   for (int j = 0; j < 8; ++j) {
     float t = v[j];
     if (p.act == SDEO_ACT_SILU) t = silu_f(t);
+    else if (p.act == SDEO_ACT_QUICK_GELU) t = quick_gelu_f(t);
     v[j] = t * p.scale;
   }
   if (res_pref) {  // residual vector was prefetched by the caller (8 columns, aligned)

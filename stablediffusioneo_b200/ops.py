@@ -7,7 +7,7 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib
-from ._lib import ConvArgs, SDEO_ACT_NONE, SDEO_ACT_SILU, SDEO_EPI_GEGLU, SDEO_EPI_NORMAL, SDEO_EPI_QKV
+from ._lib import ConvArgs, SDEO_ACT_NONE, SDEO_ACT_QUICK_GELU, SDEO_ACT_SILU, SDEO_EPI_GEGLU, SDEO_EPI_NORMAL, SDEO_EPI_QKV
 from ._lib import check as _check
 
 BF16 = torch.bfloat16
@@ -310,13 +310,33 @@ def layernorm(x, gamma, beta, eps=1e-5):
     return out
 
 
-def attention(q, k, vt, batch, heads, nq, nkv, d, ldv, scale, out=None):
+def attention(q, k, vt, batch, heads, nq, nkv, d, ldv, scale, out=None, causal=False):
     lib = _lib.load()
     if out is None:
         out = torch.empty((batch, nq, heads * d), dtype=BF16, device=q.device)
+    if causal:
+        assert nq == nkv
+        check(lib.sdeo_attention_causal(_ptr(q), _ptr(k), _ptr(vt), _ptr(out), batch, heads, nq, d, ldv, float(scale),
+                                        _stream()), "attention_causal")
+        return out
     check(lib.sdeo_attention(_ptr(q), _ptr(k), _ptr(vt), _ptr(out), batch, heads, nq, nkv, d, ldv, float(scale),
                              _stream()), "attention")
     return out
+
+
+def embedding_add(ids, tok, pos):
+    """ids int64 [B, T]; tok fp32 [V, C]; pos fp32 [T, C] -> (fp32 [B, T, C], bf16 twin)."""
+    lib = _lib.load()
+    _req(ids, torch.int64, "ids")
+    _req(tok, torch.float32, "tok")
+    _req(pos, torch.float32, "pos")
+    b, t = ids.shape
+    c = tok.shape[1]
+    y = torch.empty((b, t, c), dtype=torch.float32, device=ids.device)
+    y2 = torch.empty((b, t, c), dtype=BF16, device=ids.device)
+    check(lib.sdeo_embedding_add(_ptr(ids), _ptr(tok), _ptr(pos), _ptr(y), _ptr(y2), b * t, t, c, tok.shape[0], _stream()),
+          "embedding_add")
+    return y, y2
 
 
 def softmax_rows(x, scale, out=None):

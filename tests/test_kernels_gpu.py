@@ -404,6 +404,44 @@ def test_attention(cuda_device, case):
     assert err < 8e-3, f"rel L2 {err}"  # P is rounded to bf16 before the PV product
 
 
+@pytest.mark.parametrize("case", [(2, 12, 77, 64), (1, 4, 300, 64), (2, 8, 128, 40)])
+def test_attention_causal(cuda_device, case):
+    """Causal self-attention of the CLIP text encoder (query i sees keys 0..i), also across several K/V tiles."""
+    from stablediffusioneo_b200 import ops
+    b, heads, n, d = case
+    dev = cuda_device
+    q = gen((b * heads, n, d), 1, dev)
+    k = gen((b * heads, n, d), 2, dev)
+    v = gen((b * heads, n, d), 3, dev)
+    ldv = (n + 7) // 8 * 8
+    vt = torch.zeros((b * heads, d, ldv), dtype=torch.bfloat16, device=dev)
+    vt[:, :, :n] = v.transpose(1, 2).to(torch.bfloat16)
+    scale = d ** -0.5
+    o = ops.attention(q.to(torch.bfloat16), k.to(torch.bfloat16), vt, b, heads, n, n, d, ldv, scale, causal=True)
+    sim = torch.einsum("bid,bjd->bij", bf16r(q), bf16r(k)) * scale
+    sim = sim.masked_fill(torch.ones(n, n, dtype=torch.bool, device=dev).triu(1), float("-inf"))
+    ref = torch.einsum("bij,bjd->bid", sim.softmax(-1), bf16r(v))
+    ref = ref.view(b, heads, n, d).permute(0, 2, 1, 3).reshape(b, n, heads * d)
+    assert rel_l2(o, ref) < 8e-3
+
+
+def test_embedding_and_quick_gelu(cuda_device):
+    from stablediffusioneo_b200 import ops
+    dev = cuda_device
+    tok = gen((1000, 768), 1, dev)
+    pos = gen((77, 768), 2, dev)
+    ids = torch.randint(0, 1000, (3, 77), generator=torch.Generator().manual_seed(3)).to(dev)
+    y, y2 = ops.embedding_add(ids, tok, pos)
+    ref = tok[ids] + pos[None]
+    assert torch.equal(y, ref) and rel_l2(y2, ref) < TOL
+    x = gen((77, 768), 4, dev)
+    w = gen((3072, 768), 5, dev) / math.sqrt(768)
+    bias = gen((3072,), 6, dev) * 0.1
+    out = ops.linear(x.to(torch.bfloat16), ops.pack_conv_weight(w), bias=bias, act=ops.SDEO_ACT_QUICK_GELU)
+    z = bf16r(x) @ bf16r(w).t() + bias
+    assert rel_l2(out, z * torch.sigmoid(1.702 * z)) < TOL
+
+
 def test_elementwise(cuda_device):
     from stablediffusioneo_b200 import ops
     dev = cuda_device

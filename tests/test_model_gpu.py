@@ -241,3 +241,40 @@ def test_vae_decode_512_vs_oracle(sd15, cuda_device):
     err = rel_l2(img, ref)
     print("VAE 512x512 decode rel L2 vs oracle:", err)
     assert err < 2e-2
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SURVEY 8f-1 (first "next" row): the CLIP text encoder behind FrozenCLIPEmbedder
+# ---------------------------------------------------------------------------------------------------------------
+def test_clip_text_encoder_vs_transformers(cuda_device):
+    """Our CLIPTextModel against transformers.CLIPTextModel (the implementation the reference's FrozenCLIPEmbedder
+    wraps, ldm/modules/encoders/modules.py:99,123-141) on identical seeded random weights and token ids: ViT-L/14 text
+    tower geometry (12 layers, 768 wide, 12 heads, 77 tokens, causal mask, quick_gelu)."""
+    transformers = pytest.importorskip("transformers")
+    from stablediffusioneo_b200.ldm.modules.encoders.modules import FrozenCLIPEmbedder
+    cfg = transformers.CLIPTextConfig(vocab_size=49408, hidden_size=768, intermediate_size=3072, num_hidden_layers=12,
+                                      num_attention_heads=12, max_position_embeddings=77, hidden_act="quick_gelu",
+                                      layer_norm_eps=1e-5, attention_dropout=0.0)
+    torch.manual_seed(1234)
+    ref_model = transformers.CLIPTextModel(cfg).eval()
+    with torch.no_grad():
+        for n_, p_ in ref_model.named_parameters():  # default init is tiny (std 0.02): widen so that every op matters
+            if p_.dim() > 1 and "embedding" not in n_:
+                p_.mul_(3.0)
+            elif "bias" in n_:
+                p_.add_(0.05 * torch.randn_like(p_))
+    g = torch.Generator().manual_seed(7)
+    ids = torch.randint(0, 49408, (2, 77), generator=g)
+    ids[:, 0] = 49406
+    with torch.no_grad():
+        ref = ref_model(input_ids=ids).last_hidden_state
+    with torch.device(cuda_device):
+        ours = FrozenCLIPEmbedder(device=str(cuda_device))
+    sd = {k: v for k, v in ref_model.state_dict().items() if "position_ids" not in k}
+    missing, unexpected = ours.transformer.load_state_dict(sd, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    out = ours(ids.to(cuda_device))
+    assert out.shape == ref.shape == (2, 77, 768)
+    err = rel_l2(out, ref)
+    print("CLIP text encoder rel L2 vs transformers:", err)
+    assert err < EPS_TOL
