@@ -25,7 +25,6 @@
 namespace sdeo {
 
 constexpr int kConvThreads = 384;  // warp 0 TMA, warp 1 MMA, warps 2..5 TMEM drain; all 12 warps run epilogue phase 2
-constexpr int kEpiThreads = 128;
 constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kATileBytes = kBM * kBK * 2;  // 16 KB
@@ -61,8 +60,6 @@ struct ConvKParams {
   int heads, dhead, tokens, ldv, qkv_first;
   long long* dbg;  // optional per-CTA phase timestamps (SDEO_CONV_DEBUG), 16 slots per CTA
   int res_smem_off;        // > 0: idle warps prefetch the residual tile into shared memory at this byte offset
-  int a_tmem, a_tmem_col;  // stage the A tile in TMEM (tcgen05.cp) at this column offset
-  float* ws;       // (unused: split-K partials travel through distributed shared memory)
   // STATS == 2 (producer of a LayerNorm input): per output row (sum, sum of squares) over this N tile's columns
   float2* row_stats;      // [n_tile][row_stats_ld]
   int row_stats_ld;
@@ -88,16 +85,10 @@ struct RowInfo {
 };
 
 // ---- cluster / distributed shared memory ----
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 __device__ __forceinline__ uint32_t dsmem_addr(uint32_t local_smem_addr, uint32_t cta_rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
   return r;
-}
-__device__ __forceinline__ void st_dsmem_f4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void cluster_arrive() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -115,11 +106,6 @@ __device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_cluster_addr, uint3
 }
 __device__ __forceinline__ void st_smem_f4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
 }
 
 __device__ __forceinline__ void load8_f32(const float* p, float* f) {
@@ -535,21 +521,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         if (elect_one()) {
-          if (p.a_tmem) {
-            // optional: stage the A tile in TMEM (tcgen05.cp, in issue order with the MMAs), A operand from TMEM
-            const uint32_t a_tm = tmem_base + (uint32_t)p.a_tmem_col + (uint32_t)((i & 1) * 32);
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) tc_cp_128x256b(a_tm + (uint32_t)(8 * k), a_desc + (uint64_t)(2 * k));
-#pragma unroll
-            for (int k = 0; k < kBK / 16; ++k)
-              tc_mma_bf16_ts(tmem_base, a_tm + (uint32_t)(8 * k), b_desc + (uint64_t)(2 * k), idesc, (i > 0 || k > 0) ? 1u : 0u);
-          } else {
-#pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) {
-              // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-              tc_mma_bf16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                          (i > 0 || k > 0) ? 1u : 0u);
-            }
+          for (int k = 0; k < kBK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+            tc_mma_bf16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                        (i > 0 || k > 0) ? 1u : 0u);
           }
           tc_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
         }
@@ -1123,7 +1099,7 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl, int force_bn = 0, i
   if (res_bytes) pl->res_smem_off = 2048 + (int)body;
   pl->smem_bytes = kFixed + body + res_bytes;
   int tc = 32;
-  while (tc < pl->BN + 64) tc *= 2;  // accumulator + 2 x 32 columns of A staging
+  while (tc < pl->BN) tc *= 2;  // fp32 accumulator columns (power of two >= 32)
   pl->tmem_cols = tc;
   return pl->smem_bytes <= (size_t)kSmemMax;
 }
@@ -1391,9 +1367,6 @@ static int launch_conv(const sdeo_conv_args* a, const ConvPlan& pl, void* stream
   p.dbg = nullptr;
   if (const char* e = getenv("SDEO_CONV_DEBUG")) p.dbg = (long long*)strtoull(e, nullptr, 16);
   p.res_smem_off = pl.res_smem_off;
-  p.a_tmem = getenv("SDEO_A_TMEM") ? 1 : 0;  // measured: no gain over A from shared memory; kept as an option
-  p.a_tmem_col = pl.tmem_cols - 64;
-  p.ws = nullptr;  // (split-K partials travel through distributed shared memory; the workspace argument is unused)
   p.gn_stats = nullptr;
   p.row_stats = nullptr; p.row_stats_ld = 0;
   p.ln_stats = (const float2*)a->ln_stats; p.ln_parts = a->ln_parts; p.ln_ld = a->ln_ld;
