@@ -100,6 +100,44 @@ def test_tiny_sampler_generic_path(tiny, cuda_device):
     assert rel_l2(samples, g["samples"]) < 3e-2
 
 
+def test_tiny_control_modes_vs_oracle(tiny, cuda_device):
+    """canny2image_torch.py:48-58 knobs: graded control_scales (guess-mode strengths 0.825^(12-i)), only_mid_control,
+    and guess mode (the unconditional branch runs WITHOUT the ControlNet) -- apply_model and the sampler against the
+    oracle with the same settings."""
+    from helpers import oracle_weights
+    from stablediffusioneo_b200.cldm.ddim_hacked import DDIMSampler
+    model, g = tiny
+    sd_unet, sd_cn, _ = oracle_weights(O.TINY, O.TINY_VAE)
+    dev = cuda_device
+    x_T, cond, uncond = inputs_on(O.TINY, 8, 16, dev)
+    x_c, cond_c, uncond_c = O.make_inputs(O.TINY, 1, 8, 16)
+    scales = [0.9 * (0.825 ** float(12 - i)) for i in range(13)]
+    ts = _ts(dev)
+    try:
+        for only_mid in (False, True):
+            model.control_scales, model.only_mid_control = scales, only_mid
+            eps = model.apply_model(x_T, ts, cond)
+            with torch.no_grad():
+                ref = O.apply_model(sd_unet, sd_cn, O.TINY, x_c, ts.cpu(), cond_c, control_scales=scales,
+                                    only_mid_control=only_mid)
+            assert rel_l2(eps, ref) < EPS_TOL, only_mid
+        # guess mode through the sampler: uncond has no hint (generic path: the two branches have different graphs),
+        # and the engine path with graded scales
+        model.only_mid_control = False
+        eps_fn = lambda x, t, c: O.apply_model(sd_unet, sd_cn, O.TINY, x, t, c, control_scales=scales)
+        for guess in (True, False):
+            un_d = dict(uncond, c_concat=None) if guess else uncond
+            un_c = dict(uncond_c, c_concat=None) if guess else uncond_c
+            sampler = DDIMSampler(model)
+            samples, _ = sampler.sample(4, 1, (4, 8, 16), cond, verbose=False, eta=0.0, x_T=x_T,
+                                        unconditional_guidance_scale=9.0, unconditional_conditioning=un_d)
+            with torch.no_grad():
+                ref_s, _ = O.ddim_sample(eps_fn, x_c, cond_c, un_c, S=4, scale=9.0)
+            assert rel_l2(samples, ref_s) < 3e-2, guess
+    finally:
+        model.control_scales, model.only_mid_control = [1.0] * 13, False
+
+
 def test_tiny_decode(tiny, cuda_device):
     model, g = tiny
     img = model.decode_first_stage(g["decode_in"].to(cuda_device))
