@@ -231,6 +231,35 @@ int sdeo_bf16_to_f32(const void* x, float* y, int64_t count, void* stream);
 int sdeo_image_to_u8(const void* x, uint8_t* y, int32_t npix, int32_t c, int32_t ldx, void* stream);
 int sdeo_memset_async(void* p, int value, size_t bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * fp32 ("precise") mode: the 1e-4 parity configuration of the path (reference = PyTorch fp32 throughout,
+ * ldm/modules/attention.py, openaimodel.py, cldm/cldm.py). Contractions still run on sdeo_conv2d: fp32 operands are
+ * split into bf16 terms concatenated along K (x.w ~= hi.hi + mid.hi + hi.mid), everything else stays fp32.
+ * ---------------------------------------------------------------------------------------------- */
+/* x fp32 [rows, ldx] (or NCHW with nchw_hw = H*W > 0: rows = N*H*W) -> y bf16 [rows, terms*cp]; block t of a row holds
+ * level ((pattern >> 2t) & 3) of every channel (0 = bf16(v), 1 = bf16 of what level 0 left, 2 = of what 0+1 left);
+ * channels c..cp-1 (cp multiple of 8) are zero. */
+int sdeo_split_terms(const float* x, void* y, int64_t rows, int32_t c, int32_t cp, int64_t ldx, int32_t nchw_hw,
+                     int32_t terms, uint32_t pattern, void* stream);
+/* Filter side: w fp32 [cout, src_cin, kk], channels cin0..cin0+cin-1 -> fp32 [cout, terms*cp, kk] of exactly
+ * bf16-representable values (feed it to sdeo_pack_conv_weight with c = terms*cp). */
+int sdeo_split_terms_weight(const float* w, float* y, int32_t cout, int32_t src_cin, int32_t cin0, int32_t cin, int32_t cp,
+                            int32_t kk, int32_t terms, uint32_t pattern, void* stream);
+/* GroupNorm(+SiLU) on fp32 NHWC (optionally the concat of x1, x2) -> fp32; statistics accumulated in double. */
+int sdeo_groupnorm_f32(const float* x1, const float* x2, const float* gamma, const float* beta, float* y, int32_t n,
+                       int32_t hw, int32_t c1, int32_t c2, int32_t groups, float eps, int32_t with_silu, void* stream);
+int sdeo_layernorm_f32(const float* x, const float* gamma, const float* beta, float* y, int32_t rows, int32_t c, float eps,
+                       void* stream);
+/* o = softmax(q k^T * scale) v in fp32 on CUDA cores. q [B, nq, ldq], k [B, nkv, ldk], v [B, nkv, ldv], o [B, nq, ldo];
+ * head h occupies columns h*d .. h*d+d-1 of each; d <= 160. */
+int sdeo_attention_f32(const float* q, const float* k, const float* v, float* o, int32_t batch, int32_t heads, int32_t nq,
+                       int32_t nkv, int32_t d, int32_t ldq, int32_t ldk, int32_t ldv, int32_t ldo, float scale, void* stream);
+/* y[r, j] = x[r, j] * gelu_erf(x[r, inner + j]) for x fp32 [rows, 2*inner] (attention.py:49-56). */
+int sdeo_geglu_f32(const float* x, float* y, int64_t rows, int32_t inner, void* stream);
+int sdeo_silu_f32(const float* x, float* y, int64_t count, void* stream);
+/* fp32 [n, dim] sinusoidal embedding [cos | sin] of int64 timesteps (util.py:154-174). */
+int sdeo_timestep_embedding_f32(const int64_t* t, float* y, int32_t n, int32_t dim, float max_period, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

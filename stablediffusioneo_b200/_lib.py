@@ -79,6 +79,18 @@ SIGNATURES = {
     "sdeo_bf16_to_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "sdeo_image_to_u8": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "sdeo_memset_async": (c_int, [c_void_p, c_int, c_size_t, c_void_p]),
+    "sdeo_split_terms": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int64, c_int32, c_int32, ctypes.c_uint32,
+                                 c_void_p]),
+    "sdeo_split_terms_weight": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                        ctypes.c_uint32, c_void_p]),
+    "sdeo_groupnorm_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                   c_int32, c_float, c_int32, c_void_p]),
+    "sdeo_layernorm_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p]),
+    "sdeo_attention_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                   c_int32, c_int32, c_int32, c_int32, c_float, c_void_p]),
+    "sdeo_geglu_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
+    "sdeo_silu_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "sdeo_timestep_embedding_f32": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p]),
 }
 
 _lib = None

@@ -259,6 +259,9 @@ class ControlLDM(nn.Module):
         self.control_key = control_key
         self.only_mid_control = only_mid_control
         self.control_scales = [1.0] * 13
+        # "bf16" (default: bf16 GEMM operands, fp32 accumulation / residual stream; 1e-2 gate) or "fp32" (split-operand
+        # GEMMs + fp32 everything else, stablediffusioneo_b200/precise.py; 1e-4 gate, verification speed)
+        self.precision = "bf16"
         self.parameterization = parameterization
         self.scale_factor = scale_factor
         self.channels = unet_kw["in_channels"]
@@ -303,6 +306,11 @@ class ControlLDM(nn.Module):
     def apply_model(self, x_noisy, t, cond, *args, **kwargs):
         """cldm/cldm.py:328-341: eps = UNet(x, t, ctx, control = scales * ControlNet(x, hint, t, ctx))."""
         assert isinstance(cond, dict)
+        if self.precision == "fp32":
+            from .. import precise
+            return precise.eps(self, x_noisy, t, cond)
+        if self.precision != "bf16":
+            raise ValueError(f"ControlLDM.precision must be 'bf16' or 'fp32', got {self.precision!r}")
         cond_txt = cond["c_crossattn"]
         cond_txt = cond_txt[0] if len(cond_txt) == 1 else torch.cat(cond_txt, 1)
         ctx = _ctx_internal(cond_txt)

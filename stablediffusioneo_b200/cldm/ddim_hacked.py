@@ -103,7 +103,7 @@ class DDIMSampler(object):
     def _engine_ok(self, cond, uncond, scale, mask, callback, img_callback, quantize_denoised, score_corrector,
                    dynamic_threshold, ucg_schedule, ddim_use_original_steps, timesteps, noise_dropout, temperature):
         from .cldm import ControlLDM
-        if not (self.use_engine and isinstance(self.model, ControlLDM)):
+        if not (self.use_engine and isinstance(self.model, ControlLDM)) or self.model.precision != "bf16":
             return False
         if any(v is not None for v in (mask, callback, img_callback, score_corrector, dynamic_threshold, ucg_schedule,
                                        timesteps)) or quantize_denoised or ddim_use_original_steps:

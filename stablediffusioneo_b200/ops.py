@@ -487,3 +487,129 @@ def image_to_u8(x, c=3):
     out = torch.empty((n, h, w, c), dtype=torch.uint8, device=x.device)
     check(lib.sdeo_image_to_u8(_ptr(x), _ptr(out), n * h * w, c, ld, _stream()), "image_to_u8")
     return out
+
+
+# ---- fp32 ("precise") mode: split-term operands for the bf16 GEMM + plain fp32 passes (csrc/precise.cu) -------------
+# term patterns, 2 bits per K block (0 = hi, 1 = mid, 2 = lo): activation side / weight side. The GEMM over the
+# concatenated blocks sums a_level * w_level per block.
+SPLIT_PATTERNS = {
+    3: ((0, 1, 0), (0, 0, 1)),                       # hi.hi + mid.hi + hi.mid
+    6: ((0, 1, 0, 1, 2, 0), (0, 0, 1, 1, 0, 2)),     # + mid.mid + lo.hi + hi.lo
+}
+
+
+def _pattern_bits(levels):
+    bits = 0
+    for i, lv in enumerate(levels):
+        bits |= (lv & 3) << (2 * i)
+    return bits
+
+
+def split_terms(x, terms=3, nchw=False):
+    """fp32 [..., C] (or NCHW [N, C, H, W] when nchw) -> bf16 [..., terms * Cp] activation-side split (Cp = C rounded up
+    to 8; for nchw the result is NHWC [N, H, W, terms * Cp])."""
+    lib = _lib.load()
+    _req(x, torch.float32, "x")
+    pat = _pattern_bits(SPLIT_PATTERNS[terms][0])
+    if nchw:
+        n, c, h, w = x.shape
+        cp = (c + 7) // 8 * 8
+        out = torch.empty((n, h, w, terms * cp), dtype=BF16, device=x.device)
+        check(lib.sdeo_split_terms(_ptr(x), _ptr(out), n * h * w, c, cp, 0, h * w, terms, pat, _stream()), "split_terms")
+        return out
+    c = x.shape[-1]
+    cp = (c + 7) // 8 * 8
+    rows = x.numel() // c
+    out = torch.empty(tuple(x.shape[:-1]) + (terms * cp,), dtype=BF16, device=x.device)
+    check(lib.sdeo_split_terms(_ptr(x), _ptr(out), rows, c, cp, c, 0, terms, pat, _stream()), "split_terms")
+    return out
+
+
+def pack_conv_weight_split(weight, terms=3, c1=None, c2=0):
+    """fp32 filter [cout, cin, k, k] / [cout, cin] -> PackedWeight over the weight-side split channels
+    [terms * Cp1 (+ terms * Cp2)] matching split_terms() of the input(s)."""
+    lib = _lib.load()
+    if weight.dim() == 2:
+        weight = weight[:, :, None, None]
+    weight = weight.detach().to(torch.float32).contiguous()
+    _req(weight, torch.float32, "weight")
+    cout, cin, k, _ = weight.shape
+    if c1 is None:
+        c1 = cin
+    assert c1 + c2 == cin
+    pat = _pattern_bits(SPLIT_PATTERNS[terms][1])
+    parts, widths = [], []
+    for c0, cc in ((0, c1), (c1, c2)):
+        if cc == 0:
+            continue
+        cp = (cc + 7) // 8 * 8
+        buf = torch.empty((cout, terms * cp, k, k), dtype=torch.float32, device=weight.device)
+        check(lib.sdeo_split_terms_weight(_ptr(weight), _ptr(buf), cout, cin, c0, cc, cp, k * k, terms, pat, _stream()),
+              "split_terms_weight")
+        parts.append(buf)
+        widths.append(terms * cp)
+    w3 = parts[0] if len(parts) == 1 else torch.cat(parts, 1)
+    return pack_conv_weight(w3, c1=widths[0], c2=widths[1] if len(widths) > 1 else 0)
+
+
+def groupnorm_f32(x, gamma, beta, eps, silu, x2=None, groups=32):
+    """fp32 NHWC [N,H,W,C1] (+ x2) -> fp32 [N,H,W,C1+C2]."""
+    lib = _lib.load()
+    _req(x, torch.float32, "x")
+    _req(x2, torch.float32, "x2")
+    n, h, w, c1 = x.shape
+    c2 = x2.shape[3] if x2 is not None else 0
+    out = torch.empty((n, h, w, c1 + c2), dtype=torch.float32, device=x.device)
+    check(lib.sdeo_groupnorm_f32(_ptr(x), _ptr(x2), _ptr(gamma), _ptr(beta), _ptr(out), n, h * w, c1, c2, groups, float(eps),
+                                 1 if silu else 0, _stream()), "groupnorm_f32")
+    return out
+
+
+def layernorm_f32(x, gamma, beta, eps=1e-5):
+    lib = _lib.load()
+    _req(x, torch.float32, "x")
+    c = x.shape[-1]
+    out = torch.empty_like(x)
+    check(lib.sdeo_layernorm_f32(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), x.numel() // c, c, float(eps), _stream()),
+          "layernorm_f32")
+    return out
+
+
+def attention_f32(q, k, v, heads, scale):
+    """q [B, Nq, heads*d], k / v [B, Nkv, heads*d] fp32 -> [B, Nq, heads*d] fp32."""
+    lib = _lib.load()
+    for t, name in ((q, "q"), (k, "k"), (v, "v")):
+        _req(t, torch.float32, name)
+    b, nq, c = q.shape
+    nkv = k.shape[1]
+    d = c // heads
+    out = torch.empty_like(q)
+    check(lib.sdeo_attention_f32(_ptr(q), _ptr(k), _ptr(v), _ptr(out), b, heads, nq, nkv, d, c, c, c, c, float(scale),
+                                 _stream()), "attention_f32")
+    return out
+
+
+def geglu_f32(x):
+    lib = _lib.load()
+    _req(x, torch.float32, "x")
+    inner = x.shape[-1] // 2
+    out = torch.empty(tuple(x.shape[:-1]) + (inner,), dtype=torch.float32, device=x.device)
+    check(lib.sdeo_geglu_f32(_ptr(x), _ptr(out), x.numel() // (2 * inner), inner, _stream()), "geglu_f32")
+    return out
+
+
+def silu_f32(x):
+    lib = _lib.load()
+    _req(x, torch.float32, "x")
+    out = torch.empty_like(x)
+    check(lib.sdeo_silu_f32(_ptr(x), _ptr(out), x.numel(), _stream()), "silu_f32")
+    return out
+
+
+def timestep_embedding_f32(t, dim, max_period=10000.0):
+    lib = _lib.load()
+    _req(t, torch.int64, "t")
+    out = torch.empty((t.shape[0], dim), dtype=torch.float32, device=t.device)
+    check(lib.sdeo_timestep_embedding_f32(_ptr(t), _ptr(out), t.shape[0], dim, float(max_period), _stream()),
+          "timestep_embedding_f32")
+    return out
