@@ -111,6 +111,9 @@ typedef struct sdeo_conv_args {
   int32_t ln_parts, ln_ld, ln_c;
   float ln_eps;
   const float* ln_csum;
+  /* extra zero rows / columns AFTER the last input row / column (0, or 1 with ksize 3, stride 2, pad 0): the VAE
+   * encoder's Downsample, F.pad(x, (0,1,0,1)) + conv(stride 2, padding 0) (ldm/modules/diffusionmodules/model.py:80-84) */
+  int32_t pad_hi;
 } sdeo_conv_args;
 
 /* Bytes of workspace the planner may use for these args (fp32 partial tiles + tile counters).
@@ -230,6 +233,15 @@ int sdeo_bf16_to_f32(const void* x, float* y, int64_t count, void* stream);
 /* VAE output: uint8 NHWC image = clip(x*127.5+127.5, 0, 255) from bf16 NHWC (canny2image_torch.py:68) */
 int sdeo_image_to_u8(const void* x, uint8_t* y, int32_t npix, int32_t c, int32_t ldx, void* stream);
 int sdeo_memset_async(void* p, int value, size_t bytes, void* stream);
+/* y[i] = a[i / per_sample] * x[i] + b[i / per_sample] * z[i] (fp32; a, b device arrays, one entry per sample): the DDIM
+ * encode step x_next = sqrt(a_next/a) x + sqrt(a_next) (sqrt(1/a_next - 1) - sqrt(1/a - 1)) eps (cldm/ddim_hacked.py:262-265),
+ * stochastic_encode / q_sample sqrt(abar_t) x0 + sqrt(1 - abar_t) noise (:278-292), a CFG combine outside the fused step. */
+int sdeo_axpby_f32(const float* x, const float* z, const float* a, const float* b, float* y, int64_t count,
+                   int64_t per_sample, void* stream);
+/* Inpainting blend of ddim_sampling (cldm/ddim_hacked.py:154-157): y = mask * (a x0 + b noise) + (1 - mask) * img with the
+ * parenthesis = q_sample(x0, t). img / x0 / noise / y fp32 [n, c, hw]; mask fp32 [n, mask_c, hw], mask_c = 1 or c. */
+int sdeo_mask_blend_f32(const float* x0, const float* noise, const float* img, const float* mask, const float* a,
+                        const float* b, float* y, int32_t n, int32_t c, int32_t mask_c, int64_t hw, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * fp32 ("precise") mode: the 1e-4 parity configuration of the path (reference = PyTorch fp32 throughout,

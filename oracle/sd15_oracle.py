@@ -512,17 +512,26 @@ def ddim_update(x, e_t, a_t, a_prev, sigma_t, sqrt_one_minus_at, noise=None):
     return x_prev, pred_x0
 
 
-def ddim_sample(eps_fn, x_T, cond, uncond, S=20, scale=9.0, eta=0.0, collect=False):
-    """DDIMSampler.sample / ddim_sampling / p_sample_ddim (ddim_hacked.py:55-231) with eta == 0.
-    eps_fn(x, t, cond) plays model.apply_model; cond first, then uncond (ddim_hacked.py:190-191)."""
-    assert eta == 0.0, "oracle restates the deterministic (eta=0) path used by canny2image_torch.py"
+def ddim_sample(eps_fn, x_T, cond, uncond, S=20, scale=9.0, eta=0.0, collect=False, noises=None, mask=None, x0=None,
+                q_noises=None):
+    """DDIMSampler.sample / ddim_sampling / p_sample_ddim (ddim_hacked.py:55-231).
+    eps_fn(x, t, cond) plays model.apply_model; cond first, then uncond (ddim_hacked.py:190-191).
+    eta > 0: noises[i] is the N(0,1) draw of step i (noise_like, ddim_hacked.py:227). mask / x0: the inpainting blend
+    img = q_sample(x0, ts) * mask + (1 - mask) * img before every step (ddim_hacked.py:154-157) with q_sample(x0, t) =
+    sqrt(abar_t) x0 + sqrt(1 - abar_t) q_noises[i] (LatentDiffusion.q_sample, ddpm.py -- absent from the reference
+    checkout; the standard definition)."""
+    assert eta == 0.0 or noises is not None, "eta > 0 needs the per-step noise draws"
     sch = ddim_schedule(S, eta)
+    ac = alphas_cumprod().astype(np.float32)
     img = x_T
     b = x_T.shape[0]
     trace = []
     for i, step in enumerate(np.flip(sch["timesteps"])):
         index = S - i - 1
         ts = torch.full((b,), int(step), dtype=torch.long)
+        if mask is not None:
+            img_orig = math.sqrt(float(ac[int(step)])) * x0 + math.sqrt(1.0 - float(ac[int(step)])) * q_noises[i]
+            img = img_orig * mask + (1.0 - mask) * img
         if uncond is None or scale == 1.0:
             e_t = eps_fn(img, ts, cond)
         else:
@@ -531,10 +540,55 @@ def ddim_sample(eps_fn, x_T, cond, uncond, S=20, scale=9.0, eta=0.0, collect=Fal
             e_t = e_u + scale * (e_c - e_u)
         x_in = img
         img, pred_x0 = ddim_update(img, e_t, float(sch["alphas"][index]), float(sch["alphas_prev"][index]),
-                                   float(sch["sigmas"][index]), float(sch["sqrt_one_minus_alphas"][index]))
+                                   float(sch["sigmas"][index]), float(sch["sqrt_one_minus_alphas"][index]),
+                                   noise=noises[i] if eta != 0.0 else None)
         if collect:
             trace.append(dict(t=int(step), x_in=x_in, eps=e_t, x_prev=img))
     return img, trace
+
+
+def ddim_encode(eps_fn, x0, cond, t_enc, S=20, scale=1.0, uncond=None):
+    """DDIMSampler.encode (ddim_hacked.py:233-276), use_original_steps=False: deterministic DDIM inversion over the first
+    t_enc DDIM timesteps. The reference's CFG branch concatenates conditionings with torch.cat, which only works for tensor
+    conditionings; for the ControlNet dict conditioning the two branches are evaluated separately (same arithmetic)."""
+    sch = ddim_schedule(S)
+    alphas_next, alphas = sch["alphas"][:t_enc], sch["alphas_prev"][:t_enc]
+    x_next = x0
+    for i in range(t_enc):
+        t = torch.full((x0.shape[0],), int(sch["timesteps"][i]), dtype=torch.long)
+        if scale == 1.0:
+            noise_pred = eps_fn(x_next, t, cond)
+        else:
+            e_u, e_c = eps_fn(x_next, t, uncond), eps_fn(x_next, t, cond)
+            noise_pred = e_u + scale * (e_c - e_u)
+        an, a = float(alphas_next[i]), float(alphas[i])
+        x_next = math.sqrt(an / a) * x_next + math.sqrt(an) * (math.sqrt(1 / an - 1) - math.sqrt(1 / a - 1)) * noise_pred
+    return x_next
+
+
+def stochastic_encode(x0, t_index, S=20, noise=None):
+    """DDIMSampler.stochastic_encode (ddim_hacked.py:278-292), use_original_steps=False: t_index [B] int64 indexes the
+    DDIM tables."""
+    sch = ddim_schedule(S)
+    a = torch.tensor(sch["alphas"], dtype=torch.float32)[t_index].reshape(-1, 1, 1, 1)
+    return a.sqrt() * x0 + (1.0 - a).sqrt() * noise
+
+
+def ddim_decode(eps_fn, x_latent, cond, t_start, S=20, scale=1.0, uncond=None):
+    """DDIMSampler.decode (ddim_hacked.py:294-317): p_sample_ddim over the first t_start DDIM timesteps, reversed."""
+    sch = ddim_schedule(S)
+    x = x_latent
+    for i, step in enumerate(np.flip(sch["timesteps"][:t_start])):
+        index = t_start - i - 1
+        ts = torch.full((x.shape[0],), int(step), dtype=torch.long)
+        if uncond is None or scale == 1.0:
+            e_t = eps_fn(x, ts, cond)
+        else:
+            e_c, e_u = eps_fn(x, ts, cond), eps_fn(x, ts, uncond)
+            e_t = e_u + scale * (e_c - e_u)
+        x, _ = ddim_update(x, e_t, float(sch["alphas"][index]), float(sch["alphas_prev"][index]), 0.0,
+                           float(sch["sqrt_one_minus_alphas"][index]))
+    return x
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -582,6 +636,53 @@ def vae_decode(sd, cfg: VAEConfig, z):
             h = _conv(sd, f"{p}up.{i_level}.upsample.conv.", h)
     h = F.silu(_gn(sd, p + "norm_out.", h, 1e-6))
     return _conv(sd, p + "conv_out.", h)
+
+
+def vae_encoder_param_spec(cfg: VAEConfig):
+    """Encoder.__init__ (model.py:452-512) + AutoencoderKL.quant_conv (autoencoder.py, absent: Conv2d(2 z, 2 embed, 1))."""
+    nres = len(cfg.ch_mult)
+    z = cfg.z_channels
+    in_mult = (1,) + tuple(cfg.ch_mult)
+    s = [("quant_conv.weight", (2 * z, 2 * z, 1, 1), "w"), ("quant_conv.bias", (2 * z,), "b"),
+         ("encoder.conv_in.weight", (cfg.ch, 3, 3, 3), "w"), ("encoder.conv_in.bias", (cfg.ch,), "b")]
+    block_in = cfg.ch
+    for i_level in range(nres):
+        block_in = cfg.ch * in_mult[i_level]
+        block_out = cfg.ch * cfg.ch_mult[i_level]
+        for j in range(cfg.num_res_blocks):
+            s += _spec_vae_res(f"encoder.down.{i_level}.block.{j}.", block_in, block_out)
+            block_in = block_out
+        if i_level != nres - 1:
+            s += [(f"encoder.down.{i_level}.downsample.conv.weight", (block_in, block_in, 3, 3), "w"),
+                  (f"encoder.down.{i_level}.downsample.conv.bias", (block_in,), "b")]
+    s += _spec_vae_res("encoder.mid.block_1.", block_in, block_in)
+    a = "encoder.mid.attn_1."
+    s += [(a + "norm.weight", (block_in,), "norm_w"), (a + "norm.bias", (block_in,), "norm_b")]
+    for n in ("q", "k", "v", "proj_out"):
+        s += [(a + n + ".weight", (block_in, block_in, 1, 1), "w"), (a + n + ".bias", (block_in,), "b")]
+    s += _spec_vae_res("encoder.mid.block_2.", block_in, block_in)
+    s += [("encoder.norm_out.weight", (block_in,), "norm_w"), ("encoder.norm_out.bias", (block_in,), "norm_b"),
+          ("encoder.conv_out.weight", (2 * z, block_in, 3, 3), "w"), ("encoder.conv_out.bias", (2 * z,), "b")]
+    return s
+
+
+def vae_encode(sd, cfg: VAEConfig, x):
+    """Encoder.forward (model.py:514-543) -> quant_conv: the moments [B, 2 z, h/8, w/8] = (mean | logvar) of the
+    DiagonalGaussianDistribution (ldm/modules/distributions/distributions.py:24-35). Downsample = F.pad(x, (0,1,0,1)) +
+    conv3x3 stride 2 without padding (model.py:78-84). The latent is scale_factor * mean (mode) or a sample."""
+    p = "encoder."
+    h = _conv(sd, p + "conv_in.", x)
+    nres = len(cfg.ch_mult)
+    for i_level in range(nres):
+        for j in range(cfg.num_res_blocks):
+            h = vae_resblock(sd, f"{p}down.{i_level}.block.{j}.", h)
+        if i_level != nres - 1:
+            h = _conv(sd, f"{p}down.{i_level}.downsample.conv.", F.pad(h, (0, 1, 0, 1)), stride=2, padding=0)
+    h = vae_resblock(sd, p + "mid.block_1.", h)
+    h = vae_attn(sd, p + "mid.attn_1.", h)
+    h = vae_resblock(sd, p + "mid.block_2.", h)
+    h = _conv(sd, p + "conv_out.", F.silu(_gn(sd, p + "norm_out.", h, 1e-6)))
+    return _conv(sd, "quant_conv.", h, padding=0)
 
 
 def to_uint8_image(x):

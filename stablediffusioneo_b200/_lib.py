@@ -30,6 +30,7 @@ class ConvArgs(Structure):
         ("row_stats", c_void_p), ("row_stats_ld", c_int32),
         ("ln_stats", c_void_p), ("ln_parts", c_int32), ("ln_ld", c_int32), ("ln_c", c_int32), ("ln_eps", ctypes.c_float),
         ("ln_csum", c_void_p),
+        ("pad_hi", c_int32),
     ]
 
 
@@ -79,6 +80,9 @@ SIGNATURES = {
     "sdeo_bf16_to_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "sdeo_image_to_u8": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "sdeo_memset_async": (c_int, [c_void_p, c_int, c_size_t, c_void_p]),
+    "sdeo_axpby_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    "sdeo_mask_blend_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+                                    c_int32, c_int64, c_void_p]),
     "sdeo_split_terms": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int64, c_int32, c_int32, ctypes.c_uint32,
                                  c_void_p]),
     "sdeo_split_terms_weight": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,

@@ -19,7 +19,7 @@ from ..ldm.modules.diffusionmodules import util
 from ..ldm.modules.diffusionmodules.util import (BF16, CatPair, SiLU, conv_nd, is_internal, linear, make_beta_schedule,
                                                  nchw_view, nhwc, operand, timestep_embedding, to_external, to_internal,
                                                  zero_module)
-from ..ldm.modules.diffusionmodules.model import Decoder
+from ..ldm.modules.diffusionmodules.model import Decoder, Encoder
 
 
 def _ctx_internal(context):
@@ -216,15 +216,28 @@ class DiffusionWrapper(nn.Module):
 
 
 class FirstStage(nn.Module):
-    """AutoencoderKL's decode half: `first_stage_model.post_quant_conv.*`, `first_stage_model.decoder.*`."""
+    """AutoencoderKL (ldm/models/autoencoder.py, absent from the reference checkout): the decode half
+    `first_stage_model.post_quant_conv.*`, `first_stage_model.decoder.*` always; with_encoder adds
+    `first_stage_model.encoder.*` and `first_stage_model.quant_conv.*` (img2img / inpainting callers)."""
 
-    def __init__(self, ddconfig, embed_dim=4):
+    def __init__(self, ddconfig, embed_dim=4, with_encoder=False):
         super().__init__()
+        if with_encoder:
+            self.encoder = Encoder(**ddconfig)
+            self.quant_conv = conv_nd(2, 2 * ddconfig["z_channels"], 2 * embed_dim, 1)
         self.decoder = Decoder(**ddconfig)
         self.post_quant_conv = conv_nd(2, embed_dim, ddconfig["z_channels"], 1)
 
     def decode(self, z):
         return self.decoder(self.post_quant_conv(z))
+
+    def encode_moments(self, x):
+        """image fp32 NCHW in [-1, 1] -> moments fp32 [B, 2 embed, h/8, w/8] = (mean | logvar), i.e. the parameters of
+        AutoencoderKL.encode's DiagonalGaussianDistribution (ldm/modules/distributions/distributions.py:24-35)."""
+        if not hasattr(self, "encoder"):
+            raise RuntimeError("FirstStage was built without the encoder: ControlLDM(first_stage_encoder=True)")
+        m = self.quant_conv.run(self.encoder.run(to_internal(x)), out_fp32=True)
+        return to_external(m, self.quant_conv.out_channels)
 
 
 SD15_UNET_KW = dict(image_size=32, in_channels=4, model_channels=320, num_res_blocks=2, attention_resolutions=[4, 2, 1],
@@ -242,14 +255,15 @@ class ControlLDM(nn.Module):
 
     def __init__(self, unet_config=None, control_stage_config=None, first_stage_config=None, control_key="hint",
                  only_mid_control=False, timesteps=1000, linear_start=0.00085, linear_end=0.012, scale_factor=0.18215,
-                 parameterization="eps", cond_stage_config=None):
+                 parameterization="eps", cond_stage_config=None, first_stage_encoder=False):
         super().__init__()
         unet_kw = dict(SD15_UNET_KW if unet_config is None else unet_config)
         cn_kw = dict(control_stage_config) if control_stage_config is not None else dict(unet_kw, hint_channels=3)
         self.model = DiffusionWrapper(ControlledUnetModel(out_channels=unet_kw.pop("out_channels", 4), **unet_kw))
         cn_kw.pop("out_channels", None)
         self.control_model = ControlNet(**cn_kw)
-        self.first_stage_model = FirstStage(dict(SD15_VAE_KW if first_stage_config is None else first_stage_config))
+        self.first_stage_model = FirstStage(dict(SD15_VAE_KW if first_stage_config is None else first_stage_config),
+                                            with_encoder=first_stage_encoder)
         # optional text encoder (`cond_stage_model.*` checkpoint keys): cond_stage_config = {} builds the CLIP ViT-L/14
         # text tower of cldm_v15.yaml; None (default) leaves prompt encoding to the caller
         self.cond_stage_model = None
@@ -272,6 +286,7 @@ class ControlLDM(nn.Module):
         self.register_buffer("betas", f32(betas), persistent=False)
         self.register_buffer("alphas_cumprod", f32(alphas_cumprod), persistent=False)
         self.register_buffer("alphas_cumprod_prev", f32(np.append(1.0, alphas_cumprod[:-1])), persistent=False)
+        self.register_buffer("sqrt_alphas_cumprod", f32(np.sqrt(alphas_cumprod)), persistent=False)
         self.register_buffer("sqrt_one_minus_alphas_cumprod", f32(np.sqrt(1.0 - alphas_cumprod)), persistent=False)
         self._hint_cache = None
         # first eager call of each layer shape picks its tile / split-K configuration (SDEO_NO_AUTOTUNE=1: heuristics only)
@@ -328,6 +343,28 @@ class ControlLDM(nn.Module):
         if self.cond_stage_model is None:
             raise RuntimeError("ControlLDM was built without a text encoder: pass cond_stage_config={}")
         return self.cond_stage_model.encode(c)
+
+    @torch.no_grad()
+    def q_sample(self, x_start, t, noise=None):
+        """Forward diffusion sqrt(abar_t) x0 + sqrt(1 - abar_t) noise (LatentDiffusion.q_sample, ddpm.py -- absent from
+        the reference checkout; called by DDIMSampler's mask blending, cldm/ddim_hacked.py:156). t int64 [B]."""
+        noise = torch.randn_like(x_start) if noise is None else noise
+        return ops.axpby(x_start.float().contiguous(), noise.float().contiguous(),
+                         self.sqrt_alphas_cumprod[t], self.sqrt_one_minus_alphas_cumprod[t])
+
+    @torch.no_grad()
+    def encode_first_stage(self, x, sample=False, noise=None):
+        """image fp32 NCHW in [-1, 1] -> latent z = scale_factor * (mode or sample of the encoder posterior)
+        (encode_first_stage + get_first_stage_encoding of ddpm.py; logvar clamped to [-30, 20] like
+        DiagonalGaussianDistribution). Returns fp32 [B, 4, h/8, w/8]."""
+        m = self.first_stage_model.encode_moments(x)
+        zc = m.shape[1] // 2
+        mean = m[:, :zc].contiguous()
+        if not sample:
+            return ops.axpby(mean, mean, self.scale_factor, 0.0)
+        std = torch.exp(0.5 * m[:, zc:].clamp(-30.0, 20.0)).contiguous()
+        noise = torch.randn_like(mean) if noise is None else noise.to(mean)
+        return ops.axpby(mean, (std * noise).contiguous(), self.scale_factor, self.scale_factor)
 
     @torch.no_grad()
     def decode_first_stage(self, z):

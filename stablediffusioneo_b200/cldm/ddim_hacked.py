@@ -148,7 +148,9 @@ class DDIMSampler(object):
             index = total_steps - i - 1
             ts = torch.full((b,), int(step), device=device, dtype=torch.long)
             if mask is not None:
-                raise NotImplementedError("mask/x0 blending is not on the ControlNet-SD1.5 path")
+                # inpainting blend (ddim_hacked.py:154-157): img = q_sample(x0, ts) * mask + (1 - mask) * img, one kernel
+                assert x0 is not None
+                img = self._mask_blend(img, x0, mask, ts)
             if ucg_schedule is not None:
                 assert len(ucg_schedule) == len(time_range)
                 unconditional_guidance_scale = ucg_schedule[i]
@@ -187,6 +189,96 @@ class DDIMSampler(object):
         pred_x0 = torch.empty_like(x)
         x_prev, _ = ops.cfg_ddim_step(e_c, e_u, x.contiguous(), coef, noise=noise, pred_x0=pred_x0)
         return x_prev, pred_x0
+
+    def _mask_blend(self, img, x0, mask, ts):
+        """img_orig = model.q_sample(x0, ts) (the model's own forward-diffusion draw, as in the reference), then
+        img_orig * mask + (1 - mask) * img as one pass."""
+        dev = img.device
+        img_orig = self.model.q_sample(x0.to(device=dev, dtype=torch.float32), ts).to(device=dev, dtype=torch.float32).contiguous()
+        mask = mask.to(device=dev, dtype=torch.float32)
+        if mask.dim() != 4 or mask.shape[0] != img.shape[0] or mask.shape[1] not in (1, img.shape[1]) \
+                or mask.shape[2:] != img.shape[2:]:
+            mask = mask.expand_as(img)
+        one = torch.ones((img.shape[0],), dtype=torch.float32, device=dev)
+        return ops.mask_blend(img_orig, img_orig, img.contiguous(), mask.contiguous(), one, torch.zeros_like(one))
+
+    def _guided_eps(self, x, t, c, scale, uc):
+        """eps for encode(): the reference concatenates (uncond, cond) into one batch with torch.cat, which only works for
+        tensor conditionings (ddim_hacked.py:257-262); dict conditionings (ControlLDM) are evaluated as two calls."""
+        if scale == 1.:
+            return self.model.apply_model(x, t, c)
+        assert uc is not None
+        if isinstance(c, dict) or isinstance(uc, dict):
+            e_u = self.model.apply_model(x, t, uc).contiguous()
+            e_c = self.model.apply_model(x, t, c).contiguous()
+        else:
+            e_u, e_c = torch.chunk(self.model.apply_model(torch.cat((x, x)), torch.cat((t, t)), torch.cat((uc, c))), 2)
+            e_u, e_c = e_u.contiguous(), e_c.contiguous()
+        return ops.axpby(e_u, e_c, 1.0 - scale, scale)
+
+    @torch.no_grad()
+    def encode(self, x0, c, t_enc, use_original_steps=False, return_intermediates=None, unconditional_guidance_scale=1.0,
+               unconditional_conditioning=None, callback=None):
+        """Deterministic DDIM inversion (ddim_hacked.py:233-276): x_next = sqrt(a_next / a) x + sqrt(a_next) (sqrt(1/a_next
+        - 1) - sqrt(1/a - 1)) eps, one fused pass per step. Needs make_schedule() first, like the reference."""
+        if use_original_steps:
+            raise NotImplementedError("use_original_steps is not on the ControlNet-SD1.5 path")
+        timesteps = self.ddim_timesteps
+        assert t_enc <= timesteps.shape[0]
+        num_steps = t_enc
+        alphas_next, alphas = self._h["alphas"][:num_steps], self._h["alphas_prev"][:num_steps]
+        x_next = x0.to(device=self.model.device, dtype=torch.float32).contiguous()
+        intermediates, inter_steps = [], []
+        for i in tqdm(range(num_steps), desc='Encoding Image', disable=True):
+            t = torch.full((x0.shape[0],), int(timesteps[i]), device=self.model.device, dtype=torch.long)
+            noise_pred = self._guided_eps(x_next, t, c, unconditional_guidance_scale, unconditional_conditioning)
+            an, a = float(alphas_next[i]), float(alphas[i])
+            x_next = ops.axpby(x_next, noise_pred.contiguous(), math.sqrt(an / a),
+                               math.sqrt(an) * (math.sqrt(1 / an - 1) - math.sqrt(1 / a - 1)))
+            if return_intermediates and i % (num_steps // return_intermediates) == 0 and i < num_steps - 1:
+                intermediates.append(x_next)
+                inter_steps.append(i)
+            elif return_intermediates and i >= num_steps - 2:
+                intermediates.append(x_next)
+                inter_steps.append(i)
+            if callback:
+                callback(i)
+        out = {'x_encoded': x_next, 'intermediate_steps': inter_steps}
+        if return_intermediates:
+            out.update({'intermediates': intermediates})
+        return x_next, out
+
+    @torch.no_grad()
+    def stochastic_encode(self, x0, t, use_original_steps=False, noise=None):
+        """sqrt(a_t) x0 + sqrt(1 - a_t) noise with t [B] indexing the DDIM tables, or the 1000-step tables when
+        use_original_steps (ddim_hacked.py:278-292)."""
+        dev = self.model.device
+        x0 = x0.to(device=dev, dtype=torch.float32).contiguous()
+        a = (self.alphas_cumprod if use_original_steps else torch.as_tensor(self._h["alphas"], dtype=torch.float32)).to(dev)
+        a = a[t.to(dev)]
+        if noise is None:
+            noise = torch.randn_like(x0)
+        return ops.axpby(x0, noise.to(device=dev, dtype=torch.float32).contiguous(), a.sqrt(), (1.0 - a).sqrt())
+
+    @torch.no_grad()
+    def decode(self, x_latent, cond, t_start, unconditional_guidance_scale=1.0, unconditional_conditioning=None,
+               use_original_steps=False, callback=None):
+        """p_sample_ddim over the first t_start DDIM timesteps, latest first (ddim_hacked.py:294-317)."""
+        if use_original_steps:
+            raise NotImplementedError("use_original_steps is not on the ControlNet-SD1.5 path")
+        timesteps = self.ddim_timesteps[:t_start]
+        time_range = np.flip(timesteps)
+        total_steps = timesteps.shape[0]
+        x_dec = x_latent.to(device=self.model.device, dtype=torch.float32)
+        for i, step in enumerate(time_range):
+            index = total_steps - i - 1
+            ts = torch.full((x_latent.shape[0],), int(step), device=x_dec.device, dtype=torch.long)
+            x_dec, _ = self.p_sample_ddim(x_dec, cond, ts, index=index, use_original_steps=use_original_steps,
+                                          unconditional_guidance_scale=unconditional_guidance_scale,
+                                          unconditional_conditioning=unconditional_conditioning)
+            if callback:
+                callback(i)
+        return x_dec
 
     # --------------------------------------------------------------------------------------------------------
     def _engine_sampling(self, cond, uncond, scale, x_T, log_every_t):

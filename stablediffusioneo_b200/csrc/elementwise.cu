@@ -294,6 +294,43 @@ __global__ void embedding_add_kernel(const long long* __restrict__ ids, const fl
   }
 }
 
+// ---- fp32 linear combinations of latents (sampler modes beyond plain sampling) ---------------------
+// y[i] = a[i / per] * x[i] + b[i / per] * z[i]: per-sample device coefficients. DDIM encode step
+// (ddim_hacked.py:262-265), stochastic_encode / q_sample (:290-292), CFG combine outside the fused step kernel.
+__global__ void axpby_f32_kernel(const float* __restrict__ x, const float* __restrict__ z, const float* __restrict__ a,
+                                 const float* __restrict__ b, float* __restrict__ y, long long count, long long per) {
+  const int trc = trace_start(5);
+  griddep_launch_dependents();
+  griddep_wait();
+  trace_mark(trc, 2);
+  trace_mark(trc, 3);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    const long long s = i / per;
+    y[i] = a[s] * x[i] + b[s] * z[i];
+  }
+}
+// Inpainting blend (ddim_hacked.py:154-157): y = mask * (a x0 + b noise) + (1 - mask) * img, the parenthesis being
+// q_sample(x0, t). mask has mask_c = 1 or c channels per sample ([n, mask_c, hw]); img / x0 / noise are [n, c, hw].
+__global__ void mask_blend_f32_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
+                                      const float* __restrict__ img, const float* __restrict__ mask,
+                                      const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y,
+                                      int n, int c, int mask_c, long long hw) {
+  const int trc = trace_start(5);
+  griddep_launch_dependents();
+  griddep_wait();
+  trace_mark(trc, 2);
+  trace_mark(trc, 3);
+  const long long count = (long long)n * c * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    const long long s = i / (c * hw);
+    const int ch = (int)((i / hw) % c);
+    const long long p = i % hw;
+    const float m = mask[(s * mask_c + (mask_c == 1 ? 0 : ch)) * hw + p];
+    const float orig = a[s] * x0[i] + b[s] * noise[i];
+    y[i] = orig * m + (1.0f - m) * img[i];
+  }
+}
+
 static int grid_for(long long work, int threads) {
   long long b = (work + threads - 1) / threads;
   if (b > 148 * 8) b = 148 * 8;
@@ -388,4 +425,16 @@ extern "C" int sdeo_softmax_rows(const float* x, void* y, int32_t rows, int32_t 
 extern "C" int sdeo_image_to_u8(const void* x, uint8_t* y, int32_t npix, int32_t c, int32_t ldx, void* stream) {
   if (!x || !y || npix <= 0 || c <= 0 || ldx < c) return set_error(SDEO_EINVAL, "image_to_u8: bad args");
   return launch_k("image_to_u8", image_to_u8_kernel, dim3(grid_for((long long)npix * c, 256)), dim3(256), 0, (cudaStream_t)stream, dim3(1, 1, 1), (const __nv_bfloat16*)x, y, npix, c, ldx);
+}
+
+extern "C" int sdeo_axpby_f32(const float* x, const float* z, const float* a, const float* b, float* y, int64_t count,
+                              int64_t per_sample, void* stream) {
+  if (!x || !z || !a || !b || !y || count <= 0 || per_sample <= 0) return set_error(SDEO_EINVAL, "axpby_f32: bad args");
+  return launch_k("axpby_f32", axpby_f32_kernel, dim3(grid_for(count, 256)), dim3(256), 0, (cudaStream_t)stream, dim3(1, 1, 1), x, z, a, b, y, (long long)count, (long long)per_sample);
+}
+extern "C" int sdeo_mask_blend_f32(const float* x0, const float* noise, const float* img, const float* mask, const float* a,
+                                   const float* b, float* y, int32_t n, int32_t c, int32_t mask_c, int64_t hw, void* stream) {
+  if (!x0 || !noise || !img || !mask || !a || !b || !y || n <= 0 || c <= 0 || hw <= 0 || (mask_c != 1 && mask_c != c))
+    return set_error(SDEO_EINVAL, "mask_blend_f32: bad args");
+  return launch_k("mask_blend_f32", mask_blend_f32_kernel, dim3(grid_for((long long)n * c * hw, 256)), dim3(256), 0, (cudaStream_t)stream, dim3(1, 1, 1), x0, noise, img, mask, a, b, y, n, c, mask_c, (long long)hw);
 }

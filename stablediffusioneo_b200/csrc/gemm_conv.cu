@@ -128,7 +128,7 @@ __device__ __forceinline__ uint4 pack8_bf16(const float* x) {
 enum { OUT_BF16 = 0, OUT_F32 = 1, OUT_F32_TWIN = 2 };
 enum { RES_NONE = 0, RES_BF16 = 1, RES_F32 = 2 };
 
-// NORMAL epilogue, fast path: cout % 8 == 0 and all row pitches vector-aligned (checked on the host).
+// NORMAL epilogue, fast path: cout % 16 == 0 (every N tile full) and all row pitches vector-aligned (checked on the host).
 template <int OUT, int RES>
 __device__ __forceinline__ void epi_normal_fast(const ConvKParams& p, long long pix, int batch, int n, float* v,
                                                 const uint4& raw0, const uint4& raw1) {
@@ -980,11 +980,14 @@ static inline int cta_limit() { return g_cta_budget > 0 && g_cta_budget < 148 ? 
 static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl, int force_bn = 0, int force_splits = 0) {
   if (!(a->ksize == 1 || a->ksize == 3)) return false;
   if (!(a->stride == 1 || a->stride == 2)) return false;
-  if (a->pad != (a->ksize == 3 ? 1 : 0)) return false;
+  // symmetric "same" padding, or the VAE encoder's Downsample: 3x3 stride 2 over F.pad(x, (0,1,0,1)) = no leading padding,
+  // one trailing zero row / column (TMA out-of-bounds fill supplies it like every other padding pixel)
+  const bool tail_pad = a->ksize == 3 && a->stride == 2 && a->pad == 0 && a->pad_hi == 1;
+  if (!tail_pad && (a->pad != (a->ksize == 3 ? 1 : 0) || a->pad_hi != 0)) return false;
   if (a->c1 <= 0 || (a->ld1 % 8) != 0 || (a->x2 && (a->ld2 % 8) != 0)) return false;
   if (a->x2 && (a->c1 % 64) != 0) return false;
-  pl->Ho = (a->h + 2 * a->pad - a->ksize) / a->stride + 1;
-  pl->Wo = (a->w + 2 * a->pad - a->ksize) / a->stride + 1;
+  pl->Ho = (a->h + 2 * a->pad + a->pad_hi - a->ksize) / a->stride + 1;
+  pl->Wo = (a->w + 2 * a->pad + a->pad_hi - a->ksize) / a->stride + 1;
   // ---- M tile box: minimise tile count, then prefer wide boxes ----
   int best_tiles = INT32_MAX, bbn = 1, bbh = 1, bbw = 1;
   const int maxw = pl->Wo < kBM ? pl->Wo : kBM;
@@ -1157,7 +1160,7 @@ static int launch_conv(const sdeo_conv_args* a, const ConvPlan& pl, void* stream
 // 64 / 128 / 256 columns (the lanes that hold one row must form an aligned power-of-two group of a warp).
 static bool row_stats_ok(const sdeo_conv_args* a, const ConvPlan& pl) {
   if (!a->row_stats || a->epi_mode != SDEO_EPI_NORMAL || !a->y_fp32) return false;
-  bool fast = (a->cout % 8 == 0) && (a->ldy % 4 == 0);
+  bool fast = (a->cout % 16 == 0) && (a->ldy % 4 == 0);
   if (a->y2) fast = fast && (a->ldy2 % 8 == 0);
   if (a->residual) fast = fast && (a->residual_f32 ? (a->ldr % 4 == 0) : (a->ldr % 8 == 0));
   return fast && (pl.BN == 64 || pl.BN == 128 || pl.BN == 256);
@@ -1165,7 +1168,7 @@ static bool row_stats_ok(const sdeo_conv_args* a, const ConvPlan& pl) {
 
 static int stats_parts(const sdeo_conv_args* a, const ConvPlan& pl) {
   if (!a->gn_stats || a->row_stats || a->epi_mode != SDEO_EPI_NORMAL || !a->y_fp32) return 0;
-  bool fast = (a->cout % 8 == 0) && (a->ldy % 4 == 0);
+  bool fast = (a->cout % 16 == 0) && (a->ldy % 4 == 0);
   if (a->y2) fast = fast && (a->ldy2 % 8 == 0);
   if (a->residual) fast = fast && (a->residual_f32 ? (a->ldr % 4 == 0) : (a->ldr % 8 == 0));
   if (!fast) return 0;
@@ -1192,7 +1195,7 @@ std::mutex g_tune_mu;
 int g_autotune = 0;
 
 TuneKey tune_key(const sdeo_conv_args* a) {
-  TuneKey k = {a->n, a->h, a->w, a->c1, a->x2 ? a->c2 : 0, a->cout, a->ksize, a->stride, a->epi_mode, a->y_fp32,
+  TuneKey k = {a->n, a->h, a->w, a->c1, a->x2 ? a->c2 : 0, a->cout, a->ksize, a->stride | (a->pad_hi << 4), a->epi_mode, a->y_fp32,
                a->residual ? (a->residual_f32 ? 2 : 1) : 0, a->y2 ? 1 : 0, a->emb ? 1 : 0, a->act, a->dhead,
                (a->gn_stats ? 1 : 0) | (a->row_stats ? 2 : 0) | (a->ln_stats ? 4 : 0) | (cta_limit() << 3)};
   return k;
@@ -1401,7 +1404,9 @@ static int launch_conv(const sdeo_conv_args* a, const ConvPlan& pl, void* stream
   } else {
     const int out_kind = !a->y_fp32 ? OUT_BF16 : (p.y2 ? OUT_F32_TWIN : OUT_F32);
     const int res_kind = !a->residual ? RES_NONE : (a->residual_f32 ? RES_F32 : RES_BF16);
-    bool fast = (a->cout % 8 == 0);
+    // (rows are packed in multiples of 16: with cout % 16 == 8 the last N tile has 8 columns beyond cout, which only the
+    // generic item path masks -- e.g. the VAE encoder's 8-channel conv_out / quant_conv)
+    bool fast = (a->cout % 16 == 0);
     fast = fast && (out_kind == OUT_BF16 ? (a->ldy % 8 == 0) : (a->ldy % 4 == 0));
     if (out_kind == OUT_F32_TWIN) fast = fast && (a->ldy2 % 8 == 0);
     if (res_kind == RES_BF16) fast = fast && (a->ldr % 8 == 0);

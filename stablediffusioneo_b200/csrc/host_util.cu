@@ -80,7 +80,7 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
 }  // namespace sdeo
 
 extern "C" const char* sdeo_last_error(void) { return sdeo::g_err; }
-extern "C" int sdeo_version(void) { return 1; }
+extern "C" int sdeo_version(void) { return 2; }  // 2: sdeo_conv_args::pad_hi, fp32-mode and sampler-mode entry points
 extern "C" int sdeo_trace_set_conv(void*);
 extern "C" int sdeo_trace_set_attention(void*);
 extern "C" int sdeo_trace_set_norm(void*);

@@ -1,5 +1,5 @@
-"""VAE Decoder with the reference's names and state-dict keys (ldm/modules/diffusionmodules/model.py:41-203,
-546-652), on the same conv / GroupNorm kernels as the UNet."""
+"""VAE Decoder and Encoder with the reference's names and state-dict keys (ldm/modules/diffusionmodules/model.py:41-203,
+452-543, 546-652), on the same conv / GroupNorm kernels as the UNet."""
 import numpy as np
 import torch
 import torch.nn as nn
@@ -24,6 +24,26 @@ class Upsample(nn.Module):
     def run(self, x):
         y = nchw_view(ops.upsample_nearest2x(nhwc(x)))
         return self.conv.run(y) if self.with_conv else y
+
+    def forward(self, x):
+        if is_internal(x):
+            return self.run(x)
+        return to_external(self.run(to_internal(x)))
+
+
+class Downsample(nn.Module):
+    """F.pad(x, (0,1,0,1)) + conv3x3 stride 2 without padding (model.py:66-87): the trailing zero row / column is the
+    TMA out-of-bounds fill of the implicit-GEMM kernel (sdeo_conv_args::pad_hi), no padded copy."""
+
+    def __init__(self, in_channels, with_conv):
+        super().__init__()
+        self.with_conv = with_conv
+        if not with_conv:
+            raise NotImplementedError("avg-pool Downsample is not on the SD1.5 VAE path (resamp_with_conv=True)")
+        self.conv = Conv2d(in_channels, in_channels, kernel_size=3, stride=2, padding=0)
+
+    def run(self, x):
+        return self.conv.run(x, pad_hi=1)
 
     def forward(self, x):
         if is_internal(x):
@@ -120,6 +140,75 @@ def make_attn(in_channels, attn_type="vanilla", attn_kwargs=None):
     if attn_type != "vanilla":
         raise NotImplementedError(f"attn_type {attn_type} is not on the VAE decoder path")
     return AttnBlock(in_channels)
+
+
+class Encoder(nn.Module):
+    """model.py:452-543: conv_in -> per level ResnetBlocks (+ Downsample) -> mid (Res, Attn, Res) -> GN+swish -> conv_out
+    (2 z_channels when double_z: the moments the 1x1 quant_conv turns into mean | logvar)."""
+
+    def __init__(self, *, ch, out_ch, ch_mult=(1, 2, 4, 8), num_res_blocks, attn_resolutions, dropout=0.0,
+                 resamp_with_conv=True, in_channels, resolution, z_channels, double_z=True, use_linear_attn=False,
+                 attn_type="vanilla", **ignore_kwargs):
+        super().__init__()
+        if use_linear_attn:
+            raise NotImplementedError("linear attention is not on the SD1.5 VAE path")
+        self.ch = ch
+        self.temb_ch = 0
+        self.num_resolutions = len(ch_mult)
+        self.num_res_blocks = num_res_blocks
+        self.resolution = resolution
+        self.in_channels = in_channels
+        self.conv_in = Conv2d(in_channels, self.ch, kernel_size=3, stride=1, padding=1)
+        curr_res = resolution
+        in_ch_mult = (1,) + tuple(ch_mult)
+        self.in_ch_mult = in_ch_mult
+        self.down = nn.ModuleList()
+        block_in = ch
+        for i_level in range(self.num_resolutions):
+            block = nn.ModuleList()
+            attn = nn.ModuleList()
+            block_in = ch * in_ch_mult[i_level]
+            block_out = ch * ch_mult[i_level]
+            for _ in range(self.num_res_blocks):
+                block.append(ResnetBlock(in_channels=block_in, out_channels=block_out, temb_channels=self.temb_ch,
+                                         dropout=dropout))
+                block_in = block_out
+                if curr_res in attn_resolutions:
+                    attn.append(make_attn(block_in, attn_type=attn_type))
+            down = nn.Module()
+            down.block = block
+            down.attn = attn
+            if i_level != self.num_resolutions - 1:
+                down.downsample = Downsample(block_in, resamp_with_conv)
+                curr_res = curr_res // 2
+            self.down.append(down)
+        self.mid = nn.Module()
+        self.mid.block_1 = ResnetBlock(in_channels=block_in, out_channels=block_in, temb_channels=self.temb_ch, dropout=dropout)
+        self.mid.attn_1 = make_attn(block_in, attn_type=attn_type)
+        self.mid.block_2 = ResnetBlock(in_channels=block_in, out_channels=block_in, temb_channels=self.temb_ch, dropout=dropout)
+        self.norm_out = Normalize(block_in)
+        self.out_channels = 2 * z_channels if double_z else z_channels
+        self.conv_out = Conv2d(block_in, self.out_channels, kernel_size=3, stride=1, padding=1)
+
+    def run(self, x):
+        """model.py:514-543 on internal tensors (the reference's `hs` list only ever reads its last element)."""
+        h = self.conv_in.run(x)
+        for i_level in range(self.num_resolutions):
+            for i_block in range(self.num_res_blocks):
+                h = self.down[i_level].block[i_block].run(h)
+                if len(self.down[i_level].attn) > 0:
+                    h = self.down[i_level].attn[i_block].run(h)
+            if i_level != self.num_resolutions - 1:
+                h = self.down[i_level].downsample.run(h)
+        h = self.mid.block_1.run(h)
+        h = self.mid.attn_1.run(h)
+        h = self.mid.block_2.run(h)
+        return self.conv_out.run(self.norm_out.run(h, silu=True))
+
+    def forward(self, x):
+        if is_internal(x):
+            return self.run(x)
+        return to_external(self.run(to_internal(x)), self.out_channels)
 
 
 class Decoder(nn.Module):

@@ -199,8 +199,11 @@ class Conv2d(nn.Conv2d):
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
         k = self.kernel_size[0]
+        # padding 0 with a 3x3 stride-2 filter is the VAE encoder's Downsample, which pads (0,1,0,1) itself (model.py:78-84):
+        # only runnable through run(..., pad_hi=1)
+        self.tail_pad = k == 3 and self.stride == (2, 2) and self.padding == (0, 0)
         if self.kernel_size != (k, k) or k not in (1, 3) or self.stride[0] not in (1, 2) or self.stride[0] != self.stride[1] \
-                or self.padding != ((k // 2), (k // 2)) or self.groups != 1 or self.dilation != (1, 1):
+                or (self.padding != ((k // 2), (k // 2)) and not self.tail_pad) or self.groups != 1 or self.dilation != (1, 1):
             raise NotImplementedError(f"Conv2d configuration not on the ControlNet-SD1.5 path: {self}")
         self._cache = {}
 
@@ -223,10 +226,12 @@ class Conv2d(nn.Conv2d):
         return self.bias.detach() if self.bias is not None else None
 
     def run(self, x, emb=None, residual=None, scale=1.0, act=SDEO_ACT_NONE, out_fp32=False, stream=False, emb_step=None,
-            gn_stats=False, row_stats=False):
+            gn_stats=False, row_stats=False, pad_hi=0):
         """x: internal tensor (bf16 or fp32 stream) or CatPair. Returns an internal bf16 tensor; fp32 NHWC-physical when
         out_fp32; an fp32 stream tensor with a bf16 twin when `stream`. A bf16 output whose channel count is not a
         multiple of 8 is zero-padded to one (so a following conv can TMA it)."""
+        if self.tail_pad != bool(pad_hi):
+            raise NotImplementedError("a 3x3 stride-2 padding-0 Conv2d runs only as F.pad(x, (0,1,0,1)) + conv (pad_hi=1)")
         res = nhwc(residual) if residual is not None else None
         out = None
         cout = self.out_channels
@@ -234,11 +239,12 @@ class Conv2d(nn.Conv2d):
             assert residual is None
             n, _, h, w = x.shape
             k, s = self.kernel_size[0], self.stride[0]
-            ho, wo = (h + 2 * (k // 2) - k) // s + 1, (w + 2 * (k // 2) - k) // s + 1
+            pd = 0 if pad_hi else k // 2
+            ho, wo = (h + 2 * pd + pad_hi - k) // s + 1, (w + 2 * pd + pad_hi - k) // s + 1
             out = torch.empty((n, ho, wo, (cout + 7) // 8 * 8), dtype=BF16, device=self.weight.device)
             ops.memset(out, 0)
         kw = dict(bias=self.bias_f32(), emb=emb, residual=res, scale=scale, act=act, stride=self.stride[0],
-                  out_fp32=out_fp32 or stream, out=out, twin=stream, emb_step=emb_step,
+                  out_fp32=out_fp32 or stream, out=out, twin=stream, emb_step=emb_step, pad_hi=pad_hi,
                   gn_stats=gn_stats and (out_fp32 or stream) and FUSE_GN_STATS,
                   row_stats=row_stats and (out_fp32 or stream) and FOLD_LN)
         if isinstance(x, CatPair):

@@ -133,7 +133,7 @@ def pack_geglu_bias(bias, geglu_bn):
 
 def conv2d(x, pw, x2=None, bias=None, emb=None, residual=None, scale=1.0, act=SDEO_ACT_NONE, stride=1, out=None,
            out_fp32=False, epi_mode=SDEO_EPI_NORMAL, qkv=None, twin=False, emb_step=None, gn_stats=False, row_stats=False,
-           ln=None):
+           ln=None, pad_hi=0):
     """x: [N,H,W,C1] bf16 (+ optional x2 [N,H,W,C2] = fused torch.cat along channels). Returns [N,Ho,Wo,cout].
     residual may be bf16 or fp32. out_fp32 + twin=True additionally writes a bf16 copy and returns (y_f32, y_bf16).
     emb: fp32 [N, cout] (row = sample), or with emb_step (int32 device scalar) a table [S, cout] whose row *emb_step is
@@ -141,7 +141,9 @@ def conv2d(x, pw, x2=None, bias=None, emb=None, residual=None, scale=1.0, act=SD
     GroupNorm that consumes the result; they are attached to the returned fp32 tensor as `_gn_stats = (buffer, parts
     per sample)` when the kernel produced them (see groupnorm(stats=...)). row_stats (fp32 outputs feeding a LayerNorm):
     per-row partial statistics, attached as `_row_stats = (buffer, parts, rows)`. ln: LnFold -- this GEMM applies a
-    LayerNorm to its input rows in the epilogue (x is the raw bf16 input; pw / bias carry gamma / beta)."""
+    LayerNorm to its input rows in the epilogue (x is the raw bf16 input; pw / bias carry gamma / beta).
+    pad_hi=1 (3x3, stride 2): no leading padding, one trailing zero row / column = F.pad(x, (0,1,0,1)) + conv(padding=0),
+    the VAE encoder's Downsample (model.py:78-84)."""
     lib = _lib.load()
     _req(x, BF16, "x")
     _req(x2, BF16, "x2")
@@ -161,9 +163,13 @@ def conv2d(x, pw, x2=None, bias=None, emb=None, residual=None, scale=1.0, act=SD
         assert pw.c2 == 0
     k = pw.ksize
     pad = 1 if k == 3 else 0
-    ho = (h + 2 * pad - k) // stride + 1
-    wo = (w + 2 * pad - k) // stride + 1
+    if pad_hi:
+        assert k == 3 and stride == 2 and pad_hi == 1
+        pad = 0
+    ho = (h + 2 * pad + pad_hi - k) // stride + 1
+    wo = (w + 2 * pad + pad_hi - k) // stride + 1
     a = ConvArgs()
+    a.pad_hi = pad_hi
     a.x1, a.x2 = _ptr(x), _ptr(x2)
     a.n, a.h, a.w = n, h, w
     a.c1, a.ld1, a.c2, a.ld2 = c1, ld1, c2, ld2
@@ -448,6 +454,37 @@ def cfg_ddim_step(eps_c, eps_u, x, coef_table, step_idx=None, noise=None, x_prev
                                  _ptr(x_prev), _ptr(pred_x0), _ptr(x_next), dup, ldn, _ptr(coef_table),
                                  _ptr(step_idx), n, c, h * w, _stream()), "cfg_ddim_step")
     return x_prev, pred_x0
+
+
+def axpby(x, z, a, b, out=None):
+    """fp32 a[s] * x + b[s] * z with per-sample coefficients: a, b python floats or fp32 device tensors [N]."""
+    lib = _lib.load()
+    _req(x, torch.float32, "x")
+    _req(z, torch.float32, "z")
+    assert x.shape == z.shape
+    n = x.shape[0]
+    coef = lambda c: (c.to(device=x.device, dtype=torch.float32).reshape(n).contiguous() if torch.is_tensor(c)
+                      else torch.full((n,), float(c), dtype=torch.float32, device=x.device))
+    a, b = coef(a), coef(b)
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.sdeo_axpby_f32(_ptr(x), _ptr(z), _ptr(a), _ptr(b), _ptr(out), x.numel(), x.numel() // n, _stream()), "axpby")
+    return out
+
+
+def mask_blend(x0, noise, img, mask, a, b):
+    """mask * (a[s] * x0 + b[s] * noise) + (1 - mask) * img on fp32 [N, C, H, W]; mask [N, 1 or C, H, W]."""
+    lib = _lib.load()
+    for t, name in ((x0, "x0"), (noise, "noise"), (img, "img"), (mask, "mask")):
+        _req(t, torch.float32, name)
+    n, c, h, w = img.shape
+    assert x0.shape == img.shape == noise.shape and mask.shape[0] == n and mask.shape[2:] == img.shape[2:]
+    a = a.to(device=img.device, dtype=torch.float32).reshape(n).contiguous()
+    b = b.to(device=img.device, dtype=torch.float32).reshape(n).contiguous()
+    out = torch.empty_like(img)
+    check(lib.sdeo_mask_blend_f32(_ptr(x0), _ptr(noise), _ptr(img), _ptr(mask), _ptr(a), _ptr(b), _ptr(out), n, c,
+                                  mask.shape[1], h * w, _stream()), "mask_blend")
+    return out
 
 
 def set_autotune(enable=True):

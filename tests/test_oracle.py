@@ -102,3 +102,27 @@ def test_sd15_single_step_full_size():
     with torch.no_grad():
         eps = O.apply_model(sd_unet, sd_cn, cfg, x_T, torch.full((1,), 951, dtype=torch.long), cond)
     assert rel_l2(eps, g["eps_c_t951"]) < 1e-4
+
+
+def test_sampler_modes_and_vae_encoder_vs_reference():
+    """eta > 0, mask / x0 blending, encode / decode / stochastic_encode and the VAE Encoder, oracle vs the
+    fixtures made by the real reference classes (tests/golden/make_golden_modes.py)."""
+    g = load_golden("tiny_modes")
+    cfg, vcfg = O.TINY, O.TINY_VAE
+    sd_unet, sd_cn, _ = oracle_weights(cfg, vcfg)
+    eps_fn = lambda x, t, c: O.apply_model(sd_unet, sd_cn, cfg, x, t, c)
+    x_T, cond, uncond = O.make_inputs(cfg, 1, 8, 16)
+    S = g["S"]
+    with torch.no_grad():
+        smp, _ = O.ddim_sample(eps_fn, x_T, cond, uncond, S=S, scale=9.0, eta=g["eta"], noises=list(g["eta_noises"]))
+        assert rel_l2(smp, g["eta_samples"]) < 1e-4
+        smp, _ = O.ddim_sample(eps_fn, x_T, cond, uncond, S=S, scale=9.0, mask=g["mask"], x0=g["mask_x0"],
+                               q_noises=list(g["mask_q_noises"]))
+        assert rel_l2(smp, g["mask_samples"]) < 1e-4
+        enc = O.ddim_encode(eps_fn, g["encode_x0"], cond, g["encode_t_enc"], S=S)
+        assert rel_l2(enc, g["encoded"]) < 1e-4
+        dec = O.ddim_decode(eps_fn, g["encoded"], cond, g["decode_t_start"], S=S, scale=9.0, uncond=uncond)
+        assert rel_l2(dec, g["decoded_latent"]) < 1e-4
+        assert rel_l2(O.stochastic_encode(g["encode_x0"], g["stoch_t"], S=S, noise=g["stoch_noise"]), g["stoch_encoded"]) < 1e-6
+        sd_enc = O.make_weights(O.vae_encoder_param_spec(vcfg), seed=1234, prefix="vae.")
+        assert rel_l2(O.vae_encode(sd_enc, vcfg, g["enc_image"]), g["enc_moments"]) < 1e-5
