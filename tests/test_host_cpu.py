@@ -175,3 +175,56 @@ def test_replica_sharding_and_gather_gloo(n_items):
         p.join(120)
         assert p.exitcode == 0
     assert list(out) == [1, 1]
+
+
+def test_checkpoint_helpers_and_create_model(tmp_path):
+    """cldm/model.py:8-28 mirrors: load_state_dict for .pth ('state_dict'-wrapped) and .safetensors, create_model from a
+    cldm_v15.yaml-style config (PyYAML instead of OmegaConf); strict loading into the module tree proves the checkpoint
+    prefixes (`control_model.`, `model.diffusion_model.`, `first_stage_model.`) are the module names."""
+    import yaml
+    from helpers import O, unet_kwargs, vae_kwargs
+    from stablediffusioneo_b200.cldm.model import create_model, load_state_dict
+    cfg = {"model": {"target": "cldm.cldm.ControlLDM", "params": {
+        "linear_start": 0.00085, "linear_end": 0.0120, "timesteps": 1000, "control_key": "hint", "scale_factor": 0.18215,
+        "only_mid_control": False,
+        "control_stage_config": {"target": "cldm.cldm.ControlNet",
+                                 "params": dict({k: v for k, v in unet_kwargs(O.TINY).items() if k != "out_channels"},
+                                                hint_channels=3)},
+        "unet_config": {"target": "cldm.cldm.ControlledUnetModel", "params": unet_kwargs(O.TINY)},
+        "first_stage_config": {"target": "ldm.models.autoencoder.AutoencoderKL",
+                               "params": {"embed_dim": 4, "ddconfig": vae_kwargs(O.TINY_VAE)}},
+        "cond_stage_config": {"target": "ldm.modules.encoders.modules.FrozenCLIPEmbedder"}}}}
+    path = tmp_path / "cldm_tiny.yaml"
+    path.write_text(yaml.safe_dump(cfg))
+    model = create_model(str(path))
+    assert model.cond_stage_model is None and model.scale_factor == 0.18215
+    sd = {k: torch.randn_like(v) for k, v in model.state_dict().items()}
+    torch.save({"state_dict": sd}, tmp_path / "w.pth")
+    import safetensors.torch
+    safetensors.torch.save_file(sd, str(tmp_path / "w.safetensors"))
+    for name in ("w.pth", "w.safetensors"):
+        loaded = load_state_dict(str(tmp_path / name), location="cpu")
+        assert set(loaded) == set(sd) and all(torch.equal(loaded[k], sd[k]) for k in sd)
+        model2 = create_model(str(path))
+        missing, unexpected = model2.load_state_dict(loaded, strict=True)
+        assert not missing and not unexpected
+        k0 = "control_model.input_hint_block.0.weight"
+        assert torch.equal(model2.state_dict()[k0], sd[k0])
+    assert len(create_model().state_dict()) == 1166  # SD1.5 defaults: the reference modules' 1166 tensors
+
+
+def test_engine_surface_shapes():
+    """Engine.infer's binding names / static shapes (Engine.py:66-90, onnx2trt_static_plugin.py:79-115)."""
+    from stablediffusioneo_b200.Engine import Engine
+    from stablediffusioneo_b200.cldm.cldm import ControlLDM
+    with torch.device("meta"):
+        model = ControlLDM()
+    unet = Engine(model, "unet").shape_dict()
+    assert list(unet)[:3] == ["x_noisy", "timestep", "context"] and list(unet)[-1] == "latent"
+    want = [(1, 320, 32, 48)] * 3 + [(1, 320, 16, 24), (1, 640, 16, 24), (1, 640, 16, 24), (1, 640, 8, 12), (1, 1280, 8, 12),
+                                      (1, 1280, 8, 12)] + [(1, 1280, 4, 6)] * 4
+    assert [unet[f"control{i}"] for i in range(13)] == want
+    cn = Engine(model, "controlnet").shape_dict()
+    assert list(cn)[:4] == ["x_noisy", "hint", "timestep", "context"] and len(cn) == 17
+    assert cn["hint"] == (1, 3, 256, 384) and cn["context"] == (1, 77, 768)
+    assert Engine(model, "decoder").shape_dict()["images"] == (1, 3, 256, 384)

@@ -161,3 +161,36 @@ def test_vae_encoder(cuda_device):
     ref = 0.18215 * (mom[:, :4] + torch.exp(0.5 * mom[:, 4:].clamp(-30, 20)) * nz)
     assert rel_l2(zs, ref) < 2e-2
     assert model.decode_first_stage(z).shape == (1, 3, 64, 128)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_engine_infer_surface(tiny, cuda_device, graph):
+    """the reference's TensorRT-engine call pattern (cldm_trt/ddim_hacked.py:140-152) against
+    Engine.infer of this package -- controlnet engine -> 13 controls (dict values [4:17]) -> unet engine -> 'latent' -- equals
+    apply_model; second call with other inputs replays the captured graph."""
+    from stablediffusioneo_b200.Engine import Engine
+    model, _ = tiny
+    model.precision = "bf16"
+    dev = cuda_device
+    x_T, cond, uncond = inputs_on(O.TINY, 8, 16, dev)
+    cn = Engine(model, "controlnet", latent_h=8, latent_w=16)
+    un = Engine(model, "unet", latent_h=8, latent_w=16)
+    stream = torch.cuda.Stream(device=dev)
+    stream.wait_stream(torch.cuda.current_stream())
+    for c in (cond, uncond):
+        ts = torch.full((1,), 951, dtype=torch.int32, device=dev)  # the ONNX export feeds int32 timesteps
+        out = cn.infer({"x_noisy": x_T, "hint": c["c_concat"][0], "timestep": ts, "context": c["c_crossattn"][0]},
+                       stream=stream, use_cuda_graph=graph)
+        control = list(out.values())
+        assert len(control) == 17
+        feed = {"x_noisy": x_T, "timestep": ts, "context": c["c_crossattn"][0]}
+        feed.update({f"control{i}": control[4 + i] for i in range(13)})
+        eps = un.infer(feed, stream, use_cuda_graph=graph)["latent"].clone()
+        stream.synchronize()
+        ref = model.apply_model(x_T, ts.long(), c)
+        err = rel_l2(eps, ref)
+        print("engine surface vs apply_model rel L2:", err)
+        assert err < 1.5e-2  # two bf16 paths of ours: unfused control injection (bf16 adds) vs the fused epilogue
+    dec = Engine(model, "decoder", latent_h=8, latent_w=16)
+    img = dec.infer({"latent": x_T * 0.18215})["images"]
+    assert img.shape == (1, 3, 64, 128)
