@@ -272,6 +272,17 @@ int sdeo_silu_f32(const float* x, float* y, int64_t count, void* stream);
 /* fp32 [n, dim] sinusoidal embedding [cos | sin] of int64 timesteps (util.py:154-174). */
 int sdeo_timestep_embedding_f32(const int64_t* t, float* y, int32_t n, int32_t dim, float max_period, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Hint preprocessing: cv2.Canny on the device, bit-exact with OpenCV for 8-bit 1- or 3-channel images,
+ * aperture 3, L1 gradient (annotator/canny/__init__.py:4-6 -> cv2.Canny; canny2image_torch.py:30-38).
+ * img uint8 HWC [h, w, c]; edges uint8 [h, w] (0 / 255). Workspace from sdeo_canny_workspace_bytes.
+ * ---------------------------------------------------------------------------------------------- */
+size_t sdeo_canny_workspace_bytes(int32_t h, int32_t w);
+int sdeo_canny_u8(const uint8_t* img, int32_t h, int32_t w, int32_t c, double low_threshold, double high_threshold,
+                  uint8_t* edges, void* workspace, size_t workspace_bytes, void* stream);
+/* hint fp32 NCHW [n, 3, h*w] = HWC3(edges) / 255, repeated n times (canny2image_torch.py:34-38). */
+int sdeo_edges_to_hint(const uint8_t* edges, float* hint, int32_t n, int32_t hw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,6 +80,10 @@ SIGNATURES = {
     "sdeo_bf16_to_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "sdeo_image_to_u8": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "sdeo_memset_async": (c_int, [c_void_p, c_int, c_size_t, c_void_p]),
+    "sdeo_canny_workspace_bytes": (c_size_t, [c_int32, c_int32]),
+    "sdeo_canny_u8": (c_int, [c_void_p, c_int32, c_int32, c_int32, ctypes.c_double, ctypes.c_double, c_void_p, c_void_p,
+                              c_size_t, c_void_p]),
+    "sdeo_edges_to_hint": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "sdeo_axpby_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "sdeo_mask_blend_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                     c_int32, c_int64, c_void_p]),

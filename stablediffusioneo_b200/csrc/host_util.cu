@@ -86,9 +86,10 @@ extern "C" int sdeo_trace_set_attention(void*);
 extern "C" int sdeo_trace_set_norm(void*);
 extern "C" int sdeo_trace_set_elementwise(void*);
 extern "C" int sdeo_trace_set_precise(void*);
+extern "C" int sdeo_trace_set_canny(void*);
 extern "C" int sdeo_set_trace(void* buf) {
   int rc = sdeo_trace_set_conv(buf) | sdeo_trace_set_attention(buf) | sdeo_trace_set_norm(buf) | sdeo_trace_set_elementwise(buf) |
-           sdeo_trace_set_precise(buf);
+           sdeo_trace_set_precise(buf) | sdeo_trace_set_canny(buf);
   return rc ? sdeo::set_error(SDEO_ECUDA, "set_trace: cudaMemcpyToSymbol failed") : SDEO_OK;
 }
 extern "C" int sdeo_set_pdl(int enable) {

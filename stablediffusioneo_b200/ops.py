@@ -650,3 +650,30 @@ def timestep_embedding_f32(t, dim, max_period=10000.0):
     check(lib.sdeo_timestep_embedding_f32(_ptr(t), _ptr(out), t.shape[0], dim, float(max_period), _stream()),
           "timestep_embedding_f32")
     return out
+
+
+# ---- hint preprocessing (csrc/canny.cu) -------------------------------------------------------------------------
+def canny(img, low_threshold, high_threshold):
+    """uint8 CUDA tensor [H, W] or [H, W, C] (C = 1 or 3) -> uint8 [H, W] edge map (0 / 255), bit-exact with cv2.Canny."""
+    lib = _lib.load()
+    _req(img, torch.uint8, "img")
+    if img.dim() == 2:
+        img = img[:, :, None]
+    h, w, c = img.shape
+    edges = torch.empty((h, w), dtype=torch.uint8, device=img.device)
+    ws = torch.empty(lib.sdeo_canny_workspace_bytes(h, w), dtype=torch.uint8, device=img.device)
+    global LAUNCHES
+    check(lib.sdeo_canny_u8(_ptr(img), h, w, c, float(low_threshold), float(high_threshold), _ptr(edges), _ptr(ws),
+                            ws.numel(), _stream()), "canny")
+    LAUNCHES += 2
+    return edges
+
+
+def edges_to_hint(edges, num_samples=1):
+    """uint8 [H, W] edge map -> fp32 [num_samples, 3, H, W] = HWC3(map) / 255 (canny2image_torch.py:34-38)."""
+    lib = _lib.load()
+    _req(edges, torch.uint8, "edges")
+    h, w = edges.shape
+    hint = torch.empty((num_samples, 3, h, w), dtype=torch.float32, device=edges.device)
+    check(lib.sdeo_edges_to_hint(_ptr(edges), _ptr(hint), num_samples, h * w, _stream()), "edges_to_hint")
+    return hint

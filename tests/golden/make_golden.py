@@ -262,6 +262,7 @@ def canny_hint():
     hint = torch.from_numpy(hwc3.copy()).float() / 255.0
     hint = hint.permute(2, 0, 1)[None].contiguous()
     np.save(os.path.join(HERE, "canny_bird0.npy"), np.packbits(edges > 0))
+    np.save(os.path.join(HERE, "bird0_bgr.npy"), img)  # decoded pixels: input fixture of the device-side Canny tests
     return hint
 
 

@@ -194,3 +194,37 @@ def test_engine_infer_surface(tiny, cuda_device, graph):
     dec = Engine(model, "decoder", latent_h=8, latent_w=16)
     img = dec.infer({"latent": x_T * 0.18215})["images"]
     assert img.shape == (1, 3, 64, 128)
+
+
+def test_canny_bit_exact(cuda_device):
+    """the hint preprocessing on the device. Bit-exact against the numpy oracle (itself pinned to cv2.Canny)
+    and the committed bird_0 fixture; CannyDetector numpy / tensor interfaces; the [N,3,H,W] hint tensor."""
+    import os
+    import numpy as np
+    from helpers import GOLDEN, canny_hint
+    from oracle.canny_oracle import canny as canny_ref
+    from stablediffusioneo_b200.annotator.canny import CannyDetector
+    from stablediffusioneo_b200.annotator.util import HWC3, resize_image
+    det = CannyDetector(cuda_device)
+    img = np.load(os.path.join(GOLDEN, "bird0_bgr.npy"))
+    img = resize_image(HWC3(img), 256)                         # identity at this size (canny2image_torch.py:30)
+    bits = np.unpackbits(np.load(os.path.join(GOLDEN, "canny_bird0.npy")))[: 256 * 384].reshape(256, 384)
+    edges = det(img, 100, 200)
+    assert edges.dtype == np.uint8 and np.array_equal(edges, bits * 255)
+    hint, dmap = det.hint(img, 100, 200, num_samples=2)
+    assert hint.shape == (2, 3, 256, 384) and torch.equal(hint[1:].cpu(), canny_hint())
+    assert torch.equal(dmap.cpu(), torch.from_numpy(bits * 255).to(torch.uint8))
+    rng = np.random.default_rng(1)
+    for shape, lo, hi in (((64, 96, 3), 300, 700), ((37, 53, 3), 20, 60), ((40, 40), 100, 200), ((512, 512, 3), 250, 500),
+                          ((33, 1000, 1), 200, 100)):
+        a = rng.integers(0, 256, shape, dtype=np.uint8)
+        got = det(torch.from_numpy(a).to(cuda_device), lo, hi).cpu().numpy()
+        ref = canny_ref(a, lo, hi)
+        assert np.array_equal(got, ref), (shape, int((got != ref).sum()))
+    try:
+        import cv2
+        a = rng.integers(0, 256, (96, 128, 3), dtype=np.uint8)
+        a = cv2.GaussianBlur(a, (0, 0), 1.5)
+        assert np.array_equal(det(a, 30, 90), cv2.Canny(a, 30, 90))
+    except ImportError:
+        pass

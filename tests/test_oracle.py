@@ -126,3 +126,22 @@ def test_sampler_modes_and_vae_encoder_vs_reference():
         assert rel_l2(O.stochastic_encode(g["encode_x0"], g["stoch_t"], S=S, noise=g["stoch_noise"]), g["stoch_encoded"]) < 1e-6
         sd_enc = O.make_weights(O.vae_encoder_param_spec(vcfg), seed=1234, prefix="vae.")
         assert rel_l2(O.vae_encode(sd_enc, vcfg, g["enc_image"]), g["enc_moments"]) < 1e-5
+
+
+def test_canny_oracle_vs_cv2_and_fixture():
+    """oracle/canny_oracle.py against cv2.Canny itself (the third-party arithmetic behind annotator/canny) and against the
+    committed hint fixture (cv2.Canny of pictures_croped/bird_0.jpg as cv2.imread returns it, thresholds 100 / 200)."""
+    import os
+    from helpers import GOLDEN
+    from oracle.canny_oracle import canny
+    img = np.load(os.path.join(GOLDEN, "bird0_bgr.npy"))
+    bits = np.unpackbits(np.load(os.path.join(GOLDEN, "canny_bird0.npy")))[: 256 * 384].reshape(256, 384)
+    assert np.array_equal(canny(img, 100, 200), bits * 255)
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    cases = [(img, 100, 200), (img[:, :, 1].copy(), 50, 120)]
+    for shape in ((64, 96, 3), (37, 53, 3), (40, 40)):
+        noise = rng.integers(0, 256, shape, dtype=np.uint8)
+        cases += [(noise, 300, 700), (cv2.GaussianBlur(noise, (0, 0), 2.0), 20, 60)]
+    for a, lo, hi in cases:
+        assert np.array_equal(canny(a, lo, hi), cv2.Canny(a, lo, hi)), (a.shape, lo, hi)
