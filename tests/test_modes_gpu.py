@@ -228,3 +228,46 @@ def test_canny_bit_exact(cuda_device):
         assert np.array_equal(det(a, 30, 90), cv2.Canny(a, 30, 90))
     except ImportError:
         pass
+
+
+@pytest.mark.parametrize("guess_mode", [False, True])
+def test_process_pipeline(tiny, cuda_device, guess_mode):
+    """hackathon.process (canny2image_torch.py:28-70) end to end on the tiny model: image -> Canny hint -> seeded x_T ->
+    DDIM (engine path; generic path in guess mode) -> VAE decode -> uint8, against the oracle pipeline fed the SAME x_T
+    (drawn by the seeded CUDA generator, as the reference draws it)."""
+    import os
+    import numpy as np
+    from helpers import GOLDEN
+    from oracle.canny_oracle import canny as canny_ref
+    from stablediffusioneo_b200.canny2image import hackathon, seed_everything
+    model, _ = tiny
+    model.precision = "bf16"
+    dev = cuda_device
+    img = np.load(os.path.join(GOLDEN, "bird0_bgr.npy"))[64:128, 128:256].copy()          # 64 x 128 crop
+    _, cond_c, uncond_c = O.make_inputs(O.TINY, 1, 8, 16)
+    ctx_c, ctx_u = cond_c["c_crossattn"][0], uncond_c["c_crossattn"][0]
+    hk = hackathon()
+    hk.initialize(model=model, device=dev)
+    try:
+        out = hk.process(img, ctx_c, "", ctx_u, 1, 64, 4, guess_mode, 0.9, 9.0, 2946901, 0.0, 100, 200)
+        scales = list(model.control_scales)
+    finally:
+        model.control_scales = [1.0] * 13
+    assert len(out) == 1 and out[0].shape == (64, 128, 3) and out[0].dtype == np.uint8
+    # oracle pipeline
+    edges = canny_ref(img, 100, 200)
+    assert np.array_equal(hk.detected_map.cpu().numpy(), edges)
+    hint = torch.from_numpy(np.stack([edges] * 3, 0)[None].astype(np.float32) / 255.0)
+    seed_everything(2946901)
+    x_T = torch.randn((1, 4, 8, 16), device=dev).cpu()
+    sd_unet, sd_cn, sd_vae = oracle_weights(O.TINY, O.TINY_VAE)
+    eps_fn = lambda x, t, c: O.apply_model(sd_unet, sd_cn, O.TINY, x, t, c, control_scales=scales)
+    cond = {"c_concat": [hint], "c_crossattn": [ctx_c]}
+    un = {"c_concat": None if guess_mode else [hint], "c_crossattn": [ctx_u]}
+    with torch.no_grad():
+        lat, _ = O.ddim_sample(eps_fn, x_T, cond, un, S=4, scale=9.0)
+        ref = O.to_uint8_image(O.vae_decode(sd_vae, O.TINY_VAE, lat))[0]
+    diff = np.abs(out[0].astype(np.int32) - ref.astype(np.int32)).astype(np.float64)
+    psnr = 10 * np.log10(255.0 ** 2 / max((diff ** 2).mean(), 1e-12))
+    print(f"process() image vs oracle pipeline (guess_mode={guess_mode}): mean abs diff {diff.mean():.3f}, PSNR {psnr:.1f} dB")
+    assert psnr > 30.0
