@@ -37,7 +37,7 @@ LATENT_HW = (32, 48)
 CFG_SCALE = 9.0
 WORKLOAD = "ControlNet-canny SD1.5 256x384 batch 1, DDIM 20 steps, CFG 9.0 (BASELINE configs[1])"
 FLOPS_PER_STEP = 740.0e9          # one DDIM step = 2 x (ControlNet 95.6 + UNet 274.4) GF at 32x48
-CONV_DRAM_BYTES_PER_LAUNCH = 10284140  # ncu dram__bytes_read.sum + write.sum over one step's conv launches / launches
+CONV_DRAM_BYTES_PER_LAUNCH = 10287801  # ncu dram__bytes_read.sum + write.sum over one step's 289 conv launches / 289 (profiles/r01e_launches_step_summary.txt)
 WEIGHT_BYTES_PER_STEP = 2.442e9   # bf16 UNet 1.719 GB + ControlNet 0.723 GB, streamed once per step (cond+uncond batched)
 
 
