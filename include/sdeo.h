@@ -163,6 +163,11 @@ size_t sdeo_groupnorm_workspace_bytes(int32_t n, int32_t hw, int32_t groups);
 int sdeo_groupnorm_nhwc(const void* x1, const void* x2, int32_t x_f32, const float* gamma, const float* beta, void* y,
                         int32_t n, int32_t hw, int32_t c1, int32_t c2, int32_t groups, float eps,
                         int32_t with_silu, void* workspace, size_t workspace_bytes, void* stream);
+/* The plugin's exact I/O contract (groupNormPlugin.cpp:136-160): x / y fp16 NHWC (kHWC8), gamma / beta fp32, one tensor,
+ * optional Swish; workspace from sdeo_groupnorm_workspace_bytes. (eps IS applied, unlike groupNormKernel.cu:190-194.) */
+int sdeo_groupnorm_nhwc_f16(const void* x, const float* gamma, const float* beta, void* y, int32_t n, int32_t hw, int32_t c,
+                            int32_t groups, float eps, int32_t with_silu, void* workspace, size_t workspace_bytes,
+                            void* stream);
 /* Same normalisation with the statistics taken from the partials the producing convolutions left
  * (sdeo_conv_args::gn_stats): stats1 = fp32 [n][parts1][c1][2] for x1, stats2 likewise for x2 (NULL without x2). The
  * tensor is read once. Results match sdeo_groupnorm_nhwc up to fp32 summation order. */

@@ -4,6 +4,7 @@
 #include "host_util.h"
 #include "../../include/sdeo.h"
 #include <stdlib.h>
+#include <cuda_fp16.h>
 
 namespace sdeo {
 
@@ -19,6 +20,26 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* p, float* f) { unpack
 __device__ __forceinline__ void load8(const float* p, float* f) {
   const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
   f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// fp16 input (the TensorRT plugin's kHWC8 fp16 contract, groupNormPlugin.cpp:136-160)
+__device__ __forceinline__ void load8(const __half* p, float* f) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = __half22float2(h[j]);
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+// two outputs packed in the kernel's 16-bit output type: bf16, except fp16 in -> fp16 out
+template <typename T>
+__device__ __forceinline__ uint32_t pack2_out(float a, float b) { return pack_bf16x2(a, b); }
+template <>
+__device__ __forceinline__ uint32_t pack2_out<__half>(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
 }
 
 __device__ __forceinline__ void load8_ro(const float* p, float* f) {
@@ -209,8 +230,8 @@ gn_apply_kernel(const T* __restrict__ x1, const T* __restrict__ x2,
           f[u][j] = with_silu ? silu_f(t) : t;
         }
         uint4 o;
-        o.x = pack_bf16x2(f[u][0], f[u][1]); o.y = pack_bf16x2(f[u][2], f[u][3]);
-        o.z = pack_bf16x2(f[u][4], f[u][5]); o.w = pack_bf16x2(f[u][6], f[u][7]);
+        o.x = pack2_out<T>(f[u][0], f[u][1]); o.y = pack2_out<T>(f[u][2], f[u][3]);
+        o.z = pack2_out<T>(f[u][4], f[u][5]); o.w = pack2_out<T>(f[u][6], f[u][7]);
         *reinterpret_cast<uint4*>(y + ((long long)n * hw + pp + u * R) * C + v * 8) = o;
       }
     }
@@ -224,8 +245,8 @@ gn_apply_kernel(const T* __restrict__ x1, const T* __restrict__ x2,
         f[j] = with_silu ? silu_f(t) : t;
       }
       uint4 o;
-      o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-      o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+      o.x = pack2_out<T>(f[0], f[1]); o.y = pack2_out<T>(f[2], f[3]);
+      o.z = pack2_out<T>(f[4], f[5]); o.w = pack2_out<T>(f[6], f[7]);
       *reinterpret_cast<uint4*>(y + pix * C + v * 8) = o;
     }
   }
@@ -416,7 +437,12 @@ static int launch_gn_cluster(const void* x1, const void* x2, const float* gamma,
 static void gn_geometry(int n, int hw, int* chunks, int* ppc) {
   // about 1.5 CTAs per SM over the batch, and at least 16 pixels per CTA (these tensors are small: per-CTA fixed
   // costs and the apply kernel's per-CTA fold over the chunk partials dominate otherwise)
-  int want = (148 * 3 / 2 + n - 1) / n;
+  static int per_sm_x2 = -1;  // CTAs per SM (x2) over the batch; SDEO_GN_CTAS_X2 overrides (tuning aid)
+  if (per_sm_x2 < 0) {
+    const char* e = getenv("SDEO_GN_CTAS_X2");
+    per_sm_x2 = e ? atoi(e) : 3;
+  }
+  int want = (148 * per_sm_x2 / 2 + n - 1) / n;
   if (want < 1) want = 1;
   int p = (hw + want - 1) / want;
   if (p < 16) p = hw < 16 ? hw : 16;
@@ -670,6 +696,39 @@ extern "C" int sdeo_groupnorm_nhwc(const void* x1, const void* x2, int32_t x_f32
   return launch_k("groupnorm apply", gn_apply_kernel<__nv_bfloat16>, grid, dim3(kGNThreads), 0, st, one,
                   (const __nv_bfloat16*)x1, (const __nv_bfloat16*)x2, gamma, beta, (const float*)workspace,
                   (__nv_bfloat16*)y, hw, c1, c2, groups, chunks, ppc, eps, with_silu);
+}
+
+// The reference plugin's exact I/O contract: x / y fp16 NHWC ("kHWC8"), gamma / beta fp32, one tensor, optional Swish
+// (GroupNormPlugin::enqueue, groupNormPlugin.cpp:179-228). Two-pass grid (statistics + apply), fp32 statistics.
+extern "C" int sdeo_groupnorm_nhwc_f16(const void* x, const float* gamma, const float* beta, void* y, int32_t n, int32_t hw,
+                                       int32_t c, int32_t groups, float eps, int32_t with_silu, void* workspace,
+                                       size_t workspace_bytes, void* stream) {
+  if (!x || !gamma || !beta || !y || !workspace) return set_error(SDEO_EINVAL, "groupnorm_f16: null argument");
+  if (n <= 0 || n > 65535 || hw <= 0 || groups <= 0 || groups > 64 || c % groups != 0 || c % 8 != 0)
+    return set_error(SDEO_EINVAL, "groupnorm_f16: unsupported geometry (need C % groups == 0, C % 8 == 0, groups <= 64)");
+  int chunks, ppc;
+  gn_geometry(n, hw, &chunks, &ppc);
+  if (workspace_bytes < (size_t)n * chunks * groups * 2 * sizeof(float))
+    return set_error(SDEO_EINVAL, "groupnorm_f16: workspace too small");
+  const size_t smem = (size_t)(2 * c + kGNThreads * 16) * sizeof(float);
+  if (smem > 100 * 1024) return set_error(SDEO_EINVAL, "groupnorm_f16: too many channels");
+  if (smem > 48 * 1024) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      if (cudaFuncSetAttribute(gn_stats_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
+        return set_error(SDEO_ECUDA, "groupnorm_f16: cannot raise the shared-memory limit");
+      attr_set = true;
+    }
+  }
+  dim3 grid((unsigned)chunks, (unsigned)n);
+  cudaStream_t st = (cudaStream_t)stream;
+  const dim3 one(1, 1, 1);
+  int rc = launch_k("groupnorm_f16 stats", gn_stats_kernel<__half>, grid, dim3(kGNThreads), smem, st, one, (const __half*)x,
+                    (const __half*)nullptr, (float*)workspace, hw, c, 0, groups, chunks, ppc);
+  if (rc) return rc;
+  return launch_k("groupnorm_f16 apply", gn_apply_kernel<__half>, grid, dim3(kGNThreads), 0, st, one, (const __half*)x,
+                  (const __half*)nullptr, gamma, beta, (const float*)workspace, (__nv_bfloat16*)y, hw, c, 0, groups, chunks, ppc,
+                  eps, with_silu);
 }
 
 extern "C" int sdeo_groupnorm_apply_stats(const void* x1, const void* x2, int32_t x_f32, const float* stats1, int32_t parts1,

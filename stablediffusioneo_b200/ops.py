@@ -303,6 +303,22 @@ def groupnorm(x, gamma, beta, eps, silu, x2=None, groups=32, out=None, stats=Non
     return out
 
 
+def groupnorm_f16(x, gamma, beta, eps=1e-5, silu=False, groups=32):
+    """The TensorRT plugin's contract (groupNormPlugin.cpp:136-160): x fp16 NHWC [N,H,W,C] -> fp16, fp32 gamma / beta."""
+    lib = _lib.load()
+    _req(x, torch.float16, "x")
+    _req(gamma, torch.float32, "gamma")
+    _req(beta, torch.float32, "beta")
+    n, h, w, c = x.shape
+    out = torch.empty_like(x)
+    ws = _workspaces.gn(x.device, lib.sdeo_groupnorm_workspace_bytes(n, h * w, groups))
+    global LAUNCHES
+    check(lib.sdeo_groupnorm_nhwc_f16(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), n, h * w, c, groups, float(eps),
+                                      1 if silu else 0, _ptr(ws), ws.numel(), _stream()), "groupnorm_f16")
+    LAUNCHES += 1
+    return out
+
+
 def layernorm(x, gamma, beta, eps=1e-5):
     """x: bf16 or fp32 (residual stream) [..., C] -> bf16."""
     lib = _lib.load()

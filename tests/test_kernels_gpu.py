@@ -2,6 +2,7 @@
 Tolerances: outputs are bf16 (8 mantissa bits) from fp32 accumulation -> relative L2 <= 4e-3 per op
 (north_star's end-to-end bar for bf16 is 1e-2)."""
 import math
+import os
 
 import pytest
 import torch
@@ -510,3 +511,50 @@ def test_cfg_ddim_step(cuda_device):
     assert rel_l2(xp2, ref - sigma * noise) < 1e-5
     ops.counter_add(idx, 1)
     assert idx.item() == 2
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The TensorRT plugin's exact contract (fp16 NHWC in/out, fp32 gamma/beta, bSwish) against the REFERENCE's own CUDA
+# kernels, compiled stand-alone from /root/reference into oracle/_ref/libgroupnorm_ref.so (oracle/Makefile)
+# ---------------------------------------------------------------------------------------------------------------
+def _ref_groupnorm_lib():
+    import ctypes
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libgroupnorm_ref.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libgroupnorm_ref.so not built (needs the reference checkout at build time)")
+    lib = ctypes.CDLL(path)
+    lib.ref_groupnorm_workspace_bytes.restype = ctypes.c_size_t
+    lib.ref_groupnorm_enqueue.restype = ctypes.c_int
+    lib.ref_groupnorm_enqueue.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int32] * 5 + [ctypes.c_void_p] * 2
+    return lib
+
+
+@pytest.mark.parametrize("n,c,h,w,swish", [(2, 320, 32, 48, True), (2, 640, 16, 24, False), (2, 1280, 8, 12, True),
+                                           (1, 2560, 8, 12, True), (1, 1920, 16, 24, True), (2, 960, 32, 48, False),
+                                           (1, 512, 64, 96, True), (1, 256, 128, 192, True), (1, 128, 256, 384, True)])
+def test_groupnorm_f16_plugin_contract_vs_reference_kernels(cuda_device, n, c, h, w, swish):
+    """sdeo_groupnorm_nhwc_f16 vs GroupNormPlugin::enqueue's kernels (groupNormKernel.cu:49-266) on the UNet / VAE shapes the
+    plugin's cPerBlock table serves, and both vs torch in float64. The reference kernels ignore epsilon
+    (groupNormKernel.cu:190-194); with unit-scale inputs that is far below fp16 resolution."""
+    import torch.nn.functional as F
+    from stablediffusioneo_b200 import ops
+    ref_lib = _ref_groupnorm_lib()
+    dev = cuda_device
+    g = torch.Generator().manual_seed(c + h)
+    x = (torch.randn((n, h, w, c), generator=g) * 1.5 + 0.3).half()
+    gamma, beta = torch.randn((c,), generator=g) * 0.5 + 1.0, torch.randn((c,), generator=g) * 0.2
+    gold = F.group_norm(x.double().permute(0, 3, 1, 2), 32, gamma.double(), beta.double(), 1e-5)
+    gold = (F.silu(gold) if swish else gold).permute(0, 2, 3, 1)
+    xd, gd, bd = x.to(dev), gamma.to(dev), beta.to(dev)
+    ours = ops.groupnorm_f16(xd, gd, bd, eps=1e-5, silu=swish)
+    y_ref = torch.empty_like(xd)
+    ws = torch.empty(ref_lib.ref_groupnorm_workspace_bytes(), dtype=torch.uint8, device=dev)
+    rc = ref_lib.ref_groupnorm_enqueue(xd.data_ptr(), gd.data_ptr(), bd.data_ptr(), y_ref.data_ptr(), n, c, h, w, int(swish),
+                                       ws.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert ours.dtype == torch.float16
+    o, r, gold = ours.float().cpu(), y_ref.float().cpu(), gold.float()
+    e_ours, e_ref, e_pair = rel_l2(o, gold), rel_l2(r, gold), rel_l2(o, r)
+    print(f"GN fp16 {n}x{c}x{h}x{w}: ours vs f64 {e_ours:.2e}, reference kernels vs f64 {e_ref:.2e}, ours vs reference {e_pair:.2e}")
+    assert e_ours < 6e-4 and e_pair < 1e-3

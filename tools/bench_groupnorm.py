@@ -1,0 +1,83 @@
+"""GroupNorm(32)+Swish, fp16 NHWC (the TensorRT plugin's contract): this library's sdeo_groupnorm_nhwc_f16 next to the
+REFERENCE's own kernels (plugin/groupNormPlugin/groupNormKernel.cu compiled stand-alone into oracle/_ref, see
+oracle/Makefile) on the UNet and VAE shapes of the 256x384 workload and on the VAE shapes of BASELINE configs[4]
+(512x512). HBM roofline: 1 read + 1 write of the fp16 tensor = 4 bytes per element.
+python tools/bench_groupnorm.py [--iters N]. Inputs larger than L2 are timed as is; smaller ones with an L2 flush between
+iterations (a 256 MB memset), CUDA events around each launch."""
+import argparse
+import ctypes
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from stablediffusioneo_b200 import ops  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--only", default="")
+ap.add_argument("--no-ref", action="store_true")
+args = ap.parse_args()
+dev = torch.device("cuda:0")
+ref = None
+path = os.path.join(ROOT, "oracle", "_ref", "libgroupnorm_ref.so")
+if os.path.exists(path):
+    ref = ctypes.CDLL(path)
+    ref.ref_groupnorm_workspace_bytes.restype = ctypes.c_size_t
+    ref.ref_groupnorm_enqueue.restype = ctypes.c_int
+    ref.ref_groupnorm_enqueue.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int32] * 5 + [ctypes.c_void_p] * 2
+peak = 6445.0
+try:
+    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", peak))
+except (OSError, ValueError):
+    pass
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+# (label, n, c, h, w)
+CASES = [("unet 320@32x48 b2", 2, 320, 32, 48), ("unet 640@16x24 b2", 2, 640, 16, 24), ("unet 1280@8x12 b2", 2, 1280, 8, 12),
+         ("unet 2560@8x12 b2", 2, 2560, 8, 12), ("vae 512@64x96", 1, 512, 64, 96), ("vae 256@128x192", 1, 256, 128, 192),
+         ("vae 128@256x384", 1, 128, 256, 384), ("vae 512@128x128 b16", 16, 512, 128, 128),
+         ("vae 256@256x256 b16", 16, 256, 256, 256), ("vae 128@512x512 b16", 16, 128, 512, 512)]
+
+
+def timed(fn, nbytes):
+    fn()
+    torch.cuda.synchronize()
+    best, tot = 1e9, 0.0
+    for _ in range(args.iters):
+        if nbytes < (200 << 20):
+            flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        e.synchronize()
+        t = s.elapsed_time(e) * 1e3
+        best, tot = min(best, t), tot + t
+    return tot / args.iters, best
+
+
+print(f"HBM peak used for the fractions: {peak:.0f} GB/s (MEASURED_PEAKS.json or fallback)")
+for label, n, c, h, w in CASES:
+    if args.only and args.only not in label:
+        continue
+    x = (torch.randn((n, h, w, c), device=dev) * 1.5).half()
+    gamma, beta = torch.rand((c,), device=dev) + 0.5, torch.randn((c,), device=dev) * 0.1
+    nbytes = x.numel() * 4
+    ours_avg, ours_best = timed(lambda: ops.groupnorm_f16(x, gamma, beta, 1e-5, True), nbytes)
+    line = f"{label:24s} {nbytes / 1e6:8.1f} MB  ours {ours_avg:8.1f} us ({nbytes / ours_avg / 1e3:6.0f} GB/s, {nbytes / ours_avg / 1e3 / peak:4.0%} of HBM)"
+    if ref is not None and n <= 32 and not args.no_ref:
+        y = torch.empty_like(x)
+        ws = torch.empty(ref.ref_groupnorm_workspace_bytes(), dtype=torch.uint8, device=dev)
+        st = torch.cuda.current_stream().cuda_stream
+        call = lambda: ref.ref_groupnorm_enqueue(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), n, c, h, w, 1,
+                                                 ws.data_ptr(), st)
+        if call() == 0:
+            r_avg, _ = timed(call, nbytes)
+            line += f"   reference kernels {r_avg:8.1f} us ({nbytes / r_avg / 1e3:6.0f} GB/s)   speed-up {r_avg / ours_avg:4.2f}x"
+        else:
+            line += "   reference kernels: shape not supported"
+    print(line)
