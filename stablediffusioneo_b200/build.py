@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_C")
 LIB_PATH = os.path.join(OUT_DIR, "libsdeo.so")
-SOURCES = ["host_util.cu", "gemm_conv.cu", "attention.cu", "norm.cu", "elementwise.cu", "precise.cu", "canny.cu"]
+SOURCES = ["host_util.cu", "gemm_conv.cu", "attention.cu", "norm.cu", "groupnorm_stream.cu", "elementwise.cu", "precise.cu", "canny.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",

@@ -698,9 +698,15 @@ extern "C" int sdeo_groupnorm_nhwc(const void* x1, const void* x2, int32_t x_f32
                   (__nv_bfloat16*)y, hw, c1, c2, groups, chunks, ppc, eps, with_silu);
 }
 
-// The reference plugin's exact I/O contract: x / y fp16 NHWC ("kHWC8"), gamma / beta fp32, one tensor, optional Swish
-// (GroupNormPlugin::enqueue, groupNormPlugin.cpp:179-228). Two-pass grid (statistics + apply), fp32 statistics.
-extern "C" int sdeo_groupnorm_nhwc_f16(const void* x, const float* gamma, const float* beta, void* y, int32_t n, int32_t hw,
+// The plugin contract (fp16 NHWC in / out) as the two-launch grid (statistics + apply): the A/B partner and fallback of
+// the streamed kernel in groupnorm_stream.cu, which owns the C entry point sdeo_groupnorm_nhwc_f16.
+namespace sdeo {
+size_t groupnorm_two_pass_workspace_bytes(int32_t n, int32_t hw, int32_t groups) {
+  int chunks, ppc;
+  gn_geometry(n, hw, &chunks, &ppc);
+  return (size_t)n * chunks * groups * 2 * sizeof(float);
+}
+int groupnorm_f16_two_pass(const void* x, const float* gamma, const float* beta, void* y, int32_t n, int32_t hw,
                                        int32_t c, int32_t groups, float eps, int32_t with_silu, void* workspace,
                                        size_t workspace_bytes, void* stream) {
   if (!x || !gamma || !beta || !y || !workspace) return set_error(SDEO_EINVAL, "groupnorm_f16: null argument");
@@ -730,6 +736,7 @@ extern "C" int sdeo_groupnorm_nhwc_f16(const void* x, const float* gamma, const 
                   (const __half*)nullptr, gamma, beta, (const float*)workspace, (__nv_bfloat16*)y, hw, c, 0, groups, chunks, ppc,
                   eps, with_silu);
 }
+}  // namespace sdeo
 
 extern "C" int sdeo_groupnorm_apply_stats(const void* x1, const void* x2, int32_t x_f32, const float* stats1, int32_t parts1,
                                           const float* stats2, int32_t parts2, const float* gamma, const float* beta, void* y,

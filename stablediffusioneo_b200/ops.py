@@ -311,7 +311,7 @@ def groupnorm_f16(x, gamma, beta, eps=1e-5, silu=False, groups=32):
     _req(beta, torch.float32, "beta")
     n, h, w, c = x.shape
     out = torch.empty_like(x)
-    ws = _workspaces.gn(x.device, lib.sdeo_groupnorm_workspace_bytes(n, h * w, groups))
+    ws = _workspaces.gn(x.device, lib.sdeo_groupnorm_f16_workspace_bytes(n, h * w, c, groups))
     global LAUNCHES
     check(lib.sdeo_groupnorm_nhwc_f16(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), n, h * w, c, groups, float(eps),
                                       1 if silu else 0, _ptr(ws), ws.numel(), _stream()), "groupnorm_f16")

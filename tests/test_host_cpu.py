@@ -228,3 +228,33 @@ def test_engine_surface_shapes():
     assert list(cn)[:4] == ["x_noisy", "hint", "timestep", "context"] and len(cn) == 17
     assert cn["hint"] == (1, 3, 256, 384) and cn["context"] == (1, 77, 768)
     assert Engine(model, "decoder").shape_dict()["images"] == (1, 3, 256, 384)
+
+
+@pytest.mark.parametrize("n,c,h,w", [(2, 320, 32, 48), (2, 2560, 8, 12), (1, 128, 256, 384), (16, 256, 256, 256),
+                                     (3, 64, 7, 5), (1, 32, 1, 1), (5, 1280, 33, 17)])
+def test_groupnorm_f16_visit_schedule(n, c, h, w):
+    """The streamed GroupNorm's visit sequence (csrc/groupnorm_stream.cu): every tile gets exactly one statistics and one apply
+    visit, an apply visit comes after the statistics visits of EVERY tile of its sample (the no-deadlock argument rests on
+    this), tiles cover the sample, and the buffers fit the shared-memory budget."""
+    from stablediffusioneo_b200 import _lib
+    lib = _lib.load()
+    plan = (ctypes.c_int32 * 6)()
+    assert lib.sdeo_groupnorm_f16_plan(n, h * w, c, 32, 148, plan) == 0
+    chunks, ppc, lag, grid, smem, stride = list(plan)
+    hw = h * w
+    assert (chunks - 1) * ppc < hw <= chunks * ppc
+    assert stride % 128 == 0 and stride >= ppc * c * 2 and 4 * stride < smem <= 221 * 1024
+    tiles = n * chunks
+    assert 1 <= grid <= min(148, tiles) and chunks <= lag <= tiles
+    out = (ctypes.c_int32 * 2)()
+    stat_at, apply_at = {}, {}
+    for j in range(2 * tiles):
+        lib.sdeo_groupnorm_f16_ticket(j, tiles, lag, out)
+        d = apply_at if out[0] else stat_at
+        assert out[1] not in d and 0 <= out[1] < tiles
+        d[out[1]] = j
+    assert len(stat_at) == tiles and len(apply_at) == tiles
+    for t in range(tiles):
+        img = t // chunks
+        assert apply_at[t] > max(stat_at[u] for u in range(img * chunks, (img + 1) * chunks))
+    assert lib.sdeo_groupnorm_f16_workspace_bytes(n, hw, c, 32) >= tiles * 32 * 8 + n * 32 * 8 + (2 * n + 4) * 4

@@ -558,3 +558,45 @@ def test_groupnorm_f16_plugin_contract_vs_reference_kernels(cuda_device, n, c, h
     e_ours, e_ref, e_pair = rel_l2(o, gold), rel_l2(r, gold), rel_l2(o, r)
     print(f"GN fp16 {n}x{c}x{h}x{w}: ours vs f64 {e_ours:.2e}, reference kernels vs f64 {e_ref:.2e}, ours vs reference {e_pair:.2e}")
     assert e_ours < 6e-4 and e_pair < 1e-3
+
+
+@pytest.mark.parametrize("n,c,h,w,swish", [(3, 64, 7, 5, True), (1, 64, 1, 1, False), (5, 1280, 33, 17, True),
+                                           (4, 256, 128, 128, True), (2, 128, 250, 301, False), (40, 320, 16, 24, True)])
+@pytest.mark.parametrize("env", [{}, {"SDEO_GN_F16_HINTS": "1"}, {"SDEO_GN_F16_LAG": "0"}, {"SDEO_GN_F16_SWISH": "1"}])
+def test_groupnorm_f16_streamed_schedule_cases(cuda_device, n, c, h, w, swish, env):
+    """The streamed kernel (csrc/groupnorm_stream.cu) on ragged tiles (hw not a multiple of the tile), one-pixel samples, more
+    tiles than SMs, more samples than SMs per wave, called twice on one workspace (the call clears its own flags), with the
+    L2 hints forced on, with the smallest legal apply lag (applies wait on the ready flag) and with the fp32 Swish; against
+    torch in float64 and against the two-launch variant."""
+    import torch.nn.functional as F
+    from stablediffusioneo_b200 import ops
+    dev = cuda_device
+    g = torch.Generator().manual_seed(n * 1000 + c + h)
+    x = (torch.randn((n, h, w, c), generator=g) * 1.5 + 0.3).half()
+    x[:, :, :, : c // 32] *= 4.0  # one group per sample on a different scale: a mixed-up (mean, rstd) shows
+    gamma, beta = torch.randn((c,), generator=g) * 0.5 + 1.0, torch.randn((c,), generator=g) * 0.2
+    gold = F.group_norm(x.double().permute(0, 3, 1, 2), 32, gamma.double(), beta.double(), 1e-5)
+    gold = (F.silu(gold) if swish else gold).permute(0, 2, 3, 1).float()
+    xd, gd, bd = x.to(dev), gamma.to(dev), beta.to(dev)
+    keys = ("SDEO_GN_F16_HINTS", "SDEO_GN_F16_LAG", "SDEO_GN_F16_SWISH", "SDEO_GN_F16_TWO_PASS")
+    saved = {k: os.environ.pop(k, None) for k in keys}
+    try:
+        os.environ.update(env)
+        first = ops.groupnorm_f16(xd, gd, bd, eps=1e-5, silu=swish)
+        second = ops.groupnorm_f16(xd, gd, bd, eps=1e-5, silu=swish)
+        torch.cuda.synchronize()
+        os.environ["SDEO_GN_F16_TWO_PASS"] = "1"
+        two = ops.groupnorm_f16(xd, gd, bd, eps=1e-5, silu=swish)
+        torch.cuda.synchronize()
+    finally:
+        for k in keys:
+            os.environ.pop(k, None)
+            if saved[k] is not None:
+                os.environ[k] = saved[k]
+    assert torch.equal(first, second), "not deterministic across calls on one workspace"
+    o, t = first.float().cpu(), two.float().cpu()
+    assert torch.isfinite(o).all()
+    e_gold, e_two = rel_l2(o, gold), rel_l2(o, t)
+    worst = ((o - gold).abs() / (gold.abs() + 1.0)).max().item()
+    print(f"GN fp16 streamed {n}x{c}x{h}x{w} {env}: vs f64 {e_gold:.2e} (worst {worst:.2e}), vs two-launch {e_two:.2e}")
+    assert e_gold < 6e-4 and e_two < 6e-4 and worst < 4e-3
