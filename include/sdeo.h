@@ -166,16 +166,17 @@ int sdeo_groupnorm_nhwc(const void* x1, const void* x2, int32_t x_f32, const flo
 /* The plugin's exact I/O contract (groupNormPlugin.cpp:136-160, enqueue :179-228): x / y fp16 NHWC (kHWC8), gamma / beta
  * fp32, one tensor, optional Swish (bSwish). One persistent kernel: tiles staged in shared memory by bulk TMA copies,
  * statistics visit + apply visit per tile, the second read served from L2 (csrc/groupnorm_stream.cu). The workspace
- * (partials, per-sample (mean, rstd), arrival flags; replaces GroupNormPlugin::getWorkspaceSize :173-177) is sized by
- * sdeo_groupnorm_f16_workspace_bytes; its flag words are cleared by the call itself. eps IS applied, unlike
+ * (one 64-bit partial slot per CTA, sample and group; replaces GroupNormPlugin::getWorkspaceSize :173-177) is sized by
+ * sdeo_groupnorm_f16_workspace_bytes; the call presets the slots itself. eps IS applied, unlike
  * groupNormKernel.cu:190-194. */
 size_t sdeo_groupnorm_f16_workspace_bytes(int32_t n, int32_t hw, int32_t c, int32_t groups);
 /* Host-side view of that kernel's schedule (tests, tuning): plan[0..5] = tiles per sample, pixels per tile, apply lag in
  * tiles, grid size, dynamic shared memory bytes, tile buffer stride for `sms` SMs (<= 0: 148); returns 1 when the shape
- * falls back to the two-launch variant. sdeo_groupnorm_f16_ticket: ticket j -> out[0] = visit (0 statistics, 1 apply),
- * out[1] = tile. */
+ * falls back to the two-launch variant. sdeo_groupnorm_f16_visits: the visits CTA `cta` of `grid` makes, in order, as
+ * (kind, tile) pairs (kind 0 statistics, 1 apply); returns their number, writes at most `cap` pairs. Visits belong to
+ * units: unit u = statistics of tile u, then apply of tile u - lag; CTA b takes units b, b + grid, ... */
 int sdeo_groupnorm_f16_plan(int32_t n, int32_t hw, int32_t c, int32_t groups, int32_t sms, int32_t* plan);
-void sdeo_groupnorm_f16_ticket(int32_t j, int32_t tiles, int32_t lag, int32_t* out);
+int32_t sdeo_groupnorm_f16_visits(int32_t cta, int32_t grid, int32_t tiles, int32_t lag, int32_t* out, int32_t cap);
 int sdeo_groupnorm_nhwc_f16(const void* x, const float* gamma, const float* beta, void* y, int32_t n, int32_t hw, int32_t c,
                             int32_t groups, float eps, int32_t with_silu, void* workspace, size_t workspace_bytes,
                             void* stream);

@@ -3,16 +3,21 @@
 //
 // Layout: an NHWC sample is one contiguous byte range, so a TILE (ppc pixels x C channels) is a contiguous range too and
 // moves with 1-D bulk TMA copies (cp.async.bulk), no tensor map. Each tile is visited twice:
-//   visit 0 (statistics): HBM -> shared memory, per-group (sum, sum of squares) of the tile -> workspace; the CTA that
-//           delivers the LAST tile of a sample folds the sample's partials in fixed order (deterministic) into (mean, rstd)
-//           and raises the sample's ready flag;
-//   visit 1 (apply): tile -> shared memory again (an L2 hit: the visit order below keeps the re-read distance at about one
-//           sample + two tiles per SM), normalise + affine (+ Swish) in place, shared memory -> HBM with a bulk store.
-// Visits are numbered in one global sequence ("tickets"): statistics of tile s, then apply of tile s - lag; CTA b takes
-// tickets b, b + G, b + 2G, ... in order. An apply visit only ever waits for statistics visits with LOWER ticket numbers
-// and a statistics visit never waits, so with the G <= #SM CTAs co-resident the lowest unfinished ticket can always run:
-// no deadlock for any tile count. Loads run kGSBufs - 1 tiles ahead of the arithmetic (mbarrier per buffer), stores drain
-// behind it (bulk groups): HBM traffic is 1 read + 1 write of the tensor (4 bytes per element) while the sample fits L2.
+//   visit 0 (statistics): HBM -> shared memory, per-group (sum, sum of squares) of the tile, accumulated in registers over
+//           the tiles this CTA takes of one sample and PUBLISHED once per (CTA, sample) as self-validating 64-bit slots
+//           (see slot_publish): no fence, no atomic, no flag on the arithmetic threads' path;
+//   visit 1 (apply): tile -> shared memory again (an L2 hit while `lag` tiles of input + output fit L2), normalise +
+//           affine (+ Swish) in place, shared memory -> HBM with a bulk store. The control warp folds the sample's slots
+//           (<= one per CTA) in slot order into (mean, rstd) the first time the CTA meets the sample: deterministic.
+// Visits are grouped in UNITS: unit u = statistics of tile u (u < tiles) then apply of tile u - lag (u >= lag); CTA b takes
+// units b, b + G, b + 2G, ... in order, so every CTA carries the same mix of (light) statistics and (heavy) apply visits and
+// the re-read distance stays at `lag` tiles. An apply visit only waits for statistics visits in LOWER units (lag >= tiles per
+// sample) and a statistics visit never waits, so with the G <= #SM CTAs co-resident the lowest unfinished visit can always
+// run: no deadlock for any tile count. One control warp per CTA recycles the kGSBufs tile buffers (empty / full mbarriers),
+// issues the loads bufs - 1 visits ahead and supplies the sample's (mean, rstd) row; the 512 arithmetic threads never
+// wait on global memory.
+// Stores drain behind the arithmetic (bulk groups): HBM traffic is 1 read + 1 write of the tensor (4 bytes per element)
+// while `lag` tiles of input and output fit L2.
 #include "common.cuh"
 #include "host_util.h"
 #include "../../include/sdeo.h"
@@ -21,9 +26,10 @@
 
 namespace sdeo {
 
-constexpr int kGSThreads = 512;
-constexpr int kGSBufs = 4;
-constexpr int kGSSmemTotal = 227 * 1024 - 6 * 1024;  // dynamic shared memory budget (static arrays take the rest)
+constexpr int kGSThreads = 512;             // arithmetic threads
+constexpr int kGSAll = kGSThreads + 32;     // + one control warp (loads, buffer recycling, ready flags)
+constexpr int kGSMaxBufs = 8;               // tile buffers per CTA: GSGeom::bufs of them are used
+constexpr int kGSSmemTotal = 227 * 1024 - 7 * 1024;  // dynamic shared memory budget (static arrays take the rest)
 constexpr unsigned long long kL2EvictFirst = 0x12F0000000000000ull;  // createpolicy.fractional.L2::evict_first, fraction 1.0
 
 __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar, bool evict_first) {
@@ -46,15 +52,6 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
-__device__ __forceinline__ int ld_acquire(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release(int* p, int v) {
-  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 
 __device__ __forceinline__ void h8_to_f(const uint4& u, float* f) {
   const __half2* h = reinterpret_cast<const __half2*>(&u);
@@ -95,236 +92,257 @@ __device__ __forceinline__ uint32_t swish_pack(float t0, float t1) {
 }
 
 struct GSGeom {
-  int n, hw, C, groups, chunks, ppc, lag, tile_stride;  // tile_stride: bytes between tile buffers (multiple of 128)
+  int n, hw, C, groups, chunks, ppc, lag, bufs, tile_stride;  // tile_stride: bytes between tile buffers (multiple of 128)
 };
 
-// ticket j -> (visit, tile): tickets 0 .. lag-1 are statistics of tiles 0 .. lag-1; then pairs (statistics s, apply s - lag);
-// then the last `lag` applies.
-__host__ __device__ __forceinline__ void gs_decode(int j, int tiles, int lag, int* visit, int* tile) {
-  if (j < lag) {
-    *visit = 0;
-    *tile = j;
-    return;
+// A CTA's position in the visit sequence: unit u, visit v (0 statistics of tile u, 1 apply of tile u - lag).
+struct GSIter {
+  int u, v;
+};
+// moves `it` to the first existing visit at or after (u, v) among the units u, u + G, ...; false when the CTA is done
+__host__ __device__ __forceinline__ bool gs_settle(GSIter& it, int tiles, int lag, int G) {
+  while (it.u < tiles + lag) {
+    if (it.v == 0) {
+      if (it.u < tiles) return true;
+      it.v = 1;
+    }
+    if (it.u >= lag) return true;
+    it.u += G;
+    it.v = 0;
   }
-  const int pairs = 2 * (tiles - lag);
-  const int r = j - lag;
-  if (r < pairs) {
-    const int s = lag + (r >> 1);
-    *visit = r & 1;
-    *tile = (r & 1) ? s - lag : s;
-    return;
+  return false;
+}
+__host__ __device__ __forceinline__ bool gs_next(GSIter& it, int tiles, int lag, int G) {
+  if (it.v == 0) {
+    it.v = 1;
+  } else {
+    it.u += G;
+    it.v = 0;
   }
-  *visit = 1;
-  *tile = (r - pairs) + tiles - lag;
+  return gs_settle(it, tiles, lag, G);
+}
+
+// One published partial: (sum, sum of squares) of one group over the tiles ONE CTA took of one sample, as one 64-bit word
+// (a naturally aligned 64-bit scalar store is single-copy atomic). The call presets every slot to all-ones; a slot whose
+// high word is still 0xFFFFFFFF has not been written. Self-validating slots need no fence, no counter and no flag: the
+// writer's other stores never have to be ordered against this one.
+__device__ __forceinline__ void slot_publish(unsigned long long* p, float s, float q) {
+  uint32_t hi = __float_as_uint(q);
+  if (hi == 0xFFFFFFFFu) hi = 0x7FFFFFFFu;  // a NaN sum keeps meaning "NaN", never "empty"
+  const unsigned long long v = ((unsigned long long)hi << 32) | (unsigned long long)__float_as_uint(s);
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long slot_peek(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
 }
 
 template <int kMode>
-__global__ void __launch_bounds__(kGSThreads, 1)
+__global__ void __launch_bounds__(kGSAll, 1)
 gn_stream_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                 __half* __restrict__ y, float* __restrict__ part_ws, float2* __restrict__ final_ws, int* __restrict__ flags,
-                 GSGeom gm, float eps, int hints) {
+                 __half* __restrict__ y, unsigned long long* __restrict__ slots, GSGeom gm, float eps, int hints) {
   griddep_launch_dependents();
   griddep_wait();
   extern __shared__ __align__(128) unsigned char gs_smem[];
-  __shared__ __align__(8) uint64_t bars[kGSBufs];
-  __shared__ float2 s_mr[64];
-  __shared__ float2 s_fold[kGSThreads];
-  __shared__ int s_last;
+  __shared__ __align__(8) uint64_t full[kGSMaxBufs];   // tile (and, for an apply visit, its (mean, rstd) row) has landed
+  __shared__ __align__(8) uint64_t empty[kGSMaxBufs];  // the arithmetic threads and the bulk store are done with the buffer
+  __shared__ float2 s_mr[kGSMaxBufs][32];
   const int tid = threadIdx.x;
-  const int C = gm.C, hw = gm.hw, groups = gm.groups, chunks = gm.chunks, ppc = gm.ppc;
+  const int C = gm.C, hw = gm.hw, groups = gm.groups, chunks = gm.chunks, ppc = gm.ppc, lag = gm.lag;
   const int cv = C / 8, cpg = C / groups;
-  const int tiles = gm.n * chunks, total = 2 * tiles, G = gridDim.x;
-  float* chan = reinterpret_cast<float*>(gs_smem + (size_t)kGSBufs * gm.tile_stride);  // [cv][16]: 8 sums, 8 sums of squares
-  float* part = chan + 2 * C;                                                             // [R][cols][16]
-  float* part2 = part + kGSThreads * 16;                                                  // [nparts][S], S * nparts <= 512
-  int* arrived = flags;
-  int* ready = flags + gm.n;
-
-  const int cols = cv < kGSThreads ? cv : kGSThreads;
-  const int R = kGSThreads / cols;
-  const int tr = tid / cols, tv = tid % cols;
-  const bool active = tid < R * cols;
-  const int S = cols * 16;
+  const int tiles = gm.n * chunks, G = gridDim.x, kGSBufs = gm.bufs;
+  const int P = chunks < G ? chunks : G;  // partials per sample: one per CTA that takes tiles of it
 
   if (tid == 0) {
-    for (int b = 0; b < kGSBufs; ++b) mbar_init(&bars[b], 1);
+    for (int b = 0; b < kGSBufs; ++b) {
+      mbar_init(&full[b], 1);
+      mbar_init(&empty[b], 1);
+    }
     fence_mbar_init();
   }
   __syncthreads();
 
-  auto issue = [&](int j, int buf) {  // thread 0: start the load of ticket j's tile into buffer buf
-    int visit, tile;
-    gs_decode(j, tiles, gm.lag, &visit, &tile);
-    const int img = tile / chunks, ch = tile - img * chunks;
-    const int p0 = ch * ppc;
-    const int rows = min(ppc, hw - p0);
-    const uint32_t bytes = (uint32_t)rows * (uint32_t)C * 2u;
-    mbar_expect_tx(&bars[buf], bytes);
-    bulk_load(gs_smem + (size_t)buf * gm.tile_stride, x + ((long long)img * hw + p0) * C, bytes, &bars[buf],
-              hints && visit == 1);
-  };
-
-  if (tid == 0) {
-    for (int i = 0; i < kGSBufs - 1; ++i) {
-      const int j = blockIdx.x + i * G;
-      if (j < total) issue(j, i);
+  if (tid >= kGSThreads) {
+    // ---- control warp: buffer recycling, tile loads, the sample's (mean, rstd) row for apply visits ----
+    const int lane = tid - kGSThreads;
+    GSIter it{(int)blockIdx.x, 0};
+    int k = 0, cur_img = -1;
+    float2 my_mr = make_float2(0.f, 1.f);  // lane = group: (mean, rstd) of sample cur_img
+    for (bool ok = gs_settle(it, tiles, lag, G); ok; ok = gs_next(it, tiles, lag, G), ++k) {
+      const int buf = k % kGSBufs, use = k / kGSBufs;
+      if (use > 0) mbar_wait(&empty[buf], (uint32_t)(use - 1) & 1u);
+      const int tile = it.v ? it.u - lag : it.u;
+      const int img = tile / chunks, ch = tile - img * chunks;
+      const int p0 = ch * ppc;
+      const int rows = min(ppc, hw - p0);
+      const uint32_t bytes = (uint32_t)rows * (uint32_t)C * 2u;
+      // the copy may complete before the expect_tx below: the phase cannot close while this warp's arrival is pending
+      if (lane == 0)
+        bulk_load(gs_smem + (size_t)buf * gm.tile_stride, x + ((long long)img * hw + p0) * C, bytes, &full[buf],
+                  (hints & 1) && it.v == 1);
+      if (it.v == 1) {
+        if (img != cur_img && !(hints & 0x100)) {
+          // First apply visit of this CTA in sample img: fold the sample's P partials in slot order (the same order in
+          // every CTA: deterministic). Their writers' statistics visits all lie in LOWER units (lag >= tiles per sample).
+          float fs = 0.f, fq = 0.f;
+          if (lane < groups) {
+            const unsigned long long* base = slots + (size_t)img * P * groups + lane;
+            const long long t0 = clock64();
+            for (int j0 = 0; j0 < P; j0 += 8) {
+              unsigned long long v[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = j0 + i < P ? slot_peek(base + (size_t)(j0 + i) * groups) : 0ull;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (j0 + i >= P) break;
+                uint32_t spins = 0;
+                while ((uint32_t)(v[i] >> 32) == 0xFFFFFFFFu) {
+                  __nanosleep(32);
+                  if ((++spins & 0xFFFu) == 0 && clock64() - t0 > 4000000000LL) {
+                    printf("sdeo: groupnorm_f16 waited too long for sample %d partial %d (block %d)\n", img, j0 + i, (int)blockIdx.x);
+                    __trap();
+                  }
+                  v[i] = slot_peek(base + (size_t)(j0 + i) * groups);
+                }
+                fs += __uint_as_float((uint32_t)v[i]);
+                fq += __uint_as_float((uint32_t)(v[i] >> 32));
+              }
+            }
+            const float inv = 1.0f / ((float)hw * (float)cpg);
+            const float mean = fs * inv;
+            float var = fq * inv - mean * mean;
+            var = var < 0.f ? 0.f : var;
+            my_mr = make_float2(mean, rsqrtf(var + eps));
+          }
+          cur_img = img;
+        }
+        if (lane < groups) s_mr[buf][lane] = my_mr;
+        __syncwarp();
+      }
+      if (lane == 0) mbar_expect_tx(&full[buf], bytes);  // arrive (releases the s_mr row) + expect the tile's bytes
     }
+    return;
   }
-  uint32_t phases = 0;
+
+  // ---- arithmetic threads ----
+  float* chan = reinterpret_cast<float*>(gs_smem + (size_t)kGSBufs * gm.tile_stride);  // [cv][16]: 8 sums, 8 sums of squares
+  float* part = chan + 2 * C;                                                             // [R][cols][16]
+  float* part2 = part + kGSThreads * 16;                                                  // [nparts][S], S * nparts <= 512
+  const int cols = cv;  // <= kGSThreads (host check)
+  const int R = kGSThreads / cols;
+  const int tr = tid / cols, tv = tid % cols;
+  const bool active = tid < R * cols;
+  const int S = cols * 16;
+  const int nparts = S >= kGSThreads ? 1 : min(R, kGSThreads / S);
+  const int gfirst = (tv * 8) / cpg, rfirst = tv * 8 - gfirst * cpg;
+
+  GSIter it{(int)blockIdx.x, 0};
   int k = 0;
-  for (int j = blockIdx.x; j < total; j += G, ++k) {
+  bool prev_apply = false;
+  float acc_s = 0.f, acc_q = 0.f;  // threads 0 .. groups-1: this CTA's running (sum, sum of squares) of the current sample
+  for (bool ok = gs_settle(it, tiles, lag, G); ok; ok = gs_next(it, tiles, lag, G), ++k) {
     const int buf = k % kGSBufs;
-    int visit, tile;
-    gs_decode(j, tiles, gm.lag, &visit, &tile);
+    const uint32_t parity = (uint32_t)(k / kGSBufs) & 1u;
+    const int tile = it.v ? it.u - lag : it.u;
     const int img = tile / chunks, ch = tile - img * chunks;
     const int p0 = ch * ppc;
     const int rows = min(ppc, hw - p0);
     __half* tp = reinterpret_cast<__half*>(gs_smem + (size_t)buf * gm.tile_stride);
 
-    if (visit == 1) {
-      // the sample's statistics: published by the CTA that delivered the sample's last statistics tile
-      if (tid == 0) {
-        if (ld_acquire(ready + img) == 0) {
-          const long long t0 = clock64();
-          uint32_t spins = 0;
-          while (ld_acquire(ready + img) == 0) {
-            __nanosleep(64);
-            if ((++spins & 0xFFFu) == 0 && clock64() - t0 > 4000000000LL) {
-              printf("sdeo: groupnorm_f16 waited too long for sample %d (block %d)\n", img, (int)blockIdx.x);
-              __trap();
-            }
-          }
-        }
-      }
-      __syncthreads();
-      if (tid < groups) s_mr[tid] = __ldcg(final_ws + (size_t)img * groups + tid);
-    }
-    mbar_wait(&bars[buf], (phases >> buf) & 1u);
-    phases ^= 1u << buf;
-    if (visit == 1) __syncthreads();  // s_mr
-
-    if (visit == 0) {
+    if (it.v == 0) {
+      mbar_wait(&full[buf], parity);
       // ---- per-channel (sum, sum of squares) of this tile ----
-      for (int vbase = 0; vbase < cv; vbase += cols) {
-        const int v = vbase + tv;
-        float s[8], q[8];
+      float s[8], q[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { s[u] = 0.f; q[u] = 0.f; }
-        if (active && v < cv) {
-          int pp = tr;
-          for (; pp + R < rows; pp += 2 * R) {
-            float f0[8], f1[8];
-            h8_to_f(*reinterpret_cast<const uint4*>(tp + (size_t)pp * C + v * 8), f0);
-            h8_to_f(*reinterpret_cast<const uint4*>(tp + (size_t)(pp + R) * C + v * 8), f1);
+      for (int u = 0; u < 8; ++u) { s[u] = 0.f; q[u] = 0.f; }
+      if (active && !(hints & 0x1000)) {
+        int pp = tr;
+        for (; pp + R < rows; pp += 2 * R) {
+          float f0[8], f1[8];
+          h8_to_f(*reinterpret_cast<const uint4*>(tp + (size_t)pp * C + tv * 8), f0);
+          h8_to_f(*reinterpret_cast<const uint4*>(tp + (size_t)(pp + R) * C + tv * 8), f1);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              s[u] += f0[u] + f1[u];
-              q[u] += f0[u] * f0[u] + f1[u] * f1[u];
-            }
-          }
-          if (pp < rows) {
-            float f0[8];
-            h8_to_f(*reinterpret_cast<const uint4*>(tp + (size_t)pp * C + v * 8), f0);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) { s[u] += f0[u]; q[u] += f0[u] * f0[u]; }
+          for (int u = 0; u < 8; ++u) {
+            s[u] += f0[u] + f1[u];
+            q[u] += f0[u] * f0[u] + f1[u] * f1[u];
           }
         }
-        if (active) {
-          float4* dst = reinterpret_cast<float4*>(part + (size_t)tr * S + tv * 16);
-          dst[0] = make_float4(s[0], s[1], s[2], s[3]);
-          dst[1] = make_float4(s[4], s[5], s[6], s[7]);
-          dst[2] = make_float4(q[0], q[1], q[2], q[3]);
-          dst[3] = make_float4(q[4], q[5], q[6], q[7]);
+        if (pp < rows) {
+          float f0[8];
+          h8_to_f(*reinterpret_cast<const uint4*>(tp + (size_t)pp * C + tv * 8), f0);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { s[u] += f0[u]; q[u] += f0[u] * f0[u]; }
         }
-        __syncthreads();
-        // fold the R pixel rows with every thread: scalar i = column * 16 + slot, rows split in nparts interleaved parts
-        // (fixed order: deterministic)
-        const int nparts = S >= kGSThreads ? 1 : min(R, kGSThreads / S);
-        for (int idx = tid; idx < S * nparts; idx += kGSThreads) {
-          const int i = idx % S, rp = idx / S;
+      }
+      if (active) {
+        float4* dst = reinterpret_cast<float4*>(part + (size_t)tr * S + tv * 16);
+        dst[0] = make_float4(s[0], s[1], s[2], s[3]);
+        dst[1] = make_float4(s[4], s[5], s[6], s[7]);
+        dst[2] = make_float4(q[0], q[1], q[2], q[3]);
+        dst[3] = make_float4(q[4], q[5], q[6], q[7]);
+      }
+      bar_sync(1, kGSThreads);
+      if (tid == 0) mbar_arrive(&empty[buf]);  // the tile itself is no longer needed
+      // fold the R pixel rows with every thread: scalar i = column * 16 + slot, rows split in nparts interleaved parts
+      // (fixed order: deterministic)
+      for (int idx = tid; idx < S * nparts; idx += kGSThreads) {
+        const int i = idx % S, rp = idx / S;
+        float acc = 0.f;
+        for (int r = rp; r < R; r += nparts) acc += part[(size_t)r * S + i];
+        if (nparts == 1) chan[i] = acc;
+        else part2[rp * S + i] = acc;
+      }
+      if (nparts > 1) {
+        bar_sync(1, kGSThreads);
+        for (int i = tid; i < S; i += kGSThreads) {
           float acc = 0.f;
-          for (int r = rp; r < R; r += nparts) acc += part[(size_t)r * S + i];
-          if (nparts == 1) chan[vbase * 16 + i] = acc;
-          else part2[rp * S + i] = acc;
+          for (int rp = 0; rp < nparts; ++rp) acc += part2[rp * S + i];
+          chan[i] = acc;
         }
-        if (nparts > 1) {
-          __syncthreads();
-          for (int i = tid; i < S; i += kGSThreads) {
-            float acc = 0.f;
-            for (int rp = 0; rp < nparts; ++rp) acc += part2[rp * S + i];
-            chan[vbase * 16 + i] = acc;
-          }
-        }
-        __syncthreads();
       }
+      bar_sync(1, kGSThreads);
       if (tid < groups) {
-        float s = 0.f, q = 0.f;
+        float gs = 0.f, gq = 0.f;
         for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) {
-          s += chan[(c >> 3) * 16 + (c & 7)];
-          q += chan[(c >> 3) * 16 + 8 + (c & 7)];
+          gs += chan[(c >> 3) * 16 + (c & 7)];
+          gq += chan[(c >> 3) * 16 + 8 + (c & 7)];
         }
-        *reinterpret_cast<float2*>(part_ws + ((size_t)tile * groups + tid) * 2) = make_float2(s, q);
-        __threadfence();
-      }
-      __syncthreads();
-      if (tid == 0) s_last = (atomicAdd(arrived + img, 1) == chunks - 1);
-      __syncthreads();
-      if (s_last) {
-        // this CTA delivered the sample's last tile: fold the sample's partials in fixed order, publish (mean, rstd)
-        __threadfence();
-        const int L = kGSThreads / groups;
-        const int g = tid % groups, lane = tid / groups;
-        float s = 0.f, q = 0.f;
-        if (lane < L) {
-          for (int c2 = lane; c2 < chunks; c2 += L) {
-            const float2 p2 = __ldcg(reinterpret_cast<const float2*>(part_ws + (((size_t)img * chunks + c2) * groups + g) * 2));
-            s += p2.x;
-            q += p2.y;
-          }
+        acc_s += gs;
+        acc_q += gq;
+        // this CTA's next statistics tile is it.u + G: publish when that one belongs to another sample (or does not exist)
+        const int nxt = it.u + G;
+        if (nxt >= tiles || nxt / chunks != img) {
+          int j = ((int)blockIdx.x - img * chunks) % G;
+          if (j < 0) j += G;
+          slot_publish(slots + ((size_t)img * P + j) * groups + tid, acc_s, acc_q);
+          acc_s = 0.f;
+          acc_q = 0.f;
         }
-        s_fold[tid] = make_float2(s, q);
-        __syncthreads();
-        if (tid < groups) {
-          s = 0.f;
-          q = 0.f;
-          for (int l = 0; l < L; ++l) {
-            s += s_fold[l * groups + tid].x;
-            q += s_fold[l * groups + tid].y;
-          }
-          const float inv = 1.0f / ((float)hw * (float)cpg);
-          const float mean = s * inv;
-          float var = q * inv - mean * mean;
-          var = var < 0.f ? 0.f : var;
-          final_ws[(size_t)img * groups + tid] = make_float2(mean, rsqrtf(var + eps));
-          __threadfence();
-        }
-        __syncthreads();
-        if (tid == 0) st_release(ready + img, 1);
       }
     } else {
       // ---- normalise + affine (+ Swish) in place ----
-      for (int vbase = 0; vbase < cv; vbase += cols) {
-        const int v = vbase + tv;
-        if (!active || v >= cv) continue;
-        float a[8], b[8];
-        {
-          const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8) + 1);
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8) + 1);
-          a[0] = g0.x; a[1] = g0.y; a[2] = g0.z; a[3] = g0.w; a[4] = g1.x; a[5] = g1.y; a[6] = g1.z; a[7] = g1.w;
-          b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
-          int g = (v * 8) / cpg, r = v * 8 - g * cpg;
+      float a[8], b[8];
+      if (active) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + tv * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + tv * 8) + 1);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + tv * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + tv * 8) + 1);
+        a[0] = g0.x; a[1] = g0.y; a[2] = g0.z; a[3] = g0.w; a[4] = g1.x; a[5] = g1.y; a[6] = g1.z; a[7] = g1.w;
+        b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+      }
+      mbar_wait(&full[buf], parity);
+      if (active && !(hints & 0x800)) {
+        int g = gfirst, r = rfirst;
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const float2 mr = s_mr[g];
-            a[u] *= mr.y;
-            b[u] -= mr.x * a[u];
-            if (++r == cpg) { r = 0; ++g; }
-          }
+        for (int u = 0; u < 8; ++u) {
+          const float2 mr = s_mr[buf][g];
+          a[u] *= mr.y;
+          b[u] -= mr.x * a[u];
+          if (++r == cpg) { r = 0; ++g; }
         }
         int pp = tr;
         for (; pp + R < rows; pp += 2 * R) {
-          uint4* p0v = reinterpret_cast<uint4*>(tp + (size_t)pp * C + v * 8);
-          uint4* p1v = reinterpret_cast<uint4*>(tp + (size_t)(pp + R) * C + v * 8);
+          uint4* p0v = reinterpret_cast<uint4*>(tp + (size_t)pp * C + tv * 8);
+          uint4* p1v = reinterpret_cast<uint4*>(tp + (size_t)(pp + R) * C + tv * 8);
           float f0[8], f1[8];
           h8_to_f(*p0v, f0);
           h8_to_f(*p1v, f1);
@@ -342,7 +360,7 @@ gn_stream_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, 
           *p1v = o1;
         }
         if (pp < rows) {
-          uint4* p0v = reinterpret_cast<uint4*>(tp + (size_t)pp * C + v * 8);
+          uint4* p0v = reinterpret_cast<uint4*>(tp + (size_t)pp * C + tv * 8);
           float f0[8];
           h8_to_f(*p0v, f0);
 #pragma unroll
@@ -354,25 +372,37 @@ gn_stream_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, 
         }
       }
       fence_proxy_async_smem();  // the in-place results are read by the bulk store (async proxy)
+      bar_sync(1, kGSThreads);
+      if (tid == 0 && !(hints & 0x400)) bulk_store(y + ((long long)img * hw + p0) * C, tp, (uint32_t)rows * (uint32_t)C * 2u, (hints & 1) != 0);
     }
-    __syncthreads();  // every thread is done with buffer `buf` (and with the one the next load lands in)
     if (tid == 0) {
-      if (visit == 1)
-        bulk_store(y + ((long long)img * hw + p0) * C, tp, (uint32_t)rows * (uint32_t)C * 2u, hints != 0);
-      bulk_commit();        // one group per ticket (empty for statistics visits)
-      bulk_wait_read<1>();  // the store of the PREVIOUS ticket has left its buffer: that buffer takes the next load
-      const int jn = j + (kGSBufs - 1) * G;
-      if (jn < total) issue(jn, (k + kGSBufs - 1) % kGSBufs);
+      bulk_commit();        // one group per visit (empty for statistics visits)
+      bulk_wait_read<1>();  // the store of the PREVIOUS visit has left its buffer
+      if (prev_apply) mbar_arrive(&empty[(k + kGSBufs - 1) % kGSBufs]);
     }
+    prev_apply = it.v == 1;
   }
   if (tid == 0) bulk_wait_all();
 }
 
-// tile geometry: `chunks` tiles of `ppc` pixels per sample
+// tuning switches (read per call): SDEO_GN_F16_BUFS = tile buffers per CTA (2..8, default 4), SDEO_GN_F16_TILE_KB = upper
+// bound of a tile in KB (default: what the buffers allow)
+static int gs_env_int(const char* name, int dflt, int lo, int hi) {
+  const char* e = getenv(name);
+  if (!e) return dflt;
+  const int v = atoi(e);
+  return v < lo ? lo : (v > hi ? hi : v);
+}
+
 static int gs_geometry(int n, int hw, int c, int sms, GSGeom* g, size_t* smem) {
+  // large tensors: fewer, larger tiles (the per-visit costs weigh more than the extra look-ahead); small ones: 4 buffers
+  const int kGSBufs = gs_env_int("SDEO_GN_F16_BUFS", (long long)n * hw * c * 2 > (64LL << 20) ? 3 : 4, 2, kGSMaxBufs);
+  const size_t tile_kb = (size_t)gs_env_int("SDEO_GN_F16_TILE_KB", 1024, 1, 1024);
+  if (c % 8 != 0 || c / 8 > kGSThreads) return -1;  // one 8-channel vector column per arithmetic thread
   const size_t aux = ((size_t)2 * c + kGSThreads * 16 + 512) * sizeof(float);
   if (aux + (size_t)kGSBufs * c * 2 > (size_t)kGSSmemTotal) return -1;
-  const size_t tile_cap = ((kGSSmemTotal - aux) / kGSBufs) & ~(size_t)127;
+  size_t tile_cap = ((kGSSmemTotal - aux) / kGSBufs) & ~(size_t)127;
+  if (tile_cap > tile_kb * 1024 && tile_kb * 1024 >= (size_t)c * 2) tile_cap = tile_kb * 1024;
   const int ppc_cap = (int)(tile_cap / ((size_t)c * 2));
   int ppc_min = (int)((4096 + (size_t)c * 2 - 1) / ((size_t)c * 2));  // >= 4 KB per tile
   if (ppc_min > ppc_cap) ppc_min = ppc_cap;
@@ -385,7 +415,7 @@ static int gs_geometry(int n, int hw, int c, int sms, GSGeom* g, size_t* smem) {
     ppc = (hw + ch - 1) / ch;
   }
   if (ppc > hw) ppc = hw;
-  g->n = n; g->hw = hw; g->C = c;
+  g->n = n; g->hw = hw; g->C = c; g->bufs = kGSBufs;
   g->ppc = ppc;
   g->chunks = (hw + ppc - 1) / ppc;
   g->tile_stride = (int)((((size_t)ppc * c * 2) + 127) & ~(size_t)127);
@@ -397,7 +427,7 @@ static int gs_geometry(int n, int hw, int c, int sms, GSGeom* g, size_t* smem) {
 static int gs_plan(int n, int hw, int c, int groups, int sms, int lag_env, GSGeom* g, size_t* smem, int* grid) {
   if (gs_geometry(n, hw, c, sms, g, smem)) return -1;
   const long long tiles = (long long)n * g->chunks;
-  if (tiles > (1 << 29)) return -1;
+  if (tiles > (1 << 29) || groups > 32) return -1;  // the (mean, rstd) row is fetched by one warp
   g->groups = groups;
   const int G = (int)(tiles < sms ? tiles : sms);
   // apply lag: a sample's statistics tiles plus two rounds of the grid, so that the statistics an apply visit needs are
@@ -443,8 +473,8 @@ extern "C" size_t sdeo_groupnorm_f16_workspace_bytes(int32_t n, int32_t hw, int3
     sms = dev_sms;
   (void)cudaGetLastError();
   if (gs_geometry(n, hw, c, sms, &g, &smem)) return two_pass;
-  const size_t stream_bytes = (size_t)n * g.chunks * groups * 2 * sizeof(float) + (size_t)n * groups * sizeof(float2) +
-                              ((size_t)2 * n + 4) * sizeof(int);
+  const size_t parts = (size_t)(g.chunks < sms ? g.chunks : sms);  // partial slots per sample (<= grid size)
+  const size_t stream_bytes = (size_t)n * parts * groups * sizeof(unsigned long long);
   return stream_bytes > two_pass ? stream_bytes : two_pass;
 }
 
@@ -459,12 +489,19 @@ extern "C" int sdeo_groupnorm_f16_plan(int32_t n, int32_t hw, int32_t c, int32_t
   plan[0] = g.chunks; plan[1] = g.ppc; plan[2] = g.lag; plan[3] = G; plan[4] = (int32_t)smem; plan[5] = g.tile_stride;
   return 0;
 }
-// ticket j of the visit sequence -> out[0] = visit (0 statistics, 1 apply), out[1] = tile
-extern "C" void sdeo_groupnorm_f16_ticket(int32_t j, int32_t tiles, int32_t lag, int32_t* out) {
-  int visit, tile;
-  gs_decode(j, tiles, lag, &visit, &tile);
-  out[0] = visit;
-  out[1] = tile;
+// visits of CTA `cta` of `grid`, in order: out[2 i] = visit kind (0 statistics, 1 apply), out[2 i + 1] = tile; returns the count
+// (at most `cap` pairs are written). The kernel walks the same iterator.
+extern "C" int32_t sdeo_groupnorm_f16_visits(int32_t cta, int32_t grid, int32_t tiles, int32_t lag, int32_t* out, int32_t cap) {
+  if (cta < 0 || grid <= 0 || cta >= grid || tiles <= 0 || lag <= 0 || lag > tiles) return 0;
+  GSIter it{cta, 0};
+  int32_t cnt = 0;
+  for (bool ok = gs_settle(it, tiles, lag, grid); ok; ok = gs_next(it, tiles, lag, grid), ++cnt) {
+    if (out && cnt < cap) {
+      out[2 * cnt] = it.v;
+      out[2 * cnt + 1] = it.v ? it.u - lag : it.u;
+    }
+  }
+  return cnt;
 }
 
 // x / y fp16 NHWC, gamma / beta fp32, one tensor, optional Swish (GroupNormPlugin::enqueue, groupNormPlugin.cpp:179-228;
@@ -491,17 +528,11 @@ extern "C" int sdeo_groupnorm_nhwc_f16(const void* x, const float* gamma, const 
   int G = 0;
   if (two_pass || gs_plan(n, hw, c, groups, gs_sm_count(), lag_env, &g, &smem, &G))
     return groupnorm_f16_two_pass(x, gamma, beta, y, n, hw, c, groups, eps, with_silu, workspace, workspace_bytes, stream);
-  const long long tiles = (long long)n * g.chunks;
-  const size_t part_bytes = (size_t)tiles * groups * 2 * sizeof(float);
-  const size_t final_bytes = (size_t)n * groups * sizeof(float2);
-  const size_t flag_bytes = ((size_t)2 * n + 4) * sizeof(int);
-  if (workspace_bytes < part_bytes + final_bytes + flag_bytes)
+  const size_t slot_bytes = (size_t)n * (size_t)(g.chunks < G ? g.chunks : G) * groups * sizeof(unsigned long long);
+  if (workspace_bytes < slot_bytes)
     return set_error(SDEO_EINVAL, "groupnorm_f16: workspace too small (sdeo_groupnorm_f16_workspace_bytes)");
-  float* part_ws = (float*)workspace;
-  float2* final_ws = (float2*)((char*)workspace + part_bytes);
-  int* flags = (int*)((char*)workspace + part_bytes + final_bytes);
   cudaStream_t st = (cudaStream_t)stream;
-  if (cudaMemsetAsync(flags, 0, flag_bytes, st) != cudaSuccess) {
+  if (cudaMemsetAsync(workspace, 0xFF, slot_bytes, st) != cudaSuccess) {  // every partial slot: "not written"
     (void)cudaGetLastError();
     return set_error(SDEO_ECUDA, "groupnorm_f16: cudaMemsetAsync failed");
   }
@@ -518,6 +549,6 @@ extern "C" int sdeo_groupnorm_nhwc_f16(const void* x, const float* gamma, const 
   const dim3 one(1, 1, 1);
   const int mode = with_silu ? swish_mode : 0;
   auto fn = mode == 0 ? gn_stream_kernel<0> : (mode == 1 ? gn_stream_kernel<1> : gn_stream_kernel<2>);
-  return launch_k("groupnorm_f16 (streamed)", fn, dim3((unsigned)G), dim3(kGSThreads), smem, st, one, (const __half*)x, gamma,
-                  beta, (__half*)y, part_ws, final_ws, flags, g, eps, hints);
+  return launch_k("groupnorm_f16 (streamed)", fn, dim3((unsigned)G), dim3(kGSAll), smem, st, one, (const __half*)x, gamma,
+                  beta, (__half*)y, (unsigned long long*)workspace, g, eps, hints);
 }

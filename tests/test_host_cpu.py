@@ -233,9 +233,9 @@ def test_engine_surface_shapes():
 @pytest.mark.parametrize("n,c,h,w", [(2, 320, 32, 48), (2, 2560, 8, 12), (1, 128, 256, 384), (16, 256, 256, 256),
                                      (3, 64, 7, 5), (1, 32, 1, 1), (5, 1280, 33, 17)])
 def test_groupnorm_f16_visit_schedule(n, c, h, w):
-    """The streamed GroupNorm's visit sequence (csrc/groupnorm_stream.cu): every tile gets exactly one statistics and one apply
-    visit, an apply visit comes after the statistics visits of EVERY tile of its sample (the no-deadlock argument rests on
-    this), tiles cover the sample, and the buffers fit the shared-memory budget."""
+    """The streamed GroupNorm's visit schedule (csrc/groupnorm_stream.cu): every tile gets exactly one statistics and one apply
+    visit, the per-CTA sequences never deadlock on the per-sample ready flags, apply visits are spread evenly over the CTAs,
+    tiles cover the sample, and the buffers fit the shared-memory budget."""
     from stablediffusioneo_b200 import _lib
     lib = _lib.load()
     plan = (ctypes.c_int32 * 6)()
@@ -246,15 +246,42 @@ def test_groupnorm_f16_visit_schedule(n, c, h, w):
     assert stride % 128 == 0 and stride >= ppc * c * 2 and 4 * stride < smem <= 221 * 1024
     tiles = n * chunks
     assert 1 <= grid <= min(148, tiles) and chunks <= lag <= tiles
-    out = (ctypes.c_int32 * 2)()
-    stat_at, apply_at = {}, {}
-    for j in range(2 * tiles):
-        lib.sdeo_groupnorm_f16_ticket(j, tiles, lag, out)
-        d = apply_at if out[0] else stat_at
-        assert out[1] not in d and 0 <= out[1] < tiles
-        d[out[1]] = j
-    assert len(stat_at) == tiles and len(apply_at) == tiles
-    for t in range(tiles):
-        img = t // chunks
-        assert apply_at[t] > max(stat_at[u] for u in range(img * chunks, (img + 1) * chunks))
-    assert lib.sdeo_groupnorm_f16_workspace_bytes(n, hw, c, 32) >= tiles * 32 * 8 + n * 32 * 8 + (2 * n + 4) * 4
+    # replay the kernel's schedule: CTA b walks its visits in order; an apply visit may only wait for statistics visits that
+    # a round-robin over CTAs (one visit each, blocked applies skipped) eventually completes -> no deadlock, all tiles served
+    cap = 2 * tiles // grid + 8
+    seqs = []
+    for b_ in range(grid):
+        out = (ctypes.c_int32 * (2 * cap))()
+        cnt = lib.sdeo_groupnorm_f16_visits(b_, grid, tiles, lag, out, cap)
+        assert 0 < cnt <= cap
+        seqs.append([(out[2 * i], out[2 * i + 1]) for i in range(cnt)])
+    # partial slots: CTA b writes slot (b - sample * chunks) mod grid of every sample it takes statistics tiles of; the
+    # slots of a sample are exactly 0 .. min(chunks, grid) - 1, each written by one CTA
+    for img in range(n):
+        js = sorted((b_ - img * chunks) % grid for b_ in range(grid) if any(k_ == 0 and t_ // chunks == img for k_, t_ in seqs[b_]))
+        assert js == list(range(min(chunks, grid)))
+    kinds = [sum(1 for v in s_ if v[0] == 1) for s_ in seqs]
+    assert max(kinds) - min(kinds) <= 1, "apply visits are not balanced over the CTAs"
+    pos = [0] * grid
+    stats_done, applied, seen_stats = [0] * n, set(), set()
+    progress = True
+    while progress:
+        progress = False
+        for b_ in range(grid):
+            if pos[b_] == len(seqs[b_]):
+                continue
+            kind, t = seqs[b_][pos[b_]]
+            assert 0 <= t < tiles
+            if kind == 0:
+                assert t not in seen_stats
+                seen_stats.add(t)
+                stats_done[t // chunks] += 1  # a CTA publishes its partial right after its last statistics tile of the sample
+            else:
+                if stats_done[t // chunks] < chunks:
+                    continue  # the control warp spins on a partial slot that is not written yet
+                assert t not in applied
+                applied.add(t)
+            pos[b_] += 1
+            progress = True
+    assert len(seen_stats) == tiles and len(applied) == tiles, "schedule deadlocks or skips tiles"
+    assert lib.sdeo_groupnorm_f16_workspace_bytes(n, hw, c, 32) >= n * min(chunks, grid) * 32 * 8
