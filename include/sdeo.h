@@ -170,13 +170,18 @@ int sdeo_groupnorm_nhwc(const void* x1, const void* x2, int32_t x_f32, const flo
  * sdeo_groupnorm_f16_workspace_bytes; the call presets the slots itself. eps IS applied, unlike
  * groupNormKernel.cu:190-194. */
 size_t sdeo_groupnorm_f16_workspace_bytes(int32_t n, int32_t hw, int32_t c, int32_t groups);
-/* Host-side view of that kernel's schedule (tests, tuning): plan[0..5] = tiles per sample, pixels per tile, apply lag in
- * tiles, grid size, dynamic shared memory bytes, tile buffer stride for `sms` SMs (<= 0: 148); returns 1 when the shape
+/* Host-side view of that kernel's schedule (tests, tuning): plan[0..6] = tiles per sample, pixels per tile, apply lag in
+ * tiles, grid size, dynamic shared memory bytes, tile buffer stride, tile buffers for `sms` SMs (<= 0: 148); returns 1 when the shape
  * falls back to the two-launch variant. sdeo_groupnorm_f16_visits: the visits CTA `cta` of `grid` makes, in order, as
  * (kind, tile) pairs (kind 0 statistics, 1 apply); returns their number, writes at most `cap` pairs. Visits belong to
  * units: unit u = statistics of tile u, then apply of tile u - lag; CTA b takes units b, b + grid, ... */
 int sdeo_groupnorm_f16_plan(int32_t n, int32_t hw, int32_t c, int32_t groups, int32_t sms, int32_t* plan);
 int32_t sdeo_groupnorm_f16_visits(int32_t cta, int32_t grid, int32_t tiles, int32_t lag, int32_t* out, int32_t cap);
+/* Which kernel sdeo_groupnorm_nhwc_f16 runs for a geometry on a device with `sms` SMs and clusters of up to `max_cluster`
+ * CTAs (<= 0: 148 / 8): 2 = resident (the sample lives in the shared memory of one thread-block cluster: one read and one
+ * write from anywhere, no workspace; info[0..2] = cluster size, pixel rows per CTA, shared memory bytes), 0 = streamed,
+ * 1 = two launches. */
+int sdeo_groupnorm_f16_variant(int32_t n, int32_t hw, int32_t c, int32_t groups, int32_t sms, int32_t max_cluster, int32_t* info);
 int sdeo_groupnorm_nhwc_f16(const void* x, const float* gamma, const float* beta, void* y, int32_t n, int32_t hw, int32_t c,
                             int32_t groups, float eps, int32_t with_silu, void* workspace, size_t workspace_bytes,
                             void* stream);

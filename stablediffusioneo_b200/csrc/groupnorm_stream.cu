@@ -189,12 +189,12 @@ gn_stream_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, 
           if (lane < groups) {
             const unsigned long long* base = slots + (size_t)img * P * groups + lane;
             const long long t0 = clock64();
-            for (int j0 = 0; j0 < P; j0 += 8) {
-              unsigned long long v[8];
+            for (int j0 = 0; j0 < P; j0 += 16) {
+              unsigned long long v[16];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = j0 + i < P ? slot_peek(base + (size_t)(j0 + i) * groups) : 0ull;
+              for (int i = 0; i < 16; ++i) v[i] = j0 + i < P ? slot_peek(base + (size_t)(j0 + i) * groups) : 0ull;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
+              for (int i = 0; i < 16; ++i) {
                 if (j0 + i >= P) break;
                 uint32_t spins = 0;
                 while ((uint32_t)(v[i] >> 32) == 0xFFFFFFFFu) {
@@ -385,6 +385,220 @@ gn_stream_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, 
   if (tid == 0) bulk_wait_all();
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Resident variant, for samples that fit the shared memory of one thread-block cluster: cluster = sample, CTA rank r keeps
+// pixel rows [r * rpc, (r + 1) * rpc) in shared memory for the whole call. HBM -> shared memory once (kRChunks bulk copies,
+// statistics start when the first lands), per-group sums exchanged through distributed shared memory (every CTA folds the
+// ranks in rank order: deterministic), normalise in place, shared memory -> HBM chunk by chunk. One read + one write of the
+// tensor from anywhere, no workspace, no second launch.
+// ---------------------------------------------------------------------------------------------------------------------
+static int gs_env_int_fwd(const char* name, int dflt, int lo, int hi);
+constexpr int kRChunks = 4;
+struct RGeom {
+  int n, hw, C, groups, cs, rpc, tile_bytes;
+};
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float2 ld_cluster_f2(const void* local_smem, uint32_t rank) {
+  uint32_t ra;
+  float2 v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_smem)), "r"(rank));
+  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(ra) : "memory");
+  return v;
+}
+
+template <int kMode>
+__global__ void __launch_bounds__(kGSThreads, 1)
+gn_resident_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   __half* __restrict__ y, RGeom gm, float eps) {
+  griddep_launch_dependents();
+  griddep_wait();
+  extern __shared__ __align__(128) unsigned char gs_smem[];
+  __shared__ __align__(8) uint64_t bars[kRChunks];
+  __shared__ float2 s_group[32];
+  __shared__ float2 s_mr[32];
+  const int tid = threadIdx.x;
+  const int C = gm.C, hw = gm.hw, groups = gm.groups;
+  const int cv = C / 8, cpg = C / groups;
+  const uint32_t rank = cluster_rank();
+  const int img = blockIdx.x / gm.cs;
+  const int r0 = (int)rank * gm.rpc;
+  const int rows = max(0, min(gm.rpc, hw - r0));
+  const int rch = (rows + kRChunks - 1) / kRChunks;  // rows per chunk
+  __half* tile = reinterpret_cast<__half*>(gs_smem);
+  float* chan = reinterpret_cast<float*>(gs_smem + gm.tile_bytes);  // [cv][16]
+  float* part = chan + 2 * C;                                        // [R][cols][16]
+  float* part2 = part + kGSThreads * 16;
+  const int cols = cv, R = kGSThreads / cols;
+  const int tr = tid / cols, tv = tid % cols;
+  const bool active = tid < R * cols;
+  const int S = cols * 16;
+  const int nparts = S >= kGSThreads ? 1 : min(R, kGSThreads / S);
+
+  if (tid == 0) {
+    for (int c = 0; c < kRChunks; ++c) mbar_init(&bars[c], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const long long base = ((long long)img * hw + r0) * C;
+  if (tid == 0) {
+    for (int c = 0; c < kRChunks; ++c) {
+      const int cr = min(rch, rows - c * rch);
+      if (cr <= 0) break;
+      const uint32_t bytes = (uint32_t)cr * (uint32_t)C * 2u;
+      mbar_expect_tx(&bars[c], bytes);
+      bulk_load(tile + (size_t)c * rch * C, x + base + (long long)c * rch * C, bytes, &bars[c], false);
+    }
+  }
+  float a[8], b[8];
+  if (active) {
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + tv * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + tv * 8) + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + tv * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + tv * 8) + 1);
+    a[0] = g0.x; a[1] = g0.y; a[2] = g0.z; a[3] = g0.w; a[4] = g1.x; a[5] = g1.y; a[6] = g1.z; a[7] = g1.w;
+    b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+  }
+  // ---- statistics of this CTA's rows ----
+  float s[8], q[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) { s[u] = 0.f; q[u] = 0.f; }
+  for (int c = 0; c < kRChunks; ++c) {
+    const int cr = min(rch, rows - c * rch);
+    if (cr <= 0) break;
+    mbar_wait(&bars[c], 0);
+    if (active) {
+      const __half* tp = tile + (size_t)c * rch * C + tv * 8;
+      int pp = tr;
+      for (; pp + R < cr; pp += 2 * R) {
+        float f0[8], f1[8];
+        h8_to_f(*reinterpret_cast<const uint4*>(tp + (size_t)pp * C), f0);
+        h8_to_f(*reinterpret_cast<const uint4*>(tp + (size_t)(pp + R) * C), f1);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          s[u] += f0[u] + f1[u];
+          q[u] += f0[u] * f0[u] + f1[u] * f1[u];
+        }
+      }
+      if (pp < cr) {
+        float f0[8];
+        h8_to_f(*reinterpret_cast<const uint4*>(tp + (size_t)pp * C), f0);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { s[u] += f0[u]; q[u] += f0[u] * f0[u]; }
+      }
+    }
+  }
+  if (active) {
+    float4* dst = reinterpret_cast<float4*>(part + (size_t)tr * S + tv * 16);
+    dst[0] = make_float4(s[0], s[1], s[2], s[3]);
+    dst[1] = make_float4(s[4], s[5], s[6], s[7]);
+    dst[2] = make_float4(q[0], q[1], q[2], q[3]);
+    dst[3] = make_float4(q[4], q[5], q[6], q[7]);
+  }
+  __syncthreads();
+  for (int idx = tid; idx < S * nparts; idx += kGSThreads) {
+    const int i = idx % S, rp = idx / S;
+    float acc = 0.f;
+    for (int r = rp; r < R; r += nparts) acc += part[(size_t)r * S + i];
+    if (nparts == 1) chan[i] = acc;
+    else part2[rp * S + i] = acc;
+  }
+  if (nparts > 1) {
+    __syncthreads();
+    for (int i = tid; i < S; i += kGSThreads) {
+      float acc = 0.f;
+      for (int rp = 0; rp < nparts; ++rp) acc += part2[rp * S + i];
+      chan[i] = acc;
+    }
+  }
+  __syncthreads();
+  if (tid < groups) {
+    float gs = 0.f, gq = 0.f;
+    for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) {
+      gs += chan[(c >> 3) * 16 + (c & 7)];
+      gq += chan[(c >> 3) * 16 + 8 + (c & 7)];
+    }
+    s_group[tid] = make_float2(gs, gq);
+  }
+  cluster_sync_all();  // every rank's s_group is written
+  if (tid < groups) {
+    float fs = 0.f, fq = 0.f;
+    for (int r = 0; r < gm.cs; ++r) {  // rank order, the same in every CTA
+      const float2 p2 = ld_cluster_f2(&s_group[tid], (uint32_t)r);
+      fs += p2.x;
+      fq += p2.y;
+    }
+    const float inv = 1.0f / ((float)hw * (float)cpg);
+    const float mean = fs * inv;
+    float var = fq * inv - mean * mean;
+    var = var < 0.f ? 0.f : var;
+    s_mr[tid] = make_float2(mean, rsqrtf(var + eps));
+  }
+  __syncthreads();
+  // ---- normalise + affine (+ Swish) in place, chunk by chunk; each chunk leaves as soon as it is done ----
+  if (active) {
+    int g = (tv * 8) / cpg, r = tv * 8 - g * cpg;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float2 mr = s_mr[g];
+      a[u] *= mr.y;
+      b[u] -= mr.x * a[u];
+      if (++r == cpg) { r = 0; ++g; }
+    }
+  }
+  for (int c = 0; c < kRChunks; ++c) {
+    const int cr = min(rch, rows - c * rch);
+    if (cr <= 0) break;
+    if (active) {
+      __half* tp = tile + (size_t)c * rch * C + tv * 8;
+      for (int pp = tr; pp < cr; pp += R) {
+        uint4* pv = reinterpret_cast<uint4*>(tp + (size_t)pp * C);
+        float f0[8];
+        h8_to_f(*pv, f0);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) f0[u] = f0[u] * a[u] + b[u];
+        uint4 o0;
+        o0.x = swish_pack<kMode>(f0[0], f0[1]); o0.y = swish_pack<kMode>(f0[2], f0[3]);
+        o0.z = swish_pack<kMode>(f0[4], f0[5]); o0.w = swish_pack<kMode>(f0[6], f0[7]);
+        *pv = o0;
+      }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      bulk_store(y + base + (long long)c * rch * C, tile + (size_t)c * rch * C, (uint32_t)cr * (uint32_t)C * 2u, false);
+      bulk_commit();
+    }
+  }
+  if (tid == 0) bulk_wait_all();
+  cluster_sync_all();  // peers may read this CTA's s_group until here
+}
+
+// cluster size + rows per CTA of the resident variant; non-zero when the sample does not fit `max_cs` CTAs
+static int gr_plan(int n, int hw, int c, int groups, int sms, int max_cs, RGeom* g, size_t* smem) {
+  if (c % 8 != 0 || c / 8 > kGSThreads || groups > 32 || c % groups != 0) return -1;
+  const size_t aux = ((size_t)2 * c + kGSThreads * 16 + 512) * sizeof(float);
+  if (aux + (size_t)c * 2 > (size_t)kGSSmemTotal) return -1;
+  const size_t cap = (kGSSmemTotal - aux) & ~(size_t)127;
+  const size_t row = (size_t)c * 2;
+  int cs = 1;
+  while (cs <= max_cs && (size_t)((hw + cs - 1) / cs) * row > cap) cs *= 2;
+  if (cs > max_cs) return -1;
+  // more CTAs per sample while SMs are idle and a CTA still has a worthwhile piece
+  while (cs * 2 <= max_cs && (long long)n * cs * 2 <= sms && (size_t)((hw + cs - 1) / cs) * row > (size_t)(24 << 10)) cs *= 2;
+  const int force = gs_env_int_fwd("SDEO_GN_F16_CLUSTER", 0, 0, 16);
+  if (force && (force & (force - 1)) == 0 && force <= max_cs && (size_t)((hw + force - 1) / force) * row <= cap) cs = force;
+  g->n = n; g->hw = hw; g->C = c; g->groups = groups; g->cs = cs;
+  g->rpc = (hw + cs - 1) / cs;
+  g->tile_bytes = (int)(((size_t)g->rpc * row + 127) & ~(size_t)127);
+  *smem = (size_t)g->tile_bytes + aux;
+  return 0;
+}
+
 // tuning switches (read per call): SDEO_GN_F16_BUFS = tile buffers per CTA (2..8, default 4), SDEO_GN_F16_TILE_KB = upper
 // bound of a tile in KB (default: what the buffers allow)
 static int gs_env_int(const char* name, int dflt, int lo, int hi) {
@@ -393,6 +607,7 @@ static int gs_env_int(const char* name, int dflt, int lo, int hi) {
   const int v = atoi(e);
   return v < lo ? lo : (v > hi ? hi : v);
 }
+static int gs_env_int_fwd(const char* name, int dflt, int lo, int hi) { return gs_env_int(name, dflt, lo, hi); }
 
 static int gs_geometry(int n, int hw, int c, int sms, GSGeom* g, size_t* smem) {
   // large tensors: fewer, larger tiles (the per-visit costs weigh more than the extra look-ahead); small ones: 4 buffers
@@ -451,6 +666,42 @@ static int gs_sm_count() {
   return sms;
 }
 
+// Largest usable cluster: 16 (non-portable) when the device can host at least one such cluster of full-size CTAs, else 8.
+// Also raises the kernels' dynamic shared memory limit (first call).
+static int gr_max_cluster() {
+  static int max_cs = 0;
+  if (max_cs) return max_cs;
+  int best = 8;
+  bool ok = true;
+  void (*fns[3])(const __half*, const float*, const float*, __half*, RGeom, float) = {gn_resident_kernel<0>, gn_resident_kernel<1>,
+                                                                                     gn_resident_kernel<2>};
+  for (int i = 0; i < 3; ++i)
+    ok = ok && cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kGSSmemTotal) == cudaSuccess;
+  if (ok && !getenv("SDEO_GN_F16_NO_CLUSTER16")) {
+    bool np = true;
+    for (int i = 0; i < 3; ++i)
+      np = np && cudaFuncSetAttribute(fns[i], cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    if (np) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(16, 1, 1);
+      cfg.blockDim = dim3(kGSThreads, 1, 1);
+      cfg.dynamicSmemBytes = kGSSmemTotal;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 16;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      int nclusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, fns[2], &cfg) == cudaSuccess && nclusters >= 1) best = 16;
+    }
+  }
+  (void)cudaGetLastError();
+  max_cs = ok ? best : 1;
+  return max_cs;
+}
+
 int groupnorm_f16_two_pass(const void* x, const float* gamma, const float* beta, void* y, int32_t n, int32_t hw, int32_t c,
                            int32_t groups, float eps, int32_t with_silu, void* workspace, size_t workspace_bytes, void* stream);
 size_t groupnorm_two_pass_workspace_bytes(int32_t n, int32_t hw, int32_t groups);
@@ -478,15 +729,15 @@ extern "C" size_t sdeo_groupnorm_f16_workspace_bytes(int32_t n, int32_t hw, int3
   return stream_bytes > two_pass ? stream_bytes : two_pass;
 }
 
-// Host-side view of the schedule (tests): plan[0..5] = tiles per sample, pixels per tile, apply lag (tiles),
-// grid size, dynamic shared memory bytes, tile buffer stride; returns non-zero when the shape falls back to two launches.
+// Host-side view of the schedule (tests): plan[0..6] = tiles per sample, pixels per tile, apply lag (tiles),
+// grid size, dynamic shared memory bytes, tile buffer stride, tile buffers; returns non-zero when the shape falls back to two launches.
 extern "C" int sdeo_groupnorm_f16_plan(int32_t n, int32_t hw, int32_t c, int32_t groups, int32_t sms, int32_t* plan) {
   if (!plan || n <= 0 || hw <= 0 || c <= 0 || groups <= 0 || c % 8 != 0) return set_error(SDEO_EINVAL, "groupnorm_f16_plan: bad argument");
   GSGeom g;
   size_t smem = 0;
   int G = 0;
   if (gs_plan(n, hw, c, groups, sms > 0 ? sms : 148, -1, &g, &smem, &G)) return 1;
-  plan[0] = g.chunks; plan[1] = g.ppc; plan[2] = g.lag; plan[3] = G; plan[4] = (int32_t)smem; plan[5] = g.tile_stride;
+  plan[0] = g.chunks; plan[1] = g.ppc; plan[2] = g.lag; plan[3] = G; plan[4] = (int32_t)smem; plan[5] = g.tile_stride; plan[6] = g.bufs;
   return 0;
 }
 // visits of CTA `cta` of `grid`, in order: out[2 i] = visit kind (0 statistics, 1 apply), out[2 i + 1] = tile; returns the count
@@ -502,6 +753,23 @@ extern "C" int32_t sdeo_groupnorm_f16_visits(int32_t cta, int32_t grid, int32_t 
     }
   }
   return cnt;
+}
+
+// which kernel a call with this geometry runs on a device with `sms` SMs and clusters of up to `max_cluster` CTAs (<= 0: 148 / 8):
+// 2 resident (info[0] = cluster size, info[1] = pixel rows per CTA, info[2] = shared memory bytes), 0 streamed, 1 two launches
+extern "C" int sdeo_groupnorm_f16_variant(int32_t n, int32_t hw, int32_t c, int32_t groups, int32_t sms, int32_t max_cluster,
+                                          int32_t* info) {
+  if (n <= 0 || hw <= 0 || c <= 0 || groups <= 0 || c % 8 != 0 || c % groups != 0) return set_error(SDEO_EINVAL, "groupnorm_f16_variant: bad argument");
+  RGeom rg;
+  size_t rsmem = 0;
+  if (gr_plan(n, hw, c, groups, sms > 0 ? sms : 148, max_cluster > 0 ? max_cluster : 8, &rg, &rsmem) == 0) {
+    if (info) { info[0] = rg.cs; info[1] = rg.rpc; info[2] = (int32_t)rsmem; }
+    return 2;
+  }
+  GSGeom g;
+  size_t smem = 0;
+  int G = 0;
+  return gs_plan(n, hw, c, groups, sms > 0 ? sms : 148, -1, &g, &smem, &G) ? 1 : 0;
 }
 
 // x / y fp16 NHWC, gamma / beta fp32, one tensor, optional Swish (GroupNormPlugin::enqueue, groupNormPlugin.cpp:179-228;
@@ -523,6 +791,20 @@ extern "C" int sdeo_groupnorm_nhwc_f16(const void* x, const float* gamma, const 
     e = getenv("SDEO_GN_F16_HINTS");
     if (e) hints_env = atoi(e);
   }
+  cudaStream_t st = (cudaStream_t)stream;
+  const dim3 one(1, 1, 1);
+  const int mode = with_silu ? swish_mode : 0;
+  const char* variant = getenv("SDEO_GN_F16_VARIANT");  // "stream" | "resident" | unset: resident when the sample fits a cluster
+  if (!two_pass && !(variant && variant[0] == 's')) {
+    RGeom rg;
+    size_t rsmem = 0;
+    if (gr_plan(n, hw, c, groups, gs_sm_count(), gr_max_cluster(), &rg, &rsmem) == 0) {
+      auto rfn = mode == 0 ? gn_resident_kernel<0> : (mode == 1 ? gn_resident_kernel<1> : gn_resident_kernel<2>);
+      return launch_k("groupnorm_f16 (resident)", rfn, dim3((unsigned)(n * rg.cs)), dim3(kGSThreads), rsmem, st,
+                      dim3((unsigned)rg.cs, 1, 1), (const __half*)x, gamma, beta, (__half*)y, rg, eps);
+    }
+    if (variant && variant[0] == 'r') return set_error(SDEO_EINVAL, "groupnorm_f16: the sample does not fit a cluster (resident variant forced)");
+  }
   GSGeom g;
   size_t smem = 0;
   int G = 0;
@@ -531,7 +813,6 @@ extern "C" int sdeo_groupnorm_nhwc_f16(const void* x, const float* gamma, const 
   const size_t slot_bytes = (size_t)n * (size_t)(g.chunks < G ? g.chunks : G) * groups * sizeof(unsigned long long);
   if (workspace_bytes < slot_bytes)
     return set_error(SDEO_EINVAL, "groupnorm_f16: workspace too small (sdeo_groupnorm_f16_workspace_bytes)");
-  cudaStream_t st = (cudaStream_t)stream;
   if (cudaMemsetAsync(workspace, 0xFF, slot_bytes, st) != cudaSuccess) {  // every partial slot: "not written"
     (void)cudaGetLastError();
     return set_error(SDEO_ECUDA, "groupnorm_f16: cudaMemsetAsync failed");
@@ -546,8 +827,6 @@ extern "C" int sdeo_groupnorm_nhwc_f16(const void* x, const float* gamma, const 
     if (e != cudaSuccess) return set_error(SDEO_ECUDA, cudaGetErrorString(e));
     attr_set = true;
   }
-  const dim3 one(1, 1, 1);
-  const int mode = with_silu ? swish_mode : 0;
   auto fn = mode == 0 ? gn_stream_kernel<0> : (mode == 1 ? gn_stream_kernel<1> : gn_stream_kernel<2>);
   return launch_k("groupnorm_f16 (streamed)", fn, dim3((unsigned)G), dim3(kGSAll), smem, st, one, (const __half*)x, gamma,
                   beta, (__half*)y, (unsigned long long*)workspace, g, eps, hints);

@@ -238,12 +238,12 @@ def test_groupnorm_f16_visit_schedule(n, c, h, w):
     tiles cover the sample, and the buffers fit the shared-memory budget."""
     from stablediffusioneo_b200 import _lib
     lib = _lib.load()
-    plan = (ctypes.c_int32 * 6)()
+    plan = (ctypes.c_int32 * 7)()
     assert lib.sdeo_groupnorm_f16_plan(n, h * w, c, 32, 148, plan) == 0
-    chunks, ppc, lag, grid, smem, stride = list(plan)
+    chunks, ppc, lag, grid, smem, stride, bufs = list(plan)
     hw = h * w
     assert (chunks - 1) * ppc < hw <= chunks * ppc
-    assert stride % 128 == 0 and stride >= ppc * c * 2 and 4 * stride < smem <= 221 * 1024
+    assert stride % 128 == 0 and stride >= ppc * c * 2 and 3 <= bufs <= 4 and bufs * stride < smem <= 220 * 1024
     tiles = n * chunks
     assert 1 <= grid <= min(148, tiles) and chunks <= lag <= tiles
     # replay the kernel's schedule: CTA b walks its visits in order; an apply visit may only wait for statistics visits that
@@ -285,3 +285,20 @@ def test_groupnorm_f16_visit_schedule(n, c, h, w):
             progress = True
     assert len(seen_stats) == tiles and len(applied) == tiles, "schedule deadlocks or skips tiles"
     assert lib.sdeo_groupnorm_f16_workspace_bytes(n, hw, c, 32) >= n * min(chunks, grid) * 32 * 8
+
+
+def test_groupnorm_f16_variant_selection():
+    """sdeo_groupnorm_f16_variant: UNet samples at 256x384 fit a cluster (resident kernel), VAE-sized ones stream; the cluster
+    covers the sample and fits the shared-memory budget."""
+    from stablediffusioneo_b200 import _lib
+    lib = _lib.load()
+    info = (ctypes.c_int32 * 3)()
+    for n, c, h, w in [(2, 320, 32, 48), (2, 640, 16, 24), (2, 1280, 8, 12), (2, 2560, 8, 12), (1, 64, 1, 1), (3, 64, 7, 5)]:
+        assert lib.sdeo_groupnorm_f16_variant(n, h * w, c, 32, 148, 8, info) == 2
+        cs, rpc, smem = list(info)
+        assert cs in (1, 2, 4, 8) and rpc * cs >= h * w and (rpc - 1) * cs < h * w + cs and rpc * c * 2 < smem <= 220 * 1024
+    assert lib.sdeo_groupnorm_f16_variant(2, 32 * 48, 640, 32, 148, 8, info) == 0   # 1.9 MB per sample: needs 16 CTAs
+    assert lib.sdeo_groupnorm_f16_variant(2, 32 * 48, 640, 32, 148, 16, info) == 2 and info[0] == 16
+    assert lib.sdeo_groupnorm_f16_variant(2, 32 * 48, 960, 32, 148, 16, info) == 0  # 2.9 MB: streamed
+    assert lib.sdeo_groupnorm_f16_variant(16, 256 * 256, 256, 32, 148, 16, info) == 0
+    assert lib.sdeo_groupnorm_f16_variant(1, 64, 8192, 32, 148, 8, info) == 1       # more channel vectors than threads

@@ -578,10 +578,11 @@ def test_groupnorm_f16_streamed_schedule_cases(cuda_device, n, c, h, w, swish, e
     gold = F.group_norm(x.double().permute(0, 3, 1, 2), 32, gamma.double(), beta.double(), 1e-5)
     gold = (F.silu(gold) if swish else gold).permute(0, 2, 3, 1).float()
     xd, gd, bd = x.to(dev), gamma.to(dev), beta.to(dev)
-    keys = ("SDEO_GN_F16_HINTS", "SDEO_GN_F16_LAG", "SDEO_GN_F16_SWISH", "SDEO_GN_F16_TWO_PASS")
+    keys = ("SDEO_GN_F16_HINTS", "SDEO_GN_F16_LAG", "SDEO_GN_F16_SWISH", "SDEO_GN_F16_TWO_PASS", "SDEO_GN_F16_VARIANT")
     saved = {k: os.environ.pop(k, None) for k in keys}
     try:
         os.environ.update(env)
+        os.environ["SDEO_GN_F16_VARIANT"] = "stream"  # small samples would otherwise take the resident kernel
         first = ops.groupnorm_f16(xd, gd, bd, eps=1e-5, silu=swish)
         second = ops.groupnorm_f16(xd, gd, bd, eps=1e-5, silu=swish)
         torch.cuda.synchronize()
@@ -600,3 +601,49 @@ def test_groupnorm_f16_streamed_schedule_cases(cuda_device, n, c, h, w, swish, e
     worst = ((o - gold).abs() / (gold.abs() + 1.0)).max().item()
     print(f"GN fp16 streamed {n}x{c}x{h}x{w} {env}: vs f64 {e_gold:.2e} (worst {worst:.2e}), vs two-launch {e_two:.2e}")
     assert e_gold < 6e-4 and e_two < 6e-4 and worst < 4e-3
+
+
+@pytest.mark.parametrize("n,c,h,w,swish", [(2, 320, 32, 48, True), (2, 2560, 8, 12, True), (3, 64, 7, 5, True), (1, 64, 1, 1, False),
+                                           (5, 1280, 33, 17, True), (2, 640, 32, 48, False), (40, 320, 16, 24, True)])
+@pytest.mark.parametrize("cluster", [0, 1, 2, 4, 8, 16])
+def test_groupnorm_f16_resident_variant(cuda_device, n, c, h, w, swish, cluster):
+    """The resident kernel (sample kept in the shared memory of one thread-block cluster, statistics exchanged through
+    distributed shared memory) with the automatic and with forced cluster sizes, ragged row splits and ranks without rows;
+    against torch in float64 and bit-for-bit against itself."""
+    import ctypes
+    import torch.nn.functional as F
+    from stablediffusioneo_b200 import _lib, ops
+    dev = cuda_device
+    info = (ctypes.c_int32 * 3)()
+    if _lib.load().sdeo_groupnorm_f16_variant(n, h * w, c, 32, 148, max(cluster, 8), info) != 2:
+        pytest.skip("the sample does not fit a cluster of this size")
+    if cluster and (-(-h * w // cluster)) * c * 2 > 180 * 1024:
+        pytest.skip("forced cluster size too small for the sample")
+    g = torch.Generator().manual_seed(n * 1000 + c + h)
+    x = (torch.randn((n, h, w, c), generator=g) * 1.5 + 0.3).half()
+    x[:, :, :, : c // 32] *= 4.0
+    gamma, beta = torch.randn((c,), generator=g) * 0.5 + 1.0, torch.randn((c,), generator=g) * 0.2
+    gold = F.group_norm(x.double().permute(0, 3, 1, 2), 32, gamma.double(), beta.double(), 1e-5)
+    gold = (F.silu(gold) if swish else gold).permute(0, 2, 3, 1).float()
+    xd, gd, bd = x.to(dev), gamma.to(dev), beta.to(dev)
+    keys = ("SDEO_GN_F16_VARIANT", "SDEO_GN_F16_CLUSTER", "SDEO_GN_F16_TWO_PASS")
+    saved = {k: os.environ.pop(k, None) for k in keys}
+    try:
+        os.environ["SDEO_GN_F16_VARIANT"] = "resident"
+        if cluster:
+            os.environ["SDEO_GN_F16_CLUSTER"] = str(cluster)
+        first = ops.groupnorm_f16(xd, gd, bd, eps=1e-5, silu=swish)
+        second = ops.groupnorm_f16(xd, gd, bd, eps=1e-5, silu=swish)
+        torch.cuda.synchronize()
+    finally:
+        for k in keys:
+            os.environ.pop(k, None)
+            if saved[k] is not None:
+                os.environ[k] = saved[k]
+    assert torch.equal(first, second)
+    o = first.float().cpu()
+    assert torch.isfinite(o).all()
+    e_gold = rel_l2(o, gold)
+    worst = ((o - gold).abs() / (gold.abs() + 1.0)).max().item()
+    print(f"GN fp16 resident {n}x{c}x{h}x{w} cluster {cluster or 'auto'}: vs f64 {e_gold:.2e} (worst {worst:.2e})")
+    assert e_gold < 6e-4 and worst < 4e-3
