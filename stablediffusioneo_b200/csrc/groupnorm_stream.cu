@@ -516,21 +516,34 @@ gn_resident_kernel(const __half* __restrict__ x, const float* __restrict__ gamma
     }
   }
   __syncthreads();
-  if (tid < groups) {
-    float gs = 0.f, gq = 0.f;
-    for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) {
-      gs += chan[(c >> 3) * 16 + (c & 7)];
-      gq += chan[(c >> 3) * 16 + 8 + (c & 7)];
+  {
+    // per-group sums: warp w takes groups w, w + 16; lanes stride the group's channels, then a fixed shuffle tree
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int g = warp; g < groups; g += kGSThreads / 32) {
+      float gs = 0.f, gq = 0.f;
+      for (int c = g * cpg + lane; c < (g + 1) * cpg; c += 32) {
+        gs += chan[(c >> 3) * 16 + (c & 7)];
+        gq += chan[(c >> 3) * 16 + 8 + (c & 7)];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        gs += __shfl_xor_sync(0xFFFFFFFFu, gs, o);
+        gq += __shfl_xor_sync(0xFFFFFFFFu, gq, o);
+      }
+      if (lane == 0) s_group[g] = make_float2(gs, gq);
     }
-    s_group[tid] = make_float2(gs, gq);
   }
   cluster_sync_all();  // every rank's s_group is written
   if (tid < groups) {
+    float2 p2[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r)  // all remote loads in flight at once (cluster size <= 16)
+      p2[r] = r < gm.cs ? ld_cluster_f2(&s_group[tid], (uint32_t)r) : make_float2(0.f, 0.f);
     float fs = 0.f, fq = 0.f;
-    for (int r = 0; r < gm.cs; ++r) {  // rank order, the same in every CTA
-      const float2 p2 = ld_cluster_f2(&s_group[tid], (uint32_t)r);
-      fs += p2.x;
-      fq += p2.y;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {  // rank order, the same in every CTA
+      fs += p2[r].x;
+      fq += p2[r].y;
     }
     const float inv = 1.0f / ((float)hw * (float)cpg);
     const float mean = fs * inv;
@@ -538,6 +551,8 @@ gn_resident_kernel(const __half* __restrict__ x, const float* __restrict__ gamma
     var = var < 0.f ? 0.f : var;
     s_mr[tid] = make_float2(mean, rsqrtf(var + eps));
   }
+  // this CTA has read its peers' sums: arrive now, wait at the very end (a peer's shared memory must outlive the reads)
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   __syncthreads();
   // ---- normalise + affine (+ Swish) in place, chunk by chunk; each chunk leaves as soon as it is done ----
   if (active) {
@@ -575,7 +590,7 @@ gn_resident_kernel(const __half* __restrict__ x, const float* __restrict__ gamma
     }
   }
   if (tid == 0) bulk_wait_all();
-  cluster_sync_all();  // peers may read this CTA's s_group until here
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");  // peers are done reading this CTA's s_group
 }
 
 // cluster size + rows per CTA of the resident variant; non-zero when the sample does not fit `max_cs` CTAs
@@ -599,6 +614,8 @@ static int gr_plan(int n, int hw, int c, int groups, int sms, int max_cs, RGeom*
   return 0;
 }
 
+// SDEO_GN_F16_HINTS: bit 0 = L2 evict_first hints; bits 0x100 (no fold) / 0x400 (no store) / 0x800 (no apply arithmetic) /
+// 0x1000 (no statistics arithmetic) are TIMING-ONLY ablations that produce wrong results (tools/sweep_groupnorm.py).
 // tuning switches (read per call): SDEO_GN_F16_BUFS = tile buffers per CTA (2..8, default 4), SDEO_GN_F16_TILE_KB = upper
 // bound of a tile in KB (default: what the buffers allow)
 static int gs_env_int(const char* name, int dflt, int lo, int hi) {

@@ -15,7 +15,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from stablediffusioneo_b200 import ops  # noqa: E402
+from stablediffusioneo_b200 import _lib, ops  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--iters", type=int, default=20)
@@ -85,11 +85,12 @@ for label, n, c, h, w in CASES:
         return lambda: outs.__setitem__(0, ops.groupnorm_f16(xc, gamma, beta, 1e-5, True))
 
     os.environ.pop("SDEO_GN_F16_TWO_PASS", None)
+    variant = {0: "streamed", 1: "two-launch", 2: "resident"}[_lib.load().sdeo_groupnorm_f16_variant(n, h * w, c, 32, 148, 16, None)]
     ours_avg, ours_best = timed(ours_call, nbytes, x)
     os.environ["SDEO_GN_F16_TWO_PASS"] = "1"
     two_avg, _ = timed(ours_call, nbytes, x)
     os.environ.pop("SDEO_GN_F16_TWO_PASS", None)
-    line = (f"{label:24s} {nbytes / 1e6:8.1f} MB  streamed {ours_avg:8.1f} us ({nbytes / ours_avg / 1e3:6.0f} GB/s, "
+    line = (f"{label:24s} {nbytes / 1e6:8.1f} MB  ours ({variant}) {ours_avg:8.1f} us ({nbytes / ours_avg / 1e3:6.0f} GB/s, "
             f"{nbytes / ours_avg / 1e3 / peak:4.0%} of HBM)   two-launch {two_avg:8.1f} us")
     if ref is not None and n <= 32 and not args.no_ref:
         ws = torch.empty(ref.ref_groupnorm_workspace_bytes(), dtype=torch.uint8, device=dev)
