@@ -92,7 +92,7 @@ __device__ __forceinline__ uint32_t swish_pack(float t0, float t1) {
 }
 
 struct GSGeom {
-  int n, hw, C, groups, chunks, ppc, lag, bufs, tile_stride;  // tile_stride: bytes between tile buffers (multiple of 128)
+  int n, hw, C, groups, chunks, ppc, lag, bufs, two_level, tile_stride;  // tile_stride: bytes between tile buffers (multiple of 128)
 };
 
 // A CTA's position in the visit sequence: unit u, visit v (0 statistics of tile u, 1 apply of tile u - lag).
@@ -169,8 +169,53 @@ gn_stream_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, 
     GSIter it{(int)blockIdx.x, 0};
     int k = 0, cur_img = -1;
     float2 my_mr = make_float2(0.f, 1.f);  // lane = group: (mean, rstd) of sample cur_img
+    // lane = group: folds sample img's P partial slots in slot order (the same order wherever it runs: deterministic);
+    // spins on slots that are not written yet (their writers' statistics visits all lie in LOWER units)
+    auto fold_partials = [&](int img) -> float2 {
+      float2 res = make_float2(0.f, 1.f);
+      float fs = 0.f, fq = 0.f;
+      if (lane < groups) {
+        const unsigned long long* base = slots + (size_t)img * P * groups + lane;
+        const long long t0 = clock64();
+        for (int j0 = 0; j0 < P; j0 += 16) {
+          unsigned long long v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = j0 + i < P ? slot_peek(base + (size_t)(j0 + i) * groups) : 0ull;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (j0 + i >= P) break;
+            uint32_t spins = 0;
+            while ((uint32_t)(v[i] >> 32) == 0xFFFFFFFFu) {
+              __nanosleep(32);
+              if ((++spins & 0xFFFu) == 0 && clock64() - t0 > 4000000000LL) {
+                printf("sdeo: groupnorm_f16 waited too long for sample %d partial %d (block %d)\n", img, j0 + i, (int)blockIdx.x);
+                __trap();
+              }
+              v[i] = slot_peek(base + (size_t)(j0 + i) * groups);
+            }
+            fs += __uint_as_float((uint32_t)v[i]);
+            fq += __uint_as_float((uint32_t)(v[i] >> 32));
+          }
+        }
+        const float inv = 1.0f / ((float)hw * (float)cpg);
+        const float mean = fs * inv;
+        float var = fq * inv - mean * mean;
+        var = var < 0.f ? 0.f : var;
+        res = make_float2(mean, rsqrtf(var + eps));
+      }
+      return res;
+    };
+    unsigned long long* finals = slots + (size_t)gm.n * P * groups;  // two-level fold: (mean, rstd) per (sample, group)
+    int next_fold = (int)blockIdx.x;                                 // folder duty: samples b, b + G, ... of CTA b
     for (bool ok = gs_settle(it, tiles, lag, G); ok; ok = gs_next(it, tiles, lag, G), ++k) {
       const int buf = k % kGSBufs, use = k / kGSBufs;
+      // Folder duty (two-level fold): sample f is folded by CTA f mod G when that CTA first reaches a unit >= (f + 1) * chunks,
+      // i.e. after every statistics tile of f in unit order and (lag >= chunks + G) before every apply visit of f.
+      while (gm.two_level && next_fold < gm.n && it.u >= (next_fold + 1) * chunks && !(hints & 0x100)) {
+        const float2 mr = fold_partials(next_fold);
+        if (lane < groups) slot_publish(finals + (size_t)next_fold * groups + lane, mr.x, mr.y);
+        next_fold += G;
+      }
       if (use > 0) mbar_wait(&empty[buf], (uint32_t)(use - 1) & 1u);
       const int tile = it.v ? it.u - lag : it.u;
       const int img = tile / chunks, ch = tile - img * chunks;
@@ -183,37 +228,23 @@ gn_stream_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, 
                   (hints & 1) && it.v == 1);
       if (it.v == 1) {
         if (img != cur_img && !(hints & 0x100)) {
-          // First apply visit of this CTA in sample img: fold the sample's P partials in slot order (the same order in
-          // every CTA: deterministic). Their writers' statistics visits all lie in LOWER units (lag >= tiles per sample).
-          float fs = 0.f, fq = 0.f;
-          if (lane < groups) {
-            const unsigned long long* base = slots + (size_t)img * P * groups + lane;
+          if (!gm.two_level) {
+            my_mr = fold_partials(img);  // first apply visit of this CTA in sample img: every CTA folds for itself
+          } else if (lane < groups) {
+            // the sample's folder CTA published (mean, rstd) in a lower unit than this one (lag >= chunks + G)
+            const unsigned long long* fp = finals + (size_t)img * groups + lane;
+            unsigned long long v = slot_peek(fp);
             const long long t0 = clock64();
-            for (int j0 = 0; j0 < P; j0 += 16) {
-              unsigned long long v[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = j0 + i < P ? slot_peek(base + (size_t)(j0 + i) * groups) : 0ull;
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                if (j0 + i >= P) break;
-                uint32_t spins = 0;
-                while ((uint32_t)(v[i] >> 32) == 0xFFFFFFFFu) {
-                  __nanosleep(32);
-                  if ((++spins & 0xFFFu) == 0 && clock64() - t0 > 4000000000LL) {
-                    printf("sdeo: groupnorm_f16 waited too long for sample %d partial %d (block %d)\n", img, j0 + i, (int)blockIdx.x);
-                    __trap();
-                  }
-                  v[i] = slot_peek(base + (size_t)(j0 + i) * groups);
-                }
-                fs += __uint_as_float((uint32_t)v[i]);
-                fq += __uint_as_float((uint32_t)(v[i] >> 32));
+            uint32_t spins = 0;
+            while ((uint32_t)(v >> 32) == 0xFFFFFFFFu) {
+              __nanosleep(32);
+              if ((++spins & 0xFFFu) == 0 && clock64() - t0 > 4000000000LL) {
+                printf("sdeo: groupnorm_f16 waited too long for the statistics of sample %d (block %d)\n", img, (int)blockIdx.x);
+                __trap();
               }
+              v = slot_peek(fp);
             }
-            const float inv = 1.0f / ((float)hw * (float)cpg);
-            const float mean = fs * inv;
-            float var = fq * inv - mean * mean;
-            var = var < 0.f ? 0.f : var;
-            my_mr = make_float2(mean, rsqrtf(var + eps));
+            my_mr = make_float2(__uint_as_float((uint32_t)v), __uint_as_float((uint32_t)(v >> 32)));
           }
           cur_img = img;
         }
@@ -668,6 +699,8 @@ static int gs_plan(int n, int hw, int c, int groups, int sms, int lag_env, GSGeo
   if (lag < g->chunks) lag = g->chunks;  // ordering requirement: apply(t) after statistics of every tile of t's sample
   if (lag > tiles) lag = tiles;
   g->lag = (int)lag;
+  // one folder CTA per sample needs its fold point (< (f + 1) * chunks + G) below the sample's first apply unit
+  g->two_level = lag >= (long long)g->chunks + G && !getenv("SDEO_GN_F16_ONE_LEVEL") ? 1 : 0;
   *grid = G;
   return 0;
 }
@@ -742,7 +775,7 @@ extern "C" size_t sdeo_groupnorm_f16_workspace_bytes(int32_t n, int32_t hw, int3
   (void)cudaGetLastError();
   if (gs_geometry(n, hw, c, sms, &g, &smem)) return two_pass;
   const size_t parts = (size_t)(g.chunks < sms ? g.chunks : sms);  // partial slots per sample (<= grid size)
-  const size_t stream_bytes = (size_t)n * parts * groups * sizeof(unsigned long long);
+  const size_t stream_bytes = (size_t)n * (parts + 1) * groups * sizeof(unsigned long long);  // partial slots + (mean, rstd) slots
   return stream_bytes > two_pass ? stream_bytes : two_pass;
 }
 
@@ -827,7 +860,7 @@ extern "C" int sdeo_groupnorm_nhwc_f16(const void* x, const float* gamma, const 
   int G = 0;
   if (two_pass || gs_plan(n, hw, c, groups, gs_sm_count(), lag_env, &g, &smem, &G))
     return groupnorm_f16_two_pass(x, gamma, beta, y, n, hw, c, groups, eps, with_silu, workspace, workspace_bytes, stream);
-  const size_t slot_bytes = (size_t)n * (size_t)(g.chunks < G ? g.chunks : G) * groups * sizeof(unsigned long long);
+  const size_t slot_bytes = (size_t)n * ((size_t)(g.chunks < G ? g.chunks : G) + 1) * groups * sizeof(unsigned long long);
   if (workspace_bytes < slot_bytes)
     return set_error(SDEO_EINVAL, "groupnorm_f16: workspace too small (sdeo_groupnorm_f16_workspace_bytes)");
   if (cudaMemsetAsync(workspace, 0xFF, slot_bytes, st) != cudaSuccess) {  // every partial slot: "not written"
