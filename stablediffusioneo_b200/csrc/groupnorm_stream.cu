@@ -659,7 +659,7 @@ static int gs_env_int_fwd(const char* name, int dflt, int lo, int hi) { return g
 
 static int gs_geometry(int n, int hw, int c, int sms, GSGeom* g, size_t* smem) {
   // large tensors: fewer, larger tiles (the per-visit costs weigh more than the extra look-ahead); small ones: 4 buffers
-  const int kGSBufs = gs_env_int("SDEO_GN_F16_BUFS", (long long)n * hw * c * 2 > (64LL << 20) ? 3 : 4, 2, kGSMaxBufs);
+  const int kGSBufs = gs_env_int("SDEO_GN_F16_BUFS", (long long)n * hw * c * 2 > (64LL << 20) ? 2 : 4, 2, kGSMaxBufs);
   const size_t tile_kb = (size_t)gs_env_int("SDEO_GN_F16_TILE_KB", 1024, 1, 1024);
   if (c % 8 != 0 || c / 8 > kGSThreads) return -1;  // one 8-channel vector column per arithmetic thread
   const size_t aux = ((size_t)2 * c + kGSThreads * 16 + 512) * sizeof(float);
