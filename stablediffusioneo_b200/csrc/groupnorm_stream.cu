@@ -92,7 +92,7 @@ __device__ __forceinline__ uint32_t swish_pack(float t0, float t1) {
 }
 
 struct GSGeom {
-  int n, hw, C, groups, chunks, ppc, lag, bufs, two_level, tile_stride;  // tile_stride: bytes between tile buffers (multiple of 128)
+  int n, hw, C, groups, chunks, ppc, lag, bufs, two_level, ngroups, tile_stride;  // tile_stride: bytes between tile buffers (multiple of 128)
 };
 
 // A CTA's position in the visit sequence: unit u, visit v (0 statistics of tile u, 1 apply of tile u - lag).
@@ -152,7 +152,7 @@ gn_stream_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, 
   const int C = gm.C, hw = gm.hw, groups = gm.groups, chunks = gm.chunks, ppc = gm.ppc, lag = gm.lag;
   const int cv = C / 8, cpg = C / groups;
   const int tiles = gm.n * chunks, G = gridDim.x, kGSBufs = gm.bufs;
-  const int P = chunks < G ? chunks : G;  // partials per sample: one per CTA that takes tiles of it
+  const int P = chunks < gm.ngroups * G ? chunks : gm.ngroups * G;  // partials per sample: one per (CTA, thread group) with tiles of it
 
   if (tid == 0) {
     for (int b = 0; b < kGSBufs; ++b) {
@@ -167,7 +167,8 @@ gn_stream_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, 
     // ---- control warp: buffer recycling, tile loads, the sample's (mean, rstd) row for apply visits ----
     const int lane = tid - kGSThreads;
     GSIter it{(int)blockIdx.x, 0};
-    int k = 0, cur_img = -1;
+    int k = 0, cur_img = -1, kg0 = 0, kg1 = 0;
+    const int bpg = kGSBufs / gm.ngroups;  // buffers per thread group
     float2 my_mr = make_float2(0.f, 1.f);  // lane = group: (mean, rstd) of sample cur_img
     // lane = group: folds sample img's P partial slots in slot order (the same order wherever it runs: deterministic);
     // spins on slots that are not written yet (their writers' statistics visits all lie in LOWER units)
@@ -208,7 +209,11 @@ gn_stream_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, 
     unsigned long long* finals = slots + (size_t)gm.n * P * groups;  // two-level fold: (mean, rstd) per (sample, group)
     int next_fold = (int)blockIdx.x;                                 // folder duty: samples b, b + G, ... of CTA b
     for (bool ok = gs_settle(it, tiles, lag, G); ok; ok = gs_next(it, tiles, lag, G), ++k) {
-      const int buf = k % kGSBufs, use = k / kGSBufs;
+      // Each thread group owns bufs / ng buffers and walks them with its own visit counter: a barrier is then waited on by ONE
+      // group, phase after phase (a group that skipped the other's phases could not use parity waits).
+      const int vg = ((it.u - (int)blockIdx.x) / G) % gm.ngroups;
+      const int kgv = vg ? kg1++ : kg0++;
+      const int buf = vg * bpg + kgv % bpg, use = kgv / bpg;
       // Folder duty (two-level fold): sample f is folded by CTA f mod G when that CTA first reaches a unit >= (f + 1) * chunks,
       // i.e. after every statistics tile of f in unit order and (lag >= chunks + G) before every apply visit of f.
       while (gm.two_level && next_fold < gm.n && it.u >= (next_fold + 1) * chunks && !(hints & 0x100)) {
@@ -256,25 +261,35 @@ gn_stream_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, 
     return;
   }
 
-  // ---- arithmetic threads ----
-  float* chan = reinterpret_cast<float*>(gs_smem + (size_t)kGSBufs * gm.tile_stride);  // [cv][16]: 8 sums, 8 sums of squares
-  float* part = chan + 2 * C;                                                             // [R][cols][16]
-  float* part2 = part + kGSThreads * 16;                                                  // [nparts][S], S * nparts <= 512
-  const int cols = cv;  // <= kGSThreads (host check)
-  const int R = kGSThreads / cols;
-  const int tr = tid / cols, tv = tid % cols;
-  const bool active = tid < R * cols;
+  // ---- arithmetic threads: ng groups of nthr threads, each with its own named barrier and reduction scratch; group g takes
+  //      every ng-th unit of the CTA, so one group's barriers and hand-overs hide behind the other's arithmetic ----
+  const int ng = gm.ngroups, nthr = kGSThreads / ng;
+  const int grp = tid / nthr, t = tid - grp * nthr;
+  const uint32_t bar_id = 1u + (uint32_t)grp;
+  float* aux = reinterpret_cast<float*>(gs_smem + (size_t)kGSBufs * gm.tile_stride);
+  float* chan = aux + (size_t)grp * 2 * C;                         // [cv][16]: 8 sums, 8 sums of squares
+  float* part = aux + (size_t)ng * 2 * C + (size_t)grp * nthr * 16;  // [R][cols][16]
+  float* part2 = aux + (size_t)ng * 2 * C + kGSThreads * 16 + (size_t)grp * nthr;  // [nparts][S], S * nparts <= nthr
+  const int cols = cv;  // <= nthr (host check)
+  const int R = nthr / cols;
+  const int tr = t / cols, tv = t % cols;
+  const bool active = t < R * cols;
   const int S = cols * 16;
-  const int nparts = S >= kGSThreads ? 1 : min(R, kGSThreads / S);
+  const int nparts = S >= nthr ? 1 : min(R, nthr / S);
   const int gfirst = (tv * 8) / cpg, rfirst = tv * 8 - gfirst * cpg;
+  const int W = ng * G;  // distance between two statistics tiles of one group
 
   GSIter it{(int)blockIdx.x, 0};
   int k = 0;
   bool prev_apply = false;
+  int prev_buf = 0, kg = 0;
+  const int bpg = kGSBufs / ng;
   float acc_s = 0.f, acc_q = 0.f;  // threads 0 .. groups-1: this CTA's running (sum, sum of squares) of the current sample
   for (bool ok = gs_settle(it, tiles, lag, G); ok; ok = gs_next(it, tiles, lag, G), ++k) {
-    const int buf = k % kGSBufs;
-    const uint32_t parity = (uint32_t)(k / kGSBufs) & 1u;
+    if (((it.u - (int)blockIdx.x) / G) % ng != grp) continue;  // the other group's unit
+    const int buf = grp * bpg + kg % bpg;  // this group's own buffers, walked with its own visit counter (as the control warp does)
+    const uint32_t parity = (uint32_t)(kg / bpg) & 1u;
+    ++kg;
     const int tile = it.v ? it.u - lag : it.u;
     const int img = tile / chunks, ch = tile - img * chunks;
     const int p0 = ch * ppc;
@@ -313,11 +328,11 @@ gn_stream_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, 
         dst[2] = make_float4(q[0], q[1], q[2], q[3]);
         dst[3] = make_float4(q[4], q[5], q[6], q[7]);
       }
-      bar_sync(1, kGSThreads);
-      if (tid == 0) mbar_arrive(&empty[buf]);  // the tile itself is no longer needed
+      bar_sync(bar_id, nthr);
+      if (t == 0) mbar_arrive(&empty[buf]);  // the tile itself is no longer needed
       // fold the R pixel rows with every thread: scalar i = column * 16 + slot, rows split in nparts interleaved parts
       // (fixed order: deterministic)
-      for (int idx = tid; idx < S * nparts; idx += kGSThreads) {
+      for (int idx = t; idx < S * nparts; idx += nthr) {
         const int i = idx % S, rp = idx / S;
         float acc = 0.f;
         for (int r = rp; r < R; r += nparts) acc += part[(size_t)r * S + i];
@@ -325,28 +340,29 @@ gn_stream_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, 
         else part2[rp * S + i] = acc;
       }
       if (nparts > 1) {
-        bar_sync(1, kGSThreads);
-        for (int i = tid; i < S; i += kGSThreads) {
+        bar_sync(bar_id, nthr);
+        for (int i = t; i < S; i += nthr) {
           float acc = 0.f;
           for (int rp = 0; rp < nparts; ++rp) acc += part2[rp * S + i];
           chan[i] = acc;
         }
       }
-      bar_sync(1, kGSThreads);
-      if (tid < groups) {
+      bar_sync(bar_id, nthr);
+      if (t < groups) {
         float gs = 0.f, gq = 0.f;
-        for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) {
+        for (int c = t * cpg; c < (t + 1) * cpg; ++c) {
           gs += chan[(c >> 3) * 16 + (c & 7)];
           gq += chan[(c >> 3) * 16 + 8 + (c & 7)];
         }
         acc_s += gs;
         acc_q += gq;
-        // this CTA's next statistics tile is it.u + G: publish when that one belongs to another sample (or does not exist)
-        const int nxt = it.u + G;
+        // this group's next statistics tile is it.u + W: publish when that one belongs to another sample (or does not exist).
+        // Slot (it.u - first tile of the sample) mod W is the same for every tile this group takes of the sample, and the
+        // slots 0 .. min(chunks, W) - 1 of a sample are each written exactly once.
+        const int nxt = it.u + W;
         if (nxt >= tiles || nxt / chunks != img) {
-          int j = ((int)blockIdx.x - img * chunks) % G;
-          if (j < 0) j += G;
-          slot_publish(slots + ((size_t)img * P + j) * groups + tid, acc_s, acc_q);
+          const int j = (it.u - img * chunks) % W;
+          slot_publish(slots + ((size_t)img * P + j) * groups + t, acc_s, acc_q);
           acc_s = 0.f;
           acc_q = 0.f;
         }
@@ -403,17 +419,26 @@ gn_stream_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, 
         }
       }
       fence_proxy_async_smem();  // the in-place results are read by the bulk store (async proxy)
-      bar_sync(1, kGSThreads);
-      if (tid == 0 && !(hints & 0x400)) bulk_store(y + ((long long)img * hw + p0) * C, tp, (uint32_t)rows * (uint32_t)C * 2u, (hints & 1) != 0);
+      bar_sync(bar_id, nthr);
+      if (t == 0 && !(hints & 0x400)) bulk_store(y + ((long long)img * hw + p0) * C, tp, (uint32_t)rows * (uint32_t)C * 2u, (hints & 1) != 0);
     }
-    if (tid == 0) {
-      bulk_commit();        // one group per visit (empty for statistics visits)
-      bulk_wait_read<1>();  // the store of the PREVIOUS visit has left its buffer
-      if (prev_apply) mbar_arrive(&empty[(k + kGSBufs - 1) % kGSBufs]);
+    if (t == 0) {
+      bulk_commit();  // one bulk group per visit (empty for statistics visits)
+      if (ng == 1) {
+        bulk_wait_read<1>();  // the store of the PREVIOUS visit has left its buffer: hand that one back
+        if (prev_apply) mbar_arrive(&empty[prev_buf]);
+      } else if (it.v == 1) {
+        // Two thread groups: this group's next visit is a whole unit of the other group away, and the control warp hands
+        // buffers out in visit order, so the hand-back cannot wait for it (it would deadlock with few buffers). Wait for
+        // the store to have read the buffer now; the other group's arithmetic goes on meanwhile.
+        bulk_wait_read<0>();
+        mbar_arrive(&empty[buf]);
+      }
     }
     prev_apply = it.v == 1;
+    prev_buf = buf;
   }
-  if (tid == 0) bulk_wait_all();
+  if (t == 0) bulk_wait_all();
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -659,10 +684,15 @@ static int gs_env_int_fwd(const char* name, int dflt, int lo, int hi) { return g
 
 static int gs_geometry(int n, int hw, int c, int sms, GSGeom* g, size_t* smem) {
   // large tensors: fewer, larger tiles (the per-visit costs weigh more than the extra look-ahead); small ones: 4 buffers
-  const int kGSBufs = gs_env_int("SDEO_GN_F16_BUFS", (long long)n * hw * c * 2 > (64LL << 20) ? 2 : 4, 2, kGSMaxBufs);
+  int kGSBufs = gs_env_int("SDEO_GN_F16_BUFS", (long long)n * hw * c * 2 > (64LL << 20) ? 2 : 4, 2, kGSMaxBufs);
   const size_t tile_kb = (size_t)gs_env_int("SDEO_GN_F16_TILE_KB", 1024, 1, 1024);
   if (c % 8 != 0 || c / 8 > kGSThreads) return -1;  // one 8-channel vector column per arithmetic thread
-  const size_t aux = ((size_t)2 * c + kGSThreads * 16 + 512) * sizeof(float);
+  // SDEO_GN_F16_GROUPS=2: two thread groups of 256 on alternate units (needs C <= 2048: a group covers a pixel row). Measured
+  // on B200 and NOT the default: 16x256@256x256 591 us with two groups vs 542 us with one (4 buffers), 439 us with one group and
+  // 2 large buffers - the per-visit cost is arithmetic latency inside a group, not idle time at its barriers.
+  const int ngroups = gs_env_int("SDEO_GN_F16_GROUPS", 1, 1, c / 8 <= kGSThreads / 2 ? 2 : 1);
+  if (ngroups == 2) kGSBufs = kGSBufs < 4 ? 4 : (kGSBufs & ~1);  // each group needs a tile in hand and one in flight
+  const size_t aux = ((size_t)ngroups * 2 * c + kGSThreads * 16 + 512) * sizeof(float);
   if (aux + (size_t)kGSBufs * c * 2 > (size_t)kGSSmemTotal) return -1;
   size_t tile_cap = ((kGSSmemTotal - aux) / kGSBufs) & ~(size_t)127;
   if (tile_cap > tile_kb * 1024 && tile_kb * 1024 >= (size_t)c * 2) tile_cap = tile_kb * 1024;
@@ -678,7 +708,7 @@ static int gs_geometry(int n, int hw, int c, int sms, GSGeom* g, size_t* smem) {
     ppc = (hw + ch - 1) / ch;
   }
   if (ppc > hw) ppc = hw;
-  g->n = n; g->hw = hw; g->C = c; g->bufs = kGSBufs;
+  g->n = n; g->hw = hw; g->C = c; g->bufs = kGSBufs; g->ngroups = ngroups;
   g->ppc = ppc;
   g->chunks = (hw + ppc - 1) / ppc;
   g->tile_stride = (int)((((size_t)ppc * c * 2) + 127) & ~(size_t)127);
@@ -774,7 +804,7 @@ extern "C" size_t sdeo_groupnorm_f16_workspace_bytes(int32_t n, int32_t hw, int3
     sms = dev_sms;
   (void)cudaGetLastError();
   if (gs_geometry(n, hw, c, sms, &g, &smem)) return two_pass;
-  const size_t parts = (size_t)(g.chunks < sms ? g.chunks : sms);  // partial slots per sample (<= grid size)
+  const size_t parts = (size_t)(g.chunks < 2 * sms ? g.chunks : 2 * sms);  // partial slots per sample (<= thread groups x grid size)
   const size_t stream_bytes = (size_t)n * (parts + 1) * groups * sizeof(unsigned long long);  // partial slots + (mean, rstd) slots
   return stream_bytes > two_pass ? stream_bytes : two_pass;
 }
@@ -860,7 +890,7 @@ extern "C" int sdeo_groupnorm_nhwc_f16(const void* x, const float* gamma, const 
   int G = 0;
   if (two_pass || gs_plan(n, hw, c, groups, gs_sm_count(), lag_env, &g, &smem, &G))
     return groupnorm_f16_two_pass(x, gamma, beta, y, n, hw, c, groups, eps, with_silu, workspace, workspace_bytes, stream);
-  const size_t slot_bytes = (size_t)n * ((size_t)(g.chunks < G ? g.chunks : G) + 1) * groups * sizeof(unsigned long long);
+  const size_t slot_bytes = (size_t)n * ((size_t)(g.chunks < g.ngroups * G ? g.chunks : g.ngroups * G) + 1) * groups * sizeof(unsigned long long);
   if (workspace_bytes < slot_bytes)
     return set_error(SDEO_EINVAL, "groupnorm_f16: workspace too small (sdeo_groupnorm_f16_workspace_bytes)");
   if (cudaMemsetAsync(workspace, 0xFF, slot_bytes, st) != cudaSuccess) {  // every partial slot: "not written"

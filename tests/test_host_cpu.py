@@ -255,11 +255,19 @@ def test_groupnorm_f16_visit_schedule(n, c, h, w):
         cnt = lib.sdeo_groupnorm_f16_visits(b_, grid, tiles, lag, out, cap)
         assert 0 < cnt <= cap
         seqs.append([(out[2 * i], out[2 * i + 1]) for i in range(cnt)])
-    # partial slots: CTA b writes slot (b - sample * chunks) mod grid of every sample it takes statistics tiles of; the
-    # slots of a sample are exactly 0 .. min(chunks, grid) - 1, each written by one CTA
-    for img in range(n):
-        js = sorted((b_ - img * chunks) % grid for b_ in range(grid) if any(k_ == 0 and t_ // chunks == img for k_, t_ in seqs[b_]))
-        assert js == list(range(min(chunks, grid)))
+    # partial slots: thread group g of CTA b (it takes every ng-th unit of the CTA) writes slot (tile - sample * chunks) mod
+    # (ng * grid) once per sample it has statistics tiles of: the same slot for all its tiles of the sample, and the slots of
+    # a sample are exactly 0 .. min(chunks, ng * grid) - 1, each written by one (CTA, group)
+    for ng in (1, 2):
+        for img in range(n):
+            owner = {}
+            for b_ in range(grid):
+                for k_, t_ in seqs[b_]:
+                    if k_ == 0 and t_ // chunks == img:
+                        key = (b_, ((t_ - b_) // grid) % ng)
+                        owner.setdefault(key, set()).add((t_ - img * chunks) % (ng * grid))
+            assert all(len(v) == 1 for v in owner.values())
+            assert sorted(next(iter(v)) for v in owner.values()) == list(range(min(chunks, ng * grid)))
     kinds = [sum(1 for v in s_ if v[0] == 1) for s_ in seqs]
     assert max(kinds) - min(kinds) <= 1, "apply visits are not balanced over the CTAs"
     pos = [0] * grid
@@ -284,7 +292,7 @@ def test_groupnorm_f16_visit_schedule(n, c, h, w):
             pos[b_] += 1
             progress = True
     assert len(seen_stats) == tiles and len(applied) == tiles, "schedule deadlocks or skips tiles"
-    assert lib.sdeo_groupnorm_f16_workspace_bytes(n, hw, c, 32) >= n * min(chunks, grid) * 32 * 8
+    assert lib.sdeo_groupnorm_f16_workspace_bytes(n, hw, c, 32) >= n * (min(chunks, 2 * grid) + 1) * 32 * 8
 
 
 def test_groupnorm_f16_variant_selection():

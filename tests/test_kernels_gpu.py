@@ -563,13 +563,14 @@ def test_groupnorm_f16_plugin_contract_vs_reference_kernels(cuda_device, n, c, h
 @pytest.mark.parametrize("n,c,h,w,swish", [(3, 64, 7, 5, True), (1, 64, 1, 1, False), (5, 1280, 33, 17, True),
                                            (4, 256, 128, 128, True), (2, 128, 250, 301, False), (40, 320, 16, 24, True)])
 @pytest.mark.parametrize("env", [{}, {"SDEO_GN_F16_HINTS": "1"}, {"SDEO_GN_F16_LAG": "0"}, {"SDEO_GN_F16_SWISH": "1"},
-                                 {"SDEO_GN_F16_ONE_LEVEL": "1"}, {"SDEO_GN_F16_BUFS": "2", "SDEO_GN_F16_TILE_KB": "8"}])
+                                 {"SDEO_GN_F16_ONE_LEVEL": "1"}, {"SDEO_GN_F16_BUFS": "2", "SDEO_GN_F16_TILE_KB": "8"},
+                                 {"SDEO_GN_F16_GROUPS": "2"}, {"SDEO_GN_F16_GROUPS": "2", "SDEO_GN_F16_BUFS": "6", "SDEO_GN_F16_TILE_KB": "8"}])
 def test_groupnorm_f16_streamed_schedule_cases(cuda_device, n, c, h, w, swish, env):
     """The streamed kernel (csrc/groupnorm_stream.cu) on ragged tiles (hw not a multiple of the tile), one-pixel samples, more
     tiles than SMs, more samples than SMs per wave, called twice on one workspace (the call clears its own flags), with the
     L2 hints forced on, with the smallest legal apply lag (every CTA folds the partial slots itself), with the fp32 Swish, with
-    the two-level fold switched off and with two small tile buffers (many visits per CTA); against torch in float64 and
-    against the two-launch variant."""
+    the two-level fold switched off, with two small tile buffers (many visits per CTA) and with two thread groups on alternate
+    units (each with its own buffer set); against torch in float64 and against the two-launch variant."""
     import torch.nn.functional as F
     from stablediffusioneo_b200 import ops
     dev = cuda_device
@@ -581,7 +582,7 @@ def test_groupnorm_f16_streamed_schedule_cases(cuda_device, n, c, h, w, swish, e
     gold = (F.silu(gold) if swish else gold).permute(0, 2, 3, 1).float()
     xd, gd, bd = x.to(dev), gamma.to(dev), beta.to(dev)
     keys = ("SDEO_GN_F16_HINTS", "SDEO_GN_F16_LAG", "SDEO_GN_F16_SWISH", "SDEO_GN_F16_TWO_PASS", "SDEO_GN_F16_VARIANT",
-            "SDEO_GN_F16_ONE_LEVEL", "SDEO_GN_F16_BUFS", "SDEO_GN_F16_TILE_KB")
+            "SDEO_GN_F16_ONE_LEVEL", "SDEO_GN_F16_BUFS", "SDEO_GN_F16_TILE_KB", "SDEO_GN_F16_GROUPS")
     saved = {k: os.environ.pop(k, None) for k in keys}
     try:
         os.environ.update(env)

@@ -18,6 +18,7 @@ ap.add_argument("--bufs", default="4")
 ap.add_argument("--tile-kb", default="1024")
 ap.add_argument("--lag", default="-1")
 ap.add_argument("--hints", default="-1")
+ap.add_argument("--groups", default="2")
 args = ap.parse_args()
 n, c, h, w = args.shape
 dev = torch.device("cuda:0")
@@ -26,8 +27,9 @@ gamma, beta = torch.rand((c,), device=dev) + 0.5, torch.randn((c,), device=dev) 
 nbytes = x.numel() * 4
 k = max(1, min(64, -(-(512 << 20) // nbytes)))
 copies = [x] + [x.clone() for _ in range(k - 1)]
-for bufs, kb, lag, hints in itertools.product(args.bufs.split(","), args.tile_kb.split(","), args.lag.split(","), args.hints.split(",")):
-    os.environ["SDEO_GN_F16_BUFS"], os.environ["SDEO_GN_F16_TILE_KB"] = bufs, kb
+for bufs, kb, lag, hints, grps in itertools.product(args.bufs.split(","), args.tile_kb.split(","), args.lag.split(","), args.hints.split(","),
+                                                   args.groups.split(",")):
+    os.environ["SDEO_GN_F16_BUFS"], os.environ["SDEO_GN_F16_TILE_KB"], os.environ["SDEO_GN_F16_GROUPS"] = bufs, kb, grps
     for key, v in (("SDEO_GN_F16_LAG", lag), ("SDEO_GN_F16_HINTS", hints)):
         os.environ.pop(key, None)
         if v != "-1":
@@ -48,5 +50,5 @@ for bufs, kb, lag, hints in itertools.product(args.bufs.split(","), args.tile_kb
         e.synchronize()
         ts.append(s.elapsed_time(e) * 1e3 / k)
     t = sum(ts) / len(ts)
-    print(f"bufs {bufs} tile_kb {kb:>4s} lag {lag:>5s} hints {hints:>2s}: {t:8.1f} us  {nbytes / t / 1e3:6.0f} GB/s", flush=True)
+    print(f"groups {grps} bufs {bufs} tile_kb {kb:>4s} lag {lag:>5s} hints {hints:>2s}: {t:8.1f} us  {nbytes / t / 1e3:6.0f} GB/s", flush=True)
     del graph, outs
