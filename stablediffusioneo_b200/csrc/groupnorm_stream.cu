@@ -729,8 +729,10 @@ static int gs_plan(int n, int hw, int c, int groups, int sms, int lag_env, GSGeo
   if (lag < g->chunks) lag = g->chunks;  // ordering requirement: apply(t) after statistics of every tile of t's sample
   if (lag > tiles) lag = tiles;
   g->lag = (int)lag;
-  // one folder CTA per sample needs its fold point (< (f + 1) * chunks + G) below the sample's first apply unit
-  g->two_level = lag >= (long long)g->chunks + G && !getenv("SDEO_GN_F16_ONE_LEVEL") ? 1 : 0;
+  // One folder CTA per sample is safe when no apply visit of the folder can precede its fold point: the fold point
+  // (< (f + 1) * chunks + G) lies below the sample's first apply unit, or (lag == tiles) every CTA makes all its statistics
+  // visits before its first apply visit and the remaining folds fire at the top of that one.
+  g->two_level = (lag >= (long long)g->chunks + G || lag == tiles) && !getenv("SDEO_GN_F16_ONE_LEVEL") ? 1 : 0;
   *grid = G;
   return 0;
 }

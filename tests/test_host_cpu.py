@@ -310,3 +310,105 @@ def test_groupnorm_f16_variant_selection():
     assert lib.sdeo_groupnorm_f16_variant(2, 32 * 48, 960, 32, 148, 16, info) == 0  # 2.9 MB: streamed
     assert lib.sdeo_groupnorm_f16_variant(16, 256 * 256, 256, 32, 148, 16, info) == 0
     assert lib.sdeo_groupnorm_f16_variant(1, 64, 8192, 32, 148, 8, info) == 1       # more channel vectors than threads
+
+
+def _gn_stream_protocol_model(lib, n, c, h, w, ng, bufs, sms=148, verbose=False):
+    plan = (ctypes.c_int32 * 7)()
+    assert lib.sdeo_groupnorm_f16_plan(n, h * w, c, 32, sms, plan) == 0
+    chunks, ppc, lag, grid = plan[0], plan[1], plan[2], plan[3]
+    tiles = n * chunks
+    two_level = lag >= chunks + grid or lag == tiles
+    W = ng * grid
+    P = min(chunks, W)
+    cap = 2 * tiles // grid + 8
+    seqs = []
+    for b in range(grid):
+        out = (ctypes.c_int32 * (2 * cap))()
+        cnt = lib.sdeo_groupnorm_f16_visits(b, grid, tiles, lag, out, cap)
+        seqs.append([(out[2 * i], out[2 * i + 1]) for i in range(cnt)])
+    unit = lambda kind, t: t + lag if kind else t
+    published = [set() for _ in range(n)]
+    finals = [False] * n
+    full = [[False] * len(s) for s in seqs]
+    released = [[False] * len(s) for s in seqs]
+    kc = [0] * grid
+    next_fold = list(range(grid))
+    gl = [[[k for k, (kind, t) in enumerate(s) if ((unit(kind, t) - b) // grid) % ng == g] for g in range(ng)] for b, s in enumerate(seqs)]
+    pg = [[0] * ng for _ in range(grid)]
+    prev = [[None] * ng for _ in range(grid)]  # deferred release (ng == 1)
+    progress = True
+    while progress:
+        progress = False
+        for b in range(grid):
+            s = seqs[b]
+            # control warp
+            while kc[b] < len(s):
+                k = kc[b]
+                kind, t = s[k]
+                u = unit(kind, t)
+                blocked = False
+                while two_level and next_fold[b] < n and u >= (next_fold[b] + 1) * chunks:
+                    if len(published[next_fold[b]]) < P:
+                        blocked = True
+                        break
+                    finals[next_fold[b]] = True
+                    next_fold[b] += grid
+                    progress = True
+                if blocked:
+                    break
+                if k >= bufs and not released[b][k - bufs]:
+                    break
+                if kind == 1:
+                    img = t // chunks
+                    if (two_level and not finals[img]) or (not two_level and len(published[img]) < P):
+                        break
+                full[b][k] = True
+                kc[b] += 1
+                progress = True
+            # thread groups
+            for g in range(ng):
+                while pg[b][g] < len(gl[b][g]):
+                    k = gl[b][g][pg[b][g]]
+                    if not full[b][k]:
+                        break
+                    kind, t = s[k]
+                    if kind == 0:
+                        released[b][k] = True
+                        img = t // chunks
+                        nxt = t + W
+                        if nxt >= tiles or nxt // chunks != img:
+                            j = (t - img * chunks) % W
+                            assert j not in published[img], (b, g, t, j)
+                            published[img].add(j)
+                    else:
+                        if ng > 1:
+                            released[b][k] = True
+                    if ng == 1:
+                        if prev[b][g] is not None:
+                            released[b][prev[b][g]] = True
+                        prev[b][g] = k if kind == 1 else None
+                    pg[b][g] += 1
+                    progress = True
+    done = all(pg[b][g] == len(gl[b][g]) for b in range(grid) for g in range(ng))
+    if not done and verbose:
+        for b in range(grid):
+            if kc[b] < len(seqs[b]):
+                k = kc[b]; kind, t = seqs[b][k]
+                print("cta", b, "control at k", k, kind, t, "unit", unit(kind, t), "next_fold", next_fold[b], "pg", pg[b], [gl[b][g][pg[b][g]] if pg[b][g] < len(gl[b][g]) else None for g in range(ng)])
+                if b > 12: break
+        print("published", [len(p) for p in published], "P", P, "finals", finals, "chunks", chunks, "lag", lag, "grid", grid)
+    return done
+
+
+@pytest.mark.parametrize("shape", [(2, 320, 32, 48), (1, 512, 64, 96), (3, 64, 7, 5), (40, 320, 16, 24), (1, 64, 1, 1),
+                                   (5, 1280, 33, 17), (4, 256, 128, 128), (8, 256, 256, 256)])
+def test_groupnorm_f16_protocol_model(shape):
+    """Discrete-event model of the streamed GroupNorm's protocol (csrc/groupnorm_stream.cu) on the library's own plan and visit
+    lists: an in-order control warp per CTA (folder duty, buffer recycling, statistics wait before an apply visit), one or two
+    thread groups, partial slots published once per (CTA, group, sample). Every visit must complete for every buffer count:
+    no deadlock, no slot written twice."""
+    from stablediffusioneo_b200 import _lib
+    lib = _lib.load()
+    for ng in (1, 2):
+        for bufs in (2, 4):
+            assert _gn_stream_protocol_model(lib, *shape, ng=ng, bufs=bufs), (shape, ng, bufs)
