@@ -164,11 +164,14 @@ int sdeo_groupnorm_nhwc(const void* x1, const void* x2, int32_t x_f32, const flo
                         int32_t n, int32_t hw, int32_t c1, int32_t c2, int32_t groups, float eps,
                         int32_t with_silu, void* workspace, size_t workspace_bytes, void* stream);
 /* The plugin's exact I/O contract (groupNormPlugin.cpp:136-160, enqueue :179-228): x / y fp16 NHWC (kHWC8), gamma / beta
- * fp32, one tensor, optional Swish (bSwish). One persistent kernel: tiles staged in shared memory by bulk TMA copies,
- * statistics visit + apply visit per tile, the second read served from L2 (csrc/groupnorm_stream.cu). The workspace
- * (one 64-bit partial slot per CTA, sample and group; replaces GroupNormPlugin::getWorkspaceSize :173-177) is sized by
- * sdeo_groupnorm_f16_workspace_bytes; the call presets the slots itself. eps IS applied, unlike
- * groupNormKernel.cu:190-194. */
+ * fp32, one tensor, optional Swish (bSwish). Three kernels behind one call (csrc/groupnorm_stream.cu; which one runs:
+ * sdeo_groupnorm_f16_variant): RESIDENT when a sample fits the shared memory of one thread-block cluster (one read + one
+ * write, workspace untouched); STREAMED otherwise (one persistent kernel: tiles staged in shared memory by bulk TMA copies,
+ * a statistics visit and an apply visit per tile, the second read served from L2 while it lasts); two launches for
+ * geometries neither takes (C > 4096 or more than 32 groups). The workspace (64-bit partial slots per CTA, sample and
+ * group, plus one (mean, rstd) slot per sample and group; replaces GroupNormPlugin::getWorkspaceSize :173-177) is sized by
+ * sdeo_groupnorm_f16_workspace_bytes; the call presets the slots itself. Requires C % 8 == 0, C % groups == 0,
+ * groups <= 64. eps IS applied, unlike groupNormKernel.cu:190-194. Results are deterministic (fixed summation order). */
 size_t sdeo_groupnorm_f16_workspace_bytes(int32_t n, int32_t hw, int32_t c, int32_t groups);
 /* Host-side view of that kernel's schedule (tests, tuning): plan[0..6] = tiles per sample, pixels per tile, apply lag in
  * tiles, grid size, dynamic shared memory bytes, tile buffer stride, tile buffers for `sms` SMs (<= 0: 148); returns 1 when the shape
