@@ -28,6 +28,7 @@ namespace sdeo {
 
 constexpr int kGSThreads = 512;             // arithmetic threads
 constexpr int kGSAll = kGSThreads + 32;     // + one control warp (loads, buffer recycling, ready flags)
+constexpr int kGSTeam = 16;                 // partial slots per team in the tree fold (one batch of loads)
 constexpr int kGSMaxBufs = 8;               // tile buffers per CTA: GSGeom::bufs of them are used
 constexpr int kGSSmemTotal = 227 * 1024 - 7 * 1024;  // dynamic shared memory budget (static arrays take the rest)
 constexpr unsigned long long kL2EvictFirst = 0x12F0000000000000ull;  // createpolicy.fractional.L2::evict_first, fraction 1.0
@@ -92,7 +93,7 @@ __device__ __forceinline__ uint32_t swish_pack(float t0, float t1) {
 }
 
 struct GSGeom {
-  int n, hw, C, groups, chunks, ppc, lag, bufs, two_level, ngroups, tile_stride;  // tile_stride: bytes between tile buffers (multiple of 128)
+  int n, hw, C, groups, chunks, ppc, lag, bufs, two_level, tree, ngroups, tile_stride;  // tile_stride: bytes between tile buffers (multiple of 128)
 };
 
 // A CTA's position in the visit sequence: unit u, visit v (0 statistics of tile u, 1 apply of tile u - lag).
@@ -170,26 +171,25 @@ gn_stream_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, 
     int k = 0, cur_img = -1, kg0 = 0, kg1 = 0;
     const int bpg = kGSBufs / gm.ngroups;  // buffers per thread group
     float2 my_mr = make_float2(0.f, 1.f);  // lane = group: (mean, rstd) of sample cur_img
-    // lane = group: folds sample img's P partial slots in slot order (the same order wherever it runs: deterministic);
-    // spins on slots that are not written yet (their writers' statistics visits all lie in LOWER units)
-    auto fold_partials = [&](int img) -> float2 {
-      float2 res = make_float2(0.f, 1.f);
+    // lane = group: sums `count` slots (stride `groups` words) in slot order - the same order wherever it runs: deterministic;
+    // spins on slots that are not written yet (their writers never wait on anything this warp holds back)
+    auto fold_slots = [&](const unsigned long long* first, int count, int what) -> float2 {
       float fs = 0.f, fq = 0.f;
       if (lane < groups) {
-        const unsigned long long* base = slots + (size_t)img * P * groups + lane;
+        const unsigned long long* base = first + lane;
         const long long t0 = clock64();
-        for (int j0 = 0; j0 < P; j0 += 16) {
+        for (int j0 = 0; j0 < count; j0 += 16) {
           unsigned long long v[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = j0 + i < P ? slot_peek(base + (size_t)(j0 + i) * groups) : 0ull;
+          for (int i = 0; i < 16; ++i) v[i] = j0 + i < count ? slot_peek(base + (size_t)(j0 + i) * groups) : 0ull;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            if (j0 + i >= P) break;
+            if (j0 + i >= count) break;
             uint32_t spins = 0;
             while ((uint32_t)(v[i] >> 32) == 0xFFFFFFFFu) {
               __nanosleep(32);
               if ((++spins & 0xFFFu) == 0 && clock64() - t0 > 4000000000LL) {
-                printf("sdeo: groupnorm_f16 waited too long for sample %d partial %d (block %d)\n", img, j0 + i, (int)blockIdx.x);
+                printf("sdeo: groupnorm_f16 waited too long for slot %d of %d (kind %d, block %d)\n", j0 + i, count, what, (int)blockIdx.x);
                 __trap();
               }
               v[i] = slot_peek(base + (size_t)(j0 + i) * groups);
@@ -198,16 +198,26 @@ gn_stream_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, 
             fq += __uint_as_float((uint32_t)(v[i] >> 32));
           }
         }
-        const float inv = 1.0f / ((float)hw * (float)cpg);
-        const float mean = fs * inv;
-        float var = fq * inv - mean * mean;
-        var = var < 0.f ? 0.f : var;
-        res = make_float2(mean, rsqrtf(var + eps));
       }
-      return res;
+      return make_float2(fs, fq);
     };
-    unsigned long long* finals = slots + (size_t)gm.n * P * groups;  // two-level fold: (mean, rstd) per (sample, group)
-    int next_fold = (int)blockIdx.x;                                 // folder duty: samples b, b + G, ... of CTA b
+    auto finish = [&](float2 sums) -> float2 {  // (sum, sum of squares) of a whole sample -> (mean, rstd)
+      const float inv = 1.0f / ((float)hw * (float)cpg);
+      const float mean = sums.x * inv;
+      float var = sums.y * inv - mean * mean;
+      var = var < 0.f ? 0.f : var;
+      return make_float2(mean, rsqrtf(var + eps));
+    };
+    // Slot areas: [n][P] partials, [n] (mean, rstd) rows ("finals"), [n][M] team sums ("mids", tree fold only).
+    unsigned long long* finals = slots + (size_t)gm.n * P * groups;
+    const int M = (P + kGSTeam - 1) / kGSTeam;  // teams of kGSTeam partial slots
+    unsigned long long* mids = finals + (size_t)gm.n * groups;
+    // sample img's sums: straight from the P partials, or (tree) from the M team sums other CTAs publish
+    auto sample_sums = [&](int img) -> float2 {
+      return gm.tree ? fold_slots(mids + (size_t)img * M * groups, M, 1) : fold_slots(slots + (size_t)img * P * groups, P, 0);
+    };
+    int next_fold = (int)blockIdx.x;  // folder duty: samples b, b + G, ... of CTA b
+    int next_team = (int)blockIdx.x;  // team duty (tree fold): (sample, team) pairs b, b + G, ... in sample-major order
     for (bool ok = gs_settle(it, tiles, lag, G); ok; ok = gs_next(it, tiles, lag, G), ++k) {
       // Each thread group owns bufs / ng buffers and walks them with its own visit counter: a barrier is then waited on by ONE
       // group, phase after phase (a group that skipped the other's phases could not use parity waits).
@@ -216,8 +226,17 @@ gn_stream_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, 
       const int buf = vg * bpg + kgv % bpg, use = kgv / bpg;
       // Folder duty (two-level fold): sample f is folded by CTA f mod G when that CTA first reaches a unit >= (f + 1) * chunks,
       // i.e. after every statistics tile of f in unit order and (lag >= chunks + G) before every apply visit of f.
+      // Tree fold (single-round regime, where the fold's latency is exposed): team duties first - they wait on partials only -
+      // then the folder sums M team slots instead of P partials: 2 dependent batches of loads instead of P / 16.
+      while (gm.tree && next_team < gm.n * M && it.u >= (next_team / M + 1) * chunks && !(hints & 0x100)) {
+        const int f = next_team / M, m = next_team - f * M;
+        const int cnt = min(kGSTeam, P - m * kGSTeam);
+        const float2 sums = fold_slots(slots + ((size_t)f * P + (size_t)m * kGSTeam) * groups, cnt, 2);
+        if (lane < groups) slot_publish(mids + ((size_t)f * M + m) * groups + lane, sums.x, sums.y);
+        next_team += G;
+      }
       while (gm.two_level && next_fold < gm.n && it.u >= (next_fold + 1) * chunks && !(hints & 0x100)) {
-        const float2 mr = fold_partials(next_fold);
+        const float2 mr = finish(sample_sums(next_fold));
         if (lane < groups) slot_publish(finals + (size_t)next_fold * groups + lane, mr.x, mr.y);
         next_fold += G;
       }
@@ -234,7 +253,7 @@ gn_stream_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, 
       if (it.v == 1) {
         if (img != cur_img && !(hints & 0x100)) {
           if (!gm.two_level) {
-            my_mr = fold_partials(img);  // first apply visit of this CTA in sample img: every CTA folds for itself
+            my_mr = finish(fold_slots(slots + (size_t)img * P * groups, P, 0));  // every CTA folds for itself
           } else if (lane < groups) {
             // the sample's folder CTA published (mean, rstd) in a lower unit than this one (lag >= chunks + G)
             const unsigned long long* fp = finals + (size_t)img * groups + lane;
@@ -733,6 +752,12 @@ static int gs_plan(int n, int hw, int c, int groups, int sms, int lag_env, GSGeo
   // (< (f + 1) * chunks + G) lies below the sample's first apply unit, or (lag == tiles) every CTA makes all its statistics
   // visits before its first apply visit and the remaining folds fire at the top of that one.
   g->two_level = (lag >= (long long)g->chunks + G || lag == tiles) && !getenv("SDEO_GN_F16_ONE_LEVEL") ? 1 : 0;
+  // tree fold: only where every duty fires before the CTA's first apply visit (lag == tiles) - team duties then wait on
+  // statistics visits only - and where the folder would otherwise walk more than two batches of slots
+  {
+    const long long P = g->chunks < (long long)g->ngroups * G ? g->chunks : (long long)g->ngroups * G;
+    g->tree = g->two_level && lag == tiles && P > 2 * kGSTeam && !getenv("SDEO_GN_F16_NO_TREE") ? 1 : 0;
+  }
   *grid = G;
   return 0;
 }
@@ -807,7 +832,7 @@ extern "C" size_t sdeo_groupnorm_f16_workspace_bytes(int32_t n, int32_t hw, int3
   (void)cudaGetLastError();
   if (gs_geometry(n, hw, c, sms, &g, &smem)) return two_pass;
   const size_t parts = (size_t)(g.chunks < 2 * sms ? g.chunks : 2 * sms);  // partial slots per sample (<= thread groups x grid size)
-  const size_t stream_bytes = (size_t)n * (parts + 1) * groups * sizeof(unsigned long long);  // partial slots + (mean, rstd) slots
+  const size_t stream_bytes = (size_t)n * (parts + 1 + (parts + kGSTeam - 1) / kGSTeam) * groups * sizeof(unsigned long long);  // partial + (mean, rstd) + team slots
   return stream_bytes > two_pass ? stream_bytes : two_pass;
 }
 
@@ -892,7 +917,8 @@ extern "C" int sdeo_groupnorm_nhwc_f16(const void* x, const float* gamma, const 
   int G = 0;
   if (two_pass || gs_plan(n, hw, c, groups, gs_sm_count(), lag_env, &g, &smem, &G))
     return groupnorm_f16_two_pass(x, gamma, beta, y, n, hw, c, groups, eps, with_silu, workspace, workspace_bytes, stream);
-  const size_t slot_bytes = (size_t)n * ((size_t)(g.chunks < g.ngroups * G ? g.chunks : g.ngroups * G) + 1) * groups * sizeof(unsigned long long);
+  const size_t nparts_ = (size_t)(g.chunks < g.ngroups * G ? g.chunks : g.ngroups * G);
+  const size_t slot_bytes = (size_t)n * (nparts_ + 1 + (nparts_ + kGSTeam - 1) / kGSTeam) * groups * sizeof(unsigned long long);
   if (workspace_bytes < slot_bytes)
     return set_error(SDEO_EINVAL, "groupnorm_f16: workspace too small (sdeo_groupnorm_f16_workspace_bytes)");
   if (cudaMemsetAsync(workspace, 0xFF, slot_bytes, st) != cudaSuccess) {  // every partial slot: "not written"
