@@ -320,6 +320,11 @@ def _gn_stream_protocol_model(lib, n, c, h, w, ng, bufs, sms=148, verbose=False)
     two_level = lag >= chunks + grid or lag == tiles
     W = ng * grid
     P = min(chunks, W)
+    team = 16
+    M = -(-P // team)
+    tree = two_level and lag == tiles and P > 2 * team  # gs_plan's rule
+    mids = [set() for _ in range(n)]
+    next_team = list(range(grid))
     cap = 2 * tiles // grid + 8
     seqs = []
     for b in range(grid):
@@ -347,8 +352,16 @@ def _gn_stream_protocol_model(lib, n, c, h, w, ng, bufs, sms=148, verbose=False)
                 kind, t = s[k]
                 u = unit(kind, t)
                 blocked = False
-                while two_level and next_fold[b] < n and u >= (next_fold[b] + 1) * chunks:
-                    if len(published[next_fold[b]]) < P:
+                while tree and next_team[b] < n * M and u >= (next_team[b] // M + 1) * chunks:
+                    f, m = divmod(next_team[b], M)
+                    if not all(j in published[f] for j in range(m * team, min(P, (m + 1) * team))):
+                        blocked = True
+                        break
+                    mids[f].add(m)
+                    next_team[b] += grid
+                    progress = True
+                while not blocked and two_level and next_fold[b] < n and u >= (next_fold[b] + 1) * chunks:
+                    if (len(mids[next_fold[b]]) < M) if tree else (len(published[next_fold[b]]) < P):
                         blocked = True
                         break
                     finals[next_fold[b]] = True
@@ -404,7 +417,7 @@ def _gn_stream_protocol_model(lib, n, c, h, w, ng, bufs, sms=148, verbose=False)
                                    (5, 1280, 33, 17), (4, 256, 128, 128), (8, 256, 256, 256)])
 def test_groupnorm_f16_protocol_model(shape):
     """Discrete-event model of the streamed GroupNorm's protocol (csrc/groupnorm_stream.cu) on the library's own plan and visit
-    lists: an in-order control warp per CTA (folder duty, buffer recycling, statistics wait before an apply visit), one or two
+    lists: an in-order control warp per CTA (team and folder duties, buffer recycling, statistics wait before an apply visit), one or two
     thread groups, partial slots published once per (CTA, group, sample). Every visit must complete for every buffer count:
     no deadlock, no slot written twice."""
     from stablediffusioneo_b200 import _lib
