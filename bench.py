@@ -37,8 +37,27 @@ LATENT_HW = (32, 48)
 CFG_SCALE = 9.0
 WORKLOAD = "ControlNet-canny SD1.5 256x384 batch 1, DDIM 20 steps, CFG 9.0 (BASELINE configs[1])"
 FLOPS_PER_STEP = 740.0e9          # one DDIM step = 2 x (ControlNet 95.6 + UNet 274.4) GF at 32x48
-CONV_DRAM_BYTES_PER_LAUNCH = 10287801  # ncu dram__bytes_read.sum + write.sum over one step's 289 conv launches / 289 (profiles/r01e_launches_step_summary.txt)
 WEIGHT_BYTES_PER_STEP = 2.442e9   # bf16 UNet 1.719 GB + ControlNet 0.723 GB, streamed once per step (cond+uncond batched)
+# BASELINE.md §2 (forward hooks on the reference's modules): FLOPs of ONE DDIM step = 2 x (ControlNet + UNet) for ONE
+# image, and of one VAE decode, per latent size
+STEP_FLOPS = {(32, 48): 740.0e9, (64, 64): 2173.2e9, (96, 96): 5843.2e9}
+VAE_FLOPS = {(32, 48): 934.9e9, (64, 64): 2514.5e9, (96, 96): 5754.3e9}
+VAE_GN_ELEMS = {(32, 48): 172.2e6, (64, 64): 459.3e6, (96, 96): 1033.4e6}   # GroupNorm elements per decode (4 B each in bf16)
+
+
+def conv_dram_bytes_per_launch():
+    """dram__bytes_read.sum + dram__bytes_write.sum per conv_gemm_kernel launch, from the newest committed ncu launch list
+    of the step graph (profiles/*launches_step_summary.txt, written by tools/ncu_launch_summary.py from the ncu CSV of
+    `tools/profile_step.py --graph`). None if no such profile is committed."""
+    import glob
+    import re
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*launches_step_summary.txt"))):
+        with open(path) as f:
+            m = re.search(r"conv_gemm_kernel DRAM traffic per launch: (\d+) bytes", f.read())
+        if m:
+            best = (int(m.group(1)), os.path.relpath(path, ROOT))
+    return best
 
 
 def peaks():
@@ -51,13 +70,13 @@ def peaks():
     return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
 
 
-def host_inputs(pin):
+def host_inputs(pin, latent_hw=LATENT_HW, batch=1):
     """Synthetic inputs: x_T seed 2946901; contexts seeds 1/2; a binary edge map as the hint."""
-    h, w = LATENT_HW
-    x_T = torch.randn((1, 4, h, w), generator=torch.Generator().manual_seed(2946901))
-    ctx_c = torch.randn((1, 77, 768), generator=torch.Generator().manual_seed(1))
-    ctx_u = torch.randn((1, 77, 768), generator=torch.Generator().manual_seed(2))
-    r = torch.rand((1, 1, 8 * h, 8 * w), generator=torch.Generator().manual_seed(7))
+    h, w = latent_hw
+    x_T = torch.randn((batch, 4, h, w), generator=torch.Generator().manual_seed(2946901))
+    ctx_c = torch.randn((batch, 77, 768), generator=torch.Generator().manual_seed(1))
+    ctx_u = torch.randn((batch, 77, 768), generator=torch.Generator().manual_seed(2))
+    r = torch.rand((batch, 1, 8 * h, 8 * w), generator=torch.Generator().manual_seed(7))
     hint = (r > 0.9).float().expand(-1, 3, -1, -1).contiguous()
     ts = [x_T, ctx_c, ctx_u, hint]
     if pin:
@@ -143,6 +162,14 @@ def cpu_reference_steps(max_steps, budget_s):
     return n, dt, cores
 
 
+def main_config(world):
+    """The `config` object of BOTH arms (same keys and values, so the driver's same_config check compares like with like)."""
+    return {"workload": WORKLOAD, "latent": list(LATENT_HW), "ddim_steps": S_DDIM, "cfg_scale": CFG_SCALE,
+            "batch_per_gpu": 1, "parallelism": f"replicas x{world} (one image stream per GPU, no collective in the loop)",
+            "l2_policy": "no flush needed: 2.44 GB of bf16 weights are streamed every step (>> 126 MB L2)",
+            "weights": "random-init (N(0, var) per SURVEY 8d)"}
+
+
 def run_reference_arm(args, rank):
     if rank != 0:
         return
@@ -152,7 +179,7 @@ def run_reference_arm(args, rank):
         "impl": "reference", "metric": "denoise_steps_per_s", "value": v, "unit": "steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "latent": list(LATENT_HW), "ddim_steps": S_DDIM, "cfg_scale": CFG_SCALE},
+        "config": main_config(args.gpus),
         "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
                          "sample": f"{n} of {args.steps} DDIM steps executed on the host CPU (each = 2 x (ControlNet+UNet) fp32 "
                                    f"+ CFG + DDIM update, oracle port of the reference modules; 1 extra warm-up step)"},
@@ -212,7 +239,9 @@ def conv_roofline(eng, pk):
             "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
             # dram__bytes_read+write per launch, averaged over the conv launches of one step (ncu --graph-profiling node,
             # profiles/r01c_launches_step_summary.txt; cold-cache replays; algorithmic: 2.442 GB of weights / launches)
-            "traffic": CONV_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes/launch (ncu, cold cache)",
+            "traffic": (conv_dram_bytes_per_launch() or (None, None))[0],
+            "traffic_unit": "bytes/launch (ncu dram__bytes_read+write, cold cache)",
+            "traffic_source": (conv_dram_bytes_per_launch() or (None, None))[1],
             "launches_per_step": conv["launches"], "flops_per_step": total_flops,
             "kernel_ms_per_step": conv_us * 1e-3, "kernel_busy_ms_per_step": conv["busy_us"] * 1e-3,
             "avg_launch_us": conv_us / conv["launches"],
@@ -227,6 +256,163 @@ def conv_roofline(eng, pk):
                            for k, v in summ["kinds"].items()},
             "step_trace_span_us": summ["span_us"], "step_trace_busy_union_us": summ["busy_union_us"],
             "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)"}
+
+
+def timed_steps(eng, steps, warmup, dist, dev, min_seconds=1.0, clocks_for=None):
+    """K device-resident steps of `eng` (20-step images, latent rewound on the device between images), repeated R times
+    so that the timed region lasts >= min_seconds (the same K-step block every repeat). CUDA events on the launching
+    stream, barrier + synchronize on both sides, max over ranks. Returns (ms per K-step block, R, eager launches, clocks)."""
+    from stablediffusioneo_b200 import ops
+    pos = [0]
+
+    def run_steps(k):
+        for _ in range(k):
+            if pos[0] % S_DDIM == 0:
+                eng.reset_latent()
+            eng.step()
+            pos[0] += 1
+
+    eng.reset_latent()
+    run_steps(max(warmup, 3))
+    pos[0] = 0
+    # size the repeat count from a short probe
+    s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    s0.record()
+    run_steps(3)
+    e0.record()
+    torch.cuda.synchronize()
+    est_ms = max(s0.elapsed_time(e0) / 3.0, 1e-3)
+    repeats = max(1, int(math.ceil(min_seconds * 1e3 / (est_ms * steps))))
+    if dist is not None:
+        t = torch.tensor([repeats], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        repeats = int(t.item())
+    pos[0] = 0
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    clocks = ClockSampler(clocks_for) if clocks_for is not None else None
+    n0 = ops.LAUNCHES
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    start.record()
+    run_steps(steps * repeats)
+    end.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    elapsed_ms = start.elapsed_time(end)
+    eager = ops.LAUNCHES - n0
+    if dist is not None:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    return elapsed_ms / repeats, repeats, eager, (clocks.stop() if clocks is not None else None)
+
+
+def denoise_config(model, latent_hw, batch, steps, warmup, dist, dev, world, pk, name):
+    """One of the other BASELINE configs as a device-resident + end-to-end measurement: builds its own engine."""
+    from stablediffusioneo_b200.cldm.ddim_hacked import DDIMSampler
+    sampler = DDIMSampler(model)
+    x_T, ctx_c, ctx_u, hint = host_inputs(pin=True, latent_hw=latent_hw, batch=batch)
+    cond = {"c_concat": [hint], "c_crossattn": [ctx_c]}
+    uncond = {"c_concat": [hint], "c_crossattn": [ctx_u]}
+
+    def sample():
+        out, _ = sampler.sample(S_DDIM, batch, (4,) + tuple(latent_hw), cond, verbose=False, eta=0.0, x_T=x_T,
+                                unconditional_guidance_scale=CFG_SCALE, unconditional_conditioning=uncond)
+        return out.to("cpu")
+
+    out = sample()
+    assert torch.isfinite(out).all()
+    sample()
+    eng = sampler._engine
+    ms_block, repeats, _, _ = timed_steps(eng, steps, warmup, dist, dev, min_seconds=0.5)
+    ms_step = ms_block / steps
+    n_img = 2
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(n_img):
+        sample()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    flops = STEP_FLOPS[tuple(latent_hw)] * batch
+    tf = flops / (ms_step * 1e-3) / 1e12
+    res = {"name": name, "latent": list(latent_hw), "batch_per_gpu": batch, "n_gpus": world,
+           "steps_per_s": world * 1e3 / ms_step, "ms_per_step": ms_step,
+           "images_per_s": world * batch * 1e3 / (ms_step * S_DDIM), "timed_steps": steps * repeats,
+           "launches_per_step": getattr(eng, "launches_per_step", None),
+           "e2e": {"steps_per_s": world * n_img * S_DDIM / e2e_s, "images_per_s": world * n_img * batch / e2e_s, "images": n_img * batch,
+                   "h2d_bytes_per_step": (x_T.numel() + ctx_c.numel() + ctx_u.numel() + 2 * hint.numel()) * 4 / S_DDIM,
+                   "d2h_bytes_per_step": x_T.numel() * 4 / S_DDIM},
+           "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                        "frac": tf / pk["bf16_sustained"], "flops_per_step": flops,
+                        "note": "whole step (all kernels) vs BASELINE.md section 2 FLOPs; sustained cuBLAS bf16 peak"}}
+    del sampler._engine
+    sampler._engine = None
+    torch.cuda.empty_cache()
+    return res
+
+
+def vae_config(model, latent_hw, batch, dev, pk, name, iters=5):
+    """VAE decode (latents resident -> uint8 NHWC image on the device) and end to end (host latents -> host image)."""
+    h, w = latent_hw
+    z = (torch.randn((batch, 4, h, w), generator=torch.Generator().manual_seed(11)) * 0.18215 * 4.0).pin_memory()
+    zd = z.to(dev)
+    for _ in range(2):
+        u8 = model.decode_first_stage_u8(zd)
+    torch.cuda.synchronize()
+    assert u8.shape == (batch, 8 * h, 8 * w, 3)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        u8 = model.decode_first_stage_u8(zd)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / iters
+    t0 = time.perf_counter()
+    for _ in range(2):
+        img = model.decode_first_stage_u8(z.to(dev, non_blocking=True)).cpu()
+    e2e_s = (time.perf_counter() - t0) / 2
+    flops = VAE_FLOPS[tuple(latent_hw)] * batch
+    gn_bytes = VAE_GN_ELEMS[tuple(latent_hw)] * batch * 4.0
+    tf = flops / (ms * 1e-3) / 1e12
+    return {"name": name, "latent": list(latent_hw), "batch": batch, "images_per_s": batch * 1e3 / ms, "ms_per_batch": ms,
+            "e2e": {"images_per_s": batch / e2e_s, "h2d_bytes": z.numel() * 4, "d2h_bytes": img.numel()},
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                         "frac": tf / pk["bf16_sustained"], "flops_per_batch": flops,
+                         "groupnorm_bytes": gn_bytes, "groupnorm_hbm_floor_ms": gn_bytes / (pk["hbm_gbs"] * 1e9) * 1e3,
+                         "note": "whole decode vs BASELINE.md section 2 FLOPs; the GroupNorm floor is 4 B/element at the "
+                                 "measured HBM copy bandwidth"}}
+
+
+def other_configs(model, args, dist, dev, world, pk, rank):
+    """The other BASELINE.json configs (and batch > 1 images/s at 256x384) measured in the same run. N > 1: only
+    configs[2] (512x512, one image per GPU, sharded over the ranks). Each entry is guarded: a failure is reported in
+    place and never costs the headline line."""
+    jobs = [("configs[2] ControlNet-canny SD1.5 512x512, 1 image per GPU, DDIM 20, CFG 9", "denoise", (64, 64), 1, 20)]
+    if world == 1:
+        jobs += [("configs[3] SD1.5 UNet+ControlNet 768x768 batch 4, DDIM 20, CFG 9", "denoise", (96, 96), 4, 10),
+                 ("256x384 batch 4 per GPU (images/s)", "denoise", (32, 48), 4, 20),
+                 ("256x384 batch 8 per GPU (images/s)", "denoise", (32, 48), 8, 20),
+                 ("configs[4] VAE decode 512x512 batch 16", "vae", (64, 64), 16, 0),
+                 ("VAE decode 256x384 batch 1 (the configs[1] image)", "vae", (32, 48), 1, 0)]
+    out = []
+    for name, kind, hw, batch, steps in jobs:
+        try:
+            if kind == "denoise":
+                out.append(denoise_config(model, hw, batch, steps, 3, dist, dev, world, pk, name))
+            else:
+                out.append(vae_config(model, hw, batch, dev, pk, name))
+        except Exception as ex:  # noqa: BLE001
+            out.append({"name": name, "error": f"{type(ex).__name__}: {ex}"[:300]})
+            if dist is not None:
+                raise  # ranks must not diverge around collectives
+    return out
 
 
 def run_gpu_arm(args, rank, world, local_rank):
@@ -267,44 +453,14 @@ def run_gpu_arm(args, rank, world, local_rank):
     eng = sampler._engine
     launches_per_step = getattr(eng, "launches_per_step", None)
 
-    # ---------------- value: K steps, device-resident, CUDA events, max over ranks ----------------
-    pos = [0]
-
-    def run_steps(k):
-        for _ in range(k):
-            if pos[0] % S_DDIM == 0:
-                eng.reset_latent()
-            eng.step()
-            pos[0] += 1
-
-    eng.reset_latent()
-    pos[0] = 0
-    run_steps(max(args.warmup, 3))
-    pos[0] = 0
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    clocks = ClockSampler(local_rank) if rank == 0 else None
-    n0 = ops.LAUNCHES
-    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    start.record()
-    run_steps(args.steps)
-    end.record()
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    elapsed_ms = start.elapsed_time(end)
-    eager_launches = ops.LAUNCHES - n0   # reset_latent kernels issued outside the graph
-    if dist is not None:
-        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
-    clock_info = clocks.stop() if clocks is not None else None
+    # ---------------- value: K steps (x R repeats, >= 1 s), device-resident, CUDA events, max over ranks ----------------
+    block_ms, repeats, eager_launches, clock_info = timed_steps(eng, args.steps, args.warmup, dist, dev, min_seconds=1.0,
+                                                                clocks_for=local_rank if rank == 0 else None)
+    elapsed_ms = block_ms
     value = world * args.steps / (elapsed_ms * 1e-3)
 
-    # ---------------- e2e: public API, host buffers ----------------
-    n_img = max(1, math.ceil(args.steps / S_DDIM))
+    # ---------------- e2e: public API, host buffers, >= 10 images ----------------
+    n_img = max(10, math.ceil(args.steps / S_DDIM))
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -329,7 +485,7 @@ def run_gpu_arm(args, rank, world, local_rank):
 
     # ---------------- full image (sample + VAE decode + uint8 image to host): p50 latency ----------------
     img_lat = []
-    for _ in range(3):
+    for _ in range(5):
         t1 = time.perf_counter()
         samples, _ = sampler.sample(S_DDIM, 1, (4,) + LATENT_HW, cond, verbose=False, eta=0.0, x_T=x_T,
                                     unconditional_guidance_scale=CFG_SCALE, unconditional_conditioning=uncond)
@@ -338,27 +494,29 @@ def run_gpu_arm(args, rank, world, local_rank):
     img_lat.sort()
     assert u8.shape == (1, 256, 384, 3)
 
+    roof = conv_roofline(eng, pk) if rank == 0 else None
+    extra = [] if args.no_other_configs else other_configs(model, args, dist, dev, world, pk, rank)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    roof = conv_roofline(eng, pk)
     step_ms = elapsed_ms / args.steps
+    cfg = main_config(world)
+    cfg["cuda_graph"] = eng.graph is not None
     line = {
         "metric": "denoise_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "latent": list(LATENT_HW), "ddim_steps": S_DDIM, "cfg_scale": CFG_SCALE,
-                   "batch_per_gpu": 1, "parallelism": f"replicas x{world} (one image stream per GPU, no collective in the loop)",
-                   "l2_policy": "no flush needed: 2.44 GB of bf16 weights are streamed every step (>> 126 MB L2)",
-                   "cuda_graph": eng.graph is not None, "weights": "random-init (device-side N(0, var) per SURVEY 8d)"},
+        "config": cfg,
+        "timed_repeats": repeats, "timed_steps": repeats * args.steps,
         "images_per_s": value / S_DDIM,
         "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d / S_DDIM, "d2h_bytes_per_step": d2h / S_DDIM,
                 "images": n_img, "p50_denoise_latency_ms": 1000.0 * lat[len(lat) // 2],
                 "api": "DDIMSampler.sample(S=20, x_T/hint/context on pinned host memory) -> latents on host"},
         "p50_image_latency_ms": 1000.0 * img_lat[len(img_lat) // 2],
-        "gpu_launches": (launches_per_step or 0) * args.steps + eager_launches,
+        "gpu_launches": ((launches_per_step or 0) * args.steps * repeats + eager_launches) // repeats,
         "launches_per_step": launches_per_step,
         "clocks": clock_info,
         "roofline": roof,
@@ -366,6 +524,10 @@ def run_gpu_arm(args, rank, world, local_rank):
                           "tflops": FLOPS_PER_STEP / (step_ms * 1e-3) / 1e12,
                           "weight_stream_frac": WEIGHT_BYTES_PER_STEP / (step_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
                           "note": "whole step vs 740 GFLOP/step tensor bound and 2.442 GB/step weight-streaming HBM bound"},
+        "other_configs": extra,
+        "quality_gate": "compute_score PD (Inception-2048 features, compute_score.py:11-17) cannot run: pytorch_fid and its "
+                        "pt_inception weights are in neither this image nor the GPU box (no network); the parity tests gate "
+                        "the final uint8 image by PSNR >= 40 dB against the reference's image instead",
     }
     if world == 1 and not args.no_cpu_baseline:
         n, dt, cores = cpu_reference_steps(2, budget_s=25.0)
@@ -384,6 +546,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="sdeo", choices=["sdeo", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the other BASELINE configs (quick runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

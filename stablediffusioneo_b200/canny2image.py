@@ -37,7 +37,15 @@ class hackathon:
             kw = {"cond_stage_config": {}} if (with_text_encoder and config_path is None) else {}
             model = create_model(config_path, device=self.device, with_text_encoder=with_text_encoder, **kw)
             if ckpt_path is not None:
-                model.load_state_dict(load_state_dict(ckpt_path, location=str(self.device)), strict=False)
+                # the reference loads strictly (canny2image_torch.py:20); here the checkpoint may carry keys this object
+                # does not hold (cond_stage_model.* without a text encoder, the VAE encoder, position_ids), but every
+                # parameter of the model must be in it -- a partial checkpoint would leave random / zero-conv weights
+                res = model.load_state_dict(load_state_dict(ckpt_path, location=str(self.device)), strict=False)
+                if res.missing_keys:
+                    raise RuntimeError(f"checkpoint {ckpt_path} lacks {len(res.missing_keys)} parameters of the model, e.g. "
+                                       f"{res.missing_keys[:5]}")
+        if self.device.type == "cuda":
+            torch.cuda.set_device(self.device)  # ops launch on the current device's stream
         self.model = model.to(self.device).eval()
         self.ddim_sampler = DDIMSampler(self.model)
 

@@ -280,29 +280,48 @@ class ControlLDM(nn.Module):
         self.scale_factor = scale_factor
         self.channels = unet_kw["in_channels"]
         self.num_timesteps = int(timesteps)
+        self._schedule_args = (int(timesteps), linear_start, linear_end)
+        self.register_schedule()
+        self._hint_cache = None
+        # first eager call of each layer shape picks its tile / split-K configuration (SDEO_NO_AUTOTUNE=1: heuristics only)
+        ops.set_autotune(not os.environ.get("SDEO_NO_AUTOTUNE"))
+
+    def register_schedule(self, device=None):
+        """The DDPM schedule buffers DDIMSampler reads (ddpm.py's register_schedule: linear betas, cumulative alphas).
+        Non-persistent, so they are not checkpoint keys; callable again after constructing the module on `meta`."""
+        timesteps, linear_start, linear_end = self._schedule_args
         betas = make_beta_schedule("linear", timesteps, linear_start=linear_start, linear_end=linear_end)
         alphas_cumprod = np.cumprod(1.0 - betas, axis=0)
-        f32 = lambda a: torch.tensor(a, dtype=torch.float32)
+        f32 = lambda a: torch.tensor(a, dtype=torch.float32, device=device)
         self.register_buffer("betas", f32(betas), persistent=False)
         self.register_buffer("alphas_cumprod", f32(alphas_cumprod), persistent=False)
         self.register_buffer("alphas_cumprod_prev", f32(np.append(1.0, alphas_cumprod[:-1])), persistent=False)
         self.register_buffer("sqrt_alphas_cumprod", f32(np.sqrt(alphas_cumprod)), persistent=False)
         self.register_buffer("sqrt_one_minus_alphas_cumprod", f32(np.sqrt(1.0 - alphas_cumprod)), persistent=False)
-        self._hint_cache = None
-        # first eager call of each layer shape picks its tile / split-K configuration (SDEO_NO_AUTOTUNE=1: heuristics only)
-        ops.set_autotune(not os.environ.get("SDEO_NO_AUTOTUNE"))
 
     @property
     def device(self):
         return self.betas.device
 
+    def weights_fingerprint(self, first_stage=False):
+        """Identity + version of every parameter a captured engine bakes in (packed / folded weights, time-embedding
+        tables, hoisted K/V, the hint features): changes after load_state_dict(), an optimizer step or any other in-place
+        update, and when a parameter is replaced. Engines and caches key on it so that they never replay stale weights."""
+        mods = [self.model, self.control_model] + ([self.first_stage_model] if first_stage else [])
+        h = 0
+        for m in mods:
+            for p in m.parameters():
+                h = hash((h, p.data_ptr(), p._version))
+        return h
+
     # ---- hoisted, loop-invariant pieces ------------------------------------------------------------------
     def guided_hint(self, hint):
         """input_hint_block(hint), cached while the caller keeps passing the same (unmodified) hint tensor object."""
         c = self._hint_cache
-        if c is None or c[0]() is not hint or c[1] != hint._version:
+        wkey = util._param_key(*self.control_model.input_hint_block.parameters())
+        if c is None or c[0]() is not hint or c[1] != hint._version or c[3] != wkey:
             import weakref
-            self._hint_cache = (weakref.ref(hint), hint._version, self.control_model.run_hint(to_internal(hint)))
+            self._hint_cache = (weakref.ref(hint), hint._version, self.control_model.run_hint(to_internal(hint)), wkey)
         return self._hint_cache[2]
 
     def eps_internal(self, x, timesteps, ctx, guided_hint):

@@ -112,11 +112,18 @@ class DDIMSampler(object):
             return False  # eta > 0 draws fresh noise every step: generic path
         if not isinstance(cond, dict) or self.model.parameterization != "eps":
             return False
+        conds = [cond]
         if uncond is not None and scale != 1.0:
             if not isinstance(uncond, dict):
                 return False
             if (cond["c_concat"] is None) != (uncond["c_concat"] is None):
                 return False  # guess mode: the uncond pass skips the ControlNet -> two different graphs
+            conds.append(uncond)
+        for cd in conds:
+            # the engine's static buffers are sized from ONE context and ONE hint tensor per conditioning; lists with
+            # several entries (concatenated along dim 1 by apply_model, cldm/cldm.py:331-336) take the generic path
+            if len(cd["c_crossattn"]) != 1 or (cd["c_concat"] is not None and len(cd["c_concat"]) != 1):
+                return False
         return True
 
     @torch.no_grad()
@@ -290,21 +297,21 @@ class DDIMSampler(object):
             eng = self._engine = _Engine(self.model, key, self.use_cuda_graph)
         time_range = np.flip(self.ddim_timesteps)
         rows = [self._coef_row(S - i - 1, scale if guided else 1.0) for i in range(S)]
-        img, pred_x0, first = eng.run(x_T, cond, uncond if guided else None, [int(t) for t in time_range], rows)
-        # the reference logs x_inter / pred_x0 when index % log_every_t == 0 or index == S-1 (ddim_hacked.py:174-176):
-        # with S <= log_every_t that is the first step (index S-1) and the last (index 0)
-        inter = {'x_inter': [x_T, first[0], img], 'pred_x0': [x_T, first[1], pred_x0]}
-        if S == 1:
-            inter = {'x_inter': [x_T, img], 'pred_x0': [x_T, pred_x0]}
+        # the reference logs x_inter / pred_x0 when index % log_every_t == 0 or index == S-1 (ddim_hacked.py:174-176)
+        log_at = [i for i in range(S) if (S - i - 1) % log_every_t == 0 or i == 0]
+        img, pred_x0, logged = eng.run(x_T, cond, uncond if guided else None, [int(t) for t in time_range], rows, log_at)
+        inter = {'x_inter': [x_T] + [l[0] for l in logged], 'pred_x0': [x_T] + [l[1] for l in logged]}
         return img, inter
 
 
 class _EngineKey:
     def __init__(self, model, x_T, cond, uncond, S, graph):
         hint = cond["c_concat"]
+        # weights_fingerprint: the captured graphs, time-embedding tables and hoisted K/V bake in buffers derived from the
+        # parameters; after load_state_dict() or any in-place update the engine is rebuilt instead of replaying old weights
         self.t = (id(model), tuple(x_T.shape), tuple(cond["c_crossattn"][0].shape),
                   None if hint is None else tuple(hint[0].shape), uncond is not None, S, graph,
-                  tuple(model.control_scales), model.only_mid_control)
+                  tuple(model.control_scales), model.only_mid_control, model.weights_fingerprint())
 
     def __eq__(self, other):
         return isinstance(other, _EngineKey) and self.t == other.t
@@ -330,8 +337,6 @@ class _Engine:
         self.x_lat = torch.empty((b, c, h, w), dtype=torch.float32, device=dev)
         self.x_keep = torch.empty_like(self.x_lat)
         self.pred_x0 = torch.empty_like(self.x_lat)
-        self.first_x = torch.empty_like(self.x_lat)
-        self.first_p = torch.empty_like(self.x_lat)
         self.x_in = torch.empty((nb, h, w, 8), dtype=BF16, device=dev)
         self.ts_table = torch.zeros((S,), dtype=torch.int64, device=dev)
         self.coef = torch.zeros((S, 8), dtype=torch.float32, device=dev)
@@ -498,13 +503,13 @@ class _Engine:
         else:
             self._step()
 
-    def run(self, x_T, cond, uncond, ts, rows):
+    def run(self, x_T, cond, uncond, ts, rows, log_at=()):
+        """log_at: step numbers after which (x_{t-1}, pred_x0) are returned as copies (the reference's intermediates)."""
         self.prepare(x_T, cond, uncond, ts, rows)
-        first = None
+        log_at = set(log_at)
+        logged = []
         for i in range(self.S):
             self.step()
-            if i == 0:
-                self.first_x.copy_(self.x_lat)
-                self.first_p.copy_(self.pred_x0)
-                first = (self.first_x, self.first_p)
-        return self.x_lat.clone(), self.pred_x0.clone(), first
+            if i in log_at:
+                logged.append((self.x_lat.clone(), self.pred_x0.clone()))
+        return self.x_lat.clone(), self.pred_x0.clone(), logged

@@ -37,6 +37,10 @@ def _req(t, dtype, name):
         return
     if not t.is_cuda:
         raise _lib.SdeoError(f"{name}: expected a CUDA tensor (there is no CPU path)")
+    if t.device.index != torch.cuda.current_device():
+        # ops launch on the CURRENT device's current stream; a tensor of another device would be dereferenced there
+        raise _lib.SdeoError(f"{name}: tensor lives on {t.device} but the current CUDA device is "
+                             f"cuda:{torch.cuda.current_device()} (wrap the call in torch.cuda.device(...))")
     if t.dtype != dtype:
         raise _lib.SdeoError(f"{name}: expected dtype {dtype}, got {t.dtype}")
     if not t.is_contiguous():
@@ -50,6 +54,7 @@ class _Workspaces:
     def __init__(self):
         self._conv = {}
         self._gn = {}
+        self._retired = []
         self.slot = 0
 
     def conv(self, device):
@@ -62,10 +67,15 @@ class _Workspaces:
             self._conv[key] = ws
         return ws
 
-    def gn(self, device, nbytes):
-        key = (device.index, self.slot)
+    def gn(self, device, nbytes, kind="gn"):
+        """kind: "gn" (engine GroupNorm, zero-initialised barrier words) / "gn_f16" (the plugin-contract kernels, which
+        preset their slots to 0xFF) -- separate buffers. A workspace that has been handed out is never freed: captured CUDA
+        graphs may hold its address; growing allocates a new buffer and keeps the old one alive."""
+        key = (device.index, self.slot, kind)
         ws = self._gn.get(key)
         if ws is None or ws.numel() < nbytes:
+            if ws is not None:
+                self._retired.append(ws)
             ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)  # barrier words start at zero
             self._gn[key] = ws
         return ws
@@ -311,7 +321,7 @@ def groupnorm_f16(x, gamma, beta, eps=1e-5, silu=False, groups=32):
     _req(beta, torch.float32, "beta")
     n, h, w, c = x.shape
     out = torch.empty_like(x)
-    ws = _workspaces.gn(x.device, lib.sdeo_groupnorm_f16_workspace_bytes(n, h * w, c, groups))
+    ws = _workspaces.gn(x.device, lib.sdeo_groupnorm_f16_workspace_bytes(n, h * w, c, groups), kind="gn_f16")
     global LAUNCHES
     check(lib.sdeo_groupnorm_nhwc_f16(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), n, h * w, c, groups, float(eps),
                                       1 if silu else 0, _ptr(ws), ws.numel(), _stream()), "groupnorm_f16")

@@ -43,17 +43,22 @@ def vae_kwargs(vcfg):
 
 
 def build_control_ldm(cfg, vcfg, device, weights=None):
-    """Our ControlLDM on `device`, loaded (strict) with the oracle's weights under the SD checkpoint prefixes."""
+    """Our ControlLDM on `device`, loaded (strict) with the oracle's weights under the SD checkpoint prefixes.
+    The modules are constructed on the `meta` device and take the oracle's CPU tensors by assignment, then move to the
+    GPU as plain host->device copies: no torch init kernels (uniform_ / fill_) are launched, so a profiler's launch list
+    of a test or of smoke() starts with the library's own kernels."""
     from stablediffusioneo_b200.cldm.cldm import ControlLDM
     sd_unet, sd_cn, sd_vae = weights if weights is not None else oracle_weights(cfg, vcfg)
-    with torch.device(device):
+    with torch.device("meta"):
         model = ControlLDM(unet_config=unet_kwargs(cfg), first_stage_config=vae_kwargs(vcfg)).eval()
     sd = {}
     sd.update({"model.diffusion_model." + k: v for k, v in sd_unet.items()})
     sd.update({"control_model." + k: v for k, v in sd_cn.items()})
     sd.update({"first_stage_model." + k: v for k, v in sd_vae.items()})
-    missing, unexpected = model.load_state_dict(sd, strict=True)
+    missing, unexpected = model.load_state_dict(sd, strict=True, assign=True)
     assert not missing and not unexpected
+    model.register_schedule(device="cpu")   # the (non-persistent) schedule buffers were created on meta
+    model = model.to(device)
     for p in model.parameters():
         p.requires_grad_(False)
     return model

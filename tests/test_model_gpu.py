@@ -158,7 +158,7 @@ def test_sd15_eps_single_step(sd15, cuda_device):
 
 
 def test_sd15_eps_teacher_forced(sd15, cuda_device):
-    """Feed the reference's own x_t at several steps of its 20-step trajectory; compare eps per step."""
+    """Feed the reference's own x_t at EVERY step of its 20-step trajectory; compare eps (cond and uncond) per step."""
     model, g = sd15
     _, cond, uncond = inputs_on(O.SD15, 32, 48, cuda_device, hint=canny_hint())
     # reconstruct the reference trajectory's x_t from its eps calls: cond/uncond alternate (ddim_hacked.py:190-191)
@@ -169,10 +169,10 @@ def test_sd15_eps_teacher_forced(sd15, cuda_device):
     for i in range(20):
         index = 19 - i
         e_c_ref, e_u_ref = eps_calls[2 * i], eps_calls[2 * i + 1]
-        if i in (0, 5, 10, 15, 19):
-            t = _ts(cuda_device, int(ts[2 * i]))
-            e_c = model.apply_model(x.to(cuda_device), t, cond)
-            worst = max(worst, rel_l2(e_c, e_c_ref))
+        t = _ts(cuda_device, int(ts[2 * i]))          # every one of the 20 steps, cond and uncond
+        e_c = model.apply_model(x.to(cuda_device), t, cond)
+        e_u = model.apply_model(x.to(cuda_device), t, uncond)
+        worst = max(worst, rel_l2(e_c, e_c_ref), rel_l2(e_u, e_u_ref))
         e_t = e_u_ref + 9.0 * (e_c_ref - e_u_ref)
         x, _ = O.ddim_update(x, e_t, float(sch["alphas"][index]), float(sch["alphas_prev"][index]), 0.0,
                              float(sch["sqrt_one_minus_alphas"][index]))
@@ -191,7 +191,7 @@ def test_sd15_sample_and_decode(sd15, cuda_device):
                                 unconditional_guidance_scale=9.0, unconditional_conditioning=uncond)
     err = rel_l2(samples, g["samples"])
     print("free-running 20-step latent rel L2:", err)
-    assert err < 5e-2
+    assert err < 2e-2
     # decode the REFERENCE's latents (isolates the VAE) and our own (whole pipeline)
     img_ref_lat = model.decode_first_stage(g["samples"].to(cuda_device))
     e_dec = rel_l2(img_ref_lat, g["decoded"])
@@ -204,8 +204,15 @@ def test_sd15_sample_and_decode(sd15, cuda_device):
     mse = float((diff.astype(np.float64) ** 2).mean())
     psnr = 10 * np.log10(255.0 ** 2 / max(mse, 1e-12))
     print(f"final image vs reference: mean abs diff {diff.mean():.3f} / 255, PSNR {psnr:.1f} dB")
-    # PD (Inception features, compute_score.py:11-17) needs pytorch_fid weights that are not in the image; PSNR stands in.
-    assert psnr > 25.0
+    # PD (Inception-2048 features, compute_score.py:11-17) needs pytorch_fid and its pt_inception weights
+    pd_ran = False
+    try:
+        import pytorch_fid  # noqa: F401
+        pd_ran = True
+    except ImportError:
+        pass
+    print("compute_score PD gate ran:", pd_ran, "(pytorch_fid + Inception weights are not in the image; PSNR stands in)")
+    assert psnr > 40.0
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -245,6 +252,123 @@ def test_sd15_768x768_eps_vs_oracle(sd15, cuda_device):
     err = rel_l2(eps, ref)
     print("768x768 eps rel L2 vs oracle:", err)
     assert err < EPS_TOL
+
+
+def test_sd15_controlnet_13_outputs(sd15, cuda_device):
+    """ControlNet.forward at SD1.5 size (cldm/cldm.py:284-305): all 13 control tensors against the oracle, and the
+    norms / first / last tensors against the golden values recorded from the REAL reference ControlNet."""
+    from helpers import oracle_weights
+    model, g = sd15
+    _, sd_cn, _ = oracle_weights(O.SD15, O.SD15_VAE)
+    x_T, cond, _ = inputs_on(O.SD15, 32, 48, cuda_device, hint=canny_hint())
+    x_c, cond_c, _ = O.make_inputs(O.SD15, 1, 32, 48, hint=canny_hint())
+    ts = _ts(cuda_device)
+    control = model.control_model(x=x_T, hint=cond["c_concat"][0], timesteps=ts, context=cond["c_crossattn"][0])
+    with torch.no_grad():
+        ref = O.controlnet_forward(sd_cn, O.SD15, x_c, cond_c["c_concat"][0], ts.cpu(), cond_c["c_crossattn"][0])
+    assert len(control) == len(ref) == 13
+    errs = [rel_l2(c, r) for c, r in zip(control, ref)]
+    print("ControlNet 13 outputs rel L2 vs oracle:", [f"{e:.2e}" for e in errs])
+    assert max(errs) < 1.5e-2
+    norms = torch.tensor([c.float().norm().item() for c in control])
+    assert torch.allclose(norms, g["control_stats"][:, 1], rtol=1e-2)
+    assert rel_l2(control[0], g["control_first"]) < 1.5e-2 and rel_l2(control[-1], g["control_last"]) < 1.5e-2
+
+
+def test_sd15_outlier_context(sd15, cuda_device):
+    """SURVEY 8(d) stress input: two context channels scaled x30 (CLIP's outlier features are that large), so that
+    softmax logits and the cross-attention K/V projections see a wide dynamic range. eps against the oracle."""
+    from helpers import oracle_weights
+    model, _ = sd15
+    sd_unet, sd_cn, _ = oracle_weights(O.SD15, O.SD15_VAE)
+    x_c, cond_c, _ = O.make_inputs(O.SD15, 1, 32, 48, hint=canny_hint())
+    ctx = cond_c["c_crossattn"][0].clone()
+    ctx[:, :, 133] *= 30.0
+    ctx[:, :, 592] *= 30.0
+    cond_c = {"c_concat": cond_c["c_concat"], "c_crossattn": [ctx]}
+    ts = torch.full((1,), 651, dtype=torch.long)
+    with torch.no_grad():
+        ref = O.apply_model(sd_unet, sd_cn, O.SD15, x_c, ts, cond_c)
+    dev = cuda_device
+    cond_d = {"c_concat": [cond_c["c_concat"][0].to(dev)], "c_crossattn": [ctx.to(dev)]}
+    eps = model.apply_model(x_c.to(dev), ts.to(dev), cond_d)
+    err = rel_l2(eps, ref)
+    print("outlier-context eps rel L2 vs oracle:", err)
+    assert err < EPS_TOL
+
+
+def test_sd15_768x768_batch4_vs_oracle(sd15, cuda_device):
+    """BASELINE configs[3] as written: 768x768 (latent 96x96) at BATCH 4, four different samples and timesteps in one
+    call; every sample against the oracle run on that sample alone."""
+    from helpers import oracle_weights
+    model, _ = sd15
+    sd_unet, sd_cn, _ = oracle_weights(O.SD15, O.SD15_VAE)
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn((4, 4, 96, 96), generator=g)
+    ctx = torch.randn((4, 77, 768), generator=g)
+    hint = (torch.rand((4, 1, 768, 768), generator=g) > 0.9).float().expand(-1, 3, -1, -1).contiguous()
+    ts = torch.tensor([951, 651, 301, 51], dtype=torch.long)
+    dev = cuda_device
+    eps = model.apply_model(x.to(dev), ts.to(dev), {"c_concat": [hint.to(dev)], "c_crossattn": [ctx.to(dev)]})
+    errs = []
+    for i in range(4):
+        with torch.no_grad():
+            ref = O.apply_model(sd_unet, sd_cn, O.SD15, x[i:i + 1], ts[i:i + 1],
+                                {"c_concat": [hint[i:i + 1]], "c_crossattn": [ctx[i:i + 1]]})
+        errs.append(rel_l2(eps[i:i + 1], ref))
+    print("768x768 batch-4 eps rel L2 vs oracle:", errs)
+    assert max(errs) < EPS_TOL
+
+
+def test_vae_decode_512_batch16_vs_oracle(sd15, cuda_device):
+    """BASELINE configs[4] as written: VAE decode 512x512 at BATCH 16 (one call). Samples 0, 7 and 15 against the oracle;
+    every other sample against the batch-1 decode of the same latent (samples are independent)."""
+    from helpers import oracle_weights
+    model, _ = sd15
+    _, _, sd_vae = oracle_weights(O.SD15, O.SD15_VAE)
+    z = torch.randn((16, 4, 64, 64), generator=torch.Generator().manual_seed(9)) * 0.18215 * 4.0
+    img = model.decode_first_stage(z.to(cuda_device))
+    assert img.shape == (16, 3, 512, 512) and torch.isfinite(img).all()
+    for i in (0, 7, 15):
+        with torch.no_grad():
+            ref = O.vae_decode(sd_vae, O.SD15_VAE, z[i:i + 1])
+        err = rel_l2(img[i:i + 1], ref)
+        print(f"VAE 512x512 batch-16 sample {i} rel L2 vs oracle:", err)
+        assert err < 2e-2
+    for i in (3, 12):
+        one = model.decode_first_stage(z[i:i + 1].to(cuda_device))
+        assert rel_l2(img[i:i + 1], one) < 1e-2
+    u8 = model.decode_first_stage_u8(z.to(cuda_device))
+    assert u8.shape == (16, 512, 512, 3) and u8.dtype == torch.uint8
+
+
+def test_engine_follows_weight_updates(tiny, cuda_device):
+    """A captured engine bakes in packed weights, time-embedding tables and hoisted K/V: after load_state_dict with
+    different weights sample() must rebuild it (weights fingerprint in the engine key) -- compared with the generic
+    two-call path on the new weights. The hint cache is keyed on the hint encoder's weights as well."""
+    from stablediffusioneo_b200.cldm.ddim_hacked import DDIMSampler
+    model, g = tiny
+    x_T, cond, uncond = inputs_on(O.TINY, 8, 16, cuda_device)
+    sampler = DDIMSampler(model)
+    kw = dict(verbose=False, eta=0.0, x_T=x_T, unconditional_guidance_scale=9.0, unconditional_conditioning=uncond)
+    first, _ = sampler.sample(4, 1, (4, 8, 16), cond, **kw)
+    eng0 = sampler._engine
+    keep = {k: v.clone() for k, v in model.state_dict().items()}
+    try:
+        gen = torch.Generator(device=cuda_device).manual_seed(77)
+        changed = {k: v * (1.0 + 0.2 * torch.randn(v.shape, generator=gen, device=v.device)) for k, v in keep.items()}
+        model.load_state_dict(changed, strict=True)
+        second, _ = sampler.sample(4, 1, (4, 8, 16), cond, **kw)
+        assert sampler._engine is not eng0, "engine was not rebuilt after the weights changed"
+        generic = DDIMSampler(model)
+        generic.use_engine = False
+        ref, _ = generic.sample(4, 1, (4, 8, 16), cond, **kw)
+        assert rel_l2(second, ref) < 2e-2
+        assert rel_l2(second, first) > 5e-2, "the new weights did not change the result (stale replay?)"
+    finally:
+        model.load_state_dict(keep, strict=True)
+    third, _ = sampler.sample(4, 1, (4, 8, 16), cond, **kw)
+    assert rel_l2(third, first) < 1e-3
 
 
 def test_sd15_batch2_matches_batch1(sd15, cuda_device):
