@@ -46,6 +46,7 @@ SIGNATURES = {
     "sdeo_conv_autotune": (c_int, [c_int]),
     "sdeo_conv_set_cta_budget": (c_int, [c_int]),
     "sdeo_conv_gn_stats_slots": (c_int, [POINTER(ConvArgs), POINTER(c_int32), POINTER(c_int32)]),
+    "sdeo_conv_plan_describe": (c_int, [POINTER(ConvArgs), c_int32, POINTER(c_int32), c_int32]),
     "sdeo_conv_row_stats_parts": (c_int, [POINTER(ConvArgs), POINTER(c_int32), POINTER(c_int32)]),
     "sdeo_groupnorm_apply_stats": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p,
                                            c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, c_int32, c_void_p]),

@@ -283,6 +283,9 @@ class ControlLDM(nn.Module):
         self._schedule_args = (int(timesteps), linear_start, linear_end)
         self.register_schedule()
         self._hint_cache = None
+        def _drop_param_cache(module, incompatible_keys):  # (a post-hook must return None)
+            module.__dict__.pop("_fp_params", None)
+        self.register_load_state_dict_post_hook(_drop_param_cache)
         # first eager call of each layer shape picks its tile / split-K configuration (SDEO_NO_AUTOTUNE=1: heuristics only)
         ops.set_autotune(not os.environ.get("SDEO_NO_AUTOTUNE"))
 
@@ -307,12 +310,15 @@ class ControlLDM(nn.Module):
         """Identity + version of every parameter a captured engine bakes in (packed / folded weights, time-embedding
         tables, hoisted K/V, the hint features): changes after load_state_dict(), an optimizer step or any other in-place
         update, and when a parameter is replaced. Engines and caches key on it so that they never replay stale weights."""
-        mods = [self.model, self.control_model] + ([self.first_stage_model] if first_stage else [])
-        h = 0
-        for m in mods:
-            for p in m.parameters():
-                h = hash((h, p.data_ptr(), p._version))
-        return h
+        cache = self.__dict__.get("_fp_params")
+        if cache is None:
+            # the parameter list is cached (walking the module tree costs ~1 ms per call); load_state_dict -- the one
+            # supported way of replacing Parameter objects (assign=True) -- drops the cache through a post-hook
+            cache = self.__dict__["_fp_params"] = (
+                list(self.model.parameters()) + list(self.control_model.parameters()),
+                list(self.first_stage_model.parameters()))
+        params = cache[0] + cache[1] if first_stage else cache[0]
+        return hash(tuple([p._version for p in params] + [p.data_ptr() for p in params]))
 
     # ---- hoisted, loop-invariant pieces ------------------------------------------------------------------
     def guided_hint(self, hint):

@@ -71,6 +71,17 @@ struct ConvKParams {
   float ln_invc, ln_eps;
   const float* ln_csum;    // [rows_packed] column sums of the packed (bf16) weight, packed row order
   float2* gn_stats;  // STATS == 1: per-(M tile, K-slice rank) per-channel (sum, sum of squares) of the final outputs
+  // HALO mode (3x3, stride 1, one sample per tile): ONE A tile per 64-channel chunk -- the (bh+2) x (bw+2) halo box of the
+  // output tile, pixel pitch hpitch = bw+2 -- serves all nine taps: tap (ky,kx) is the same tile read from row offset
+  // ky*hpitch + kx (a 128-byte-aligned descriptor start; the 128B swizzle is a function of the absolute shared-memory
+  // address, so TMA's layout and the MMA's reads agree for any row offset -- measured, tools/exp_rowshift.cu). MMA row r
+  // is halo position (r / hpitch, r % hpitch): rows with r % hpitch >= bw are the halo columns, computed and discarded.
+  // A and B (one weight tile per tap) travel through separate rings. K order: chunk-major, tap-minor.
+  int halo, hpitch, a_stages, a_stage_bytes;
+  // PAIR mode (cta_group::2): CTAs (2i, 2i+1) of grid.x form a pair inside the (2,1,S) cluster and run ONE M=256 MMA per
+  // K step: each stages its own 128 rows of A and its half (BN/2 rows) of the weight tile. m_tiles = real M tiles (grid.x is
+  // rounded up to even; the odd one out is a null tile whose loads fall outside the tensor and whose rows are all invalid).
+  int pair, m_tiles;
 };
 
 #define SDEO_DBG(slot)                                                                               \
@@ -368,13 +379,65 @@ __device__ __forceinline__ void epi_geglu_item(const ConvKParams& p, const RowIn
   *reinterpret_cast<uint4*>(yp) = pack8_bf16(x);
 }
 
+// TMA loads signalling an mbarrier given by its 32-bit shared-memory address: this CTA's own barrier, or (PAIR mode, via
+// the cta_group::2 form) the pair leader's barrier as a shared::cluster address.
+__device__ __forceinline__ void tma2d_to(void* dst, const CUtensorMap* m, uint32_t bar, bool pair, int c0, int c1) {
+  if (pair) {
+    tma_load_2d_pair(dst, m, bar, c0, c1);
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma4d_to(void* dst, const CUtensorMap* m, uint32_t bar, bool pair, int c0, int c1, int c2,
+                                         int c3) {
+  if (pair) {
+    tma_load_4d_pair(dst, m, bar, c0, c1, c2, c3);
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+        "[%2];" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void commit_to(uint64_t* bar, bool pair, uint16_t pair_mask) {
+  if (pair) tc_commit_pair(bar, pair_mask);
+  else tc_commit(bar);
+}
+__device__ __forceinline__ void mma_any(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc, bool pair) {
+  if (pair) tc_mma_bf16_pair(d, a, b, idesc, acc);
+  else tc_mma_bf16(d, a, b, idesc, acc);
+}
+
+// Output pixel (n, h, w) of tile row `row`, or false for a padding row / halo column / pixel outside the tensor.
+__device__ __forceinline__ bool tile_row_coords(const ConvKParams& p, int row, int n0, int h0, int w0, int* nn, int* hh,
+                                                int* ww) {
+  int nl, hl, wl;
+  if (p.halo) {
+    nl = 0; hl = row / p.hpitch; wl = row % p.hpitch;
+    if (wl >= p.bw || hl >= p.bh) return false;
+  } else {
+    const int per_img = p.bh * p.bw;
+    nl = row / per_img;
+    const int rem = row % per_img;
+    hl = rem / p.bw; wl = rem % p.bw;
+  }
+  *nn = n0 + nl; *hh = h0 + hl; *ww = w0 + wl;
+  return (row < p.rows_valid) && (*nn < p.N) && (*hh < p.Ho) && (*ww < p.Wo);
+}
+
 // MODE: SDEO_EPI_*; OUT / RES: see enums above; FAST: vector-aligned NORMAL epilogue (else the generic item path).
 // STATS (NORMAL + FAST + fp32 output only): the epilogue also reduces the FINAL output values of this CTA's rows to
 // per-channel (sum, sum of squares) and writes them to p.gn_stats[(M tile * S + K-slice rank)][cout] -- the GroupNorm
 // that consumes this tensor folds those partials instead of re-reading the tensor for its statistics.
 // (STATS == 2: per-row statistics for a LayerNorm consumer instead, see ConvKParams::row_stats.)
 // LNF: a LayerNorm is folded into this GEMM (ConvKParams::ln_stats); kept out of the other instantiations' code.
-template <int MODE, int OUT, int RES, bool FAST, int STATS, bool LNF>
+// PAIR: CTA pairs (cta_group::2). A compile-time variant, not a run-time flag: a kernel that contains cta_group::2
+// instructions can only be launched with an even cluster width (measured: "cluster misconfiguration" otherwise).
+template <int MODE, int OUT, int RES, bool FAST, int STATS, bool LNF, bool PAIR>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmB, const ConvKParams p) {
@@ -388,17 +451,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   uint64_t* tmem_full_bar = empty_bar + 16;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
   uint64_t* recv_bar = full_bar + 48;  // split-K: completes when all S partial slices of this CTA's rows have arrived
+  uint64_t* full_a = full_bar + 40;    // HALO mode: the A (halo tile) ring, up to 4 stages
+  uint64_t* empty_a = full_bar + 44;
   int* row_pix = reinterpret_cast<int*>(smem + 512);  // [128] output pixel index per tile row
   float2* ln_vec = reinterpret_cast<float2*>(smem + 1024);  // [128] (mean, rstd) of the folded LayerNorm per tile row
   uint8_t* tiles = smem + 2048;
-  const int stage_bytes = kATileBytes + p.BN * 128;
-
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   const int m_tile = blockIdx.x;
   const int n_tile = blockIdx.y;
-  const int split = blockIdx.z;  // == rank in the (1,1,S) cluster
+  const int split = blockIdx.z;  // K slice; cluster = (1,1,S), or (2,1,S) in PAIR mode: cluster rank = px + 2 * split
+  constexpr bool pair = PAIR;
+  const uint32_t px = pair ? (cluster_ctarank() & 1u) : 0u;  // position inside the CTA pair; 0 = leader (issues the MMAs)
+  const bool leader = px == 0;
+  const uint32_t leader_rank = pair ? (uint32_t)(2 * split) : 0u;
+  const uint16_t pair_mask = (uint16_t)(3u << leader_rank);
+  const int bn_cta = pair ? p.BN / 2 : p.BN;            // weight rows this CTA stages per K step
+  const int b_bytes = bn_cta * 128;
+  const int stage_bytes = kATileBytes + b_bytes;
+  const int tx_mult = pair ? 2 : 1;                      // the leader's barrier counts both CTAs' bytes
   const int iw = m_tile % p.tiles_w;
   const int ih = (m_tile / p.tiles_w) % p.tiles_h;
   const int in_ = m_tile / (p.tiles_w * p.tiles_h);
@@ -411,7 +483,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
 
   if (threadIdx.x == 0) SDEO_DBG(0);
   const int trc = trace_start(1ULL | ((unsigned long long)MODE << 40) | ((unsigned long long)p.splits << 44) |
-                              ((unsigned long long)p.BN << 48));
+                              ((unsigned long long)p.BN << 48) | ((unsigned long long)(p.halo & 1) << 60));
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmB);
@@ -419,6 +491,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < p.a_stages; ++s) {
+      mbar_init(&full_a[s], 1);
+      mbar_init(&empty_a[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
     mbar_init(recv_bar, 1);
@@ -433,11 +509,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     }
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr_smem, (uint32_t)p.tmem_cols);
-    tmem_relinquish();
+    if (pair) {
+      tmem_alloc_pair(tmem_ptr_smem, (uint32_t)p.tmem_cols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_ptr_smem, (uint32_t)p.tmem_cols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (pair) {  // the partner's barriers must be initialised before a TMA completion or a multicast commit can reach them
+    cluster_arrive();
+    cluster_wait();
+  }
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   if (threadIdx.x == 0) SDEO_DBG(1);
@@ -454,27 +539,114 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   if (threadIdx.x >= 128 && threadIdx.x < 256) {
     // output pixel of every tile row (-1: padding row / outside the image), read by epilogue phase 2
     const int row = (int)threadIdx.x - 128;
-    const int per_img = p.bh * p.bw;
-    const int nl = row / per_img;
-    const int rem = row % per_img;
-    const int hl = rem / p.bw, wl = rem % p.bw;
-    const int nn = n0 + nl, hh = h0 + hl, ww = w0 + wl;
-    const bool ok = (row < p.rows_valid) && (nn < p.N) && (hh < p.Ho) && (ww < p.Wo);
+    int nn, hh, ww;
+    const bool ok = tile_row_coords(p, row, n0, h0, w0, &nn, &hh, &ww);
     row_pix[row] = ok ? (nn * p.Ho + hh) * p.Wo + ww : -1;
   }
 
-  if (warp == 0) {
+  // HALO mode ring geometry: [A ring: a_stages x a_stage_bytes][B ring: stages x BN*128]
+  uint8_t* b_ring = tiles + (size_t)p.a_stages * p.a_stage_bytes;
+  // barrier the TMA completions go to: this CTA's own, or the pair leader's
+  auto full_addr = [&](uint64_t* bar) -> uint32_t {
+    return pair ? mapa_u32(smem_u32(bar), leader_rank) : smem_u32(bar);
+  };
+  if (warp == 0 && p.halo) {
+    // ===================== TMA producer, HALO mode =====================
+    // K step i (global index k_begin + i): chunk c = idx / 9, tap t = idx % 9. One halo A tile per chunk, one weight tile
+    // per step; the weight tile of (c, t) sits at packed K offset (t * chunks_per_tap + c) * 64.
+    if (lane == 0) {
+      const int nb0 = n_tile * p.BN + (int)px * bn_cta;
+      const uint32_t a_tx = (uint32_t)((p.bh + 2) * p.hpitch) * 128u * (uint32_t)tx_mult;
+      const uint32_t b_tx = (uint32_t)(b_bytes * tx_mult);
+      int c = k_begin / 9, t = k_begin % 9;
+      const int npre = nchunks < p.stages ? nchunks : p.stages;
+      {
+        int cc = c, tt = t;
+        for (int i = 0; i < npre; ++i) {  // weight tiles of the first ring pass: before the grid dependency resolves
+          if (leader) mbar_expect_tx(&full_bar[i], b_tx);
+          tma2d_to(b_ring + (size_t)i * b_bytes, &tmB, full_addr(&full_bar[i]), pair, (tt * p.chunks_per_tap + cc) * kBK, nb0);
+          if (++tt == 9) { tt = 0; ++cc; }
+        }
+      }
+      griddep_wait();
+      trace_mark(trc, 2);
+      int sb = 0, sa = 0, na = 0;
+      uint32_t phb = 0, pha = 0;
+      for (int i = 0; i < nchunks; ++i) {
+        if (i == 0 || t == 0) {  // first step of a chunk inside this CTA's K range: its halo tile
+          if (na >= p.a_stages) mbar_wait(&empty_a[sa], pha ^ 1u);
+          if (leader) mbar_expect_tx(&full_a[sa], a_tx);
+          uint8_t* a_dst = tiles + (size_t)sa * p.a_stage_bytes;
+          if (c < p.c1_chunks)
+            tma4d_to(a_dst, &tmA1, full_addr(&full_a[sa]), pair, c * kBK, w0 - 1, h0 - 1, n0);
+          else
+            tma4d_to(a_dst, &tmA2, full_addr(&full_a[sa]), pair, (c - p.c1_chunks) * kBK, w0 - 1, h0 - 1, n0);
+          ++na;
+          if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
+        }
+        if (i >= npre) {
+          mbar_wait(&empty_bar[sb], phb ^ 1u);
+          if (leader) mbar_expect_tx(&full_bar[sb], b_tx);
+          tma2d_to(b_ring + (size_t)sb * b_bytes, &tmB, full_addr(&full_bar[sb]), pair, (t * p.chunks_per_tap + c) * kBK, nb0);
+        }
+        if (++sb == p.stages) { sb = 0; phb ^= 1u; }
+        if (++t == 9) { t = 0; ++c; }
+      }
+    }
+  } else if (warp == 1 && p.halo) {
+    // ===================== MMA issuer, HALO mode (PAIR mode: the leader CTA only) =====================
+    if (leader) {
+    const uint32_t idesc = umma_idesc_bf16(pair ? 2 * kBM : kBM, (uint32_t)p.BN);
+    const uint64_t a_desc0 = umma_desc_k_sw128(smem_u32(tiles));
+    const uint64_t b_desc0 = umma_desc_k_sw128(smem_u32(b_ring));
+    const uint64_t a_step = (uint64_t)(p.a_stage_bytes >> 4), b_step = (uint64_t)(b_bytes >> 4);
+    int sb = 0, sa = 0;
+    uint32_t phb = 0, pha = 0;
+    uint64_t a_desc = a_desc0, b_desc = b_desc0;
+    int t = k_begin % 9;
+    int ky = t / 3, kx = t % 3;
+    for (int i = 0; i < nchunks; ++i) {
+      if (i == 0 || t == 0) {
+        mbar_wait(&full_a[sa], pha);
+      }
+      mbar_wait(&full_bar[sb], phb);
+      tc_fence_after();
+      const bool last_of_chunk = (t == 8) || (i == nchunks - 1);
+      if (elect_one()) {
+        // tap shift = row offset inside the halo tile: (ky * pitch + kx) rows of 128 bytes = 8 descriptor units each
+        const uint64_t a_tap = a_desc + (uint64_t)((ky * p.hpitch + kx) * 8);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k)
+          mma_any(tmem_base, a_tap + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (i > 0 || k > 0) ? 1u : 0u, pair);
+        commit_to(&empty_bar[sb], pair, pair_mask);
+        if (last_of_chunk) commit_to(&empty_a[sa], pair, pair_mask);
+      }
+      __syncwarp();
+      b_desc += b_step;
+      if (++sb == p.stages) { sb = 0; phb ^= 1u; b_desc = b_desc0; }
+      if (last_of_chunk) {
+        a_desc += a_step;
+        if (++sa == p.a_stages) { sa = 0; pha ^= 1u; a_desc = a_desc0; }
+      }
+      if (++kx == 3) { kx = 0; ++ky; }
+      if (++t == 9) { t = 0; ky = 0; }
+    }
+    if (elect_one()) commit_to(tmem_full_bar, pair, pair_mask);
+    __syncwarp();
+    if (lane == 0) SDEO_DBG(3);
+    }
+  } else if (warp == 0) {
     // ===================== TMA producer =====================
     // (all ring / tap / chunk indices advance incrementally: no integer division on the per-chunk path)
     if (lane == 0) {
-      const uint32_t tx_bytes = (uint32_t)(p.rows_valid + p.BN) * 128u;
-      const int nb0 = n_tile * p.BN;
+      const uint32_t tx_bytes = (uint32_t)(p.rows_valid * 128 + b_bytes) * (uint32_t)tx_mult;
+      const int nb0 = n_tile * p.BN + (int)px * bn_cta;
       // the first ring pass needs no empty-slot wait; its weight tiles are requested before the grid dependency
       // resolves, so the weight stream of this layer overlaps the tail of the previous kernel
       const int npre = nchunks < p.stages ? nchunks : p.stages;
       for (int i = 0; i < npre; ++i) {
-        mbar_expect_tx(&full_bar[i], tx_bytes);
-        tma_load_2d(tiles + (size_t)i * stage_bytes + kATileBytes, &tmB, &full_bar[i], (k_begin + i) * kBK, nb0);
+        if (leader) mbar_expect_tx(&full_bar[i], tx_bytes);
+        tma2d_to(tiles + (size_t)i * stage_bytes + kATileBytes, &tmB, full_addr(&full_bar[i]), pair, (k_begin + i) * kBK, nb0);
       }
       griddep_wait();
       trace_mark(trc, 2);
@@ -483,24 +655,34 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       int tap = k_begin / p.chunks_per_tap, within = k_begin % p.chunks_per_tap;
       int ky = tap / p.kw, kx = tap % p.kw;
       uint8_t* a_dst = tiles;
+      long long dbg_wait = 0;
       for (int i = 0; i < nchunks; ++i) {
         if (i >= npre) {
+          const long long t_w0 = p.dbg ? clock64() : 0;
           mbar_wait(&empty_bar[s], ph ^ 1u);
-          mbar_expect_tx(&full_bar[s], tx_bytes);
+          if (p.dbg) dbg_wait += clock64() - t_w0;
+          if (leader) mbar_expect_tx(&full_bar[s], tx_bytes);
         }
         const int wc = w0 * p.stride + kx - p.pad;
         const int hc = h0 * p.stride + ky - p.pad;
+        const uint32_t fb = full_addr(&full_bar[s]);
         if (within < p.c1_chunks)
-          tma_load_4d(a_dst, &tmA1, &full_bar[s], within * kBK, wc, hc, n0);
+          tma4d_to(a_dst, &tmA1, fb, pair, within * kBK, wc, hc, n0);
         else
-          tma_load_4d(a_dst, &tmA2, &full_bar[s], (within - p.c1_chunks) * kBK, wc, hc, n0);
-        if (i >= npre) tma_load_2d(a_dst + kATileBytes, &tmB, &full_bar[s], (k_begin + i) * kBK, nb0);
+          tma4d_to(a_dst, &tmA2, fb, pair, (within - p.c1_chunks) * kBK, wc, hc, n0);
+        if (i >= npre) tma2d_to(a_dst + kATileBytes, &tmB, fb, pair, (k_begin + i) * kBK, nb0);
         if (++within == p.chunks_per_tap) {
           within = 0;
           if (++kx == p.kw) { kx = 0; ++ky; }
         }
         a_dst += stage_bytes;
         if (++s == p.stages) { s = 0; ph ^= 1u; a_dst = tiles; }
+      }
+      if (p.dbg) {
+        long long* d = p.dbg + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16;
+        d[10] = dbg_wait;
+        d[11] = clock64();   // producer done (all loads issued)
+        d[12] = p.stages;
       }
     }
   } else if (warp == 1) {
@@ -509,34 +691,38 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     // while this thread probes the barrier), so the loop carries precomputed descriptors and no divisions.
     // The whole warp runs the loop (warp-uniform control flow and descriptor arithmetic stay in uniform registers);
     // one elected lane issues the tcgen05 instructions.
-    {
-      const uint32_t idesc = umma_idesc_bf16(kBM, (uint32_t)p.BN);
+    if (leader) {  // (PAIR mode: the leader CTA issues the M=256 MMAs for both)
+      const uint32_t idesc = umma_idesc_bf16(pair ? 2 * kBM : kBM, (uint32_t)p.BN);
       const uint64_t a_desc0 = umma_desc_k_sw128(smem_u32(tiles));
       const uint64_t b_desc0 = umma_desc_k_sw128(smem_u32(tiles) + kATileBytes);
       const uint64_t desc_step = (uint64_t)(stage_bytes >> 4);  // start-address field advances by one stage
       int s = 0;
       uint32_t ph = 0;
       uint64_t a_desc = a_desc0, b_desc = b_desc0;
+      long long dbg_wait = 0;
       for (int i = 0; i < nchunks; ++i) {
+        const long long t_w0 = p.dbg ? clock64() : 0;
         mbar_wait(&full_bar[s], ph);
+        if (p.dbg) dbg_wait += clock64() - t_w0;
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-            tc_mma_bf16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                        (i > 0 || k > 0) ? 1u : 0u);
+            mma_any(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                    (i > 0 || k > 0) ? 1u : 0u, pair);
           }
-          tc_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
+          commit_to(&empty_bar[s], pair, pair_mask);  // frees this smem stage (in both CTAs) once the MMAs above have read it
         }
         __syncwarp();
         a_desc += desc_step;
         b_desc += desc_step;
         if (++s == p.stages) { s = 0; ph ^= 1u; a_desc = a_desc0; b_desc = b_desc0; }
       }
-      if (elect_one()) tc_commit(tmem_full_bar);  // accumulator complete (all MMAs done => every stage consumed)
+      if (elect_one()) commit_to(tmem_full_bar, pair, pair_mask);  // accumulator complete (all MMAs done => every stage consumed)
       __syncwarp();
       if (lane == 0) SDEO_DBG(3);
+      if (lane == 0 && p.dbg) p.dbg[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + 9] = dbg_wait;
     }
   }
 
@@ -593,18 +779,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     const int r_begin = split * rows_per;
     const int r_end = min(p.rows_valid, r_begin + rows_per);
     const int vpr = p.BN * kElem / 16;  // 16-byte vectors per row
-    const int per_img = p.bh * p.bw;
     const int n_base = n_tile * p.BN;
     const uint32_t res_s = smem_u32(smem + p.res_smem_off);
     const uint8_t* res_g = reinterpret_cast<const uint8_t*>(p.residual);
     const int total = (r_end > r_begin ? r_end - r_begin : 0) * vpr;
     for (int it = (int)threadIdx.x - 192; it < total; it += kConvThreads - 192) {
       const int row = r_begin + it / vpr, v = it % vpr;
-      const int nl = row / per_img, rem = row % per_img;
-      const int hl = rem / p.bw, wl = rem % p.bw;
-      const int nn = n0 + nl, hh = h0 + hl, ww = w0 + wl;
+      int nn, hh, ww;
+      const bool ok = tile_row_coords(p, row, n0, h0, w0, &nn, &hh, &ww);
       const int col = v * (16 / kElem);
-      if (nn < p.N && hh < p.Ho && ww < p.Wo && n_base + col < p.cout) {
+      if (ok && n_base + col < p.cout) {
         const long long pix = ((long long)nn * p.Ho + hh) * p.Wo + ww;
         const uint8_t* src = res_g + ((size_t)pix * p.ldr + n_base + col) * kElem;
         const uint32_t dst = res_s + (uint32_t)((row * p.BN + col) * kElem);
@@ -669,8 +853,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       int rows_r = min(p.rows_valid, (r + 1) * rows_per) - r * rows_per;
       if (rows_r > 0) {
         const uint32_t src = smem_u32(tile) + (uint32_t)(r * rows_per * LD * 4);
-        const uint32_t dst = dsmem_addr(smem_u32(recv) + (uint32_t)(split * rows_per * LD * 4), (uint32_t)r);
-        dsmem_bulk_copy(dst, src, (uint32_t)(rows_r * LD * 4), dsmem_addr(smem_u32(recv_bar), (uint32_t)r));
+        const uint32_t peer = pair ? (uint32_t)(2 * r) + px : (uint32_t)r;  // cluster rank of K slice r of this M tile
+        const uint32_t dst = dsmem_addr(smem_u32(recv) + (uint32_t)(split * rows_per * LD * 4), peer);
+        dsmem_bulk_copy(dst, src, (uint32_t)(rows_r * LD * 4), dsmem_addr(smem_u32(recv_bar), peer));
       }
     }
     mbar_wait(recv_bar, 0);
@@ -874,7 +1059,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
             pps = per_img / rows_per;
           }
           // (one sample per tile: a rank without rows still owns a slot and writes zeros into it)
-          if (p.bn_ == 1 || (r_begin < p.rows_valid && sample < p.N))
+          // (a null tile of PAIR mode lies beyond the last sample and owns no slot)
+          if (sample < p.N && (p.bn_ == 1 || r_begin < p.rows_valid))
             reinterpret_cast<float*>(p.gn_stats)[(((size_t)sample * pps + part) * p.cout + n_base + c) * 2 + sq] = acc;
         }
       }
@@ -885,12 +1071,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   // ---- teardown (split-K: peers may still be reading this CTA's tile until the second cluster barrier completes) ----
   tc_fence_before();
   if (p.splits > 1 && STATS != 1) cluster_wait();
+  if (pair && p.splits == 1) {  // both CTAs of the pair are done with their accumulators before the pair-wide dealloc
+    cluster_arrive();
+    cluster_wait();
+  }
   __syncthreads();
   trace_mark(trc, 3);
   if (threadIdx.x == 64) SDEO_DBG(8);
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (pair) tmem_dealloc_pair(tmem_base, (uint32_t)p.tmem_cols);
+    else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
 }
 
@@ -952,6 +1143,8 @@ struct ConvPlan {
   int stages, tmem_cols;
   int res_smem_off;
   size_t smem_bytes;
+  int halo, hpitch, a_stages, a_stage_bytes, rows_valid;
+  int pair;  // CTA pairs (cta_group::2): grid.x = M tiles rounded up to even, cluster (2,1,S)
 };
 
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -977,7 +1170,12 @@ static int pick_bn_impl(int rows_packed, int epi_mode) {
 static int g_cta_budget = 0;
 static inline int cta_limit() { return g_cta_budget > 0 && g_cta_budget < 148 ? g_cta_budget : 148; }
 
-static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl, int force_bn = 0, int force_splits = 0) {
+// HALO mode is available for 3x3 stride-1 "same" convolutions whose M tiles hold one sample each (feature maps of at
+// least ~64 pixels; smaller ones are weight-streaming layers where the A operand does not matter).
+// force_halo: -1 = heuristic (SDEO_HALO=0/1 overrides), 0 = off, 1 = on (fails if not available).
+// force_pair: -1 = heuristic (SDEO_PAIR=0/1 overrides), 0 = off, 1 = on (fails with fewer than two M tiles).
+static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl, int force_bn = 0, int force_splits = 0, int force_halo = -1,
+                      int force_pair = -1) {
   if (!(a->ksize == 1 || a->ksize == 3)) return false;
   if (!(a->stride == 1 || a->stride == 2)) return false;
   // symmetric "same" padding, or the VAE encoder's Downsample: 3x3 stride 2 over F.pad(x, (0,1,0,1)) = no leading padding,
@@ -1007,7 +1205,43 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl, int force_bn = 0, i
       }
     }
   }
+  // ---- HALO tile: (bh x bw) output pixels laid out with pitch bw+2; rows used = (bh-1)*(bw+2) + bw <= 128 ----
+  pl->halo = 0; pl->hpitch = 0; pl->a_stages = 0; pl->a_stage_bytes = 0;
+  {
+    int want = force_halo;
+    if (want < 0) {
+      if (const char* e = getenv("SDEO_HALO")) want = atoi(e) ? 1 : 0;
+    }
+    const bool eligible = a->ksize == 3 && a->stride == 1 && a->pad == 1 && a->pad_hi == 0 && bbn == 1;
+    if (want == 1 && !eligible) return false;
+    if (eligible && want != 0) {
+      int h_tiles = INT32_MAX, hbh = 0, hbw = 0;
+      long long h_area = 0;
+      for (int bw = (pl->Wo < 126 ? pl->Wo : 126); bw >= 4; --bw) {
+        int bh = (kBM - bw) / (bw + 2) + 1;
+        if (bh > pl->Ho) bh = pl->Ho;
+        if (bh < 1) continue;
+        const int tiles = a->n * ((pl->Ho + bh - 1) / bh) * ((pl->Wo + bw - 1) / bw);
+        const long long area = (long long)(bh + 2) * (bw + 2);   // halo pixels fetched per tile and chunk
+        if (tiles < h_tiles || (tiles == h_tiles && area < h_area)) { h_tiles = tiles; hbh = bh; hbw = bw; h_area = area; }
+      }
+      // the heuristic accepts up to 1/3 more M tiles than the tap-by-tap tiling (the A operand shrinks ~5x)
+      if (hbw > 0 && (want == 1 || 3LL * h_tiles <= 4LL * best_tiles)) {
+        pl->halo = 1; pl->hpitch = hbw + 2;
+        bbn = 1; bbh = hbh; bbw = hbw;
+        best_tiles = h_tiles;
+        // the MMA reads 128 rows from row offset up to 2*pitch+2: the stage covers that even where the box is smaller
+        int rows = (hbh + 2) * (hbw + 2);
+        const int touched = 2 * (hbw + 2) + 2 + kBM;
+        if (rows < touched) rows = touched;
+        pl->a_stage_bytes = round_up(rows * 128, 1024);
+      } else if (want == 1) {
+        return false;
+      }
+    }
+  }
   pl->bn_ = bbn; pl->bh = bbh; pl->bw = bbw;
+  pl->rows_valid = pl->halo ? (bbh - 1) * pl->hpitch + bbw : bbn * bbh * bbw;
   pl->tiles_n = (a->n + bbn - 1) / bbn;
   pl->tiles_h = (pl->Ho + bbh - 1) / bbh;
   pl->tiles_w = (pl->Wo + bbw - 1) / bbw;
@@ -1044,6 +1278,21 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl, int force_bn = 0, i
   }
   if (pl->BN <= 0 || pl->BN > 256 || (pl->BN % 16) != 0) return false;
   pl->n_tiles = pl->rows_packed / pl->BN;
+  // ---- CTA pairs ----
+  {
+    int want = force_pair;
+    if (want < 0) {
+      if (const char* e = getenv("SDEO_PAIR")) want = atoi(e) ? 1 : 0;
+    }
+    if (want == 1 && best_tiles < 2) return false;
+    pl->pair = (best_tiles >= 2 && want != 0) ? 1 : 0;
+    // a forced K-slice count beyond what fits a cluster next to the pair wins over the pair HEURISTIC
+    int fs = force_splits;
+    if (const char* e = getenv("SDEO_FORCE_SPLITS")) fs = atoi(e);
+    if (pl->pair && want < 0 && fs > kMaxCluster / 2) pl->pair = 0;
+    if (pl->pair) best_tiles = (best_tiles + 1) & ~1;
+  }
+  const int max_splits = pl->pair ? kMaxCluster / 2 : kMaxCluster;
   // ---- split-K over a thread-block cluster ----
   const int base = best_tiles * pl->n_tiles;
   int splits = 1;
@@ -1051,21 +1300,25 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl, int force_bn = 0, i
     splits = cta_limit() / base;  // one CTA per SM: never spill into a second wave
     const int max_by_k = pl->total_chunks / 4;  // at least 4 K chunks per slice
     if (splits > max_by_k) splits = max_by_k;
-    if (splits > kMaxCluster) splits = kMaxCluster;
+    if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
   }
-  if (force_splits > 0 && a->epi_mode != SDEO_EPI_QKV)
-    splits = force_splits > pl->total_chunks ? pl->total_chunks : (force_splits > kMaxCluster ? kMaxCluster : force_splits);
+  if (force_splits > 0 && a->epi_mode != SDEO_EPI_QKV) {
+    if (force_splits > max_splits) return false;  // (the autotuner skips this candidate)
+    splits = force_splits > pl->total_chunks ? pl->total_chunks : force_splits;
+  }
   if (const char* e = getenv("SDEO_FORCE_SPLITS")) {  // tuning aid (tools/bench_conv.py)
     const int f = atoi(e);
-    if (f >= 1 && f <= kMaxCluster && a->epi_mode != SDEO_EPI_QKV) splits = f > pl->total_chunks ? pl->total_chunks : f;
+    if (f > max_splits) return false;
+    if (f >= 1 && a->epi_mode != SDEO_EPI_QKV) splits = f > pl->total_chunks ? pl->total_chunks : f;
   }
   pl->cps = (pl->total_chunks + splits - 1) / splits;
   pl->splits = (pl->total_chunks + pl->cps - 1) / pl->cps;  // every slice gets >= 1 chunk
   // ---- smem / tmem ----
   const int kSmemMax = 227 * 1024, kFixed = 3072;  // 1 KB alignment slack + 2 KB barriers / row tables
-  const int stage_bytes = kATileBytes + pl->BN * 128;
-  const int rows_valid = pl->bn_ * pl->bh * pl->bw;
+  const int b_stage = (pl->pair ? pl->BN / 2 : pl->BN) * 128;   // weight rows one CTA stages per K step
+  const int stage_bytes = pl->halo ? b_stage : kATileBytes + b_stage;   // HALO: the B ring's stage
+  const int rows_valid = pl->rows_valid;
   // fp32 epilogue tile, aliases the pipeline stages. Split-K: the tile (valid rows only) plus the receive area
   // [S][ceil(rows/S)][LD] the peers' bulk copies land in.
   auto tile_bytes_for = [&](int sp) {
@@ -1078,10 +1331,19 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl, int force_bn = 0, i
     pl->cps = pl->total_chunks;
   }
   const int tile_bytes = tile_bytes_for(pl->splits);
+  // HALO: two A stages (three when at least six weight stages still fit)
+  auto a_ring_for = [&](int extra) {
+    if (!pl->halo) return 0;
+    const int chunks = (pl->cps + 8) / 9 + 1;   // halo tiles a K slice can touch
+    int ast = chunks < 2 ? chunks : 2;
+    if (chunks >= 3 && (kSmemMax - kFixed - extra - 3 * pl->a_stage_bytes) / stage_bytes >= 6) ast = 3;
+    return ast;
+  };
   auto stages_for = [&](int extra) {  // pipeline depth that fits next to `extra` bytes of residual buffer
     if (kFixed + tile_bytes + extra > kSmemMax) return 0;
-    int st = (kSmemMax - kFixed - extra) / stage_bytes;
-    if (st > 8) st = 8;
+    const int a_ring = a_ring_for(extra) * pl->a_stage_bytes;
+    int st = (kSmemMax - kFixed - extra - a_ring) / stage_bytes;
+    if (st > (pl->halo ? 12 : 8)) st = pl->halo ? 12 : 8;
     if (st > pl->cps) st = pl->cps < 2 ? 2 : pl->cps;
     return st;
   };
@@ -1097,7 +1359,8 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl, int force_bn = 0, i
     if (st2 >= need) stages = st2; else res_bytes = 0;
   }
   pl->stages = stages;
-  size_t body = (size_t)stages * stage_bytes;
+  pl->a_stages = a_ring_for(res_bytes);
+  size_t body = (size_t)stages * stage_bytes + (size_t)pl->a_stages * pl->a_stage_bytes;
   if (body < (size_t)tile_bytes) body = tile_bytes;
   if (res_bytes) pl->res_smem_off = 2048 + (int)body;
   pl->smem_bytes = kFixed + body + res_bytes;
@@ -1190,7 +1453,8 @@ static int stats_parts(const sdeo_conv_args* a, const ConvPlan& pl) {
 #include <mutex>
 namespace {
 typedef std::array<int, 16> TuneKey;
-std::map<TuneKey, std::pair<int, int>> g_tuned;
+struct Tuned { int first, second, halo, pair; };   // N tile, K slices, HALO mode, CTA pairs
+std::map<TuneKey, Tuned> g_tuned;
 std::mutex g_tune_mu;
 int g_autotune = 0;
 
@@ -1214,7 +1478,7 @@ bool any_within_budget(const sdeo_conv_args* a, const ConvPlan& base) {
   return false;
 }
 
-bool tune_shape(const sdeo_conv_args* a, void* stream, std::pair<int, int>* best) {
+bool tune_shape(const sdeo_conv_args* a, void* stream, Tuned* best) {
   cudaStream_t st = (cudaStream_t)stream;
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return false;
@@ -1232,15 +1496,24 @@ bool tune_shape(const sdeo_conv_args* a, void* stream, std::pair<int, int>* best
     if (getenv("SDEO_TUNE_WARM") || cudaMalloc(&flush, kFlushBytes) != cudaSuccess) { flush = nullptr; (void)cudaGetLastError(); }
   }
   float best_ms = 1e30f;
-  *best = std::make_pair(base.BN, base.splits);
+  *best = Tuned{base.BN, base.splits, base.halo, base.pair};
+  const bool no_halo_tune = getenv("SDEO_HALO") != nullptr;   // forced on / off: tune within that mode only
+  const bool no_pair_tune = getenv("SDEO_PAIR") != nullptr;
+  for (int pair = 0; pair < 2; ++pair)
+  for (int halo = 0; halo < 2; ++halo)
   for (int bn : bns) {
     if (bn == 0) bn = base.BN;
     else if (a->epi_mode == SDEO_EPI_GEGLU || bn == base.BN || base.rows_packed % bn != 0) continue;
     for (int sp : ss) {
       if (a->epi_mode == SDEO_EPI_QKV && sp > 1) continue;
       ConvPlan pl;
-      if (!make_plan(a, &pl, bn, sp) || pl.BN != bn || pl.splits != sp) continue;
-      const int ctas = pl.tiles_n * pl.tiles_h * pl.tiles_w * pl.n_tiles * pl.splits;
+      if ((no_halo_tune && halo != base.halo) || (no_pair_tune && pair != base.pair)) continue;
+      if (!make_plan(a, &pl, bn, sp, no_halo_tune ? -1 : halo, no_pair_tune ? -1 : pair) || pl.BN != bn || pl.splits != sp ||
+          pl.halo != halo || pl.pair != pair)
+        continue;
+      int mt = pl.tiles_n * pl.tiles_h * pl.tiles_w;
+      if (pl.pair) mt = (mt + 1) & ~1;
+      const int ctas = mt * pl.n_tiles * pl.splits;
       if (sp > 1 && ctas > cta_limit()) continue;  // K slices must not spill into a second wave
       if (g_cta_budget > 0 && ctas > cta_limit() && any_within_budget(a, base)) continue;  // honour the CTA budget
       if (launch_conv(a, pl, stream) != 0) { (void)cudaGetLastError(); continue; }
@@ -1259,7 +1532,7 @@ bool tune_shape(const sdeo_conv_args* a, void* stream, std::pair<int, int>* best
         if (t < ms) ms = t;
       }
       if (!ok) { (void)cudaGetLastError(); continue; }
-      if (ms < best_ms) { best_ms = ms; *best = std::make_pair(bn, sp); }
+      if (ms < best_ms) { best_ms = ms; *best = Tuned{bn, sp, halo, pair}; }
     }
   }
   cudaEventDestroy(e0);
@@ -1281,18 +1554,22 @@ extern "C" int sdeo_conv_autotune(int enable) {
 // Resolves the plan sdeo_conv2d uses for these args: the autotuned (N tile, K slices) if the shape has been tuned
 // (tuning it first when `stream` is given and autotuning is on), the heuristic otherwise.
 static bool resolve_plan(const sdeo_conv_args* a, void* stream, bool may_tune, ConvPlan* pl) {
-  int force_bn = 0, force_s = 0;
+  int force_bn = 0, force_s = 0, force_halo = -1, force_pair = -1;
   if (g_autotune && !getenv("SDEO_FORCE_BN") && !getenv("SDEO_FORCE_SPLITS")) {
     std::lock_guard<std::mutex> lock(g_tune_mu);
     const TuneKey key = tune_key(a);
     auto it = g_tuned.find(key);
     if (it == g_tuned.end() && may_tune) {
-      std::pair<int, int> best;
+      Tuned best;
       if (tune_shape(a, stream, &best)) it = g_tuned.emplace(key, best).first;
     }
-    if (it != g_tuned.end()) { force_bn = it->second.first; force_s = it->second.second; }
+    if (it != g_tuned.end()) {
+      force_bn = it->second.first; force_s = it->second.second;
+      if (!getenv("SDEO_HALO")) force_halo = it->second.halo;
+      if (!getenv("SDEO_PAIR")) force_pair = it->second.pair;
+    }
   }
-  return make_plan(a, pl, force_bn, force_s);
+  return make_plan(a, pl, force_bn, force_s, force_halo, force_pair);
 }
 
 extern "C" int sdeo_conv2d(const sdeo_conv_args* a, void* stream) {
@@ -1317,12 +1594,33 @@ extern "C" int sdeo_conv_gn_stats_slots(const sdeo_conv_args* a, int32_t* max_sl
   if (!a) return set_error(SDEO_EINVAL, "conv_gn_stats_slots: null argument");
   ConvPlan pl;
   if (!resolve_plan(a, nullptr, false, &pl)) return set_error(SDEO_EINVAL, "conv_gn_stats_slots: unsupported geometry");
-  if (max_slots_total) *max_slots_total = pl.tiles_n * pl.tiles_h * pl.tiles_w * kMaxCluster;
+  if (max_slots_total) {
+    // upper bound over every plan the autotuner may still pick for this shape (the HALO tiling has its own tile count)
+    int tiles = pl.tiles_n * pl.tiles_h * pl.tiles_w;
+    for (int halo = 0; halo < 2; ++halo) {
+      ConvPlan alt;
+      if (make_plan(a, &alt, 0, 0, halo) && alt.tiles_n * alt.tiles_h * alt.tiles_w > tiles)
+        tiles = alt.tiles_n * alt.tiles_h * alt.tiles_w;
+    }
+    *max_slots_total = tiles * kMaxCluster;
+  }
   if (parts_per_sample) {
     sdeo_conv_args b = *a;
     if (!b.gn_stats) b.gn_stats = (float*)(uintptr_t)16;  // "would be produced if a buffer were given"
     *parts_per_sample = stats_parts(&b, pl);
   }
+  return SDEO_OK;
+}
+
+extern "C" int sdeo_conv_plan_describe(const sdeo_conv_args* a, int32_t halo, int32_t* out, int32_t n_out) {
+  if (!a || !out || n_out < 16) return set_error(SDEO_EINVAL, "conv_plan_describe: bad args");
+  ConvPlan pl;
+  const bool ok = halo < 0 ? resolve_plan(a, nullptr, false, &pl) : make_plan(a, &pl, 0, 0, halo);
+  if (!ok) return set_error(SDEO_EINVAL, "conv_plan_describe: unsupported geometry");
+  const int32_t v[16] = {pl.BN, pl.splits, pl.halo | (pl.pair << 1), pl.bn_, pl.bh, pl.bw, pl.tiles_n * pl.tiles_h * pl.tiles_w, pl.n_tiles,
+                         pl.stages, pl.a_stages, pl.a_stage_bytes, (int32_t)pl.smem_bytes, pl.rows_valid, pl.tmem_cols,
+                         pl.hpitch, pl.cps};
+  for (int i = 0; i < 16; ++i) out[i] = v[i];
   return SDEO_OK;
 }
 
@@ -1343,6 +1641,7 @@ static int launch_conv(const sdeo_conv_args* a, const ConvPlan& pl, void* stream
     uint64_t dims[4] = {(uint64_t)a->c1, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n};
     uint64_t strides[3] = {(uint64_t)a->ld1 * 2, (uint64_t)a->w * a->ld1 * 2, (uint64_t)a->h * a->w * a->ld1 * 2};
     uint32_t box[4] = {64, (uint32_t)pl.bw * st, (uint32_t)pl.bh * st, (uint32_t)pl.bn_};
+    if (pl.halo) { box[1] = (uint32_t)pl.bw + 2; box[2] = (uint32_t)pl.bh + 2; }
     uint32_t es[4] = {1, st, st, 1};
     int rc = encode_tmap_bf16(&tmA1, a->x1, 4, dims, strides, box, es);
     if (rc) return rc;
@@ -1352,6 +1651,7 @@ static int launch_conv(const sdeo_conv_args* a, const ConvPlan& pl, void* stream
     uint64_t dims[4] = {(uint64_t)a->c2, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n};
     uint64_t strides[3] = {(uint64_t)a->ld2 * 2, (uint64_t)a->w * a->ld2 * 2, (uint64_t)a->h * a->w * a->ld2 * 2};
     uint32_t box[4] = {64, (uint32_t)pl.bw * st, (uint32_t)pl.bh * st, (uint32_t)pl.bn_};
+    if (pl.halo) { box[1] = (uint32_t)pl.bw + 2; box[2] = (uint32_t)pl.bh + 2; }
     uint32_t es[4] = {1, st, st, 1};
     int rc = encode_tmap_bf16(&tmA2, a->x2, 4, dims, strides, box, es);
     if (rc) return rc;
@@ -1360,7 +1660,7 @@ static int launch_conv(const sdeo_conv_args* a, const ConvPlan& pl, void* stream
     const uint64_t kp = (uint64_t)a->ksize * a->ksize * pl.cpt * 64;
     uint64_t dims[2] = {kp, (uint64_t)pl.rows_packed};
     uint64_t strides[1] = {kp * 2};
-    uint32_t box[2] = {64, (uint32_t)pl.BN};
+    uint32_t box[2] = {64, (uint32_t)(pl.pair ? pl.BN / 2 : pl.BN)};
     uint32_t es[2] = {1, 1};
     int rc = encode_tmap_bf16(&tmB, a->w_packed, 2, dims, strides, box, es);
     if (rc) return rc;
@@ -1370,7 +1670,9 @@ static int launch_conv(const sdeo_conv_args* a, const ConvPlan& pl, void* stream
   p.kw = a->ksize; p.pad = a->pad; p.stride = a->stride;
   p.c1_chunks = pl.c1c; p.chunks_per_tap = pl.cpt;
   p.total_chunks = pl.total_chunks; p.chunks_per_split = pl.cps; p.splits = pl.splits;
-  p.bn_ = pl.bn_; p.bh = pl.bh; p.bw = pl.bw; p.rows_valid = pl.bn_ * pl.bh * pl.bw;
+  p.bn_ = pl.bn_; p.bh = pl.bh; p.bw = pl.bw; p.rows_valid = pl.rows_valid;
+  p.halo = pl.halo; p.hpitch = pl.hpitch; p.a_stages = pl.a_stages; p.a_stage_bytes = pl.a_stage_bytes;
+  p.pair = pl.pair; p.m_tiles = pl.tiles_n * pl.tiles_h * pl.tiles_w;
   p.tiles_h = pl.tiles_h; p.tiles_w = pl.tiles_w;
   p.N = a->n; p.Ho = pl.Ho; p.Wo = pl.Wo;
   p.BN = pl.BN; p.cout = a->cout; p.stages = pl.stages; p.tmem_cols = pl.tmem_cols;
@@ -1393,14 +1695,15 @@ static int launch_conv(const sdeo_conv_args* a, const ConvPlan& pl, void* stream
     return set_error(SDEO_EINVAL, "conv2d: folded LayerNorm needs ln_csum, ln_parts and ln_c");
 
   // ---- pick the kernel instantiation ----
+#define KSEL(...) (pl.pair ? conv_gemm_kernel<__VA_ARGS__, true> : conv_gemm_kernel<__VA_ARGS__, false>)
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvKParams);
   KernelFn fn = nullptr;
   if (a->epi_mode == SDEO_EPI_GEGLU) {
-    fn = p.ln_stats ? conv_gemm_kernel<SDEO_EPI_GEGLU, OUT_BF16, RES_NONE, true, 0, true>
-                    : conv_gemm_kernel<SDEO_EPI_GEGLU, OUT_BF16, RES_NONE, true, 0, false>;
+    fn = p.ln_stats ? KSEL(SDEO_EPI_GEGLU, OUT_BF16, RES_NONE, true, 0, true)
+                    : KSEL(SDEO_EPI_GEGLU, OUT_BF16, RES_NONE, true, 0, false);
   } else if (a->epi_mode == SDEO_EPI_QKV) {
-    fn = p.ln_stats ? conv_gemm_kernel<SDEO_EPI_QKV, OUT_BF16, RES_NONE, true, 0, true>
-                    : conv_gemm_kernel<SDEO_EPI_QKV, OUT_BF16, RES_NONE, true, 0, false>;
+    fn = p.ln_stats ? KSEL(SDEO_EPI_QKV, OUT_BF16, RES_NONE, true, 0, true)
+                    : KSEL(SDEO_EPI_QKV, OUT_BF16, RES_NONE, true, 0, false);
   } else {
     const int out_kind = !a->y_fp32 ? OUT_BF16 : (p.y2 ? OUT_F32_TWIN : OUT_F32);
     const int res_kind = !a->residual ? RES_NONE : (a->residual_f32 ? RES_F32 : RES_BF16);
@@ -1413,47 +1716,50 @@ static int launch_conv(const sdeo_conv_args* a, const ConvPlan& pl, void* stream
     if (res_kind == RES_F32) fast = fast && (a->ldr % 4 == 0);
     if (!fast) {
       if (p.ln_stats) return set_error(SDEO_EINVAL, "conv2d: folded LayerNorm needs the vector-aligned epilogue");
-      fn = conv_gemm_kernel<SDEO_EPI_NORMAL, OUT_BF16, RES_NONE, false, 0, false>;
+      fn = KSEL(SDEO_EPI_NORMAL, OUT_BF16, RES_NONE, false, 0, false);
     } else if (p.ln_stats) {
       // (plain-epilogue consumers of a folded LayerNorm: bf16 or fp32 output, no residual; used by the tests)
       if (res_kind != RES_NONE || out_kind == OUT_F32_TWIN)
         return set_error(SDEO_EINVAL, "conv2d: folded LayerNorm supports the QKV, GEGLU and residual-free plain epilogues");
-      fn = out_kind == OUT_F32 ? conv_gemm_kernel<SDEO_EPI_NORMAL, OUT_F32, RES_NONE, true, 0, true>
-                               : conv_gemm_kernel<SDEO_EPI_NORMAL, OUT_BF16, RES_NONE, true, 0, true>;
+      fn = out_kind == OUT_F32 ? KSEL(SDEO_EPI_NORMAL, OUT_F32, RES_NONE, true, 0, true)
+                               : KSEL(SDEO_EPI_NORMAL, OUT_BF16, RES_NONE, true, 0, true);
     } else if (row_stats_ok(a, pl)) {
       p.row_stats = (float2*)a->row_stats;
       p.row_stats_ld = a->row_stats_ld;
-#define SDEO_PICK(O, R) if (out_kind == O && res_kind == R) fn = conv_gemm_kernel<SDEO_EPI_NORMAL, O, R, true, 2, false>;
+#define SDEO_PICK(O, R) if (out_kind == O && res_kind == R) fn = KSEL(SDEO_EPI_NORMAL, O, R, true, 2, false);
       SDEO_PICK(OUT_F32, RES_NONE) SDEO_PICK(OUT_F32, RES_BF16) SDEO_PICK(OUT_F32, RES_F32)
       SDEO_PICK(OUT_F32_TWIN, RES_NONE) SDEO_PICK(OUT_F32_TWIN, RES_BF16) SDEO_PICK(OUT_F32_TWIN, RES_F32)
 #undef SDEO_PICK
     } else if (stats_parts(a, pl) > 0) {
       p.gn_stats = (float2*)a->gn_stats;
-#define SDEO_PICK(O, R) if (out_kind == O && res_kind == R) fn = conv_gemm_kernel<SDEO_EPI_NORMAL, O, R, true, 1, false>;
+#define SDEO_PICK(O, R) if (out_kind == O && res_kind == R) fn = KSEL(SDEO_EPI_NORMAL, O, R, true, 1, false);
       SDEO_PICK(OUT_F32, RES_NONE) SDEO_PICK(OUT_F32, RES_BF16) SDEO_PICK(OUT_F32, RES_F32)
       SDEO_PICK(OUT_F32_TWIN, RES_NONE) SDEO_PICK(OUT_F32_TWIN, RES_BF16) SDEO_PICK(OUT_F32_TWIN, RES_F32)
 #undef SDEO_PICK
     } else {
-#define SDEO_PICK(O, R) if (out_kind == O && res_kind == R) fn = conv_gemm_kernel<SDEO_EPI_NORMAL, O, R, true, 0, false>;
+#define SDEO_PICK(O, R) if (out_kind == O && res_kind == R) fn = KSEL(SDEO_EPI_NORMAL, O, R, true, 0, false);
       SDEO_PICK(OUT_BF16, RES_NONE) SDEO_PICK(OUT_BF16, RES_BF16) SDEO_PICK(OUT_BF16, RES_F32)
       SDEO_PICK(OUT_F32, RES_NONE) SDEO_PICK(OUT_F32, RES_BF16) SDEO_PICK(OUT_F32, RES_F32)
       SDEO_PICK(OUT_F32_TWIN, RES_NONE) SDEO_PICK(OUT_F32_TWIN, RES_BF16) SDEO_PICK(OUT_F32_TWIN, RES_F32)
 #undef SDEO_PICK
     }
   }
+#undef KSEL
   if (!fn) return set_error(SDEO_EINVAL, "conv2d: no kernel instantiation");
   {
     // opt in to > 48 KB of dynamic shared memory, once per instantiation
-    static KernelFn configured[48];
+    static KernelFn configured[96];
     static int n_configured = 0;
     bool seen = false;
     for (int i = 0; i < n_configured; ++i) seen = seen || (configured[i] == fn);
     if (!seen) {
       cudaError_t e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess) return set_error(SDEO_ECUDA, cudaGetErrorString(e));
-      if (n_configured < 48) configured[n_configured++] = fn;
+      if (n_configured < 96) configured[n_configured++] = fn;
     }
   }
-  return launch_k("conv2d", fn, dim3((unsigned)(pl.tiles_n * pl.tiles_h * pl.tiles_w), (unsigned)pl.n_tiles, (unsigned)pl.splits),
-                  dim3(kConvThreads), pl.smem_bytes, (cudaStream_t)stream, dim3(1, 1, (unsigned)pl.splits), tmA1, tmA2, tmB, p);
+  unsigned gx = (unsigned)(pl.tiles_n * pl.tiles_h * pl.tiles_w);
+  if (pl.pair) gx = (gx + 1u) & ~1u;
+  return launch_k("conv2d", fn, dim3(gx, (unsigned)pl.n_tiles, (unsigned)pl.splits), dim3(kConvThreads), pl.smem_bytes,
+                  (cudaStream_t)stream, dim3(pl.pair ? 2u : 1u, 1, (unsigned)pl.splits), tmA1, tmA2, tmB, p);
 }

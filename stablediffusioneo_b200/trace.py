@@ -9,7 +9,7 @@ import torch
 from . import _lib
 
 KINDS = {1: "conv", 2: "attention", 3: "groupnorm", 4: "layernorm", 5: "elementwise"}
-Record = collections.namedtuple("Record", "kind grid mode splits bn start dep end")
+Record = collections.namedtuple("Record", "kind grid mode splits bn start dep end halo", defaults=(0,))
 
 
 def capture(fn, device, capacity=8192):
@@ -35,7 +35,7 @@ def capture(fn, device, capacity=8192):
         tag = int(rec[i, 0])
         out.append(Record(KINDS.get(tag & 0xFF, "?"), (tag >> 8) & 0xFFFFFFFF, (tag >> 40) & 0xF, (tag >> 44) & 0xF,
                           (tag >> 48) & 0xFFF, (int(rec[i, 1]) - t0) / 1e3, (int(rec[i, 2]) - t0) / 1e3,
-                          (int(rec[i, 3]) - t0) / 1e3))
+                          (int(rec[i, 3]) - t0) / 1e3, (tag >> 60) & 1))
     return out
 
 

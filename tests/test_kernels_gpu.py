@@ -78,6 +78,75 @@ def test_conv2d_plain(cuda_device, case):
     assert err < TOL, f"rel L2 {err}"
 
 
+HALO_CASES = [
+    # (n, c1, c2, cout, h, w)  3x3 stride 1: the HALO tiling (one A tile per channel chunk serves the nine taps)
+    (2, 320, 0, 320, 32, 48),      # 14 tiles of 5 x 24 pixels, pitch 26
+    (2, 640, 320, 320, 32, 48),    # fused concat: chunks from two tensor maps
+    (2, 640, 0, 640, 16, 24),
+    (2, 1280, 0, 1280, 8, 12),     # one tile per sample; split-K over (chunk, tap) steps
+    (1, 96, 0, 96, 20, 28),        # ragged tiles: halo boxes hang over the right / bottom edge
+    (1, 64, 0, 128, 64, 64),
+    (1, 128, 0, 64, 40, 100),      # pitch 102: one image row per tile
+    (1, 24, 0, 48, 13, 9),         # partial channel chunk (24 of 64), tiny map
+]
+
+
+@pytest.mark.parametrize("splits", [0, 1, 2, 3, 8])
+@pytest.mark.parametrize("case", HALO_CASES)
+def test_conv2d_halo_tiles(cuda_device, case, splits):
+    """SDEO_HALO=1 forces the halo tiling (0 forces the tap-by-tap tiling), SDEO_PAIR=1 forces CTA pairs (cta_group::2:
+    two CTAs run one M=256 MMA, each staging half of the weight tile; an odd M-tile count adds a null tile): all four
+    combinations against F.conv2d on the bf16-rounded operands and against each other, plain bf16 output and the full fp32 epilogue (bias, residual, twin, GroupNorm
+    statistics). splits = forced K slices (cluster split-K; slices start in the middle of a channel chunk)."""
+    import os
+    from stablediffusioneo_b200 import ops
+    n, c1, c2, cout, h, w = case
+    dev = cuda_device
+    cin = c1 + c2
+    x = gen((n, cin, h, w), 1, dev)
+    wt = gen((cout, cin, 3, 3), 2, dev, scale=1.0 / math.sqrt(cin * 9))
+    b = gen((cout,), 3, dev)
+    res = gen((n, h, w, cout), 5, dev)
+    pw = ops.pack_conv_weight(wt, c1=c1, c2=c2) if c2 else ops.pack_conv_weight(wt)
+    xa = nhwc(x[:, :c1])
+    xb = nhwc(x[:, c1:]) if c2 else None
+    ref = ref_conv(x, wt, b, 1)
+    ref32 = ref + res.permute(0, 3, 1, 2)
+    got = {}
+    try:
+        if splits:
+            os.environ["SDEO_FORCE_SPLITS"] = str(splits)
+        for halo, pair in (("1", "1"), ("1", "0"), ("0", "1"), ("0", "0")):
+            os.environ["SDEO_HALO"], os.environ["SDEO_PAIR"] = halo, pair
+            if pair == "1" and (splits > 4 or n * ((h * w + 127) // 128) < 2):
+                continue  # a CTA pair leaves room for 4 K slices in a cluster of 8; needs two M tiles
+            try:
+                y = ops.conv2d(xa, pw, x2=xb, bias=b)
+                ys, yt = ops.conv2d(xa, pw, x2=xb, bias=b, residual=res, out_fp32=True, twin=True, gn_stats=True)
+            except Exception as ex:  # split count does not fit shared memory for this shape
+                assert splits > 1, ex
+                pytest.skip(f"splits={splits} does not fit: {ex}")
+            torch.cuda.synchronize()
+            assert rel_l2(y.permute(0, 3, 1, 2), ref) < TOL, (halo, pair)
+            assert rel_l2(ys.permute(0, 3, 1, 2), ref32) < 2e-3, (halo, pair)
+            assert torch.equal(yt, ys.to(torch.bfloat16))
+            st = getattr(ys, "_gn_stats", None)
+            if cout % 32 == 0:
+                assert st is not None
+                gamma, beta = gen((cout,), 6, dev) * 0.2 + 1.0, gen((cout,), 7, dev) * 0.2
+                out = ops.groupnorm(ys, gamma, beta, 1e-5, True, stats=st)
+                gref = F.silu(F.group_norm(ys.permute(0, 3, 1, 2), 32, gamma, beta, 1e-5))
+                assert rel_l2(out.permute(0, 3, 1, 2), gref) < TOL, (halo, pair)
+            got[halo + pair] = ys
+    finally:
+        os.environ.pop("SDEO_HALO", None)
+        os.environ.pop("SDEO_PAIR", None)
+        os.environ.pop("SDEO_FORCE_SPLITS", None)
+    base = got["00"]
+    for k_, v_ in got.items():
+        assert rel_l2(v_, base) < 1e-5, k_   # same products, different fp32 summation order
+
+
 def test_conv2d_full_epilogue(cuda_device):
     """bias + per-sample time-embedding term + SiLU + scale + residual, fp32 and bf16 outputs."""
     from stablediffusioneo_b200 import ops
@@ -135,6 +204,45 @@ def test_linear(cuda_device, rows, kdim, ndim):
     y = ops.linear(x.to(torch.bfloat16), pw, bias=b, residual=res.to(torch.bfloat16))
     ref = F.linear(bf16r(x), bf16r(wt), b) + bf16r(res)
     assert rel_l2(y, ref) < TOL
+
+
+@pytest.mark.parametrize("pair", ["0", "1"])
+@pytest.mark.parametrize("rows,kdim,ndim", [(384, 320, 320), (640, 640, 1280), (1000, 96, 48), (3072, 1280, 320)])
+def test_linear_cta_pairs(cuda_device, rows, kdim, ndim, pair):
+    """Linears under forced CTA pairs (cta_group::2), including ODD M-tile counts (384 rows = 3 tiles, 640 = 5, 1000 = 8
+    with a ragged last tile): the pair's null tile loads nothing but zeros and writes nothing. Plain, residual-stream
+    (fp32 + twin + row statistics) and GEGLU epilogues."""
+    import os
+    from stablediffusioneo_b200 import ops
+    dev = cuda_device
+    x = gen((rows, kdim), 1, dev)
+    wt = gen((ndim, kdim), 2, dev, scale=1.0 / math.sqrt(kdim))
+    b = gen((ndim,), 3, dev)
+    res = gen((rows, ndim), 4, dev)
+    xb = x.to(torch.bfloat16)
+    ref = bf16r(x) @ bf16r(wt).t() + b
+    os.environ["SDEO_PAIR"] = pair
+    try:
+        y = ops.linear(xb, ops.pack_conv_weight(wt), bias=b)
+        assert rel_l2(y, ref) < TOL
+        ys, yt = ops.linear(xb, ops.pack_conv_weight(wt), bias=b, residual=res, out_fp32=True, twin=True,
+                            row_stats=ndim % 64 == 0)   # row statistics need an N tile of 64 / 128 / 256 columns
+        assert rel_l2(ys, ref + res) < 2e-3 and torch.equal(yt, ys.to(torch.bfloat16))
+        rs = getattr(ys, "_row_stats", None)
+        if rs is not None:
+            buf, parts, nrows = rs
+            tot = buf[:parts].sum(0)
+            assert torch.allclose(tot[:, 0], ys.sum(1), rtol=1e-3, atol=1e-2)
+        if ndim % 64 == 0:
+            w2 = gen((2 * ndim, kdim), 5, dev, scale=1.0 / math.sqrt(kdim))
+            b2 = gen((2 * ndim,), 6, dev)
+            pw = ops.pack_conv_weight(w2, geglu=True)
+            yg = ops.linear(xb, pw, bias=ops.pack_geglu_bias(b2, pw.geglu_bn), geglu=True)
+            full = bf16r(x) @ bf16r(w2).t() + b2
+            gref = full[:, :ndim] * F.gelu(full[:, ndim:])
+            assert rel_l2(yg, gref) < TOL
+    finally:
+        os.environ.pop("SDEO_PAIR", None)
 
 
 @pytest.mark.parametrize("rows,c", [(3072, 320), (768, 640), (192, 1280), (48, 1280)])

@@ -363,7 +363,7 @@ def test_engine_follows_weight_updates(tiny, cuda_device):
         generic = DDIMSampler(model)
         generic.use_engine = False
         ref, _ = generic.sample(4, 1, (4, 8, 16), cond, **kw)
-        assert rel_l2(second, ref) < 2e-2
+        assert rel_l2(second, ref) < 3e-2   # engine vs generic path on the tiny model (the 4-step sampler gate)
         assert rel_l2(second, first) > 5e-2, "the new weights did not change the result (stale replay?)"
     finally:
         model.load_state_dict(keep, strict=True)

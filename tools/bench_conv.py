@@ -15,6 +15,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--only", default="")
 ap.add_argument("--autotune", action="store_true")
+ap.add_argument("--set", default="step", choices=["step", "large"], help="step: 256x384 batch-2 layer shapes; large: the "
+                "3x3 shapes of 512x512, 768x768 batch 4 (x2 for cond+uncond) and the VAE decoder at 512x512")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 if args.autotune:
@@ -42,6 +44,36 @@ CASES = [
     ("conv3 8->320 @32x48 conv_in", 2, 32, 48, 8, 0, 320, 3, 1, "stream"),
     ("conv3 320->4 @32x48 out", 2, 32, 48, 320, 0, 4, 3, 1, "plain32"),
 ]
+
+LARGE = [
+    ("conv3 320->320 @64x64 b2", 2, 64, 64, 320, 0, 320, 3, 1, "stream"),
+    ("conv3 640->640 @32x32 b2", 2, 32, 32, 640, 0, 640, 3, 1, "stream"),
+    ("conv3 1280->1280 @16x16 b2", 2, 16, 16, 1280, 0, 1280, 3, 1, "stream"),
+    ("conv3 320->320 @96x96 b8", 8, 96, 96, 320, 0, 320, 3, 1, "stream"),
+    ("conv3 960->320 @96x96 b8 dual", 8, 96, 96, 640, 320, 320, 3, 1, "plain32"),
+    ("conv3 640->640 @48x48 b8", 8, 48, 48, 640, 0, 640, 3, 1, "stream"),
+    ("conv3 1280->1280 @24x24 b8", 8, 24, 24, 1280, 0, 1280, 3, 1, "stream"),
+    ("lin   320->2560 geglu M=73728", 1, 1, 73728, 320, 0, 2560, 1, 1, "geglu"),
+    ("vae conv3 512->512 @128x128 b4", 4, 128, 128, 512, 0, 512, 3, 1, "plain"),
+    ("vae conv3 256->256 @256x256 b4", 4, 256, 256, 256, 0, 256, 3, 1, "plain"),
+    ("vae conv3 128->128 @512x512 b4", 4, 512, 512, 128, 0, 128, 3, 1, "plain"),
+]
+if args.set == "large":
+    CASES = LARGE
+
+
+def plan_of(a_kwargs):
+    """(N tile, K slices, halo, bh x bw, M tiles) of the plan the library uses for the last call's shape."""
+    import ctypes
+    from stablediffusioneo_b200 import _lib
+    a = _lib.ConvArgs()
+    for k_, v_ in a_kwargs.items():
+        setattr(a, k_, v_)
+    out = (ctypes.c_int32 * 16)()
+    if _lib.load().sdeo_conv_plan_describe(ctypes.byref(a), -1, out, 16) != 0:
+        return "?"
+    return f"BN {out[0]:3d} S {out[1]} halo {out[2]} box {out[4]}x{out[5]} tiles {out[6]}x{out[7]}"
+
 
 tot = 0.0
 for name, n, h, w, c1, c2, cout, k, stride, mode in CASES:
@@ -95,5 +127,15 @@ for name, n, h, w, c1, c2, cout, k, stride, mode in CASES:
     flops = 2.0 * n * ho * wo * cout * cin * k * k
     wbytes = pw.data.numel() * 2
     tot += us
-    print(f"{name:34s} {us:8.1f} us  {flops / us / 1e6:7.1f} TFLOP/s  weights {wbytes / us / 1e3:7.1f} GB/s")
+    import ctypes
+    P = lambda v: ctypes.c_void_p(256)
+    pk = dict(x1=P(0), w_packed=P(0), y=P(0), n=n, h=h, w=w, c1=c1, ld1=c1, c2=c2, ld2=c2, cout=cout, ksize=k, stride=stride,
+              pad=pad, scale=1.0, ldy=cout, epi_mode=kw.get("epi_mode", 0))
+    if c2:
+        pk["x2"] = P(0)
+    if mode == "stream":
+        pk.update(residual=P(0), ldr=cout, residual_f32=1, y_fp32=1, y2=P(0), ldy2=cout)
+    elif mode == "plain32":
+        pk.update(emb=P(0), y_fp32=1)
+    print(f"{name:34s} {us:8.1f} us  {flops / us / 1e6:7.1f} TFLOP/s  weights {wbytes / us / 1e3:7.1f} GB/s   {plan_of(pk) if mode != 'qkv' else ''}")
 print(f"sum {tot:.1f} us")

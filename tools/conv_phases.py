@@ -19,6 +19,10 @@ CASES = {
     "c1_res16": (2, 32, 48, 320, 320, 1, "res16"),
     "c1_f32": (2, 32, 48, 320, 320, 1, "plain32"),
     "c1_f32res": (2, 32, 48, 320, 320, 1, "f32res"),
+    "conv3_plain": (2, 32, 48, 320, 320, 3, "plain"),
+    "conv3_64": (2, 64, 64, 320, 320, 3, "stream"),
+    "conv3_96": (8, 96, 96, 320, 320, 3, "stream"),
+    "vae128": (4, 512, 512, 128, 128, 3, "plain"),
 }
 names = sys.argv[1:] or list(CASES)
 for name in names:
@@ -35,7 +39,7 @@ for name in names:
         kw.update(residual=torch.randn((n, h, w, cout), device=dev).to(BF))
     elif mode == "plain32":
         kw.update(out_fp32=True)
-    dbg = torch.zeros((4096, 16), dtype=torch.int64, device=dev)
+    dbg = torch.zeros((40000, 16), dtype=torch.int64, device=dev)
     for _ in range(3):
         ops.conv2d(x, pw, **kw)
     torch.cuda.synchronize()
@@ -51,7 +55,12 @@ for name in names:
     for i in range(1, 9):
         col = rel[:, i]
         print(f"   {lab[i]:11s} {col.median().item():9.0f} {col.max().item():9.0f}")
-    if used[:, 9].max() > 0:
+    if used[:, 9].max() > 0 or used[:, 10].max() > 0:
+        lead = used[used[:, 9] > 0]
+        print(f"   MMA warp: cycles waiting for operand data (full barriers) {lead[:, 9].float().median().item():.0f}; "
+              f"producer: cycles waiting for free stages (empty barriers) {used[:, 10].float().median().item():.0f}; "
+              f"producer issued its last load at {(used[:, 11] - used[:, 0]).float().median().item():.0f}; stages {int(used[0, 12])}")
+    if False:
         for a, b, c, nm in ((9, 10, 11, "chunk 8"), (12, 13, 14, "chunk 16")):
             print(f"   {nm}: at {rel[:, a].median().item():.0f}; wait-for-data {(used[:, b] - used[:, a]).float().median().item():.0f}"
                   f" cycles; issue 4 MMAs + commit {(used[:, c] - used[:, b]).float().median().item():.0f} cycles")
