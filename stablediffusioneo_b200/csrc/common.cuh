@@ -265,6 +265,62 @@ __device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t a_des
       : "memory");
 }
 
+// One K step of the mainloop (four K=16 MMAs on consecutive 32-byte slices of a 64-wide operand chunk, then the commit that
+// frees the stage) with a NON-BLOCKING probe of the next stage's full barrier issued behind the first MMA: the probe's
+// ~150-cycle latency then overlaps the MMA issue instead of sitting between two steps (the tensor pipe queues about one
+// MMA, so whatever the issuing thread does between steps is idle pipe time -- tools/exp_issue.cu). Returns 1 if the probed
+// phase is complete (the caller then skips the blocking wait).
+template <bool PAIR>
+__device__ __forceinline__ uint32_t tc_mma_step_probe(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                      uint32_t accumulate, uint64_t* commit_bar, uint16_t pair_mask,
+                                                      uint64_t* probe_bar, uint32_t probe_parity) {
+  uint32_t ready;
+  if (PAIR) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pacc, prdy, pt;\n\t"
+        ".reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+        "setp.ne.b32 pacc, %5, 0;\n\t"
+        "setp.eq.b32 pt, %5, %5;\n\t"
+        "add.u64 a1, %2, 2;\n\tadd.u64 a2, %2, 4;\n\tadd.u64 a3, %2, 6;\n\t"
+        "add.u64 b1, %3, 2;\n\tadd.u64 b2, %3, 4;\n\tadd.u64 b3, %3, 6;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%1], %2, %3, %4, pacc;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 prdy, [%8], %9;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%1], a1, b1, %4, pt;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%1], a2, b2, %4, pt;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%1], a3, b3, %4, pt;\n\t"
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%6], %7;\n\t"
+        "selp.u32 %0, 1, 0, prdy;\n\t"
+        "}\n"
+        : "=r"(ready)
+        : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(smem_u32(commit_bar)), "h"(pair_mask),
+          "r"(smem_u32(probe_bar)), "r"(probe_parity)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pacc, prdy, pt;\n\t"
+        ".reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+        "setp.ne.b32 pacc, %5, 0;\n\t"
+        "setp.eq.b32 pt, %5, %5;\n\t"
+        "add.u64 a1, %2, 2;\n\tadd.u64 a2, %2, 4;\n\tadd.u64 a3, %2, 6;\n\t"
+        "add.u64 b1, %3, 2;\n\tadd.u64 b2, %3, 4;\n\tadd.u64 b3, %3, 6;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %3, %4, pacc;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 prdy, [%7], %8;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], a1, b1, %4, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], a2, b2, %4, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], a3, b3, %4, pt;\n\t"
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t"
+        "selp.u32 %0, 1, 0, prdy;\n\t"
+        "}\n"
+        : "=r"(ready)
+        : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(smem_u32(commit_bar)),
+          "r"(smem_u32(probe_bar)), "r"(probe_parity)
+        : "memory");
+  }
+  return ready;
+}
+
 // K-major, 128-byte-swizzled operand tile: rows are 128 B (64 bf16) apart, 8-row groups 1024 B apart.
 // (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
 //  layout_type [61,64) with SWIZZLE_128B = 2.)

@@ -25,6 +25,13 @@
 namespace sdeo {
 
 constexpr int kConvThreads = 384;  // warp 0 TMA, warp 1 MMA, warps 2..5 TMEM drain; all 12 warps run epilogue phase 2
+// TMA producers: lane 0 of warps 0, 9, 10, 11. One thread pays ~200 cycles per mbarrier.try_wait (even on a completed phase)
+// plus ~45 + 3 cycles/KB per cp.async.bulk.tensor it issues (tools/exp_issue.cu) -- 450..600 cycles per K step, more than the
+// MMAs of the step take (2 N cycles for a 128 x N x 64 step). K step i belongs to producer i % nprod, so the waits and
+// issues of consecutive steps overlap. The ring depth is a multiple of nprod: a ring slot is then always refilled by the
+// same thread, whose program order keeps it at most one barrier phase ahead (a parity wait cannot tell phases two apart).
+constexpr int kProducers = 4;
+constexpr int kHelperThreads = 96;  // warps 6..8: column vectors, folded-LayerNorm row statistics, residual prefetch
 constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kATileBytes = kBM * kBK * 2;  // 16 KB
@@ -59,7 +66,8 @@ struct ConvKParams {
   __nv_bfloat16* vt;
   int heads, dhead, tokens, ldv, qkv_first;
   long long* dbg;  // optional per-CTA phase timestamps (SDEO_CONV_DEBUG), 16 slots per CTA
-  int res_smem_off;        // > 0: idle warps prefetch the residual tile into shared memory at this byte offset
+  int res_smem_off;        // > 0: the residual tile is fetched into shared memory at this byte offset by one TMA box of
+  int res_tx;              //      res_tx bytes during the mainloop
   // STATS == 2 (producer of a LayerNorm input): per output row (sum, sum of squares) over this N tile's columns
   float2* row_stats;      // [n_tile][row_stats_ld]
   int row_stats_ld;
@@ -82,6 +90,12 @@ struct ConvKParams {
   // K step: each stages its own 128 rows of A and its half (BN/2 rows) of the weight tile. m_tiles = real M tiles (grid.x is
   // rounded up to even; the odd one out is a null tile whose loads fall outside the tensor and whose rows are all invalid).
   int pair, m_tiles;
+  int nprod;  // TMA producer threads in use (<= kProducers); stages % nprod == 0
+  // epilogue phase 2 geometry, computed on the host (integer divisions by run-time values cost ~100 cycles each on the
+  // epilogue's critical path): rows per K-slice rank, (row, 8- or 16-column) items per row, rows / leftover items one
+  // pass of the 384 threads covers, and the multiplier that turns threadIdx.x / cols_items into a multiply-shift
+  int rows_per, cols_items, step_rows, step_cols, ci_magic;
+  int probe;  // MMA issuer probes the next stage's barrier while it issues the current step (SDEO_NO_PROBE=1: off)
 };
 
 #define SDEO_DBG(slot)                                                                               \
@@ -140,16 +154,16 @@ enum { OUT_BF16 = 0, OUT_F32 = 1, OUT_F32_TWIN = 2 };
 enum { RES_NONE = 0, RES_BF16 = 1, RES_F32 = 2 };
 
 // NORMAL epilogue, fast path: cout % 16 == 0 (every N tile full) and all row pitches vector-aligned (checked on the host).
+// cv: this item's 8 entries of the CTA's column vector in shared memory (bias, plus the time-embedding row when the whole
+// tile adds the same one); batch >= 0: the embedding row differs between the rows of the tile and comes from global memory.
 template <int OUT, int RES>
 __device__ __forceinline__ void epi_normal_fast(const ConvKParams& p, long long pix, int batch, int n, float* v,
-                                                const uint4& raw0, const uint4& raw1) {
-  if (p.bias) {
-    float b[8];
-    load8_f32(p.bias + n, b);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] += b[j];
+                                                const uint4& raw0, const uint4& raw1, const float* cv) {
+  {
+    const float4 c0 = *reinterpret_cast<const float4*>(cv), c1 = *reinterpret_cast<const float4*>(cv + 4);
+    v[0] += c0.x; v[1] += c0.y; v[2] += c0.z; v[3] += c0.w; v[4] += c1.x; v[5] += c1.y; v[6] += c1.z; v[7] += c1.w;
   }
-  if (p.emb) {
+  if (batch >= 0) {
     float e[8];
     load8_f32(p.emb + (long long)batch * p.cout + n, e);
 #pragma unroll
@@ -291,7 +305,7 @@ __device__ __noinline__ void epi_normal_item(const ConvKParams& p, const RowInfo
 }
 
 // QKV epilogue of one item: scatter into head-major q/k and transposed v.
-__device__ __forceinline__ void epi_qkv_item(const ConvKParams& p, const RowInfo& ri, int n, float* v) {
+__device__ __forceinline__ void epi_qkv_item(const ConvKParams& p, const RowInfo& ri, int n, float* v, const float* cv) {
   if (n >= p.cout) return;
   const int C = p.heads * p.dhead;
   const int which = n / C + p.qkv_first;
@@ -300,11 +314,9 @@ __device__ __forceinline__ void epi_qkv_item(const ConvKParams& p, const RowInfo
   const int dd = nc % p.dhead;
   const int b = (int)(ri.pix / p.tokens);
   const int tok = (int)(ri.pix % p.tokens);
-  if (p.bias) {
-    float bb[8];
-    load8_f32(p.bias + n, bb);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] += bb[j];
+  {
+    const float4 c0 = *reinterpret_cast<const float4*>(cv), c1 = *reinterpret_cast<const float4*>(cv + 4);
+    v[0] += c0.x; v[1] += c0.y; v[2] += c0.z; v[3] += c0.w; v[4] += c1.x; v[5] += c1.y; v[6] += c1.z; v[7] += c1.w;
   }
   const long long bh = (long long)b * p.heads + head;
   if (which < 2) {
@@ -317,7 +329,8 @@ __device__ __forceinline__ void epi_qkv_item(const ConvKParams& p, const RowInfo
 // V^T part of the QKV epilogue: item = (8 consecutive token rows, one v column) -> ONE 16-byte store into
 // vt[b*heads + head][dd][tok .. tok+7]. Lanes run along the columns so the shared-memory reads are conflict-free.
 __device__ __forceinline__ void qkv_store_vt(const ConvKParams& p, const float* tile, int LD, const int* row_pix,
-                                             const float2* ln_vec, int n_base, int tid, int nthreads) {
+                                             const float2* ln_vec, int n_base, int tid, int nthreads, const float* colv,
+                                             const float* csumv) {
   const int C = p.heads * p.dhead;
   int vb = (2 - p.qkv_first) * C, ve = (3 - p.qkv_first) * C;  // global column range holding v
   if (vb < n_base) vb = n_base;
@@ -331,8 +344,8 @@ __device__ __forceinline__ void qkv_store_vt(const ConvKParams& p, const float* 
     const int n = vb + c;
     const int nc = n - (2 - p.qkv_first) * C;
     const int head = nc / p.dhead, dd = nc % p.dhead;
-    const float bias = p.bias ? __ldg(p.bias + n) : 0.f;
-    const float csum = ln_vec ? __ldg(p.ln_csum + n) : 0.f;
+    const float bias = colv[n - n_base];
+    const float csum = ln_vec ? csumv[n - n_base] : 0.f;
     float x[8];
     int pix[8];
 #pragma unroll
@@ -363,16 +376,11 @@ __device__ __forceinline__ void qkv_store_vt(const ConvKParams& p, const float* 
 }
 
 // GEGLU epilogue of one item: y[:, n_out..+7] = (x + bx) * gelu(gate + bg); nb_x / nb_g index the packed bias.
-__device__ __forceinline__ void epi_geglu_item(const ConvKParams& p, const RowInfo& ri, int n_out, int nb_x, int nb_g,
-                                               const float* vx, const float* vg) {
+__device__ __forceinline__ void epi_geglu_item(const ConvKParams& p, const RowInfo& ri, int n_out, const float* cv_x,
+                                               const float* cv_g, const float* vx, const float* vg) {
   float bx[8], bg[8], x[8];
-  if (p.bias) {
-    load8_f32(p.bias + nb_x, bx);
-    load8_f32(p.bias + nb_g, bg);
-  } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { bx[j] = 0.f; bg[j] = 0.f; }
-  }
+  for (int j = 0; j < 8; ++j) { bx[j] = cv_x[j]; bg[j] = cv_g[j]; }
 #pragma unroll
   for (int j = 0; j < 8; ++j) x[j] = (vx[j] + bx[j]) * gelu_erf_f(vg[j] + bg[j]);
   __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + ri.pix * p.ldy + n_out;
@@ -440,7 +448,7 @@ __device__ __forceinline__ bool tile_row_coords(const ConvKParams& p, int row, i
 template <int MODE, int OUT, int RES, bool FAST, int STATS, bool LNF, bool PAIR>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
-                 const __grid_constant__ CUtensorMap tmB, const ConvKParams p) {
+                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmR, const ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -451,11 +459,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   uint64_t* tmem_full_bar = empty_bar + 16;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
   uint64_t* recv_bar = full_bar + 48;  // split-K: completes when all S partial slices of this CTA's rows have arrived
+  uint64_t* res_bar = full_bar + 49;   // completes when the residual tile (one TMA box) has landed
   uint64_t* full_a = full_bar + 40;    // HALO mode: the A (halo tile) ring, up to 4 stages
   uint64_t* empty_a = full_bar + 44;
   int* row_pix = reinterpret_cast<int*>(smem + 512);  // [128] output pixel index per tile row
   float2* ln_vec = reinterpret_cast<float2*>(smem + 1024);  // [128] (mean, rstd) of the folded LayerNorm per tile row
-  uint8_t* tiles = smem + 2048;
+  float* colv = reinterpret_cast<float*>(smem + 2048);   // [BN] bias (+ the tile's time-embedding row) per column of this N tile
+  float* csumv = reinterpret_cast<float*>(smem + 3072);  // [BN] folded-LayerNorm column sums
+  uint8_t* tiles = smem + 4096;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
@@ -488,6 +499,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmB);
     if (p.chunks_per_tap > p.c1_chunks) tma_prefetch_desc(&tmA2);
+    if (p.res_smem_off) tma_prefetch_desc(&tmR);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -498,6 +510,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     }
     mbar_init(tmem_full_bar, 1);
     mbar_init(recv_bar, 1);
+    mbar_init(res_bar, 1);
     fence_mbar_init();
     if (p.splits > 1) {
       // bytes this CTA will receive: one slice of its own rows from each of the S K-slice ranks (armed here, long
@@ -532,7 +545,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   griddep_launch_dependents();
   // PDL: activations, residual, emb and the output buffers belong to earlier kernels of the stream until the grid
   // dependency resolves. Only the TMA thread goes on without waiting: it first streams WEIGHT tiles (constants).
-  if (threadIdx.x != 0) griddep_wait();
+  // producer index of this thread (-1: not a producer)
+  // (single-thread loops sit inside `if (elect_one())` under warp-uniform branches: ptxas then issues their TMA / MMA
+  //  instructions straight from uniform registers; under a `lane == 0` test it wraps each one in an election loop with
+  //  vector -> uniform register moves, several times the cost -- tools/exp_issue.cu)
+  const int prod = warp == 0 ? 0 : (warp >= 12 - (kProducers - 1) ? warp - (12 - kProducers) : -1);   // warp-uniform
+  const int np = p.nprod;
+  const bool prod_warp = prod >= 0 && prod < np;
+  if (prod_warp) {
+    if (!elect_one()) griddep_wait();   // (the elected lane waits inside its producer loop, after the weight prefetch)
+  } else {
+    griddep_wait();
+  }
 
   const int LD = p.BN + 4;  // fp32 tile row pitch in floats: 16-byte aligned rows, conflict-free 16 B row writes
   float* tile = reinterpret_cast<float*>(tiles);
@@ -550,52 +574,66 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   auto full_addr = [&](uint64_t* bar) -> uint32_t {
     return pair ? mapa_u32(smem_u32(bar), leader_rank) : smem_u32(bar);
   };
-  if (warp == 0 && p.halo) {
-    // ===================== TMA producer, HALO mode =====================
-    // K step i (global index k_begin + i): chunk c = idx / 9, tap t = idx % 9. One halo A tile per chunk, one weight tile
-    // per step; the weight tile of (c, t) sits at packed K offset (t * chunks_per_tap + c) * 64.
-    if (lane == 0) {
+  if (prod_warp && p.halo) {
+    // ===================== TMA producers, HALO mode =====================
+    // K step i (global index g = k_begin + i): chunk c = g / 9, tap t = g % 9. One halo A tile per chunk, one weight tile
+    // per step; the weight tile of (c, t) sits at packed K offset (t * chunks_per_tap + c) * 64. The producer that owns
+    // the first step of a chunk inside this CTA's K range also loads the chunk's halo tile.
+    if (elect_one()) {
       const int nb0 = n_tile * p.BN + (int)px * bn_cta;
       const uint32_t a_tx = (uint32_t)((p.bh + 2) * p.hpitch) * 128u * (uint32_t)tx_mult;
       const uint32_t b_tx = (uint32_t)(b_bytes * tx_mult);
-      int c = k_begin / 9, t = k_begin % 9;
       const int npre = nchunks < p.stages ? nchunks : p.stages;
+      const int c_first = k_begin / 9;
       {
-        int cc = c, tt = t;
-        for (int i = 0; i < npre; ++i) {  // weight tiles of the first ring pass: before the grid dependency resolves
+        int cc = (k_begin + prod) / 9, tt = (k_begin + prod) % 9;
+        for (int i = prod; i < npre; i += np) {  // weight tiles of the first ring pass: before the grid dependency resolves
           if (leader) mbar_expect_tx(&full_bar[i], b_tx);
           tma2d_to(b_ring + (size_t)i * b_bytes, &tmB, full_addr(&full_bar[i]), pair, (tt * p.chunks_per_tap + cc) * kBK, nb0);
-          if (++tt == 9) { tt = 0; ++cc; }
+          tt += np;
+          while (tt >= 9) { tt -= 9; ++cc; }
         }
       }
       griddep_wait();
-      trace_mark(trc, 2);
-      int sb = 0, sa = 0, na = 0;
-      uint32_t phb = 0, pha = 0;
-      for (int i = 0; i < nchunks; ++i) {
+      if (prod == 0) trace_mark(trc, 2);
+      if (prod == np - 1 && p.res_smem_off) {
+        // the residual tile of the epilogue: ONE unswizzled box (BN channels x the tile's pixel box, with the halo
+        // tiling's pixel pitch), dense [tile row][BN] in shared memory; always this CTA's own barrier
+        mbar_expect_tx(res_bar, (uint32_t)p.res_tx);
+        tma_load_4d(smem + p.res_smem_off, &tmR, res_bar, n_tile * p.BN, w0, h0, n0);
+      }
+      int c = (k_begin + prod) / 9, t = (k_begin + prod) % 9;
+      int sb = prod % p.stages;
+      uint32_t phb = (uint32_t)((prod / p.stages) & 1);
+      for (int i = prod; i < nchunks; i += np) {
         if (i == 0 || t == 0) {  // first step of a chunk inside this CTA's K range: its halo tile
-          if (na >= p.a_stages) mbar_wait(&empty_a[sa], pha ^ 1u);
+          const int na = c - c_first;           // halo tiles before this one
+          const int sa = na % p.a_stages;
+          if (na >= p.a_stages) mbar_wait(&empty_a[sa], (uint32_t)(((na / p.a_stages) & 1) ^ 1));
           if (leader) mbar_expect_tx(&full_a[sa], a_tx);
           uint8_t* a_dst = tiles + (size_t)sa * p.a_stage_bytes;
           if (c < p.c1_chunks)
             tma4d_to(a_dst, &tmA1, full_addr(&full_a[sa]), pair, c * kBK, w0 - 1, h0 - 1, n0);
           else
             tma4d_to(a_dst, &tmA2, full_addr(&full_a[sa]), pair, (c - p.c1_chunks) * kBK, w0 - 1, h0 - 1, n0);
-          ++na;
-          if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
         }
         if (i >= npre) {
           mbar_wait(&empty_bar[sb], phb ^ 1u);
           if (leader) mbar_expect_tx(&full_bar[sb], b_tx);
           tma2d_to(b_ring + (size_t)sb * b_bytes, &tmB, full_addr(&full_bar[sb]), pair, (t * p.chunks_per_tap + c) * kBK, nb0);
         }
-        if (++sb == p.stages) { sb = 0; phb ^= 1u; }
-        if (++t == 9) { t = 0; ++c; }
+        sb += np;
+        while (sb >= p.stages) { sb -= p.stages; phb ^= 1u; }
+        t += np;
+        while (t >= 9) { t -= 9; ++c; }
       }
     }
   } else if (warp == 1 && p.halo) {
     // ===================== MMA issuer, HALO mode (PAIR mode: the leader CTA only) =====================
-    if (leader) {
+    // ONE thread runs the whole loop: a warp-wide loop with an elected issuer inside pays ~150 cycles per K step for the
+    // election, the reconvergence and the vector -> uniform register moves (tools/exp_issue.cu: 343 vs 192 cycles per
+    // 128x64x64 step), more than the MMAs of a narrow N tile take.
+    if (leader && elect_one()) {
     const uint32_t idesc = umma_idesc_bf16(pair ? 2 * kBM : kBM, (uint32_t)p.BN);
     const uint64_t a_desc0 = umma_desc_k_sw128(smem_u32(tiles));
     const uint64_t b_desc0 = umma_desc_k_sw128(smem_u32(b_ring));
@@ -605,25 +643,38 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     uint64_t a_desc = a_desc0, b_desc = b_desc0;
     int t = k_begin % 9;
     int ky = t / 3, kx = t % 3;
+    long long dbg_wait = 0;
+    uint32_t ready = 0;   // the weight tile of step i was probed (landed) while step i - 1 was being issued
     for (int i = 0; i < nchunks; ++i) {
+      const long long t_w0 = p.dbg ? clock64() : 0;
       if (i == 0 || t == 0) {
         mbar_wait(&full_a[sa], pha);
       }
-      mbar_wait(&full_bar[sb], phb);
+      if (!ready) mbar_wait(&full_bar[sb], phb);
+      if (p.dbg) dbg_wait += clock64() - t_w0;
       tc_fence_after();
       const bool last_of_chunk = (t == 8) || (i == nchunks - 1);
-      if (elect_one()) {
+      int sbn = sb + 1;
+      uint32_t phbn = phb;
+      if (sbn == p.stages) { sbn = 0; phbn ^= 1u; }
+      {
         // tap shift = row offset inside the halo tile: (ky * pitch + kx) rows of 128 bytes = 8 descriptor units each
         const uint64_t a_tap = a_desc + (uint64_t)((ky * p.hpitch + kx) * 8);
+        if (p.probe) {
+          ready = tc_mma_step_probe<PAIR>(tmem_base, a_tap, b_desc, idesc, i > 0 ? 1u : 0u, &empty_bar[sb], pair_mask,
+                                          &full_bar[sbn], phbn);
+          if (i + 1 == nchunks) ready = 0;
+        } else {
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k)
-          mma_any(tmem_base, a_tap + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (i > 0 || k > 0) ? 1u : 0u, pair);
-        commit_to(&empty_bar[sb], pair, pair_mask);
+          for (int k = 0; k < kBK / 16; ++k)
+            mma_any(tmem_base, a_tap + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (i > 0 || k > 0) ? 1u : 0u, pair);
+          commit_to(&empty_bar[sb], pair, pair_mask);
+        }
         if (last_of_chunk) commit_to(&empty_a[sa], pair, pair_mask);
       }
-      __syncwarp();
       b_desc += b_step;
-      if (++sb == p.stages) { sb = 0; phb ^= 1u; b_desc = b_desc0; }
+      sb = sbn; phb = phbn;
+      if (sb == 0) b_desc = b_desc0;
       if (last_of_chunk) {
         a_desc += a_step;
         if (++sa == p.a_stages) { sa = 0; pha ^= 1u; a_desc = a_desc0; }
@@ -631,32 +682,40 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       if (++kx == 3) { kx = 0; ++ky; }
       if (++t == 9) { t = 0; ky = 0; }
     }
-    if (elect_one()) commit_to(tmem_full_bar, pair, pair_mask);
-    __syncwarp();
-    if (lane == 0) SDEO_DBG(3);
+    commit_to(tmem_full_bar, pair, pair_mask);
+    SDEO_DBG(3);
+    if (p.dbg) p.dbg[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + 9] = dbg_wait;
     }
-  } else if (warp == 0) {
-    // ===================== TMA producer =====================
+    __syncwarp();
+  } else if (prod_warp) {
+    // ===================== TMA producers =====================
     // (all ring / tap / chunk indices advance incrementally: no integer division on the per-chunk path)
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t tx_bytes = (uint32_t)(p.rows_valid * 128 + b_bytes) * (uint32_t)tx_mult;
       const int nb0 = n_tile * p.BN + (int)px * bn_cta;
       // the first ring pass needs no empty-slot wait; its weight tiles are requested before the grid dependency
       // resolves, so the weight stream of this layer overlaps the tail of the previous kernel
       const int npre = nchunks < p.stages ? nchunks : p.stages;
-      for (int i = 0; i < npre; ++i) {
+      for (int i = prod; i < npre; i += np) {
         if (leader) mbar_expect_tx(&full_bar[i], tx_bytes);
         tma2d_to(tiles + (size_t)i * stage_bytes + kATileBytes, &tmB, full_addr(&full_bar[i]), pair, (k_begin + i) * kBK, nb0);
       }
       griddep_wait();
-      trace_mark(trc, 2);
-      int s = 0;
-      uint32_t ph = 0;
-      int tap = k_begin / p.chunks_per_tap, within = k_begin % p.chunks_per_tap;
+      if (prod == 0) trace_mark(trc, 2);
+      if (prod == np - 1 && p.res_smem_off) {
+        // the residual tile of the epilogue: ONE unswizzled box (BN channels x the tile's pixel box, with the halo
+        // tiling's pixel pitch), dense [tile row][BN] in shared memory; always this CTA's own barrier
+        mbar_expect_tx(res_bar, (uint32_t)p.res_tx);
+        tma_load_4d(smem + p.res_smem_off, &tmR, res_bar, n_tile * p.BN, w0, h0, n0);
+      }
+      int s = prod % p.stages;
+      uint32_t ph = (uint32_t)((prod / p.stages) & 1);
+      const int g0 = k_begin + prod;
+      int tap = g0 / p.chunks_per_tap, within = g0 % p.chunks_per_tap;
       int ky = tap / p.kw, kx = tap % p.kw;
-      uint8_t* a_dst = tiles;
       long long dbg_wait = 0;
-      for (int i = 0; i < nchunks; ++i) {
+      for (int i = prod; i < nchunks; i += np) {
+        uint8_t* a_dst = tiles + (size_t)s * stage_bytes;
         if (i >= npre) {
           const long long t_w0 = p.dbg ? clock64() : 0;
           mbar_wait(&empty_bar[s], ph ^ 1u);
@@ -671,17 +730,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         else
           tma4d_to(a_dst, &tmA2, fb, pair, (within - p.c1_chunks) * kBK, wc, hc, n0);
         if (i >= npre) tma2d_to(a_dst + kATileBytes, &tmB, fb, pair, (k_begin + i) * kBK, nb0);
-        if (++within == p.chunks_per_tap) {
-          within = 0;
+        within += np;
+        while (within >= p.chunks_per_tap) {
+          within -= p.chunks_per_tap;
           if (++kx == p.kw) { kx = 0; ++ky; }
         }
-        a_dst += stage_bytes;
-        if (++s == p.stages) { s = 0; ph ^= 1u; a_dst = tiles; }
+        s += np;
+        while (s >= p.stages) { s -= p.stages; ph ^= 1u; }
       }
-      if (p.dbg) {
+      if (p.dbg && prod == 0) {
         long long* d = p.dbg + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16;
         d[10] = dbg_wait;
-        d[11] = clock64();   // producer done (all loads issued)
+        d[11] = clock64();   // producer 0 done (all its loads issued)
         d[12] = p.stages;
       }
     }
@@ -689,9 +749,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     // ===================== MMA issuer =====================
     // One thread feeds the tensor pipe: everything between two chunks' MMAs is on the critical path (the pipe idles
     // while this thread probes the barrier), so the loop carries precomputed descriptors and no divisions.
-    // The whole warp runs the loop (warp-uniform control flow and descriptor arithmetic stay in uniform registers);
-    // one elected lane issues the tcgen05 instructions.
-    if (leader) {  // (PAIR mode: the leader CTA issues the M=256 MMAs for both)
+    if (leader && elect_one()) {  // (PAIR mode: the leader CTA issues the M=256 MMAs for both)
       const uint32_t idesc = umma_idesc_bf16(pair ? 2 * kBM : kBM, (uint32_t)p.BN);
       const uint64_t a_desc0 = umma_desc_k_sw128(smem_u32(tiles));
       const uint64_t b_desc0 = umma_desc_k_sw128(smem_u32(tiles) + kATileBytes);
@@ -700,52 +758,67 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       uint32_t ph = 0;
       uint64_t a_desc = a_desc0, b_desc = b_desc0;
       long long dbg_wait = 0;
+      uint32_t ready = 0;   // the full barrier of step i was probed (complete) while step i - 1 was being issued
       for (int i = 0; i < nchunks; ++i) {
-        const long long t_w0 = p.dbg ? clock64() : 0;
-        mbar_wait(&full_bar[s], ph);
-        if (p.dbg) dbg_wait += clock64() - t_w0;
-        tc_fence_after();
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-            mma_any(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                    (i > 0 || k > 0) ? 1u : 0u, pair);
-          }
-          commit_to(&empty_bar[s], pair, pair_mask);  // frees this smem stage (in both CTAs) once the MMAs above have read it
+        if (!ready) {
+          const long long t_w0 = p.dbg ? clock64() : 0;
+          mbar_wait(&full_bar[s], ph);
+          if (p.dbg) dbg_wait += clock64() - t_w0;
         }
-        __syncwarp();
+        tc_fence_after();
+        int sn = s + 1;
+        uint32_t phn = ph;
+        if (sn == p.stages) { sn = 0; phn ^= 1u; }
+        // four MMAs on the 32-byte K slices of the chunk (+2 per slice in the descriptor's (addr >> 4) field), the commit
+        // that frees this stage (in both CTAs of a pair) once they have read it, and the probe of the next stage
+        if (p.probe) {
+          ready = tc_mma_step_probe<PAIR>(tmem_base, a_desc, b_desc, idesc, i > 0 ? 1u : 0u, &empty_bar[s], pair_mask,
+                                          &full_bar[sn], phn);
+          if (i + 1 == nchunks) ready = 0;
+        } else {
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k)
+            mma_any(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (i > 0 || k > 0) ? 1u : 0u, pair);
+          commit_to(&empty_bar[s], pair, pair_mask);
+        }
         a_desc += desc_step;
         b_desc += desc_step;
-        if (++s == p.stages) { s = 0; ph ^= 1u; a_desc = a_desc0; b_desc = b_desc0; }
+        if (sn == 0) { a_desc = a_desc0; b_desc = b_desc0; }
+        s = sn; ph = phn;
       }
-      if (elect_one()) commit_to(tmem_full_bar, pair, pair_mask);  // accumulator complete (all MMAs done => every stage consumed)
-      __syncwarp();
-      if (lane == 0) SDEO_DBG(3);
-      if (lane == 0 && p.dbg) p.dbg[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + 9] = dbg_wait;
+      commit_to(tmem_full_bar, pair, pair_mask);  // accumulator complete (all MMAs done => every stage consumed)
+      SDEO_DBG(3);
+      if (p.dbg) p.dbg[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + 9] = dbg_wait;
     }
+    __syncwarp();
   }
 
-  if (warp >= 6) {
-    // the epilogue's per-column vectors (bias, time-embedding row, folded-LayerNorm column sums) are its only global
-    // loads that are not prefetched otherwise: the idle warps pull their cache lines into L1 during the mainloop
-    const int t = (int)threadIdx.x - 192;
+  // the time-embedding row is the same for every row of the tile (one sample per tile, or table mode): it joins the bias
+  // in the column vector; otherwise the epilogue reads it per row from global memory
+  const bool emb_in_colv = p.emb && (p.emb_step || p.bn_ == 1);
+  if (warp >= 6 && warp < 9) {
+    // the epilogue's per-column vectors (bias + time-embedding row, folded-LayerNorm column sums): global memory ->
+    // shared memory during the mainloop (read from global memory inside the epilogue they cost an L2 round trip per item
+    // batch -- measured: the largest share of epilogue phase 2)
     const int nb = n_tile * p.BN;
-    const int lines = (p.BN * 4 + 127) / 128;
-    if (t < lines && nb + t * 32 < p.cout) {
-      if (p.bias) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + nb + t * 32));
-      if (LNF) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.ln_csum + nb + t * 32));
-      if (p.emb) {
-        const int erow = p.emb_step ? __ldg(p.emb_step) : n0;
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(p.emb + (long long)erow * p.cout + nb + t * 32));
+    const long long erow = emb_in_colv ? (p.emb_step ? __ldg(p.emb_step) : n0) : 0;
+    for (int c = (int)threadIdx.x - 192; c < p.BN; c += kHelperThreads) {
+      const int n = nb + c;
+      float v = 0.f, cs = 0.f;
+      if (n < p.cout) {
+        if (p.bias) v = __ldg(p.bias + n);
+        if (emb_in_colv) v += __ldg(p.emb + erow * p.cout + n);
+        if (LNF) cs = __ldg(p.ln_csum + n);
       }
+      colv[c] = v;
+      if (LNF) csumv[c] = cs;
     }
   }
 
-  if (LNF && warp >= 6) {
+  if (LNF && warp >= 6 && warp < 9) {
     // ===================== folded LayerNorm: (mean, rstd) of every tile row (warps 6..11, during the mainloop) =========
     const int per_img = p.bh * p.bw;
-    for (int row = (int)threadIdx.x - 192; row < kBM; row += kConvThreads - 192) {
+    for (int row = (int)threadIdx.x - 192; row < kBM; row += kHelperThreads) {
       const int nl = row / per_img, rem = row % per_img;
       const int hl = rem / p.bw, wl = rem % p.bw;
       const int nn = n0 + nl, hh = h0 + hl, ww = w0 + wl;
@@ -770,34 +843,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     }
   }
 
-  if (MODE == SDEO_EPI_NORMAL && FAST && RES != RES_NONE && warp >= 6 && p.res_smem_off) {
-    // ===================== residual prefetch (warps 6..11, concurrent with the mainloop) =====================
-    // cp.async 16-byte copies of the residual rows this CTA's epilogue will add, into a dense [row][BN] buffer.
-    constexpr int kElem = (RES == RES_F32) ? 4 : 2;
-    const int S = p.splits;
-    const int rows_per = (p.rows_valid + S - 1) / S;
-    const int r_begin = split * rows_per;
-    const int r_end = min(p.rows_valid, r_begin + rows_per);
-    const int vpr = p.BN * kElem / 16;  // 16-byte vectors per row
-    const int n_base = n_tile * p.BN;
-    const uint32_t res_s = smem_u32(smem + p.res_smem_off);
-    const uint8_t* res_g = reinterpret_cast<const uint8_t*>(p.residual);
-    const int total = (r_end > r_begin ? r_end - r_begin : 0) * vpr;
-    for (int it = (int)threadIdx.x - 192; it < total; it += kConvThreads - 192) {
-      const int row = r_begin + it / vpr, v = it % vpr;
-      int nn, hh, ww;
-      const bool ok = tile_row_coords(p, row, n0, h0, w0, &nn, &hh, &ww);
-      const int col = v * (16 / kElem);
-      if (ok && n_base + col < p.cout) {
-        const long long pix = ((long long)nn * p.Ho + hh) * p.Wo + ww;
-        const uint8_t* src = res_g + ((size_t)pix * p.ldr + n_base + col) * kElem;
-        const uint32_t dst = res_s + (uint32_t)((row * p.BN + col) * kElem);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-      }
-    }
-    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-  }
-
   // ===================== epilogue phase 1: TMEM -> fp32 tile in shared memory, all 12 warps =====================
   // A warp may read the TMEM lane quarter (warp % 4); the three warps of a quarter split the columns in 32-wide
   // chunks; rows land in this CTA's own tile (the drained pipeline stages).
@@ -810,7 +855,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   // at teardown) keeps every CTA's shared memory alive until its outgoing copies have been read.
   __syncwarp();
   const int S = p.splits;
-  const int rows_per = (p.rows_valid + S - 1) / S;
+  const int rows_per = p.rows_per;
   float* recv = tile + (size_t)p.rows_valid * LD;  // S > 1 only: right behind the valid rows of the tile
   mbar_wait(tmem_full_bar, 0);
   tc_fence_after();
@@ -874,17 +919,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     constexpr bool geglu = (MODE == SDEO_EPI_GEGLU);
     const int r_begin = split * rows_per;
     const int r_end = min(p.rows_valid, r_begin + rows_per);
-    const int cols_items = geglu ? p.BN / 16 : p.BN / 8;  // items per row
+    const int cols_items = p.cols_items;  // items per row (BN / 8; GEGLU: BN / 16)
     const int n_base = n_tile * p.BN;
     const uint32_t slice_bytes = (uint32_t)(rows_per * LD) * 4u;  // S > 1: one received slice per K-slice rank
     const int hw_out = p.Ho * p.Wo;
     const int half = p.BN / 2;
-    const int emb_row_fixed = (p.emb && p.emb_step) ? __ldg(p.emb_step) : -1;
+    const bool emb_global = p.emb && !emb_in_colv;   // (several samples per tile without a step table)
+    if (MODE == SDEO_EPI_NORMAL && FAST && RES != RES_NONE && p.res_smem_off) mbar_wait(res_bar, 0);
+    if (threadIdx.x == 64) SDEO_DBG(13);
+    int dbg_iter = 0;
     // STATS: every thread keeps ONE column item (ci) and strides over rows, so that it can accumulate column sums in
     // registers; the (at most cols_items - 1) threads beyond the last full row group stay idle.
-    const int step_rows = kConvThreads / cols_items, step_cols = STATS ? 0 : kConvThreads % cols_items;
-    int row = r_begin + (int)threadIdx.x / cols_items;
-    int ci = (int)threadIdx.x % cols_items;
+    const int step_rows = p.step_rows, step_cols = STATS ? 0 : p.step_cols;
+    const int row_of_tid = (int)(((uint32_t)threadIdx.x * (uint32_t)p.ci_magic) >> 16);   // threadIdx.x / cols_items
+    int row = r_begin + row_of_tid;
+    int ci = (int)threadIdx.x - row_of_tid * cols_items;
     if (STATS && (int)threadIdx.x >= step_rows * cols_items) row = r_end;
     float st_s[STATS == 1 ? 8 : 1], st_q[STATS == 1 ? 8 : 1];
     if (STATS == 1) {
@@ -895,6 +944,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     // the same number of iterations (items beyond the last row are dummies)
     int iters_left = (max(r_end - r_begin, 0) + step_rows * U - 1) / (step_rows * U);
     while (STATS == 2 ? (iters_left-- > 0) : (row < r_end)) {
+      if (threadIdx.x == 64 && dbg_iter++ == 1) SDEO_DBG(14);
       float v[U][8], g[U][8];
       uint4 raw0[U], raw1[U];
       int pixs[U], cols[U], rws[U];
@@ -967,14 +1017,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         for (int u = 0; u < U; ++u) {
           if (pixs[u] < 0) continue;
           const float2 mr = ln_vec[rws[u]];
-          float cs[8];
-          load8_f32(p.ln_csum + n_base + cols[u], cs);
+          const float* cs = csumv + cols[u];
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[u][j] = mr.y * (v[u][j] - mr.x * cs[j]);
           if (geglu) {
-            load8_f32(p.ln_csum + n_base + half + cols[u], cs);
+            const float* cg = csumv + half + cols[u];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) g[u][j] = mr.y * (g[u][j] - mr.x * cs[j]);
+            for (int j = 0; j < 8; ++j) g[u][j] = mr.y * (g[u][j] - mr.x * cg[j]);
           }
         }
       }
@@ -984,7 +1033,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           // every lane takes part in the shuffles; lanes without a valid item contribute zeros
           float rs = 0.f, rq = 0.f;
           if (pixs[u] >= 0) {
-            epi_normal_fast<OUT, RES>(p, (long long)pixs[u], p.emb ? (emb_row_fixed >= 0 ? emb_row_fixed : pixs[u] / hw_out) : 0, n_base + cols[u], v[u], raw0[u], raw1[u]);
+            epi_normal_fast<OUT, RES>(p, (long long)pixs[u], emb_global ? pixs[u] / hw_out : -1, n_base + cols[u], v[u], raw0[u], raw1[u], colv + cols[u]);
 #pragma unroll
             for (int j = 0; j < 8; ++j) { rs += v[u][j]; rq += v[u][j] * v[u][j]; }
           }
@@ -999,23 +1048,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         const int col = cols[u];
         if (MODE == SDEO_EPI_GEGLU) {
           RowInfo ri; ri.valid = true; ri.pix = pixs[u]; ri.batch = 0;
-          epi_geglu_item(p, ri, n_tile * half + col, n_base + col, n_base + half + col, v[u], g[u]);
+          epi_geglu_item(p, ri, n_tile * half + col, colv + col, colv + half + col, v[u], g[u]);
         } else if (MODE == SDEO_EPI_QKV) {
           RowInfo ri; ri.valid = true; ri.pix = pixs[u]; ri.batch = 0;
-          epi_qkv_item(p, ri, n_base + col, v[u]);
+          epi_qkv_item(p, ri, n_base + col, v[u], colv + col);
         } else if (FAST) {
-          epi_normal_fast<OUT, RES>(p, (long long)pixs[u], p.emb ? (emb_row_fixed >= 0 ? emb_row_fixed : pixs[u] / hw_out) : 0, n_base + col, v[u], raw0[u], raw1[u]);
+          epi_normal_fast<OUT, RES>(p, (long long)pixs[u], emb_global ? pixs[u] / hw_out : -1, n_base + col, v[u], raw0[u], raw1[u], colv + col);
           if (STATS == 1) {  // v[u] now holds the values that were stored
 #pragma unroll
             for (int j = 0; j < 8; ++j) { st_s[j] += v[u][j]; st_q[j] += v[u][j] * v[u][j]; }
           }
         } else {
-          RowInfo ri; ri.valid = true; ri.pix = pixs[u]; ri.batch = p.emb ? (emb_row_fixed >= 0 ? emb_row_fixed : pixs[u] / hw_out) : 0;
+          RowInfo ri; ri.valid = true; ri.pix = pixs[u]; ri.batch = p.emb ? (p.emb_step ? __ldg(p.emb_step) : pixs[u] / hw_out) : 0;
           epi_normal_item(p, ri, n_base + col, v[u], false, raw0[u], raw1[u]);
         }
       }
     }
-    if (MODE == SDEO_EPI_QKV) qkv_store_vt(p, tile, LD, row_pix, LNF ? ln_vec : nullptr, n_base, (int)threadIdx.x, kConvThreads);  // S == 1
+    if (MODE == SDEO_EPI_QKV) qkv_store_vt(p, tile, LD, row_pix, LNF ? ln_vec : nullptr, n_base, (int)threadIdx.x, kConvThreads, colv, csumv);  // S == 1
     if (STATS == 1) {
       // column sums of this CTA's rows: registers -> shared memory (one 16-float record per thread) -> one thread per
       // channel adds the row groups in fixed order (deterministic) -> global partial [M tile * S + rank][channel]
@@ -1145,6 +1194,7 @@ struct ConvPlan {
   size_t smem_bytes;
   int halo, hpitch, a_stages, a_stage_bytes, rows_valid;
   int pair;  // CTA pairs (cta_group::2): grid.x = M tiles rounded up to even, cluster (2,1,S)
+  int nprod;
 };
 
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -1315,7 +1365,7 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl, int force_bn = 0, i
   pl->cps = (pl->total_chunks + splits - 1) / splits;
   pl->splits = (pl->total_chunks + pl->cps - 1) / pl->cps;  // every slice gets >= 1 chunk
   // ---- smem / tmem ----
-  const int kSmemMax = 227 * 1024, kFixed = 3072;  // 1 KB alignment slack + 2 KB barriers / row tables
+  const int kSmemMax = 227 * 1024, kFixed = 5120;  // 1 KB alignment slack + 4 KB barriers / row tables / column vectors
   const int b_stage = (pl->pair ? pl->BN / 2 : pl->BN) * 128;   // weight rows one CTA stages per K step
   const int stage_bytes = pl->halo ? b_stage : kATileBytes + b_stage;   // HALO: the B ring's stage
   const int rows_valid = pl->rows_valid;
@@ -1352,17 +1402,25 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl, int force_bn = 0, i
   // residual tile prefetched into shared memory by the otherwise idle warps, if enough pipeline stages still fit
   pl->res_smem_off = 0;
   int res_bytes = 0;
-  if (a->residual && a->epi_mode == SDEO_EPI_NORMAL && !getenv("SDEO_NO_RES_PREFETCH")) {
-    res_bytes = kBM * pl->BN * (a->residual_f32 ? 4 : 2);
-    const int st2 = stages_for(res_bytes);
+  // (only the vector-aligned NORMAL epilogue reads the prefetched tile; the same conditions make the TMA box legal)
+  bool res_fast = a->residual && a->epi_mode == SDEO_EPI_NORMAL && (a->cout % 16 == 0) &&
+                  (a->residual_f32 ? (a->ldr % 4 == 0) : (a->ldr % 8 == 0)) && ((reinterpret_cast<uintptr_t>(a->residual) & 15) == 0);
+  res_fast = res_fast && (a->y_fp32 ? (a->ldy % 4 == 0) : (a->ldy % 8 == 0)) && (!(a->y_fp32 && a->y2) || (a->ldy2 % 8 == 0));
+  if (res_fast && !getenv("SDEO_NO_RES_PREFETCH")) {
+    const int res_rows = pl->halo ? pl->hpitch * pl->bh : kBM;
+    res_bytes = (res_rows > kBM ? res_rows : kBM) * pl->BN * (a->residual_f32 ? 4 : 2);
+    const int st2 = stages_for(res_bytes + 128);
     const int need = pl->cps < 3 ? (pl->cps < 2 ? 2 : pl->cps) : 3;
     if (st2 >= need) stages = st2; else res_bytes = 0;
   }
+  pl->nprod = stages < kProducers ? stages : kProducers;
+  stages -= stages % pl->nprod;
   pl->stages = stages;
   pl->a_stages = a_ring_for(res_bytes);
   size_t body = (size_t)stages * stage_bytes + (size_t)pl->a_stages * pl->a_stage_bytes;
   if (body < (size_t)tile_bytes) body = tile_bytes;
-  if (res_bytes) pl->res_smem_off = 2048 + (int)body;
+  body = (body + 127) & ~(size_t)127;   // (the residual tile behind it is a TMA destination)
+  if (res_bytes) pl->res_smem_off = 4096 + (int)body;
   pl->smem_bytes = kFixed + body + res_bytes;
   int tc = 32;
   while (tc < pl->BN) tc *= 2;  // fp32 accumulator columns (power of two >= 32)
@@ -1672,7 +1730,13 @@ static int launch_conv(const sdeo_conv_args* a, const ConvPlan& pl, void* stream
   p.total_chunks = pl.total_chunks; p.chunks_per_split = pl.cps; p.splits = pl.splits;
   p.bn_ = pl.bn_; p.bh = pl.bh; p.bw = pl.bw; p.rows_valid = pl.rows_valid;
   p.halo = pl.halo; p.hpitch = pl.hpitch; p.a_stages = pl.a_stages; p.a_stage_bytes = pl.a_stage_bytes;
-  p.pair = pl.pair; p.m_tiles = pl.tiles_n * pl.tiles_h * pl.tiles_w;
+  p.pair = pl.pair; p.m_tiles = pl.tiles_n * pl.tiles_h * pl.tiles_w; p.nprod = pl.nprod;
+  p.probe = getenv("SDEO_NO_PROBE") ? 0 : 1;
+  p.rows_per = (pl.rows_valid + pl.splits - 1) / pl.splits;
+  p.cols_items = a->epi_mode == SDEO_EPI_GEGLU ? pl.BN / 16 : pl.BN / 8;
+  p.step_rows = kConvThreads / p.cols_items;
+  p.step_cols = kConvThreads % p.cols_items;
+  p.ci_magic = (65536 + p.cols_items - 1) / p.cols_items;   // exact for threadIdx.x < 384, cols_items <= 32
   p.tiles_h = pl.tiles_h; p.tiles_w = pl.tiles_w;
   p.N = a->n; p.Ho = pl.Ho; p.Wo = pl.Wo;
   p.BN = pl.BN; p.cout = a->cout; p.stages = pl.stages; p.tmem_cols = pl.tmem_cols;
@@ -1687,6 +1751,17 @@ static int launch_conv(const sdeo_conv_args* a, const ConvPlan& pl, void* stream
   p.dbg = nullptr;
   if (const char* e = getenv("SDEO_CONV_DEBUG")) p.dbg = (long long*)strtoull(e, nullptr, 16);
   p.res_smem_off = pl.res_smem_off;
+  p.res_tx = 0;
+  CUtensorMap tmR = tmB;
+  if (pl.res_smem_off) {
+    const int eb = a->residual_f32 ? 4 : 2;
+    uint64_t dims[4] = {(uint64_t)a->cout, (uint64_t)pl.Wo, (uint64_t)pl.Ho, (uint64_t)a->n};
+    uint64_t strides[3] = {(uint64_t)a->ldr * eb, (uint64_t)pl.Wo * a->ldr * eb, (uint64_t)pl.Ho * pl.Wo * a->ldr * eb};
+    uint32_t box[4] = {(uint32_t)pl.BN, (uint32_t)(pl.halo ? pl.hpitch : pl.bw), (uint32_t)pl.bh, (uint32_t)pl.bn_};
+    int rc = encode_tmap_plain(&tmR, a->residual, eb, 4, dims, strides, box);
+    if (rc) return rc;
+    p.res_tx = (int)(box[0] * box[1] * box[2] * box[3]) * eb;
+  }
   p.gn_stats = nullptr;
   p.row_stats = nullptr; p.row_stats_ld = 0;
   p.ln_stats = (const float2*)a->ln_stats; p.ln_parts = a->ln_parts; p.ln_ld = a->ln_ld;
@@ -1696,7 +1771,7 @@ static int launch_conv(const sdeo_conv_args* a, const ConvPlan& pl, void* stream
 
   // ---- pick the kernel instantiation ----
 #define KSEL(...) (pl.pair ? conv_gemm_kernel<__VA_ARGS__, true> : conv_gemm_kernel<__VA_ARGS__, false>)
-  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvKParams);
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvKParams);
   KernelFn fn = nullptr;
   if (a->epi_mode == SDEO_EPI_GEGLU) {
     fn = p.ln_stats ? KSEL(SDEO_EPI_GEGLU, OUT_BF16, RES_NONE, true, 0, true)
@@ -1761,5 +1836,5 @@ static int launch_conv(const sdeo_conv_args* a, const ConvPlan& pl, void* stream
   unsigned gx = (unsigned)(pl.tiles_n * pl.tiles_h * pl.tiles_w);
   if (pl.pair) gx = (gx + 1u) & ~1u;
   return launch_k("conv2d", fn, dim3(gx, (unsigned)pl.n_tiles, (unsigned)pl.splits), dim3(kConvThreads), pl.smem_bytes,
-                  (cudaStream_t)stream, dim3(pl.pair ? 2u : 1u, 1, (unsigned)pl.splits), tmA1, tmA2, tmB, p);
+                  (cudaStream_t)stream, dim3(pl.pair ? 2u : 1u, 1, (unsigned)pl.splits), tmA1, tmA2, tmB, tmR, p);
 }

@@ -77,6 +77,34 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
   return SDEO_OK;
 }
 
+int encode_tmap_plain(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(SDEO_ENOSYS, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(SDEO_EINVAL, "tensor map: base not 16-byte aligned");
+  cuuint64_t d[5], s[4];
+  cuuint32_t b[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    d[i] = dims[i];
+    b[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) {
+    s[i] = strides_bytes[i];
+    if (s[i] % 16 != 0) return set_error(SDEO_EINVAL, "tensor map: stride not a multiple of 16 bytes");
+  }
+  const CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[256];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled (plain) failed: CUresult %d (rank %d, dims %llu %llu, box %u %u)", (int)r,
+             rank, (unsigned long long)d[0], (unsigned long long)(rank > 1 ? d[1] : 0), b[0], rank > 1 ? b[1] : 0);
+    return set_error(SDEO_ECUDA, msg);
+  }
+  return SDEO_OK;
+}
+
 }  // namespace sdeo
 
 extern "C" const char* sdeo_last_error(void) { return sdeo::g_err; }

@@ -17,6 +17,11 @@ int check_launch(const char* what);
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                      const uint32_t* box, const uint32_t* elem_strides);
 
+// The same for an UNSWIZZLED box of a bf16 (elem_bytes 2) or fp32 (elem_bytes 4) tensor: the box lands in shared memory
+// dense, innermost dimension first (the conv epilogue's residual tile).
+int encode_tmap_plain(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box);
+
 // Programmatic dependent launch switch (default on; SDEO_NO_PDL=1 or sdeo_set_pdl(0) turns it off).
 bool pdl_enabled();
 

@@ -24,8 +24,18 @@ CASES = {
     "conv3_96": (8, 96, 96, 320, 320, 3, "stream"),
     "vae128": (4, 512, 512, 128, 128, 3, "plain"),
 }
-names = sys.argv[1:] or list(CASES)
-for name in names:
+names = [a for a in sys.argv[1:] if "=" not in a] or list(CASES)
+# optional plan overrides: combos=00,01,10,11 (PAIR HALO digits) bn=160 splits=1
+opts = dict(a.split("=") for a in sys.argv[1:] if "=" in a)
+combos = opts.get("combos", "").split(",") if opts.get("combos") else [None]
+if "bn" in opts:
+    os.environ["SDEO_FORCE_BN"] = opts["bn"]
+if "splits" in opts:
+    os.environ["SDEO_FORCE_SPLITS"] = opts["splits"]
+for name, combo in [(n_, c_) for n_ in names for c_ in combos]:
+    if combo:
+        os.environ["SDEO_PAIR"], os.environ["SDEO_HALO"] = combo[0], combo[1]
+        print(f"#### {name} PAIR={combo[0]} HALO={combo[1]}")
     n, h, w, cin, cout, k, mode = CASES[name]
     wt = torch.randn((cout, cin, k, k), device=dev) / math.sqrt(cin * k * k)
     x = torch.randn((n, h, w, cin), device=dev).to(BF)
@@ -40,8 +50,12 @@ for name in names:
     elif mode == "plain32":
         kw.update(out_fp32=True)
     dbg = torch.zeros((40000, 16), dtype=torch.int64, device=dev)
-    for _ in range(3):
-        ops.conv2d(x, pw, **kw)
+    try:
+        for _ in range(3):
+            ops.conv2d(x, pw, **kw)
+    except Exception as ex:
+        print(f"   not available: {ex}")
+        continue
     torch.cuda.synchronize()
     os.environ["SDEO_CONV_DEBUG"] = hex(dbg.data_ptr())
     ops.conv2d(x, pw, **kw)
@@ -55,6 +69,8 @@ for name in names:
     for i in range(1, 9):
         col = rel[:, i]
         print(f"   {lab[i]:11s} {col.median().item():9.0f} {col.max().item():9.0f}")
+    if used[:, 13].max() > 0:
+        print(f"   phase 2: residual tile waited for until {rel[:, 13].median().item():.0f}; first item batch done at {rel[:, 14].median().item():.0f}")
     if used[:, 9].max() > 0 or used[:, 10].max() > 0:
         lead = used[used[:, 9] > 0]
         print(f"   MMA warp: cycles waiting for operand data (full barriers) {lead[:, 9].float().median().item():.0f}; "

@@ -22,7 +22,7 @@ issue_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
   uint8_t* tiles = smem + 1024;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 64; ++s) mbar_init(&bars[s], 1);
+    for (int s = 0; s < 64; ++s) mbar_init(&bars[s], s == 30 ? 1000000 : 1);
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -107,6 +107,56 @@ issue_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CU
     }
     __syncthreads();
   }
+  // T7: pipe-bound MMA rate with the A descriptor start shifted by `sh` rows of 128 bytes (the halo tiling's tap offsets)
+  for (int v = 0; v < 4; ++v) {
+    if (warp == 1) {
+      const int sh = v == 0 ? 0 : (v == 1 ? 1 : (v == 2 ? 27 : 54));
+      const uint64_t a0 = umma_desc_k_sw128(smem_u32(tiles) + sh * 128);
+      const uint64_t b0 = umma_desc_k_sw128(smem_u32(tiles) + 32768);
+      uint64_t* done = &bars[56 + v];
+      const long long t0 = clock64();
+      if (elect_one()) {
+        for (int i = 0; i < kRep; ++i) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma_bf16(tmem_base, a0 + 2 * k + (i & 1) * 4096, b0 + 2 * k + (i & 1) * 4096, idesc, (i | k) ? 1u : 0u);
+        }
+      }
+      __syncwarp();
+      if (elect_one()) tc_commit(done);
+      __syncwarp();
+      mbar_wait(done, 0);
+      const long long t2 = clock64();
+      if (lane == 0) o[36 + v] = t2 - t0;
+    }
+    __syncthreads();
+  }
+  // T6: the consumer's K step = [try_wait on a completed phase] [tcgen05.fence::after_thread_sync] 4 MMAs [commit]
+  //   variant 0: MMAs only, 1: + commit, 2: + fence, 3: + fence + try_wait, 4: try_wait + MMAs + commit (no fence)
+  for (int variant = 0; variant < 5; ++variant) {
+    if (warp == 1) {
+      const uint64_t a0 = umma_desc_k_sw128(smem_u32(tiles));
+      const uint64_t b0 = umma_desc_k_sw128(smem_u32(tiles) + 16384);
+      uint64_t* done = &bars[50 + variant];
+      const long long t0 = clock64();
+      for (int i = 0; i < kRep; ++i) {
+        if (variant >= 3) mbar_wait(&bars[0], 0);
+        if (variant == 2 || variant == 3) tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma_bf16(tmem_base, a0 + 2 * k + (i & 1) * 2048, b0 + 2 * k + (i & 1) * 2048, idesc, (i | k) ? 1u : 0u);
+          if (variant >= 1) tc_commit(&bars[30]);
+        }
+        __syncwarp();
+      }
+      const long long t1 = clock64();
+      if (elect_one()) tc_commit(done);
+      __syncwarp();
+      mbar_wait(done, 0);
+      const long long t2 = clock64();
+      if (lane == 0) { o[24 + variant * 2] = t1 - t0; o[25 + variant * 2] = t2 - t0; }
+    }
+    __syncthreads();
+  }
   // T5: commit issue cost (nothing outstanding)
   if (warp == 1) {
     const long long t0 = clock64();
@@ -161,7 +211,7 @@ int main() {
   cudaFuncSetAttribute(issue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   CUtensorMap tmS = make_map2(dA, rows, kcols, 16), tmL = make_map2(dA, rows, kcols, 128), tm3 = make_map3(dA, rows, kcols, 128);
   for (int grid : {1, 148}) {
-    for (int N : {64, 128, 256}) {
+    for (int N : {64, 160, 256}) {
       cudaMemset(dOut, 0, 148 * 64 * 8);
       for (int rep = 0; rep < 2; ++rep) issue_kernel<<<grid, 128, smem>>>(tmS, tmL, tm3, dOut, N);
       cudaError_t e = cudaDeviceSynchronize();
@@ -172,6 +222,11 @@ int main() {
       printf("grid %3d N %3d | per instruction: TMA 2KB issue %.0f (all landed %.0f) | TMA 16KB issue %.0f (landed %.0f) | TMA 3-D 32KB issue %.0f "
              "(landed %.0f) | try_wait(done) %.0f | expect_tx %.0f | commit %.0f | single load latency 2KB %lld 16KB %lld\n",
              grid, N, h[0] / r, h[1] / r, h[2] / r, h[3] / r, h[4] / (r / 2), h[5] / (r / 2), h[6] / r, h[7] / r, h[20] / r, h[8], h[9]);
+      printf("             consumer step (4 MMAs): issue/done cycles per step: MMAs only %.0f/%.0f | +commit %.0f/%.0f | +commit+fence %.0f/%.0f | "
+             "+commit+fence+try_wait %.0f/%.0f | try_wait+commit (no fence) %.0f/%.0f\n", h[24] / r, h[25] / r, h[26] / r, h[27] / r, h[28] / r,
+             h[29] / r, h[30] / r, h[31] / r, h[32] / r, h[33] / r);
+      printf("             pipe-bound MMA, A start shifted by 0 / 1 / 27 / 54 rows: %.0f %.0f %.0f %.0f cycles per MMA\n", h[36] / (4 * r),
+             h[37] / (4 * r), h[38] / (4 * r), h[39] / (4 * r));
       printf("             MMA x%d: one warp issue %.0f /MMA, done %.0f /MMA | two warps: issue %.0f, %.0f done %.0f, %.0f /MMA (per warp)\n",
              4 * kRep, h[10] / (4 * r), h[11] / (4 * r), h[14] / (4 * r), h[16] / (4 * r), h[15] / (4 * r), h[17] / (4 * r));
     }

@@ -62,6 +62,14 @@ for k, a in sorted(summ["kinds"].items(), key=lambda kv: -kv[1]["busy_us"]):
 print("longest kernels (dep->end us):")
 for r in sorted(rec, key=lambda r: -(r.end - r.dep))[:25]:
     print(f"  {r.kind:10s} grid {r.grid:5d} mode {r.mode} splits {r.splits} BN {r.bn:3d}  {r.end - r.dep:7.2f} us  (start {r.start:8.1f})")
+print("by launch signature (kind grid mode splits BN halo): count, sum(dep->end) us, avg us")
+agg = collections.OrderedDict()
+for r in rec:
+    a = agg.setdefault((r.kind, r.grid, r.mode, r.splits, r.bn, r.halo), [0, 0.0])
+    a[0] += 1
+    a[1] += r.end - r.dep
+for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+    print(f"  {k[0]:10s} grid {k[1]:5d} mode {k[2]} splits {k[3]} BN {k[4]:3d} halo {k[5]}  x{a[0]:3d}  {a[1]:8.1f} us  avg {a[1] / a[0]:6.2f}")
 hist = collections.Counter()
 for r in rec:
     if r.kind == "conv":
