@@ -73,9 +73,18 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)
 // CLIP's quick_gelu: x * sigmoid(1.702 x) (transformers activations.py QuickGELUActivation)
 __device__ __forceinline__ float quick_gelu_f(float x) { return x / (1.0f + __expf(-1.702f * x)); }
 
-// exact-erf GELU (F.gelu default in the reference, attention.py:56)
+// erf GELU (F.gelu default in the reference, attention.py:56). erf by Abramowitz & Stegun 7.1.26 (|error| < 1.5e-7, far below
+// the bf16 rounding of the result): one reciprocal, one exponential and a degree-5 polynomial, branch-free -- libdevice's
+// erff costs ~3x the instructions, and the GEGLU epilogue is issue-bound (128 x 128 activations per tile).
 __device__ __forceinline__ float gelu_erf_f(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = 1.0f - poly * t * __expf(-z * z);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -141,6 +150,11 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+// pulls one box of the tensor into L2 (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
+               : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
   asm volatile(

@@ -95,6 +95,7 @@ struct ConvKParams {
   // epilogue's critical path): rows per K-slice rank, (row, 8- or 16-column) items per row, rows / leftover items one
   // pass of the 384 threads covers, and the multiplier that turns threadIdx.x / cols_items into a multiply-shift
   int rows_per, cols_items, step_rows, step_cols, ci_magic;
+  int l2_prefetch;  // producers pull the CTA's whole weight slice into L2 before the grid dependency resolves (SDEO_L2_PREFETCH=1: on)
   int probe;  // MMA issuer probes the next stage's barrier while it issues the current step (SDEO_NO_PROBE=1: off)
 };
 
@@ -446,7 +447,7 @@ __device__ __forceinline__ bool tile_row_coords(const ConvKParams& p, int row, i
 // PAIR: CTA pairs (cta_group::2). A compile-time variant, not a run-time flag: a kernel that contains cta_group::2
 // instructions can only be launched with an even cluster width (measured: "cluster misconfiguration" otherwise).
 template <int MODE, int OUT, int RES, bool FAST, int STATS, bool LNF, bool PAIR>
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kConvThreads, 2)   // 80 registers: two CTAs fit one SM when the plan halves its shared memory (occ2)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmR, const ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -593,6 +594,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           tt += np;
           while (tt >= 9) { tt -= 9; ++cc; }
         }
+        // ... and the rest of this CTA's weight slice into L2: inside a denoising step every layer's weights come from
+        // HBM (2.4 GB per step), and a 4..12-stage ring does not cover DRAM latency; the wait for the previous kernel
+        // (several microseconds under programmatic dependent launch) does
+        if (p.l2_prefetch) {
+          for (int i = npre + prod; i < nchunks; i += np) {
+            const int g = k_begin + i;
+            tma_prefetch_l2_2d(&tmB, ((g % 9) * p.chunks_per_tap + g / 9) * kBK, nb0);
+          }
+        }
       }
       griddep_wait();
       if (prod == 0) trace_mark(trc, 2);
@@ -699,6 +709,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       for (int i = prod; i < npre; i += np) {
         if (leader) mbar_expect_tx(&full_bar[i], tx_bytes);
         tma2d_to(tiles + (size_t)i * stage_bytes + kATileBytes, &tmB, full_addr(&full_bar[i]), pair, (k_begin + i) * kBK, nb0);
+      }
+      // ... and the rest of this CTA's weight slice into L2 (see the HALO producer)
+      if (p.l2_prefetch) {
+        for (int i = npre + prod; i < nchunks; i += np) tma_prefetch_l2_2d(&tmB, (k_begin + i) * kBK, nb0);
       }
       griddep_wait();
       if (prod == 0) trace_mark(trc, 2);
@@ -980,6 +994,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         row += step_rows;
         if (ci >= cols_items) { ci -= cols_items; ++row; }
       }
+      if (threadIdx.x == 64 && dbg_iter == 1) SDEO_DBG(9);
       if (S == 1) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -1012,6 +1027,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           }
         }
       }
+      if (threadIdx.x == 64 && dbg_iter == 1) SDEO_DBG(10);
       if (LNF) {  // folded LayerNorm: acc -> rstd * (acc - mean * csum)
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -1062,7 +1078,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           RowInfo ri; ri.valid = true; ri.pix = pixs[u]; ri.batch = p.emb ? (p.emb_step ? __ldg(p.emb_step) : pixs[u] / hw_out) : 0;
           epi_normal_item(p, ri, n_base + col, v[u], false, raw0[u], raw1[u]);
         }
+        if (threadIdx.x == 64 && dbg_iter == 1 && u == 0) SDEO_DBG(11);
       }
+      if (threadIdx.x == 64 && dbg_iter == 1) SDEO_DBG(12);
     }
     if (MODE == SDEO_EPI_QKV) qkv_store_vt(p, tile, LD, row_pix, LNF ? ln_vec : nullptr, n_base, (int)threadIdx.x, kConvThreads, colv, csumv);  // S == 1
     if (STATS == 1) {
@@ -1195,6 +1213,7 @@ struct ConvPlan {
   int halo, hpitch, a_stages, a_stage_bytes, rows_valid;
   int pair;  // CTA pairs (cta_group::2): grid.x = M tiles rounded up to even, cluster (2,1,S)
   int nprod;
+  int occ2;  // the plan leaves room for two CTAs per SM (<= 112 KB of shared memory): one CTA's epilogue overlaps the other's mainloop
 };
 
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -1225,7 +1244,7 @@ static inline int cta_limit() { return g_cta_budget > 0 && g_cta_budget < 148 ? 
 // force_halo: -1 = heuristic (SDEO_HALO=0/1 overrides), 0 = off, 1 = on (fails if not available).
 // force_pair: -1 = heuristic (SDEO_PAIR=0/1 overrides), 0 = off, 1 = on (fails with fewer than two M tiles).
 static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl, int force_bn = 0, int force_splits = 0, int force_halo = -1,
-                      int force_pair = -1) {
+                      int force_pair = -1, int force_occ2 = -1) {
   if (!(a->ksize == 1 || a->ksize == 3)) return false;
   if (!(a->stride == 1 || a->stride == 2)) return false;
   // symmetric "same" padding, or the VAE encoder's Downsample: 3x3 stride 2 over F.pad(x, (0,1,0,1)) = no leading padding,
@@ -1365,7 +1384,20 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl, int force_bn = 0, i
   pl->cps = (pl->total_chunks + splits - 1) / splits;
   pl->splits = (pl->total_chunks + pl->cps - 1) / pl->cps;  // every slice gets >= 1 chunk
   // ---- smem / tmem ----
-  const int kSmemMax = 227 * 1024, kFixed = 5120;  // 1 KB alignment slack + 4 KB barriers / row tables / column vectors
+  // Two CTAs per SM (occ2): grids of several waves whose tiles pay a long epilogue (TMEM drain + ~30 B/clk of stores) --
+  // a second resident CTA runs its mainloop meanwhile. Needs <= 112 KB per CTA and <= 256 TMEM columns (always true).
+  // force_occ2: -1 = heuristic (SDEO_OCC2=0/1 overrides), 0 / 1.
+  int want_occ2 = force_occ2;
+  if (want_occ2 < 0) {
+    if (const char* e = getenv("SDEO_OCC2")) want_occ2 = atoi(e) ? 1 : 0;
+  }
+  {
+    const long long ctas = (long long)best_tiles * pl->n_tiles * pl->splits;
+    if (want_occ2 < 0) want_occ2 = (ctas >= 2 * 148 && pl->splits == 1) ? 1 : 0;
+    if (pl->splits > 1) want_occ2 = 0;   // (split-K clusters keep one CTA per SM)
+  }
+  pl->occ2 = want_occ2;
+  const int kSmemMax = pl->occ2 ? 112 * 1024 : 227 * 1024, kFixed = 5120;  // 1 KB alignment slack + 4 KB barriers / row tables / column vectors
   const int b_stage = (pl->pair ? pl->BN / 2 : pl->BN) * 128;   // weight rows one CTA stages per K step
   const int stage_bytes = pl->halo ? b_stage : kATileBytes + b_stage;   // HALO: the B ring's stage
   const int rows_valid = pl->rows_valid;
@@ -1398,6 +1430,11 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl, int force_bn = 0, i
     return st;
   };
   int stages = stages_for(0);
+  if (pl->occ2 && (stages < 3 || (pl->halo && a_ring_for(0) < 2))) {
+    // too shallow a ring (or no room for the epilogue tile) at half the shared memory
+    if (force_occ2 == 1) return false;
+    return make_plan(a, pl, force_bn, force_splits, force_halo, force_pair, 0);
+  }
   if (stages < 2) return false;
   // residual tile prefetched into shared memory by the otherwise idle warps, if enough pipeline stages still fit
   pl->res_smem_off = 0;
@@ -1410,7 +1447,7 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl, int force_bn = 0, i
     const int res_rows = pl->halo ? pl->hpitch * pl->bh : kBM;
     res_bytes = (res_rows > kBM ? res_rows : kBM) * pl->BN * (a->residual_f32 ? 4 : 2);
     const int st2 = stages_for(res_bytes + 128);
-    const int need = pl->cps < 3 ? (pl->cps < 2 ? 2 : pl->cps) : 3;
+    const int need = pl->cps < 4 ? (pl->cps < 2 ? 2 : pl->cps) : 4;   // (measured: a 3-stage ring costs more than the residual prefetch saves)
     if (st2 >= need) stages = st2; else res_bytes = 0;
   }
   pl->nprod = stages < kProducers ? stages : kProducers;
@@ -1511,7 +1548,7 @@ static int stats_parts(const sdeo_conv_args* a, const ConvPlan& pl) {
 #include <mutex>
 namespace {
 typedef std::array<int, 16> TuneKey;
-struct Tuned { int first, second, halo, pair; };   // N tile, K slices, HALO mode, CTA pairs
+struct Tuned { int first, second, halo, pair, occ2; };   // N tile, K slices, HALO mode, CTA pairs, two CTAs per SM
 std::map<TuneKey, Tuned> g_tuned;
 std::mutex g_tune_mu;
 int g_autotune = 0;
@@ -1554,9 +1591,11 @@ bool tune_shape(const sdeo_conv_args* a, void* stream, Tuned* best) {
     if (getenv("SDEO_TUNE_WARM") || cudaMalloc(&flush, kFlushBytes) != cudaSuccess) { flush = nullptr; (void)cudaGetLastError(); }
   }
   float best_ms = 1e30f;
-  *best = Tuned{base.BN, base.splits, base.halo, base.pair};
+  *best = Tuned{base.BN, base.splits, base.halo, base.pair, base.occ2};
   const bool no_halo_tune = getenv("SDEO_HALO") != nullptr;   // forced on / off: tune within that mode only
   const bool no_pair_tune = getenv("SDEO_PAIR") != nullptr;
+  const bool no_occ_tune = getenv("SDEO_OCC2") != nullptr;
+  for (int occ2 = 0; occ2 < 2; ++occ2)
   for (int pair = 0; pair < 2; ++pair)
   for (int halo = 0; halo < 2; ++halo)
   for (int bn : bns) {
@@ -1566,9 +1605,11 @@ bool tune_shape(const sdeo_conv_args* a, void* stream, Tuned* best) {
       if (a->epi_mode == SDEO_EPI_QKV && sp > 1) continue;
       ConvPlan pl;
       if ((no_halo_tune && halo != base.halo) || (no_pair_tune && pair != base.pair)) continue;
-      if (!make_plan(a, &pl, bn, sp, no_halo_tune ? -1 : halo, no_pair_tune ? -1 : pair) || pl.BN != bn || pl.splits != sp ||
-          pl.halo != halo || pl.pair != pair)
+      if (no_occ_tune && occ2 != base.occ2) continue;
+      if (!make_plan(a, &pl, bn, sp, no_halo_tune ? -1 : halo, no_pair_tune ? -1 : pair, no_occ_tune ? -1 : occ2) || pl.BN != bn ||
+          pl.splits != sp || pl.halo != halo || pl.pair != pair || pl.occ2 != occ2)
         continue;
+      if (occ2 && (long long)pl.tiles_n * pl.tiles_h * pl.tiles_w * pl.n_tiles <= 148) continue;   // nothing to co-schedule
       int mt = pl.tiles_n * pl.tiles_h * pl.tiles_w;
       if (pl.pair) mt = (mt + 1) & ~1;
       const int ctas = mt * pl.n_tiles * pl.splits;
@@ -1590,7 +1631,7 @@ bool tune_shape(const sdeo_conv_args* a, void* stream, Tuned* best) {
         if (t < ms) ms = t;
       }
       if (!ok) { (void)cudaGetLastError(); continue; }
-      if (ms < best_ms) { best_ms = ms; *best = Tuned{bn, sp, halo, pair}; }
+      if (ms < best_ms) { best_ms = ms; *best = Tuned{bn, sp, halo, pair, occ2}; }
     }
   }
   cudaEventDestroy(e0);
@@ -1612,7 +1653,7 @@ extern "C" int sdeo_conv_autotune(int enable) {
 // Resolves the plan sdeo_conv2d uses for these args: the autotuned (N tile, K slices) if the shape has been tuned
 // (tuning it first when `stream` is given and autotuning is on), the heuristic otherwise.
 static bool resolve_plan(const sdeo_conv_args* a, void* stream, bool may_tune, ConvPlan* pl) {
-  int force_bn = 0, force_s = 0, force_halo = -1, force_pair = -1;
+  int force_bn = 0, force_s = 0, force_halo = -1, force_pair = -1, force_occ2 = -1;
   if (g_autotune && !getenv("SDEO_FORCE_BN") && !getenv("SDEO_FORCE_SPLITS")) {
     std::lock_guard<std::mutex> lock(g_tune_mu);
     const TuneKey key = tune_key(a);
@@ -1625,9 +1666,10 @@ static bool resolve_plan(const sdeo_conv_args* a, void* stream, bool may_tune, C
       force_bn = it->second.first; force_s = it->second.second;
       if (!getenv("SDEO_HALO")) force_halo = it->second.halo;
       if (!getenv("SDEO_PAIR")) force_pair = it->second.pair;
+      if (!getenv("SDEO_OCC2")) force_occ2 = it->second.occ2;
     }
   }
-  return make_plan(a, pl, force_bn, force_s, force_halo, force_pair);
+  return make_plan(a, pl, force_bn, force_s, force_halo, force_pair, force_occ2);
 }
 
 extern "C" int sdeo_conv2d(const sdeo_conv_args* a, void* stream) {
@@ -1675,7 +1717,7 @@ extern "C" int sdeo_conv_plan_describe(const sdeo_conv_args* a, int32_t halo, in
   ConvPlan pl;
   const bool ok = halo < 0 ? resolve_plan(a, nullptr, false, &pl) : make_plan(a, &pl, 0, 0, halo);
   if (!ok) return set_error(SDEO_EINVAL, "conv_plan_describe: unsupported geometry");
-  const int32_t v[16] = {pl.BN, pl.splits, pl.halo | (pl.pair << 1), pl.bn_, pl.bh, pl.bw, pl.tiles_n * pl.tiles_h * pl.tiles_w, pl.n_tiles,
+  const int32_t v[16] = {pl.BN, pl.splits, pl.halo | (pl.pair << 1) | (pl.occ2 << 2), pl.bn_, pl.bh, pl.bw, pl.tiles_n * pl.tiles_h * pl.tiles_w, pl.n_tiles,
                          pl.stages, pl.a_stages, pl.a_stage_bytes, (int32_t)pl.smem_bytes, pl.rows_valid, pl.tmem_cols,
                          pl.hpitch, pl.cps};
   for (int i = 0; i < 16; ++i) out[i] = v[i];
@@ -1732,6 +1774,7 @@ static int launch_conv(const sdeo_conv_args* a, const ConvPlan& pl, void* stream
   p.halo = pl.halo; p.hpitch = pl.hpitch; p.a_stages = pl.a_stages; p.a_stage_bytes = pl.a_stage_bytes;
   p.pair = pl.pair; p.m_tiles = pl.tiles_n * pl.tiles_h * pl.tiles_w; p.nprod = pl.nprod;
   p.probe = getenv("SDEO_NO_PROBE") ? 0 : 1;
+  p.l2_prefetch = getenv("SDEO_L2_PREFETCH") ? 1 : 0;   // (measured neutral inside the step graph: opt-in)
   p.rows_per = (pl.rows_valid + pl.splits - 1) / pl.splits;
   p.cols_items = a->epi_mode == SDEO_EPI_GEGLU ? pl.BN / 16 : pl.BN / 8;
   p.step_rows = kConvThreads / p.cols_items;
@@ -1830,6 +1873,8 @@ static int launch_conv(const sdeo_conv_args* a, const ConvPlan& pl, void* stream
     if (!seen) {
       cudaError_t e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess) return set_error(SDEO_ECUDA, cudaGetErrorString(e));
+      // (occ2 plans: two 112 KB CTAs per SM need the whole shared-memory carve-out)
+      (void)cudaFuncSetAttribute((const void*)fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       if (n_configured < 96) configured[n_configured++] = fn;
     }
   }

@@ -72,7 +72,7 @@ def plan_of(a_kwargs):
     out = (ctypes.c_int32 * 16)()
     if _lib.load().sdeo_conv_plan_describe(ctypes.byref(a), -1, out, 16) != 0:
         return "?"
-    return f"BN {out[0]:3d} S {out[1]} halo {out[2]} box {out[4]}x{out[5]} tiles {out[6]}x{out[7]}"
+    return f"BN {out[0]:3d} S {out[1]} halo {out[2] & 1} pair {(out[2] >> 1) & 1} occ2 {(out[2] >> 2) & 1} box {out[4]}x{out[5]} tiles {out[6]}x{out[7]} stages {out[8]}"
 
 
 tot = 0.0

@@ -69,6 +69,9 @@ for name, combo in [(n_, c_) for n_ in names for c_ in combos]:
     for i in range(1, 9):
         col = rel[:, i]
         print(f"   {lab[i]:11s} {col.median().item():9.0f} {col.max().item():9.0f}")
+    if used[:, 13].max() > 0 and os.environ.get("SDEO_PHASE2_DETAIL"):
+        print("   phase 2 detail (thread 64, first item batch): after residual wait %.0f | gather done %.0f | tile loads issued %.0f | item 0 "
+              "stored %.0f | batch done %.0f" % tuple(rel[:, k].median().item() for k in (13, 9, 10, 11, 12)))
     if used[:, 13].max() > 0:
         print(f"   phase 2: residual tile waited for until {rel[:, 13].median().item():.0f}; first item batch done at {rel[:, 14].median().item():.0f}")
     if used[:, 9].max() > 0 or used[:, 10].max() > 0:
