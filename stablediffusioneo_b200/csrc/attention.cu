@@ -21,12 +21,18 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float y;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
+  return y;
+}
+
 struct AttParams {
   int nq, nkv, d, heads;
   int causal;     // 1: query i attends keys 0..i only (CLIP text encoder)
   int nkc;        // ceil(d / 64): 64-wide K chunks of the QK^T contraction
   int dk16;       // round_up(d, 16): contraction length actually multiplied
-  int dv16;       // round_up(d, 16): N of the PV MMA
+  int dv16;       // round_up(d + 1, 16): N of the PV MMA -- V^T row d is all ones, so O[:, d] accumulates the row sums of P
   int kv_stages;  // 1 or 2
   int tmem_cols;
   float scale_log2;
@@ -55,7 +61,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* s_full = bars + 5;
   uint64_t* p_full = bars + 6;
   uint64_t* o_done = bars + 7;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* s_read = bars + 9;        // the softmax warps hold S(j) in registers: the MMA warp may overwrite the S columns
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);   // (bars + 9: s_read)
   float* s_xchg = reinterpret_cast<float*>(bars + 16);  // [2][128] partner exchange (row max / row sum)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -76,6 +83,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     mbar_init(s_full, 1);
     mbar_init(p_full, 1);
     mbar_init(o_done, 1);
+    mbar_init(s_read, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -139,9 +147,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         // the softmax warps have read S(j) into registers and written P(j) once p_full(j) completes: S(j+1) may
         // overwrite the S columns now and runs on the tensor pipe ahead of PV(j), so that the next tile's row
         // maxima overlap this tile's PV (needs the second K/V stage; with one stage K_{j+1} waits for PV(j))
+        // S(j+1) is issued as soon as the softmax warps have S(j) in REGISTERS (s_read), not when P(j) is written: the
+        // QK^T of the next tile then runs under this tile's exponentials instead of between two softmax passes
+        if (j + 1 < n_kv_tiles && p.kv_stages > 1) {
+          mbar_wait(s_read, (uint32_t)j & 1u);
+          tc_fence_after();
+          issue_s(j + 1);
+        }
         mbar_wait(p_full, (uint32_t)j & 1u);
         tc_fence_after();
-        if (j + 1 < n_kv_tiles && p.kv_stages > 1) issue_s(j + 1);
         // ---- O += P V : M=128, N=dv16, K=kv16 ----
         for (int kk = 0; kk < kv16 / 16; ++kk) {
           const int c = kk >> 2, ki = kk & 3;
@@ -164,7 +178,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const int st = threadIdx.x - 64;  // 0..255
     float m_run = -INFINITY;  // running max of s * scale_log2 (identical in both partners)
-    float l_run = 0.f;        // running sum over this thread's columns
     uint8_t* p_row = sP + half * (kTileQ * 128) + row * 128;  // this thread's 64 columns = one 128-byte chunk row
     const int n_oc = p.dv16 / 16;                 // 16-column chunks of O
     const int oc_begin = half == 0 ? 0 : (n_oc + 1) / 2, oc_end = half == 0 ? (n_oc + 1) / 2 : n_oc;
@@ -181,13 +194,29 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (ncols > 32) tmem_ld32(tmem_S + lane_off + (uint32_t)(half * 64 + 32), r1);
       tmem_ld_wait();
       float m_loc = -INFINITY;
+      const bool full_tile = __all_sync(0xffffffffu, ncols == 64);  // (all but the last tile; never under the causal mask's edge)
+      if (full_tile) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        if (i < ncols) m_loc = fmaxf(m_loc, __uint_as_float(r0[i]));
-        if (32 + i < ncols) m_loc = fmaxf(m_loc, __uint_as_float(r1[i]));
+        for (int i = 0; i < 32; i += 2) m_loc = fmax3(m_loc, __uint_as_float(r0[i]), __uint_as_float(r0[i + 1]));
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) m_loc = fmax3(m_loc, __uint_as_float(r1[i]), __uint_as_float(r1[i + 1]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i < ncols) m_loc = fmaxf(m_loc, __uint_as_float(r0[i]));
+          if (32 + i < ncols) m_loc = fmaxf(m_loc, __uint_as_float(r1[i]));
+        }
+      }
+      // V^T row d of this tile := 1.0 (both 64-key chunks): the PV MMA then accumulates sum_k P[q, k] in O[:, d]. (V(j) has
+      // landed: S(j) needed the same barrier; PV(j) starts only after p_full(j), which follows the fence + barrier below.)
+      if (st < 16) {
+        uint8_t* vrow = sKV + (size_t)(j % p.kv_stages) * kv_stage_bytes + k_bytes + (st >> 3) * v_chunk_bytes + p.d * 128 + (st & 7) * 16;
+        *reinterpret_cast<uint4*>(vrow) = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
       }
       s_xchg[half * kTileQ + row] = m_loc;
+      tc_fence_before();   // (this thread's TMEM loads of S(j) are complete: ordered before the MMA warp's next write)
       bar_sync(2, 256);
+      if (st == 0) mbar_arrive(s_read);
       const float m_tile = fmaxf(m_loc, s_xchg[(half ^ 1) * kTileQ + row]);
       const float m_new = fmaxf(m_run, m_tile * p.scale_log2);
       const float alpha = fast_exp2(m_run - m_new);  // 0 on the first tile (m_run = -inf)
@@ -196,8 +225,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_wait(o_done, (uint32_t)(j - 1) & 1u);
         tc_fence_after();
       }
-      float l_tile = 0.f;
-      if (half * 64 < ((kv_cols + 15) & ~15)) {  // the PV contraction reads this chunk
+      if (full_tile) {  // no column masks
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          float pv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int cidx = u * 8 + i;
+            const float sv = __uint_as_float(cidx < 32 ? r0[cidx & 31] : r1[cidx & 31]);
+            pv[i] = fast_exp2(fmaf(sv, p.scale_log2, -m_new));
+          }
+          uint4 v;
+          v.x = pack_bf16x2(pv[0], pv[1]); v.y = pack_bf16x2(pv[2], pv[3]);
+          v.z = pack_bf16x2(pv[4], pv[5]); v.w = pack_bf16x2(pv[6], pv[7]);
+          *reinterpret_cast<uint4*>(p_row + ((u ^ (row & 7)) << 4)) = v;
+        }
+      } else if (half * 64 < ((kv_cols + 15) & ~15)) {  // the PV contraction reads this chunk
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           float pv[8];
@@ -207,7 +250,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             const float sv = __uint_as_float(cidx < 32 ? r0[cidx & 31] : r1[cidx & 31]);
             const float e = fast_exp2(sv * p.scale_log2 - m_new);
             pv[i] = (cidx < ncols) ? e : 0.f;
-            l_tile += pv[i];
           }
           uint4 v;
           v.x = pack_bf16x2(pv[0], pv[1]); v.y = pack_bf16x2(pv[2], pv[3]);
@@ -215,7 +257,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           *reinterpret_cast<uint4*>(p_row + ((u ^ (row & 7)) << 4)) = v;
         }
       }
-      l_run = l_run * alpha + l_tile;
       m_run = m_new;
       // rescale this thread's share of the O columns (skipped when no row of the warp moved its max)
       if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
@@ -235,11 +276,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (st == 0) mbar_arrive(p_full);
     }
     // ---- epilogue: O / l -> bf16 [B, nq, heads*d] ----
-    s_xchg[half * kTileQ + row] = l_run;
-    bar_sync(2, 256);
-    const float inv_l = 1.0f / (l_run + s_xchg[(half ^ 1) * kTileQ + row]);
     mbar_wait(o_done, (uint32_t)(n_kv_tiles - 1) & 1u);
     tc_fence_after();
+    float inv_l;
+    {  // the row sum sits in O column d
+      uint32_t r[16];
+      tmem_ld16(tmem_O + lane_off + (uint32_t)((p.d >> 4) * 16), r);
+      tmem_ld_wait();
+      float l = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i == (p.d & 15)) l = __uint_as_float(r[i]);
+      inv_l = 1.0f / l;
+    }
     const int qi = q_tile * kTileQ + row;
     const int b = bh / p.heads, head = bh % p.heads;
     __nv_bfloat16* orow = p.o + ((size_t)b * p.nq + qi) * ((size_t)p.heads * p.d) + (size_t)head * p.d;
@@ -303,7 +352,7 @@ static int attention_impl(const void* q, const void* k, const void* vt, void* o,
   p.causal = causal;
   p.nkc = (d + 63) / 64;
   p.dk16 = (d + 15) & ~15;
-  p.dv16 = p.dk16;
+  p.dv16 = (d + 1 + 15) & ~15;   // one spare V^T row (index d) for the row sums
   p.scale_log2 = scale * 1.4426950408889634f;
   p.o = (__nv_bfloat16*)o;
   const int q_bytes = p.nkc * kTileQ * 128;

@@ -18,19 +18,21 @@ from stablediffusioneo_b200.cldm.ddim_hacked import DDIMSampler  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--latent", type=int, nargs=2, default=[32, 48])
 ap.add_argument("--csv", default="")
+ap.add_argument("--batch", type=int, default=1)
 args = ap.parse_args()
 h, w = args.latent
 dev = torch.device("cuda:0")
 with torch.device(dev):
     model = ControlLDM().eval()
 synth.randomize_(model)
-x_T = torch.randn((1, 4, h, w), device=dev)
-ctx = lambda s: torch.randn((1, 77, 768), generator=torch.Generator().manual_seed(s)).to(dev)
-hint = (torch.rand((1, 1, 8 * h, 8 * w)) > 0.9).float().expand(-1, 3, -1, -1).contiguous().to(dev)
+B = args.batch
+x_T = torch.randn((B, 4, h, w), device=dev)
+ctx = lambda s: torch.randn((B, 77, 768), generator=torch.Generator().manual_seed(s)).to(dev)
+hint = (torch.rand((B, 1, 8 * h, 8 * w)) > 0.9).float().expand(-1, 3, -1, -1).contiguous().to(dev)
 cond = {"c_concat": [hint], "c_crossattn": [ctx(1)]}
 uncond = {"c_concat": [hint], "c_crossattn": [ctx(2)]}
 sampler = DDIMSampler(model)
-sampler.sample(4, 1, (4, h, w), cond, verbose=False, eta=0.0, x_T=x_T, unconditional_guidance_scale=9.0,
+sampler.sample(4, B, (4, h, w), cond, verbose=False, eta=0.0, x_T=x_T, unconditional_guidance_scale=9.0,
                unconditional_conditioning=uncond)
 torch.cuda.synchronize()
 eng = sampler._engine
