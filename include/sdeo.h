@@ -132,7 +132,9 @@ int sdeo_conv_gn_stats_slots(const sdeo_conv_args* a, int32_t* max_slots_total, 
 int sdeo_conv_row_stats_parts(const sdeo_conv_args* a, int32_t* max_parts, int32_t* parts);
 /* The launch plan for these args (host logic only, no device work): halo < 0 = the plan sdeo_conv2d currently uses (tuned
  * if the shape has been tuned), 0 / 1 = the heuristic plan of the tap-by-tap / HALO tiling. out[16] = {N tile, K slices,
- * halo | pair << 1 (pair: two CTAs run one M=256 cta_group::2 MMA, each staging half of the weight tile), tile samples, tile rows (bh), tile columns (bw), M tiles, N tiles, B (or A+B) pipeline stages, halo A stages, halo
+ * halo | pair << 1 | occ2 << 2 | producers << 4 (pair: two CTAs run one M=256 cta_group::2 MMA, each staging half of the
+ * weight tile; occ2: the plan uses at most 112 KB of shared memory so that two CTAs share an SM; producers: TMA producer
+ * threads, a divisor of the ring depth), tile samples, tile rows (bh), tile columns (bw), M tiles, N tiles, B (or A+B) pipeline stages, halo A stages, halo
  * A stage bytes, dynamic shared memory bytes, MMA rows in use, TMEM columns, halo pixel pitch, K steps per slice}.
  * HALO tiling (3x3, stride 1): one (bh+2) x (bw+2) input box per 64-channel chunk serves all nine filter taps. */
 int sdeo_conv_plan_describe(const sdeo_conv_args* a, int32_t halo, int32_t* out, int32_t n_out);

@@ -28,8 +28,9 @@ constexpr int kConvThreads = 384;  // warp 0 TMA, warp 1 MMA, warps 2..5 TMEM dr
 // TMA producers: lane 0 of warps 0, 9, 10, 11. One thread pays ~200 cycles per mbarrier.try_wait (even on a completed phase)
 // plus ~45 + 3 cycles/KB per cp.async.bulk.tensor it issues (tools/exp_issue.cu) -- 450..600 cycles per K step, more than the
 // MMAs of the step take (2 N cycles for a 128 x N x 64 step). K step i belongs to producer i % nprod, so the waits and
-// issues of consecutive steps overlap. The ring depth is a multiple of nprod: a ring slot is then always refilled by the
-// same thread, whose program order keeps it at most one barrier phase ahead (a parity wait cannot tell phases two apart).
+// issues of consecutive steps overlap. nprod <= ring depth (a parity wait cannot tell barrier phases two apart: with the
+// in-order consumer that bound keeps every producer less than two phases ahead of any slot -- tests/test_host_cpu.py
+// models it), and the depth is a multiple of nprod, so a ring slot is always refilled by the same thread.
 constexpr int kProducers = 4;
 constexpr int kHelperThreads = 96;  // warps 6..8: column vectors, folded-LayerNorm row statistics, residual prefetch
 constexpr int kBM = 128;
@@ -1732,7 +1733,7 @@ extern "C" int sdeo_conv_plan_describe(const sdeo_conv_args* a, int32_t halo, in
   ConvPlan pl;
   const bool ok = halo < 0 ? resolve_plan(a, nullptr, false, &pl) : make_plan(a, &pl, 0, 0, halo);
   if (!ok) return set_error(SDEO_EINVAL, "conv_plan_describe: unsupported geometry");
-  const int32_t v[16] = {pl.BN, pl.splits, pl.halo | (pl.pair << 1) | (pl.occ2 << 2), pl.bn_, pl.bh, pl.bw, pl.tiles_n * pl.tiles_h * pl.tiles_w, pl.n_tiles,
+  const int32_t v[16] = {pl.BN, pl.splits, pl.halo | (pl.pair << 1) | (pl.occ2 << 2) | (pl.nprod << 4), pl.bn_, pl.bh, pl.bw, pl.tiles_n * pl.tiles_h * pl.tiles_w, pl.n_tiles,
                          pl.stages, pl.a_stages, pl.a_stage_bytes, (int32_t)pl.smem_bytes, pl.rows_valid, pl.tmem_cols,
                          pl.hpitch, pl.cps};
   for (int i = 0; i < 16; ++i) out[i] = v[i];

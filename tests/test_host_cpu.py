@@ -425,3 +425,122 @@ def test_groupnorm_f16_protocol_model(shape):
     for ng in (1, 2):
         for bufs in (2, 4):
             assert _gn_stream_protocol_model(lib, *shape, ng=ng, bufs=bufs), (shape, ng, bufs)
+
+
+# ---- conv launch plans (host logic of csrc/gemm_conv.cu, no device work) ----------------------------------------
+_PLAN_SHAPES = [
+    # (n, h, w, c1, c2, cout, ksize, stride, epi_mode, stream)
+    (2, 32, 48, 320, 0, 320, 3, 1, 0, 1), (2, 32, 48, 320, 0, 320, 1, 1, 0, 1), (2, 32, 48, 640, 320, 320, 3, 1, 0, 0),
+    (2, 16, 24, 640, 0, 640, 3, 1, 0, 1), (2, 8, 12, 1280, 0, 1280, 3, 1, 0, 1), (2, 4, 6, 1280, 0, 1280, 3, 1, 0, 1),
+    (2, 32, 48, 320, 0, 320, 3, 2, 0, 1), (1, 1, 3072, 320, 0, 2560, 1, 1, 1, 0), (1, 1, 192, 5120, 0, 1280, 1, 1, 0, 1),
+    (8, 96, 96, 320, 0, 320, 3, 1, 0, 1), (8, 48, 48, 640, 0, 640, 3, 1, 0, 1), (4, 512, 512, 128, 0, 128, 3, 1, 0, 0),
+    (4, 128, 128, 512, 0, 512, 3, 1, 0, 0), (1, 1, 73728, 320, 0, 2560, 1, 1, 1, 0), (16, 512, 512, 128, 0, 3, 3, 1, 0, 0),
+]
+
+
+def _describe(lib, _lib, shape, halo):
+    n, h, w, c1, c2, cout, k, stride, epi, stream = shape
+    a = _lib.ConvArgs()
+    P = ctypes.c_void_p(256)
+    a.x1, a.w_packed, a.y = P, P, P
+    a.n, a.h, a.w, a.c1, a.ld1, a.c2, a.ld2 = n, h, w, c1, c1, c2, c2
+    if c2:
+        a.x2 = P
+    a.cout, a.ksize, a.stride, a.pad, a.scale = cout, k, stride, k // 2, 1.0
+    a.ldy = (cout // 2 if epi == 1 else cout + (-cout) % 8)
+    a.epi_mode = epi
+    if stream:
+        a.residual, a.ldr, a.residual_f32, a.y_fp32, a.y2, a.ldy2 = P, cout, 1, 1, P, cout
+    out = (ctypes.c_int32 * 16)()
+    rc = lib.sdeo_conv_plan_describe(ctypes.byref(a), halo, out, 16)
+    return rc, list(out)
+
+
+@pytest.mark.parametrize("env", [{}, {"SDEO_PAIR": "0"}, {"SDEO_PAIR": "1"}, {"SDEO_OCC2": "1"}, {"SDEO_OCC2": "0", "SDEO_PAIR": "0"}])
+def test_conv_plan_invariants(env, monkeypatch):
+    """Every plan the host logic hands to conv_gemm_kernel keeps the kernel's structural assumptions: ring depth a multiple
+    of the producer count (a ring slot is always refilled by the same thread), shared memory within the per-SM budget
+    (half of it for two-CTA-per-SM plans), accumulator columns >= N tile, an even M-tile grid for CTA pairs."""
+    from stablediffusioneo_b200 import _lib
+    lib = _lib.load()
+    for k_, v_ in env.items():
+        monkeypatch.setenv(k_, v_)
+    seen = 0
+    for shape in _PLAN_SHAPES:
+        for halo in (0, 1):
+            rc, o = _describe(lib, _lib, shape, halo)
+            if rc != 0:
+                continue  # this tiling is not available for the shape (1x1, stride 2, forced pair with one M tile, ...)
+            seen += 1
+            bn, splits, flags, bn_, bh, bw, m_tiles, n_tiles, stages, a_stages, a_stage_bytes, smem, rows, tmem, pitch, cps = o
+            is_halo, pair, occ2, nprod = flags & 1, (flags >> 1) & 1, (flags >> 2) & 1, flags >> 4
+            assert 1 <= nprod <= 4 and stages >= 2 and stages % nprod == 0, (shape, o)
+            assert smem <= (112 if occ2 else 227) * 1024, (shape, o)
+            assert tmem >= bn and tmem in (32, 64, 128, 256), (shape, o)
+            assert 16 <= bn <= 256 and bn % 16 == 0 and rows <= 128 and 1 <= splits <= 8, (shape, o)
+            assert is_halo == halo
+            if is_halo:
+                assert a_stages >= 2 and pitch == bw + 2 and a_stage_bytes % 1024 == 0 and a_stage_bytes >= (bh + 2) * pitch * 128
+            if occ2:
+                assert splits == 1
+            if pair:
+                assert splits <= 4
+    assert seen >= 15
+
+
+def _simulate_ring(stages, nprod, steps, rng):
+    """Discrete model of the conv mainloop's ring: `nprod` producers (K step i belongs to producer i % nprod) and one
+    consumer, synchronised by per-slot full / empty mbarriers that waiters test by PHASE PARITY (a waiter cannot tell a
+    phase from the one two later). Returns None, or a description of the first hazard (a slot refilled before its previous
+    contents were consumed, or consumed before it was filled). Random interleaving of the actors."""
+    full_done = [0] * stages    # completed phases of full[s]
+    empty_done = [0] * stages   # completed phases of empty[s]
+    written = [0] * stages      # fills of slot s so far
+    consumed = [0] * stages
+    prod_next = [p for p in range(nprod)]   # next K step of producer p
+    cons_next = 0
+    while cons_next < steps:
+        actors = []
+        for p in range(nprod):
+            i = prod_next[p]
+            if i >= steps:
+                continue
+            s, rnd = i % stages, i // stages
+            # wait(empty[s], parity (rnd & 1) ^ 1) when rnd > 0: passes while the barrier's phase parity differs
+            if rnd == 0 or (empty_done[s] & 1) != ((rnd & 1) ^ 1):
+                actors.append(("p", p))
+        s, rnd = cons_next % stages, cons_next // stages
+        if (full_done[s] & 1) != (rnd & 1):
+            actors.append(("c", 0))
+        if not actors:
+            return f"deadlock at consumer step {cons_next}"
+        kind, p = actors[rng.integers(len(actors))]
+        if kind == "p":
+            i = prod_next[p]
+            s, rnd = i % stages, i // stages
+            if consumed[s] != rnd:
+                return f"producer {p} refills slot {s} for step {i} before step {i - stages} was consumed"
+            written[s] += 1
+            full_done[s] += 1
+            prod_next[p] += nprod
+        else:
+            if written[s] != rnd + 1:
+                return f"consumer reads slot {s} for step {cons_next} before it was filled"
+            consumed[s] += 1
+            empty_done[s] += 1
+            cons_next += 1
+    return None
+
+
+def test_conv_ring_protocol_model():
+    """No interleaving produces a hazard as long as the ring is at least as deep as the producer count (the in-order
+    consumer then bounds how far a producer can run ahead to less than two phases of any slot) -- make_plan keeps
+    nprod <= stages, and the depth a multiple of nprod so that a slot is always refilled by the same thread. With more
+    producers than slots a producer two phases ahead passes its parity wait and overwrites live data."""
+    rng = np.random.default_rng(7)
+    for stages, nprod in ((2, 2), (3, 3), (4, 4), (8, 4), (12, 4), (4, 2), (6, 3), (4, 1), (5, 1), (5, 4), (7, 4), (5, 3)):
+        for _ in range(200):
+            assert _simulate_ring(stages, nprod, 61, rng) is None, (stages, nprod)
+    for stages, nprod in ((2, 4), (3, 4), (2, 3)):
+        bad = [_simulate_ring(stages, nprod, 61, rng) for _ in range(200)]
+        assert any(b is not None for b in bad), (stages, nprod)

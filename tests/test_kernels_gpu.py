@@ -245,6 +245,46 @@ def test_linear_cta_pairs(cuda_device, rows, kdim, ndim, pair):
         os.environ.pop("SDEO_PAIR", None)
 
 
+@pytest.mark.parametrize("case", [(2, 128, 128, 64, 64, 3), (2, 320, 320, 48, 96, 3), (4, 256, 128, 40, 40, 1), (1, 640, 640, 96, 96, 3)])
+def test_conv2d_plan_switches(cuda_device, case):
+    """The plan / pipeline switches of conv_gemm_kernel on multi-wave grids: two CTAs per SM (SDEO_OCC2: <= 112 KB of shared
+    memory, the 80-register entry point), the MMA issuer's barrier probe (SDEO_NO_PROBE), the L2 weight prefetch
+    (SDEO_L2_PREFETCH) and the residual TMA prefetch (SDEO_NO_RES_PREFETCH): every combination against F.conv2d on the
+    bf16-rounded operands, plain bf16 output and the fp32 + twin + residual + GroupNorm-statistics epilogue."""
+    import os
+    from stablediffusioneo_b200 import ops
+    n, cin, cout, h, w, k = case
+    dev = cuda_device
+    x = gen((n, cin, h, w), 1, dev)
+    wt = gen((cout, cin, k, k), 2, dev, scale=1.0 / math.sqrt(cin * k * k))
+    b = gen((cout,), 3, dev)
+    res = gen((n, h, w, cout), 5, dev)
+    pw = ops.pack_conv_weight(wt)
+    ref = ref_conv(x, wt, b, 1)
+    ref32 = ref + res.permute(0, 3, 1, 2)
+    keys = ("SDEO_OCC2", "SDEO_NO_PROBE", "SDEO_L2_PREFETCH", "SDEO_NO_RES_PREFETCH")
+    base = None
+    try:
+        for occ2 in ("0", "1"):
+            for extra in ({}, {"SDEO_NO_PROBE": "1"}, {"SDEO_L2_PREFETCH": "1"}, {"SDEO_NO_RES_PREFETCH": "1"}):
+                for k_ in keys:
+                    os.environ.pop(k_, None)
+                os.environ["SDEO_OCC2"] = occ2
+                os.environ.update(extra)
+                y = ops.conv2d(nhwc(x), pw, bias=b)
+                ys, yt = ops.conv2d(nhwc(x), pw, bias=b, residual=res, out_fp32=True, twin=True, gn_stats=True)
+                torch.cuda.synchronize()
+                assert rel_l2(y.permute(0, 3, 1, 2), ref) < TOL, (occ2, extra)
+                assert rel_l2(ys.permute(0, 3, 1, 2), ref32) < 2e-3, (occ2, extra)
+                assert torch.equal(yt, ys.to(torch.bfloat16))
+                if base is None:
+                    base = ys
+                assert rel_l2(ys, base) < 1e-5, (occ2, extra)
+    finally:
+        for k_ in keys:
+            os.environ.pop(k_, None)
+
+
 @pytest.mark.parametrize("rows,c", [(3072, 320), (768, 640), (192, 1280), (48, 1280)])
 def test_linear_geglu(cuda_device, rows, c):
     """GEGLU (attention.py:49-56): proj -> chunk(2) -> x * gelu(gate), fused into the projection epilogue."""
