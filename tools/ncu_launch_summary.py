@@ -10,6 +10,7 @@ per = collections.defaultdict(lambda: collections.defaultdict(float))
 cnt = collections.Counter()
 for d in csv.DictReader(lines):
     name = re.sub(r"[<(].*", "", d["Kernel Name"]).replace("void ", "").replace("sdeo::", "")
+    name = name.replace("conv_gemm_kernel_occ2", "conv_gemm_kernel")   # (the 80-register entry point of the same kernel body)
     v = float(d["Metric Value"].replace(",", ""))
     unit, m = d["Metric Unit"], d["Metric Name"]
     if m == "gpu__time_duration.sum":
