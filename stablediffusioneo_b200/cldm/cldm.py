@@ -398,9 +398,40 @@ class ControlLDM(nn.Module):
         zi = to_internal(z, scale=1.0 / self.scale_factor)
         return to_external(fs.decoder.run(fs.post_quant_conv.run(zi)), fs.decoder.out_ch)
 
-    def decode_first_stage_u8(self, z):
-        """decode + 'b c h w -> b h w c' * 127.5 + 127.5, clip, uint8 (canny2image_torch.py:68) on the device."""
+    def _decode_u8_eager(self, z):
         fs = self.first_stage_model
         zi = to_internal(z, scale=1.0 / self.scale_factor)
         img = fs.decoder.run(fs.post_quant_conv.run(zi))
         return ops.image_to_u8(nhwc(img), fs.decoder.out_ch)
+
+    def decode_first_stage_u8(self, z):
+        """decode + 'b c h w -> b h w c' * 127.5 + 127.5, clip, uint8 (canny2image_torch.py:68) on the device.
+        The decoder is ~65 kernel launches; from the third call with the same latent shape (and unchanged VAE weights) they
+        are replayed as ONE captured CUDA graph (SDEO_NO_VAE_GRAPH=1: always eager). The result is a fresh tensor."""
+        if os.environ.get("SDEO_NO_VAE_GRAPH") or not z.is_cuda or torch.cuda.is_current_stream_capturing():
+            return self._decode_u8_eager(z)
+        cache = self.__dict__.setdefault("_vae_graphs", {})
+        fsp = self.__dict__.get("_fp_params")
+        if fsp is None:
+            self.weights_fingerprint(first_stage=True)
+            fsp = self.__dict__["_fp_params"]
+        wkey = hash(tuple([p._version for p in fsp[1]] + [p.data_ptr() for p in fsp[1]]))
+        key = (tuple(z.shape), z.dtype, z.device.index)
+        ent = cache.get(key)
+        if ent is not None and ent["wkey"] != wkey:
+            ent = None
+        if ent is None:
+            ent = cache[key] = {"wkey": wkey, "calls": 0, "graph": None}
+        ent["calls"] += 1
+        if ent["graph"] is None:
+            if ent["calls"] < 3:   # first call packs weights / tunes the conv shapes, second confirms the steady state
+                return self._decode_u8_eager(z)
+            ent["z"] = z.detach().clone()
+            torch.cuda.synchronize(z.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                ent["out"] = self._decode_u8_eager(ent["z"])
+            ent["graph"] = g
+        ent["z"].copy_(z, non_blocking=True)
+        ent["graph"].replay()
+        return ent["out"].clone()

@@ -144,6 +144,35 @@ def test_tiny_decode(tiny, cuda_device):
     assert rel_l2(img, g["decoded"]) < 2e-2
 
 
+def test_tiny_decode_u8_graph_replay(tiny, cuda_device):
+    """decode_first_stage_u8 replays a captured CUDA graph from the third call with the same latent shape: identical
+    bytes to the eager path, for new latents too, and a weight update drops the captured graph."""
+    import os
+    model, g = tiny
+    z0 = g["decode_in"].to(cuda_device)
+    os.environ["SDEO_NO_VAE_GRAPH"] = "1"
+    try:
+        want0 = model.decode_first_stage_u8(z0)
+        want1 = model.decode_first_stage_u8(z0 * 0.5 + 0.1)
+    finally:
+        del os.environ["SDEO_NO_VAE_GRAPH"]
+    model.__dict__.pop("_vae_graphs", None)
+    outs = [model.decode_first_stage_u8(z0) for _ in range(4)]
+    ent = next(iter(model._vae_graphs.values()))
+    assert ent["graph"] is not None and ent["calls"] == 4
+    for o in outs:
+        assert torch.equal(o, want0)
+    assert torch.equal(model.decode_first_stage_u8(z0 * 0.5 + 0.1), want1)
+    assert outs[2].data_ptr() != outs[3].data_ptr()
+    # in-place weight change: the fingerprint differs, the entry restarts (eager again, then a new capture)
+    p0 = next(model.first_stage_model.decoder.parameters())
+    with torch.no_grad():
+        p0.mul_(1.0)
+    model.decode_first_stage_u8(z0)
+    ent = next(iter(model._vae_graphs.values()))
+    assert ent["graph"] is None and ent["calls"] == 1
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # full SD1.5 size, BASELINE configs[1]: 256x384, batch 1, DDIM 20, CFG 9.0
 # ---------------------------------------------------------------------------------------------------------------
