@@ -234,12 +234,19 @@ int sdeo_embedding_add(const int64_t* ids, const float* tok, const float* pos, f
  * (device-resident so that a captured CUDA graph replays for every step without host patching).
  * eps_c / eps_u: fp32, NHWC with ld_eps floats per pixel when eps_nhwc != 0 (the UNet out-conv layout), else NCHW.
  * eps_u may be NULL (no guidance: e = ec). x, noise, x_prev, pred_x0: fp32 NCHW [n, c, hw]; noise/pred_x0 may be NULL.
+ * (a row whose sigma is 0 never reads noise).
  * x_next (optional): bf16 NHWC [dup*n, hw, ldn] copy of x_prev, channels >= c zero-filled, written dup times
  * (the next step's cond+uncond network input). */
 int sdeo_cfg_ddim_step(const float* eps_c, const float* eps_u, int32_t eps_nhwc, int32_t ld_eps, const float* x,
                        const float* noise, float* x_prev, float* pred_x0, void* x_next, int32_t dup, int32_t ldn,
                        const float* coef_table, const int32_t* step_idx, int32_t n, int32_t c, int32_t hw,
                        void* stream);
+/* The same with the noise as a device TABLE [steps][n, c, hw] of which row *step_idx is read: eta > 0 inside a captured step
+ * graph (the sampler engine draws the per-step noise up front, ddim_hacked.py:227-230). step_idx must not be NULL. */
+int sdeo_cfg_ddim_step_noise_table(const float* eps_c, const float* eps_u, int32_t eps_nhwc, int32_t ld_eps, const float* x,
+                                   const float* noise_table, float* x_prev, float* pred_x0, void* x_next, int32_t dup,
+                                   int32_t ldn, const float* coef_table, const int32_t* step_idx, int32_t n, int32_t c,
+                                   int32_t hw, void* stream);
 /* *ctr += delta (single thread) — advances the device-side step index between graph replays. */
 int sdeo_counter_add(int32_t* ctr, int32_t delta, void* stream);
 /* fp32 NCHW -> bf16 NHWC (y = scale * x) with channel padding to ldy (zeros), and back (first c channels).

@@ -70,6 +70,9 @@ SIGNATURES = {
     "sdeo_cfg_ddim_step": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                    c_void_p]),
+    "sdeo_cfg_ddim_step_noise_table": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                               c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                               c_void_p]),
     "sdeo_counter_add": (c_int, [c_void_p, c_int32, c_void_p]),
     "sdeo_nchw_to_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_float, c_void_p]),
     "sdeo_nhwc_bf16_to_nchw": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),

@@ -108,8 +108,8 @@ class DDIMSampler(object):
         if any(v is not None for v in (mask, callback, img_callback, score_corrector, dynamic_threshold, ucg_schedule,
                                        timesteps)) or quantize_denoised or ddim_use_original_steps:
             return False
-        if float(np.max(np.abs(self._h["sigmas"]))) != 0.0:
-            return False  # eta > 0 draws fresh noise every step: generic path
+        if noise_dropout != 0.0:
+            return False  # (eta > 0 itself runs in the engine: the per-step noise is drawn up front into a device table)
         if not isinstance(cond, dict) or self.model.parameterization != "eps":
             return False
         conds = [cond]
@@ -138,7 +138,7 @@ class DDIMSampler(object):
                            quantize_denoised, score_corrector, dynamic_threshold, ucg_schedule,
                            ddim_use_original_steps, timesteps, noise_dropout, temperature):
             return self._engine_sampling(cond, unconditional_conditioning, unconditional_guidance_scale, img,
-                                         log_every_t)
+                                         log_every_t, temperature)
 
         if timesteps is None:
             timesteps = self.ddpm_num_timesteps if ddim_use_original_steps else self.ddim_timesteps
@@ -288,7 +288,7 @@ class DDIMSampler(object):
         return x_dec
 
     # --------------------------------------------------------------------------------------------------------
-    def _engine_sampling(self, cond, uncond, scale, x_T, log_every_t):
+    def _engine_sampling(self, cond, uncond, scale, x_T, log_every_t, temperature=1.0):
         guided = not (uncond is None or scale == 1.)
         S = int(self.ddim_timesteps.shape[0])
         eng = self._engine
@@ -299,7 +299,8 @@ class DDIMSampler(object):
         rows = [self._coef_row(S - i - 1, scale if guided else 1.0) for i in range(S)]
         # the reference logs x_inter / pred_x0 when index % log_every_t == 0 or index == S-1 (ddim_hacked.py:174-176)
         log_at = [i for i in range(S) if (S - i - 1) % log_every_t == 0 or i == 0]
-        img, pred_x0, logged = eng.run(x_T, cond, uncond if guided else None, [int(t) for t in time_range], rows, log_at)
+        img, pred_x0, logged = eng.run(x_T, cond, uncond if guided else None, [int(t) for t in time_range], rows, log_at,
+                                       temperature=temperature)
         inter = {'x_inter': [x_T] + [l[0] for l in logged], 'pred_x0': [x_T] + [l[1] for l in logged]}
         return img, inter
 
@@ -341,6 +342,9 @@ class _Engine:
         self.ts_table = torch.zeros((S,), dtype=torch.int64, device=dev)
         self.coef = torch.zeros((S, 8), dtype=torch.float32, device=dev)
         self.step_ctr = torch.zeros((1,), dtype=torch.int32, device=dev)
+        # eta > 0 (ddim_hacked.py:227-230): sigma_t * noise, one fresh tensor per step, read by the captured step graph as
+        # row *step_ctr of this table
+        self.noise = torch.zeros((S, b, c, h, w), dtype=torch.float32, device=dev)
         ctx_shape = cond["c_crossattn"][0].shape
         self.ctx = torch.empty((nb, ctx_shape[1], ctx_shape[2]), dtype=BF16, device=dev)
         self.has_hint = cond["c_concat"] is not None
@@ -348,9 +352,14 @@ class _Engine:
             hs = cond["c_concat"][0].shape
             self.hint = torch.empty((nb, hs[1], hs[2], hs[3]), dtype=torch.float32, device=dev)
 
-    def _load_inputs(self, x_T, cond, uncond, ts, rows):
+    def _load_inputs(self, x_T, cond, uncond, ts, rows, temperature=1.0):
         b = x_T.shape[0]
         self.x_keep.copy_(x_T, non_blocking=True)
+        for i, row in enumerate(rows):
+            if row[5] != 0.0:
+                # the same draws, in the same order, as the step-by-step path (p_sample_ddim: one noise_like per step
+                # whose sigma is not zero), so both paths produce the same trajectory from the same generator state
+                self.noise[i].copy_(noise_like(tuple(self.noise[i].shape), self.noise.device, False) * temperature)
         self._ts_host = [int(v) for v in ts]
         self.ts_table.copy_(torch.tensor(ts, dtype=torch.int64), non_blocking=True)
         self.coef.copy_(torch.tensor(rows, dtype=torch.float32), non_blocking=True)
@@ -470,17 +479,17 @@ class _Engine:
             eps = nhwc(unet.run_decoder(h, hs, emb_u, self.ctx))          # fp32 [nb, h, w, 4]
         eps_c = eps[:b]
         eps_u = eps[b:] if self.dup == 2 else None
-        ops.cfg_ddim_step(eps_c, eps_u, self.x_lat, self.coef, step_idx=self.step_ctr, x_prev=self.x_lat,
+        ops.cfg_ddim_step(eps_c, eps_u, self.x_lat, self.coef, step_idx=self.step_ctr, noise_table=self.noise, x_prev=self.x_lat,
                           pred_x0=self.pred_x0, x_next=self.x_in, dup=self.dup, eps_nhwc=True)
         ops.counter_add(self.step_ctr, 1)
 
-    def prepare(self, x_T, cond, uncond, ts, rows):
+    def prepare(self, x_T, cond, uncond, ts, rows, temperature=1.0):
         """Upload inputs, run the loop-invariant prologue and (first time) capture the per-step CUDA graph."""
         S = len(ts)
         if not self.ready:
             self._alloc(x_T, cond, uncond, S)
         self.S = S
-        self._load_inputs(x_T, cond, uncond, ts, rows)
+        self._load_inputs(x_T, cond, uncond, ts, rows, temperature)
         self._prologue()
         if self.use_graph and self.graph is None:
             # warm-up once eagerly (packs weights, sizes workspaces), then capture the step
@@ -503,9 +512,9 @@ class _Engine:
         else:
             self._step()
 
-    def run(self, x_T, cond, uncond, ts, rows, log_at=()):
+    def run(self, x_T, cond, uncond, ts, rows, log_at=(), temperature=1.0):
         """log_at: step numbers after which (x_{t-1}, pred_x0) are returned as copies (the reference's intermediates)."""
-        self.prepare(x_T, cond, uncond, ts, rows)
+        self.prepare(x_T, cond, uncond, ts, rows, temperature)
         log_at = set(log_at)
         logged = []
         for i in range(self.S):

@@ -12,7 +12,7 @@ __global__ void cfg_ddim_kernel(const float* __restrict__ eps_c, const float* __
                                 float* __restrict__ x_prev, float* __restrict__ pred_x0,
                                 __nv_bfloat16* __restrict__ x_next, int dup, int ldn,
                                 const float* __restrict__ coef_table, const int* __restrict__ step_idx, int n, int c,
-                                int hw) {
+                                int hw, int noise_table) {
   const int trc = trace_start(5);
   griddep_launch_dependents();
   griddep_wait();
@@ -22,6 +22,9 @@ __global__ void cfg_ddim_kernel(const float* __restrict__ eps_c, const float* __
   const float* cf = coef_table + (size_t)row * 8;
   const float s = cf[0], sqrt_1m_at = cf[1], rsqrt_at = cf[2], sqrt_aprev = cf[3], dir_coef = cf[4], sigma = cf[5];
   const long long total = (long long)n * hw;
+  // eta > 0: `noise` is this step's tensor, or (noise_table) a table [steps][n*c*hw] indexed by the device step counter
+  // (the captured step graph of the sampler engine); rows with sigma == 0 are never read
+  const float* noise_row = (noise && sigma != 0.f) ? noise + (noise_table ? (size_t)row * (size_t)(total * c) : 0) : nullptr;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int b = (int)(i / hw);
@@ -38,7 +41,7 @@ __global__ void cfg_ddim_kernel(const float* __restrict__ eps_c, const float* __
       const float xv = x[nchw];
       const float x0 = (xv - sqrt_1m_at * e) * rsqrt_at;
       float xp = sqrt_aprev * x0 + dir_coef * e;
-      if (noise) xp += sigma * noise[nchw];
+      if (noise_row) xp += sigma * noise_row[nchw];
       x_prev[nchw] = xp;
       if (pred_x0) pred_x0[nchw] = x0;
       if (x_next) {
@@ -351,7 +354,19 @@ extern "C" int sdeo_cfg_ddim_step(const float* eps_c, const float* eps_u, int32_
   if (x_next && (dup <= 0 || ldn < c)) return set_error(SDEO_EINVAL, "cfg_ddim_step: bad x_next geometry");
   if (eps_nhwc && ld_eps < c) return set_error(SDEO_EINVAL, "cfg_ddim_step: ld_eps < c");
   const long long total = (long long)n * hw;
-  return launch_k("cfg_ddim_step", cfg_ddim_kernel, dim3(grid_for(total, 128)), dim3(128), 0, (cudaStream_t)stream, dim3(1, 1, 1), eps_c, eps_u, eps_nhwc, ld_eps, x, noise, x_prev, pred_x0, (__nv_bfloat16*)x_next, dup, ldn, coef_table, step_idx, n, c, hw);
+  return launch_k("cfg_ddim_step", cfg_ddim_kernel, dim3(grid_for(total, 128)), dim3(128), 0, (cudaStream_t)stream, dim3(1, 1, 1), eps_c, eps_u, eps_nhwc, ld_eps, x, noise, x_prev, pred_x0, (__nv_bfloat16*)x_next, dup, ldn, coef_table, step_idx, n, c, hw, 0);
+}
+
+extern "C" int sdeo_cfg_ddim_step_noise_table(const float* eps_c, const float* eps_u, int32_t eps_nhwc, int32_t ld_eps,
+                                              const float* x, const float* noise_table, float* x_prev, float* pred_x0,
+                                              void* x_next, int32_t dup, int32_t ldn, const float* coef_table,
+                                              const int32_t* step_idx, int32_t n, int32_t c, int32_t hw, void* stream) {
+  if (!eps_c || !x || !x_prev || !coef_table || !noise_table || !step_idx || n <= 0 || c <= 0 || hw <= 0)
+    return set_error(SDEO_EINVAL, "cfg_ddim_step_noise_table: bad args");
+  if (x_next && (dup <= 0 || ldn < c)) return set_error(SDEO_EINVAL, "cfg_ddim_step_noise_table: bad x_next geometry");
+  if (eps_nhwc && ld_eps < c) return set_error(SDEO_EINVAL, "cfg_ddim_step_noise_table: ld_eps < c");
+  const long long total = (long long)n * hw;
+  return launch_k("cfg_ddim_step", cfg_ddim_kernel, dim3(grid_for(total, 128)), dim3(128), 0, (cudaStream_t)stream, dim3(1, 1, 1), eps_c, eps_u, eps_nhwc, ld_eps, x, noise_table, x_prev, pred_x0, (__nv_bfloat16*)x_next, dup, ldn, coef_table, step_idx, n, c, hw, 1);
 }
 
 extern "C" int sdeo_counter_add(int32_t* ctr, int32_t delta, void* stream) {

@@ -467,8 +467,9 @@ def to_f32(x):
 
 
 def cfg_ddim_step(eps_c, eps_u, x, coef_table, step_idx=None, noise=None, x_prev=None, pred_x0=None, x_next=None,
-                  dup=0, eps_nhwc=False):
-    """x: fp32 [N,C,H,W]. eps_*: fp32 NCHW, or NHWC [N,H,W,ld] when eps_nhwc. Returns (x_prev, pred_x0)."""
+                  dup=0, eps_nhwc=False, noise_table=None):
+    """x: fp32 [N,C,H,W]. eps_*: fp32 NCHW, or NHWC [N,H,W,ld] when eps_nhwc. Returns (x_prev, pred_x0).
+    noise_table: fp32 [S, N, C, H, W] of which row *step_idx is added (times sigma) instead of `noise`."""
     lib = _lib.load()
     _req(x, torch.float32, "x")
     n, c, h, w = x.shape
@@ -476,6 +477,14 @@ def cfg_ddim_step(eps_c, eps_u, x, coef_table, step_idx=None, noise=None, x_prev
     if x_prev is None:
         x_prev = torch.empty_like(x)
     ldn = x_next.shape[-1] if x_next is not None else 0
+    if noise_table is not None:
+        assert noise is None and step_idx is not None and tuple(noise_table.shape[1:]) == (n, c, h, w)
+        _req(noise_table, torch.float32, "noise_table")
+        check(lib.sdeo_cfg_ddim_step_noise_table(_ptr(eps_c), _ptr(eps_u), 1 if eps_nhwc else 0, ld_eps, _ptr(x),
+                                                 _ptr(noise_table), _ptr(x_prev), _ptr(pred_x0), _ptr(x_next), dup, ldn,
+                                                 _ptr(coef_table), _ptr(step_idx), n, c, h * w, _stream()),
+              "cfg_ddim_step_noise_table")
+        return x_prev, pred_x0
     check(lib.sdeo_cfg_ddim_step(_ptr(eps_c), _ptr(eps_u), 1 if eps_nhwc else 0, ld_eps, _ptr(x), _ptr(noise),
                                  _ptr(x_prev), _ptr(pred_x0), _ptr(x_next), dup, ldn, _ptr(coef_table),
                                  _ptr(step_idx), n, c, h * w, _stream()), "cfg_ddim_step")

@@ -657,6 +657,10 @@ def test_cfg_ddim_step(cuda_device):
     eu_l = eu.permute(0, 2, 3, 1).contiguous()
     xp2, _ = ops.cfg_ddim_step(ec_l, eu_l, x, table, step_idx=idx, eps_nhwc=True)
     assert rel_l2(xp2, ref - sigma * noise) < 1e-5
+    # noise as a table indexed by the device step counter (eta > 0 inside the captured step graph)
+    nt = torch.stack([torch.full_like(noise, float("nan")), noise])
+    xp3, _ = ops.cfg_ddim_step(ec, eu, x, table, step_idx=idx, noise_table=nt)
+    assert rel_l2(xp3, ref) < 1e-5
     ops.counter_add(idx, 1)
     assert idx.item() == 2
 

@@ -100,6 +100,29 @@ def test_tiny_sampler_generic_path(tiny, cuda_device):
     assert rel_l2(samples, g["samples"]) < 3e-2
 
 
+def test_tiny_sampler_eta_engine_vs_generic(tiny, cuda_device):
+    """eta > 0 (ddim_hacked.py:227-230) inside the captured-graph engine: the per-step noise is drawn up front into a device
+    table (same torch draws, same order, as the step-by-step path), so with the same generator state both paths follow the
+    same trajectory; temperature scales the noise; eta = 0 differs."""
+    from stablediffusioneo_b200.cldm.ddim_hacked import DDIMSampler
+    model, g = tiny
+    x_T, cond, uncond = inputs_on(O.TINY, 8, 16, cuda_device)
+    kw = dict(verbose=False, x_T=x_T, unconditional_guidance_scale=9.0, unconditional_conditioning=uncond)
+    out = {}
+    for engine in (True, False):
+        sampler = DDIMSampler(model)
+        sampler.use_engine = engine
+        for eta, temp in ((0.7, 1.0), (0.7, 0.5), (0.0, 1.0)):
+            torch.manual_seed(1234)
+            out[(engine, eta, temp)], _ = sampler.sample(g["S"], 1, (4, 8, 16), cond, eta=eta, temperature=temp, **kw)
+        assert (sampler._engine is not None) == engine
+    for eta, temp in ((0.7, 1.0), (0.7, 0.5), (0.0, 1.0)):
+        # (engine vs step-by-step on the tiny random model: 3e-2 gate at eta = 0, a little more once noise is injected)
+        assert rel_l2(out[(True, eta, temp)], out[(False, eta, temp)]) < (3e-2 if eta == 0.0 else 5e-2), (eta, temp)
+    assert rel_l2(out[(True, 0.7, 1.0)], out[(True, 0.0, 1.0)]) > 5e-2
+    assert rel_l2(out[(True, 0.7, 1.0)], out[(True, 0.7, 0.5)]) > 2e-2
+
+
 def test_tiny_control_modes_vs_oracle(tiny, cuda_device):
     """canny2image_torch.py:48-58 knobs: graded control_scales (guess-mode strengths 0.825^(12-i)), only_mid_control,
     and guess mode (the unconditional branch runs WITHOUT the ControlNet) -- apply_model and the sampler against the
