@@ -482,21 +482,36 @@ gn_apply_stats_kernel(const T* __restrict__ x1, const T* __restrict__ x2, const 
   const int c_lo = g_lo * cpg, cs = ng * cpg;  // this CTA's channels [c_lo, c_lo + cs), cs % 8 == 0
   float* chan_sum = sm;       // [cs]
   float* chan_sq = sm + cs;   // [cs]
-  for (int cl = threadIdx.x; cl < cs; cl += kGNThreads) {
+  // The fold sits in front of every CTA's first load of the tensor, and each pass of 4 partials is an L2 round trip: the
+  // `pgs` thread groups of a channel take partials pg, pg + pgs, ... (24..72 partials: 2-6 round trips instead of 6-18),
+  // then one thread per channel adds the group sums in group order (fixed order: deterministic).
+  const int pgs = cs <= kGNThreads ? min(8, kGNThreads / cs) : 1;
+  float2* part = reinterpret_cast<float2*>(sm + 2 * cs);   // [pgs][cs]
+  for (int idx = threadIdx.x; idx < cs * pgs; idx += kGNThreads) {
+    const int cl = idx % cs, pg = idx / cs;
     const int c = c_lo + cl;
     const bool first = c < c1;
     const float2* src = first ? st1 + (size_t)n * parts1 * c1 + c : st2 + (size_t)n * parts2 * c2 + (c - c1);
     const int parts = first ? parts1 : parts2, ld = first ? c1 : c2;
     float s = 0.f, q = 0.f;
-    int k = 0;
-    for (; k + 4 <= parts; k += 4) {  // 4 independent loads in flight, added in slot order
-      const float2 a0 = __ldcg(src + (size_t)k * ld), a1 = __ldcg(src + (size_t)(k + 1) * ld);
-      const float2 a2 = __ldcg(src + (size_t)(k + 2) * ld), a3 = __ldcg(src + (size_t)(k + 3) * ld);
+    int k = pg;
+    for (; k + 3 * pgs < parts; k += 4 * pgs) {  // 4 independent loads in flight, added in slot order
+      const float2 a0 = __ldcg(src + (size_t)k * ld), a1 = __ldcg(src + (size_t)(k + pgs) * ld);
+      const float2 a2 = __ldcg(src + (size_t)(k + 2 * pgs) * ld), a3 = __ldcg(src + (size_t)(k + 3 * pgs) * ld);
       s += a0.x; q += a0.y; s += a1.x; q += a1.y; s += a2.x; q += a2.y; s += a3.x; q += a3.y;
     }
-    for (; k < parts; ++k) {
+    for (; k < parts; k += pgs) {
       const float2 a0 = __ldcg(src + (size_t)k * ld);
       s += a0.x; q += a0.y;
+    }
+    part[(size_t)pg * cs + cl] = make_float2(s, q);
+  }
+  __syncthreads();
+  for (int cl = threadIdx.x; cl < cs; cl += kGNThreads) {
+    float s = 0.f, q = 0.f;
+    for (int pg = 0; pg < pgs; ++pg) {
+      const float2 v2 = part[(size_t)pg * cs + cl];
+      s += v2.x; q += v2.y;
     }
     chan_sum[cl] = s;
     chan_sq[cl] = q;
@@ -765,7 +780,10 @@ extern "C" int sdeo_groupnorm_apply_stats(const void* x1, const void* x2, int32_
   int ppc = (hw + want - 1) / want;
   if (ppc < 4) ppc = hw < 4 ? hw : 4;
   const int chunks = (hw + ppc - 1) / ppc;
-  const size_t smem = (size_t)2 * gslab * cpg * sizeof(float);
+  // channel sums [2][cs] + the fold's group partials [pgs][cs] float2 (pgs as in the kernel)
+  const int cs_max = gslab * cpg;
+  const int pgs = cs_max <= kGNThreads ? (kGNThreads / cs_max < 8 ? kGNThreads / cs_max : 8) : 1;
+  const size_t smem = (size_t)2 * cs_max * sizeof(float) * (size_t)(1 + pgs);
   const dim3 grid((unsigned)chunks, (unsigned)slabs, (unsigned)n), one(1, 1, 1);
   cudaStream_t st = (cudaStream_t)stream;
   if (x_f32)
