@@ -114,6 +114,23 @@ typedef struct sdeo_conv_args {
   /* extra zero rows / columns AFTER the last input row / column (0, or 1 with ksize 3, stride 2, pad 0): the VAE
    * encoder's Downsample, F.pad(x, (0,1,0,1)) + conv(stride 2, padding 0) (ldm/modules/diffusionmodules/model.py:80-84) */
   int32_t pad_hi;
+  /* optional, GroupNorm (+ SiLU) FOLDED into this convolution's operand path (GroupNorm32 -> SiLU -> conv of ResBlock
+   * in_layers / out_layers, openaimodel.py:200-240; Normalize -> proj_in of SpatialTransformer, attention.py:406-418;
+   * norm1/norm2 -> conv1/conv2 of the VAE ResnetBlock, model.py:125-139; the plugin's bSwish contract,
+   * groupNormPlugin.cpp:291-304): x1 / x2 are the RAW bf16 tensors; each operand tile is normalised (and SiLU'd) in shared
+   * memory before the MMA reads it, so the normalised tensor never exists in global memory and the GroupNorm costs no
+   * launch. Statistics come from the producers' epilogues (gn_stats of the convolutions that wrote x1 / x2):
+   * gnf_stats1 = fp32 [n][gnf_parts1][c1][2], gnf_stats2 likewise for x2 (NULL without x2). gnf_gamma / gnf_beta: fp32
+   * [c1 + c2]; groups of (c1 + c2) / gnf_groups consecutive channels of the virtual concat (a group may straddle the
+   * seam). Zero padding stays zero (it pads the NORMALISED tensor). Not with ln_stats. NULL gnf_stats1 = off. */
+  const float* gnf_stats1;
+  const float* gnf_stats2;
+  int32_t gnf_parts1, gnf_parts2;
+  const float* gnf_gamma;
+  const float* gnf_beta;
+  int32_t gnf_groups;
+  float gnf_eps;
+  int32_t gnf_silu;
 } sdeo_conv_args;
 
 /* Bytes of workspace the planner may use for these args (fp32 partial tiles + tile counters).
@@ -203,6 +220,11 @@ int sdeo_groupnorm_apply_stats(const void* x1, const void* x2, int32_t x_f32, co
                                const float* stats2, int32_t parts2, const float* gamma, const float* beta, void* y,
                                int32_t n, int32_t hw, int32_t c1, int32_t c2, int32_t groups, float eps, int32_t with_silu,
                                void* stream);
+
+/* Folds partial statistics [n][parts][c][2] down to [n][*out_parts][c][2], *out_parts = ceil(parts / 256) (fixed order):
+ * large feature maps leave one slot per 128-pixel tile, too many for every CTA of a consumer with a folded GroupNorm
+ * (sdeo_conv_args::gnf_*) to add up on its own. stats == NULL or out == NULL: geometry query only. */
+int sdeo_gn_stats_fold(const float* stats, float* out, int32_t n, int32_t parts, int32_t c, int32_t* out_parts, void* stream);
 
 /* LayerNorm over the last dim of [rows, c] bf16 (nn.LayerNorm, attention.py:372-374), eps 1e-5. */
 int sdeo_layernorm(const void* x, int32_t x_f32, const float* gamma, const float* beta, void* y, int32_t rows,

@@ -31,6 +31,9 @@ class ConvArgs(Structure):
         ("ln_stats", c_void_p), ("ln_parts", c_int32), ("ln_ld", c_int32), ("ln_c", c_int32), ("ln_eps", ctypes.c_float),
         ("ln_csum", c_void_p),
         ("pad_hi", c_int32),
+        ("gnf_stats1", c_void_p), ("gnf_stats2", c_void_p), ("gnf_parts1", c_int32), ("gnf_parts2", c_int32),
+        ("gnf_gamma", c_void_p), ("gnf_beta", c_void_p), ("gnf_groups", c_int32), ("gnf_eps", ctypes.c_float),
+        ("gnf_silu", c_int32),
     ]
 
 
@@ -50,6 +53,7 @@ SIGNATURES = {
     "sdeo_conv_row_stats_parts": (c_int, [POINTER(ConvArgs), POINTER(c_int32), POINTER(c_int32)]),
     "sdeo_groupnorm_apply_stats": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p,
                                            c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, c_int32, c_void_p]),
+    "sdeo_gn_stats_fold": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, POINTER(c_int32), c_void_p]),
     "sdeo_packed_rows": (c_int32, [c_int32]),
     "sdeo_packed_k": (c_int32, [c_int32, c_int32, c_int32]),
     "sdeo_pick_bn": (c_int32, [c_int32, c_int32, c_int32]),

@@ -37,6 +37,8 @@ constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kATileBytes = kBM * kBK * 2;  // 16 KB
 constexpr int kMaxCluster = 8;              // portable cluster size limit
+constexpr int kGnfWarps = 7;                // folded GroupNorm: warps 2..8 normalise the A tiles
+constexpr int kGnfThreads = kGnfWarps * 32;
 
 struct ConvKParams {
   // K loop
@@ -96,6 +98,18 @@ struct ConvKParams {
   // epilogue's critical path): rows per K-slice rank, (row, 8- or 16-column) items per row, rows / leftover items one
   // pass of the 384 threads covers, and the multiplier that turns threadIdx.x / cols_items into a multiply-shift
   int rows_per, cols_items, step_rows, step_cols, ci_magic;
+  // GroupNorm (+ SiLU) folded into the A operand path (sdeo_conv_args::gnf_*): warps 2..8 fold the producers' partial
+  // statistics into a per-(sample of the tile, channel) table (a, b) in shared memory while the first tiles are in flight,
+  // then turn every A tile that lands into silu(a * x + b) IN PLACE (positions outside the input stay zero: the
+  // convolution pads the normalised tensor) and hand it to the MMA issuer through a second barrier set (xf_bar / xf_a).
+  int gnf, gnf_silu, gnf_off;            // on / SiLU / byte offset of the table in shared memory
+  const float2* gnf_st1;
+  const float2* gnf_st2;
+  int gnf_parts1, gnf_parts2, gnf_c1, gnf_c2, gnf_groups, gnf_cpg;
+  const float* gnf_gamma;
+  const float* gnf_beta;
+  float gnf_eps, gnf_inv;                // 1 / (H * W * channels per group)
+  int Hin, Win;
   int l2_prefetch;  // producers pull the CTA's whole weight slice into L2 before the grid dependency resolves (SDEO_L2_PREFETCH=1: on)
   int probe;  // MMA issuer probes the next stage's barrier while it issues the current step (SDEO_NO_PROBE=1: off)
 };
@@ -463,6 +477,8 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmA1, const CU
   uint64_t* res_bar = full_bar + 49;   // completes when the residual tile (one TMA box) has landed
   uint64_t* full_a = full_bar + 40;    // HALO mode: the A (halo tile) ring, up to 4 stages
   uint64_t* empty_a = full_bar + 44;
+  uint64_t* xf_bar = full_bar + 50;    // folded GroupNorm: stage s holds the NORMALISED A tile (tap-by-tap ring, <= 8 stages)
+  uint64_t* xf_a = full_bar + 58;      // folded GroupNorm, HALO mode: halo tile slot sa is normalised (<= 4 slots)
   int* row_pix = reinterpret_cast<int*>(smem + 512);  // [128] output pixel index per tile row
   float2* ln_vec = reinterpret_cast<float2*>(smem + 1024);  // [128] (mean, rstd) of the folded LayerNorm per tile row
   float* colv = reinterpret_cast<float*>(smem + 2048);   // [BN] bias (+ the tile's time-embedding row) per column of this N tile
@@ -508,6 +524,9 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmA1, const CU
     for (int s = 0; s < p.a_stages; ++s) {
       mbar_init(&full_a[s], 1);
       mbar_init(&empty_a[s], 1);
+    }
+    if (p.gnf) {  // one arrival per transforming warp (warps 2..8)
+      for (int s = 0; s < (p.halo ? p.a_stages : p.stages); ++s) mbar_init(p.halo ? &xf_a[s] : &xf_bar[s], kGnfWarps);
     }
     mbar_init(tmem_full_bar, 1);
     mbar_init(recv_bar, 1);
@@ -658,7 +677,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmA1, const CU
     for (int i = 0; i < nchunks; ++i) {
       const long long t_w0 = p.dbg ? clock64() : 0;
       if (i == 0 || t == 0) {
-        mbar_wait(&full_a[sa], pha);
+        mbar_wait(p.gnf ? &xf_a[sa] : &full_a[sa], pha);
       }
       if (!ready) mbar_wait(&full_bar[sb], phb);
       if (p.dbg) dbg_wait += clock64() - t_w0;
@@ -773,10 +792,11 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmA1, const CU
       uint64_t a_desc = a_desc0, b_desc = b_desc0;
       long long dbg_wait = 0;
       uint32_t ready = 0;   // the full barrier of step i was probed (complete) while step i - 1 was being issued
+      uint64_t* const data_bar = p.gnf ? xf_bar : full_bar;   // folded GroupNorm: wait for the normalised tile
       for (int i = 0; i < nchunks; ++i) {
         if (!ready) {
           const long long t_w0 = p.dbg ? clock64() : 0;
-          mbar_wait(&full_bar[s], ph);
+          mbar_wait(&data_bar[s], ph);
           if (p.dbg) dbg_wait += clock64() - t_w0;
         }
         tc_fence_after();
@@ -787,7 +807,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmA1, const CU
         // that frees this stage (in both CTAs of a pair) once they have read it, and the probe of the next stage
         if (p.probe) {
           ready = tc_mma_step_probe<PAIR>(tmem_base, a_desc, b_desc, idesc, i > 0 ? 1u : 0u, &empty_bar[s], pair_mask,
-                                          &full_bar[sn], phn);
+                                          &data_bar[sn], phn);
           if (i + 1 == nchunks) ready = 0;
         } else {
 #pragma unroll
@@ -854,6 +874,146 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmA1, const CU
         mr = make_float2(mean, rsqrtf(var + p.ln_eps));
       }
       ln_vec[row] = mr;
+    }
+  }
+
+  if (p.gnf && warp >= 2 && warp < 2 + kGnfWarps) {
+    // ===================== folded GroupNorm: statistics -> (a, b) table, then every A tile in place =====================
+    const int t = (int)threadIdx.x - 64;
+    const int Cp = p.chunks_per_tap * 64;                 // table row: one entry per K position of a tap (padded channels)
+    float2* ab = reinterpret_cast<float2*>(smem + p.gnf_off);   // [bn_][Cp]: first (sum, sum of squares), then (a, b)
+    float2* gst = ab + (size_t)p.bn_ * Cp;                      // [bn_][groups] (mean, rstd)
+    const int C = p.gnf_c1 + p.gnf_c2;
+    const int n_entries = p.bn_ * Cp;
+    // tile row -> input position table (shares the folded-LayerNorm row vector's space: the two never meet)
+    int* row_hw = reinterpret_cast<int*>(ln_vec);           // tap-by-tap: (sample << 16 | h << 8 | w) inside the tile, -1 = none
+    uint8_t* halo_ok = reinterpret_cast<uint8_t*>(ln_vec);  // HALO: halo position lies inside the input
+    const int halo_rows = (p.bh + 2) * p.hpitch;
+    if (p.halo) {
+      for (int r = t; r < halo_rows; r += kGnfThreads) {
+        const int hy = r / p.hpitch, hx = r - hy * p.hpitch;
+        const int hh = h0 - 1 + hy, ww = w0 - 1 + hx;
+        halo_ok[r] = (hh >= 0 && hh < p.Hin && ww >= 0 && ww < p.Win && n0 < p.N) ? 1 : 0;
+      }
+    } else {
+      const int per_img = p.bh * p.bw;
+      for (int r = t; r < kBM; r += kGnfThreads) {
+        const int nl = r / per_img, rem = r - nl * per_img;
+        const int hl = rem / p.bw, wl = rem - hl * p.bw;
+        row_hw[r] = (r < p.rows_valid && n0 + nl < p.N) ? ((nl << 16) | (hl << 8) | wl) : -1;
+      }
+    }
+    // 1. per-channel (sum, sum of squares): the producers' partial slots, added in slot order (deterministic)
+    for (int idx = t; idx < n_entries; idx += kGnfThreads) {
+      const int nl = idx / Cp, c = idx - nl * Cp;
+      const int n = n0 + nl;
+      float sum = 0.f, sq = 0.f;
+      if (c < C && n < p.N) {
+        const bool first = c < p.gnf_c1;
+        const int parts = first ? p.gnf_parts1 : p.gnf_parts2, ld = first ? p.gnf_c1 : p.gnf_c2;
+        const float2* src = first ? p.gnf_st1 + (size_t)n * parts * ld + c : p.gnf_st2 + (size_t)n * parts * ld + (c - p.gnf_c1);
+        int k = 0;
+        for (; k + 8 <= parts; k += 8) {   // 8 independent loads in flight
+          float2 a[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) a[u] = __ldcg(src + (size_t)(k + u) * ld);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { sum += a[u].x; sq += a[u].y; }
+        }
+        for (; k < parts; ++k) {
+          const float2 a0 = __ldcg(src + (size_t)k * ld);
+          sum += a0.x; sq += a0.y;
+        }
+      }
+      ab[idx] = make_float2(sum, sq);
+    }
+    bar_sync(1, kGnfThreads);
+    // 2. (mean, rstd) of every (sample of the tile, group)
+    for (int idx = t; idx < p.bn_ * p.gnf_groups; idx += kGnfThreads) {
+      const int nl = idx / p.gnf_groups, g = idx - nl * p.gnf_groups;
+      const float2* src = ab + (size_t)nl * Cp + g * p.gnf_cpg;
+      float sum = 0.f, sq = 0.f;
+      for (int j = 0; j < p.gnf_cpg; ++j) { sum += src[j].x; sq += src[j].y; }
+      const float mean = sum * p.gnf_inv;
+      float var = sq * p.gnf_inv - mean * mean;
+      var = var < 0.f ? 0.f : var;
+      gst[idx] = make_float2(mean, rsqrtf(var + p.gnf_eps));
+    }
+    bar_sync(1, kGnfThreads);
+    // 3. y = a * x + b per (sample, channel); channels beyond the tensor (K padding) stay finite: the weights there are zero
+    for (int idx = t; idx < n_entries; idx += kGnfThreads) {
+      const int nl = idx / Cp, c = idx - nl * Cp;
+      float2 v = make_float2(0.f, 0.f);
+      if (c < C) {
+        const float2 mr = gst[nl * p.gnf_groups + c / p.gnf_cpg];
+        v.x = __ldg(p.gnf_gamma + c) * mr.y;
+        v.y = __ldg(p.gnf_beta + c) - mr.x * v.x;
+      }
+      ab[idx] = v;
+    }
+    bar_sync(1, kGnfThreads);
+    if (t == 0) SDEO_DBG(2);
+    const bool with_silu = p.gnf_silu != 0;
+    // one 16-byte unit (8 channels of one tile row) at physical offset `off` inside a 128B-swizzled tile: the logical
+    // 8-channel index is the physical one XOR (row & 7) -- both are bits of the shared-memory address
+    auto xform_unit = [&](uint32_t addr, const float2* abrow) {
+      const uint32_t lu = ((addr >> 4) ^ (addr >> 7)) & 7u;
+      uint4 raw;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w) : "r"(addr));
+      const float4* abp = reinterpret_cast<const float4*>(abrow + lu * 8);
+      const float4 ab0 = abp[0], ab1 = abp[1], ab2 = abp[2], ab3 = abp[3];
+      float2 x0 = unpack_bf16x2(raw.x), x1 = unpack_bf16x2(raw.y), x2 = unpack_bf16x2(raw.z), x3 = unpack_bf16x2(raw.w);
+      float y[8];
+      y[0] = fmaf(x0.x, ab0.x, ab0.y); y[1] = fmaf(x0.y, ab0.z, ab0.w);
+      y[2] = fmaf(x1.x, ab1.x, ab1.y); y[3] = fmaf(x1.y, ab1.z, ab1.w);
+      y[4] = fmaf(x2.x, ab2.x, ab2.y); y[5] = fmaf(x2.y, ab2.z, ab2.w);
+      y[6] = fmaf(x3.x, ab3.x, ab3.y); y[7] = fmaf(x3.y, ab3.z, ab3.w);
+      if (with_silu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = silu_f(y[j]);
+      }
+      st_smem_f4(addr, pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+    };
+    if (p.halo) {
+      const int c_first = k_begin / 9, c_last = (k_end - 1) / 9;
+      const int units = halo_rows * 8;
+      for (int c = c_first; c <= c_last; ++c) {
+        const int na = c - c_first, sa = na % p.a_stages;
+        mbar_wait(&full_a[sa], (uint32_t)((na / p.a_stages) & 1));
+        const uint32_t base = smem_u32(tiles) + (uint32_t)(sa * p.a_stage_bytes);
+        const float2* abrow = ab + c * 64;
+        for (int q = t; q < units; q += kGnfThreads) {
+          if (halo_ok[q >> 3]) xform_unit(base + (uint32_t)q * 16u, abrow);
+        }
+        fence_proxy_async_smem();   // generic-proxy stores -> visible to the MMA's operand reads (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xf_a[sa]);
+      }
+    } else {
+      const int units = p.rows_valid * 8;
+      int s = 0;
+      uint32_t ph = 0;
+      int tap = k_begin / p.chunks_per_tap, within = k_begin % p.chunks_per_tap;
+      int ky = tap / p.kw, kx = tap % p.kw;
+      for (int i = 0; i < nchunks; ++i) {
+        mbar_wait(&full_bar[s], ph);
+        const uint32_t base = smem_u32(tiles) + (uint32_t)(s * stage_bytes);
+        const int hb = h0 * p.stride + ky - p.pad, wb = w0 * p.stride + kx - p.pad;
+        for (int q = t; q < units; q += kGnfThreads) {
+          const int info = row_hw[q >> 3];
+          const int hh = hb + ((info >> 8) & 255) * p.stride, ww = wb + (info & 255) * p.stride;
+          if (info >= 0 && hh >= 0 && hh < p.Hin && ww >= 0 && ww < p.Win)
+            xform_unit(base + (uint32_t)q * 16u, ab + (size_t)(info >> 16) * Cp + within * 64);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xf_bar[s]);
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+        if (++within == p.chunks_per_tap) {
+          within = 0;
+          if (++kx == p.kw) { kx = 0; ++ky; }
+        }
+      }
     }
   }
 
@@ -1230,6 +1390,7 @@ struct ConvPlan {
   int pair;  // CTA pairs (cta_group::2): grid.x = M tiles rounded up to even, cluster (2,1,S)
   int nprod;
   int occ2;  // the plan leaves room for two CTAs per SM (<= 112 KB of shared memory): one CTA's epilogue overlaps the other's mainloop
+  int gnf_off, gnf_bytes;  // folded GroupNorm: the (a, b) table + group statistics behind the pipeline / residual tile
 };
 
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -1374,7 +1535,10 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl, int force_bn = 0, i
       if (const char* e = getenv("SDEO_PAIR")) want = atoi(e) ? 1 : 0;
     }
     if (want == 1 && best_tiles < 2) return false;
-    pl->pair = (best_tiles >= 2 && want != 0) ? 1 : 0;
+    // (folded GroupNorm: every CTA normalises the A tiles it stages after waiting on its OWN barrier; in a pair the
+    //  partner's loads complete on the leader's barrier, which a remote CTA cannot wait on)
+    if (want == 1 && a->gnf_stats1) return false;
+    pl->pair = (best_tiles >= 2 && want != 0 && !a->gnf_stats1) ? 1 : 0;
     // a forced K-slice count beyond what fits a cluster next to the pair wins over the pair HEURISTIC
     int fs = force_splits;
     if (const char* e = getenv("SDEO_FORCE_SPLITS")) fs = atoi(e);
@@ -1441,7 +1605,16 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl, int force_bn = 0, i
     if (chunks >= 3 && (kSmemMax - kFixed - extra - 3 * pl->a_stage_bytes) / stage_bytes >= 6) ast = 3;
     return ast;
   };
-  auto stages_for = [&](int extra) {  // pipeline depth that fits next to `extra` bytes of residual buffer
+  pl->gnf_off = 0; pl->gnf_bytes = 0;
+  if (a->gnf_stats1) {
+    if (a->ln_stats || a->gnf_groups <= 0 || (a->c1 + (a->x2 ? a->c2 : 0)) % a->gnf_groups != 0 || !a->gnf_gamma || !a->gnf_beta ||
+        (a->x2 && !a->gnf_stats2) || pl->bn_ > 128 || pl->bh > 255 || pl->bw > 255)
+      return false;
+    pl->gnf_bytes = round_up(pl->bn_ * (pl->cpt * 64 + a->gnf_groups) * 8, 128);
+  }
+  const int gnf_bytes = pl->gnf_bytes;
+  auto stages_for = [&](int extra0) {  // pipeline depth that fits next to `extra` bytes of residual buffer (+ the folded GroupNorm table)
+    const int extra = extra0 + gnf_bytes;
     if (kFixed + tile_bytes + extra > kSmemMax) return 0;
     const int a_ring = a_ring_for(extra) * pl->a_stage_bytes;
     int st = (kSmemMax - kFixed - extra - a_ring) / stage_bytes;
@@ -1450,7 +1623,7 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl, int force_bn = 0, i
     return st;
   };
   int stages = stages_for(0);
-  if (pl->occ2 && (stages < 3 || (pl->halo && a_ring_for(0) < 2))) {
+  if (pl->occ2 && (stages < 3 || (pl->halo && a_ring_for(gnf_bytes) < 2))) {
     // too shallow a ring (or no room for the epilogue tile) at half the shared memory
     if (force_occ2 == 1) return false;
     return make_plan(a, pl, force_bn, force_splits, force_halo, force_pair, 0);
@@ -1473,12 +1646,13 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl, int force_bn = 0, i
   pl->nprod = stages < kProducers ? stages : kProducers;
   stages -= stages % pl->nprod;
   pl->stages = stages;
-  pl->a_stages = a_ring_for(res_bytes);
+  pl->a_stages = a_ring_for(res_bytes + gnf_bytes);
   size_t body = (size_t)stages * stage_bytes + (size_t)pl->a_stages * pl->a_stage_bytes;
   if (body < (size_t)tile_bytes) body = tile_bytes;
   body = (body + 127) & ~(size_t)127;   // (the residual tile behind it is a TMA destination)
   if (res_bytes) pl->res_smem_off = 4096 + (int)body;
-  pl->smem_bytes = kFixed + body + res_bytes;
+  if (gnf_bytes) pl->gnf_off = 4096 + (int)body + ((res_bytes + 127) & ~127);
+  pl->smem_bytes = kFixed + body + ((res_bytes + 127) & ~127) + gnf_bytes;
   int tc = 32;
   while (tc < pl->BN) tc *= 2;  // fp32 accumulator columns (power of two >= 32)
   pl->tmem_cols = tc;
@@ -1545,8 +1719,8 @@ static bool row_stats_ok(const sdeo_conv_args* a, const ConvPlan& pl) {
 }
 
 static int stats_parts(const sdeo_conv_args* a, const ConvPlan& pl) {
-  if (!a->gn_stats || a->row_stats || a->epi_mode != SDEO_EPI_NORMAL || !a->y_fp32) return 0;
-  bool fast = (a->cout % 16 == 0) && (a->ldy % 4 == 0);
+  if (!a->gn_stats || a->row_stats || a->epi_mode != SDEO_EPI_NORMAL) return 0;
+  bool fast = (a->cout % 16 == 0) && (a->y_fp32 ? (a->ldy % 4 == 0) : (a->ldy % 8 == 0));
   if (a->y2) fast = fast && (a->ldy2 % 8 == 0);
   if (a->residual) fast = fast && (a->residual_f32 ? (a->ldr % 4 == 0) : (a->ldr % 8 == 0));
   if (!fast) return 0;
@@ -1576,7 +1750,8 @@ int g_autotune = 0;
 TuneKey tune_key(const sdeo_conv_args* a) {
   TuneKey k = {a->n, a->h, a->w, a->c1, a->x2 ? a->c2 : 0, a->cout, a->ksize, a->stride | (a->pad_hi << 4), a->epi_mode, a->y_fp32,
                a->residual ? (a->residual_f32 ? 2 : 1) : 0, a->y2 ? 1 : 0, a->emb ? 1 : 0, a->act, a->dhead,
-               (a->gn_stats ? 1 : 0) | (a->row_stats ? 2 : 0) | (a->ln_stats ? 4 : 0) | (cta_limit() << 3)};
+               (a->gn_stats ? 1 : 0) | (a->row_stats ? 2 : 0) | (a->ln_stats ? 4 : 0) | (cta_limit() << 3) |
+                   (a->gnf_stats1 ? (1 << 12) | (a->gnf_silu ? 1 << 13 : 0) : 0)};
   return k;
 }
 
@@ -1827,6 +2002,15 @@ static int launch_conv(const sdeo_conv_args* a, const ConvPlan& pl, void* stream
   }
   p.gn_stats = nullptr;
   p.row_stats = nullptr; p.row_stats_ld = 0;
+  p.gnf = a->gnf_stats1 ? 1 : 0; p.gnf_silu = a->gnf_silu; p.gnf_off = pl.gnf_off;
+  p.gnf_st1 = (const float2*)a->gnf_stats1; p.gnf_st2 = (const float2*)a->gnf_stats2;
+  p.gnf_parts1 = a->gnf_parts1; p.gnf_parts2 = a->gnf_parts2; p.gnf_c1 = a->c1; p.gnf_c2 = a->x2 ? a->c2 : 0;
+  p.gnf_groups = a->gnf_groups; p.gnf_cpg = a->gnf_groups > 0 ? (a->c1 + (a->x2 ? a->c2 : 0)) / a->gnf_groups : 0;
+  p.gnf_gamma = a->gnf_gamma; p.gnf_beta = a->gnf_beta; p.gnf_eps = a->gnf_eps;
+  p.gnf_inv = p.gnf ? 1.0f / ((float)a->h * (float)a->w * (float)p.gnf_cpg) : 0.f;
+  p.Hin = a->h; p.Win = a->w;
+  if (p.gnf && (pl.pair || !pl.gnf_off || a->gnf_parts1 <= 0 || (a->x2 && a->gnf_parts2 <= 0)))
+    return set_error(SDEO_EINVAL, "conv2d: folded GroupNorm needs statistics for every source and a plan without CTA pairs");
   p.ln_stats = (const float2*)a->ln_stats; p.ln_parts = a->ln_parts; p.ln_ld = a->ln_ld;
   p.ln_invc = a->ln_c > 0 ? 1.0f / (float)a->ln_c : 0.f; p.ln_eps = a->ln_eps; p.ln_csum = a->ln_csum;
   if (p.ln_stats && (!p.ln_csum || p.ln_parts <= 0 || a->ln_c <= 0))
@@ -1873,6 +2057,7 @@ static int launch_conv(const sdeo_conv_args* a, const ConvPlan& pl, void* stream
     } else if (stats_parts(a, pl) > 0) {
       p.gn_stats = (float2*)a->gn_stats;
 #define SDEO_PICK(O, R) if (out_kind == O && res_kind == R) fn = KSEL(SDEO_EPI_NORMAL, O, R, true, 1, false);
+      SDEO_PICK(OUT_BF16, RES_NONE) SDEO_PICK(OUT_BF16, RES_BF16) SDEO_PICK(OUT_BF16, RES_F32)
       SDEO_PICK(OUT_F32, RES_NONE) SDEO_PICK(OUT_F32, RES_BF16) SDEO_PICK(OUT_F32, RES_F32)
       SDEO_PICK(OUT_F32_TWIN, RES_NONE) SDEO_PICK(OUT_F32_TWIN, RES_BF16) SDEO_PICK(OUT_F32_TWIN, RES_F32)
 #undef SDEO_PICK

@@ -795,6 +795,56 @@ extern "C" int sdeo_groupnorm_apply_stats(const void* x1, const void* x2, int32_
                   parts2, gamma, beta, (__nv_bfloat16*)y, hw, c1, c2, groups, gslab, ppc, eps, with_silu);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Folds GroupNorm partial statistics [n][parts][c] (sdeo_conv_args::gn_stats) down to [n][out_parts][c], out_parts =
+// ceil(parts / 256): large feature maps leave thousands of partial slots per sample (one per 128-pixel M tile), too many
+// for every consumer CTA to fold on its own (folded GroupNorm, sdeo_conv_args::gnf_*). Fixed summation order.
+// grid: (32-channel slabs, out_parts, n); 256 threads = 8 slot lanes x 32 channels.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gn_stats_fold_kernel(const float2* __restrict__ st, float2* __restrict__ out, int parts, int out_parts, int c) {
+  griddep_launch_dependents();
+  griddep_wait();
+  __shared__ float2 sm[8][32];
+  const int cl = threadIdx.x & 31, pg = threadIdx.x >> 5;
+  const int ch = blockIdx.x * 32 + cl;
+  const int n = blockIdx.z, op = blockIdx.y;
+  const int k_lo = op * 256, k_hi = min(parts, k_lo + 256);
+  float s = 0.f, q = 0.f;
+  if (ch < c) {
+    const float2* src = st + ((size_t)n * parts) * c + ch;
+    int k = k_lo + pg;
+    for (; k + 24 < k_hi; k += 32) {  // 4 independent loads in flight, added in slot order
+      const float2 a0 = __ldcg(src + (size_t)k * c), a1 = __ldcg(src + (size_t)(k + 8) * c);
+      const float2 a2 = __ldcg(src + (size_t)(k + 16) * c), a3 = __ldcg(src + (size_t)(k + 24) * c);
+      s += a0.x; q += a0.y; s += a1.x; q += a1.y; s += a2.x; q += a2.y; s += a3.x; q += a3.y;
+    }
+    for (; k < k_hi; k += 8) {
+      const float2 a0 = __ldcg(src + (size_t)k * c);
+      s += a0.x; q += a0.y;
+    }
+  }
+  sm[pg][cl] = make_float2(s, q);
+  __syncthreads();
+  if (pg == 0 && ch < c) {
+    float ts = 0.f, tq = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ts += sm[j][cl].x; tq += sm[j][cl].y; }
+    out[((size_t)n * out_parts + op) * c + ch] = make_float2(ts, tq);
+  }
+}
+
+extern "C" int sdeo_gn_stats_fold(const float* stats, float* out, int32_t n, int32_t parts, int32_t c, int32_t* out_parts,
+                                  void* stream) {
+  if (n <= 0 || parts <= 0 || c <= 0 || n > 65535) return set_error(SDEO_EINVAL, "gn_stats_fold: bad geometry");
+  const int op = (parts + 255) / 256;
+  if (out_parts) *out_parts = op;
+  if (!stats || !out) return SDEO_OK;  // geometry query
+  const dim3 grid((unsigned)((c + 31) / 32), (unsigned)op, (unsigned)n), one(1, 1, 1);
+  return launch_k("gn_stats_fold", gn_stats_fold_kernel, grid, dim3(256), 0, (cudaStream_t)stream, one, (const float2*)stats,
+                  (float2*)out, parts, op, c);
+}
+
 extern "C" int sdeo_layernorm(const void* x, int32_t x_f32, const float* gamma, const float* beta, void* y, int32_t rows,
                               int32_t c, float eps, void* stream) {
   if (!x || !gamma || !beta || !y) return set_error(SDEO_EINVAL, "layernorm: null argument");

@@ -247,7 +247,7 @@ class SpatialTransformer(nn.Module):
         b, c, h, w = x.shape
         x_in = x
         st = util.STREAM_FP32
-        t = self.proj_in.run(self.norm.run(x, silu=False), out_fp32=st, stream=st, row_stats=st)  # the token stream
+        t = self.proj_in.run(self.norm.run(x, silu=False, defer=True), out_fp32=st, stream=st, row_stats=st)  # the token stream
         tok = nhwc(t).reshape(b, h * w, t.shape[1])
         if getattr(t, "_sdeo_stream", False):  # [B,H,W,C] stream -> [B,T,C] stream (same memory), attributes carried over
             tok._sdeo_stream = True

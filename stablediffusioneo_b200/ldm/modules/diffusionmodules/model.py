@@ -23,7 +23,7 @@ class Upsample(nn.Module):
 
     def run(self, x):
         y = nchw_view(ops.upsample_nearest2x(nhwc(x)))
-        return self.conv.run(y) if self.with_conv else y
+        return self.conv.run(y, gn_stats=True) if self.with_conv else y
 
     def forward(self, x):
         if is_internal(x):
@@ -43,7 +43,7 @@ class Downsample(nn.Module):
         self.conv = Conv2d(in_channels, in_channels, kernel_size=3, stride=2, padding=0)
 
     def run(self, x):
-        return self.conv.run(x, pad_hi=1)
+        return self.conv.run(x, pad_hi=1, gn_stats=True)
 
     def forward(self, x):
         if is_internal(x):
@@ -71,10 +71,10 @@ class ResnetBlock(nn.Module):
             self.nin_shortcut = Conv2d(in_channels, out_channels, kernel_size=1, stride=1, padding=0)
 
     def run(self, x, temb=None):
-        h = self.conv1.run(self.norm1.run(x, silu=True))
-        h = self.norm2.run(h, silu=True)
+        h = self.conv1.run(self.norm1.run(x, silu=True, defer=True), gn_stats=True)
+        h = self.norm2.run(h, silu=True, defer=True)
         skip = self.nin_shortcut.run(x) if self.in_channels != self.out_channels else x
-        return self.conv2.run(h, residual=skip)
+        return self.conv2.run(h, residual=skip, gn_stats=True)
 
     def forward(self, x, temb=None):
         if is_internal(x):
@@ -128,7 +128,7 @@ class AttnBlock(nn.Module):
             p = ops.softmax_rows(s, scale)                            # bf16
             v_as_filter = ops.PackedWeight(vt[i], c, 1, t, 0)         # rows = channels, K = keys
             ops.conv2d(p.reshape(1, 1, t, t), v_as_filter, out=o[i].reshape(1, 1, t, c))
-        return self.proj_out.run(nchw_view(o.reshape(b, h, w, c)), residual=x)
+        return self.proj_out.run(nchw_view(o.reshape(b, h, w, c)), residual=x, gn_stats=True)
 
     def forward(self, x):
         if is_internal(x):
@@ -192,7 +192,7 @@ class Encoder(nn.Module):
 
     def run(self, x):
         """model.py:514-543 on internal tensors (the reference's `hs` list only ever reads its last element)."""
-        h = self.conv_in.run(x)
+        h = self.conv_in.run(x, gn_stats=True)
         for i_level in range(self.num_resolutions):
             for i_block in range(self.num_res_blocks):
                 h = self.down[i_level].block[i_block].run(h)
@@ -203,7 +203,7 @@ class Encoder(nn.Module):
         h = self.mid.block_1.run(h)
         h = self.mid.attn_1.run(h)
         h = self.mid.block_2.run(h)
-        return self.conv_out.run(self.norm_out.run(h, silu=True))
+        return self.conv_out.run(self.norm_out.run(h, silu=True, defer=True))
 
     def forward(self, x):
         if is_internal(x):
@@ -258,7 +258,7 @@ class Decoder(nn.Module):
 
     def run(self, z):
         """model.py:619-652 on internal tensors. Returns an internal tensor with out_ch (padded to 8) channels."""
-        h = self.conv_in.run(z)
+        h = self.conv_in.run(z, gn_stats=True)
         h = self.mid.block_1.run(h)
         h = self.mid.attn_1.run(h)
         h = self.mid.block_2.run(h)
@@ -269,7 +269,7 @@ class Decoder(nn.Module):
                     h = self.up[i_level].attn[i_block].run(h)
             if i_level != 0:
                 h = self.up[i_level].upsample.run(h)
-        return self.conv_out.run(self.norm_out.run(h, silu=True))
+        return self.conv_out.run(self.norm_out.run(h, silu=True, defer=True))
 
     def forward(self, z):
         self.last_z_shape = z.shape

@@ -177,15 +177,18 @@ class ResBlock(TimestepBlock):
 
     def run(self, x, emb):
         """x: internal tensor or CatPair (decoder blocks); emb: bf16 [N, emb_channels]."""
-        h = self.in_layers[0].run(x, silu=True)
+        h = self.in_layers[0].run(x, silu=True, defer=True)   # folded into in_layers[2]'s operand path when it can be
         emb_step = None
         if isinstance(emb, StepEmb):
             emb_out, emb_step = emb.tables[id(self)], emb.step_ctr          # fp32 [S, Cout], row = DDIM step
         else:
             emb_out = self.emb_layers[1].run(silu_of(emb), out_fp32=True)   # fp32 [N, Cout]
         # GEMM results that feed a normalisation or a residual add stay fp32 (no extra bf16 rounding in the branch)
-        h = self.in_layers[2].run(h, emb=emb_out, emb_step=emb_step, out_fp32=util.STREAM_FP32, gn_stats=True)
-        h = self.out_layers[0].run(h, silu=True)
+        # (with the GroupNorm folded into the consumer, h is only ever read as a bf16 operand: written once, in bf16, with
+        #  its statistics taken from the fp32 accumulators)
+        fold = util.FOLD_GN and util.FUSE_GN_STATS
+        h = self.in_layers[2].run(h, emb=emb_out, emb_step=emb_step, out_fp32=util.STREAM_FP32 and not fold, gn_stats=True)
+        h = self.out_layers[0].run(h, silu=True, defer=True)
         if isinstance(self.skip_connection, nn.Identity):
             assert not isinstance(x, CatPair)
             skip = x
@@ -294,7 +297,7 @@ class UNetModel(nn.Module):
 
     def run_out(self, h, out_fp32=True):
         """out: GroupNorm32 + SiLU + conv3x3 (openaimodel.py:728-732). fp32 NHWC-physical result by default."""
-        return self.out[2].run(self.out[0].run(h, silu=True), out_fp32=out_fp32)
+        return self.out[2].run(self.out[0].run(h, silu=True, defer=True), out_fp32=out_fp32)
 
     def run(self, x, emb, context):
         hs = []

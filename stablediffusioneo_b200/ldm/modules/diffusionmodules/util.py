@@ -47,6 +47,40 @@ FUSE_GN_STATS = not os.environ.get("SDEO_NO_GN_STATS")
 # on the raw bf16 input with gamma folded into its weight and corrects acc -> rstd * (acc - mean * colsum) + bias' in its
 # epilogue. SDEO_NO_LN_FOLD=1 restores the standalone LayerNorm pass.
 FOLD_LN = not os.environ.get("SDEO_NO_LN_FOLD")
+# GroupNorms whose input carries its producers' partial statistics and whose consumer is a convolution are folded into that
+# convolution's operand path (sdeo_conv_args::gnf_*): no GroupNorm launch, no normalised tensor in memory; the conv reads
+# the RAW bf16 tensor (an fp32 stream's bf16 twin). SDEO_NO_GN_FOLD=1 restores the standalone apply pass.
+FOLD_GN = not os.environ.get("SDEO_NO_GN_FOLD")
+
+
+class DeferredGN:
+    """GroupNorm(x) (+ SiLU) that has not been computed: the raw input (internal tensor or CatPair), the module, the
+    activation flag. Conv2d.run folds it into its operand path; `.value()` materialises it for anything else."""
+
+    def __init__(self, x, gn, silu):
+        self.x, self.gn, self.silu = x, gn, silu
+
+    @property
+    def shape(self):
+        return self.x.shape
+
+    def value(self):
+        return self.gn.run(self.x, silu=self.silu)
+
+    def fold(self):
+        """(x1, x2 or None, ops.GnFold) with the raw bf16 operands in NHWC."""
+        gn = self.gn
+        if isinstance(self.x, CatPair):
+            a, b = self.x.a, self.x.b
+            n = a.shape[0]
+            sa = ops.gn_stats_fold(a._gn_stats, n, a.shape[1])
+            sb = ops.gn_stats_fold(b._gn_stats, n, b.shape[1])
+            return nhwc(operand(a)), nhwc(operand(b)), ops.GnFold(sa, sb, gn.weight.detach(), gn.bias.detach(),
+                                                                   gn.num_groups, gn.eps, self.silu)
+        x = self.x
+        st = ops.gn_stats_fold(x._gn_stats, x.shape[0], x.shape[1])
+        return nhwc(operand(x)), None, ops.GnFold(st, None, gn.weight.detach(), gn.bias.detach(), gn.num_groups, gn.eps,
+                                                   self.silu)
 
 
 class DeferredLN:
@@ -235,6 +269,9 @@ class Conv2d(nn.Conv2d):
         res = nhwc(residual) if residual is not None else None
         out = None
         cout = self.out_channels
+        gnf = None
+        if isinstance(x, DeferredGN):
+            x1, x2, gnf = x.fold()
         if not (out_fp32 or stream) and cout % 8 != 0:
             assert residual is None
             n, _, h, w = x.shape
@@ -245,9 +282,11 @@ class Conv2d(nn.Conv2d):
             ops.memset(out, 0)
         kw = dict(bias=self.bias_f32(), emb=emb, residual=res, scale=scale, act=act, stride=self.stride[0],
                   out_fp32=out_fp32 or stream, out=out, twin=stream, emb_step=emb_step, pad_hi=pad_hi,
-                  gn_stats=gn_stats and (out_fp32 or stream) and FUSE_GN_STATS,
+                  gn_stats=gn_stats and (out_fp32 or stream or FOLD_GN) and FUSE_GN_STATS,
                   row_stats=row_stats and (out_fp32 or stream) and FOLD_LN)
-        if isinstance(x, CatPair):
+        if gnf is not None:
+            y = ops.conv2d(x1, self.packed((x1.shape[3], x2.shape[3])) if x2 is not None else self.packed(), x2=x2, gnf=gnf, **kw)
+        elif isinstance(x, CatPair):
             a, b = operand(x.a), operand(x.b)
             y = ops.conv2d(nhwc(a), self.packed((a.shape[1], b.shape[1])), x2=nhwc(b), **kw)
         else:
@@ -300,7 +339,16 @@ class GroupNorm32(nn.GroupNorm):
     (the groupNormPlugin bSwish contract, groupNormPlugin.cpp:291-304). Accepts a CatPair (concat seam may fall
     inside a group)."""
 
-    def run(self, x, silu=False):
+    def run(self, x, silu=False, defer=False):
+        """defer=True (the caller hands the result straight to a Conv2d.run): a DeferredGN when the input carries its
+        producers' statistics -- the convolution then applies the normalisation inside its operand path."""
+        if defer and FOLD_GN and FUSE_GN_STATS and self.affine:
+            parts = (x.a, x.b) if isinstance(x, CatPair) else (x,)
+            # (K chunks of 64 channels per source: the first of two sources must fill its chunks)
+            ok = all(getattr(p_, "_gn_stats", None) is not None and
+                     (p_.dtype == BF16 or getattr(p_, "_twin", None) is not None) for p_ in parts)
+            if ok and (len(parts) == 1 or parts[0].shape[1] % 64 == 0):
+                return DeferredGN(x, self, silu)
         if isinstance(x, CatPair):
             a, b = x.a, x.b
             sa, sb = getattr(a, "_gn_stats", None), getattr(b, "_gn_stats", None)

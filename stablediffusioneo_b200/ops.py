@@ -143,7 +143,7 @@ def pack_geglu_bias(bias, geglu_bn):
 
 def conv2d(x, pw, x2=None, bias=None, emb=None, residual=None, scale=1.0, act=SDEO_ACT_NONE, stride=1, out=None,
            out_fp32=False, epi_mode=SDEO_EPI_NORMAL, qkv=None, twin=False, emb_step=None, gn_stats=False, row_stats=False,
-           ln=None, pad_hi=0):
+           ln=None, pad_hi=0, gnf=None):
     """x: [N,H,W,C1] bf16 (+ optional x2 [N,H,W,C2] = fused torch.cat along channels). Returns [N,Ho,Wo,cout].
     residual may be bf16 or fp32. out_fp32 + twin=True additionally writes a bf16 copy and returns (y_f32, y_bf16).
     emb: fp32 [N, cout] (row = sample), or with emb_step (int32 device scalar) a table [S, cout] whose row *emb_step is
@@ -152,6 +152,8 @@ def conv2d(x, pw, x2=None, bias=None, emb=None, residual=None, scale=1.0, act=SD
     per sample)` when the kernel produced them (see groupnorm(stats=...)). row_stats (fp32 outputs feeding a LayerNorm):
     per-row partial statistics, attached as `_row_stats = (buffer, parts, rows)`. ln: LnFold -- this GEMM applies a
     LayerNorm to its input rows in the epilogue (x is the raw bf16 input; pw / bias carry gamma / beta).
+    gnf: GnFold -- a GroupNorm (+ SiLU) applied to the RAW bf16 x (| x2) inside the operand path of this convolution
+    (statistics from the producers' epilogues); gn_stats then also works with a bf16 output.
     pad_hi=1 (3x3, stride 2): no leading padding, one trailing zero row / column = F.pad(x, (0,1,0,1)) + conv(padding=0),
     the VAE encoder's Downsample (model.py:78-84)."""
     lib = _lib.load()
@@ -220,6 +222,15 @@ def conv2d(x, pw, x2=None, bias=None, emb=None, residual=None, scale=1.0, act=SD
         a.ln_stats, a.ln_parts, a.ln_ld = _ptr(ln.stats), ln.parts, ln.rows
         a.ln_c, a.ln_eps, a.ln_csum = ln.c, float(ln.eps), _ptr(ln.csum)
         assert ln.rows == n * ho * wo and ln.c == c1 and c2 == 0
+    if gnf is not None:
+        assert ln is None and gnf.gamma.numel() == c1 + c2 and (x2 is None) == (gnf.stats2 is None)
+        _req(gnf.gamma, torch.float32, "gnf.gamma")
+        _req(gnf.beta, torch.float32, "gnf.beta")
+        a.gnf_stats1, a.gnf_parts1 = _ptr(gnf.stats1[0]), gnf.stats1[1]
+        if x2 is not None:
+            a.gnf_stats2, a.gnf_parts2 = _ptr(gnf.stats2[0]), gnf.stats2[1]
+        a.gnf_gamma, a.gnf_beta = _ptr(gnf.gamma), _ptr(gnf.beta)
+        a.gnf_groups, a.gnf_eps, a.gnf_silu = gnf.groups, float(gnf.eps), 1 if gnf.silu else 0
     rows_buf = None
     if row_stats and out_fp32 and epi_mode == SDEO_EPI_NORMAL:
         mx = ctypes.c_int32(0)
@@ -228,7 +239,7 @@ def conv2d(x, pw, x2=None, bias=None, emb=None, residual=None, scale=1.0, act=SD
         a.row_stats, a.row_stats_ld = _ptr(rows_buf), n * ho * wo
         gn_stats = False
     stats_buf = None
-    if gn_stats and out_fp32 and epi_mode == SDEO_EPI_NORMAL:
+    if gn_stats and epi_mode == SDEO_EPI_NORMAL and (out_fp32 or out.shape[3] % 8 == 0):
         mx = ctypes.c_int32(0)
         _check(lib.sdeo_conv_gn_stats_slots(ctypes.byref(a), ctypes.byref(mx), None), "conv_gn_stats_slots")
         stats_buf = torch.empty((mx.value, pw.cout, 2), dtype=torch.float32, device=x.device)
@@ -245,6 +256,35 @@ def conv2d(x, pw, x2=None, bias=None, emb=None, residual=None, scale=1.0, act=SD
         if parts.value > 0:
             out._row_stats = (rows_buf, parts.value, n * ho * wo)
     return (out, out2) if twin else out
+
+
+GN_FOLD_MAX_PARTS = 48   # more partial slots per sample than this are folded by one small kernel first
+
+
+def gn_stats_fold(stats, n, c):
+    """(buffer, parts) of GroupNorm partial statistics -> the same with parts <= GN_FOLD_MAX_PARTS (sdeo_gn_stats_fold)."""
+    lib = _lib.load()
+    buf, parts = stats
+    while parts > GN_FOLD_MAX_PARTS:
+        op = ctypes.c_int32(0)
+        _check(lib.sdeo_gn_stats_fold(None, None, n, parts, c, ctypes.byref(op), None), "gn_stats_fold")
+        out = torch.empty((n * op.value, c, 2), dtype=torch.float32, device=buf.device)
+        check(lib.sdeo_gn_stats_fold(_ptr(buf), _ptr(out), n, parts, c, ctypes.byref(op), _stream()), "gn_stats_fold")
+        buf, parts = out, op.value
+    return buf, parts
+
+
+@dataclass
+class GnFold:
+    """A GroupNorm (+ SiLU) folded into the convolution that consumes it: the producers' partial statistics
+    ((buffer, parts per sample) for x and x2), affine parameters of the virtual concat, group count, eps."""
+    stats1: tuple
+    stats2: object
+    gamma: torch.Tensor
+    beta: torch.Tensor
+    groups: int
+    eps: float
+    silu: bool
 
 
 @dataclass

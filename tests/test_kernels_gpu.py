@@ -430,6 +430,97 @@ def test_groupnorm_from_conv_statistics(cuda_device, case, autotune):
     assert rel_l2(y_fused, y_plain) < 2e-3   # same math, different fp32 summation order (+ bf16 rounding flips)
 
 
+GNF_CASES = [
+    # (n, c_a, c_b, cout, h, w, k, silu, halo)   producer convs -> GroupNorm(+SiLU) folded into the consumer conv
+    (2, 320, 0, 320, 32, 48, 3, True, 1),       # ResBlock in_layers at the top level, HALO tiling
+    (2, 320, 0, 320, 32, 48, 3, True, 0),       # ... tap-by-tap tiling (padding rows depend on the tap)
+    (2, 320, 0, 320, 32, 48, 1, False, 0),      # SpatialTransformer norm -> proj_in (no SiLU)
+    (2, 640, 320, 320, 32, 48, 3, True, 1),     # decoder block: GroupNorm over a concat (30 channels per group), HALO
+    (2, 640, 320, 320, 32, 48, 3, True, 0),
+    (2, 1280, 1280, 1280, 8, 12, 3, True, 0),   # split-K cluster, 96-row tiles, concat 2560 channels
+    (2, 1280, 0, 1280, 4, 6, 3, True, 0),       # tile box spans the batch: one table row per sample of the tile
+    (2, 1280, 1280, 1280, 4, 6, 3, True, 0),
+    (1, 96, 0, 96, 20, 28, 3, True, 1),         # ragged tiles, 3 channels per group, K padding (96 -> 128)
+    (1, 96, 0, 96, 20, 28, 3, True, 0),
+    (3, 64, 0, 48, 5, 7, 3, True, 0),           # odd everything
+    (1, 128, 0, 128, 64, 96, 3, True, 1),       # VAE ResnetBlock shape
+    (2, 320, 0, 4, 32, 48, 3, True, 0),         # UNet out: GroupNorm + SiLU + conv to 4 channels (masked epilogue)
+]
+
+
+@pytest.mark.parametrize("stream_in", [True, False])
+@pytest.mark.parametrize("case", GNF_CASES)
+def test_conv2d_folded_groupnorm(cuda_device, case, stream_in):
+    """producer conv(s) (epilogue statistics) -> consumer conv with the GroupNorm (+ SiLU) folded into its operand path,
+    against F.group_norm + F.silu + F.conv2d in fp32 on the very bf16 tensor(s) the consumer reads (the fp32 stream's
+    bf16 twin, or a bf16 output). The normalised operand is bf16 in both (the reference rounds it like the kernel does)."""
+    from stablediffusioneo_b200 import ops
+    n, ca, cb, cout, h, w, k, silu, halo = case
+    dev = cuda_device
+    srcs = []
+    for i, c in enumerate([ca, cb] if cb else [ca]):
+        x = gen((n, c, h, w), 1 + i, dev)
+        pk = 3 if n * h * w <= 128 else 1   # (tiny maps: a tile spans samples; only a split-K producer leaves statistics)
+        wt = gen((c, c, pk, pk), 10 + i, dev) / math.sqrt(c * pk * pk)
+        bias = gen((c,), 20 + i, dev) * 0.3
+        if stream_in:
+            y, twin = ops.conv2d(nhwc(x), ops.pack_conv_weight(wt), bias=bias, out_fp32=True, twin=True, gn_stats=True)
+            st = getattr(y, "_gn_stats", None)
+        else:
+            twin = ops.conv2d(nhwc(x), ops.pack_conv_weight(wt), bias=bias, gn_stats=True)
+            st = getattr(twin, "_gn_stats", None)
+        if st is None:
+            pytest.skip("this producer geometry leaves no statistics (M tile spans samples without K slices)")
+        srcs.append((twin, st))
+    ctot = ca + cb
+    gamma = gen((ctot,), 3, dev) * 0.2 + 1.0
+    beta = gen((ctot,), 4, dev) * 0.2
+    wt = gen((cout, ctot, k, k), 5, dev) / math.sqrt(ctot * k * k)
+    bias = gen((cout,), 6, dev) * 0.1
+    pw = ops.pack_conv_weight(wt, c1=ca, c2=cb) if cb else ops.pack_conv_weight(wt)
+    gnf = ops.GnFold(srcs[0][1], srcs[1][1] if cb else None, gamma, beta, 32, 1e-5, silu)
+    os.environ["SDEO_HALO"] = str(halo)
+    try:
+        y = ops.conv2d(srcs[0][0], pw, x2=srcs[1][0] if cb else None, bias=bias, out_fp32=True, gnf=gnf)
+    finally:
+        os.environ.pop("SDEO_HALO", None)
+    full = torch.cat([t.float() for t, _ in srcs], 3).permute(0, 3, 1, 2)
+    hn = F.group_norm(full, 32, gamma, beta, 1e-5)
+    if silu:
+        hn = F.silu(hn)
+    ref = F.conv2d(bf16r(hn), bf16r(wt), bias, padding=1 if k == 3 else 0)
+    err = rel_l2(y.permute(0, 3, 1, 2), ref)
+    assert err < TOL, err
+    # and the same through the standalone GroupNorm kernel + plain conv (what the fold replaces)
+    hn2 = ops.groupnorm(srcs[0][0], gamma, beta, 1e-5, silu, x2=srcs[1][0] if cb else None)
+    pw1 = ops.pack_conv_weight(wt)
+    y2 = ops.conv2d(hn2, pw1, bias=bias, out_fp32=True)
+    assert rel_l2(y, y2) < 3e-3
+
+
+def test_conv2d_folded_groupnorm_many_parts(cuda_device):
+    """A large feature map leaves hundreds of partial slots per sample: ops.gn_stats_fold reduces them first."""
+    from stablediffusioneo_b200 import ops
+    dev = cuda_device
+    n, c, h, w = 2, 128, 192, 256
+    x = gen((n, c, h, w), 1, dev)
+    wt = gen((c, c, 3, 3), 10, dev) / math.sqrt(c * 9)
+    t = ops.conv2d(nhwc(x), ops.pack_conv_weight(wt), gn_stats=True)
+    st = t._gn_stats
+    assert st[1] > ops.GN_FOLD_MAX_PARTS
+    st2 = ops.gn_stats_fold(st, n, c)
+    assert st2[1] <= ops.GN_FOLD_MAX_PARTS
+    full = st[0][:n * st[1]].reshape(n, st[1], c, 2).sum(1)
+    assert torch.allclose(st2[0][:n * st2[1]].reshape(n, st2[1], c, 2).sum(1), full, rtol=1e-5, atol=1e-3)
+    gamma = gen((c,), 3, dev) * 0.2 + 1.0
+    beta = gen((c,), 4, dev) * 0.2
+    w2 = gen((c, c, 3, 3), 5, dev) / math.sqrt(c * 9)
+    y = ops.conv2d(t, ops.pack_conv_weight(w2), gnf=ops.GnFold(st2, None, gamma, beta, 32, 1e-6, True))
+    hn = F.silu(F.group_norm(t.float().permute(0, 3, 1, 2), 32, gamma, beta, 1e-6))
+    ref = F.conv2d(bf16r(hn), bf16r(w2), None, padding=1)
+    assert rel_l2(y.permute(0, 3, 1, 2), ref) < TOL
+
+
 def test_groupnorm_statistics_every_tile_config(cuda_device):
     """The fused statistics under every (N tile, K slices) configuration the planner / autotuner can pick, forced
     through SDEO_FORCE_BN / SDEO_FORCE_SPLITS (N tile 256 carries 512 statistics values for 384 threads)."""

@@ -57,6 +57,10 @@ for name, combo in [(n_, c_) for n_ in names for c_ in combos]:
         print(f"   not available: {ex}")
         continue
     torch.cuda.synchronize()
+    if opts.get("cold"):   # weights (and everything else) out of L2: inside the step every layer's weights come from HBM
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        flush.fill_(1)
+        torch.cuda.synchronize()
     os.environ["SDEO_CONV_DEBUG"] = hex(dbg.data_ptr())
     ops.conv2d(x, pw, **kw)
     torch.cuda.synchronize()
