@@ -453,6 +453,219 @@ __device__ __forceinline__ bool tile_row_coords(const ConvKParams& p, int row, i
   return (row < p.rows_valid) && (*nn < p.N) && (*hh < p.Ho) && (*ww < p.Wo);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Folded GroupNorm (sdeo_conv_args::gnf_*), run by warps 2..8 during the mainloop: fold the producers' partial statistics
+// into the (a, b) table, then normalise every A tile that lands, in place. A separate (not inlined) function: inlined, its
+// register pressure and code size changed the allocation of the whole kernel body (every conv launch, folded GroupNorm
+// or not, ran 3-20% slower).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __noinline__ void gnf_transform_warps(const ConvKParams& p, uint8_t* smem, uint8_t* tiles, float2* ln_vec,
+                                                 uint64_t* full_bar, uint64_t* full_a, uint64_t* xf_bar, uint64_t* xf_a,
+                                                 int k_begin, int k_end, int nchunks, int stage_bytes, int n0, int h0, int w0) {
+  const int lane = threadIdx.x & 31;
+  {
+    // ===================== folded GroupNorm: statistics -> (a, b) table, then every A tile in place =====================
+    const int t = (int)threadIdx.x - 64;
+    const int Cp = p.chunks_per_tap * 64;                 // one entry per K position of a tap (padded channels)
+    // table row of one sample: entry of channel c at float2 index (c / 8) * 10 + c % 8 -- 8-channel vectors 80 bytes apart,
+    // so that the eight vectors a quarter-warp reads lie in different banks
+    const int Cpp = (Cp / 8) * 10;
+    float2* ab = reinterpret_cast<float2*>(smem + p.gnf_off);   // [bn_][Cpp]: first (sum, sum of squares), then (a, b)
+    float2* gst = ab + (size_t)p.bn_ * Cpp;                     // [bn_][groups] (mean, rstd)
+    const int C = p.gnf_c1 + p.gnf_c2;
+    const int n_entries = p.bn_ * Cp;
+    // tile row -> input position table (shares the folded-LayerNorm row vector's space: the two never meet)
+    int* row_hw = reinterpret_cast<int*>(ln_vec);           // tap-by-tap: (sample << 16 | h << 8 | w) inside the tile, -1 = none
+    uint8_t* halo_ok = reinterpret_cast<uint8_t*>(ln_vec);  // HALO: halo position lies inside the input
+    const int halo_rows = (p.bh + 2) * p.hpitch;
+    if (p.halo) {
+      for (int r = t; r < halo_rows; r += kGnfThreads) {
+        const int hy = r / p.hpitch, hx = r - hy * p.hpitch;
+        const int hh = h0 - 1 + hy, ww = w0 - 1 + hx;
+        halo_ok[r] = (hh >= 0 && hh < p.Hin && ww >= 0 && ww < p.Win && n0 < p.N) ? 1 : 0;
+      }
+    } else {
+      const int per_img = p.bh * p.bw;
+      for (int r = t; r < kBM; r += kGnfThreads) {
+        const int nl = r / per_img, rem = r - nl * per_img;
+        const int hl = rem / p.bw, wl = rem - hl * p.bw;
+        row_hw[r] = (r < p.rows_valid && n0 + nl < p.N) ? ((nl << 16) | (hl << 8) | wl) : -1;
+      }
+    }
+    // 1. per-channel (sum, sum of squares): the producers' partial slots, added in slot order (deterministic). The fold sits
+    // in front of the first MMA and every batch of loads is an L2 round trip: four table entries x eight slots in flight
+    for (int idx0 = t; idx0 < n_entries; idx0 += 4 * kGnfThreads) {
+      const float2* src[4];
+      int parts[4], ld[4], slot[4];
+      float sum[4], sq[4];
+      int max_parts = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int idx = idx0 + e * kGnfThreads;
+        src[e] = nullptr; parts[e] = 0; ld[e] = 0; slot[e] = -1; sum[e] = 0.f; sq[e] = 0.f;
+        if (idx < n_entries) {
+          const int nl = idx / Cp, c = idx - nl * Cp;
+          const int n = n0 + nl;
+          slot[e] = nl * Cpp + (c >> 3) * 10 + (c & 7);
+          if (c < C && n < p.N) {
+            const bool first = c < p.gnf_c1;
+            parts[e] = first ? p.gnf_parts1 : p.gnf_parts2;
+            ld[e] = first ? p.gnf_c1 : p.gnf_c2;
+            src[e] = first ? p.gnf_st1 + (size_t)n * parts[e] * ld[e] + c : p.gnf_st2 + (size_t)n * parts[e] * ld[e] + (c - p.gnf_c1);
+            max_parts = max(max_parts, parts[e]);
+          }
+        }
+      }
+      for (int k = 0; k < max_parts; k += 8) {
+        float2 v[4][8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            v[e][u] = (k + u < parts[e]) ? __ldcg(src[e] + (size_t)(k + u) * ld[e]) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { sum[e] += v[e][u].x; sq[e] += v[e][u].y; }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (slot[e] >= 0) ab[slot[e]] = make_float2(sum[e], sq[e]);
+    }
+    bar_sync(1, kGnfThreads);
+    // 2. (mean, rstd) of every (sample of the tile, group)
+    for (int idx = t; idx < p.bn_ * p.gnf_groups; idx += kGnfThreads) {
+      const int nl = idx / p.gnf_groups, g = idx - nl * p.gnf_groups;
+      float sum = 0.f, sq = 0.f;
+      for (int j = 0, c = g * p.gnf_cpg; j < p.gnf_cpg; ++j, ++c) {
+        const float2 v = ab[nl * Cpp + (c >> 3) * 10 + (c & 7)];
+        sum += v.x; sq += v.y;
+      }
+      const float mean = sum * p.gnf_inv;
+      float var = sq * p.gnf_inv - mean * mean;
+      var = var < 0.f ? 0.f : var;
+      gst[idx] = make_float2(mean, rsqrtf(var + p.gnf_eps));
+    }
+    bar_sync(1, kGnfThreads);
+    // 3. y = a * x + b per (sample, channel); channels beyond the tensor (K padding) stay finite: the weights there are zero
+    for (int idx = t; idx < n_entries; idx += kGnfThreads) {
+      const int nl = idx / Cp, c = idx - nl * Cp;
+      float2 v = make_float2(0.f, 0.f);
+      if (c < C) {
+        const float2 mr = gst[nl * p.gnf_groups + c / p.gnf_cpg];
+        v.x = __ldg(p.gnf_gamma + c) * mr.y;
+        v.y = __ldg(p.gnf_beta + c) - mr.x * v.x;
+      }
+      ab[nl * Cpp + (c >> 3) * 10 + (c & 7)] = v;
+    }
+    bar_sync(1, kGnfThreads);
+    if (t == 0) SDEO_DBG(2);
+    const bool with_silu = p.gnf_silu != 0;
+    long long dbg_x = 0;
+    // One 16-byte unit = 8 channels of one tile row. Thread t owns the LOGICAL 8-channel vector lu = t % 8 of rows
+    // t / 8, t / 8 + 28, ...: inside a 128B-swizzled tile that vector sits at physical position lu ^ (row % 8), so a warp
+    // still touches four whole 128-byte rows per access (no bank conflicts), and with one sample per tile the thread's
+    // sixteen (a, b) values are loaded ONCE per tile into registers instead of once per unit (the table reads were four
+    // times the tile's own bytes and bank-conflicted: measured 3400 cycles per 16 KB tile before, ...). Rows are handled kU
+    // at a time: all loads of a batch are issued before the first value is used.
+    constexpr int kU = 4;
+    constexpr int kRowStep = kGnfThreads / 8;   // 28
+    const uint32_t lu = (uint32_t)t & 7u;
+    const int r0 = t >> 3;
+    const bool one_sample = p.bn_ == 1;
+    auto xform_tile = [&](uint32_t base, int rows, const float2* abk, auto&& row_of) {
+      // row_of(row) -> table row offset (in float2) of the row's sample, or -1: the row stays as it is (zero padding)
+      float4 ab0, ab1, ab2, ab3;
+      if (one_sample) {
+        const float4* abp = reinterpret_cast<const float4*>(abk + lu * 10);
+        ab0 = abp[0]; ab1 = abp[1]; ab2 = abp[2]; ab3 = abp[3];
+      }
+      for (int rb = r0; rb < rows; rb += kU * kRowStep) {
+        uint4 raw[kU];
+        int off[kU];
+        uint32_t addr[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const int r = rb + u * kRowStep;
+          off[u] = (r < rows) ? row_of(r) : -1;
+          addr[u] = base + (uint32_t)r * 128u + ((lu ^ ((uint32_t)r & 7u)) << 4);
+          if (off[u] >= 0) asm("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(raw[u].x), "=r"(raw[u].y), "=r"(raw[u].z), "=r"(raw[u].w) : "r"(addr[u]) : "memory");
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          if (off[u] < 0) continue;
+          if (!one_sample) {
+            const float4* abp = reinterpret_cast<const float4*>(abk + off[u] + lu * 10);
+            ab0 = abp[0]; ab1 = abp[1]; ab2 = abp[2]; ab3 = abp[3];
+          }
+          const float2 x0 = unpack_bf16x2(raw[u].x), x1 = unpack_bf16x2(raw[u].y), x2 = unpack_bf16x2(raw[u].z), x3 = unpack_bf16x2(raw[u].w);
+          float y[8];
+          y[0] = fmaf(x0.x, ab0.x, ab0.y); y[1] = fmaf(x0.y, ab0.z, ab0.w);
+          y[2] = fmaf(x1.x, ab1.x, ab1.y); y[3] = fmaf(x1.y, ab1.z, ab1.w);
+          y[4] = fmaf(x2.x, ab2.x, ab2.y); y[5] = fmaf(x2.y, ab2.z, ab2.w);
+          y[6] = fmaf(x3.x, ab3.x, ab3.y); y[7] = fmaf(x3.y, ab3.z, ab3.w);
+          if (with_silu) {
+            // silu(y) = h + h * tanh(h), h = y / 2: ONE special-function op per element (tanh.approx, relative error 2^-11 --
+            // below the bf16 rounding of the result) where y / (1 + exp(-y)) takes two
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float hlf = 0.5f * y[j];
+              float th;
+              asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(hlf));
+              y[j] = fmaf(hlf, th, hlf);
+            }
+          }
+          st_smem_f4(addr[u], pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+        }
+      }
+    };
+    if (p.halo) {
+      const int c_first = k_begin / 9, c_last = (k_end - 1) / 9;
+      for (int c = c_first; c <= c_last; ++c) {
+        const int na = c - c_first, sa = na % p.a_stages;
+        // ONE thread polls the barrier and releases the other six warps through a named barrier: mbarrier.try_wait costs
+        // ~200 cycles per warp instruction even on a completed phase and the barrier unit serialises them (seven polling
+        // warps: measured ~1500 cycles per tile before the first byte was touched)
+        if (t == 0) mbar_wait(&full_a[sa], (uint32_t)((na / p.a_stages) & 1));
+        bar_sync(1, kGnfThreads);
+        const long long t_x0 = (p.dbg && t == 0) ? clock64() : 0;
+        xform_tile(smem_u32(tiles) + (uint32_t)(sa * p.a_stage_bytes), halo_rows, ab + c * 80,
+                   [&](int row) -> int { return halo_ok[row] ? 0 : -1; });
+        fence_proxy_async_smem();   // generic-proxy stores -> visible to the MMA's operand reads (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xf_a[sa]);
+        if (p.dbg && t == 0) dbg_x += clock64() - t_x0;
+      }
+    } else {
+      int s = 0;
+      uint32_t ph = 0;
+      int tap = k_begin / p.chunks_per_tap, within = k_begin % p.chunks_per_tap;
+      int ky = tap / p.kw, kx = tap % p.kw;
+      for (int i = 0; i < nchunks; ++i) {
+        if (t == 0) mbar_wait(&full_bar[s], ph);
+        bar_sync(1, kGnfThreads);
+        const long long t_x0 = (p.dbg && t == 0) ? clock64() : 0;
+        const int hb = h0 * p.stride + ky - p.pad, wb = w0 * p.stride + kx - p.pad;
+        xform_tile(smem_u32(tiles) + (uint32_t)(s * stage_bytes), p.rows_valid, ab + within * 80, [&](int row) -> int {
+          const int info = row_hw[row];
+          const int hh = hb + ((info >> 8) & 255) * p.stride, ww = wb + (info & 255) * p.stride;
+          return (info >= 0 && hh >= 0 && hh < p.Hin && ww >= 0 && ww < p.Win) ? (info >> 16) * Cpp : -1;
+        });
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xf_bar[s]);
+        if (p.dbg && t == 0) dbg_x += clock64() - t_x0;
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+        if (++within == p.chunks_per_tap) {
+          within = 0;
+          if (++kx == p.kw) { kx = 0; ++ky; }
+        }
+      }
+    }
+    if (p.dbg && t == 0) p.dbg[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + 15] = dbg_x;
+    }
+}
+
 // MODE: SDEO_EPI_*; OUT / RES: see enums above; FAST: vector-aligned NORMAL epilogue (else the generic item path).
 // STATS (NORMAL + FAST + fp32 output only): the epilogue also reduces the FINAL output values of this CTA's rows to
 // per-channel (sum, sum of squares) and writes them to p.gn_stats[(M tile * S + K-slice rank)][cout] -- the GroupNorm
@@ -877,145 +1090,8 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmA1, const CU
     }
   }
 
-  if (p.gnf && warp >= 2 && warp < 2 + kGnfWarps) {
-    // ===================== folded GroupNorm: statistics -> (a, b) table, then every A tile in place =====================
-    const int t = (int)threadIdx.x - 64;
-    const int Cp = p.chunks_per_tap * 64;                 // table row: one entry per K position of a tap (padded channels)
-    float2* ab = reinterpret_cast<float2*>(smem + p.gnf_off);   // [bn_][Cp]: first (sum, sum of squares), then (a, b)
-    float2* gst = ab + (size_t)p.bn_ * Cp;                      // [bn_][groups] (mean, rstd)
-    const int C = p.gnf_c1 + p.gnf_c2;
-    const int n_entries = p.bn_ * Cp;
-    // tile row -> input position table (shares the folded-LayerNorm row vector's space: the two never meet)
-    int* row_hw = reinterpret_cast<int*>(ln_vec);           // tap-by-tap: (sample << 16 | h << 8 | w) inside the tile, -1 = none
-    uint8_t* halo_ok = reinterpret_cast<uint8_t*>(ln_vec);  // HALO: halo position lies inside the input
-    const int halo_rows = (p.bh + 2) * p.hpitch;
-    if (p.halo) {
-      for (int r = t; r < halo_rows; r += kGnfThreads) {
-        const int hy = r / p.hpitch, hx = r - hy * p.hpitch;
-        const int hh = h0 - 1 + hy, ww = w0 - 1 + hx;
-        halo_ok[r] = (hh >= 0 && hh < p.Hin && ww >= 0 && ww < p.Win && n0 < p.N) ? 1 : 0;
-      }
-    } else {
-      const int per_img = p.bh * p.bw;
-      for (int r = t; r < kBM; r += kGnfThreads) {
-        const int nl = r / per_img, rem = r - nl * per_img;
-        const int hl = rem / p.bw, wl = rem - hl * p.bw;
-        row_hw[r] = (r < p.rows_valid && n0 + nl < p.N) ? ((nl << 16) | (hl << 8) | wl) : -1;
-      }
-    }
-    // 1. per-channel (sum, sum of squares): the producers' partial slots, added in slot order (deterministic)
-    for (int idx = t; idx < n_entries; idx += kGnfThreads) {
-      const int nl = idx / Cp, c = idx - nl * Cp;
-      const int n = n0 + nl;
-      float sum = 0.f, sq = 0.f;
-      if (c < C && n < p.N) {
-        const bool first = c < p.gnf_c1;
-        const int parts = first ? p.gnf_parts1 : p.gnf_parts2, ld = first ? p.gnf_c1 : p.gnf_c2;
-        const float2* src = first ? p.gnf_st1 + (size_t)n * parts * ld + c : p.gnf_st2 + (size_t)n * parts * ld + (c - p.gnf_c1);
-        int k = 0;
-        for (; k + 8 <= parts; k += 8) {   // 8 independent loads in flight
-          float2 a[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) a[u] = __ldcg(src + (size_t)(k + u) * ld);
-#pragma unroll
-          for (int u = 0; u < 8; ++u) { sum += a[u].x; sq += a[u].y; }
-        }
-        for (; k < parts; ++k) {
-          const float2 a0 = __ldcg(src + (size_t)k * ld);
-          sum += a0.x; sq += a0.y;
-        }
-      }
-      ab[idx] = make_float2(sum, sq);
-    }
-    bar_sync(1, kGnfThreads);
-    // 2. (mean, rstd) of every (sample of the tile, group)
-    for (int idx = t; idx < p.bn_ * p.gnf_groups; idx += kGnfThreads) {
-      const int nl = idx / p.gnf_groups, g = idx - nl * p.gnf_groups;
-      const float2* src = ab + (size_t)nl * Cp + g * p.gnf_cpg;
-      float sum = 0.f, sq = 0.f;
-      for (int j = 0; j < p.gnf_cpg; ++j) { sum += src[j].x; sq += src[j].y; }
-      const float mean = sum * p.gnf_inv;
-      float var = sq * p.gnf_inv - mean * mean;
-      var = var < 0.f ? 0.f : var;
-      gst[idx] = make_float2(mean, rsqrtf(var + p.gnf_eps));
-    }
-    bar_sync(1, kGnfThreads);
-    // 3. y = a * x + b per (sample, channel); channels beyond the tensor (K padding) stay finite: the weights there are zero
-    for (int idx = t; idx < n_entries; idx += kGnfThreads) {
-      const int nl = idx / Cp, c = idx - nl * Cp;
-      float2 v = make_float2(0.f, 0.f);
-      if (c < C) {
-        const float2 mr = gst[nl * p.gnf_groups + c / p.gnf_cpg];
-        v.x = __ldg(p.gnf_gamma + c) * mr.y;
-        v.y = __ldg(p.gnf_beta + c) - mr.x * v.x;
-      }
-      ab[idx] = v;
-    }
-    bar_sync(1, kGnfThreads);
-    if (t == 0) SDEO_DBG(2);
-    const bool with_silu = p.gnf_silu != 0;
-    // one 16-byte unit (8 channels of one tile row) at physical offset `off` inside a 128B-swizzled tile: the logical
-    // 8-channel index is the physical one XOR (row & 7) -- both are bits of the shared-memory address
-    auto xform_unit = [&](uint32_t addr, const float2* abrow) {
-      const uint32_t lu = ((addr >> 4) ^ (addr >> 7)) & 7u;
-      uint4 raw;
-      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w) : "r"(addr));
-      const float4* abp = reinterpret_cast<const float4*>(abrow + lu * 8);
-      const float4 ab0 = abp[0], ab1 = abp[1], ab2 = abp[2], ab3 = abp[3];
-      float2 x0 = unpack_bf16x2(raw.x), x1 = unpack_bf16x2(raw.y), x2 = unpack_bf16x2(raw.z), x3 = unpack_bf16x2(raw.w);
-      float y[8];
-      y[0] = fmaf(x0.x, ab0.x, ab0.y); y[1] = fmaf(x0.y, ab0.z, ab0.w);
-      y[2] = fmaf(x1.x, ab1.x, ab1.y); y[3] = fmaf(x1.y, ab1.z, ab1.w);
-      y[4] = fmaf(x2.x, ab2.x, ab2.y); y[5] = fmaf(x2.y, ab2.z, ab2.w);
-      y[6] = fmaf(x3.x, ab3.x, ab3.y); y[7] = fmaf(x3.y, ab3.z, ab3.w);
-      if (with_silu) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] = silu_f(y[j]);
-      }
-      st_smem_f4(addr, pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
-    };
-    if (p.halo) {
-      const int c_first = k_begin / 9, c_last = (k_end - 1) / 9;
-      const int units = halo_rows * 8;
-      for (int c = c_first; c <= c_last; ++c) {
-        const int na = c - c_first, sa = na % p.a_stages;
-        mbar_wait(&full_a[sa], (uint32_t)((na / p.a_stages) & 1));
-        const uint32_t base = smem_u32(tiles) + (uint32_t)(sa * p.a_stage_bytes);
-        const float2* abrow = ab + c * 64;
-        for (int q = t; q < units; q += kGnfThreads) {
-          if (halo_ok[q >> 3]) xform_unit(base + (uint32_t)q * 16u, abrow);
-        }
-        fence_proxy_async_smem();   // generic-proxy stores -> visible to the MMA's operand reads (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&xf_a[sa]);
-      }
-    } else {
-      const int units = p.rows_valid * 8;
-      int s = 0;
-      uint32_t ph = 0;
-      int tap = k_begin / p.chunks_per_tap, within = k_begin % p.chunks_per_tap;
-      int ky = tap / p.kw, kx = tap % p.kw;
-      for (int i = 0; i < nchunks; ++i) {
-        mbar_wait(&full_bar[s], ph);
-        const uint32_t base = smem_u32(tiles) + (uint32_t)(s * stage_bytes);
-        const int hb = h0 * p.stride + ky - p.pad, wb = w0 * p.stride + kx - p.pad;
-        for (int q = t; q < units; q += kGnfThreads) {
-          const int info = row_hw[q >> 3];
-          const int hh = hb + ((info >> 8) & 255) * p.stride, ww = wb + (info & 255) * p.stride;
-          if (info >= 0 && hh >= 0 && hh < p.Hin && ww >= 0 && ww < p.Win)
-            xform_unit(base + (uint32_t)q * 16u, ab + (size_t)(info >> 16) * Cp + within * 64);
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&xf_bar[s]);
-        if (++s == p.stages) { s = 0; ph ^= 1u; }
-        if (++within == p.chunks_per_tap) {
-          within = 0;
-          if (++kx == p.kw) { kx = 0; ++ky; }
-        }
-      }
-    }
-  }
+  if (p.gnf && warp >= 2 && warp < 2 + kGnfWarps)
+    gnf_transform_warps(p, smem, tiles, ln_vec, full_bar, full_a, xf_bar, xf_a, k_begin, k_end, nchunks, stage_bytes, n0, h0, w0);
 
   // ===================== epilogue phase 1: TMEM -> fp32 tile in shared memory, all 12 warps =====================
   // A warp may read the TMEM lane quarter (warp % 4); the three warps of a quarter split the columns in 32-wide
@@ -1318,13 +1394,15 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmA1, const CU
 template <int MODE, int OUT, int RES, bool FAST, int STATS, bool LNF, bool PAIR>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
-                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmR, const ConvKParams p) {
+                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmR,
+                 const __grid_constant__ ConvKParams p) {
   conv_gemm_body<MODE, OUT, RES, FAST, STATS, LNF, PAIR>(tmA1, tmA2, tmB, tmR, p);
 }
 template <int MODE, int OUT, int RES, bool FAST, int STATS, bool LNF, bool PAIR>
 __global__ void __launch_bounds__(kConvThreads, 2)
 conv_gemm_kernel_occ2(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
-                      const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmR, const ConvKParams p) {
+                      const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmR,
+                 const __grid_constant__ ConvKParams p) {
   conv_gemm_body<MODE, OUT, RES, FAST, STATS, LNF, PAIR>(tmA1, tmA2, tmB, tmR, p);
 }
 
@@ -1476,7 +1554,8 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl, int force_bn = 0, i
         if (tiles < h_tiles || (tiles == h_tiles && area < h_area)) { h_tiles = tiles; hbh = bh; hbw = bw; h_area = area; }
       }
       // the heuristic accepts up to 1/3 more M tiles than the tap-by-tap tiling (the A operand shrinks ~5x)
-      if (hbw > 0 && (want == 1 || 3LL * h_tiles <= 4LL * best_tiles)) {
+      // (a folded GroupNorm normalises every A tile it stages: once per chunk here, once per TAP and chunk otherwise)
+      if (hbw > 0 && (want == 1 || 3LL * h_tiles <= 4LL * best_tiles || (a->gnf_stats1 && 2LL * h_tiles <= 4LL * best_tiles))) {
         pl->halo = 1; pl->hpitch = hbw + 2;
         bbn = 1; bbh = hbh; bbw = hbw;
         best_tiles = h_tiles;
@@ -1610,7 +1689,7 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl, int force_bn = 0, i
     if (a->ln_stats || a->gnf_groups <= 0 || (a->c1 + (a->x2 ? a->c2 : 0)) % a->gnf_groups != 0 || !a->gnf_gamma || !a->gnf_beta ||
         (a->x2 && !a->gnf_stats2) || pl->bn_ > 128 || pl->bh > 255 || pl->bw > 255)
       return false;
-    pl->gnf_bytes = round_up(pl->bn_ * (pl->cpt * 64 + a->gnf_groups) * 8, 128);
+    pl->gnf_bytes = round_up(pl->bn_ * (pl->cpt * 80 + a->gnf_groups) * 8, 128);   // (a, b) rows padded 8 -> 10 entries
   }
   const int gnf_bytes = pl->gnf_bytes;
   auto stages_for = [&](int extra0) {  // pipeline depth that fits next to `extra` bytes of residual buffer (+ the folded GroupNorm table)
@@ -1897,7 +1976,8 @@ extern "C" int sdeo_conv_gn_stats_slots(const sdeo_conv_args* a, int32_t* max_sl
       if (make_plan(a, &alt, 0, 0, halo) && alt.tiles_n * alt.tiles_h * alt.tiles_w > tiles)
         tiles = alt.tiles_n * alt.tiles_h * alt.tiles_w;
     }
-    *max_slots_total = tiles * kMaxCluster;
+    // (K slices only exist where all CTAs of the launch fit one wave: see make_plan and the autotuner's candidate filter)
+    *max_slots_total = tiles * ((tiles > 148 && !getenv("SDEO_FORCE_SPLITS")) ? 1 : kMaxCluster);
   }
   if (parts_per_sample) {
     sdeo_conv_args b = *a;

@@ -47,10 +47,20 @@ FUSE_GN_STATS = not os.environ.get("SDEO_NO_GN_STATS")
 # on the raw bf16 input with gamma folded into its weight and corrects acc -> rstd * (acc - mean * colsum) + bias' in its
 # epilogue. SDEO_NO_LN_FOLD=1 restores the standalone LayerNorm pass.
 FOLD_LN = not os.environ.get("SDEO_NO_LN_FOLD")
-# GroupNorms whose input carries its producers' partial statistics and whose consumer is a convolution are folded into that
-# convolution's operand path (sdeo_conv_args::gnf_*): no GroupNorm launch, no normalised tensor in memory; the conv reads
-# the RAW bf16 tensor (an fp32 stream's bf16 twin). SDEO_NO_GN_FOLD=1 restores the standalone apply pass.
-FOLD_GN = not os.environ.get("SDEO_NO_GN_FOLD")
+# GroupNorms whose input carries its producers' partial statistics and whose consumer is a convolution CAN be folded into
+# that convolution's operand path (sdeo_conv_args::gnf_*): no GroupNorm launch, no normalised tensor in memory; the conv
+# reads the RAW bf16 tensor (an fp32 stream's bf16 twin). Opt-in (SDEO_GN_FOLD=1): measured on B200 it removes 81 of the
+# step's 428 launches but the step gets SLOWER (3.79 -> 4.65 ms at 256x384): normalising a 16 KB operand tile costs ~100
+# instructions per 8 channels on the seven otherwise idle warps (~2500 cycles per tile against ~320 for the tile's MMAs; the
+# HALO tiling amortises that over nine taps, the tap-by-tap tiling of the small feature maps cannot), every CTA re-folds
+# the producers' partial statistics (4 us in front of the first MMA), CTA pairs are lost, and reading the bf16 twin
+# instead of the fp32 stream adds one rounding per GroupNorm (tiny-model eps 1.13e-2 against the 1e-2 gate). DESIGN 5a.
+FOLD_GN = bool(os.environ.get("SDEO_GN_FOLD"))
+# bf16 outputs (the VAE's activations) CAN also leave epilogue statistics for their GroupNorm (SDEO_BF16_GN_STATS=1). Opt-in:
+# measured on the 512x512 batch-16 decode the statistics epilogue (three block-wide barriers and a shared-memory reduction
+# per tile, on grids of thousands of tiles) costs the convs more (~5 ms) than the standalone statistics pass it replaces
+# (4.6 ms), and the apply pass then folds the partials first (+1.5 ms).
+BF16_GN_STATS = bool(os.environ.get("SDEO_BF16_GN_STATS"))
 
 
 class DeferredGN:
@@ -282,7 +292,7 @@ class Conv2d(nn.Conv2d):
             ops.memset(out, 0)
         kw = dict(bias=self.bias_f32(), emb=emb, residual=res, scale=scale, act=act, stride=self.stride[0],
                   out_fp32=out_fp32 or stream, out=out, twin=stream, emb_step=emb_step, pad_hi=pad_hi,
-                  gn_stats=gn_stats and (out_fp32 or stream or FOLD_GN) and FUSE_GN_STATS,
+                  gn_stats=gn_stats and (out_fp32 or stream or FOLD_GN or BF16_GN_STATS) and FUSE_GN_STATS,
                   row_stats=row_stats and (out_fp32 or stream) and FOLD_LN)
         if gnf is not None:
             y = ops.conv2d(x1, self.packed((x1.shape[3], x2.shape[3])) if x2 is not None else self.packed(), x2=x2, gnf=gnf, **kw)

@@ -341,7 +341,9 @@ def groupnorm(x, gamma, beta, eps, silu, x2=None, groups=32, out=None, stats=Non
     if out is None:
         out = torch.empty((n, h, w, c1 + c2), dtype=BF16, device=x.device)
     if stats is not None and (x2 is None or stats2 is not None):
-        s2 = stats2 if x2 is not None else (None, 0)
+        # (large feature maps leave one slot per 128-pixel tile: thousands per sample -- one small kernel folds them first)
+        stats = gn_stats_fold(stats, n, c1)
+        s2 = gn_stats_fold(stats2, n, c2) if x2 is not None else (None, 0)
         check(lib.sdeo_groupnorm_apply_stats(_ptr(x), _ptr(x2), 1 if f32 else 0, _ptr(stats[0]), stats[1], _ptr(s2[0]), s2[1],
                                              _ptr(gamma), _ptr(beta), _ptr(out), n, h * w, c1, c2, groups, float(eps),
                                              1 if silu else 0, _stream()), "groupnorm_apply_stats")

@@ -23,6 +23,14 @@ CASES = {
     "conv3_64": (2, 64, 64, 320, 320, 3, "stream"),
     "conv3_96": (8, 96, 96, 320, 320, 3, "stream"),
     "vae128": (4, 512, 512, 128, 128, 3, "plain"),
+    # folded GroupNorm (+SiLU) in the operand path: "gnf" = ResBlock conv2 (residual, stream out), "gnfh" = conv1 (bf16 out)
+    "gnf3": (2, 32, 48, 320, 320, 3, "gnf"),
+    "gnf3h": (2, 32, 48, 320, 320, 3, "gnfh"),
+    "gnf1": (2, 32, 48, 320, 320, 1, "gnf1"),
+    "gnf_l2": (2, 16, 24, 640, 640, 3, "gnf"),
+    "gnf_mid": (2, 8, 12, 1280, 1280, 3, "gnf"),
+    "gnf_deep": (2, 4, 6, 1280, 1280, 3, "gnf"),
+    "gnf_vae": (4, 512, 512, 128, 128, 3, "gnfv"),
 }
 names = [a for a in sys.argv[1:] if "=" not in a] or list(CASES)
 # optional plan overrides: combos=00,01,10,11 (PAIR HALO digits) bn=160 splits=1
@@ -49,6 +57,21 @@ for name, combo in [(n_, c_) for n_ in names for c_ in combos]:
         kw.update(residual=torch.randn((n, h, w, cout), device=dev).to(BF))
     elif mode == "plain32":
         kw.update(out_fp32=True)
+    if mode.startswith("gnf"):
+        # producer: 3x3 conv that leaves statistics (bf16 output = the raw operand)
+        wp = torch.randn((cin, cin, 3, 3), device=dev) / math.sqrt(cin * 9)
+        x = ops.conv2d(x, ops.pack_conv_weight(wp), gn_stats=True)
+        st = ops.gn_stats_fold(x._gn_stats, n, cin)
+        gnf = ops.GnFold(st, None, torch.ones(cin, device=dev), torch.zeros(cin, device=dev), 32, 1e-5, mode != "gnf1")
+        kw.update(gnf=gnf)
+        if mode in ("gnf", "gnf1"):
+            kw.update(residual=torch.randn((n, h, w, cout), device=dev), out_fp32=True, twin=True, gn_stats=(mode == "gnf"))
+        elif mode == "gnfh":
+            kw.update(gn_stats=True)
+        elif mode == "gnfv":
+            kw.update(gn_stats=True)
+        if opts.get("nofold"):   # the same conv without the fold (on the raw operand: timing reference only)
+            del kw["gnf"]
     dbg = torch.zeros((40000, 16), dtype=torch.int64, device=dev)
     try:
         for _ in range(3):
@@ -78,6 +101,8 @@ for name, combo in [(n_, c_) for n_ in names for c_ in combos]:
               "stored %.0f | batch done %.0f" % tuple(rel[:, k].median().item() for k in (13, 9, 10, 11, 12)))
     if used[:, 13].max() > 0:
         print(f"   phase 2: residual tile waited for until {rel[:, 13].median().item():.0f}; first item batch done at {rel[:, 14].median().item():.0f}")
+    if used[:, 15].max() > 0:
+        print(f"   folded GroupNorm: table ready at {rel[:, 2].median().item():.0f}; cycles spent normalising tiles (thread 64) {used[:, 15].float().median().item():.0f}")
     if used[:, 9].max() > 0 or used[:, 10].max() > 0:
         lead = used[used[:, 9] > 0]
         print(f"   MMA warp: cycles waiting for operand data (full barriers) {lead[:, 9].float().median().item():.0f}; "
