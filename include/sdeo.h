@@ -67,7 +67,7 @@ typedef struct sdeo_conv_args {
   /* filter */
   const void* w_packed; /* bf16 [n_rows_packed, k_packed] from sdeo_pack_conv_weight (K-major)         */
   int32_t cout;         /* logical output channels (rows of w before packing/padding)                  */
-  int32_t ksize;        /* 1 or 3                                                                      */
+  int32_t ksize;        /* 1 or 3 (2 only with up2_phase)                                              */
   int32_t stride;       /* 1 or 2                                                                      */
   int32_t pad;          /* 0 or 1                                                                      */
   /* epilogue */
@@ -131,6 +131,13 @@ typedef struct sdeo_conv_args {
   int32_t gnf_groups;
   float gnf_eps;
   int32_t gnf_silu;
+  /* optional, one sub-pixel phase of nearest-x2 upsampling followed by a 3x3 "same" convolution (Upsample:
+   * openaimodel.py:108-118, model.py:50-65): output pixel (2i + a, 2j + b) of that pair only sees the 2x2 input pixels
+   * (i - 1 + a .. i + a, j - 1 + b .. j + b), with the 3x3 taps that coincide after upsampling summed -- four 2x2 filters
+   * over the LOW resolution input (16 tap-pixels instead of 36: 2.25x fewer multiply-adds, and the 4x tensor is never
+   * written). up2_phase = 1 + 2a + b (0 = off); ksize = 2, stride 1; w_packed holds that phase's [cout, cin, 2, 2] filter;
+   * y is the FULL [n, 2h, 2w, ldy] output, of which this call writes one pixel in four. No gn_stats / row_stats. */
+  int32_t up2_phase;
 } sdeo_conv_args;
 
 /* Bytes of workspace the planner may use for these args (fp32 partial tiles + tile counters).

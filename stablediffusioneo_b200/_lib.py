@@ -34,6 +34,7 @@ class ConvArgs(Structure):
         ("gnf_stats1", c_void_p), ("gnf_stats2", c_void_p), ("gnf_parts1", c_int32), ("gnf_parts2", c_int32),
         ("gnf_gamma", c_void_p), ("gnf_beta", c_void_p), ("gnf_groups", c_int32), ("gnf_eps", ctypes.c_float),
         ("gnf_silu", c_int32),
+        ("up2_phase", c_int32),
     ]
 
 

@@ -43,6 +43,11 @@ constexpr int kGnfThreads = kGnfWarps * 32;
 struct ConvKParams {
   // K loop
   int kw, pad, stride;
+  // sub-pixel phase of a nearest-x2-upsample + 3x3 convolution (sdeo_conv_args::up2_phase): a 2x2 filter over the LOW
+  // resolution input whose leading padding differs per axis (pad_h / pad_w = 1 - phase bit) and whose output pixel (h, w)
+  // lands at (2h + out_off_h, 2w + out_off_w) of the [N, Ho_full, Wo_full] output. Ordinary convs: pad_h = pad_w = pad,
+  // out_mul = 1, offsets 0, Ho_full / Wo_full = Ho / Wo.
+  int pad_h, pad_w, out_mul, out_off_h, out_off_w, Ho_full, Wo_full;
   int c1_chunks, chunks_per_tap;
   int total_chunks, chunks_per_split, splits;
   // M tiling
@@ -645,7 +650,7 @@ __device__ __noinline__ void gnf_transform_warps(const ConvKParams& p, uint8_t* 
         if (t == 0) mbar_wait(&full_bar[s], ph);
         bar_sync(1, kGnfThreads);
         const long long t_x0 = (p.dbg && t == 0) ? clock64() : 0;
-        const int hb = h0 * p.stride + ky - p.pad, wb = w0 * p.stride + kx - p.pad;
+        const int hb = h0 * p.stride + ky - p.pad_h, wb = w0 * p.stride + kx - p.pad_w;
         xform_tile(smem_u32(tiles) + (uint32_t)(s * stage_bytes), p.rows_valid, ab + within * 80, [&](int row) -> int {
           const int info = row_hw[row];
           const int hh = hb + ((info >> 8) & 255) * p.stride, ww = wb + (info & 255) * p.stride;
@@ -798,7 +803,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmA1, const CU
     const int row = (int)threadIdx.x - 128;
     int nn, hh, ww;
     const bool ok = tile_row_coords(p, row, n0, h0, w0, &nn, &hh, &ww);
-    row_pix[row] = ok ? (nn * p.Ho + hh) * p.Wo + ww : -1;
+    row_pix[row] = ok ? (nn * p.Ho_full + hh * p.out_mul + p.out_off_h) * p.Wo_full + ww * p.out_mul + p.out_off_w : -1;
   }
 
   // HALO mode ring geometry: [A ring: a_stages x a_stage_bytes][B ring: stages x BN*128]
@@ -968,8 +973,8 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmA1, const CU
           if (p.dbg) dbg_wait += clock64() - t_w0;
           if (leader) mbar_expect_tx(&full_bar[s], tx_bytes);
         }
-        const int wc = w0 * p.stride + kx - p.pad;
-        const int hc = h0 * p.stride + ky - p.pad;
+        const int wc = w0 * p.stride + kx - p.pad_w;
+        const int hc = h0 * p.stride + ky - p.pad_h;
         const uint32_t fb = full_addr(&full_bar[s]);
         if (within < p.c1_chunks)
           tma4d_to(a_dst, &tmA1, fb, pair, within * kBK, wc, hc, n0);
@@ -1172,7 +1177,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmA1, const CU
     const int cols_items = p.cols_items;  // items per row (BN / 8; GEGLU: BN / 16)
     const int n_base = n_tile * p.BN;
     const uint32_t slice_bytes = (uint32_t)(rows_per * LD) * 4u;  // S > 1: one received slice per K-slice rank
-    const int hw_out = p.Ho * p.Wo;
+    const int hw_out = p.Ho_full * p.Wo_full;
     const int half = p.BN / 2;
     const bool emb_global = p.emb && !emb_in_colv;   // (several samples per tile without a step table)
     if (MODE == SDEO_EPI_NORMAL && FAST && RES != RES_NONE && p.res_smem_off) mbar_wait(res_bar, 0);
@@ -1504,16 +1509,23 @@ static inline int cta_limit() { return g_cta_budget > 0 && g_cta_budget < 148 ? 
 // force_pair: -1 = heuristic (SDEO_PAIR=0/1 overrides), 0 = off, 1 = on (fails with fewer than two M tiles).
 static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl, int force_bn = 0, int force_splits = 0, int force_halo = -1,
                       int force_pair = -1, int force_occ2 = -1) {
-  if (!(a->ksize == 1 || a->ksize == 3)) return false;
+  const bool up2 = a->up2_phase != 0;
+  if (up2) {  // 2x2 phase filter of upsample + conv3x3: no other geometry options, no fused statistics / LayerNorm / GroupNorm
+    if (a->ksize != 2 || a->stride != 1 || a->pad_hi != 0 || a->up2_phase < 1 || a->up2_phase > 4 || a->ln_stats || a->gnf_stats1 ||
+        a->epi_mode != SDEO_EPI_NORMAL)
+      return false;
+  }
+  if (!(a->ksize == 1 || a->ksize == 3 || up2)) return false;
   if (!(a->stride == 1 || a->stride == 2)) return false;
   // symmetric "same" padding, or the VAE encoder's Downsample: 3x3 stride 2 over F.pad(x, (0,1,0,1)) = no leading padding,
   // one trailing zero row / column (TMA out-of-bounds fill supplies it like every other padding pixel)
   const bool tail_pad = a->ksize == 3 && a->stride == 2 && a->pad == 0 && a->pad_hi == 1;
-  if (!tail_pad && (a->pad != (a->ksize == 3 ? 1 : 0) || a->pad_hi != 0)) return false;
+  if (!tail_pad && !up2 && (a->pad != (a->ksize == 3 ? 1 : 0) || a->pad_hi != 0)) return false;
   if (a->c1 <= 0 || (a->ld1 % 8) != 0 || (a->x2 && (a->ld2 % 8) != 0)) return false;
   if (a->x2 && (a->c1 % 64) != 0) return false;
   pl->Ho = (a->h + 2 * a->pad + a->pad_hi - a->ksize) / a->stride + 1;
   pl->Wo = (a->w + 2 * a->pad + a->pad_hi - a->ksize) / a->stride + 1;
+  if (up2) { pl->Ho = a->h; pl->Wo = a->w; }   // one output pixel per input pixel and phase
   // ---- M tile box: minimise tile count, then prefer wide boxes ----
   int best_tiles = INT32_MAX, bbn = 1, bbh = 1, bbw = 1;
   const int maxw = pl->Wo < kBM ? pl->Wo : kBM;
@@ -1712,7 +1724,7 @@ static bool make_plan(const sdeo_conv_args* a, ConvPlan* pl, int force_bn = 0, i
   pl->res_smem_off = 0;
   int res_bytes = 0;
   // (only the vector-aligned NORMAL epilogue reads the prefetched tile; the same conditions make the TMA box legal)
-  bool res_fast = a->residual && a->epi_mode == SDEO_EPI_NORMAL && (a->cout % 16 == 0) &&
+  bool res_fast = a->residual && !up2 && a->epi_mode == SDEO_EPI_NORMAL && (a->cout % 16 == 0) &&
                   (a->residual_f32 ? (a->ldr % 4 == 0) : (a->ldr % 8 == 0)) && ((reinterpret_cast<uintptr_t>(a->residual) & 15) == 0);
   res_fast = res_fast && (a->y_fp32 ? (a->ldy % 4 == 0) : (a->ldy % 8 == 0)) && (!(a->y_fp32 && a->y2) || (a->ldy2 % 8 == 0));
   if (res_fast && !getenv("SDEO_NO_RES_PREFETCH")) {
@@ -1790,7 +1802,7 @@ static int launch_conv(const sdeo_conv_args* a, const ConvPlan& pl, void* stream
 // Row statistics (sdeo_conv_args::row_stats) need the vector-aligned NORMAL epilogue with an fp32 output and an N tile of
 // 64 / 128 / 256 columns (the lanes that hold one row must form an aligned power-of-two group of a warp).
 static bool row_stats_ok(const sdeo_conv_args* a, const ConvPlan& pl) {
-  if (!a->row_stats || a->epi_mode != SDEO_EPI_NORMAL || !a->y_fp32) return false;
+  if (!a->row_stats || a->epi_mode != SDEO_EPI_NORMAL || !a->y_fp32 || a->up2_phase) return false;
   bool fast = (a->cout % 16 == 0) && (a->ldy % 4 == 0);
   if (a->y2) fast = fast && (a->ldy2 % 8 == 0);
   if (a->residual) fast = fast && (a->residual_f32 ? (a->ldr % 4 == 0) : (a->ldr % 8 == 0));
@@ -1798,7 +1810,7 @@ static bool row_stats_ok(const sdeo_conv_args* a, const ConvPlan& pl) {
 }
 
 static int stats_parts(const sdeo_conv_args* a, const ConvPlan& pl) {
-  if (!a->gn_stats || a->row_stats || a->epi_mode != SDEO_EPI_NORMAL) return 0;
+  if (!a->gn_stats || a->row_stats || a->epi_mode != SDEO_EPI_NORMAL || a->up2_phase) return 0;
   bool fast = (a->cout % 16 == 0) && (a->y_fp32 ? (a->ldy % 4 == 0) : (a->ldy % 8 == 0));
   if (a->y2) fast = fast && (a->ldy2 % 8 == 0);
   if (a->residual) fast = fast && (a->residual_f32 ? (a->ldr % 4 == 0) : (a->ldr % 8 == 0));
@@ -1827,7 +1839,7 @@ std::mutex g_tune_mu;
 int g_autotune = 0;
 
 TuneKey tune_key(const sdeo_conv_args* a) {
-  TuneKey k = {a->n, a->h, a->w, a->c1, a->x2 ? a->c2 : 0, a->cout, a->ksize, a->stride | (a->pad_hi << 4), a->epi_mode, a->y_fp32,
+  TuneKey k = {a->n, a->h, a->w, a->c1, a->x2 ? a->c2 : 0, a->cout, a->ksize, a->stride | (a->pad_hi << 4) | (a->up2_phase << 8), a->epi_mode, a->y_fp32,
                a->residual ? (a->residual_f32 ? 2 : 1) : 0, a->y2 ? 1 : 0, a->emb ? 1 : 0, a->act, a->dhead,
                (a->gn_stats ? 1 : 0) | (a->row_stats ? 2 : 0) | (a->ln_stats ? 4 : 0) | (cta_limit() << 3) |
                    (a->gnf_stats1 ? (1 << 12) | (a->gnf_silu ? 1 << 13 : 0) : 0)};
@@ -2043,6 +2055,12 @@ static int launch_conv(const sdeo_conv_args* a, const ConvPlan& pl, void* stream
 
   ConvKParams p;
   p.kw = a->ksize; p.pad = a->pad; p.stride = a->stride;
+  p.pad_h = p.pad_w = a->pad; p.out_mul = 1; p.out_off_h = p.out_off_w = 0; p.Ho_full = pl.Ho; p.Wo_full = pl.Wo;
+  if (a->up2_phase) {
+    const int ph_h = (a->up2_phase - 1) >> 1, ph_w = (a->up2_phase - 1) & 1;
+    p.pad_h = 1 - ph_h; p.pad_w = 1 - ph_w; p.pad = 0;
+    p.out_mul = 2; p.out_off_h = ph_h; p.out_off_w = ph_w; p.Ho_full = 2 * pl.Ho; p.Wo_full = 2 * pl.Wo;
+  }
   p.c1_chunks = pl.c1c; p.chunks_per_tap = pl.cpt;
   p.total_chunks = pl.total_chunks; p.chunks_per_split = pl.cps; p.splits = pl.splits;
   p.bn_ = pl.bn_; p.bh = pl.bh; p.bw = pl.bw; p.rows_valid = pl.rows_valid;

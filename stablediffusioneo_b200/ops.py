@@ -117,7 +117,7 @@ def pack_conv_weight(weight, c1=None, c2=0, geglu=False):
     weight = weight.detach().to(torch.float32).contiguous()
     _req(weight, torch.float32, "weight")
     cout, cin, k, k2 = weight.shape
-    assert k == k2 and k in (1, 3)
+    assert k == k2 and k in (1, 2, 3)   # (2: a sub-pixel phase filter of upsample + conv3x3, see conv2d(up2_phase=...))
     if c1 is None:
         c1 = cin
     assert c1 + c2 == cin
@@ -143,7 +143,7 @@ def pack_geglu_bias(bias, geglu_bn):
 
 def conv2d(x, pw, x2=None, bias=None, emb=None, residual=None, scale=1.0, act=SDEO_ACT_NONE, stride=1, out=None,
            out_fp32=False, epi_mode=SDEO_EPI_NORMAL, qkv=None, twin=False, emb_step=None, gn_stats=False, row_stats=False,
-           ln=None, pad_hi=0, gnf=None):
+           ln=None, pad_hi=0, gnf=None, up2_phase=0):
     """x: [N,H,W,C1] bf16 (+ optional x2 [N,H,W,C2] = fused torch.cat along channels). Returns [N,Ho,Wo,cout].
     residual may be bf16 or fp32. out_fp32 + twin=True additionally writes a bf16 copy and returns (y_f32, y_bf16).
     emb: fp32 [N, cout] (row = sample), or with emb_step (int32 device scalar) a table [S, cout] whose row *emb_step is
@@ -154,6 +154,8 @@ def conv2d(x, pw, x2=None, bias=None, emb=None, residual=None, scale=1.0, act=SD
     LayerNorm to its input rows in the epilogue (x is the raw bf16 input; pw / bias carry gamma / beta).
     gnf: GnFold -- a GroupNorm (+ SiLU) applied to the RAW bf16 x (| x2) inside the operand path of this convolution
     (statistics from the producers' epilogues); gn_stats then also works with a bf16 output.
+    up2_phase = 1 + 2a + b: pw is the 2x2 phase filter (upsample2x_conv_weights) of nearest-x2 upsampling + conv3x3; `out`
+    is the full [N, 2H, 2W, cout] tensor (allocated when None), of which this call writes the pixels (2i + a, 2j + b).
     pad_hi=1 (3x3, stride 2): no leading padding, one trailing zero row / column = F.pad(x, (0,1,0,1)) + conv(padding=0),
     the VAE encoder's Downsample (model.py:78-84)."""
     lib = _lib.load()
@@ -180,7 +182,13 @@ def conv2d(x, pw, x2=None, bias=None, emb=None, residual=None, scale=1.0, act=SD
         pad = 0
     ho = (h + 2 * pad + pad_hi - k) // stride + 1
     wo = (w + 2 * pad + pad_hi - k) // stride + 1
+    if up2_phase:
+        assert k == 2 and stride == 1 and 1 <= up2_phase <= 4 and epi_mode == SDEO_EPI_NORMAL and residual is None
+        ho, wo = 2 * h, 2 * w
+    else:
+        assert k != 2
     a = ConvArgs()
+    a.up2_phase = up2_phase
     a.pad_hi = pad_hi
     a.x1, a.x2 = _ptr(x), _ptr(x2)
     a.n, a.h, a.w = n, h, w
@@ -272,6 +280,28 @@ def gn_stats_fold(stats, n, c):
         check(lib.sdeo_gn_stats_fold(_ptr(buf), _ptr(out), n, parts, c, ctypes.byref(op), _stream()), "gn_stats_fold")
         buf, parts = out, op.value
     return buf, parts
+
+
+def upsample2x_conv_weights(weight):
+    """3x3 filter [cout, cin, 3, 3] of a conv that follows nearest-x2 upsampling -> the four packed 2x2 phase filters
+    (index 2a + b): along each axis phase 0 sees input pixels (i-1, i) with taps (w0, w1 + w2), phase 1 sees (i, i+1)
+    with (w0 + w1, w2). Sums in fp32, one bf16 rounding when packed."""
+    w = weight.detach().float()
+    rows = (torch.stack([w[:, :, 0], w[:, :, 1] + w[:, :, 2]], 2), torch.stack([w[:, :, 0] + w[:, :, 1], w[:, :, 2]], 2))
+    out = []
+    for a_ in range(2):
+        r = rows[a_]                                     # [cout, cin, 2, 3]
+        cols = (torch.stack([r[..., 0], r[..., 1] + r[..., 2]], 3), torch.stack([r[..., 0] + r[..., 1], r[..., 2]], 3))
+        for b_ in range(2):
+            out.append(pack_conv_weight(cols[b_].contiguous()))
+    return out
+
+
+def upsample2x_conv(x, phase_weights, bias=None, out=None):
+    """conv3x3(nearest_x2(x)) as four sub-pixel phase convolutions over the low-resolution x [N,H,W,C] -> [N,2H,2W,cout]."""
+    for ph in range(4):
+        out = conv2d(x, phase_weights[ph], bias=bias, out=out, up2_phase=ph + 1)
+    return out
 
 
 @dataclass

@@ -430,6 +430,32 @@ def test_groupnorm_from_conv_statistics(cuda_device, case, autotune):
     assert rel_l2(y_fused, y_plain) < 2e-3   # same math, different fp32 summation order (+ bf16 rounding flips)
 
 
+@pytest.mark.parametrize("case", [
+    # (n, cin, cout, h, w)
+    (1, 512, 512, 32, 48),      # VAE decoder, first Upsample at 256x384
+    (2, 256, 256, 64, 64),
+    (1, 64, 48, 13, 9),         # ragged tiles, odd sizes
+    (3, 128, 128, 20, 28),
+])
+def test_upsample2x_conv_subpixel(cuda_device, case):
+    """conv3x3(nearest_x2(x)) as four 2x2 phase convolutions over the low-resolution input (sdeo_conv_args::up2_phase)
+    against F.interpolate + F.conv2d in fp32 on the bf16-rounded input (weights: fp32 sums rounded once, so the gate is the
+    per-op one), and against the library's own upsample kernel + 3x3 conv."""
+    from stablediffusioneo_b200 import ops
+    n, cin, cout, h, w = case
+    dev = cuda_device
+    x = gen((n, cin, h, w), 1, dev)
+    wt = gen((cout, cin, 3, 3), 2, dev) / math.sqrt(cin * 9)
+    bias = gen((cout,), 3, dev) * 0.1
+    phases = ops.upsample2x_conv_weights(wt)
+    y = ops.upsample2x_conv(nhwc(x), phases, bias=bias)
+    assert y.shape == (n, 2 * h, 2 * w, cout)
+    ref = F.conv2d(F.interpolate(bf16r(x), scale_factor=2, mode="nearest"), wt, bias, padding=1)
+    assert rel_l2(y.permute(0, 3, 1, 2), ref) < TOL
+    y2 = ops.conv2d(ops.upsample_nearest2x(nhwc(x)), ops.pack_conv_weight(wt), bias=bias)
+    assert rel_l2(y, y2) < TOL
+
+
 GNF_CASES = [
     # (n, c_a, c_b, cout, h, w, k, silu, halo)   producer convs -> GroupNorm(+SiLU) folded into the consumer conv
     (2, 320, 0, 320, 32, 48, 3, True, 1),       # ResBlock in_layers at the top level, HALO tiling
