@@ -309,6 +309,11 @@ int sdeo_axpby_f32(const float* x, const float* z, const float* a, const float* 
                    int64_t per_sample, void* stream);
 /* Inpainting blend of ddim_sampling (cldm/ddim_hacked.py:154-157): y = mask * (a x0 + b noise) + (1 - mask) * img with the
  * parenthesis = q_sample(x0, t). img / x0 / noise / y fp32 [n, c, hw]; mask fp32 [n, mask_c, hw], mask_c = 1 or c. */
+/* The same blend as a node of the captured step graph: orig_table fp32 [S][n, c, hw] holds q_sample(x0, t_s) of every DDIM
+ * step (drawn up front, in the step-by-step path's order); row *step_idx (device step counter) is blended into img.
+ * y may alias img. */
+int sdeo_mask_blend_table_f32(const float* orig_table, const float* img, const float* mask, float* y, const int32_t* step_idx,
+                              int32_t n, int32_t c, int32_t mask_c, int64_t hw, void* stream);
 int sdeo_mask_blend_f32(const float* x0, const float* noise, const float* img, const float* mask, const float* a,
                         const float* b, float* y, int32_t n, int32_t c, int32_t mask_c, int64_t hw, void* stream);
 

@@ -100,6 +100,8 @@ SIGNATURES = {
                               c_size_t, c_void_p]),
     "sdeo_edges_to_hint": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "sdeo_axpby_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    "sdeo_mask_blend_table_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                          ctypes.c_int64, c_void_p]),
     "sdeo_mask_blend_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                     c_int32, c_int64, c_void_p]),
     "sdeo_split_terms": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int64, c_int32, c_int32, ctypes.c_uint32,

@@ -177,9 +177,13 @@ class ControlNet(nn.Module):
         feats.append(self.middle_block.run(h, emb, context))
         return feats
 
-    def run_zero_convs(self, feats, scales=None, add_to=None, only_mid=False, order=None, after=None):
+    def run_zero_convs(self, feats, scales=None, add_to=None, only_mid=False, order=None, after=None, rows=None):
         """13 outputs: scale_i * zero_conv_i(h_i) [+ add_to[i]] (only_mid: entries 0..11 are add_to[i] untouched).
-        order: launch order of the 13 convs (default 0..12); after(i): hook called once output i has been enqueued."""
+        order: launch order of the 13 convs (default 0..12); after(i): hook called once output i has been enqueued.
+        rows (guess mode in the step engine, needs add_to): the feature maps hold only the first `rows` samples of the
+        batch; zero_conv_i(h_i) is added IN PLACE onto those rows of the stream tensor add_to[i] (and of its bf16 twin),
+        the other rows stay as they are; outs[i] is add_to[i] itself (without epilogue statistics: the rows' producers
+        differ)."""
         scales = [1.0] * (len(self.zero_convs) + 1) if scales is None else list(scales)
         convs = [z[0] for z in self.zero_convs] + [self.middle_block_out[0]]
         outs = [None] * len(convs)
@@ -188,6 +192,13 @@ class ControlNet(nn.Module):
             last = i == len(convs) - 1
             if only_mid and add_to is not None and not last:
                 outs[i] = add_to[i]
+            elif rows is not None:
+                tgt = add_to[i]
+                assert util.is_stream(tgt) and tgt._twin is not None and h.shape[0] == rows
+                f32, twin = nhwc(tgt)[:rows], nhwc(tgt._twin)[:rows]
+                conv.run(h, scale=scales[i], residual=nchw_view(f32), stream=True, out_f32=f32, out_twin=twin)
+                tgt._gn_stats = None
+                outs[i] = tgt
             else:
                 outs[i] = conv.run(h, scale=scales[i], residual=add_to[i] if add_to is not None else None,
                                    stream=util.STREAM_FP32, gn_stats=add_to is not None)

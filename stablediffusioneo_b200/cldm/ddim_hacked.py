@@ -105,9 +105,10 @@ class DDIMSampler(object):
         from .cldm import ControlLDM
         if not (self.use_engine and isinstance(self.model, ControlLDM)) or self.model.precision != "bf16":
             return False
-        if any(v is not None for v in (mask, callback, img_callback, score_corrector, dynamic_threshold, ucg_schedule,
+        if any(v is not None for v in (callback, img_callback, score_corrector, dynamic_threshold, ucg_schedule,
                                        timesteps)) or quantize_denoised or ddim_use_original_steps:
             return False
+        # (mask / x0 inpainting blend runs in the engine: q_sample(x0, t) of every step is drawn up front into a table)
         if noise_dropout != 0.0:
             return False  # (eta > 0 itself runs in the engine: the per-step noise is drawn up front into a device table)
         if not isinstance(cond, dict) or self.model.parameterization != "eps":
@@ -116,8 +117,10 @@ class DDIMSampler(object):
         if uncond is not None and scale != 1.0:
             if not isinstance(uncond, dict):
                 return False
-            if (cond["c_concat"] is None) != (uncond["c_concat"] is None):
-                return False  # guess mode: the uncond pass skips the ControlNet -> two different graphs
+            if cond["c_concat"] is None and uncond["c_concat"] is not None:
+                return False  # (a hint on the unconditional branch only: no caller does that -> generic path)
+            # cond with a hint, uncond without = guess mode (canny2image_torch.py:48): the engine runs the ControlNet on the
+            # conditional rows only and adds its outputs onto those rows of the UNet's skip tensors
             conds.append(uncond)
         for cd in conds:
             # the engine's static buffers are sized from ONE context and ONE hint tensor per conditioning; lists with
@@ -137,8 +140,10 @@ class DDIMSampler(object):
         if self._engine_ok(cond, unconditional_conditioning, unconditional_guidance_scale, mask, callback, img_callback,
                            quantize_denoised, score_corrector, dynamic_threshold, ucg_schedule,
                            ddim_use_original_steps, timesteps, noise_dropout, temperature):
+            if mask is not None:
+                assert x0 is not None
             return self._engine_sampling(cond, unconditional_conditioning, unconditional_guidance_scale, img,
-                                         log_every_t, temperature)
+                                         log_every_t, temperature, mask=mask, x0=x0)
 
         if timesteps is None:
             timesteps = self.ddpm_num_timesteps if ddim_use_original_steps else self.ddim_timesteps
@@ -288,30 +293,39 @@ class DDIMSampler(object):
         return x_dec
 
     # --------------------------------------------------------------------------------------------------------
-    def _engine_sampling(self, cond, uncond, scale, x_T, log_every_t, temperature=1.0):
+    def _engine_sampling(self, cond, uncond, scale, x_T, log_every_t, temperature=1.0, mask=None, x0=None):
         guided = not (uncond is None or scale == 1.)
         S = int(self.ddim_timesteps.shape[0])
         eng = self._engine
-        key = _EngineKey(self.model, x_T, cond, uncond if guided else None, S, self.use_cuda_graph)
+        key = _EngineKey(self.model, x_T, cond, uncond if guided else None, S, self.use_cuda_graph, mask is not None)
         if eng is None or eng.key != key:
             eng = self._engine = _Engine(self.model, key, self.use_cuda_graph)
         time_range = np.flip(self.ddim_timesteps)
         rows = [self._coef_row(S - i - 1, scale if guided else 1.0) for i in range(S)]
         # the reference logs x_inter / pred_x0 when index % log_every_t == 0 or index == S-1 (ddim_hacked.py:174-176)
         log_at = [i for i in range(S) if (S - i - 1) % log_every_t == 0 or i == 0]
+        blend = None
+        if mask is not None:
+            dev = x_T.device
+            m = mask.to(device=dev, dtype=torch.float32)
+            if m.dim() != 4 or m.shape[0] != x_T.shape[0] or m.shape[1] not in (1, x_T.shape[1]) or m.shape[2:] != x_T.shape[2:]:
+                m = m.expand_as(x_T)
+            blend = (m.contiguous(), x0.to(device=dev, dtype=torch.float32).contiguous(), self.model)
         img, pred_x0, logged = eng.run(x_T, cond, uncond if guided else None, [int(t) for t in time_range], rows, log_at,
-                                       temperature=temperature)
+                                       temperature=temperature, blend=blend)
         inter = {'x_inter': [x_T] + [l[0] for l in logged], 'pred_x0': [x_T] + [l[1] for l in logged]}
         return img, inter
 
 
 class _EngineKey:
-    def __init__(self, model, x_T, cond, uncond, S, graph):
+    def __init__(self, model, x_T, cond, uncond, S, graph, masked=False):
         hint = cond["c_concat"]
+        self.masked = masked
         # weights_fingerprint: the captured graphs, time-embedding tables and hoisted K/V bake in buffers derived from the
         # parameters; after load_state_dict() or any in-place update the engine is rebuilt instead of replaying old weights
         self.t = (id(model), tuple(x_T.shape), tuple(cond["c_crossattn"][0].shape),
-                  None if hint is None else tuple(hint[0].shape), uncond is not None, S, graph,
+                  None if hint is None else tuple(hint[0].shape), uncond is not None,
+                  uncond is not None and hint is not None and uncond["c_concat"] is None, masked, S, graph,
                   tuple(model.control_scales), model.only_mid_control, model.weights_fingerprint())
 
     def __eq__(self, other):
@@ -345,17 +359,33 @@ class _Engine:
         # eta > 0 (ddim_hacked.py:227-230): sigma_t * noise, one fresh tensor per step, read by the captured step graph as
         # row *step_ctr of this table
         self.noise = torch.zeros((S, b, c, h, w), dtype=torch.float32, device=dev)
+        # inpainting (mask / x0, ddim_hacked.py:154-157): q_sample(x0, t_i) of every step, blended into the latent by the
+        # first node of the step graph (row *step_ctr)
+        self.masked = self.key.masked
+        if self.masked:
+            self.orig_table = torch.zeros((S, b, c, h, w), dtype=torch.float32, device=dev)
+            self.mask = torch.zeros((b, c, h, w), dtype=torch.float32, device=dev)
         ctx_shape = cond["c_crossattn"][0].shape
         self.ctx = torch.empty((nb, ctx_shape[1], ctx_shape[2]), dtype=BF16, device=dev)
         self.has_hint = cond["c_concat"] is not None
+        # guess mode: only the conditional rows go through the ControlNet
+        self.guess = self.has_hint and uncond is not None and uncond["c_concat"] is None
+        self.ctx_cn = self.ctx[:b] if self.guess else self.ctx   # (ONE view object: the hoisted K/V are keyed on its identity)
         if self.has_hint:
             hs = cond["c_concat"][0].shape
-            self.hint = torch.empty((nb, hs[1], hs[2], hs[3]), dtype=torch.float32, device=dev)
+            self.hint = torch.empty((b if self.guess else nb, hs[1], hs[2], hs[3]), dtype=torch.float32, device=dev)
 
-    def _load_inputs(self, x_T, cond, uncond, ts, rows, temperature=1.0):
+    def _load_inputs(self, x_T, cond, uncond, ts, rows, temperature=1.0, blend=None):
         b = x_T.shape[0]
         self.x_keep.copy_(x_T, non_blocking=True)
+        if self.masked:
+            mask, x0, model = blend
+            self.mask.copy_(mask.expand_as(self.mask))
         for i, row in enumerate(rows):
+            if self.masked:
+                # (the step-by-step path draws q_sample's noise at the top of every step, before the step's own noise)
+                t_i = torch.full((b,), int(ts[i]), device=x_T.device, dtype=torch.long)
+                self.orig_table[i].copy_(model.q_sample(x0, t_i))
             if row[5] != 0.0:
                 # the same draws, in the same order, as the step-by-step path (p_sample_ddim: one noise_like per step
                 # whose sigma is not zero), so both paths produce the same trajectory from the same generator state
@@ -368,7 +398,7 @@ class _Engine:
             ctx = cd["c_crossattn"][0] if len(cd["c_crossattn"]) == 1 else torch.cat(cd["c_crossattn"], 1)
             ctx = ctx.to(self.ctx.device)
             self.ctx[i * b:(i + 1) * b].copy_(ctx if ctx.dtype == BF16 else ops.to_bf16(ctx.float().contiguous()))
-            if self.has_hint:
+            if self.has_hint and cd["c_concat"] is not None:
                 hint = cd["c_concat"][0] if len(cd["c_concat"]) == 1 else torch.cat(cd["c_concat"], 1)
                 self.hint[i * b:(i + 1) * b].copy_(hint, non_blocking=True)
         self.reset_latent()
@@ -427,21 +457,28 @@ class _Engine:
         else:
             self.guided = None
         from ..ldm.modules.attention import CrossAttention
-        mods = list(m.model.diffusion_model.modules()) + (list(m.control_model.modules()) if self.has_hint else [])
-        for mod in mods:
+        mods = [(mod, self.ctx) for mod in m.model.diffusion_model.modules()]
+        if self.has_hint:
+            mods += [(mod, self.ctx_cn) for mod in m.control_model.modules()]
+        for mod, ctx in mods:
             if isinstance(mod, CrossAttention) and not mod.is_self:
                 st = mod.kv_static
-                if st is not None and st[0] is self.ctx:
-                    mod.project_kv(self.ctx, k=st[1], vt=st[2])
+                if st is not None and st[0] is ctx:
+                    mod.project_kv(ctx, k=st[1], vt=st[2])
                 else:
-                    k, vt, nkv, ldv = mod.project_kv(self.ctx)
-                    mod.kv_static = (self.ctx, k, vt, nkv, ldv)
+                    k, vt, nkv, ldv = mod.project_kv(ctx)
+                    mod.kv_static = (ctx, k, vt, nkv, ldv)
 
     def _step(self):
         m = self.model
         unet = m.model.diffusion_model
         nb = self.x_in.shape[0]
         b = self.x_lat.shape[0]
+        if self.masked:
+            ops.mask_blend_table_(self.x_lat, self.orig_table, self.mask, self.step_ctr)
+            x_b = ops.nchw_to_nhwc(self.x_lat, 8)   # the network input of this step is the BLENDED latent
+            for i in range(self.dup):
+                self.x_in[i * b:(i + 1) * b].copy_(x_b)
         x = self.x_in.permute(0, 3, 1, 2)
         emb_u = self.emb_u  # per-image [S, Cout] tables, row selected on the device by step_ctr (see _prologue)
         if self.has_hint:
@@ -455,7 +492,8 @@ class _Engine:
             # streams' kernels really run side by side (SDEO_BRANCH_CTAS, default 74; 0 = no limit)
             with ops.cta_budget(int(os.environ.get("SDEO_BRANCH_CTAS", "74"))):
                 with torch.cuda.stream(side), ops.workspace_slot(1):
-                    feats = cn.run_body(x, self.guided, self.emb_c, self.ctx)
+                    x_cn = self.x_in[:b].permute(0, 3, 1, 2) if self.guess else x
+                    feats = cn.run_body(x_cn, self.guided, self.emb_c, self.ctx_cn)
                 hs, h = unet.run_encoder(x, emb_u, self.ctx)
             # the 13 zero convs (+ control scale + add onto the UNet skips) stay on the side stream, launched in the
             # order the decoder consumes them; the decoder waits per tensor, so only the first ones are on its path
@@ -466,7 +504,8 @@ class _Engine:
             evs = self._zc_events
             with torch.cuda.stream(side), ops.workspace_slot(1):
                 outs = cn.run_zero_convs(feats, scales=m.control_scales, add_to=hs + [h], only_mid=m.only_mid_control,
-                                         order=range(n_out - 1, -1, -1), after=lambda i: evs[i].record(side))
+                                         order=range(n_out - 1, -1, -1), after=lambda i: evs[i].record(side),
+                                         rows=b if self.guess else None)
             main.wait_event(evs[n_out - 1])
             # the encoder outputs are read (as residuals) by the side stream: keep them alive until the step has been
             # enqueued, or main's allocator would hand their memory to the decoder while the zero convs still read it
@@ -483,13 +522,13 @@ class _Engine:
                           pred_x0=self.pred_x0, x_next=self.x_in, dup=self.dup, eps_nhwc=True)
         ops.counter_add(self.step_ctr, 1)
 
-    def prepare(self, x_T, cond, uncond, ts, rows, temperature=1.0):
+    def prepare(self, x_T, cond, uncond, ts, rows, temperature=1.0, blend=None):
         """Upload inputs, run the loop-invariant prologue and (first time) capture the per-step CUDA graph."""
         S = len(ts)
         if not self.ready:
             self._alloc(x_T, cond, uncond, S)
         self.S = S
-        self._load_inputs(x_T, cond, uncond, ts, rows, temperature)
+        self._load_inputs(x_T, cond, uncond, ts, rows, temperature, blend)
         self._prologue()
         if self.use_graph and self.graph is None:
             # warm-up once eagerly (packs weights, sizes workspaces), then capture the step
@@ -512,9 +551,9 @@ class _Engine:
         else:
             self._step()
 
-    def run(self, x_T, cond, uncond, ts, rows, log_at=(), temperature=1.0):
+    def run(self, x_T, cond, uncond, ts, rows, log_at=(), temperature=1.0, blend=None):
         """log_at: step numbers after which (x_{t-1}, pred_x0) are returned as copies (the reference's intermediates)."""
-        self.prepare(x_T, cond, uncond, ts, rows, temperature)
+        self.prepare(x_T, cond, uncond, ts, rows, temperature, blend)
         log_at = set(log_at)
         logged = []
         for i in range(self.S):

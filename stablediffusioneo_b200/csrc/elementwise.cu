@@ -334,6 +334,27 @@ __global__ void mask_blend_f32_kernel(const float* __restrict__ x0, const float*
   }
 }
 
+// The same blend inside the captured step graph: img_orig = q_sample(x0, t_step) of EVERY step is drawn up front into a
+// table [S][n, c, hw]; the row is selected on the device by the step counter. y may alias img.
+__global__ void mask_blend_table_f32_kernel(const float* __restrict__ orig_table, const float* img,
+                                            const float* __restrict__ mask, float* y, const int* __restrict__ step_idx,
+                                            int n, int c, int mask_c, long long hw) {
+  const int trc = trace_start(5);
+  griddep_launch_dependents();
+  griddep_wait();
+  trace_mark(trc, 2);
+  trace_mark(trc, 3);
+  const long long count = (long long)n * c * hw;
+  const float* orig = orig_table + (long long)__ldg(step_idx) * count;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    const long long s = i / (c * hw);
+    const int ch = (int)((i / hw) % c);
+    const long long p = i % hw;
+    const float m = mask[(s * mask_c + (mask_c == 1 ? 0 : ch)) * hw + p];
+    y[i] = orig[i] * m + (1.0f - m) * img[i];
+  }
+}
+
 static int grid_for(long long work, int threads) {
   long long b = (work + threads - 1) / threads;
   if (b > 148 * 8) b = 148 * 8;
@@ -446,6 +467,13 @@ extern "C" int sdeo_axpby_f32(const float* x, const float* z, const float* a, co
                               int64_t per_sample, void* stream) {
   if (!x || !z || !a || !b || !y || count <= 0 || per_sample <= 0) return set_error(SDEO_EINVAL, "axpby_f32: bad args");
   return launch_k("axpby_f32", axpby_f32_kernel, dim3(grid_for(count, 256)), dim3(256), 0, (cudaStream_t)stream, dim3(1, 1, 1), x, z, a, b, y, (long long)count, (long long)per_sample);
+}
+extern "C" int sdeo_mask_blend_table_f32(const float* orig_table, const float* img, const float* mask, float* y,
+                                         const int32_t* step_idx, int32_t n, int32_t c, int32_t mask_c, int64_t hw, void* stream) {
+  if (!orig_table || !img || !mask || !y || !step_idx || n <= 0 || c <= 0 || hw <= 0 || (mask_c != 1 && mask_c != c))
+    return set_error(SDEO_EINVAL, "mask_blend_table_f32: bad args");
+  return launch_k("mask_blend_table_f32", mask_blend_table_f32_kernel, dim3(grid_for((long long)n * c * hw, 256)), dim3(256), 0,
+                  (cudaStream_t)stream, dim3(1, 1, 1), orig_table, img, mask, y, (const int*)step_idx, n, c, mask_c, (long long)hw);
 }
 extern "C" int sdeo_mask_blend_f32(const float* x0, const float* noise, const float* img, const float* mask, const float* a,
                                    const float* b, float* y, int32_t n, int32_t c, int32_t mask_c, int64_t hw, void* stream) {

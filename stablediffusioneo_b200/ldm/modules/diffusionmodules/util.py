@@ -270,7 +270,7 @@ class Conv2d(nn.Conv2d):
         return self.bias.detach() if self.bias is not None else None
 
     def run(self, x, emb=None, residual=None, scale=1.0, act=SDEO_ACT_NONE, out_fp32=False, stream=False, emb_step=None,
-            gn_stats=False, row_stats=False, pad_hi=0):
+            gn_stats=False, row_stats=False, pad_hi=0, out_f32=None, out_twin=None):
         """x: internal tensor (bf16 or fp32 stream) or CatPair. Returns an internal bf16 tensor; fp32 NHWC-physical when
         out_fp32; an fp32 stream tensor with a bf16 twin when `stream`. A bf16 output whose channel count is not a
         multiple of 8 is zero-padded to one (so a following conv can TMA it)."""
@@ -290,8 +290,11 @@ class Conv2d(nn.Conv2d):
             ho, wo = (h + 2 * pd + pad_hi - k) // s + 1, (w + 2 * pd + pad_hi - k) // s + 1
             out = torch.empty((n, ho, wo, (cout + 7) // 8 * 8), dtype=BF16, device=self.weight.device)
             ops.memset(out, 0)
+        if out_f32 is not None:   # stream output written into caller-owned NHWC buffers (fp32 + bf16 twin)
+            assert stream and out_twin is not None
+            out = out_f32
         kw = dict(bias=self.bias_f32(), emb=emb, residual=res, scale=scale, act=act, stride=self.stride[0],
-                  out_fp32=out_fp32 or stream, out=out, twin=stream, emb_step=emb_step, pad_hi=pad_hi,
+                  out_fp32=out_fp32 or stream, out=out, out2=out_twin, twin=stream, emb_step=emb_step, pad_hi=pad_hi,
                   gn_stats=gn_stats and (out_fp32 or stream or FOLD_GN or BF16_GN_STATS) and FUSE_GN_STATS,
                   row_stats=row_stats and (out_fp32 or stream) and FOLD_LN)
         if gnf is not None:

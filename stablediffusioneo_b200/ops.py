@@ -143,7 +143,7 @@ def pack_geglu_bias(bias, geglu_bn):
 
 def conv2d(x, pw, x2=None, bias=None, emb=None, residual=None, scale=1.0, act=SDEO_ACT_NONE, stride=1, out=None,
            out_fp32=False, epi_mode=SDEO_EPI_NORMAL, qkv=None, twin=False, emb_step=None, gn_stats=False, row_stats=False,
-           ln=None, pad_hi=0, gnf=None, up2_phase=0):
+           ln=None, pad_hi=0, gnf=None, up2_phase=0, out2=None):
     """x: [N,H,W,C1] bf16 (+ optional x2 [N,H,W,C2] = fused torch.cat along channels). Returns [N,Ho,Wo,cout].
     residual may be bf16 or fp32. out_fp32 + twin=True additionally writes a bf16 copy and returns (y_f32, y_bf16).
     emb: fp32 [N, cout] (row = sample), or with emb_step (int32 device scalar) a table [S, cout] whose row *emb_step is
@@ -219,10 +219,14 @@ def conv2d(x, pw, x2=None, bias=None, emb=None, residual=None, scale=1.0, act=SD
             assert residual.shape[:3] == (n, ho, wo) and residual.shape[3] >= cols and residual.is_contiguous()
             a.residual, a.ldr = _ptr(residual), residual.shape[3]
             a.residual_f32 = 1 if residual.dtype == torch.float32 else 0
-    out2 = None
+    if not twin:
+        assert out2 is None
     if twin:
         assert out_fp32 and epi_mode == SDEO_EPI_NORMAL
-        out2 = torch.empty(out.shape, dtype=BF16, device=x.device)
+        if out2 is None:
+            out2 = torch.empty(out.shape, dtype=BF16, device=x.device)
+        else:
+            assert out2.shape == out.shape and out2.dtype == BF16 and out2.is_contiguous()
         a.y2, a.ldy2 = _ptr(out2), out2.shape[3]
     ws = _workspaces.conv(x.device)
     a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
@@ -592,6 +596,20 @@ def mask_blend(x0, noise, img, mask, a, b):
     check(lib.sdeo_mask_blend_f32(_ptr(x0), _ptr(noise), _ptr(img), _ptr(mask), _ptr(a), _ptr(b), _ptr(out), n, c,
                                   mask.shape[1], h * w, _stream()), "mask_blend")
     return out
+
+
+def mask_blend_table_(img, orig_table, mask, step_idx):
+    """In place: img = mask * orig_table[*step_idx] + (1 - mask) * img (fp32 [N, C, H, W]; orig_table [S, N, C, H, W]; mask
+    [N, 1 or C, H, W]; step_idx int32 device scalar) -- the inpainting blend as a node of the captured step graph."""
+    lib = _lib.load()
+    for t, name in ((orig_table, "orig_table"), (img, "img"), (mask, "mask")):
+        _req(t, torch.float32, name)
+    _req(step_idx, torch.int32, "step_idx")
+    n, c, h, w = img.shape
+    assert orig_table.shape[1:] == img.shape and mask.shape[0] == n and mask.shape[2:] == img.shape[2:]
+    check(lib.sdeo_mask_blend_table_f32(_ptr(orig_table), _ptr(img), _ptr(mask), _ptr(img), _ptr(step_idx), n, c,
+                                        mask.shape[1], h * w, _stream()), "mask_blend_table")
+    return img
 
 
 def set_autotune(enable=True):

@@ -154,6 +154,7 @@ def test_tiny_control_modes_vs_oracle(tiny, cuda_device):
             sampler = DDIMSampler(model)
             samples, _ = sampler.sample(4, 1, (4, 8, 16), cond, verbose=False, eta=0.0, x_T=x_T,
                                         unconditional_guidance_scale=9.0, unconditional_conditioning=un_d)
+            assert sampler._engine is not None and sampler._engine.guess == guess   # guess mode runs in the engine too
             with torch.no_grad():
                 ref_s, _ = O.ddim_sample(eps_fn, x_c, cond_c, un_c, S=4, scale=9.0)
             assert rel_l2(samples, ref_s) < 3e-2, guess
