@@ -311,13 +311,18 @@ def timed_steps(eng, steps, warmup, dist, dev, min_seconds=1.0, clocks_for=None)
     return elapsed_ms / repeats, repeats, eager, (clocks.stop() if clocks is not None else None)
 
 
-def denoise_config(model, latent_hw, batch, steps, warmup, dist, dev, world, pk, name):
-    """One of the other BASELINE configs as a device-resident + end-to-end measurement: builds its own engine."""
+def denoise_config(model, latent_hw, batch, steps, warmup, dist, dev, world, pk, name, guess=False):
+    """One of the other BASELINE configs as a device-resident + end-to-end measurement: builds its own engine.
+    guess: hackathon.process(guess_mode=True) (canny2image_torch.py:48,54): no hint on the unconditional branch (the ControlNet
+    runs on the conditional rows only), control strengths 0.825^(12-i)."""
     from stablediffusioneo_b200.cldm.ddim_hacked import DDIMSampler
     sampler = DDIMSampler(model)
     x_T, ctx_c, ctx_u, hint = host_inputs(pin=True, latent_hw=latent_hw, batch=batch)
     cond = {"c_concat": [hint], "c_crossattn": [ctx_c]}
-    uncond = {"c_concat": [hint], "c_crossattn": [ctx_u]}
+    uncond = {"c_concat": None if guess else [hint], "c_crossattn": [ctx_u]}
+    saved_scales = list(model.control_scales)
+    if guess:
+        model.control_scales = [1.0 * (0.825 ** float(12 - i)) for i in range(13)]
 
     def sample():
         out, _ = sampler.sample(S_DDIM, batch, (4,) + tuple(latent_hw), cond, verbose=False, eta=0.0, x_T=x_T,
@@ -354,6 +359,7 @@ def denoise_config(model, latent_hw, batch, steps, warmup, dist, dev, world, pk,
                         "note": "whole step (all kernels) vs BASELINE.md section 2 FLOPs; sustained cuBLAS bf16 peak"}}
     del sampler._engine
     sampler._engine = None
+    model.control_scales = saved_scales
     torch.cuda.empty_cache()
     return res
 
@@ -399,13 +405,14 @@ def other_configs(model, args, dist, dev, world, pk, rank):
         jobs += [("configs[3] SD1.5 UNet+ControlNet 768x768 batch 4, DDIM 20, CFG 9", "denoise", (96, 96), 4, 10),
                  ("256x384 batch 4 per GPU (images/s)", "denoise", (32, 48), 4, 20),
                  ("256x384 batch 8 per GPU (images/s)", "denoise", (32, 48), 8, 20),
+                 ("256x384 batch 1, guess mode (no ControlNet on the unconditional branch, strengths 0.825^(12-i))", "guess", (32, 48), 1, 20),
                  ("configs[4] VAE decode 512x512 batch 16", "vae", (64, 64), 16, 0),
                  ("VAE decode 256x384 batch 1 (the configs[1] image)", "vae", (32, 48), 1, 0)]
     out = []
     for name, kind, hw, batch, steps in jobs:
         try:
-            if kind == "denoise":
-                out.append(denoise_config(model, hw, batch, steps, 3, dist, dev, world, pk, name))
+            if kind in ("denoise", "guess"):
+                out.append(denoise_config(model, hw, batch, steps, 3, dist, dev, world, pk, name, guess=kind == "guess"))
             else:
                 out.append(vae_config(model, hw, batch, dev, pk, name))
         except Exception as ex:  # noqa: BLE001

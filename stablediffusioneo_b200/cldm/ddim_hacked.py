@@ -67,8 +67,18 @@ class DDIMSampler(object):
                        sqrt_one_minus_alphas=np.asarray(np.sqrt(1. - ddim_alphas), dtype=np.float64))
 
     # --------------------------------------------------------------------------------------------------------
-    def _coef_row(self, index, scale):
-        """The six scalars of one step (ddim_hacked.py:208-230) as the fused kernel's coefficient row."""
+    def _coef_row(self, index, scale, use_original_steps=False):
+        """The six scalars of one step (ddim_hacked.py:208-230) as the fused kernel's coefficient row.
+        use_original_steps (:203-206): the 1000-step DDPM tables instead of the DDIM subsequence. (The reference reads the
+        sigmas from `self.model.ddim_sigmas_for_original_num_steps`, a buffer that lives on the SAMPLER -- its own
+        use_original_steps path dies with an AttributeError; the sampler's buffer is what it meant.)"""
+        if use_original_steps:
+            a_t = float(self.alphas_cumprod[index])
+            a_prev = float(self.alphas_cumprod_prev[index])
+            sigma_t = float(self.ddim_sigmas_for_original_num_steps[index])
+            sqrt_1m_at = float(self.sqrt_one_minus_alphas_cumprod[index])
+            return [float(scale), sqrt_1m_at, 1.0 / math.sqrt(a_t), math.sqrt(a_prev),
+                    math.sqrt(max(1.0 - a_prev - sigma_t ** 2, 0.0)), sigma_t, 0.0, 0.0]
         a_t = float(self._h["alphas"][index])
         a_prev = float(self._h["alphas_prev"][index])
         sigma_t = float(self._h["sigmas"][index])
@@ -150,11 +160,10 @@ class DDIMSampler(object):
         elif timesteps is not None and not ddim_use_original_steps:
             subset_end = int(min(timesteps / self.ddim_timesteps.shape[0], 1) * self.ddim_timesteps.shape[0]) - 1
             timesteps = self.ddim_timesteps[:subset_end]
-        if ddim_use_original_steps:
-            raise NotImplementedError("ddim_use_original_steps is not on the ControlNet-SD1.5 path")
         intermediates = {'x_inter': [img], 'pred_x0': [img]}
-        time_range = np.flip(timesteps)
-        total_steps = timesteps.shape[0]
+        # ddim_hacked.py:144-145: all ddpm_num_timesteps steps, latest first, when ddim_use_original_steps
+        time_range = list(reversed(range(0, timesteps))) if ddim_use_original_steps else np.flip(timesteps)
+        total_steps = timesteps if ddim_use_original_steps else timesteps.shape[0]
         iterator = tqdm(time_range, desc='DDIM Sampler', total=total_steps, disable=not verbose)
         for i, step in enumerate(iterator):
             index = total_steps - i - 1
@@ -166,7 +175,7 @@ class DDIMSampler(object):
             if ucg_schedule is not None:
                 assert len(ucg_schedule) == len(time_range)
                 unconditional_guidance_scale = ucg_schedule[i]
-            img, pred_x0 = self.p_sample_ddim(img, cond, ts, index=index, use_original_steps=False,
+            img, pred_x0 = self.p_sample_ddim(img, cond, ts, index=index, use_original_steps=ddim_use_original_steps,
                                               quantize_denoised=quantize_denoised, temperature=temperature,
                                               noise_dropout=noise_dropout, score_corrector=score_corrector,
                                               corrector_kwargs=corrector_kwargs,
@@ -187,13 +196,13 @@ class DDIMSampler(object):
                       temperature=1., noise_dropout=0., score_corrector=None, corrector_kwargs=None,
                       unconditional_guidance_scale=1., unconditional_conditioning=None, dynamic_threshold=None):
         """ddim_hacked.py:181-231. eps from model.apply_model (cond, then uncond); CFG + x0 + x_{t-1} in one kernel."""
-        if use_original_steps or quantize_denoised or score_corrector is not None or dynamic_threshold is not None \
+        if quantize_denoised or score_corrector is not None or dynamic_threshold is not None \
                 or noise_dropout > 0. or self.model.parameterization != "eps":
             raise NotImplementedError("option not on the ControlNet-SD1.5 path")
         guided = not (unconditional_conditioning is None or unconditional_guidance_scale == 1.)
         e_c = self.model.apply_model(x, t, c).contiguous()
         e_u = self.model.apply_model(x, t, unconditional_conditioning).contiguous() if guided else None
-        row = self._coef_row(index, unconditional_guidance_scale if guided else 1.0)
+        row = self._coef_row(index, unconditional_guidance_scale if guided else 1.0, use_original_steps)
         coef = torch.tensor([row], dtype=torch.float32, device=x.device)
         noise = None
         if row[5] != 0.0:
@@ -233,12 +242,14 @@ class DDIMSampler(object):
                unconditional_conditioning=None, callback=None):
         """Deterministic DDIM inversion (ddim_hacked.py:233-276): x_next = sqrt(a_next / a) x + sqrt(a_next) (sqrt(1/a_next
         - 1) - sqrt(1/a - 1)) eps, one fused pass per step. Needs make_schedule() first, like the reference."""
-        if use_original_steps:
-            raise NotImplementedError("use_original_steps is not on the ControlNet-SD1.5 path")
-        timesteps = self.ddim_timesteps
+        timesteps = np.arange(self.ddpm_num_timesteps) if use_original_steps else self.ddim_timesteps
         assert t_enc <= timesteps.shape[0]
         num_steps = t_enc
-        alphas_next, alphas = self._h["alphas"][:num_steps], self._h["alphas_prev"][:num_steps]
+        if use_original_steps:   # ddim_hacked.py:242-244
+            alphas_next = self.alphas_cumprod[:num_steps].cpu().numpy().astype(np.float64)
+            alphas = self.alphas_cumprod_prev[:num_steps].cpu().numpy().astype(np.float64)
+        else:
+            alphas_next, alphas = self._h["alphas"][:num_steps], self._h["alphas_prev"][:num_steps]
         x_next = x0.to(device=self.model.device, dtype=torch.float32).contiguous()
         intermediates, inter_steps = [], []
         for i in tqdm(range(num_steps), desc='Encoding Image', disable=True):
@@ -276,9 +287,7 @@ class DDIMSampler(object):
     def decode(self, x_latent, cond, t_start, unconditional_guidance_scale=1.0, unconditional_conditioning=None,
                use_original_steps=False, callback=None):
         """p_sample_ddim over the first t_start DDIM timesteps, latest first (ddim_hacked.py:294-317)."""
-        if use_original_steps:
-            raise NotImplementedError("use_original_steps is not on the ControlNet-SD1.5 path")
-        timesteps = self.ddim_timesteps[:t_start]
+        timesteps = (np.arange(self.ddpm_num_timesteps) if use_original_steps else self.ddim_timesteps)[:t_start]
         time_range = np.flip(timesteps)
         total_steps = timesteps.shape[0]
         x_dec = x_latent.to(device=self.model.device, dtype=torch.float32)

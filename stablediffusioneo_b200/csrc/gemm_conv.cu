@@ -1053,7 +1053,9 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tmA1, const CU
     // shared memory during the mainloop (read from global memory inside the epilogue they cost an L2 round trip per item
     // batch -- measured: the largest share of epilogue phase 2)
     const int nb = n_tile * p.BN;
-    const long long erow = emb_in_colv ? (p.emb_step ? __ldg(p.emb_step) : n0) : 0;
+    // (the null tile of an odd PAIR grid lies beyond the last sample: clamp its row -- it read 4 * cout bytes past the end of
+    //  emb, an illegal address whenever emb happened to end a mapped segment; its results are discarded either way)
+    const long long erow = emb_in_colv ? (p.emb_step ? __ldg(p.emb_step) : (n0 < p.N ? n0 : p.N - 1)) : 0;
     for (int c = (int)threadIdx.x - 192; c < p.BN; c += kHelperThreads) {
       const int n = nb + c;
       float v = 0.f, cs = 0.f;
@@ -1901,7 +1903,21 @@ bool tune_shape(const sdeo_conv_args* a, void* stream, Tuned* best) {
       const int ctas = mt * pl.n_tiles * pl.splits;
       if (sp > 1 && ctas > cta_limit()) continue;  // K slices must not spill into a second wave
       if (g_cta_budget > 0 && ctas > cta_limit() && any_within_budget(a, base)) continue;  // honour the CTA budget
-      if (launch_conv(a, pl, stream) != 0) { (void)cudaGetLastError(); continue; }
+      if (launch_conv(a, pl, stream) != 0) {
+        (void)cudaGetLastError();
+        if (getenv("SDEO_TUNE_VERBOSE"))
+          fprintf(stderr, "sdeo tune: candidate bn %d splits %d halo %d pair %d occ2 %d failed to launch: %s\n", bn, sp, halo, pair, occ2,
+                  sdeo_last_error());
+        continue;
+      }
+      if (getenv("SDEO_TUNE_VERBOSE")) {   // debugging aid: run every candidate to completion and name the one that faults
+        const cudaError_t ce = cudaStreamSynchronize(st);
+        if (ce != cudaSuccess) {
+          fprintf(stderr, "sdeo tune: candidate bn %d splits %d halo %d pair %d occ2 %d (n %d h %d w %d c1 %d cout %d k %d) FAULTED: %s\n", bn, sp,
+                  halo, pair, occ2, a->n, a->h, a->w, a->c1, a->cout, a->ksize, cudaGetErrorString(ce));
+          return false;
+        }
+      }
       // Timed COLD: inside a denoising step every layer's weights come from HBM (2.4 GB are streamed per step, the L2
       // holds 126 MB), so the L2 is flushed before each timed launch. Back-to-back launches of one layer would measure
       // L2-resident weights and favour configurations with few CTAs on the weight stream.

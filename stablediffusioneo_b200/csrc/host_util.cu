@@ -21,6 +21,15 @@ int check_launch(const char* what) {
   return SDEO_ECUDA;
 }
 
+bool sync_launches() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SDEO_SYNC_LAUNCH");
+    v = (e && e[0] && e[0] != '0') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 static int g_pdl = -1;
 bool pdl_enabled() {
   if (g_pdl < 0) {

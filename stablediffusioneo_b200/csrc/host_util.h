@@ -1,5 +1,6 @@
 // Host-side helpers shared by the C-ABI translation units: error reporting and TMA descriptor encoding.
 #pragma once
+#include <stdio.h>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -24,6 +25,7 @@ int encode_tmap_plain(CUtensorMap* out, const void* base, int elem_bytes, int ra
 
 // Programmatic dependent launch switch (default on; SDEO_NO_PDL=1 or sdeo_set_pdl(0) turns it off).
 bool pdl_enabled();
+bool sync_launches();
 
 // Launches `fn` with an optional thread-block cluster and, when enabled, the programmatic-stream-serialization
 // attribute. EVERY kernel launched through here must execute griddep_wait() before its first access to memory that an
@@ -56,6 +58,18 @@ int launch_k(const char* what, void (*fn)(KArgs...), dim3 grid, dim3 block, size
   if (e != cudaSuccess) {
     (void)cudaGetLastError();
     return set_error(-5 /* SDEO_ECUDA */, cudaGetErrorString(e));
+  }
+  cudaStreamCaptureStatus cap_ = cudaStreamCaptureStatusNone;
+  if (sync_launches() && cudaStreamIsCapturing(st, &cap_) == cudaSuccess && cap_ == cudaStreamCaptureStatusNone) {
+    // SDEO_SYNC_LAUNCH=1 (debugging aid): wait for the kernel and report ITS error under its own name
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      char buf[256];
+      snprintf(buf, sizeof(buf), "%s: kernel failed: %s (grid %u,%u,%u block %u smem %zu)", what, cudaGetErrorString(e), grid.x, grid.y,
+               grid.z, block.x, smem);
+      return set_error(-5 /* SDEO_ECUDA */, buf);
+    }
   }
   return check_launch(what);
 }

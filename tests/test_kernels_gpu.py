@@ -430,6 +430,29 @@ def test_groupnorm_from_conv_statistics(cuda_device, case, autotune):
     assert rel_l2(y_fused, y_plain) < 2e-3   # same math, different fp32 summation order (+ bf16 rounding flips)
 
 
+def test_conv2d_pair_null_tile_with_emb(cuda_device):
+    """CTA pairs over an ODD number of M tiles (n = 1, 16x24 -> three 128-pixel tiles + one null tile) with a per-sample
+    time-embedding row: the null tile lies beyond the last sample and must not read emb[n] (regression: it read 4 * cout
+    bytes past the end of emb -- an illegal address when emb ends a mapped block, as arranged here)."""
+    from stablediffusioneo_b200 import ops
+    dev = cuda_device
+    n, c, h, w = 1, 640, 16, 24
+    x = gen((n, c, h, w), 1, dev)
+    wt = gen((c, c, 3, 3), 2, dev) / math.sqrt(c * 9)
+    bias = gen((c,), 3, dev) * 0.1
+    block = torch.empty((20 << 20) // 4, dtype=torch.float32, device=dev)   # one allocator block; emb = its last row
+    emb = block[-c:].view(1, c)
+    emb.copy_(gen((1, c), 4, dev))
+    os.environ["SDEO_PAIR"] = "1"
+    try:
+        y = ops.conv2d(nhwc(x), ops.pack_conv_weight(wt), bias=bias, emb=emb, out_fp32=True, gn_stats=True)
+        torch.cuda.synchronize()
+    finally:
+        os.environ.pop("SDEO_PAIR", None)
+    ref = ref_conv(x, wt, bias, 1, emb=emb)
+    assert rel_l2(y.permute(0, 3, 1, 2), ref) < TOL
+
+
 @pytest.mark.parametrize("case", [
     # (n, cin, cout, h, w)
     (1, 512, 512, 32, 48),      # VAE decoder, first Upsample at 256x384

@@ -103,6 +103,46 @@ def test_encode_decode_stochastic(tiny, cuda_device, prec):
     assert rel_l2(enc2, ref) < prec[1]
 
 
+def test_use_original_steps(tiny, cuda_device, prec):
+    """use_original_steps (ddim_hacked.py:203-206, 236-244, 301): decode / encode over the 1000-step DDPM tables instead of
+    the DDIM subsequence, against the oracle's eps + the closed-form update with those tables. (The reference's own
+    p_sample_ddim reads the sigmas from the wrong object on this path and raises; the tables are what it specifies.)"""
+    import numpy as np
+    model, g = tiny
+    dev = cuda_device
+    _, cond, uncond = inputs_on(O.TINY, 8, 16, dev)
+    sd_unet, sd_cn, _ = oracle_weights(O.TINY, O.TINY_VAE)
+    _, cond_c, uncond_c = O.make_inputs(O.TINY, 1, 8, 16)
+    eps_fn = lambda x, t, c: O.apply_model(sd_unet, sd_cn, O.TINY, x, t, c)
+    ac = O.alphas_cumprod().astype(np.float32)
+    ac_prev = np.append(np.float32(1.0), ac[:-1])
+    s = _sampler(model)
+    s.make_schedule(ddim_num_steps=g["S"], ddim_eta=0.0, verbose=False)
+    x = torch.randn((1, 4, 8, 16), generator=torch.Generator().manual_seed(7))
+    t_start, scale = 3, 3.0
+    dec = s.decode(x.to(dev), cond, t_start=t_start, unconditional_guidance_scale=scale, unconditional_conditioning=uncond,
+                   use_original_steps=True)
+    ref = x.clone()
+    with torch.no_grad():
+        for step in reversed(range(t_start)):      # DDPM timesteps t_start-1 .. 0, index == timestep
+            t = torch.full((1,), step, dtype=torch.long)
+            e_c, e_u = eps_fn(ref, t, cond_c), eps_fn(ref, t, uncond_c)
+            e_t = e_u + scale * (e_c - e_u)
+            ref, _ = O.ddim_update(ref, e_t, float(ac[step]), float(ac_prev[step]), 0.0, float(np.sqrt(1.0 - ac[step])))
+    e1 = rel_l2(dec, ref)
+    enc, _ = s.encode(x.to(dev), cond, t_enc=3, use_original_steps=True)
+    ref = x.clone()
+    with torch.no_grad():
+        for i in range(3):                          # ddim_hacked.py:242-265 with alphas_cumprod[_prev][:num_steps]
+            t = torch.full((1,), i, dtype=torch.long)
+            e = eps_fn(ref, t, cond_c)
+            an, a = float(ac[i]), float(ac_prev[i])
+            ref = np.sqrt(an / a) * ref + np.sqrt(an) * (np.sqrt(1 / an - 1) - np.sqrt(1 / a - 1)) * e
+    e2 = rel_l2(enc, ref)
+    print(f"use_original_steps decode / encode rel L2 ({prec[0]}):", e1, e2)
+    assert e1 < 3 * prec[1] and e2 < prec[1]
+
+
 def test_asymmetric_pad_downsample_conv(cuda_device):
     """F.pad(x, (0,1,0,1)) + conv3x3 stride 2 padding 0 through sdeo_conv_args::pad_hi, even and odd sizes."""
     from stablediffusioneo_b200 import ops
