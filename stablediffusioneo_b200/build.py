@@ -53,14 +53,32 @@ def build(force=False, verbose=False):
     obj_dir = os.path.join(OUT_DIR, "obj")
     os.makedirs(obj_dir, exist_ok=True)
 
+    def unit_hash(src):
+        # one translation unit = its .cu + every header it may include (all of csrc's and the public one) + the flags
+        h = hashlib.sha256()
+        deps = [src] + sorted(n for n in os.listdir(CSRC) if n.endswith((".cuh", ".h"))) + ["../../include/sdeo.h"]
+        for name in deps:
+            with open(os.path.join(CSRC, name), "rb") as f:
+                h.update(name.encode())
+                h.update(f.read())
+        h.update(" ".join(NVCC_FLAGS).encode())
+        return h.hexdigest()
+
     def compile_one(src):
         obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        tag, want = obj + ".hash", unit_hash(src)
+        if not force and os.path.exists(obj) and os.path.exists(tag):
+            with open(tag) as f:
+                if f.read().strip() == want:
+                    return obj  # unchanged unit: keep its object (gemm_conv.cu alone takes minutes)
         cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd))
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+        with open(tag, "w") as f:
+            f.write(want)
         return obj
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:

@@ -863,7 +863,8 @@ extern "C" int32_t sdeo_groupnorm_f16_visits(int32_t cta, int32_t grid, int32_t 
 }
 
 // which kernel a call with this geometry runs on a device with `sms` SMs and clusters of up to `max_cluster` CTAs (<= 0: 148 / 8):
-// 2 resident (info[0] = cluster size, info[1] = pixel rows per CTA, info[2] = shared memory bytes), 0 streamed, 1 two launches
+// 2 resident (info[0] = cluster size, info[1] = pixel rows per CTA, info[2] = shared memory bytes), 1 two launches (the default
+// beyond a cluster), 0 streamed (only under SDEO_GN_F16_VARIANT=stream)
 extern "C" int sdeo_groupnorm_f16_variant(int32_t n, int32_t hw, int32_t c, int32_t groups, int32_t sms, int32_t max_cluster,
                                           int32_t* info) {
   if (n <= 0 || hw <= 0 || c <= 0 || groups <= 0 || c % 8 != 0 || c % groups != 0) return set_error(SDEO_EINVAL, "groupnorm_f16_variant: bad argument");
@@ -876,6 +877,10 @@ extern "C" int sdeo_groupnorm_f16_variant(int32_t n, int32_t hw, int32_t c, int3
   GSGeom g;
   size_t smem = 0;
   int G = 0;
+  // samples that do not fit a cluster take the two-launch grid (round 2: its pipelined row loads run both passes at ~5.9 TB/s,
+  // ahead of the streamed kernel on every shape measured); SDEO_GN_F16_VARIANT=stream opts into the streamed kernel
+  const char* variant = getenv("SDEO_GN_F16_VARIANT");
+  if (!(variant && variant[0] == 's')) return 1;
   return gs_plan(n, hw, c, groups, sms > 0 ? sms : 148, -1, &g, &smem, &G) ? 1 : 0;
 }
 
@@ -901,7 +906,7 @@ extern "C" int sdeo_groupnorm_nhwc_f16(const void* x, const float* gamma, const 
   cudaStream_t st = (cudaStream_t)stream;
   const dim3 one(1, 1, 1);
   const int mode = with_silu ? swish_mode : 0;
-  const char* variant = getenv("SDEO_GN_F16_VARIANT");  // "stream" | "resident" | unset: resident when the sample fits a cluster
+  const char* variant = getenv("SDEO_GN_F16_VARIANT");  // "stream" | "resident" | unset: resident when the sample fits a cluster, else two launches
   if (!two_pass && !(variant && variant[0] == 's')) {
     RGeom rg;
     size_t rsmem = 0;
@@ -915,7 +920,9 @@ extern "C" int sdeo_groupnorm_nhwc_f16(const void* x, const float* gamma, const 
   GSGeom g;
   size_t smem = 0;
   int G = 0;
-  if (two_pass || gs_plan(n, hw, c, groups, gs_sm_count(), lag_env, &g, &smem, &G))
+  // default for samples beyond a cluster: the two-launch grid (statistics + apply, norm.cu); the streamed single-launch
+  // kernel below (spin-waits on slots of co-resident CTAs) runs only when asked for by SDEO_GN_F16_VARIANT=stream
+  if (two_pass || !(variant && variant[0] == 's') || gs_plan(n, hw, c, groups, gs_sm_count(), lag_env, &g, &smem, &G))
     return groupnorm_f16_two_pass(x, gamma, beta, y, n, hw, c, groups, eps, with_silu, workspace, workspace_bytes, stream);
   const size_t nparts_ = (size_t)(g.chunks < g.ngroups * G ? g.chunks : g.ngroups * G);
   const size_t slot_bytes = (size_t)n * (nparts_ + 1 + (nparts_ + kGSTeam - 1) / kGSTeam) * groups * sizeof(unsigned long long);

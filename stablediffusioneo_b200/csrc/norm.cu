@@ -9,6 +9,8 @@
 namespace sdeo {
 
 constexpr int kGNThreads = 256;
+constexpr int kGNBigPerSM = 6;  // CTAs per SM the two-pass grid is capped at (gn_geometry)
+constexpr int kGNMaxChunks = 256;  // CTAs per sample the two-pass grid is capped at (the apply pass folds that many partials)
 
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
   float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
@@ -67,9 +69,64 @@ __device__ __forceinline__ void gn_load8(const T* x1, const T* x2, int c1, int c
   else load8(x2 + pix * c2 + (c - c1), f);
 }
 
+// ---- software-pipelined row loads (the big-tensor passes are HBM-bound: bytes in flight per SM are what set their speed) ----
+// An 8-channel vector as it was loaded, kept packed until it is used (4 registers for the 16-bit types). A thread
+// holds two batches of kGNBatch<T> of them: the batch being processed and the next one, already in flight.
+template <typename T>
+struct Raw8 { uint4 u; };
+template <>
+struct Raw8<float> { float4 a, b; };
+template <typename T>
+struct GNBatch { static constexpr int H = 4; };
+template <>
+struct GNBatch<float> { static constexpr int H = 2; };
+
+__device__ __forceinline__ void raw_load(const __nv_bfloat16* p, Raw8<__nv_bfloat16>& r) { r.u = __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void raw_load(const __half* p, Raw8<__half>& r) { r.u = __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void raw_load(const float* p, Raw8<float>& r) {
+  r.a = __ldg(reinterpret_cast<const float4*>(p));
+  r.b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+}
+__device__ __forceinline__ void raw_zero(Raw8<__nv_bfloat16>& r) { r.u = make_uint4(0u, 0u, 0u, 0u); }
+__device__ __forceinline__ void raw_zero(Raw8<__half>& r) { r.u = make_uint4(0u, 0u, 0u, 0u); }
+__device__ __forceinline__ void raw_zero(Raw8<float>& r) { r.a = make_float4(0.f, 0.f, 0.f, 0.f); r.b = r.a; }
+__device__ __forceinline__ void raw_unpack(const Raw8<__nv_bfloat16>& r, float* f) { unpack8(r.u, f); }
+__device__ __forceinline__ void raw_unpack(const Raw8<__half>& r, float* f) {
+  const __half2* h = reinterpret_cast<const __half2*>(&r.u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = __half22float2(h[j]);
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void raw_unpack(const Raw8<float>& r, float* f) {
+  f[0] = r.a.x; f[1] = r.a.y; f[2] = r.a.z; f[3] = r.a.w; f[4] = r.b.x; f[5] = r.b.y; f[6] = r.b.z; f[7] = r.b.w;
+}
+
+// This thread's column of the virtual concat [x1 | x2]: base pointer of channel vector `v` at row 0 and the row pitch.
+template <typename T>
+__device__ __forceinline__ const T* gn_column(const T* x1, const T* x2, int c1, int c2, int v, int* ld) {
+  const int c = v * 8;
+  if (c < c1) { *ld = c1; return x1 + c; }
+  *ld = c2;
+  return x2 + (c - c1);
+}
+
+// Rows pp, pp + R, ... (H of them) of one column; rows at or beyond p_end load nothing and read as zero.
+template <typename T>
+__device__ __forceinline__ void gn_load_batch(const T* col, int ld, long long row0, int pp, int R, int p_end, Raw8<T>* r) {
+#pragma unroll
+  for (int u = 0; u < GNBatch<T>::H; ++u) {
+    const int p = pp + u * R;
+    if (p < p_end) raw_load(col + (row0 + p) * ld, r[u]);
+    else raw_zero(r[u]);
+  }
+}
+
 // Pass 1: per (sample, pixel-chunk) partial sums per group -> ws[n][chunk][group][2]
 template <typename T>
-__global__ void __launch_bounds__(kGNThreads)
+__global__ void __launch_bounds__(kGNThreads, 3)
 gn_stats_kernel(const T* __restrict__ x1, const T* __restrict__ x2, float* __restrict__ ws,
                 int hw, int c1, int c2, int groups, int chunks, int ppc) {
   const int trc = trace_start(3);
@@ -99,24 +156,26 @@ gn_stats_kernel(const T* __restrict__ x1, const T* __restrict__ x2, float* __res
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
     if (active && v < cv) {
+      constexpr int H = GNBatch<T>::H;
+      int ld;
+      const T* col = gn_column(x1, x2, c1, c2, v, &ld);
+      const long long row0 = (long long)n * hw;
+      Raw8<T> cur[H], nxt[H];
       int pp = p_begin + tr;
-      for (; pp + 3 * R < p_end; pp += 4 * R) {  // 4 independent loads in flight per thread
-        float f0[8], f1[8], f2[8], f3[8];
-        gn_load8(x1, x2, c1, c2, (long long)n * hw + pp, v, f0);
-        gn_load8(x1, x2, c1, c2, (long long)n * hw + pp + R, v, f1);
-        gn_load8(x1, x2, c1, c2, (long long)n * hw + pp + 2 * R, v, f2);
-        gn_load8(x1, x2, c1, c2, (long long)n * hw + pp + 3 * R, v, f3);
+      gn_load_batch(col, ld, row0, pp, R, p_end, cur);
+      while (pp < p_end) {  // the next batch is in flight while this one is summed
+        const int pn = pp + H * R;
+        gn_load_batch(col, ld, row0, pn, R, p_end, nxt);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          s[j] += (f0[j] + f1[j]) + (f2[j] + f3[j]);
-          q[j] += (f0[j] * f0[j] + f1[j] * f1[j]) + (f2[j] * f2[j] + f3[j] * f3[j]);
+        for (int u = 0; u < H; ++u) {
+          float f[8];
+          raw_unpack(cur[u], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] = fmaf(f[j], f[j], q[j]); }
         }
-      }
-      for (; pp < p_end; pp += R) {
-        float f[8];
-        gn_load8(x1, x2, c1, c2, (long long)n * hw + pp, v, f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] += f[j] * f[j]; }
+        for (int u = 0; u < H; ++u) cur[u] = nxt[u];
+        pp = pn;
       }
     }
     if (active) {
@@ -149,9 +208,44 @@ gn_stats_kernel(const T* __restrict__ x1, const T* __restrict__ x2, float* __res
   }  trace_mark(trc, 3);
 }
 
+// One column (8 channels) of a CTA's pixel rows: y = x * a + b (+SiLU), rows pp0, pp0 + R, ... < p_end; the next batch
+// of rows is in flight while this one is normalised and stored. Output: 16-bit, bf16 (fp16 for fp16 inputs).
+template <typename T>
+__device__ __forceinline__ void gn_apply_column(const T* col, int ld, long long row0, int pp0, int R, int p_end,
+                                                const float* a, const float* b, int with_silu, __nv_bfloat16* ycol, int C) {
+  constexpr int H = GNBatch<T>::H;
+  Raw8<T> cur[H], nxt[H];
+  int pp = pp0;
+  gn_load_batch(col, ld, row0, pp, R, p_end, cur);
+  while (pp < p_end) {
+    const int pn = pp + H * R;
+    gn_load_batch(col, ld, row0, pn, R, p_end, nxt);
+#pragma unroll
+    for (int u = 0; u < H; ++u) {
+      const int p = pp + u * R;
+      if (p < p_end) {
+        float f[8];
+        raw_unpack(cur[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float t = fmaf(f[j], a[j], b[j]);
+          f[j] = with_silu ? silu_f(t) : t;
+        }
+        uint4 o;
+        o.x = pack2_out<T>(f[0], f[1]); o.y = pack2_out<T>(f[2], f[3]);
+        o.z = pack2_out<T>(f[4], f[5]); o.w = pack2_out<T>(f[6], f[7]);
+        *reinterpret_cast<uint4*>(ycol + (row0 + p) * C) = o;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < H; ++u) cur[u] = nxt[u];
+    pp = pn;
+  }
+}
+
 // Pass 2: finalize mean / rstd per group from the partials, normalise, affine, optional SiLU, store bf16.
 template <typename T>
-__global__ void __launch_bounds__(kGNThreads)
+__global__ void __launch_bounds__(kGNThreads, 3)
 gn_apply_kernel(const T* __restrict__ x1, const T* __restrict__ x2,
                 const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ ws,
                 __nv_bfloat16* __restrict__ y, int hw, int c1, int c2, int groups, int chunks, int ppc, float eps,
@@ -174,10 +268,18 @@ gn_apply_kernel(const T* __restrict__ x1, const T* __restrict__ x2,
     const int g = threadIdx.x % groups, lane_k = threadIdx.x / groups;
     float s = 0.f, q = 0.f;
     if (lane_k < L) {
-      for (int k = lane_k; k < chunks; k += L) {
-        const float2 v2 = __ldcg(reinterpret_cast<const float2*>(ws + (((size_t)n * chunks + k) * groups + g) * 2));
-        s += v2.x;
-        q += v2.y;
+      // eight independent loads per round trip to L2 (a mid-size sample has ~220 chunks: 4 rounds instead of 28), added
+      // in chunk order
+      const float2* src = reinterpret_cast<const float2*>(ws) + (size_t)n * chunks * groups + g;
+      for (int k0 = lane_k; k0 < chunks; k0 += 8 * L) {
+        float2 v2[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int k = k0 + u * L;
+          v2[u] = k < chunks ? __ldcg(src + (size_t)k * groups) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { s += v2[u].x; q += v2[u].y; }
       }
     }
     s_fold[threadIdx.x] = make_float2(s, q);
@@ -217,38 +319,9 @@ gn_apply_kernel(const T* __restrict__ x1, const T* __restrict__ x2,
       a[j] *= s_rstd[g];
       b[j] -= s_mean[g] * a[j];
     }
-    int pp = p_begin + tr;
-    for (; pp + 3 * R < p_end; pp += 4 * R) {  // 4 independent loads in flight per thread
-      float f[4][8];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) gn_load8(x1, x2, c1, c2, (long long)n * hw + pp + u * R, v, f[u]);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float t = f[u][j] * a[j] + b[j];
-          f[u][j] = with_silu ? silu_f(t) : t;
-        }
-        uint4 o;
-        o.x = pack2_out<T>(f[u][0], f[u][1]); o.y = pack2_out<T>(f[u][2], f[u][3]);
-        o.z = pack2_out<T>(f[u][4], f[u][5]); o.w = pack2_out<T>(f[u][6], f[u][7]);
-        *reinterpret_cast<uint4*>(y + ((long long)n * hw + pp + u * R) * C + v * 8) = o;
-      }
-    }
-    for (; pp < p_end; pp += R) {
-      const long long pix = (long long)n * hw + pp;
-      float f[8];
-      gn_load8(x1, x2, c1, c2, pix, v, f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float t = f[j] * a[j] + b[j];
-        f[j] = with_silu ? silu_f(t) : t;
-      }
-      uint4 o;
-      o.x = pack2_out<T>(f[0], f[1]); o.y = pack2_out<T>(f[2], f[3]);
-      o.z = pack2_out<T>(f[4], f[5]); o.w = pack2_out<T>(f[6], f[7]);
-      *reinterpret_cast<uint4*>(y + pix * C + v * 8) = o;
-    }
+    int ld;
+    const T* col = gn_column(x1, x2, c1, c2, v, &ld);
+    gn_apply_column<T>(col, ld, (long long)n * hw, p_begin + tr, R, p_end, a, b, with_silu, y + v * 8, C);
   }
   trace_mark(trc, 3);
 }
@@ -434,25 +507,36 @@ static int launch_gn_cluster(const void* x1, const void* x2, const float* gamma,
                   eps, with_silu, cache_rows);
 }
 
-static void gn_geometry(int n, int hw, int* chunks, int* ppc) {
-  // about 1.5 CTAs per SM over the batch, and at least 16 pixels per CTA (these tensors are small: per-CTA fixed
+// Grid of the two-pass kernels: `chunks` CTAs per sample of `ppc` pixel rows each. row_bytes = bytes of one pixel row.
+static void gn_geometry(int n, int hw, long long row_bytes, int* chunks, int* ppc) {
+  // small tensors (the denoiser's): about 1.5 CTAs per SM over the batch, and at least 16 pixels per CTA (per-CTA fixed
   // costs and the apply kernel's per-CTA fold over the chunk partials dominate otherwise)
   static int per_sm_x2 = -1;  // CTAs per SM (x2) over the batch; SDEO_GN_CTAS_X2 overrides (tuning aid)
   if (per_sm_x2 < 0) {
     const char* e = getenv("SDEO_GN_CTAS_X2");
     per_sm_x2 = e ? atoi(e) : 3;
   }
-  // big tensors (the VAE decoder: up to 16 x 512 x 512 pixels) are bandwidth-bound, and 222 CTAs with four 16-byte loads
-  // per thread keep ~3.6 MB in flight -- measured 1.2 TB/s: one CTA per 256 pixels of the batch, up to 8 per SM
-  long long total = ((long long)n * hw) / 256;
-  if (total > 148 * 8) total = 148 * 8;
+  // larger ones (the VAE decoder: up to 16 x 512 x 512 pixels) are bandwidth-bound: one CTA per 32 KB of the batch, up to
+  // kGNBigPerSM per SM = two waves of the three CTAs an SM holds (the pipelined row loads keep 4-8 vectors per thread in
+  // flight: 48-96 KB per SM), and never more than kGNMaxChunks per sample: every apply CTA folds its sample's partials
+  // (8 lanes x 8 loads per L2 round trip: 256 chunks = 4 round trips)
+  long long total = ((long long)n * hw * row_bytes) >> 15;
+  const bool big = total > 148 * kGNBigPerSM;
+  if (big) total = 148 * kGNBigPerSM;
   if (total < 148 * per_sm_x2 / 2) total = 148 * per_sm_x2 / 2;
-  int want = (int)((total + n - 1) / n);
+  // big tensors: never more CTAs than the cap (whole waves of the resident set); small ones: round up
+  int want = big ? (int)(total / n) : (int)((total + n - 1) / n);
+  if (want > kGNMaxChunks) want = kGNMaxChunks;
   if (want < 1) want = 1;
   int p = (hw + want - 1) / want;
   if (p < 16) p = hw < 16 ? hw : 16;
   *ppc = p;
   *chunks = (hw + p - 1) / p;
+}
+// Upper bound of `chunks` over every row size (the workspace queries do not know the channel count).
+static int gn_max_chunks(int n, int hw) {
+  (void)n;
+  return hw < kGNMaxChunks ? hw : kGNMaxChunks;  // chunks <= want <= kGNMaxChunks, and a chunk holds at least one pixel
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -548,38 +632,9 @@ gn_apply_stats_kernel(const T* __restrict__ x1, const T* __restrict__ x2, const 
         a[j] *= s_rstd[g];
         b[j] -= s_mean[g] * a[j];
       }
-      int pp = p_begin + tr;
-      for (; pp + 3 * R < p_end; pp += 4 * R) {  // 4 independent loads in flight per thread
-        float f[4][8];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) gn_load8(x1, x2, c1, c2, (long long)n * hw + pp + u * R, v, f[u]);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float t = f[u][j] * a[j] + b[j];
-            f[u][j] = with_silu ? silu_f(t) : t;
-          }
-          uint4 o;
-          o.x = pack_bf16x2(f[u][0], f[u][1]); o.y = pack_bf16x2(f[u][2], f[u][3]);
-          o.z = pack_bf16x2(f[u][4], f[u][5]); o.w = pack_bf16x2(f[u][6], f[u][7]);
-          *reinterpret_cast<uint4*>(y + ((long long)n * hw + pp + u * R) * C + v * 8) = o;
-        }
-      }
-      for (; pp < p_end; pp += R) {
-        const long long pix = (long long)n * hw + pp;
-        float f[8];
-        gn_load8(x1, x2, c1, c2, pix, v, f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float t = f[j] * a[j] + b[j];
-          f[j] = with_silu ? silu_f(t) : t;
-        }
-        uint4 o;
-        o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-        o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-        *reinterpret_cast<uint4*>(y + pix * C + v * 8) = o;
-      }
+      int ld;
+      const T* col = gn_column(x1, x2, c1, c2, v, &ld);
+      gn_apply_column<T>(col, ld, (long long)n * hw, p_begin + tr, R, p_end, a, b, with_silu, y + v * 8, C);
     }
   }
   trace_mark(trc, 3);
@@ -656,9 +711,7 @@ using namespace sdeo;
 SDEO_DEFINE_TRACE_SETTER(sdeo_trace_set_norm)
 
 extern "C" size_t sdeo_groupnorm_workspace_bytes(int32_t n, int32_t hw, int32_t groups) {
-  int chunks, ppc;
-  gn_geometry(n, hw, &chunks, &ppc);
-  return (size_t)n * chunks * groups * 2 * sizeof(float);
+  return (size_t)n * gn_max_chunks(n, hw) * groups * 2 * sizeof(float);
 }
 
 extern "C" int sdeo_groupnorm_nhwc(const void* x1, const void* x2, int32_t x_f32, const float* gamma, const float* beta,
@@ -683,7 +736,7 @@ extern "C" int sdeo_groupnorm_nhwc(const void* x1, const void* x2, int32_t x_f32
     return launch_gn_cluster<__nv_bfloat16>(x1, x2, gamma, beta, y, n, hw, c1, c2, groups, eps, with_silu, (cudaStream_t)stream);
   }
   int chunks, ppc;
-  gn_geometry(n, hw, &chunks, &ppc);
+  gn_geometry(n, hw, (long long)C * (x_f32 ? 4 : 2), &chunks, &ppc);
   if (workspace_bytes < (size_t)n * chunks * groups * 2 * sizeof(float))
     return set_error(SDEO_EINVAL, "groupnorm: workspace too small");
   const size_t smem = (size_t)(2 * C + kGNThreads * 16) * sizeof(float);
@@ -722,9 +775,7 @@ extern "C" int sdeo_groupnorm_nhwc(const void* x1, const void* x2, int32_t x_f32
 // the streamed kernel in groupnorm_stream.cu, which owns the C entry point sdeo_groupnorm_nhwc_f16.
 namespace sdeo {
 size_t groupnorm_two_pass_workspace_bytes(int32_t n, int32_t hw, int32_t groups) {
-  int chunks, ppc;
-  gn_geometry(n, hw, &chunks, &ppc);
-  return (size_t)n * chunks * groups * 2 * sizeof(float);
+  return (size_t)n * gn_max_chunks(n, hw) * groups * 2 * sizeof(float);
 }
 int groupnorm_f16_two_pass(const void* x, const float* gamma, const float* beta, void* y, int32_t n, int32_t hw,
                                        int32_t c, int32_t groups, float eps, int32_t with_silu, void* workspace,
@@ -733,7 +784,7 @@ int groupnorm_f16_two_pass(const void* x, const float* gamma, const float* beta,
   if (n <= 0 || n > 65535 || hw <= 0 || groups <= 0 || groups > 64 || c % groups != 0 || c % 8 != 0)
     return set_error(SDEO_EINVAL, "groupnorm_f16: unsupported geometry (need C % groups == 0, C % 8 == 0, groups <= 64)");
   int chunks, ppc;
-  gn_geometry(n, hw, &chunks, &ppc);
+  gn_geometry(n, hw, (long long)c * 2, &chunks, &ppc);
   if (workspace_bytes < (size_t)n * chunks * groups * 2 * sizeof(float))
     return set_error(SDEO_EINVAL, "groupnorm_f16: workspace too small");
   const size_t smem = (size_t)(2 * c + kGNThreads * 16) * sizeof(float);

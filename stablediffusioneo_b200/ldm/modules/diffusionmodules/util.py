@@ -61,6 +61,19 @@ FOLD_GN = bool(os.environ.get("SDEO_GN_FOLD"))
 # per tile, on grids of thousands of tiles) costs the convs more (~5 ms) than the standalone statistics pass it replaces
 # (4.6 ms), and the apply pass then folds the partials first (+1.5 ms).
 BF16_GN_STATS = bool(os.environ.get("SDEO_BF16_GN_STATS"))
+# ... but SMALL bf16 outputs (the batch-1 decode: tens of tiles per conv, every launch latency-bound) do leave them: the
+# statistics launch disappears and the apply reads the tensor once. Limit in output elements (SDEO_BF16_GN_STATS_MAX).
+BF16_GN_STATS_MAX = int(os.environ.get("SDEO_BF16_GN_STATS_MAX", "0"))
+
+
+def _out_elems(x, cout, stride):
+    """Output elements of a same-padded conv over x (internal tensor / CatPair), or None when the shape is not at hand."""
+    t = x.a if isinstance(x, CatPair) else x
+    shp = getattr(t, "shape", None)
+    if shp is None or len(shp) != 4:
+        return None
+    n, _, h, w = shp
+    return n * ((h + stride - 1) // stride) * ((w + stride - 1) // stride) * cout
 
 
 class DeferredGN:
@@ -293,9 +306,13 @@ class Conv2d(nn.Conv2d):
         if out_f32 is not None:   # stream output written into caller-owned NHWC buffers (fp32 + bf16 twin)
             assert stream and out_twin is not None
             out = out_f32
+        small_out = False
+        if gn_stats and BF16_GN_STATS_MAX > 0 and not (out_fp32 or stream):
+            ne = _out_elems(x, cout, self.stride[0])
+            small_out = ne is not None and ne <= BF16_GN_STATS_MAX
         kw = dict(bias=self.bias_f32(), emb=emb, residual=res, scale=scale, act=act, stride=self.stride[0],
                   out_fp32=out_fp32 or stream, out=out, out2=out_twin, twin=stream, emb_step=emb_step, pad_hi=pad_hi,
-                  gn_stats=gn_stats and (out_fp32 or stream or FOLD_GN or BF16_GN_STATS) and FUSE_GN_STATS,
+                  gn_stats=gn_stats and (out_fp32 or stream or FOLD_GN or BF16_GN_STATS or small_out) and FUSE_GN_STATS,
                   row_stats=row_stats and (out_fp32 or stream) and FOLD_LN)
         if gnf is not None:
             y = ops.conv2d(x1, self.packed((x1.shape[3], x2.shape[3])) if x2 is not None else self.packed(), x2=x2, gnf=gnf, **kw)

@@ -305,11 +305,21 @@ def test_groupnorm_f16_variant_selection():
         assert lib.sdeo_groupnorm_f16_variant(n, h * w, c, 32, 148, 8, info) == 2
         cs, rpc, smem = list(info)
         assert cs in (1, 2, 4, 8) and rpc * cs >= h * w and (rpc - 1) * cs < h * w + cs and rpc * c * 2 < smem <= 220 * 1024
-    assert lib.sdeo_groupnorm_f16_variant(2, 32 * 48, 640, 32, 148, 8, info) == 0   # 1.9 MB per sample: needs 16 CTAs
-    assert lib.sdeo_groupnorm_f16_variant(2, 32 * 48, 640, 32, 148, 16, info) == 2 and info[0] == 16
-    assert lib.sdeo_groupnorm_f16_variant(2, 32 * 48, 960, 32, 148, 16, info) == 0  # 2.9 MB: streamed
-    assert lib.sdeo_groupnorm_f16_variant(16, 256 * 256, 256, 32, 148, 16, info) == 0
-    assert lib.sdeo_groupnorm_f16_variant(1, 64, 8192, 32, 148, 8, info) == 1       # more channel vectors than threads
+    saved = os.environ.pop("SDEO_GN_F16_VARIANT", None)
+    try:
+        # beyond a cluster: the two-launch grid by default, the streamed kernel only when asked for
+        assert lib.sdeo_groupnorm_f16_variant(2, 32 * 48, 640, 32, 148, 8, info) == 1   # 1.9 MB per sample: needs 16 CTAs
+        assert lib.sdeo_groupnorm_f16_variant(2, 32 * 48, 640, 32, 148, 16, info) == 2 and info[0] == 16
+        assert lib.sdeo_groupnorm_f16_variant(16, 256 * 256, 256, 32, 148, 16, info) == 1
+        os.environ["SDEO_GN_F16_VARIANT"] = "stream"
+        assert lib.sdeo_groupnorm_f16_variant(2, 32 * 48, 640, 32, 148, 8, info) == 0
+        assert lib.sdeo_groupnorm_f16_variant(2, 32 * 48, 960, 32, 148, 16, info) == 0  # 2.9 MB: streamed
+        assert lib.sdeo_groupnorm_f16_variant(16, 256 * 256, 256, 32, 148, 16, info) == 0
+        assert lib.sdeo_groupnorm_f16_variant(1, 64, 8192, 32, 148, 8, info) == 1       # more channel vectors than threads
+    finally:
+        os.environ.pop("SDEO_GN_F16_VARIANT", None)
+        if saved is not None:
+            os.environ["SDEO_GN_F16_VARIANT"] = saved
 
 
 def _gn_stream_protocol_model(lib, n, c, h, w, ng, bufs, sms=148, verbose=False):

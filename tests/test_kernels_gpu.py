@@ -338,6 +338,9 @@ GN_CASES = [
     (2, 1280, 0, 4, 6, 1e-5, True),
     (1, 128, 0, 64, 96, 1e-6, True),       # VAE: 4 channels per group
     (3, 512, 0, 9, 7, 1e-6, False),
+    (2, 128, 0, 384, 320, 1e-6, True),     # big-tensor grid (two waves of resident CTAs), pipelined row batches
+    (3, 64, 0, 301, 277, 1e-6, False),     # same, ragged: chunk tails shorter than a batch of rows
+    (5, 64, 32, 250, 200, 1e-5, True),     # same, over a concat with 3 channels per group
 ]
 
 
