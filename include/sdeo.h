@@ -213,7 +213,9 @@ size_t sdeo_groupnorm_f16_workspace_bytes(int32_t n, int32_t hw, int32_t c, int3
 int sdeo_groupnorm_f16_plan(int32_t n, int32_t hw, int32_t c, int32_t groups, int32_t sms, int32_t* plan);
 int32_t sdeo_groupnorm_f16_visits(int32_t cta, int32_t grid, int32_t tiles, int32_t lag, int32_t* out, int32_t cap);
 /* Which kernel sdeo_groupnorm_nhwc_f16 runs for a geometry on a device with `sms` SMs and clusters of up to `max_cluster`
- * CTAs (<= 0: 148 / 8): 2 = resident (the sample lives in the shared memory of one thread-block cluster: one read and one
+ * CTAs (<= 0: 148 / 8): 3 = slab (one CTA per sample and slab of whole groups, the slab parked in shared memory: one read,
+ * one write, nothing exchanged between CTAs, no workspace; info[0..2] = groups per slab, 16-byte vectors per slab row,
+ * shared memory bytes; slabs up to SDEO_GN_F16_SLAB_KB, default 128), 2 = resident (the sample lives in the shared memory of one thread-block cluster: one read and one
  * write from anywhere, no workspace; info[0..2] = cluster size, pixel rows per CTA, shared memory bytes), 1 = two launches
  * (statistics + apply over the whole GPU: the default for samples beyond a cluster), 0 = streamed (one persistent kernel;
  * only when the environment asks for it with SDEO_GN_F16_VARIANT=stream). */

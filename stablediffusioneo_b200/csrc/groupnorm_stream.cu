@@ -668,6 +668,175 @@ gn_resident_kernel(const __half* __restrict__ x, const float* __restrict__ gamma
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");  // peers are done reading this CTA's s_group
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Slab kernel (small samples: every UNet GroupNorm of the 256x384 workload): ONE CTA per (sample, slab of `sg` whole
+// groups), the slab -- hw rows of sg * cpg channels -- parked in the CTA's shared memory by per-thread cp.async. A CTA
+// owns complete groups, so nothing is exchanged between CTAs: no cluster, no barrier across CTAs, no workspace; the
+// tensor is read once and written once. A thread keeps one 8-channel column and rows tr, tr + R, ... through all three
+// phases (load, statistics, normalise).
+// sg = the smallest group count whose channels fill whole 16-byte vectors (cpg 10 -> 4 groups = 40 channels, ...).
+// Few, large slabs (2 x 320 @ 32x48: 16 slabs of 123 KB) are SPLIT: `split` CTAs each load the whole slab and compute the
+// same statistics redundantly (cheap: adds and FMAs out of shared memory, the extra loads are L2 hits), but each
+// normalises and stores only its own rows_per rows (the expensive part: Swish, stores) -- still nothing exchanged.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kSlabThreads = 512;
+constexpr int kSlabDefaultKB = 128;  // largest slab the default dispatch gives to the slab kernel (SDEO_GN_F16_SLAB_KB)
+struct SlabGeom {
+  int hw, C, cpg, sg, sv, slabs, tile_bytes;  // sv = 16-byte vectors per slab row, slabs per sample
+  int split, rows_per;                        // CTAs per slab (each normalises rows_per rows), see slab_plan
+  int threads;                                // CTA size: 256 when a slab holds few vectors, else kSlabThreads
+};
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+
+template <int kMode>
+__global__ void __launch_bounds__(kSlabThreads, 1)
+gn_slab_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+               __half* __restrict__ y, SlabGeom gm, float eps) {
+  griddep_launch_dependents();
+  griddep_wait();
+  extern __shared__ __align__(128) unsigned char gs_smem[];
+  __shared__ float s_mean[8], s_rstd[8];
+  const int tid = threadIdx.x;
+  const int sv = gm.sv, hw = gm.hw, C = gm.C, cpg = gm.cpg;
+  const int piece = blockIdx.x % gm.split, is = blockIdx.x / gm.split;
+  const int img = is / gm.slabs, slab = is - img * gm.slabs;
+  const int c0 = slab * gm.sg * cpg;
+  const int T = (int)blockDim.x;  // 256 for small slabs, 512 otherwise (slab_plan)
+  const int R = T / sv;
+  const int tr = tid / sv, tj = tid - tr * sv;
+  const bool active = tr < R;
+  uint4* tile = reinterpret_cast<uint4*>(gs_smem);                       // [hw][sv]
+  float* part = reinterpret_cast<float*>(gs_smem + gm.tile_bytes);       // [T][16]
+  float* part2 = part + T * 16;                                          // [P][W], P * W <= T
+  const long long col0 = ((long long)img * hw) * C + c0 + tj * 8;
+  if (active)
+    for (int r = tr; r < hw; r += R) cp_async16(&tile[r * sv + tj], x + col0 + (long long)r * C);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  // the affine parameters of this thread's column travel while the tile lands
+  float a[8], b[8];
+  if (active) {
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + tj * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + tj * 8) + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0 + tj * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + tj * 8) + 1);
+    a[0] = g0.x; a[1] = g0.y; a[2] = g0.z; a[3] = g0.w; a[4] = g1.x; a[5] = g1.y; a[6] = g1.z; a[7] = g1.w;
+    b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  // ---- statistics: per-thread column sums, then a fixed-order fold (deterministic) ----
+  {
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+    if (active)
+      for (int r = tr; r < hw; r += R) {
+        float f[8];
+        h8_to_f(tile[r * sv + tj], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] = fmaf(f[j], f[j], q[j]); }
+      }
+    float4* dst = reinterpret_cast<float4*>(part + (size_t)tid * 16);
+    dst[0] = make_float4(s[0], s[1], s[2], s[3]); dst[1] = make_float4(s[4], s[5], s[6], s[7]);
+    dst[2] = make_float4(q[0], q[1], q[2], q[3]); dst[3] = make_float4(q[4], q[5], q[6], q[7]);
+  }
+  __syncthreads();
+  // stage A: part is [R][W] (W = sv * 16 values per row of threads); P thread groups each sum rows p, p + P, ...
+  const int W = sv * 16, P = T / W;
+  {
+    const int p = tid / W, col = tid - p * W;
+    if (p < P) {
+      float acc = 0.f;
+      for (int r = p; r < R; r += P) acc += part[(size_t)r * W + col];
+      part2[p * W + col] = acc;
+    }
+  }
+  __syncthreads();
+  // stage B: warp g folds group g: cpg channels x P parts, lanes strided, then a shuffle tree (fixed pattern)
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    if (warp < gm.sg) {
+      float ss = 0.f, qq = 0.f;
+      for (int i = lane; i < cpg * P; i += 32) {
+        const int p = i / cpg, ch = warp * cpg + (i - p * cpg);  // slab-relative channel
+        const int col = (ch >> 3) * 16 + (ch & 7);
+        ss += part2[p * W + col];
+        qq += part2[p * W + col + 8];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        qq += __shfl_xor_sync(0xffffffffu, qq, o);
+      }
+      if (lane == 0) {
+        const float inv = 1.0f / ((float)hw * (float)cpg);
+        const float mean = ss * inv;
+        float var = qq * inv - mean * mean;
+        var = var < 0.f ? 0.f : var;
+        s_mean[warp] = mean;
+        s_rstd[warp] = rsqrtf(var + eps);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- normalise this thread's own vectors out of shared memory, straight to global ----
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (tj * 8 + j) / cpg;
+      a[j] *= s_rstd[g];
+      b[j] -= s_mean[g] * a[j];
+    }
+    // (rows of this CTA's piece; with split > 1 they were loaded by other threads: the barriers above order that)
+    const int r_hi = min(hw, (piece + 1) * gm.rows_per);
+    for (int r = piece * gm.rows_per + tr; r < r_hi; r += R) {
+      float f[8];
+      h8_to_f(tile[r * sv + tj], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], a[j], b[j]);
+      uint4 o;
+      o.x = swish_pack<kMode>(f[0], f[1]); o.y = swish_pack<kMode>(f[2], f[3]);
+      o.z = swish_pack<kMode>(f[4], f[5]); o.w = swish_pack<kMode>(f[6], f[7]);
+      *reinterpret_cast<uint4*>(y + col0 + (long long)r * C) = o;
+    }
+  }
+}
+
+// Slab geometry; non-zero when the shape does not suit the slab kernel (no slab of <= 8 whole groups fills 16-byte
+// vectors, or a slab does not fit `max_kb` of shared memory).
+static int slab_plan(int n, int hw, int c, int groups, int max_kb, SlabGeom* g, size_t* smem) {
+  if (c % 8 != 0 || groups <= 0 || c % groups != 0 || max_kb <= 0) return -1;
+  const int cpg = c / groups;
+  int sg = 1;
+  while (sg <= 8 && ((sg * cpg) % 8 != 0 || groups % sg != 0)) sg *= 2;
+  if (sg > 8) return -1;
+  const int sv = sg * cpg / 8;
+  if (sv * 16 > kSlabThreads) return -1;  // stage A needs one thread per (column, value)
+  const size_t tile = ((size_t)hw * sv * 16 + 127) & ~(size_t)127;
+  if (tile > ((size_t)max_kb << 10)) return -1;
+  const size_t total = tile + (size_t)kSlabThreads * 16 * sizeof(float) + (size_t)kSlabThreads * sizeof(float);
+  if (total > (size_t)kGSSmemTotal) return -1;
+  // big slabs are split into pieces of <= 16 KB (measured on 2 x 320 @ 32x48, 123 KB slabs: 12.4 / 10.1 / 9.1 / 8.6 us at
+  // 1 / 2 / 4 / 8 CTAs per slab); slabs under 48 KB are not (2 x 640 @ 16x24, 30 KB: 6.0 us alone, 7.8 split in two).
+  // SDEO_GN_F16_SLAB_SPLIT forces 1 / 2 / 4 / 8.
+  int split = 1;
+  if (tile >= (size_t)(48 << 10))
+    while (split < 8 && tile / (size_t)split > (size_t)(16 << 10)) split *= 2;
+  const int force = gs_env_int_fwd("SDEO_GN_F16_SLAB_SPLIT", 0, 0, 8);
+  if (force == 1 || force == 2 || force == 4 || force == 8) split = force;
+  if ((long long)n * (groups / sg) * split > 0x7fffffffLL) return -1;
+  g->hw = hw; g->C = c; g->cpg = cpg; g->sg = sg; g->sv = sv; g->slabs = groups / sg; g->tile_bytes = (int)tile;
+  g->split = split;
+  g->rows_per = (hw + split - 1) / split;
+  // CTA size: 256 threads whenever the fold fits (one thread per (column, value): sv <= 16) -- measured 8.1 / 5.5 / 4.6 / 4.8 us
+  // on the four UNet shapes against 8.6 / 6.1 / 5.9 / 6.9 with 512
+  int threads = sv * 16 <= 256 ? 256 : kSlabThreads;
+  const int tf = gs_env_int_fwd("SDEO_GN_F16_SLAB_THREADS", 0, 0, kSlabThreads);
+  if ((tf == 256 || tf == 512) && sv * 16 <= tf) threads = tf;
+  g->threads = threads;
+  *smem = total;
+  return 0;
+}
+
 // cluster size + rows per CTA of the resident variant; non-zero when the sample does not fit `max_cs` CTAs
 static int gr_plan(int n, int hw, int c, int groups, int sms, int max_cs, RGeom* g, size_t* smem) {
   if (c % 8 != 0 || c / 8 > kGSThreads || groups > 32 || c % groups != 0) return -1;
@@ -863,11 +1032,23 @@ extern "C" int32_t sdeo_groupnorm_f16_visits(int32_t cta, int32_t grid, int32_t 
 }
 
 // which kernel a call with this geometry runs on a device with `sms` SMs and clusters of up to `max_cluster` CTAs (<= 0: 148 / 8):
-// 2 resident (info[0] = cluster size, info[1] = pixel rows per CTA, info[2] = shared memory bytes), 1 two launches (the default
-// beyond a cluster), 0 streamed (only under SDEO_GN_F16_VARIANT=stream)
+// 3 slab (info[0] = groups per slab, info[1] = 16-byte vectors per slab row, info[2] = shared memory bytes), 2 resident (info[0] =
+// cluster size, info[1] = pixel rows per CTA, info[2] = shared memory bytes), 1 two launches (the default beyond a cluster),
+// 0 streamed (only under SDEO_GN_F16_VARIANT=stream)
 extern "C" int sdeo_groupnorm_f16_variant(int32_t n, int32_t hw, int32_t c, int32_t groups, int32_t sms, int32_t max_cluster,
                                           int32_t* info) {
   if (n <= 0 || hw <= 0 || c <= 0 || groups <= 0 || c % 8 != 0 || c % groups != 0) return set_error(SDEO_EINVAL, "groupnorm_f16_variant: bad argument");
+  const char* variant = getenv("SDEO_GN_F16_VARIANT");
+  if (!variant || variant[0] == 's') {
+    if (!variant || variant[1] == 'l') {  // unset or "slab"
+      SlabGeom sg_;
+      size_t ssmem = 0;
+      if (slab_plan(n, hw, c, groups, gs_env_int("SDEO_GN_F16_SLAB_KB", kSlabDefaultKB, 0, 200), &sg_, &ssmem) == 0) {
+        if (info) { info[0] = sg_.sg; info[1] = sg_.sv; info[2] = (int32_t)ssmem; }
+        return 3;
+      }
+    }
+  }
   RGeom rg;
   size_t rsmem = 0;
   if (gr_plan(n, hw, c, groups, sms > 0 ? sms : 148, max_cluster > 0 ? max_cluster : 8, &rg, &rsmem) == 0) {
@@ -879,8 +1060,7 @@ extern "C" int sdeo_groupnorm_f16_variant(int32_t n, int32_t hw, int32_t c, int3
   int G = 0;
   // samples that do not fit a cluster take the two-launch grid (round 2: its pipelined row loads run both passes at ~5.9 TB/s,
   // ahead of the streamed kernel on every shape measured); SDEO_GN_F16_VARIANT=stream opts into the streamed kernel
-  const char* variant = getenv("SDEO_GN_F16_VARIANT");
-  if (!(variant && variant[0] == 's')) return 1;
+  if (!(variant && variant[0] == 's' && variant[1] == 't')) return 1;
   return gs_plan(n, hw, c, groups, sms > 0 ? sms : 148, -1, &g, &smem, &G) ? 1 : 0;
 }
 
@@ -906,8 +1086,30 @@ extern "C" int sdeo_groupnorm_nhwc_f16(const void* x, const float* gamma, const 
   cudaStream_t st = (cudaStream_t)stream;
   const dim3 one(1, 1, 1);
   const int mode = with_silu ? swish_mode : 0;
-  const char* variant = getenv("SDEO_GN_F16_VARIANT");  // "stream" | "resident" | unset: resident when the sample fits a cluster, else two launches
-  if (!two_pass && !(variant && variant[0] == 's')) {
+  // "slab" | "resident" | "stream" | unset: slab when a slab of whole groups fits kSlabDefaultKB of shared memory, else
+  // resident when the sample fits a cluster, else two launches
+  const char* variant = getenv("SDEO_GN_F16_VARIANT");
+  const bool want_stream = variant && variant[0] == 's' && variant[1] == 't';
+  const bool want_slab = variant && variant[0] == 's' && variant[1] == 'l';
+  if (!two_pass && (!variant || want_slab)) {
+    SlabGeom sg_;
+    size_t ssmem = 0;
+    if (slab_plan(n, hw, c, groups, gs_env_int("SDEO_GN_F16_SLAB_KB", kSlabDefaultKB, 0, 200), &sg_, &ssmem) == 0) {
+      static bool slab_attr = false;
+      if (!slab_attr) {
+        cudaError_t e = cudaFuncSetAttribute(gn_slab_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSSmemTotal);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gn_slab_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSSmemTotal);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gn_slab_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSSmemTotal);
+        if (e != cudaSuccess) return set_error(SDEO_ECUDA, cudaGetErrorString(e));
+        slab_attr = true;
+      }
+      auto sfn = mode == 0 ? gn_slab_kernel<0> : (mode == 1 ? gn_slab_kernel<1> : gn_slab_kernel<2>);
+      return launch_k("groupnorm_f16 (slab)", sfn, dim3((unsigned)(n * sg_.slabs * sg_.split)), dim3((unsigned)sg_.threads), ssmem, st, one,
+                      (const __half*)x, gamma, beta, (__half*)y, sg_, eps);
+    }
+    if (want_slab) return set_error(SDEO_EINVAL, "groupnorm_f16: the shape does not suit the slab kernel (slab variant forced)");
+  }
+  if (!two_pass && !want_stream && !want_slab) {
     RGeom rg;
     size_t rsmem = 0;
     if (gr_plan(n, hw, c, groups, gs_sm_count(), gr_max_cluster(), &rg, &rsmem) == 0) {
@@ -922,7 +1124,7 @@ extern "C" int sdeo_groupnorm_nhwc_f16(const void* x, const float* gamma, const 
   int G = 0;
   // default for samples beyond a cluster: the two-launch grid (statistics + apply, norm.cu); the streamed single-launch
   // kernel below (spin-waits on slots of co-resident CTAs) runs only when asked for by SDEO_GN_F16_VARIANT=stream
-  if (two_pass || !(variant && variant[0] == 's') || gs_plan(n, hw, c, groups, gs_sm_count(), lag_env, &g, &smem, &G))
+  if (two_pass || !want_stream || gs_plan(n, hw, c, groups, gs_sm_count(), lag_env, &g, &smem, &G))
     return groupnorm_f16_two_pass(x, gamma, beta, y, n, hw, c, groups, eps, with_silu, workspace, workspace_bytes, stream);
   const size_t nparts_ = (size_t)(g.chunks < g.ngroups * G ? g.chunks : g.ngroups * G);
   const size_t slot_bytes = (size_t)n * (nparts_ + 1 + (nparts_ + kGSTeam - 1) / kGSTeam) * groups * sizeof(unsigned long long);

@@ -10,7 +10,7 @@ namespace sdeo {
 
 constexpr int kGNThreads = 256;
 constexpr int kGNBigPerSM = 6;  // CTAs per SM the two-pass grid is capped at (gn_geometry)
-constexpr int kGNMaxChunks = 256;  // CTAs per sample the two-pass grid is capped at (the apply pass folds that many partials)
+constexpr int kGNMaxChunks = 384;  // CTAs per sample the two-pass grid is capped at (the apply pass folds that many partials)
 
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
   float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
@@ -516,17 +516,26 @@ static void gn_geometry(int n, int hw, long long row_bytes, int* chunks, int* pp
     const char* e = getenv("SDEO_GN_CTAS_X2");
     per_sm_x2 = e ? atoi(e) : 3;
   }
-  // larger ones (the VAE decoder: up to 16 x 512 x 512 pixels) are bandwidth-bound: one CTA per 32 KB of the batch, up to
+  // larger ones (the VAE decoder: up to 16 x 512 x 512 pixels) are bandwidth-bound: one CTA per 64 KB of the batch, up to
   // kGNBigPerSM per SM = two waves of the three CTAs an SM holds (the pipelined row loads keep 4-8 vectors per thread in
   // flight: 48-96 KB per SM), and never more than kGNMaxChunks per sample: every apply CTA folds its sample's partials
-  // (8 lanes x 8 loads per L2 round trip: 256 chunks = 4 round trips)
-  long long total = ((long long)n * hw * row_bytes) >> 15;
+  // (8 lanes x 8 loads per L2 round trip: 384 chunks = 6 round trips). Swept on B200 over 32 / 64 / 128 KB and caps of
+  // 128 ... 1024 chunks (tools/sweep_gn_geometry.sh, profiles/r02b_gn_geometry_sweep.txt): single samples of 6-25 MB run
+  // 13.1 / 16.9 / 25.5 us here, up to 40 us with 1024 chunks (fold) or 128 chunks (too few bytes in flight)
+  static int chunk_kb = -1, max_chunks = -1;  // tuning aids: SDEO_GN_CHUNK_KB, SDEO_GN_MAX_CHUNKS (<= kGNMaxChunks)
+  if (chunk_kb < 0) {
+    const char* e = getenv("SDEO_GN_CHUNK_KB");
+    chunk_kb = e && atoi(e) > 0 ? atoi(e) : 64;
+    e = getenv("SDEO_GN_MAX_CHUNKS");
+    max_chunks = e && atoi(e) > 0 && atoi(e) <= kGNMaxChunks ? atoi(e) : kGNMaxChunks;
+  }
+  long long total = ((long long)n * hw * row_bytes) / ((long long)chunk_kb << 10);
   const bool big = total > 148 * kGNBigPerSM;
   if (big) total = 148 * kGNBigPerSM;
   if (total < 148 * per_sm_x2 / 2) total = 148 * per_sm_x2 / 2;
   // big tensors: never more CTAs than the cap (whole waves of the resident set); small ones: round up
   int want = big ? (int)(total / n) : (int)((total + n - 1) / n);
-  if (want > kGNMaxChunks) want = kGNMaxChunks;
+  if (want > max_chunks) want = max_chunks;
   if (want < 1) want = 1;
   int p = (hw + want - 1) / want;
   if (p < 16) p = hw < 16 ? hw : 16;
@@ -567,7 +576,7 @@ gn_apply_stats_kernel(const T* __restrict__ x1, const T* __restrict__ x2, const 
   float* chan_sum = sm;       // [cs]
   float* chan_sq = sm + cs;   // [cs]
   // The fold sits in front of every CTA's first load of the tensor, and each pass of 4 partials is an L2 round trip: the
-  // `pgs` thread groups of a channel take partials pg, pg + pgs, ... (24..72 partials: 2-6 round trips instead of 6-18),
+  // `pgs` thread groups of a channel take partials pg, pg + pgs, ... eight loads at a time (24..72 partials: 1-3 round trips),
   // then one thread per channel adds the group sums in group order (fixed order: deterministic).
   const int pgs = cs <= kGNThreads ? min(8, kGNThreads / cs) : 1;
   float2* part = reinterpret_cast<float2*>(sm + 2 * cs);   // [pgs][cs]
@@ -578,15 +587,15 @@ gn_apply_stats_kernel(const T* __restrict__ x1, const T* __restrict__ x2, const 
     const float2* src = first ? st1 + (size_t)n * parts1 * c1 + c : st2 + (size_t)n * parts2 * c2 + (c - c1);
     const int parts = first ? parts1 : parts2, ld = first ? c1 : c2;
     float s = 0.f, q = 0.f;
-    int k = pg;
-    for (; k + 3 * pgs < parts; k += 4 * pgs) {  // 4 independent loads in flight, added in slot order
-      const float2 a0 = __ldcg(src + (size_t)k * ld), a1 = __ldcg(src + (size_t)(k + pgs) * ld);
-      const float2 a2 = __ldcg(src + (size_t)(k + 2 * pgs) * ld), a3 = __ldcg(src + (size_t)(k + 3 * pgs) * ld);
-      s += a0.x; q += a0.y; s += a1.x; q += a1.y; s += a2.x; q += a2.y; s += a3.x; q += a3.y;
-    }
-    for (; k < parts; k += pgs) {
-      const float2 a0 = __ldcg(src + (size_t)k * ld);
-      s += a0.x; q += a0.y;
+    for (int k0 = pg; k0 < parts; k0 += 8 * pgs) {  // 8 independent loads per L2 round trip (no serial tail), added in slot order
+      float2 v2[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = k0 + u * pgs;
+        v2[u] = k < parts ? __ldcg(src + (size_t)k * ld) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { s += v2[u].x; q += v2[u].y; }
     }
     part[(size_t)pg * cs + cl] = make_float2(s, q);
   }
@@ -864,15 +873,15 @@ gn_stats_fold_kernel(const float2* __restrict__ st, float2* __restrict__ out, in
   float s = 0.f, q = 0.f;
   if (ch < c) {
     const float2* src = st + ((size_t)n * parts) * c + ch;
-    int k = k_lo + pg;
-    for (; k + 24 < k_hi; k += 32) {  // 4 independent loads in flight, added in slot order
-      const float2 a0 = __ldcg(src + (size_t)k * c), a1 = __ldcg(src + (size_t)(k + 8) * c);
-      const float2 a2 = __ldcg(src + (size_t)(k + 16) * c), a3 = __ldcg(src + (size_t)(k + 24) * c);
-      s += a0.x; q += a0.y; s += a1.x; q += a1.y; s += a2.x; q += a2.y; s += a3.x; q += a3.y;
-    }
-    for (; k < k_hi; k += 8) {
-      const float2 a0 = __ldcg(src + (size_t)k * c);
-      s += a0.x; q += a0.y;
+    for (int k0 = k_lo + pg; k0 < k_hi; k0 += 64) {  // 8 independent loads per round trip, added in slot order
+      float2 v2[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = k0 + u * 8;
+        v2[u] = k < k_hi ? __ldcg(src + (size_t)k * c) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { s += v2[u].x; q += v2[u].y; }
     }
   }
   sm[pg][cl] = make_float2(s, q);

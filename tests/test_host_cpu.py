@@ -296,30 +296,49 @@ def test_groupnorm_f16_visit_schedule(n, c, h, w):
 
 
 def test_groupnorm_f16_variant_selection():
-    """sdeo_groupnorm_f16_variant: UNet samples at 256x384 fit a cluster (resident kernel), VAE-sized ones stream; the cluster
-    covers the sample and fits the shared-memory budget."""
+    """sdeo_groupnorm_f16_variant: UNet samples at 256x384 go to the slab kernel (one CTA per slab of whole groups); with the
+    slab kernel ruled out they fit a cluster (resident kernel: the cluster covers the sample and fits the shared-memory
+    budget); VAE-sized samples take two launches, the streamed kernel only when asked for."""
     from stablediffusioneo_b200 import _lib
     lib = _lib.load()
     info = (ctypes.c_int32 * 3)()
-    for n, c, h, w in [(2, 320, 32, 48), (2, 640, 16, 24), (2, 1280, 8, 12), (2, 2560, 8, 12), (1, 64, 1, 1), (3, 64, 7, 5)]:
-        assert lib.sdeo_groupnorm_f16_variant(n, h * w, c, 32, 148, 8, info) == 2
-        cs, rpc, smem = list(info)
-        assert cs in (1, 2, 4, 8) and rpc * cs >= h * w and (rpc - 1) * cs < h * w + cs and rpc * c * 2 < smem <= 220 * 1024
+    unet = [(2, 320, 32, 48), (2, 640, 16, 24), (2, 1280, 8, 12), (2, 2560, 8, 12), (1, 64, 1, 1), (3, 64, 7, 5)]
     saved = os.environ.pop("SDEO_GN_F16_VARIANT", None)
+    saved_kb = os.environ.pop("SDEO_GN_F16_SLAB_KB", None)
     try:
+        for n, c, h, w in unet:
+            assert lib.sdeo_groupnorm_f16_variant(n, h * w, c, 32, 148, 8, info) == 3
+            sg, sv, smem = list(info)
+            cpg = c // 32
+            assert sg in (1, 2, 4, 8) and (sg * cpg) % 8 == 0 and sv == sg * cpg // 8 and 32 % sg == 0
+            assert h * w * sv * 16 <= 128 * 1024 and h * w * sv * 16 < smem <= 220 * 1024
+        assert lib.sdeo_groupnorm_f16_variant(1, 48 * 96, 512, 32, 148, 16, info) == 1    # 147 KB slab: beyond the default limit
+        os.environ["SDEO_GN_F16_SLAB_KB"] = "200"
+        assert lib.sdeo_groupnorm_f16_variant(1, 48 * 96, 512, 32, 148, 16, info) == 3
+        assert lib.sdeo_groupnorm_f16_variant(1, 64 * 96, 512, 32, 148, 16, info) == 1    # 196 KB + fold scratch: does not fit
+        os.environ.pop("SDEO_GN_F16_SLAB_KB")
+        os.environ["SDEO_GN_F16_VARIANT"] = "resident"
+        for n, c, h, w in unet:
+            assert lib.sdeo_groupnorm_f16_variant(n, h * w, c, 32, 148, 8, info) == 2
+            cs, rpc, smem = list(info)
+            assert cs in (1, 2, 4, 8) and rpc * cs >= h * w and (rpc - 1) * cs < h * w + cs and rpc * c * 2 < smem <= 220 * 1024
         # beyond a cluster: the two-launch grid by default, the streamed kernel only when asked for
         assert lib.sdeo_groupnorm_f16_variant(2, 32 * 48, 640, 32, 148, 8, info) == 1   # 1.9 MB per sample: needs 16 CTAs
         assert lib.sdeo_groupnorm_f16_variant(2, 32 * 48, 640, 32, 148, 16, info) == 2 and info[0] == 16
         assert lib.sdeo_groupnorm_f16_variant(16, 256 * 256, 256, 32, 148, 16, info) == 1
+        os.environ.pop("SDEO_GN_F16_VARIANT")
+        assert lib.sdeo_groupnorm_f16_variant(16, 256 * 256, 256, 32, 148, 16, info) == 1
         os.environ["SDEO_GN_F16_VARIANT"] = "stream"
-        assert lib.sdeo_groupnorm_f16_variant(2, 32 * 48, 640, 32, 148, 8, info) == 0
-        assert lib.sdeo_groupnorm_f16_variant(2, 32 * 48, 960, 32, 148, 16, info) == 0  # 2.9 MB: streamed
+        assert lib.sdeo_groupnorm_f16_variant(2, 32 * 48, 960, 32, 148, 8, info) == 0   # 2.9 MB: streamed
         assert lib.sdeo_groupnorm_f16_variant(16, 256 * 256, 256, 32, 148, 16, info) == 0
         assert lib.sdeo_groupnorm_f16_variant(1, 64, 8192, 32, 148, 8, info) == 1       # more channel vectors than threads
     finally:
         os.environ.pop("SDEO_GN_F16_VARIANT", None)
+        os.environ.pop("SDEO_GN_F16_SLAB_KB", None)
         if saved is not None:
             os.environ["SDEO_GN_F16_VARIANT"] = saved
+        if saved_kb is not None:
+            os.environ["SDEO_GN_F16_SLAB_KB"] = saved_kb
 
 
 def _gn_stream_protocol_model(lib, n, c, h, w, ng, bufs, sms=148, verbose=False):

@@ -914,7 +914,15 @@ def test_groupnorm_f16_resident_variant(cuda_device, n, c, h, w, swish, cluster)
     from stablediffusioneo_b200 import _lib, ops
     dev = cuda_device
     info = (ctypes.c_int32 * 3)()
-    if _lib.load().sdeo_groupnorm_f16_variant(n, h * w, c, 32, 148, max(cluster, 8), info) != 2:
+    saved_v = os.environ.get("SDEO_GN_F16_VARIANT")
+    os.environ["SDEO_GN_F16_VARIANT"] = "resident"  # (the default dispatch gives these shapes to the slab kernel)
+    try:
+        fits = _lib.load().sdeo_groupnorm_f16_variant(n, h * w, c, 32, 148, max(cluster, 8), info) == 2
+    finally:
+        os.environ.pop("SDEO_GN_F16_VARIANT")
+        if saved_v is not None:
+            os.environ["SDEO_GN_F16_VARIANT"] = saved_v
+    if not fits:
         pytest.skip("the sample does not fit a cluster of this size")
     if cluster and (-(-h * w // cluster)) * c * 2 > 180 * 1024:
         pytest.skip("forced cluster size too small for the sample")
@@ -946,3 +954,56 @@ def test_groupnorm_f16_resident_variant(cuda_device, n, c, h, w, swish, cluster)
     worst = ((o - gold).abs() / (gold.abs() + 1.0)).max().item()
     print(f"GN fp16 resident {n}x{c}x{h}x{w} cluster {cluster or 'auto'}: vs f64 {e_gold:.2e} (worst {worst:.2e})")
     assert e_gold < 6e-4 and worst < 4e-3
+
+
+@pytest.mark.parametrize("n,c,h,w,swish", [(2, 320, 32, 48, True), (2, 640, 16, 24, False), (2, 1280, 8, 12, True), (2, 2560, 8, 12, True),
+                                           (3, 64, 7, 5, True), (1, 64, 1, 1, False), (5, 1280, 33, 17, True), (1, 32, 9, 11, True),
+                                           (40, 320, 16, 24, True), (1, 512, 48, 96, True), (2, 128, 100, 77, False),
+                                           (1, 4096, 5, 3, True)])
+@pytest.mark.parametrize("split", [0, 2, 8])
+def test_groupnorm_f16_slab_variant(cuda_device, n, c, h, w, swish, split):
+    """The slab kernel (one CTA per sample and slab of whole groups, the slab parked in shared memory: no traffic between
+    CTAs) forced on shapes up to the shared-memory limit -- 1 / 2 / 4 / 8 groups per slab, one-pixel samples, ragged row
+    counts, 1 to 16 vectors per slab row, the automatic and forced splits of a slab over several CTAs (redundant
+    statistics, disjoint rows normalised; pieces without rows); against torch in float64, the two-launch variant and
+    bit-for-bit against itself."""
+    import ctypes
+    import torch.nn.functional as F
+    from stablediffusioneo_b200 import _lib, ops
+    dev = cuda_device
+    g = torch.Generator().manual_seed(n * 1000 + c + h)
+    x = (torch.randn((n, h, w, c), generator=g) * 1.5 + 0.3).half()
+    x[:, :, :, : c // 32] *= 4.0  # one group per sample on a different scale: a mixed-up (mean, rstd) shows
+    gamma, beta = torch.randn((c,), generator=g) * 0.5 + 1.0, torch.randn((c,), generator=g) * 0.2
+    gold = F.group_norm(x.double().permute(0, 3, 1, 2), 32, gamma.double(), beta.double(), 1e-5)
+    gold = (F.silu(gold) if swish else gold).permute(0, 2, 3, 1).float()
+    xd, gd, bd = x.to(dev), gamma.to(dev), beta.to(dev)
+    keys = ("SDEO_GN_F16_VARIANT", "SDEO_GN_F16_SLAB_KB", "SDEO_GN_F16_TWO_PASS", "SDEO_GN_F16_SLAB_SPLIT")
+    saved = {k: os.environ.pop(k, None) for k in keys}
+    try:
+        os.environ["SDEO_GN_F16_VARIANT"] = "slab"
+        os.environ["SDEO_GN_F16_SLAB_KB"] = "200"
+        if split:
+            os.environ["SDEO_GN_F16_SLAB_SPLIT"] = str(split)
+        info = (ctypes.c_int32 * 3)()
+        assert _lib.load().sdeo_groupnorm_f16_variant(n, h * w, c, 32, 148, 8, info) == 3
+        first = ops.groupnorm_f16(xd, gd, bd, eps=1e-5, silu=swish)
+        second = ops.groupnorm_f16(xd, gd, bd, eps=1e-5, silu=swish)
+        torch.cuda.synchronize()
+        os.environ.pop("SDEO_GN_F16_VARIANT")
+        os.environ["SDEO_GN_F16_TWO_PASS"] = "1"
+        two = ops.groupnorm_f16(xd, gd, bd, eps=1e-5, silu=swish)
+        torch.cuda.synchronize()
+    finally:
+        for k in keys:
+            os.environ.pop(k, None)
+            if saved[k] is not None:
+                os.environ[k] = saved[k]
+    assert torch.equal(first, second)
+    o, t = first.float().cpu(), two.float().cpu()
+    assert torch.isfinite(o).all()
+    e_gold, e_two = rel_l2(o, gold), rel_l2(o, t)
+    worst = ((o - gold).abs() / (gold.abs() + 1.0)).max().item()
+    print(f"GN fp16 slab {n}x{c}x{h}x{w} (groups per slab {info[0]}, vectors per row {info[1]}): vs f64 {e_gold:.2e} "
+          f"(worst {worst:.2e}), vs two-launch {e_two:.2e}")
+    assert e_gold < 6e-4 and e_two < 6e-4 and worst < 4e-3

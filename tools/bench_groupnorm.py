@@ -21,6 +21,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--only", default="")
 ap.add_argument("--no-ref", action="store_true")
+ap.add_argument("--no-partner", action="store_true", help="time only the default dispatch (geometry sweeps)")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 ref = None
@@ -86,13 +87,16 @@ for label, n, c, h, w in CASES:
 
     os.environ.pop("SDEO_GN_F16_TWO_PASS", None)
     os.environ.pop("SDEO_GN_F16_VARIANT", None)
-    variant = {0: "streamed", 1: "two-launch", 2: "resident"}[_lib.load().sdeo_groupnorm_f16_variant(n, h * w, c, 32, 148, 16, None)]
+    variant = {0: "streamed", 1: "two-launch", 2: "resident", 3: "slab"}[_lib.load().sdeo_groupnorm_f16_variant(n, h * w, c, 32, 148, 16, None)]
     ours_avg, ours_best = timed(ours_call, nbytes, x)
     # the A/B partner: the two-launch grid for shapes the resident kernel takes, the (opt-in) streamed kernel otherwise
-    other, env = ("two-launch", ("SDEO_GN_F16_TWO_PASS", "1")) if variant == "resident" else ("streamed", ("SDEO_GN_F16_VARIANT", "stream"))
-    os.environ[env[0]] = env[1]
-    two_avg, _ = timed(ours_call, nbytes, x)
-    os.environ.pop(env[0], None)
+    other, env = {"slab": ("resident", ("SDEO_GN_F16_VARIANT", "resident")), "resident": ("two-launch", ("SDEO_GN_F16_TWO_PASS", "1"))}.get(
+        variant, ("streamed", ("SDEO_GN_F16_VARIANT", "stream")))
+    two_avg = float("nan")
+    if not args.no_partner:
+        os.environ[env[0]] = env[1]
+        two_avg, _ = timed(ours_call, nbytes, x)
+        os.environ.pop(env[0], None)
     line = (f"{label:24s} {nbytes / 1e6:8.1f} MB  ours ({variant}) {ours_avg:8.1f} us ({nbytes / ours_avg / 1e3:6.0f} GB/s, "
             f"{nbytes / ours_avg / 1e3 / peak:4.0%} of HBM)   {other} {two_avg:8.1f} us")
     if ref is not None and n <= 32 and not args.no_ref:

@@ -1,0 +1,4 @@
+for kb in 32 64 128; do for mc in 128 222 256 384 512 1024; do
+echo "== chunk_kb $kb max_chunks $mc"
+SDEO_GN_CHUNK_KB=$kb SDEO_GN_MAX_CHUNKS=$mc timeout 100 python tools/bench_groupnorm.py --only vae --no-ref --no-partner --iters 10 2>&1 | grep vae | cut -c1-110
+done; done
