@@ -191,6 +191,10 @@ int sdeo_pack_geglu_bias(const float* b, int32_t n2, int32_t geglu_bn, float* b_
  * ---------------------------------------------------------------------------------------------- */
 /* One workspace per stream: calls that may run concurrently must not share it. */
 size_t sdeo_groupnorm_workspace_bytes(int32_t n, int32_t hw, int32_t groups);
+/* Host-side view of the two-launch grid (tests, tuning): plan[0] = CTAs (chunks) per sample, plan[1] = pixel rows per chunk
+ * for a tensor of n samples x hw pixels x row_bytes bytes per pixel row. One CTA per 64 KB of the batch, at least ~1.5 CTAs
+ * per SM, at most two waves of the three resident CTAs per SM over the batch and 384 chunks per sample. */
+int sdeo_groupnorm_plan(int32_t n, int32_t hw, int64_t row_bytes, int32_t* plan);
 /* x1/x2: bf16, or fp32 when x_f32 != 0 (fp32 residual-stream tensors); y is always bf16. */
 int sdeo_groupnorm_nhwc(const void* x1, const void* x2, int32_t x_f32, const float* gamma, const float* beta, void* y,
                         int32_t n, int32_t hw, int32_t c1, int32_t c2, int32_t groups, float eps,

@@ -61,6 +61,7 @@ SIGNATURES = {
     "sdeo_pack_conv_weight": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "sdeo_pack_geglu_bias": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "sdeo_groupnorm_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
+    "sdeo_groupnorm_plan": (c_int, [c_int32, c_int32, c_int64, c_void_p]),
     "sdeo_groupnorm_nhwc": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                     c_int32, c_int32, c_float, c_int32, c_void_p, c_size_t, c_void_p]),
     "sdeo_groupnorm_f16_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),

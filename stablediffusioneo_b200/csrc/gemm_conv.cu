@@ -1933,6 +1933,10 @@ bool tune_shape(const sdeo_conv_args* a, void* stream, Tuned* best) {
         if (t < ms) ms = t;
       }
       if (!ok) { (void)cudaGetLastError(); continue; }
+      // A plan that cannot leave the GroupNorm statistics the caller asked for (a tile that spans samples without a K split
+      // on sample boundaries, stats_parts) sends the consumer to the standalone cluster GroupNorm: ~8 us per launch in the
+      // step instead of ~4 for the statistics-fed apply. Charge that difference to the candidate.
+      if (a->gn_stats && stats_parts(a, pl) == 0) ms += 0.004f;
       if (ms < best_ms) { best_ms = ms; *best = Tuned{bn, sp, halo, pair, occ2}; }
     }
   }

@@ -295,6 +295,32 @@ def test_groupnorm_f16_visit_schedule(n, c, h, w):
     assert lib.sdeo_groupnorm_f16_workspace_bytes(n, hw, c, 32) >= n * (min(chunks, 2 * grid) + 1) * 32 * 8
 
 
+def test_groupnorm_two_pass_plan_invariants():
+    """sdeo_groupnorm_plan (the grid of the statistics + apply kernels): the chunks cover the sample exactly once, stay within
+    the caps (384 per sample; two waves of three CTAs per SM over a big batch), the workspace query covers every row size,
+    and the tuned points of the round-2 sweep come out (one CTA per 64 KB; 222 CTAs for small tensors)."""
+    from stablediffusioneo_b200 import _lib
+    lib = _lib.load()
+    plan = (ctypes.c_int32 * 2)()
+    for n in (1, 2, 3, 5, 16, 40):
+        for hw in (1, 7, 96, 1536, 4096, 6144, 24576, 98304, 262144):
+            for row_bytes in (16, 256, 512, 1024, 2560, 5120, 10240):
+                assert lib.sdeo_groupnorm_plan(n, hw, row_bytes, plan) == 0
+                chunks, ppc = plan[0], plan[1]
+                assert chunks >= 1 and ppc >= 1 and chunks * ppc >= hw and (chunks - 1) * ppc < hw
+                assert chunks <= 384
+                total = n * hw * row_bytes
+                if total // (64 << 10) > 148 * 6:       # big: whole waves of the resident set
+                    assert n * chunks <= 148 * 6 or chunks == 1
+                assert lib.sdeo_groupnorm_workspace_bytes(n, hw, 32) >= n * chunks * 32 * 8
+    assert lib.sdeo_groupnorm_plan(16, 512 * 512, 256, plan) == 0 and plan[0] == 55          # configs[4]: 880 CTAs
+    assert lib.sdeo_groupnorm_plan(1, 256 * 384, 256, plan) == 0 and (plan[0], plan[1]) == (384, 256)   # 25 MB: 64 KB per CTA
+    assert lib.sdeo_groupnorm_plan(1, 128 * 192, 512, plan) == 0 and plan[0] == 222          # 12.6 MB: the small-tensor floor
+    assert lib.sdeo_groupnorm_plan(2, 32 * 48, 1280, plan) == 0 and (plan[0], plan[1]) == (96, 16)   # UNet: >= 16 rows per CTA
+    assert lib.sdeo_groupnorm_plan(2, 64 * 96, 640, plan) == 0 and (plan[0], plan[1]) == (110, 56)   # ~1.5 CTAs per SM
+    assert lib.sdeo_groupnorm_plan(0, 4, 16, plan) != 0
+
+
 def test_groupnorm_f16_variant_selection():
     """sdeo_groupnorm_f16_variant: UNet samples at 256x384 go to the slab kernel (one CTA per slab of whole groups); with the
     slab kernel ruled out they fit a cluster (resident kernel: the cluster covers the sample and fits the shared-memory
