@@ -259,6 +259,58 @@ softmax_rows_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, 
     yr[i] = __float2bfloat16(exp2f((xr[i] - m) * scale_log2) * inv);
 }
 
+// Same softmax with the row held in registers: ONE read of the fp32 scores (the three-pass kernel above re-reads the row
+// for the sum and for the output and evaluates every exponential twice). 256 threads x kV float4 vectors: cols <= 1024 * kV,
+// cols % 4 == 0, 16-byte aligned rows. The VAE mid-block attention has cols = 1536 (256x384 image) ... 9216 (768x768).
+template <int kV>
+__global__ void __launch_bounds__(256)
+softmax_rows_reg_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int cols, int ld, int ldy, float scale_log2) {
+  griddep_launch_dependents();
+  griddep_wait();
+  __shared__ float red[8];
+  __shared__ float red2[8];
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)blockIdx.x * ld);
+  uint2* yr = reinterpret_cast<uint2*>(y + (size_t)blockIdx.x * ldy);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nv = cols >> 2;
+  float4 v[kV];
+  float m = -INFINITY;
+#pragma unroll
+  for (int u = 0; u < kV; ++u) {
+    const int i = threadIdx.x + u * 256;
+    v[u] = i < nv ? __ldg(xr + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  }
+#pragma unroll
+  for (int u = 0; u < kV; ++u) m = fmaxf(m, fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+  float s = 0.f;
+#pragma unroll
+  for (int u = 0; u < kV; ++u) {   // (padding lanes hold -inf: exp2 gives 0)
+    v[u].x = exp2f((v[u].x - m) * scale_log2); v[u].y = exp2f((v[u].y - m) * scale_log2);
+    v[u].z = exp2f((v[u].z - m) * scale_log2); v[u].w = exp2f((v[u].w - m) * scale_log2);
+    s += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) red2[warp] = s;
+  __syncthreads();
+  s = red2[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) s += red2[i];
+  const float inv = 1.0f / s;
+#pragma unroll
+  for (int u = 0; u < kV; ++u) {
+    const int i = threadIdx.x + u * 256;
+    if (i < nv) yr[i] = make_uint2(pack_bf16x2(v[u].x * inv, v[u].y * inv), pack_bf16x2(v[u].z * inv, v[u].w * inv));
+  }
+}
+
 __global__ void image_to_u8_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ y, long long npix, int c,
                                    int ldx) {
   const int trc = trace_start(5);
@@ -455,7 +507,14 @@ extern "C" int sdeo_bf16_to_f32(const void* x, float* y, int64_t count, void* st
 extern "C" int sdeo_softmax_rows(const float* x, void* y, int32_t rows, int32_t cols, int32_t ldx, int32_t ldy, float scale,
                                  void* stream) {
   if (!x || !y || rows <= 0 || cols <= 0 || ldx < cols || ldy < cols) return set_error(SDEO_EINVAL, "softmax_rows: bad args");
-  return launch_k("softmax_rows", softmax_rows_kernel, dim3(rows), dim3(256), 0, (cudaStream_t)stream, dim3(1, 1, 1), x, (__nv_bfloat16*)y, cols, ldx, ldy, scale * 1.4426950408889634f);
+  const float sl2 = scale * 1.4426950408889634f;
+  // register-resident row (one read) when the row is vector-aligned and fits 256 threads x 12 float4
+  if (cols % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 7) == 0 && cols <= 12288 &&
+      !getenv("SDEO_SOFTMAX_THREE_PASS")) {
+    auto fn = cols <= 2048 ? softmax_rows_reg_kernel<2> : (cols <= 4096 ? softmax_rows_reg_kernel<4> : (cols <= 8192 ? softmax_rows_reg_kernel<8> : softmax_rows_reg_kernel<12>));
+    return launch_k("softmax_rows", fn, dim3(rows), dim3(256), 0, (cudaStream_t)stream, dim3(1, 1, 1), x, (__nv_bfloat16*)y, cols, ldx, ldy, sl2);
+  }
+  return launch_k("softmax_rows", softmax_rows_kernel, dim3(rows), dim3(256), 0, (cudaStream_t)stream, dim3(1, 1, 1), x, (__nv_bfloat16*)y, cols, ldx, ldy, sl2);
 }
 
 extern "C" int sdeo_image_to_u8(const void* x, uint8_t* y, int32_t npix, int32_t c, int32_t ldx, void* stream) {

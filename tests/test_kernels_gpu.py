@@ -768,9 +768,14 @@ def test_elementwise(cuda_device):
     assert rel_l2(ops.silu(z.to(torch.bfloat16)), F.silu(bf16r(z))) < TOL
     assert torch.equal(ops.to_f32(ops.to_bf16(z)), bf16r(z))
     # row softmax
-    sm = gen((37, 1536), 6, dev) * 3
-    p = ops.softmax_rows(sm, 0.125)
-    assert rel_l2(p, (sm * 0.125).softmax(-1)) < TOL
+    # (register-resident single-read kernel for 2 / 4 / 8 / 12 vectors per thread; 1538 and 13000 columns take the three-pass one)
+    for rows, cols in ((37, 1536), (5, 4096), (3, 6000), (2, 9216), (4, 12288), (3, 1538), (2, 13000), (7, 4)):
+        sm = gen((rows, cols), 6 + cols, dev) * 3
+        sm[0, cols // 2] = 40.0   # a dominant score: the row maximum matters
+        p = ops.softmax_rows(sm, 0.125)
+        ref = (sm * 0.125).softmax(-1)
+        assert rel_l2(p, ref) < TOL, (rows, cols)
+        assert (p.float().sum(-1) - 1).abs().max().item() < 2e-2
 
 
 def test_cfg_ddim_step(cuda_device):
