@@ -295,6 +295,31 @@ def test_groupnorm_f16_visit_schedule(n, c, h, w):
     assert lib.sdeo_groupnorm_f16_workspace_bytes(n, hw, c, 32) >= n * (min(chunks, 2 * grid) + 1) * 32 * 8
 
 
+def test_silu_pair_formula():
+    """The GroupNorm apply pass computes SiLU for two values with ONE reciprocal (norm.cu silu_pair): r = 1 / ((1 + e0)(1 + e1)),
+    y0 = x0 * (1 + e1) * r, with the exponent clamped to 63 so the product of the denominators stays finite. Restated in
+    float32 numpy: finite for every pair (including both values far below -88, where 1 + e^-x alone overflows), and within
+    a few float32 ulps of x / (1 + e^-x) everywhere the result is not below 1e-17 in magnitude."""
+    f32 = np.float32
+    xs = np.array([-1e4, -200.0, -89.0, -88.0, -60.0, -44.0, -43.5, -30.0, -10.0, -3.0, -1.0, -1e-3, 0.0, 1e-3, 0.5, 2.0, 10.0,
+                   50.0, 90.0, 1e4], dtype=f32)
+    x0, x1 = [a.ravel() for a in np.meshgrid(xs, xs)]
+    k = f32(-1.4426950408889634)
+    with np.errstate(over="raise", invalid="raise"):
+        e0 = np.exp2(np.minimum(x0 * k, f32(63.0))).astype(f32)
+        e1 = np.exp2(np.minimum(x1 * k, f32(63.0))).astype(f32)
+        d0, d1 = f32(1.0) + e0, f32(1.0) + e1
+        r = f32(1.0) / (d0 * d1)
+        y0, y1 = x0 * (d1 * r), x1 * (d0 * r)
+    assert np.isfinite(y0).all() and np.isfinite(y1).all()
+    for x, y in ((x0, y0), (x1, y1)):
+        with np.errstate(over="ignore"):   # e^1e4 = inf in float64 too: gold = -0.0 there
+            gold = x.astype(np.float64) / (1.0 + np.exp(-x.astype(np.float64)))
+        big = np.abs(gold) > 1e-17
+        assert np.all(np.abs(y[big] - gold[big]) <= 4e-6 * np.abs(gold[big]) + 1e-30)   # (fp32 exponent argument: ~1e-6 at x = -30)
+        assert np.all(np.abs(y[~big]) < 1e-13)     # clamped tail: ~x * 2^-63, zero in any 16-bit output
+
+
 def test_groupnorm_two_pass_plan_invariants():
     """sdeo_groupnorm_plan (the grid of the statistics + apply kernels): the chunks cover the sample exactly once, stay within
     the caps (384 per sample; two waves of three CTAs per SM over a big batch), the workspace query covers every row size,
