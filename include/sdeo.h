@@ -224,6 +224,10 @@ int32_t sdeo_groupnorm_f16_visits(int32_t cta, int32_t grid, int32_t tiles, int3
  * (statistics + apply over the whole GPU: the default for samples beyond a cluster), 0 = streamed (one persistent kernel;
  * only when the environment asks for it with SDEO_GN_F16_VARIANT=stream). */
 int sdeo_groupnorm_f16_variant(int32_t n, int32_t hw, int32_t c, int32_t groups, int32_t sms, int32_t max_cluster, int32_t* info);
+/* Host-side view of the slab kernel's geometry (tests): plan[0..6] = groups per slab, 16-byte vectors per slab row, slabs per
+ * sample, CTAs per slab, pixel rows each of them normalises, threads per CTA, dynamic shared memory bytes. Returns 1 when
+ * the shape does not suit the slab kernel within max_kb (<= 0: the default 128) KB of shared memory per slab. */
+int sdeo_groupnorm_f16_slab_plan(int32_t n, int32_t hw, int32_t c, int32_t groups, int32_t max_kb, int32_t* plan);
 int sdeo_groupnorm_nhwc_f16(const void* x, const float* gamma, const float* beta, void* y, int32_t n, int32_t hw, int32_t c,
                             int32_t groups, float eps, int32_t with_silu, void* workspace, size_t workspace_bytes,
                             void* stream);

@@ -67,6 +67,7 @@ SIGNATURES = {
     "sdeo_groupnorm_f16_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
     "sdeo_groupnorm_f16_plan": (c_int, [c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "sdeo_groupnorm_f16_variant": (c_int, [c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "sdeo_groupnorm_f16_slab_plan": (c_int, [c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "sdeo_groupnorm_f16_visits": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32]),
     "sdeo_groupnorm_nhwc_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_float,
                                         c_int32, c_void_p, c_size_t, c_void_p]),

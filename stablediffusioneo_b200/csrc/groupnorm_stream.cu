@@ -1064,6 +1064,19 @@ extern "C" int sdeo_groupnorm_f16_variant(int32_t n, int32_t hw, int32_t c, int3
   return gs_plan(n, hw, c, groups, sms > 0 ? sms : 148, -1, &g, &smem, &G) ? 1 : 0;
 }
 
+// Host-side view of the slab kernel's geometry (tests): plan[0..6] = groups per slab, 16-byte vectors per slab row, slabs per
+// sample, CTAs per slab (split), pixel rows each of them normalises, threads per CTA, dynamic shared memory bytes; non-zero
+// when the shape does not suit the slab kernel within `max_kb` (<= 0: the default limit) of shared memory per slab.
+extern "C" int sdeo_groupnorm_f16_slab_plan(int32_t n, int32_t hw, int32_t c, int32_t groups, int32_t max_kb, int32_t* plan) {
+  if (!plan || n <= 0 || hw <= 0 || c <= 0 || groups <= 0) return set_error(SDEO_EINVAL, "groupnorm_f16_slab_plan: bad argument");
+  SlabGeom g;
+  size_t smem = 0;
+  if (slab_plan(n, hw, c, groups, max_kb > 0 ? max_kb : kSlabDefaultKB, &g, &smem)) return 1;
+  plan[0] = g.sg; plan[1] = g.sv; plan[2] = g.slabs; plan[3] = g.split; plan[4] = g.rows_per; plan[5] = g.threads;
+  plan[6] = (int32_t)smem;
+  return 0;
+}
+
 // x / y fp16 NHWC, gamma / beta fp32, one tensor, optional Swish (GroupNormPlugin::enqueue, groupNormPlugin.cpp:179-228;
 // unlike groupNormKernel.cu:190-194, epsilon IS applied). SDEO_GN_F16_TWO_PASS=1 selects the two-launch grid variant,
 // SDEO_GN_F16_SWISH=1|2 the Swish arithmetic (see swish_pack; default 2), SDEO_GN_F16_LAG the apply lag in tiles.

@@ -295,6 +295,72 @@ def test_groupnorm_f16_visit_schedule(n, c, h, w):
     assert lib.sdeo_groupnorm_f16_workspace_bytes(n, hw, c, 32) >= n * (min(chunks, 2 * grid) + 1) * 32 * 8
 
 
+@pytest.mark.parametrize("n,c,h,w", [(2, 320, 32, 48), (2, 640, 16, 24), (2, 1280, 8, 12), (2, 2560, 8, 12), (3, 64, 7, 5),
+                                     (1, 32, 9, 11), (1, 4096, 5, 3), (1, 512, 48, 96), (1, 64, 1, 1)])
+def test_groupnorm_f16_slab_index_model(n, c, h, w):
+    """Index model of gn_slab_kernel (csrc/groupnorm_stream.cu) from sdeo_groupnorm_f16_slab_plan: the thread -> (row
+    phase, column) map loads every 16-byte vector of a slab exactly once, the two-stage fold of the per-thread column sums
+    ([T][16] -> stage A [P][W] -> one warp per group) adds every channel of a group exactly once, and the pieces of a split
+    slab normalise disjoint row ranges that cover the slab. Checked by pushing exact integers through the maps."""
+    from stablediffusioneo_b200 import _lib
+    lib = _lib.load()
+    plan = (ctypes.c_int32 * 7)()
+    hw, groups = h * w, 32
+    assert lib.sdeo_groupnorm_f16_slab_plan(n, hw, c, groups, 200, plan) == 0
+    sg, sv, slabs, split, rows_per, T, smem = list(plan)
+    cpg = c // groups
+    assert slabs * sg == groups and sv * 8 == sg * cpg and T in (256, 512) and sv * 16 <= T
+    assert hw * sv * 16 + T * 16 * 4 + T * 4 <= smem <= 220 * 1024
+    assert split in (1, 2, 4, 8) and rows_per * split >= hw and (split == 1 or hw * sv * 16 >= 48 * 1024)
+    R = T // sv
+    rng = np.random.default_rng(hw * 131 + c)
+    slab = rng.integers(-8, 9, size=(hw, sv * 8)).astype(np.int64)      # one slab's channels, exact integers
+    # ---- load phase / statistics phase: thread tid owns column tj and rows tr, tr + R, ...
+    loaded = np.zeros((hw, sv), dtype=np.int64)
+    part = np.zeros((T, 16), dtype=np.int64)                            # [tid][8 sums | 8 sums of squares]
+    for tid in range(T):
+        tr, tj = divmod(tid, sv)
+        if tr >= R:
+            continue
+        for r in range(tr, hw, R):
+            loaded[r, tj] += 1
+            v = slab[r, tj * 8:(tj + 1) * 8]
+            part[tid, :8] += v
+            part[tid, 8:] += v * v
+    assert (loaded == 1).all()
+    # ---- stage A: part viewed as [R][W]; thread group p of P sums rows p, p + P, ... per column
+    W, P = sv * 16, T // (sv * 16)
+    flat = part.reshape(-1)                                             # index tid * 16 + k == tr * W + tj * 16 + k
+    part2 = np.zeros((P, W), dtype=np.int64)
+    for p in range(P):
+        for col in range(W):
+            part2[p, col] = sum(flat[r * W + col] for r in range(p, R, P))
+    # ---- stage B: warp g folds group g: cpg channels x P parts (lane-strided, then a shuffle tree: any order is exact here)
+    for g in range(sg):
+        ss = qq = 0
+        for i in range(cpg * P):
+            p, ch = divmod(i, cpg)
+            ch += g * cpg
+            col = (ch >> 3) * 16 + (ch & 7)
+            ss += part2[p, col]
+            qq += part2[p, col + 8]
+        block = slab[:, g * cpg:(g + 1) * cpg]
+        assert ss == block.sum() and qq == (block * block).sum()
+    # ---- normalise phase: piece q of a split slab takes rows [q * rows_per, min(hw, (q + 1) * rows_per)), same thread map
+    done = np.zeros((hw, sv), dtype=np.int64)
+    for piece in range(split):
+        r_hi = min(hw, (piece + 1) * rows_per)
+        for tid in range(T):
+            tr, tj = divmod(tid, sv)
+            if tr >= R:
+                continue
+            for r in range(piece * rows_per + tr, r_hi, R):
+                done[r, tj] += 1
+    assert (done == 1).all()
+    # the channel -> group map of the normalise phase stays inside the slab
+    assert max((tj * 8 + j) // cpg for tj in range(sv) for j in range(8)) == sg - 1
+
+
 def test_silu_pair_formula():
     """The GroupNorm apply pass computes SiLU for two values with ONE reciprocal (norm.cu silu_pair): r = 1 / ((1 + e0)(1 + e1)),
     y0 = x0 * (1 + e1) * r, with the exponent clamped to 63 so the product of the denominators stays finite. Restated in
