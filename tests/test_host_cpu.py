@@ -412,6 +412,40 @@ def test_groupnorm_two_pass_plan_invariants():
     assert lib.sdeo_groupnorm_plan(0, 4, 16, plan) != 0
 
 
+@pytest.mark.parametrize("c,elt", [(128, 2), (320, 4), (512, 2), (96, 2), (2560, 4), (4096, 2)])
+def test_groupnorm_two_pass_row_batches_model(c, elt):
+    """Row schedule of the pipelined two-pass kernels (norm.cu gn_load_batch / gn_apply_column): a CTA of 256 threads is
+    (R row phases) x (cols channel vectors); thread (tr, tv) walks rows pp = p_begin + tr, + H * R, ... and each step takes the
+    H rows pp + u * R that lie inside the chunk (the rest read as zero). Every (row, vector) of every chunk of the plan is
+    taken exactly once, for the 16-bit (H = 4) and fp32 (H = 2) batch depths, including more channel vectors than threads."""
+    from stablediffusioneo_b200 import _lib
+    lib = _lib.load()
+    plan = (ctypes.c_int32 * 2)()
+    H = 4 if elt == 2 else 2
+    cv = c // 8
+    cols = min(cv, 256)
+    R = 256 // cols
+    for n, hw in ((1, 37), (2, 1536), (1, 6144), (16, 4096), (3, 1000)):
+        assert lib.sdeo_groupnorm_plan(n, hw, c * elt, plan) == 0
+        chunks, ppc = plan[0], plan[1]
+        seen = np.zeros((hw, cv), dtype=np.int32)
+        for chunk in range(chunks):
+            p_begin, p_end = chunk * ppc, min(hw, (chunk + 1) * ppc)
+            for vbase in range(0, cv, cols):
+                for tid in range(R * cols):
+                    tr, tv = divmod(tid, cols)
+                    v = vbase + tv
+                    if v >= cv:
+                        continue
+                    pp = p_begin + tr
+                    while pp < p_end:
+                        for u in range(H):
+                            if pp + u * R < p_end:
+                                seen[pp + u * R, v] += 1
+                        pp += H * R
+        assert (seen == 1).all(), (n, hw, chunks, ppc)
+
+
 def test_groupnorm_f16_variant_selection():
     """sdeo_groupnorm_f16_variant: UNet samples at 256x384 go to the slab kernel (one CTA per slab of whole groups); with the
     slab kernel ruled out they fit a cluster (resident kernel: the cluster covers the sample and fits the shared-memory
