@@ -22,6 +22,7 @@ ap.add_argument("--groups", default="2")
 args = ap.parse_args()
 n, c, h, w = args.shape
 dev = torch.device("cuda:0")
+os.environ["SDEO_GN_F16_VARIANT"] = "stream"  # the streamed kernel is opt-in since round 2 (the default beyond a cluster is two launches)
 x = (torch.randn((n, h, w, c), device=dev) * 1.5).half()
 gamma, beta = torch.rand((c,), device=dev) + 0.5, torch.randn((c,), device=dev) * 0.1
 nbytes = x.numel() * 4
